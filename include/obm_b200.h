@@ -1,0 +1,276 @@
+/*
+ * obm_b200.h — C ABI of the B200-native biogeochemical hot path.
+ *
+ * Every entry point replaces one piece of OceanBioME.jl (v0.17.6) arithmetic; the
+ * reference interface each one stands in for is cited as `path:line` relative to the
+ * reference tree.  The Julia glue `ccall`s these from the same
+ * hooks OceanBioME implements today (`update_biogeochemical_state!`,
+ * `update_tendencies!`, …), so nothing else in a user script changes.
+ *
+ * Conventions
+ *  - plain C linkage, POD structs, no C++ / torch types, no exceptions;
+ *  - all data pointers are DEVICE pointers owned by the caller (CUDA.jl CuArray
+ *    parents); the library never allocates, frees or retains them;
+ *  - pointer tables (`const double* const*`) and parameter structs are HOST memory,
+ *    read synchronously at call time (copied into the kernel parameter space);
+ *  - every call only enqueues work on the caller's CUDA stream (`void* stream` is a
+ *    `cudaStream_t`; NULL = legacy default stream) and returns immediately;
+ *  - return value: 0 = OK, negative = argument error (OBM_E*), positive = cudaError_t
+ *    from the launch; `obm_last_error()` gives a thread-local message;
+ *  - numerical non-convergence is not an error (the reference returns its last
+ *    iterate, src/Utils/solvers.jl:118-120); NaNs propagate.
+ *
+ * Field layout (all 3-D fields): the parent array of an Oceananigans `Field` — Julia
+ * column-major with halos.  Interior cell (i,j,k), 0-based, lives at parent index
+ *     (i+Hx) + (Nx+2Hx) * ((j+Hy) + (Ny+2Hy) * (k+Hz)).
+ * 2-D fields (`Field{Center,Center,Nothing}`) use the same x-y plane layout with a
+ * single k plane.  `Flat` dimensions have N = 1, H = 0.
+ */
+#ifndef OBM_B200_H
+#define OBM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OBM_VERSION 100 /* 0.1.0 */
+
+/* error codes (negative = argument errors) */
+#define OBM_OK 0
+#define OBM_ENULL (-1)    /* required pointer is NULL                        */
+#define OBM_ESIZE (-2)    /* bad grid size / range / count                   */
+#define OBM_EENUM (-3)    /* unsupported enum / model combination            */
+#define OBM_ENOTIMPL (-4) /* valid request that this build does not support  */
+
+/* ------------------------------------------------------------------------------------
+ * Grid descriptor.  Mirrors what the kernels of the reference read from an Oceananigans
+ * grid: sizes, halos, and z nodes (`znodes(grid, Center/Face)` — src/Light/2band.jl:15-16).
+ * ------------------------------------------------------------------------------------ */
+typedef struct obm_grid {
+    int32_t Nx, Ny, Nz;     /* interior size                                                  */
+    int32_t Hx, Hy, Hz;     /* halo widths (0 in Flat dimensions)                             */
+    int32_t i0, i1, j0, j1; /* half-open 0-based interior sub-range; i1<=0 → Nx, j1<=0 → Ny   */
+    const double* zc;       /* DEVICE: parent of z centres, Nz+2Hz entries, cell k at zc[k+Hz] */
+    const double* zf;       /* DEVICE: parent of z faces, Nz+1+2Hz entries, face k at zf[k+Hz] */
+} obm_grid;
+
+/* ------------------------------------------------------------------------------------
+ * (a1, a2) Nutrients–Plankton–Detritus family: NPZD, LOBSTER and every component mix of
+ * src/Models/AdvectedPopulations/NutrientsPlanktonDetritus/ (struct :27-33).
+ * ------------------------------------------------------------------------------------ */
+enum { OBM_NUT_NUTRIENT = 0, OBM_NUT_NITRATE_AMMONIA = 1, OBM_NUT_NITRATE_AMMONIA_IRON = 2 };
+enum { OBM_DET_NONE = 0, OBM_DET_DETRITUS = 1, OBM_DET_TWO_PARTICLE = 2, OBM_DET_VARIABLE_REDFIELD = 3 };
+enum { OBM_LIGHT_MONDO = 0, OBM_LIGHT_ANALYTICAL = 1 }; /* plankton.jl:216-220 */
+enum { OBM_LINEAR = 0, OBM_QUADRATIC = 1 };             /* plankton.jl:83-90   */
+
+typedef struct obm_npd_params {
+    int32_t nutrients;                           /* OBM_NUT_*  nutrients.jl:16,41,81          */
+    int32_t detritus;                            /* OBM_DET_*  detritus.jl:25,71,264          */
+    int32_t carbonate_replicates;                /* 0 = no CarbonateSystem, N = CarbonateSystem(N) carbonate_system.jl:39-46 */
+    int32_t oxygen;                              /* 0/1        oxygen.jl:14                   */
+    int32_t light_limitation;                    /* OBM_LIGHT_*                               */
+    int32_t phytoplankton_mortality_formulation; /* OBM_LINEAR / OBM_QUADRATIC                */
+    int32_t grazing_concentration_formulation;   /* OBM_LINEAR / OBM_QUADRATIC                */
+    int32_t has_temperature_coefficient;         /* Q10 present ⇒ tracer T is required (plankton.jl:80) */
+    /* PhytoZoo — plankton.jl:19-58 */
+    double nitrate_half_saturation;
+    double ammonia_half_saturation;
+    double iron_half_saturation;
+    double nitrate_ammonia_inhibition;
+    double light_half_saturation;
+    double phytoplankton_maximum_growth_rate;
+    double iron_ratio;
+    double phytoplankton_exudation_fraction;
+    double ammonia_fraction_of_exudate;
+    double temperature_coefficient;
+    double phytoplankton_mortality_rate;
+    double zooplankton_mortality_rate;
+    double zooplankton_excretion_rate;
+    double phytoplankton_solid_waste_fraction;
+    double excretion_inorganic_fraction;
+    double preference_for_phytoplankton;
+    double maximum_grazing_rate;
+    double grazing_half_saturation;
+    double zooplankton_assimilation_fraction;
+    double zooplankton_calcite_dissolution;
+    double redfield_ratio;
+    double carbon_calcite_ratio;
+    double zooplankton_gut_calcite_dissolution;
+    double phytoplankton_chlorophyll_ratio;
+    /* NitrateAmmonia / NitrateAmmoniaIron — nutrients.jl:16-19,41-43 */
+    double nitrification_rate;
+    /* TwoParticleAndDissolved / VariableRedfieldDetritus — detritus.jl:25-37,71-81 */
+    double remineralisation_inorganic_fraction;
+    double small_remineralisation_rate;
+    double large_remineralisation_rate;
+    double dissolved_remineralisation_rate;
+    double small_solid_waste_fraction;
+    double detritus_redfield_ratio; /* TwoParticleAndDissolved.redfield_ratio / Detritus.redfield_ratio */
+    /* Detritus (Kuhn 2015) — detritus.jl:264-270 */
+    double remineralisation_rate;
+    double small_particle_fraction;
+    /* Oxygen — oxygen.jl:14-17 */
+    double respiration_oxygen_nitrogen_ratio;
+    double nitrification_oxygen_nitrogen_ratio;
+} obm_npd_params;
+
+#define OBM_NPD_MAX_TRACERS 32
+
+/* Number of tracers and their order = `required_biogeochemical_tracers(bgc)`
+ * (NutrientsPlanktonDetritus.jl:69-74).  Writes up to OBM_NPD_MAX_TRACERS NUL-terminated
+ * UTF-8 names (≤ 15 bytes each) into names[i][16] when names != NULL.  Returns the count,
+ * or a negative error. */
+int obm_npd_tracer_names(const obm_npd_params* p, char (*names)[16]);
+
+/* Fused replacement of the per-tracer callables
+ *   bgc(i, j, k, grid, Val(name), clock, fields, auxiliary_fields)
+ * (nutrients.jl:48-90, plankton.jl:92-116, detritus.jl:85-158,282-288,
+ *  carbonate_system.jl:50-83, oxygen.jl:21-31) evaluated for EVERY tracer of a cell in one
+ * pass.  `tracers[n]`, `G[n]` follow obm_npd_tracer_names order; a NULL G[n] is skipped
+ * (e.g. T, which has no biogeochemical tendency).  accumulate = 0: G = tendency;
+ * accumulate = 1: G += tendency (the `update_tendencies!` seam, src/OceanBioME.jl:148-152,
+ * same pattern as src/Sediments/tracer_coupling.jl:37). */
+int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p,
+                       const double* const* tracers, const double* PAR,
+                       double* const* G, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (a4) Two-band PAR — src/Light/2band.jl:1-33 (kernel), :35-70 (struct), :106-117 (defaults)
+ * ------------------------------------------------------------------------------------ */
+typedef struct obm_twoband_params {
+    double water_red_attenuation;
+    double water_blue_attenuation;
+    double chlorophyll_red_attenuation;
+    double chlorophyll_blue_attenuation;
+    double chlorophyll_red_exponent;
+    double chlorophyll_blue_exponent;
+    double pigment_ratio;
+    double phytoplankton_chlorophyll_ratio;
+} obm_twoband_params;
+
+/* Replaces `update_biogeochemical_state!(model, PAR::TwoBandPhotosyntheticallyActiveRadiation)`
+ * (2band.jl:148-155).  `surface_PAR_xy` is the glue-evaluated `getbc(surface_PAR, i, j, …)`
+ * (2band.jl:4) as a 2-D field in parent x-y layout; if NULL, `surface_PAR_const` is used. */
+int obm_par_twoband(const obm_grid* grid, const obm_twoband_params* p, const double* P,
+                    const double* surface_PAR_xy, double surface_PAR_const, double* PAR,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (a5, a6) Multi-band PAR — src/Light/multi_band.jl:147-185 — all bands in one launch,
+ * plus the euphotic-depth diagnostic src/Light/compute_euphotic_depth.jl:3-29.
+ * ------------------------------------------------------------------------------------ */
+#define OBM_MAX_BANDS 8
+typedef struct obm_multiband_params {
+    int32_t nbands;
+    int32_t _pad;
+    double water_attenuation_coefficient[OBM_MAX_BANDS];
+    double chlorophyll_exponent[OBM_MAX_BANDS];
+    double chlorophyll_attenuation_coefficient[OBM_MAX_BANDS];
+    double surface_PAR_division[OBM_MAX_BANDS];
+} obm_multiband_params;
+
+/* Chl = chl_scale * (chl_a + chl_b) with chl_b nullable: PISCES passes PChl, DChl with
+ * scale 1 (PISCES/coupling_utils.jl:7), the NPD family passes P with
+ * scale = phytoplankton_chlorophyll_ratio (NutrientsPlanktonDetritus/coupling_utils.jl:54).
+ * PAR_bands[n] receives band n; PAR_total (nullable) receives Σ bands (the lazy `sum(fields)`
+ * multi_band.jl:120 materialised). */
+int obm_par_multiband(const obm_grid* grid, const obm_multiband_params* p, const double* chl_a,
+                      const double* chl_b, double chl_scale, const double* surface_PAR_xy,
+                      double surface_PAR_const, double* const* PAR_bands, double* PAR_total,
+                      void* stream);
+
+/* `compute_euphotic_depth!(euphotic_depth, PAR, cutoff)` compute_euphotic_depth.jl:31-40.
+ * Reads PAR[i,j,Nz+1] — a halo cell — exactly as the reference does (:6). zeu_xy is a 2-D
+ * field in parent x-y layout. */
+int obm_euphotic_depth(const obm_grid* grid, const double* PAR, double cutoff, double* zeu_xy,
+                       void* stream);
+
+/* `compute_mixed_layer_mean!(Cₘₓₗ, mixed_layer_depth, C, grid)`
+ * PISCES/mean_mixed_layer_properties.jl:10-49 — depth-weighted mean of C above zₘₓₗ (used for
+ * κ̄ and PAR̄, PISCES/update_state.jl:9,11).  C == NULL ⇒ the constant C_const (ConstantField). */
+int obm_mixed_layer_mean(const obm_grid* grid, const double* mixed_layer_depth_xy, const double* C,
+                         double C_const, double* mean_xy, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (a7) Carbonate chemistry — src/Models/CarbonChemistry/carbon_chemistry.jl:111-210,
+ * alkalinity_residual.jl:18-75, equilibrium_constants.jl, calcite_concentration.jl:1-80,
+ * density src/Models/seawater_density.jl:33-39 (SeawaterPolynomials TEOS-10, 55 terms).
+ * All default constants of `CarbonChemistry()` (carbon_chemistry.jl:66-87).
+ * ------------------------------------------------------------------------------------ */
+enum {
+    OBM_CC_FCO2 = 0,      /* output = Val(:fCO₂)  carbon_chemistry.jl:167  */
+    OBM_CC_PCO2 = 1,      /* Val(:pCO₂)  :170-193                           */
+    OBM_CC_PH_FREE = 2,   /* Val(:pHᶠ)   :168                               */
+    OBM_CC_PH_TOTAL = 3,  /* Val(:pHᵗ)   :195-200                           */
+    OBM_CC_PH_SEAWATER = 4, /* Val(:pHˢ) :202-210                           */
+    OBM_CC_CO3 = 5,       /* carbonate_concentration  calcite_concentration.jl:1-53 */
+    OBM_CC_OMEGA_CALCITE = 6 /* calcite_saturation  calcite_concentration.jl:55-80  */
+};
+
+typedef struct obm_carbchem_params {
+    int32_t newton_iterations; /* fixed iteration count of the branch-free ln[H] Newton (default 12 when <= 0) */
+    int32_t _pad;
+    double initial_pH_guess;   /* default 8 (carbon_chemistry.jl:121) when <= 0 */
+} obm_carbchem_params;
+
+/* Flat sweep over n cells.  T °C, S PSU, DIC mmol/m³, Alk meq/m³; optional (nullable)
+ * P bar, silicate & phosphate mmol/m³, pH (given ⇒ skip the solve, carbon_chemistry.jl:213). */
+int obm_carbon_chemistry(int64_t n, const obm_carbchem_params* p, const double* T,
+                         const double* S, const double* DIC, const double* Alk,
+                         const double* P_bar, const double* silicate, const double* phosphate,
+                         const double* pH, int output_kind, double* out, void* stream);
+
+/* Gridded Ω for PISCES — `compute_calcite_saturation!`
+ * (PISCES/compute_calcite_saturation.jl:9-37): P = |z|·g·1026/1e5 bar, silicate = Si. */
+int obm_calcite_saturation(const obm_grid* grid, const obm_carbchem_params* p, const double* T,
+                           const double* S, const double* DIC, const double* Alk,
+                           const double* Si, double* Omega, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (a9) ScaleNegativeTracers — src/Utils/negative_tracers.jl:137-276.  All groups of a model
+ * in ONE launch, applied sequentially in the given order (PISCES: carbon, iron, phosphate,
+ * silicon, nitrogen — PISCES/coupling_utils.jl:31).
+ * ------------------------------------------------------------------------------------ */
+#define OBM_MAX_SCALE_TRACERS 32
+#define OBM_MAX_SCALE_GROUPS 8
+#define OBM_MAX_GROUP_SIZE 16
+typedef struct obm_scale_group {
+    int32_t n;                                /* tracers in this group                          */
+    int32_t index[OBM_MAX_GROUP_SIZE];        /* indices into the `tracers` pointer table        */
+    double scalefactor[OBM_MAX_GROUP_SIZE];   /* negative_tracers.jl:40                          */
+} obm_scale_group;
+
+int obm_scale_negative_tracers(const obm_grid* grid, int ntracers, double* const* tracers,
+                               int ngroups, const obm_scale_group* groups,
+                               double invalid_fill_value, void* stream);
+
+/* `ZeroNegativeTracers` negative_tracers.jl:22-32: parent .= max.(0, parent) over the whole
+ * parent array (halos included, as the reference does). n = parent element count. */
+int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tracers,
+                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
+ * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
+ * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics
+ * on doubles).  `workspace` is a caller-provided DEVICE buffer of
+ * obm_inventory_workspace_bytes(ngroups) bytes.  The multi-GPU all-reduce of `out` is done by
+ * the caller with NCCL (see oceanbiome.jl_b200/distributed.py).
+ * ------------------------------------------------------------------------------------ */
+int64_t obm_inventory_workspace_bytes(int ngroups);
+int obm_inventory(const obm_grid* grid, int ntracers, const double* const* tracers, int ngroups,
+                  const obm_scale_group* groups, const double* cell_volume /*nullable: 3-D field*/,
+                  double uniform_volume, double* out, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------ */
+const char* obm_last_error(void);
+int obm_version(void);
+/* compile-time facts, for the test-suite: sizeof of each param struct */
+int obm_sizeof(const char* struct_name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OBM_B200_H */

@@ -1,0 +1,169 @@
+"""ctypes binding of libobm_b200.so — a line-for-line mirror of include/obm_b200.h.
+
+The same C ABI is what the Julia glue `ccall`s; parity through this binding
+therefore certifies the ABI itself.  There is NO CPU fallback: if the CUDA library is missing the
+import of any compute entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libobm_b200.so")
+
+c_double_p = C.POINTER(C.c_double)
+c_double_pp = C.POINTER(c_double_p)
+
+OBM_MAX_BANDS = 8
+OBM_MAX_SCALE_TRACERS = 32
+OBM_MAX_SCALE_GROUPS = 8
+OBM_MAX_GROUP_SIZE = 16
+OBM_NPD_MAX_TRACERS = 32
+
+# enums (include/obm_b200.h)
+NUT_NUTRIENT, NUT_NITRATE_AMMONIA, NUT_NITRATE_AMMONIA_IRON = 0, 1, 2
+DET_NONE, DET_DETRITUS, DET_TWO_PARTICLE, DET_VARIABLE_REDFIELD = 0, 1, 2, 3
+LIGHT_MONDO, LIGHT_ANALYTICAL = 0, 1
+LINEAR, QUADRATIC = 0, 1
+CC_FCO2, CC_PCO2, CC_PH_FREE, CC_PH_TOTAL, CC_PH_SEAWATER, CC_CO3, CC_OMEGA_CALCITE = range(7)
+
+
+class obm_grid(C.Structure):
+    _fields_ = [
+        ("Nx", C.c_int32), ("Ny", C.c_int32), ("Nz", C.c_int32),
+        ("Hx", C.c_int32), ("Hy", C.c_int32), ("Hz", C.c_int32),
+        ("i0", C.c_int32), ("i1", C.c_int32), ("j0", C.c_int32), ("j1", C.c_int32),
+        ("zc", C.c_void_p), ("zf", C.c_void_p),
+    ]
+
+
+_NPD_DOUBLES = [
+    "nitrate_half_saturation", "ammonia_half_saturation", "iron_half_saturation",
+    "nitrate_ammonia_inhibition", "light_half_saturation", "phytoplankton_maximum_growth_rate",
+    "iron_ratio", "phytoplankton_exudation_fraction", "ammonia_fraction_of_exudate",
+    "temperature_coefficient", "phytoplankton_mortality_rate", "zooplankton_mortality_rate",
+    "zooplankton_excretion_rate", "phytoplankton_solid_waste_fraction",
+    "excretion_inorganic_fraction", "preference_for_phytoplankton", "maximum_grazing_rate",
+    "grazing_half_saturation", "zooplankton_assimilation_fraction",
+    "zooplankton_calcite_dissolution", "redfield_ratio", "carbon_calcite_ratio",
+    "zooplankton_gut_calcite_dissolution", "phytoplankton_chlorophyll_ratio",
+    "nitrification_rate",
+    "remineralisation_inorganic_fraction", "small_remineralisation_rate",
+    "large_remineralisation_rate", "dissolved_remineralisation_rate",
+    "small_solid_waste_fraction", "detritus_redfield_ratio",
+    "remineralisation_rate", "small_particle_fraction",
+    "respiration_oxygen_nitrogen_ratio", "nitrification_oxygen_nitrogen_ratio",
+]
+
+
+class obm_npd_params(C.Structure):
+    _fields_ = [
+        ("nutrients", C.c_int32), ("detritus", C.c_int32), ("carbonate_replicates", C.c_int32),
+        ("oxygen", C.c_int32), ("light_limitation", C.c_int32),
+        ("phytoplankton_mortality_formulation", C.c_int32),
+        ("grazing_concentration_formulation", C.c_int32),
+        ("has_temperature_coefficient", C.c_int32),
+    ] + [(n, C.c_double) for n in _NPD_DOUBLES]
+
+
+class obm_twoband_params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in (
+        "water_red_attenuation", "water_blue_attenuation", "chlorophyll_red_attenuation",
+        "chlorophyll_blue_attenuation", "chlorophyll_red_exponent", "chlorophyll_blue_exponent",
+        "pigment_ratio", "phytoplankton_chlorophyll_ratio")]
+
+
+class obm_multiband_params(C.Structure):
+    _fields_ = [
+        ("nbands", C.c_int32), ("_pad", C.c_int32),
+        ("water_attenuation_coefficient", C.c_double * OBM_MAX_BANDS),
+        ("chlorophyll_exponent", C.c_double * OBM_MAX_BANDS),
+        ("chlorophyll_attenuation_coefficient", C.c_double * OBM_MAX_BANDS),
+        ("surface_PAR_division", C.c_double * OBM_MAX_BANDS),
+    ]
+
+
+class obm_carbchem_params(C.Structure):
+    _fields_ = [("newton_iterations", C.c_int32), ("_pad", C.c_int32), ("initial_pH_guess", C.c_double)]
+
+
+class obm_scale_group(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32),
+        ("index", C.c_int32 * OBM_MAX_GROUP_SIZE),
+        ("scalefactor", C.c_double * OBM_MAX_GROUP_SIZE),
+    ]
+
+
+STRUCTS = {
+    "obm_grid": obm_grid,
+    "obm_npd_params": obm_npd_params,
+    "obm_twoband_params": obm_twoband_params,
+    "obm_multiband_params": obm_multiband_params,
+    "obm_carbchem_params": obm_carbchem_params,
+    "obm_scale_group": obm_scale_group,
+}
+
+# name → (restype, argtypes); exactly the prototypes of include/obm_b200.h
+PROTOTYPES = {
+    "obm_npd_tracer_names": (C.c_int, [C.POINTER(obm_npd_params), C.c_void_p]),
+    "obm_npd_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_par_twoband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_twoband_params), C.c_void_p, C.c_void_p,
+                                  C.c_double, C.c_void_p, C.c_void_p]),
+    "obm_par_multiband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_multiband_params), C.c_void_p, C.c_void_p,
+                                    C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_euphotic_depth": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
+    "obm_mixed_layer_mean": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
+                                       C.c_void_p]),
+    "obm_carbon_chemistry": (C.c_int, [C.c_int64, C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8
+                             + [C.c_int, C.c_void_p, C.c_void_p]),
+    "obm_calcite_saturation": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 7),
+    "obm_scale_negative_tracers": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int,
+                                             C.POINTER(obm_scale_group), C.c_double, C.c_void_p]),
+    "obm_zero_negative_tracers": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),
+    "obm_inventory": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.POINTER(obm_scale_group),
+                                C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_last_error": (C.c_char_p, []),
+    "obm_version": (C.c_int, []),
+    "obm_sizeof": (C.c_int, [C.c_char_p]),
+}
+
+_lib = None
+
+
+class ObmError(RuntimeError):
+    pass
+
+
+def load(path: str | None = None):
+    """Load libobm_b200.so (once).  Raises ImportError — loudly — when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or os.environ.get("OBM_B200_LIB", LIB_PATH)
+    if not os.path.exists(path):
+        raise ImportError(
+            f"libobm_b200.so not found at {path}: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  oceanbiome.jl_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().obm_last_error().decode("utf-8", "replace")
+        raise ObmError(f"{what} failed with code {rc}: {msg}")
+
+
+def pointer_table(ptrs):
+    """Host array of device pointers (`const double* const*`)."""
+    arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(p) if p else None for p in ptrs])
+    return arr

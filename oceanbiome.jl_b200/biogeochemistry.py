@@ -1,0 +1,165 @@
+"""The `Biogeochemistry` wrapper and the plugin hooks Oceananigans calls — host-side mirror of
+src/OceanBioME.jl:64-169 — plus `BiogeochemicalModel`, a minimal stand-in for the Oceananigans model
+(tracers, clock, Gⁿ, RK3/Euler tracer update) that drives the hooks in the reference's order so the
+parity tests read like the reference's own (test/test_NutrientsPlanktonDetritus.jl, test_PISCES.jl).
+
+Julia's `f!(…)` names are spelled `f(…)` here; argument order follows the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from .grids import CenterField, Field, RectilinearGrid
+from .negative_tracers import ScaleNegativeTracers, apply_scalers
+
+
+class Biogeochemistry:
+    """`Biogeochemistry(underlying; light_attenuation, sediment, particles, modifiers)` — OceanBioME.jl:100-120."""
+
+    def __init__(self, underlying_biogeochemistry, light_attenuation=None, sediment=None, particles=None,
+                 modifiers=None):
+        if particles is not None:
+            raise NotImplementedError("BiogeochemicalParticles are outside the B200 hot path (SURVEY §2 row 9)")
+        self.underlying_biogeochemistry = underlying_biogeochemistry
+        self.light_attenuation = light_attenuation
+        self.sediment = sediment
+        self.particles = particles
+        self.modifiers = modifiers
+
+    # ---- forwarding (OceanBioME.jl:122-131) -------------------------------------------------------
+    def required_biogeochemical_tracers(self):
+        return self.underlying_biogeochemistry.required_biogeochemical_tracers()
+
+    def required_biogeochemical_auxiliary_fields(self):
+        return self.underlying_biogeochemistry.required_biogeochemical_auxiliary_fields()
+
+    def biogeochemical_drift_velocity(self, name):
+        return self.underlying_biogeochemistry.biogeochemical_drift_velocity(name)
+
+    def biogeochemical_auxiliary_fields(self):
+        aux = dict(self.underlying_biogeochemistry.biogeochemical_auxiliary_fields())
+        if self.light_attenuation is not None:
+            aux.update(self.light_attenuation.biogeochemical_auxiliary_fields())
+        return aux
+
+    def chlorophyll(self, model):
+        return self.underlying_biogeochemistry.chlorophyll(model)
+
+    def conserved_tracers(self, *args, **kwargs):
+        return self.underlying_biogeochemistry.conserved_tracers(*args, **kwargs)
+
+    # ---- update_biogeochemical_state!(bgc, model) — OceanBioME.jl:161-167, fixed order ----------
+    def update_biogeochemical_state(self, model, stream: Optional[int] = None):
+        _update_modifiers(model, self.modifiers, stream)
+        if self.light_attenuation is not None:
+            self.light_attenuation.update_biogeochemical_state(model, stream)
+        self.underlying_biogeochemistry.update_biogeochemical_state(model)
+        if self.sediment is not None:
+            self.sediment.update_biogeochemical_state(model, stream)
+
+    # ---- update_tendencies!(bgc, model) — OceanBioME.jl:148-152 -----------------------------------
+    def update_tendencies(self, model, stream: Optional[int] = None):
+        """The seam for the fused tendency kernel: every BGC tendency of every tracer is added to
+        `model.timestepper.Gⁿ` in one launch (the per-point callable is reduced to zero(grid));
+        then the sediment adds its bottom fluxes (Sediments/tracer_coupling.jl:3-28)."""
+        self.underlying_biogeochemistry.compute_tendencies(model.grid, model.tracers,
+                                                           self.biogeochemical_auxiliary_fields(), model.Gn,
+                                                           accumulate=True, stream=stream)
+        if self.sediment is not None:
+            self.sediment.update_tendencies(self, model, stream)
+
+    def __call__(self, *args):
+        """Per-point callable `bgc(i, j, k, grid, Val(name), clock, fields)` — reduced to zero(grid)
+        because `update_tendencies` already added every tendency."""
+        return 0.0
+
+    def summary(self):
+        return f"Biogeochemical model based on {self.underlying_biogeochemistry.summary()}"
+
+    def __repr__(self):
+        s = lambda x: "Nothing" if x is None else (tuple(m.summary() for m in x) if isinstance(x, tuple) else x.summary())  # noqa: E731
+        return (f"{self.underlying_biogeochemistry.summary()} \n Light attenuation: {s(self.light_attenuation)}\n"
+                f" Sediment: {s(self.sediment)}\n Particles: {s(self.particles)}\n Modifiers: {s(self.modifiers)}")
+
+
+def _update_modifiers(model, modifiers, stream):
+    """update_biogeochemical_state!(model, modifiers) with tuple broadcast (OceanBioME.jl:169);
+    consecutive ScaleNegativeTracers are fused into one launch, order preserved."""
+    if modifiers is None:
+        return
+    mods = modifiers if isinstance(modifiers, tuple) else (modifiers,)
+    run = []
+    for m in mods:
+        if isinstance(m, ScaleNegativeTracers):
+            run.append(m)
+            continue
+        if run:
+            apply_scalers(model, run, stream)
+            run = []
+        m.update_biogeochemical_state(model, stream)
+    if run:
+        apply_scalers(model, run, stream)
+
+
+@dataclass
+class Clock:
+    time: float = 0.0
+    iteration: int = 0
+
+
+class BiogeochemicalModel:
+    """Stand-in for `NonhydrostaticModel(; grid, biogeochemistry)` restricted to what the BGC path
+    touches: it materialises `required_biogeochemical_tracers` (+ T, S if asked), owns Gⁿ, and steps
+    tracers with the BGC source terms only (no advection / diffusion: that is Oceananigans' job)."""
+
+    RK3 = ((8 / 15, 0.0), (5 / 12, -17 / 60), (3 / 4, -5 / 12))  # (γⁿ, ζⁿ) of Oceananigans' RK3
+
+    def __init__(self, grid: RectilinearGrid, biogeochemistry, extra_tracers=(), timestepper="RungeKutta3"):
+        self.grid = grid
+        self.biogeochemistry = biogeochemistry
+        self.clock = Clock()
+        names = list(biogeochemistry.required_biogeochemical_tracers())
+        names += [t for t in extra_tracers if t not in names]
+        self.tracers = {n: CenterField(grid, n) for n in names}
+        self.Gn = {n: CenterField(grid, "G" + n) for n in names}
+        self.Gm = {n: CenterField(grid, "G⁻" + n) for n in names}
+        self.timestepper = timestepper
+
+    @property
+    def auxiliary_fields(self):
+        return self.biogeochemistry.biogeochemical_auxiliary_fields()
+
+    def set(self, **values):
+        for n, v in values.items():
+            self.tracers[n].set(v)
+        return self
+
+    def update_state(self):
+        self.biogeochemistry.update_biogeochemical_state(self)
+
+    def compute_tendencies(self):
+        for g in self.Gn.values():
+            g.data.zero_()
+        self.biogeochemistry.update_tendencies(self)
+
+    def time_step(self, dt: float):
+        if self.timestepper == "Euler":
+            self.update_state()
+            self.compute_tendencies()
+            for n, c in self.tracers.items():
+                c.data.add_(self.Gn[n].data, alpha=dt)
+            self.clock.time += dt
+        else:
+            for stage, (gamma, zeta) in enumerate(self.RK3):
+                self.update_state()
+                self.compute_tendencies()
+                for n, c in self.tracers.items():
+                    c.data.add_(self.Gn[n].data, alpha=dt * gamma)
+                    if zeta:
+                        c.data.add_(self.Gm[n].data, alpha=dt * zeta)
+                    self.Gm[n].data.copy_(self.Gn[n].data)
+                self.clock.time += dt * (gamma + zeta)
+        self.clock.iteration += 1

@@ -1,0 +1,284 @@
+// carbon_chemistry.cuh — per-cell carbonate-system solve as a branch-free, fixed-iteration
+// Newton iteration in x = ln[H⁺] (device functions shared by the flat sweep kernel, the gridded
+// Ω kernel and the gas-exchange kernel).
+//
+// Replaces src/Models/CarbonChemistry/carbon_chemistry.jl:111-210 + alkalinity_residual.jl +
+// equilibrium_constants.jl + calcite_concentration.jl + Utils/solvers.jl:81-131 +
+// seawater_density.jl:33-39 (SeawaterPolynomials TEOS-10).
+//
+// Why not the reference's solver: DampedNewtonRaphsonSolver runs with atol = 1e-20, below the
+// residual's ulp, so it exits only on an exactly-zero residual — bimodal 3–10 vs 100 outer
+// iterations, each failed one burning a 10-step back-tracking loop (SURVEY §8 a7, App. A bug 3).
+// On SIMT hardware every warp pays the slow path.  The ROOT is what must match (|ΔpH| ≤ 1e-10);
+// Newton in ln H with the step clamped to ± ln 10 is globally safe over the reference's whole
+// validation box and converges to the same root to ~1e-15 in ≤ 8 (physical) / 12 (robust) steps.
+//
+// Work sharing: log T, √S, S^1.5, Is, √Is, log(1 − 0.001005 S) are computed once for all twelve
+// constants, and each pressure correction is folded into the exponent of its constant (one
+// exp per constant instead of two).
+#pragma once
+
+#include "obm_common.cuh"
+
+namespace obm {
+namespace cc {
+
+// ---- TEOS-10 55-term polynomial (Roquet et al. 2015) as used through SeawaterPolynomials 0.3 ----
+__device__ __forceinline__ double teos10_rho(double T, double Sp, double Pbar) {
+    const double t = T / 40.0;
+    const double s = sqrt((Sp + 32.0) / (40.0 * 35.16504 / 35.0));
+    const double z = -(10.0 * Pbar) / 1e4;
+    const double r0 = (((((-1.7243708991e-03 * z + 1.5616995503e-02) * z + 6.4326772569e-02) * z + 2.2601900708e-01) * z
+                        + -5.2099962525e+00) * z + 4.6494977072e+01) * z;
+    const double rp3 = 3.7969820455e-01 * t + -1.8507636718e-02 * s + -2.3342758797e-02;
+    const double rp2 = (-1.2419983026e+00 * t + -2.1311365518e-01 * s + 2.0564311499e+00) * t
+                       + (2.5019633244e+00 * s + -4.9527603989e+00) * s + 2.0660924175e+00;
+    const double rp1 = (((5.5927935970e-01 * t + -5.5077101279e-01 * s + -2.4649669534e+00) * t
+                         + (-1.8795372996e+00 * s + 3.5063081279e+00) * s + 6.7080479603e+00) * t
+                        + ((-6.5399043664e-01 * s + 5.0042598061e+00) * s + -4.4870114575e+00) * s + -1.3336301113e+01) * t
+                       + (((6.6051753097e+00 * s + -3.0938076334e+01) * s + 5.0774768218e+01) * s + -4.2549998214e+01) * s
+                       + 1.9681925209e+01;
+    const double rp0 = (((((-1.9083568888e-01 * t + 4.8169980163e-01 * s + 5.4048723791e-01) * t
+                           + (-5.3563304045e+00 * s + 1.1311538584e+01) * s + -8.3627885467e+00) * t
+                          + ((-3.1742946532e+00 * s + 1.9717078466e+01) * s + -3.3449108469e+01) * s + 2.1661789529e+01) * t
+                         + (((-5.4723692739e+00 * s + 2.9130021253e+01) * s + -6.0362551501e+01) * s + 6.1548258127e+01) * s
+                         + -3.7074170417e+01) * t
+                        + ((((-1.9193502195e+00 * s + 1.7681814114e+01) * s + -5.6888046321e+01) * s + 8.1770425108e+01) * s
+                           + -6.5281885265e+01) * s + 2.6010145068e+01) * t
+                       + (((((-6.0579916612e+01 * s + 4.3227585684e+02) * s + -1.2849161071e+03) * s + 2.0375295546e+03) * s
+                           + -1.7864682637e+03) * s + 8.6672408165e+02) * s + 8.0189615746e+02;
+    return r0 + (((rp3 * z + rp2) * z + rp1) * z + rp0);
+}
+
+struct PC { double a0, a1, a2, b0, b1; };
+// ln of the pressure-correction factor, equilibrium_constants.jl:29-38
+__device__ __forceinline__ double ln_pc(double a0, double a1, double a2, double b0, double b1, double Tc, double P,
+                                        double inv_RT) {
+    const double dV = a0 + a1 * Tc + a2 * (Tc * Tc);
+    const double dk = b0 + b1 * Tc;
+    return (-dV + 0.5 * dk * P) * P * inv_RT;
+}
+
+struct Constants {
+    double K1, K2, KB, KW, KS, KF, KP1, KP2, KP3, KSi;
+    double Tk, Is, sqrtS, logT;
+};
+
+// all equilibrium constants of carbon_chemistry.jl:140-149 (defaults of :66-87)
+template <bool HAS_P>
+__device__ __forceinline__ void constants(double Tc_in, double S, double P, bool need_phosphate, bool need_silicate,
+                                          Constants& c) {
+    constexpr double LN10 = 2.302585092994045684;
+    const double T = Tc_in + 273.15;
+    const double invT = 1.0 / T;
+    const double logT = log(T);
+    const double sqS = sqrt(S);
+    const double S15 = S * sqS;
+    const double Is = 19.924 * S / (1000.0 + -1.005 * S);  // :341
+    const double sqIs = sqrt(Is);
+    const double Is15 = Is * sqIs;
+    const double logS1 = log(1 + -0.001005 * S);
+    double Tc = 0, inv_RT = 0;
+    if (HAS_P) {
+        Tc = T - 273.15;
+        inv_RT = 1.0 / (83.14472 * T);
+    }
+    // K1 :124-126, K2 :170-172 (10^x)
+    double e1 = 61.2172 + -3633.86 * invT + -9.67770 * logT + 0.011555 * S + -0.0001152 * (S * S);
+    double e2 = -25.9290 + -471.78 * invT + 0.01781 * S + -0.0001122 * (S * S) + 3.16967 * logT;
+    e1 *= LN10;
+    e2 *= LN10;
+    // KB :243-250
+    double eB = 148.0248 + (-8966.90 + -2890.53 * sqS + -77.942 * S + 1.728 * S15 + -0.0996 * (S * S)) * invT
+                + 137.1942 * sqS + 1.62142 * S + (-24.4344 + -25.085 * sqS + -0.2474 * S) * logT + 0.053105 * sqS * T;
+    // KW :307-313
+    double eW = 148.9652 + -13847.26 * invT + -23.6521 * logT + (-5.977 + 118.67 * invT + 1.0495 * logT) * sqS + -0.01615 * S;
+    // KS :410-419
+    double eS = 141.328 + -4276.1 * invT + -23.093 * logT + (324.57 + -13856.0 * invT + -47.986 * logT) * sqIs
+                + (-771.54 + 35474.0 * invT + 114.723 * logT) * Is + -2698.0 * Is15 * invT + 1776.0 * (Is * Is) * invT + logS1;
+    // KF :481-487 (log(1 + 0·S) terms are exactly 0)
+    double eF = -9.68 + 874.0 * invT + 0.111 * sqS;
+    if (HAS_P) {
+        e1 += ln_pc(-25.50, 0.1271, 0.0, -0.00308, 0.0000877, Tc, P, inv_RT);
+        e2 += ln_pc(-15.82, -0.0219, 0.0, 0.00113, -0.0001475, Tc, P, inv_RT);
+        eB += ln_pc(-29.48, 0.1622, -0.0026080, -0.00284, 0.0, Tc, P, inv_RT);
+        eW += ln_pc(-20.02, 0.1119, -0.001409, -0.00513, 0.0000794, Tc, P, inv_RT);
+        eS += ln_pc(-18.03, 0.0466, 0.000316, -0.00453, 0.00009, Tc, P, inv_RT);
+        eF += ln_pc(-9.78, -0.0090, -0.000942, -0.00391, 0.000054, Tc, P, inv_RT);
+    }
+    c.K1 = exp(e1);
+    c.K2 = exp(e2);
+    c.KB = exp(eB);
+    c.KW = exp(eW);
+    c.KS = exp(eS);
+    c.KF = exp(eF);
+    c.KP1 = c.KP2 = c.KP3 = 1.0;
+    if (need_phosphate) {  // KP1-3 :523-529, :558-651
+        double p1 = 115.525 + -4576.752 * invT + -18.453 * logT + (0.69171 + -106.736 * invT) * sqS + (-0.01844 + -0.65643 * invT) * S;
+        double p2 = 172.0883 + -8814.715 * invT + -27.927 * logT + (1.3566 + -160.340 * invT) * sqS + (-0.05778 + 0.37335 * invT) * S;
+        double p3 = -18.141 + -3070.75 * invT + 0.0 * logT + (2.81197 + 17.27039 * invT) * sqS + (-0.09984 + -44.99486 * invT) * S;
+        if (HAS_P) {
+            p1 += ln_pc(-14.51, 0.1211, -0.000321, -0.00267, 0.0000427, Tc, P, inv_RT);
+            p2 += ln_pc(-23.12, 0.1758, -0.002647, -0.00515, 0.00009, Tc, P, inv_RT);
+            p3 += ln_pc(-26.57, 0.2020, -0.0030420, -0.00408, 0.0000714, Tc, P, inv_RT);
+        }
+        c.KP1 = exp(p1);
+        c.KP2 = exp(p2);
+        c.KP3 = exp(p3);
+    }
+    c.KSi = 1.0;
+    if (need_silicate)  // KSi :706-713 (no pressure correction)
+        c.KSi = exp(117.385 + -8904.2 * invT + -19.334 * logT + (3.5913 + -458.79 * invT) * sqIs + (-1.5998 + 188.74 * invT) * Is
+                    + (0.07871 + -12.1652 * invT) * (Is * Is) + logS1);
+    c.Tk = T;
+    c.Is = Is;
+    c.sqrtS = sqS;
+    c.logT = logT;
+}
+
+struct Totals {  // mol/kg (already divided by density), carbon_chemistry.jl:129-134, :116-118
+    double DIC, Alk, boron, sulfate, fluoride, silicate, phosphate;
+};
+
+// alkalinity_residual(H) and H·∂ₕ residual — alkalinity_residual.jl:18-75 with shared denominators
+__device__ __forceinline__ void residual(double H, const Constants& c, const Totals& t, bool need_phosphate,
+                                         bool need_silicate, double& f, double& Hdf) {
+    const double K1K2 = c.K1 * c.K2;
+    const double cd = H * H + c.K1 * H + K1K2;
+    const double icd = 1.0 / cd;
+    // bicarbonate + carbonate
+    f = c.K1 * t.DIC * (H + 2 * c.K2) * icd;
+    double df = c.K1 * t.DIC * ((K1K2 - H * H) - 2 * c.K2 * (2 * H + c.K1)) * (icd * icd);
+    // borate
+    const double ib = 1.0 / (c.KB + H);
+    f += t.boron * c.KB * ib;
+    df -= t.boron * c.KB * (ib * ib);
+    // hydroxide − free hydrogen
+    const double iH = 1.0 / H;
+    const double isd = 1.0 / (1 + t.sulfate / c.KS);
+    f += c.KW * iH - H * isd;
+    df -= c.KW * (iH * iH) + isd;
+    // hydrogen sulfate: −ST·H / (H + KS·sd)
+    const double KSsd = c.KS * (1 + t.sulfate / c.KS);
+    const double ihs = 1.0 / (H + KSsd);
+    f -= t.sulfate * H * ihs;
+    df -= t.sulfate * KSsd * (ihs * ihs);
+    // hydrogen fluoride: −FT·H / (H + KF)
+    const double ihf = 1.0 / (H + c.KF);
+    f -= t.fluoride * H * ihf;
+    df -= t.fluoride * c.KF * (ihf * ihf);
+    if (need_silicate) {
+        const double isi = 1.0 / (c.KSi + H);
+        f += t.silicate * c.KSi * isi;
+        df -= t.silicate * c.KSi * (isi * isi);
+    }
+    if (need_phosphate) {
+        const double k12 = c.KP1 * c.KP2, k123 = k12 * c.KP3;
+        const double H2 = H * H, H3 = H2 * H;
+        const double pd = H3 + c.KP1 * H2 + k12 * H + k123;
+        const double dpd = 3 * H2 + 2 * c.KP1 * H + k12;
+        const double ipd = 1.0 / pd;
+        const double num = k12 * H + 2 * k123 - H3;  // [HPO₄²⁻] + 2[PO₄³⁻] − [H₃PO₄] numerator
+        f += t.phosphate * num * ipd;
+        df += t.phosphate * ((k12 - 3 * H2) * pd - num * dpd) * (ipd * ipd);
+    }
+    f -= t.Alk;
+    Hdf = H * df;
+}
+
+// solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]; fixed iteration count, step clamped to one pH unit
+__device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, bool need_phosphate, bool need_silicate,
+                                          double initial_pH, int iterations) {
+    constexpr double LN10 = 2.302585092994045684;
+    double x = -initial_pH * LN10;
+    double H = exp(x);
+#pragma unroll 1
+    for (int n = 0; n < iterations; n++) {
+        double f, Hdf;
+        residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
+        double dx = f / Hdf;
+        dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
+        x -= dx;
+        H = exp(x);
+    }
+    return H;
+}
+
+// K0 — equilibrium_constants.jl:65-80
+__device__ __forceinline__ double K0(double T, double logT, double S) {
+    return exp(-60.2409 + (93.4517 * 100) / T + 23.3585 * (logT - 4.605170185988092) + 0.0 * (T * T)
+               + (0.023517 + (-0.023656 / 100) * T + (0.0047036 / (100.0 * 100.0)) * (T * T)) * S);
+}
+
+// KSP calcite — equilibrium_constants.jl:754-764, :789-810 (the log10(T) in a "ln K" is the reference's, :758)
+template <bool HAS_P>
+__device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P) {
+    constexpr double LN10 = 2.302585092994045684;
+    const double therm = -171.9065 + -0.077993 * T + 2839.319 / T + 71.595 * (logT / LN10);
+    const double sea = ((-0.77712 + 0.0028426 * T + 178.34 / T) * sqS + -0.07711 * S + 0.0041249 * (S * sqS));
+    double e = (therm + sea) * LN10;
+    if (HAS_P) e += ln_pc(-48.76, 0.5304, -0.0, -0.01176, 0.0003692, T - 273.15, P, 1.0 / (83.14472 * T));
+    return exp(e);
+}
+
+// The whole `(p::CarbonChemistry)(; DIC, T, S, Alk, pH, P, output, silicate, phosphate)` call.
+template <bool HAS_P>
+__device__ __forceinline__ double solve(int output_kind, double T, double S, double DIC, double Alk, double P,
+                                        bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
+                                        double pH, double initial_pH, int iterations) {
+    constexpr double LN10 = 2.302585092994045684;
+    const bool calcite_path = (output_kind == OBM_CC_CO3 || output_kind == OBM_CC_OMEGA_CALCITE);
+    // density: P|1 for the main call (carbon_chemistry.jl:123), P|0 for carbonate_concentration
+    // (calcite_concentration.jl:13) — reproduced as found (SURVEY App. A bug 4)
+    const double rho = teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
+    Constants c;
+    constants<HAS_P>(T, S, P, has_phos, has_sil, c);
+    const double scale = 1e-3 / rho;
+    Totals t;
+    t.DIC = DIC * scale;
+    t.Alk = Alk * scale;
+    t.phosphate = phosphate * scale;
+    t.silicate = silicate * scale;
+    t.boron = 0.000232 / 10.811 * S / 1.80655;
+    t.sulfate = 0.14 / 96.06 * S / 1.80655;
+    t.fluoride = 0.000067 / 18.9984 * S / 1.80655;
+
+    const double H = has_pH ? exp(-pH * LN10) : solve_H(c, t, has_phos, has_sil, initial_pH, iterations);
+
+    switch (output_kind) {
+        case OBM_CC_PH_FREE: return -log10(H);
+        case OBM_CC_PH_TOTAL: return -log10(H + t.sulfate / (1 + c.KS / H));
+        case OBM_CC_PH_SEAWATER: return -log10(H + t.sulfate / (1 + c.KS / H) + t.fluoride / (1 + c.KF / H));
+        case OBM_CC_CO3:
+        case OBM_CC_OMEGA_CALCITE: {
+            const double denom1 = (H * (H + c.K1));
+            const double denom2 = (1.0 + c.K1 * c.K2 / denom1);
+            const double CO3 = t.DIC * c.K1 * c.K2 / denom1 / denom2;
+            if (output_kind == OBM_CC_CO3) return CO3;
+            const double calcium = 0.0103 * S / 35;
+            return calcium * CO3 / KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P);
+        }
+        default: break;
+    }
+    const double CO2 = t.DIC * (H * H) / (H * H + c.K1 * H + c.K1 * c.K2);
+    double fCO2 = (CO2 / K0(c.Tk, c.logT, S)) * 1000000.0;
+    if (output_kind == OBM_CC_FCO2) return fCO2;
+    // pCO₂: carbon_chemistry.jl:170-193 (3 fixed-point virial iterations)
+    const double Pp = (HAS_P ? P : 1.0) * 101325.0;
+    const double Tk = c.Tk;
+    const double B = (-1636.75 + 12.0408 * Tk + -3.27957e-2 * (Tk * Tk) + 3.16528e-5 * (Tk * Tk * Tk)) * 1e-6;
+    const double dl = (57.7 + -0.118 * Tk) * 1e-6;
+    fCO2 *= 0.09807;
+    double phi = 1.0;
+    double x = fCO2 / (phi * Pp);
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const double om = 1.0 - x;
+        phi = exp((B + 2.0 * (om * om) * dl) * Pp / (8.31446261815324 * Tk));
+        x = fCO2 / (phi * Pp);
+    }
+    return fCO2 / phi / 0.09807;
+}
+
+}  // namespace cc
+}  // namespace obm

@@ -1,0 +1,232 @@
+// negative_tracers.cu — ScaleNegativeTracers (all conserved groups of a model in ONE launch),
+// ZeroNegativeTracers, and the fused tracer-inventory reduction.
+//
+// Replaces src/Utils/negative_tracers.jl:137-276: the reference launches one :xyz kernel per
+// conserved group (PISCES: 5 launches re-reading 36 fields; OceanBioME.jl:169).  Here a cell's
+// distinct tracers are read once into shared memory (one 8-byte slot per tracer per thread,
+// conflict-free), the groups are applied back to back on those staged values in the reference's
+// order, and every tracer is written once.  HBM-bound: 16 B per distinct tracer per cell.
+//
+// Arithmetic uses explicit round-to-nearest mul/add/div (no FMA contraction) so results are
+// bit-identical to the reference's `t += value * scale`, `value * t / p` sequence.
+#include <string.h>
+
+#include "obm_common.cuh"
+
+namespace obm {
+
+constexpr int SN_BLOCK = 128;
+
+struct ScaleArgs {
+    GridDims d;
+    int ntracers, ngroups;
+    double fill;
+    double* tracers[OBM_MAX_SCALE_TRACERS];
+    obm_scale_group groups[OBM_MAX_SCALE_GROUPS];
+};
+
+__global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_constant__ ScaleArgs a) {
+    extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    double* mine = sm + threadIdx.x;
+    for (int t = 0; t < a.ntracers; t++) mine[t * SN_BLOCK] = a.tracers[t][idx];
+    for (int q = 0; q < a.ngroups; q++) {
+        const obm_scale_group& g = a.groups[q];
+        double t = 0.0, p = 0.0;
+        for (int m = 0; m < g.n; m++) {  // negative_tracers.jl:256-264
+            const double v = mine[g.index[m] * SN_BLOCK];
+            const double s = __dmul_rn(v, g.scalefactor[m]);
+            t = __dadd_rn(t, s);
+            if (v > 0) p = __dadd_rn(p, s);
+        }
+        t = t < 0 ? a.fill : t;  // :266
+        for (int m = 0; m < g.n; m++) {  // :268-274
+            const double v = mine[g.index[m] * SN_BLOCK];
+            const bool keep = !isfinite(v) | (v > 0);
+            mine[g.index[m] * SN_BLOCK] = keep ? __ddiv_rn(__dmul_rn(v, t), p) : 0.0;
+        }
+    }
+    for (int t = 0; t < a.ntracers; t++) a.tracers[t][idx] = mine[t * SN_BLOCK];
+}
+
+struct ZeroArgs {
+    long long n;
+    int ntracers;
+    double* tracers[OBM_MAX_SCALE_TRACERS];
+};
+__global__ void __launch_bounds__(256) zero_negative_kernel(const __grid_constant__ ZeroArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (int t = 0; t < a.ntracers; t++) {
+        double* c = a.tracers[t];
+        for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < a.n; q += stride) {
+            const double v = c[q];
+            c[q] = jl_max(0.0, v);  // parent .= max.(0.0, parent), NaN-propagating, -0.0 → 0.0
+        }
+    }
+}
+
+// ---- inventory: out[g] = Σ_cells (Σ_f sf·c_f)·V — deterministic two-level tree, no double atomics ----
+constexpr int INV_BLOCKS = 148 * 4;
+constexpr int INV_THREADS = 256;
+
+struct InvArgs {
+    GridDims d;
+    int ntracers, ngroups;
+    const double* tracers[OBM_MAX_SCALE_TRACERS];
+    obm_scale_group groups[OBM_MAX_SCALE_GROUPS];
+    const double* volume;
+    double uniform_volume;
+    double* partial;  // [ngroups][INV_BLOCKS]
+    double* out;
+};
+
+__global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __grid_constant__ InvArgs a) {
+    __shared__ double red[INV_THREADS / 32];
+    const GridDims& d = a.d;
+    const int nx = d.i1 - d.i0, ny = d.j1 - d.j0;
+    const long long total = (long long)nx * ny * d.Nz;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = 0; q < a.ngroups; q++) {
+        const obm_scale_group& g = a.groups[q];
+        double acc = 0.0;
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+            const long long row = t / nx;
+            const int i = d.i0 + (int)(t - row * nx);
+            const int k = (int)(row / ny);
+            const int j = d.j0 + (int)(row - (long long)k * ny);
+            const long long idx = cell_index(d, i, j, k);
+            double s = 0.0;
+            for (int m = 0; m < g.n; m++) s += g.scalefactor[m] * a.tracers[g.index[m]][idx];
+            acc += s * (a.volume ? a.volume[idx] : a.uniform_volume);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[warp] = acc;
+        __syncthreads();
+        if (warp == 0) {
+            double v = lane < INV_THREADS / 32 ? red[lane] : 0.0;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) a.partial[q * INV_BLOCKS + blockIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(INV_THREADS) inventory_final_kernel(const double* partial, int nblocks, double* out) {
+    __shared__ double red[INV_THREADS / 32];
+    const int q = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) acc += partial[q * nblocks + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double v = lane < INV_THREADS / 32 ? red[lane] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) out[q] = v;
+    }
+}
+
+static int check_groups(const char* who, int ntracers, int ngroups, const obm_scale_group* groups) {
+    OBM_REQUIRE(ntracers >= 1 && ntracers <= OBM_MAX_SCALE_TRACERS, OBM_ESIZE, "%s: ntracers = %d outside [1, %d]", who,
+                ntracers, OBM_MAX_SCALE_TRACERS);
+    OBM_REQUIRE(ngroups >= 0 && ngroups <= OBM_MAX_SCALE_GROUPS, OBM_ESIZE, "%s: ngroups = %d outside [0, %d]", who, ngroups,
+                OBM_MAX_SCALE_GROUPS);
+    OBM_REQUIRE(ngroups == 0 || groups != nullptr, OBM_ENULL, "%s: groups is NULL", who);
+    for (int q = 0; q < ngroups; q++) {
+        OBM_REQUIRE(groups[q].n >= 1 && groups[q].n <= OBM_MAX_GROUP_SIZE, OBM_ESIZE, "%s: group %d has n = %d", who, q,
+                    groups[q].n);
+        for (int m = 0; m < groups[q].n; m++)
+            OBM_REQUIRE(groups[q].index[m] >= 0 && groups[q].index[m] < ntracers, OBM_ESIZE,
+                        "%s: group %d member %d indexes tracer %d of %d", who, q, m, groups[q].index[m], ntracers);
+    }
+    return 0;
+}
+
+}  // namespace obm
+
+using namespace obm;
+
+extern "C" int obm_scale_negative_tracers(const obm_grid* grid, int ntracers, double* const* tracers, int ngroups,
+                                          const obm_scale_group* groups, double invalid_fill_value, void* stream) {
+    OBM_REQUIRE(tracers != nullptr, OBM_ENULL, "obm_scale_negative_tracers: tracers is NULL");
+    int rc = check_groups("obm_scale_negative_tracers", ntracers, ngroups, groups);
+    if (rc) return rc;
+    if (ngroups == 0) return 0;
+    ScaleArgs a;
+    memset(&a, 0, sizeof(a));
+    rc = make_dims(grid, &a.d, false);
+    if (rc) return rc;
+    a.ntracers = ntracers;
+    a.ngroups = ngroups;
+    a.fill = invalid_fill_value;
+    for (int t = 0; t < ntracers; t++) {
+        OBM_REQUIRE(tracers[t] != nullptr, OBM_ENULL, "obm_scale_negative_tracers: tracers[%d] is NULL", t);
+        a.tracers[t] = tracers[t];
+    }
+    for (int q = 0; q < ngroups; q++) a.groups[q] = groups[q];
+    const long long cells = cell_count(a.d);
+    const size_t smem = (size_t)ntracers * SN_BLOCK * sizeof(double);
+    scale_negative_kernel<<<(unsigned)((cells + SN_BLOCK - 1) / SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
+    return launch_status("scale_negative_kernel");
+}
+
+extern "C" int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tracers, void* stream) {
+    OBM_REQUIRE(tracers != nullptr, OBM_ENULL, "obm_zero_negative_tracers: tracers is NULL");
+    OBM_REQUIRE(ntracers >= 0 && ntracers <= OBM_MAX_SCALE_TRACERS && n_parent >= 0, OBM_ESIZE,
+                "obm_zero_negative_tracers: ntracers = %d, n = %lld", ntracers, (long long)n_parent);
+    if (ntracers == 0 || n_parent == 0) return 0;
+    ZeroArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n_parent;
+    a.ntracers = ntracers;
+    for (int t = 0; t < ntracers; t++) {
+        OBM_REQUIRE(tracers[t] != nullptr, OBM_ENULL, "obm_zero_negative_tracers: tracers[%d] is NULL", t);
+        a.tracers[t] = tracers[t];
+    }
+    long long blocks = (n_parent + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    zero_negative_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    return launch_status("zero_negative_kernel");
+}
+
+extern "C" int64_t obm_inventory_workspace_bytes(int ngroups) {
+    if (ngroups < 0 || ngroups > OBM_MAX_SCALE_GROUPS) return OBM_ESIZE;
+    return (int64_t)ngroups * INV_BLOCKS * (int64_t)sizeof(double);
+}
+
+extern "C" int obm_inventory(const obm_grid* grid, int ntracers, const double* const* tracers, int ngroups,
+                             const obm_scale_group* groups, const double* cell_volume, double uniform_volume, double* out,
+                             void* workspace, void* stream) {
+    OBM_REQUIRE(tracers && out && workspace, OBM_ENULL, "obm_inventory: tracers / out / workspace is NULL");
+    int rc = check_groups("obm_inventory", ntracers, ngroups, groups);
+    if (rc) return rc;
+    if (ngroups == 0) return 0;
+    InvArgs a;
+    memset(&a, 0, sizeof(a));
+    rc = make_dims(grid, &a.d, false);
+    if (rc) return rc;
+    a.ntracers = ntracers;
+    a.ngroups = ngroups;
+    for (int t = 0; t < ntracers; t++) {
+        OBM_REQUIRE(tracers[t] != nullptr, OBM_ENULL, "obm_inventory: tracers[%d] is NULL", t);
+        a.tracers[t] = tracers[t];
+    }
+    for (int q = 0; q < ngroups; q++) a.groups[q] = groups[q];
+    a.volume = cell_volume;
+    a.uniform_volume = uniform_volume;
+    a.partial = (double*)workspace;
+    a.out = out;
+    cudaStream_t s = (cudaStream_t)stream;
+    inventory_partial_kernel<<<INV_BLOCKS, INV_THREADS, 0, s>>>(a);
+    rc = launch_status("inventory_partial_kernel");
+    if (rc) return rc;
+    inventory_final_kernel<<<ngroups, INV_THREADS, 0, s>>>(a.partial, INV_BLOCKS, out);
+    return launch_status("inventory_final_kernel");
+}

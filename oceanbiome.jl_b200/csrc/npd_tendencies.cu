@@ -1,0 +1,308 @@
+// npd_tendencies.cu — fused multi-tracer tendency kernel for the Nutrients–Plankton–Detritus
+// family (NPZD, LOBSTER ± Fe ± CarbonateSystem(N) ± Oxygen, four detritus choices).
+//
+// Replaces the per-tracer callables of
+//   src/Models/AdvectedPopulations/NutrientsPlanktonDetritus/{nutrients,plankton,detritus,
+//   carbonate_system,oxygen}.jl
+// which Oceananigans evaluates in one compute_Gc! launch PER TRACER: here every
+// tracer of a cell is read once (coalesced along x), the shared intermediates
+// (phytoplankton_growth, grazing, wastes) are evaluated once in registers, and every tendency
+// is written in the same pass.  HBM-bound: 144 B/cell for LOBSTER+carbonate+O₂.
+//
+// The arithmetic keeps the reference's operation order inside each expression so that the only
+// differences from the CPU oracle are FMA contraction and libdevice vs libm transcendentals.
+#include <string.h>
+
+#include "obm_common.cuh"
+
+namespace obm {
+
+constexpr int MAX_REPLICATES = 8;
+
+struct NpdArgs {
+    GridDims d;
+    obm_npd_params p;
+    const double *NO3, *NH4, *Fe, *N, *P, *Z, *T, *D, *sPOM, *bPOM, *DOM, *sPOC, *bPOC, *DOC, *PAR;
+    double *gNO3, *gNH4, *gFe, *gN, *gP, *gZ, *gD, *gsPOM, *gbPOM, *gDOM, *gsPOC, *gbPOC, *gDOC, *gO2;
+    double* gDIC[MAX_REPLICATES];
+    double* gAlk[MAX_REPLICATES];
+    int nrep;
+    int accumulate;
+};
+
+__device__ __forceinline__ void put(double* g, long long idx, double t, int accumulate) {
+    if (g == nullptr) return;
+    if (accumulate) t += g[idx];
+    g[idx] = t;
+}
+
+// plankton.jl:86-90
+__device__ __forceinline__ double mortality(int form, double X, double m) { return form == OBM_LINEAR ? m * X : m * (X * X); }
+__device__ __forceinline__ double concentration_limit(int form, double X, double k) {
+    return form == OBM_LINEAR ? X / (X + k) : (X * X) / (X * X + k * k);
+}
+
+template <int NUT, int DET>
+__global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant__ NpdArgs a) {
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    const obm_npd_params& p = a.p;
+    constexpr bool HAS_NA = (NUT != OBM_NUT_NUTRIENT);
+    constexpr bool TWO_SIZE = (DET == OBM_DET_TWO_PARTICLE || DET == OBM_DET_VARIABLE_REDFIELD);
+
+    // ---- one coalesced read of everything the cell needs -----------------------------------
+    const double P = a.P[idx], Z = a.Z[idx], PAR = a.PAR[idx];
+    double NO3 = 0, NH4 = 0, Fe = 0, N = 0, D = 0, sPOM = 0, bPOM = 0, DOM = 0, sPOC = 0, bPOC = 0, DOC = 0;
+    if constexpr (HAS_NA) { NO3 = a.NO3[idx]; NH4 = a.NH4[idx]; } else { N = a.N[idx]; }
+    if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) Fe = a.Fe[idx];
+    if constexpr (DET == OBM_DET_DETRITUS) D = a.D[idx];
+    if constexpr (TWO_SIZE) { sPOM = a.sPOM[idx]; bPOM = a.bPOM[idx]; DOM = a.DOM[idx]; }
+    if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) { sPOC = a.sPOC[idx]; bPOC = a.bPOC[idx]; DOC = a.DOC[idx]; }
+
+    // ---- growth: plankton.jl:150-220 -----------------------------------------------------------
+    double nl = 0, al = 0, Ln;
+    if constexpr (HAS_NA) {
+        nl = NO3 * exp(-p.nitrate_ammonia_inhibition * NH4) / (NO3 + p.nitrate_half_saturation);
+        al = jl_max(0.0, NH4 / (p.ammonia_half_saturation + NH4));
+        Ln = (nl + al) / 2;
+        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) Ln = Ln * (Fe / (p.iron_half_saturation + Fe));
+    } else {
+        Ln = N / (N + p.nitrate_half_saturation);
+    }
+    const double kPAR = p.light_half_saturation;
+    const double Ll = p.light_limitation == OBM_LIGHT_MONDO ? PAR / (kPAR + PAR) : PAR / sqrt(PAR * PAR + kPAR * kPAR);
+    double Lt = 1.0;
+    if (p.has_temperature_coefficient) Lt = pow(p.temperature_coefficient, a.T[idx] / 10);
+    const double muP = p.phytoplankton_maximum_growth_rate * Ll * Ln * Lt * P;  // plankton.jl:205
+
+    // ---- grazing: plankton.jl:118-135, 352-397 -----------------------------------------------
+    double sPc = 0.0;  // small_particulate_concentration detritus.jl:41,103,295,308
+    if constexpr (TWO_SIZE) sPc = sPOM;
+    if constexpr (DET == OBM_DET_DETRITUS) sPc = D * p.small_particle_fraction;
+    const double pt = p.preference_for_phytoplankton;
+    const double pr = pt * P / (pt * P + (1 - pt) * sPc + eps0());
+    const double food = pr * P + (1 - pr) * sPc;
+    const double L = concentration_limit(p.grazing_concentration_formulation, food, p.grazing_half_saturation);
+    const double g = p.maximum_grazing_rate;
+    const double Gtot = g * L * Z;
+    const double fden = food + jl_eps(food);
+    const double Gp = g * pr * L * P / fden * Z;
+    const double Gd = g * (1 - pr) * L * sPc / fden * Z;
+
+    // ---- wastes: plankton.jl:292-346 ----------------------------------------------------------
+    const double nuP = mortality(p.phytoplankton_mortality_formulation, P, p.phytoplankton_mortality_rate);
+    const double exc = p.zooplankton_excretion_rate;
+    const double pinw = p.excretion_inorganic_fraction * exc * Z + (1 - p.phytoplankton_solid_waste_fraction) * nuP;
+    const double ponw = (1 - p.ammonia_fraction_of_exudate) * p.phytoplankton_exudation_fraction * muP
+                        + (1 - p.excretion_inorganic_fraction) * exc * Z;
+    const double mZZ = p.zooplankton_mortality_rate * (Z * Z);
+    const double sw = (1 - p.zooplankton_assimilation_fraction) * Gtot + p.phytoplankton_solid_waste_fraction * nuP + mZZ;
+
+    // detritus_inorganic_nitrogen_waste: detritus.jl:161-172, 298-299, 311-313
+    double dinw;
+    const double sm = p.small_remineralisation_rate, bm = p.large_remineralisation_rate, dm = p.dissolved_remineralisation_rate;
+    const double af = p.remineralisation_inorganic_fraction;
+    if constexpr (TWO_SIZE) dinw = (af * (sm * sPOM + bm * bPOM) + dm * DOM);
+    else if constexpr (DET == OBM_DET_DETRITUS) dinw = D * p.remineralisation_rate;
+    else dinw = ponw + sw;
+
+    // ---- plankton: plankton.jl:92-116 -----------------------------------------------------------
+    put(a.gP, idx, (1 - p.phytoplankton_exudation_fraction) * muP - Gp - nuP, a.accumulate);
+    put(a.gZ, idx, p.zooplankton_assimilation_fraction * Gtot - mZZ - exc * Z, a.accumulate);
+
+    // ---- nutrients: nutrients.jl:22-64, uptake plankton.jl:223-278 --------------------------
+    double tNO3 = 0, tNH4 = 0, tN = 0, nitrif = 0;
+    const double ag = p.ammonia_fraction_of_exudate * p.phytoplankton_exudation_fraction;
+    if constexpr (HAS_NA) {
+        nitrif = p.nitrification_rate * NH4;
+        const double lim = nl + al + eps0();
+        tNO3 = nitrif - muP * nl / lim;
+        tNH4 = pinw + dinw - nitrif - (muP * al / lim - ag * muP);
+        put(a.gNO3, idx, tNO3, a.accumulate);
+        put(a.gNH4, idx, tNH4, a.accumulate);
+        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) put(a.gFe, idx, -(p.iron_ratio * muP), a.accumulate);
+    } else {
+        tN = pinw + dinw - muP * (1 - ag);
+        put(a.gN, idx, tN, a.accumulate);
+    }
+
+    // ---- detritus: detritus.jl:85-101, 143-158, 282-288 --------------------------------------
+    const double R = p.redfield_ratio;
+    if constexpr (DET == OBM_DET_DETRITUS) {
+        put(a.gD, idx, ponw + sw - Gd - p.remineralisation_rate * D, a.accumulate);
+    }
+    if constexpr (TWO_SIZE) {
+        const double ssf = p.small_solid_waste_fraction;
+        put(a.gsPOM, idx, ssf * sw - Gd - sm * sPOM, a.accumulate);
+        put(a.gbPOM, idx, (1 - ssf) * sw - bm * bPOM, a.accumulate);
+        put(a.gDOM, idx, ponw + (1 - af) * (sm * sPOM + bm * bPOM) - dm * DOM, a.accumulate);
+        if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) {
+            const double scw = sw * R;  // solid_carbon_waste plankton.jl:348
+            // calcite_production plankton.jl:399-412
+            const double cprod = (Gp * (1 - p.zooplankton_gut_calcite_dissolution) + nuP) * p.carbon_calcite_ratio * R;
+            put(a.gsPOC, idx, ssf * scw - Gd * R - sm * sPOC, a.accumulate);
+            put(a.gbPOC, idx, (1 - ssf) * scw + cprod - bm * bPOC, a.accumulate);
+            put(a.gDOC, idx, R * ponw + (1 - af) * (sm * sPOC + bm * bPOC) - dm * DOC, a.accumulate);
+        }
+    }
+
+    // ---- carbonate system: carbonate_system.jl:50-68 ------------------------------------------
+    double cdis = 0, cupt = 0;
+    if (a.nrep > 0) {
+        const double rho = p.carbon_calcite_ratio, gam = p.phytoplankton_exudation_fraction;
+        // phytoplankton_primary_production plankton.jl:280-289
+        const double ppp = (1 + rho * (1 - gam) - ag) * muP * R;
+        // detritus_inorganic_carbon_waste detritus.jl:185-196, 301-302, 315-317
+        double dicw;
+        if constexpr (DET == OBM_DET_TWO_PARTICLE) {
+            const double Rd = p.detritus_redfield_ratio;
+            dicw = af * (sm * (sPOM * Rd) + bm * (bPOM * Rd)) + dm * (DOM * Rd);
+        } else if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) {
+            dicw = af * (sm * sPOC + bm * bPOC) + dm * DOC;
+        } else if constexpr (DET == OBM_DET_DETRITUS) {
+            dicw = D * p.remineralisation_rate * p.detritus_redfield_ratio;
+        } else {
+            dicw = (ponw + sw) * R;
+        }
+        // calcite_dissolution plankton.jl:414-441 (fixed-Redfield override unless VariableRedfield)
+        if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) cdis = Gp * p.zooplankton_gut_calcite_dissolution * rho * R;
+        else cdis = (Gp + nuP) * rho * R;
+        cupt = 2 * rho * muP * R;  // calcite_uptake plankton.jl:443-450
+        const double tDIC = -ppp + R * pinw + dicw + cdis;
+        double tAlk;
+        if constexpr (HAS_NA) tAlk = tNH4 * (1 - 1.0 / 16) - tNO3 * (1 + 1.0 / 16) - 2.0 * cupt + 2.0 * cdis;
+        else tAlk = tN - 2.0 * cupt + 2.0 * cdis;
+#pragma unroll 1
+        for (int r = 0; r < a.nrep; r++) {  // CarbonateSystem(N): every replicate gets the same tendency (:70-83)
+            put(a.gDIC[r], idx, tDIC, a.accumulate);
+            put(a.gAlk[r], idx, tAlk, a.accumulate);
+        }
+    }
+
+    // ---- oxygen: oxygen.jl:21-31 (Nutrient models: bgc(Val(:NH₄)) = 0, nitrification = 0) -------
+    if (a.gO2 != nullptr) {
+        const double Rp = p.respiration_oxygen_nitrogen_ratio, Rn = p.nitrification_oxygen_nitrogen_ratio;
+        put(a.gO2, idx, Rp * muP - (Rp - Rn) * tNH4 - Rp * nitrif, a.accumulate);
+    }
+}
+
+// tracer order = required_biogeochemical_tracers (NutrientsPlanktonDetritus.jl:69-74)
+enum Role { R_NO3, R_NH4, R_FE, R_N, R_P, R_Z, R_T, R_D, R_SPOM, R_BPOM, R_DOM, R_SPOC, R_BPOC, R_DOC, R_DIC, R_ALK, R_O2 };
+
+static int npd_layout(const obm_npd_params* p, int* roles, char (*names)[16]) {
+    int n = 0;
+    auto add = [&](int role, const char* nm) {
+        if (roles) roles[n] = role;
+        if (names) {
+            memset(names[n], 0, 16);
+            strncpy(names[n], nm, 15);
+        }
+        n++;
+    };
+    switch (p->nutrients) {
+        case OBM_NUT_NUTRIENT: add(R_N, "N"); break;
+        case OBM_NUT_NITRATE_AMMONIA: add(R_NO3, "NO₃"); add(R_NH4, "NH₄"); break;
+        case OBM_NUT_NITRATE_AMMONIA_IRON: add(R_NO3, "NO₃"); add(R_NH4, "NH₄"); add(R_FE, "Fe"); break;
+        default: set_error("unknown nutrients enum %d", p->nutrients); return OBM_EENUM;
+    }
+    add(R_P, "P");
+    add(R_Z, "Z");
+    if (p->has_temperature_coefficient) add(R_T, "T");
+    switch (p->detritus) {
+        case OBM_DET_NONE: break;
+        case OBM_DET_DETRITUS: add(R_D, "D"); break;
+        case OBM_DET_TWO_PARTICLE: add(R_SPOM, "sPOM"); add(R_BPOM, "bPOM"); add(R_DOM, "DOM"); break;
+        case OBM_DET_VARIABLE_REDFIELD:
+            add(R_SPOC, "sPOC"); add(R_BPOC, "bPOC"); add(R_DOC, "DOC");
+            add(R_SPOM, "sPON"); add(R_BPOM, "bPON"); add(R_DOM, "DON");
+            break;
+        default: set_error("unknown detritus enum %d", p->detritus); return OBM_EENUM;
+    }
+    const int N = p->carbonate_replicates;
+    if (N < 0 || N > MAX_REPLICATES) {
+        set_error("carbonate_replicates = %d outside [0, %d]", N, MAX_REPLICATES);
+        return N < 0 ? OBM_ESIZE : OBM_ENOTIMPL;
+    }
+    if (N == 1) {
+        add(R_DIC, "DIC");
+        add(R_ALK, "Alk");
+    } else if (N > 1) {
+        char buf[16];
+        for (int r = 1; r <= N; r++) { snprintf(buf, 16, "DIC%d", r); add(R_DIC, buf); }
+        for (int r = 1; r <= N; r++) { snprintf(buf, 16, "Alk%d", r); add(R_ALK, buf); }
+    }
+    if (p->oxygen) add(R_O2, "O₂");
+    return n;
+}
+
+template <int NUT>
+static void launch_det(const NpdArgs& a, int det, unsigned blocks, cudaStream_t s) {
+    switch (det) {
+        case OBM_DET_NONE: npd_tendency_kernel<NUT, OBM_DET_NONE><<<blocks, 256, 0, s>>>(a); break;
+        case OBM_DET_DETRITUS: npd_tendency_kernel<NUT, OBM_DET_DETRITUS><<<blocks, 256, 0, s>>>(a); break;
+        case OBM_DET_TWO_PARTICLE: npd_tendency_kernel<NUT, OBM_DET_TWO_PARTICLE><<<blocks, 256, 0, s>>>(a); break;
+        default: npd_tendency_kernel<NUT, OBM_DET_VARIABLE_REDFIELD><<<blocks, 256, 0, s>>>(a); break;
+    }
+}
+
+}  // namespace obm
+
+using namespace obm;
+
+extern "C" int obm_npd_tracer_names(const obm_npd_params* p, char (*names)[16]) {
+    OBM_REQUIRE(p != nullptr, OBM_ENULL, "params is NULL");
+    return npd_layout(p, nullptr, names);
+}
+
+extern "C" int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p, const double* const* tracers,
+                                  const double* PAR, double* const* G, int accumulate, void* stream) {
+    OBM_REQUIRE(p != nullptr && tracers != nullptr && G != nullptr && PAR != nullptr, OBM_ENULL,
+                "obm_npd_tendencies: params / tracers / G / PAR is NULL");
+    NpdArgs a;
+    memset(&a, 0, sizeof(a));
+    int rc = make_dims(grid, &a.d, false);
+    if (rc) return rc;
+    int roles[OBM_NPD_MAX_TRACERS];
+    const int nt = npd_layout(p, roles, nullptr);
+    if (nt < 0) return nt;
+    a.p = *p;
+    a.PAR = PAR;
+    a.accumulate = accumulate ? 1 : 0;
+    int nd = 0, na = 0;
+    for (int n = 0; n < nt; n++) {
+        const double* c = tracers[n];
+        double* g = G[n];
+        const bool read = !(roles[n] == R_DIC || roles[n] == R_ALK || roles[n] == R_O2);  // one-way coupled: never read
+        OBM_REQUIRE(!read || c != nullptr, OBM_ENULL, "obm_npd_tendencies: tracers[%d] is NULL", n);
+        switch (roles[n]) {
+            case R_NO3: a.NO3 = c; a.gNO3 = g; break;
+            case R_NH4: a.NH4 = c; a.gNH4 = g; break;
+            case R_FE: a.Fe = c; a.gFe = g; break;
+            case R_N: a.N = c; a.gN = g; break;
+            case R_P: a.P = c; a.gP = g; break;
+            case R_Z: a.Z = c; a.gZ = g; break;
+            case R_T: a.T = c; break;  // no biogeochemical tendency: zero(grid) NutrientsPlanktonDetritus.jl:88
+            case R_D: a.D = c; a.gD = g; break;
+            case R_SPOM: a.sPOM = c; a.gsPOM = g; break;
+            case R_BPOM: a.bPOM = c; a.gbPOM = g; break;
+            case R_DOM: a.DOM = c; a.gDOM = g; break;
+            case R_SPOC: a.sPOC = c; a.gsPOC = g; break;
+            case R_BPOC: a.bPOC = c; a.gbPOC = g; break;
+            case R_DOC: a.DOC = c; a.gDOC = g; break;
+            case R_DIC: a.gDIC[nd++] = g; break;
+            case R_ALK: a.gAlk[na++] = g; break;
+            case R_O2: a.gO2 = g; break;
+        }
+    }
+    a.nrep = nd;
+    const long long cells = cell_count(a.d);
+    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (p->nutrients) {
+        case OBM_NUT_NUTRIENT: launch_det<OBM_NUT_NUTRIENT>(a, p->detritus, blocks, s); break;
+        case OBM_NUT_NITRATE_AMMONIA: launch_det<OBM_NUT_NITRATE_AMMONIA>(a, p->detritus, blocks, s); break;
+        default: launch_det<OBM_NUT_NITRATE_AMMONIA_IRON>(a, p->detritus, blocks, s); break;
+    }
+    return launch_status("npd_tendency_kernel");
+}

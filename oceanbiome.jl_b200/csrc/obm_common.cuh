@@ -1,0 +1,99 @@
+// obm_common.cuh — shared device/host helpers of libobm_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/obm_b200.h"
+
+namespace obm {
+
+// ---- thread-local error string (obm_last_error) -------------------------------------------
+void set_error(const char* fmt, ...);
+int launch_status(const char* what);  // cudaGetLastError → 0 or positive cudaError_t (+ message)
+
+#define OBM_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            obm::set_error(__VA_ARGS__);  \
+            return (code);                \
+        }                                 \
+    } while (0)
+
+// ---- Julia semantics ---------------------------------------------------------
+// Julia max/min propagate NaN; CUDA fmax/fmin return the non-NaN operand.
+__device__ __forceinline__ double jl_max(double a, double b) {
+    double m = fmax(a, b);
+    return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000LL) : m;
+}
+__device__ __forceinline__ double jl_min(double a, double b) {
+    double m = fmin(a, b);
+    return (a != a || b != b) ? __longlong_as_double(0x7ff8000000000000LL) : m;
+}
+// eps(0.0): smallest subnormal. FP64 subnormals are honoured on sm_100a (no FTZ for doubles).
+__device__ __forceinline__ double eps0() { return __longlong_as_double(1LL); }
+// eps(x) = ulp(x) (NaN for NaN/Inf)
+__device__ __forceinline__ double jl_eps(double x) {
+    double ax = fabs(x);
+    return __longlong_as_double(__double_as_longlong(ax) + 1) - ax;  // Inf: NaN-pattern − Inf = NaN
+}
+
+// ---- grid indexing -----------------------------------------------------------------------------
+struct GridDims {
+    int Nx, Ny, Nz, Hx, Hy, Hz;
+    int i0, i1, j0, j1;
+    long long sy, sz;  // element strides of the parent array (sx = 1)
+    const double* zc;  // shifted so that zc[k] is interior level k (k = -Hz … Nz-1+Hz valid)
+    const double* zf;
+};
+
+inline int make_dims(const obm_grid* g, GridDims* d, bool need_z) {
+    OBM_REQUIRE(g != nullptr, OBM_ENULL, "grid is NULL");
+    OBM_REQUIRE(g->Nx > 0 && g->Ny > 0 && g->Nz > 0 && g->Hx >= 0 && g->Hy >= 0 && g->Hz >= 0, OBM_ESIZE,
+                "bad grid size N=(%d,%d,%d) H=(%d,%d,%d)", g->Nx, g->Ny, g->Nz, g->Hx, g->Hy, g->Hz);
+    d->Nx = g->Nx; d->Ny = g->Ny; d->Nz = g->Nz;
+    d->Hx = g->Hx; d->Hy = g->Hy; d->Hz = g->Hz;
+    d->i0 = g->i0; d->j0 = g->j0;
+    d->i1 = g->i1 > 0 ? g->i1 : g->Nx;
+    d->j1 = g->j1 > 0 ? g->j1 : g->Ny;
+    OBM_REQUIRE(d->i0 >= 0 && d->i1 <= g->Nx && d->i0 < d->i1 && d->j0 >= 0 && d->j1 <= g->Ny && d->j0 < d->j1,
+                OBM_ESIZE, "bad sub-range i=[%d,%d) j=[%d,%d)", d->i0, d->i1, d->j0, d->j1);
+    d->sy = (long long)g->Nx + 2 * g->Hx;
+    d->sz = d->sy * ((long long)g->Ny + 2 * g->Hy);
+    if (need_z) {
+        OBM_REQUIRE(g->zc != nullptr && g->zf != nullptr, OBM_ENULL, "grid.zc / grid.zf is NULL");
+        d->zc = g->zc + g->Hz;
+        d->zf = g->zf + g->Hz;
+    } else {
+        d->zc = g->zc ? g->zc + g->Hz : nullptr;
+        d->zf = g->zf ? g->zf + g->Hz : nullptr;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ long long cell_index(const GridDims& d, int i, int j, int k) {
+    return (long long)(i + d.Hx) + d.sy * (j + d.Hy) + d.sz * (k + d.Hz);
+}
+__device__ __forceinline__ long long plane_index(const GridDims& d, int i, int j) {
+    return (long long)(i + d.Hx) + d.sy * (j + d.Hy);
+}
+
+// One thread per interior cell of the sub-range, x fastest (coalesced along the contiguous axis).
+// Returns false for out-of-range threads.
+__device__ __forceinline__ bool thread_cell(const GridDims& d, int& i, int& j, int& k) {
+    const int nx = d.i1 - d.i0, ny = d.j1 - d.j0;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)nx * ny * d.Nz;
+    if (t >= total) return false;
+    long long row = t / nx;
+    i = d.i0 + (int)(t - row * nx);
+    k = (int)(row / ny);
+    j = d.j0 + (int)(row - (long long)k * ny);
+    return true;
+}
+inline long long cell_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0) * d.Nz; }
+inline long long column_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0); }
+
+}  // namespace obm

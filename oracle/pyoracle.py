@@ -1,0 +1,264 @@
+"""pyoracle — numpy/ctypes front-end of the CPU ORACLE (oracle/src/*.c → oracle/_build/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs as the checker or as the timed CPU baseline — never by the product package.
+All arrays are float64 numpy parent arrays in the same halo'd layout the CUDA library uses
+(shape (Nz+2Hz, Ny+2Hy, Nx+2Hx), x fastest); the struct definitions are those of include/obm_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from oceanbiome_b200 import _lib as abi  # noqa: E402  (struct layouts only — no compute)
+
+LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+dp = C.POINTER(C.c_double)
+
+
+def build(force: bool = False):
+    """Compile the oracle with its Makefile (gcc -O2 -ffp-contract=off -fopenmp)."""
+    if force or not os.path.exists(LIB_PATH) or any(
+            os.path.getmtime(os.path.join(_HERE, "src", f)) > os.path.getmtime(LIB_PATH)
+            for f in os.listdir(os.path.join(_HERE, "src"))):
+        subprocess.run(["make", "-C", _HERE], check=True, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        _lib = C.CDLL(LIB_PATH)
+        _lib.orc_carbon_chemistry.restype = C.c_double
+        _lib.orc_carbon_chemistry.argtypes = [C.c_double] * 4 + [C.c_int, C.c_double, C.c_int, C.c_double, C.c_double,
+                                                                 C.c_double, C.c_double, C.c_int, C.POINTER(C.c_int),
+                                                                 C.POINTER(C.c_int)]
+        for name in ("orc_K0",):
+            getattr(_lib, name).restype = C.c_double
+            getattr(_lib, name).argtypes = [C.c_double, C.c_double]
+        for name in ("orc_K1", "orc_K2", "orc_KB", "orc_KW", "orc_KP1", "orc_KP2", "orc_KP3", "orc_KSP_calcite",
+                     "orc_KSP_aragonite"):
+            getattr(_lib, name).restype = C.c_double
+            getattr(_lib, name).argtypes = [C.c_double, C.c_double, C.c_int, C.c_double]
+        _lib.orc_KS.restype = C.c_double
+        _lib.orc_KS.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+        _lib.orc_KF.restype = C.c_double
+        _lib.orc_KF.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_double]
+        _lib.orc_KSi.restype = C.c_double
+        _lib.orc_KSi.argtypes = [C.c_double, C.c_double, C.c_double]
+        _lib.orc_ionic_strength.restype = C.c_double
+        _lib.orc_ionic_strength.argtypes = [C.c_double]
+        _lib.orc_pressure_correction.restype = C.c_double
+        _lib.orc_pressure_correction.argtypes = [C.c_int, C.c_double, C.c_double]
+        _lib.orc_first_virial.restype = C.c_double
+        _lib.orc_first_virial.argtypes = [C.c_double]
+        _lib.orc_cross_virial.restype = C.c_double
+        _lib.orc_cross_virial.argtypes = [C.c_double]
+        _lib.orc_teos10_polynomial_approximation.restype = C.c_double
+        _lib.orc_teos10_polynomial_approximation.argtypes = [C.c_double] * 3
+        _lib.orc_numerical_mean.restype = C.c_double
+        _lib.orc_numerical_mean.argtypes = [dp, dp, C.c_int, C.c_double, C.c_double]
+    return _lib
+
+
+def set_threads(n: int):
+    """OpenMP thread count of the oracle (cpu_baseline.cores)."""
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+class Grid:
+    """Host twin of oceanbiome_b200.RectilinearGrid for the oracle: same sizes/halos, host z arrays."""
+
+    def __init__(self, Nx, Ny, Nz, Hx, Hy, Hz, zc_parent, zf_parent):
+        self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz = Nx, Ny, Nz, Hx, Hy, Hz
+        self.zc_parent = np.ascontiguousarray(zc_parent, dtype=np.float64)
+        self.zf_parent = np.ascontiguousarray(zf_parent, dtype=np.float64)
+
+    @classmethod
+    def like(cls, g):
+        return cls(g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz, g.zc_host, g.zf_host)
+
+    @property
+    def parent_shape(self):
+        return (self.Nz + 2 * self.Hz, self.Ny + 2 * self.Hy, self.Nx + 2 * self.Hx)
+
+    @property
+    def plane_shape(self):
+        return (1, self.Ny + 2 * self.Hy, self.Nx + 2 * self.Hx)
+
+    def interior(self, a):
+        if a.shape[0] == 1:
+            return a[:, self.Hy:self.Hy + self.Ny, self.Hx:self.Hx + self.Nx]
+        return a[self.Hz:self.Hz + self.Nz, self.Hy:self.Hy + self.Ny, self.Hx:self.Hx + self.Nx]
+
+    def c_grid(self, i0=0, i1=0, j0=0, j1=0):
+        return abi.obm_grid(self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz, i0, i1, j0, j1,
+                            self.zc_parent.ctypes.data, self.zf_parent.ctypes.data)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+def _table(arrays):
+    return (C.c_void_p * len(arrays))(*[C.c_void_p(_ptr(a)) if a is not None else None for a in arrays])
+
+
+def _check(arrs):
+    for a in arrs:
+        if a is not None:
+            assert a.dtype == np.float64 and a.flags.c_contiguous, "oracle needs contiguous float64 parent arrays"
+
+
+# ---- NPD --------------------------------------------------------------------------------------------
+def npd_tracer_names(params):
+    names = ((C.c_char * 16) * abi.OBM_NPD_MAX_TRACERS)()
+    n = lib().orc_npd_layout(C.byref(params), None, names)
+    assert n >= 0, f"orc_npd_layout → {n}"
+    return tuple(bytes(names[i]).split(b"\0")[0].decode("utf-8") for i in range(n))
+
+
+def npd_tendencies(grid: Grid, params, tracers, PAR, G=None, accumulate=False):
+    """One full-grid pass per tracer (reference launch structure).  Returns list of G parent arrays."""
+    _check(list(tracers) + [PAR])
+    if G is None:
+        G = [np.zeros(grid.parent_shape) for _ in tracers]
+    cg = grid.c_grid()
+    rc = lib().orc_npd_tendencies(C.byref(cg), C.byref(params), _table(tracers), C.c_void_p(_ptr(PAR)), _table(G),
+                                  1 if accumulate else 0)
+    assert rc == 0, f"orc_npd_tendencies → {rc}"
+    return G
+
+
+# ---- light ------------------------------------------------------------------------------------------
+def par_twoband(grid: Grid, params, P, surface_PAR, PAR=None):
+    PAR = np.zeros(grid.parent_shape) if PAR is None else PAR
+    s_arr = surface_PAR if isinstance(surface_PAR, np.ndarray) else None
+    _check([P, PAR, s_arr])
+    cg = grid.c_grid()
+    rc = lib().orc_par_twoband(C.byref(cg), C.byref(params), C.c_void_p(_ptr(P)), C.c_void_p(_ptr(s_arr)),
+                               C.c_double(0.0 if s_arr is not None else float(surface_PAR)), C.c_void_p(_ptr(PAR)))
+    assert rc == 0
+    return PAR
+
+
+def par_multiband(grid: Grid, params, chl_a, chl_b, chl_scale, surface_PAR, bands=None, total=None):
+    nb = params.nbands
+    bands = [np.zeros(grid.parent_shape) for _ in range(nb)] if bands is None else bands
+    total = np.zeros(grid.parent_shape) if total is None else total
+    s_arr = surface_PAR if isinstance(surface_PAR, np.ndarray) else None
+    _check([chl_a, chl_b, s_arr, total] + bands)
+    cg = grid.c_grid()
+    rc = lib().orc_par_multiband(C.byref(cg), C.byref(params), C.c_void_p(_ptr(chl_a)), C.c_void_p(_ptr(chl_b)),
+                                 C.c_double(chl_scale), C.c_void_p(_ptr(s_arr)),
+                                 C.c_double(0.0 if s_arr is not None else float(surface_PAR)), _table(bands),
+                                 C.c_void_p(_ptr(total)))
+    assert rc == 0
+    return bands, total
+
+
+def euphotic_depth(grid: Grid, PAR, cutoff=1 / 1000):
+    zeu = np.zeros(grid.plane_shape)
+    _check([PAR])
+    cg = grid.c_grid()
+    rc = lib().orc_euphotic_depth(C.byref(cg), C.c_void_p(_ptr(PAR)), C.c_double(cutoff), C.c_void_p(_ptr(zeu)))
+    assert rc == 0
+    return zeu
+
+
+def mixed_layer_mean(grid: Grid, zmxl, Cfield):
+    out = np.zeros(grid.plane_shape)
+    _check([zmxl, Cfield])
+    cg = grid.c_grid()
+    rc = lib().orc_mixed_layer_mean(C.byref(cg), C.c_void_p(_ptr(zmxl)), C.c_void_p(_ptr(Cfield)), C.c_void_p(_ptr(out)))
+    assert rc == 0
+    return out
+
+
+def numerical_mean(lam, Cc, lo, hi):
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    Cc = np.ascontiguousarray(Cc, dtype=np.float64)
+    return lib().orc_numerical_mean(lam.ctypes.data_as(dp), Cc.ctypes.data_as(dp), len(lam), float(lo), float(hi))
+
+
+# ---- carbon chemistry -------------------------------------------------------------------------------
+def carbon_chemistry(DIC, T, S, Alk=0.0, pH=None, P=None, silicate=0.0, phosphate=0.0, output=abi.CC_FCO2,
+                     initial_pH_guess=8.0, return_iters=False):
+    ni, nf = C.c_int(), C.c_int()
+    v = lib().orc_carbon_chemistry(DIC, T, S, Alk, pH is not None, pH or 0.0, P is not None, P or 0.0, silicate,
+                                   phosphate, initial_pH_guess, output, C.byref(ni), C.byref(nf))
+    return (v, ni.value, nf.value) if return_iters else v
+
+
+def carbon_chemistry_sweep(T, S, DIC, Alk, P=None, silicate=None, phosphate=None, pH=None, output=abi.CC_FCO2,
+                           initial_pH_guess=8.0):
+    arrs = [T, S, DIC, Alk, P, silicate, phosphate, pH]
+    _check(arrs)
+    out = np.empty_like(DIC)
+    fe = C.c_int64()
+    rc = lib().orc_carbon_chemistry_sweep(C.c_int64(DIC.size), *[C.c_void_p(_ptr(a)) for a in arrs],
+                                          C.c_double(initial_pH_guess), C.c_int(output), C.c_void_p(_ptr(out)),
+                                          C.byref(fe))
+    assert rc == 0
+    return out, fe.value
+
+
+def calcite_saturation(grid: Grid, T, S, DIC, Alk, Si):
+    Om = np.zeros(grid.parent_shape)
+    _check([T, S, DIC, Alk, Si])
+    cg = grid.c_grid()
+    rc = lib().orc_calcite_saturation(C.byref(cg), *[C.c_void_p(_ptr(a)) for a in (T, S, DIC, Alk, Si, Om)])
+    assert rc == 0
+    return Om
+
+
+# ---- negative tracers / inventory ----------------------------------------------------------------
+def make_groups(names, groups):
+    """groups: list of (tracer_names, scalefactors) → ctypes obm_scale_group array indexing `names`."""
+    arr = (abi.obm_scale_group * len(groups))()
+    for q, (tn, sf) in enumerate(groups):
+        arr[q].n = len(tn)
+        for m, (t, f) in enumerate(zip(tn, sf)):
+            arr[q].index[m] = list(names).index(t)
+            arr[q].scalefactor[m] = float(f)
+    return arr
+
+
+def scale_negative_tracers(grid: Grid, tracers, groups, invalid_fill_value=float("nan")):
+    """In place on the list of parent arrays; `groups` from make_groups.  One pass per group."""
+    _check(tracers)
+    cg = grid.c_grid()
+    rc = lib().orc_scale_negative_tracers(C.byref(cg), len(tracers), _table(tracers), len(groups), groups,
+                                          C.c_double(invalid_fill_value))
+    assert rc == 0
+    return tracers
+
+
+def zero_negative_tracers(tracers):
+    _check(tracers)
+    rc = lib().orc_zero_negative_tracers(C.c_int64(tracers[0].size), len(tracers), _table(tracers))
+    assert rc == 0
+    return tracers
+
+
+def inventory(grid: Grid, tracers, groups, cell_volume=None, uniform_volume=1.0):
+    _check(list(tracers) + [cell_volume])
+    out = np.zeros(len(groups))
+    cg = grid.c_grid()
+    rc = lib().orc_inventory(C.byref(cg), len(tracers), _table(tracers), len(groups), groups,
+                             C.c_void_p(_ptr(cell_volume)), C.c_double(uniform_volume), C.c_void_p(_ptr(out)))
+    assert rc == 0
+    return out

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import pyoracle
+    pyoracle.build()
+    pyoracle.lib()
+    return pyoracle
+
+
+@pytest.fixture(scope="session")
+def ob():
+    import oceanbiome_b200
+    return oceanbiome_b200
+
+
+@pytest.fixture(scope="session")
+def cuda(ob):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    ob.load_library()  # fail loudly if the extension was not built
+    return torch.device("cuda:0")

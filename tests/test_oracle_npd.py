@@ -1,0 +1,115 @@
+"""Pin the ORACLE's NPD family on the properties the reference's own tests assert
+(test/test_NutrientsPlanktonDetritus.jl:41-139): the all-zero state has exactly zero tendencies,
+and total nitrogen / carbon (with scale factors) is conserved for all 36 non-sinking variants —
+both instantaneously (Σ tendencies = 0) and over 100 unit time steps (rtol √eps)."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oceanbiome_b200 as ob
+
+NUTRIENTS = (ob.NitrateAmmonia, ob.NitrateAmmoniaIron, ob.Nutrient)
+DETRITUS = (ob.TwoParticleAndDissolved, ob.VariableRedfieldDetritus, ob.Detritus)
+VARIANTS = list(itertools.product(DETRITUS, (None, ob.Oxygen), (None, ob.CarbonateSystem), NUTRIENTS))
+
+
+def make(det, oxy, car, nut):
+    return ob.NutrientsPlanktonDetritus(nutrients=nut(), plankton=ob.PhytoZoo(), detritus=det(),
+                                        carbonate_system=car() if car else None, oxygen=oxy() if oxy else None)
+
+
+def random_state(bgc, rng):
+    """initial values as in test_NutrientsPlanktonDetritus.jl:57-91"""
+    v = {"P": rng.random(), "Z": rng.random(), "NO₃": 10 * rng.random(), "NH₄": rng.random(), "Fe": 1e-3 * rng.random(),
+         "N": 10 * rng.random(), "DIC": 2000 * rng.random(), "Alk": 2000 * rng.random(), "O₂": 300 * rng.random(),
+         "sPOM": rng.random(), "bPOM": rng.random(), "DOM": rng.random(), "D": rng.random(), "T": 10.0}
+    v["sPON"], v["bPON"], v["DON"] = rng.random(), rng.random(), rng.random()
+    v["sPOC"], v["bPOC"], v["DOC"] = 6.56 * v["sPON"], 6.56 * v["bPON"], 6.56 * v["DON"]
+    return {n: v[n] for n in bgc.required_biogeochemical_tracers()}
+
+
+def tendencies(oracle, og, bgc, state, PAR=100.0):
+    names = bgc.required_biogeochemical_tracers()
+    tr = []
+    for n in names:
+        a = np.zeros(og.parent_shape)
+        og.interior(a)[...] = state[n]
+        tr.append(a)
+    par = np.full(og.parent_shape, PAR)
+    G = oracle.npd_tendencies(og, bgc.c_params(), tr, par)
+    return {n: float(og.interior(g)[0, 0, 0]) for n, g in zip(names, G)}
+
+
+def totals(bgc, values):
+    cons = bgc.conserved_tracers(labeled=True)
+    out = {"nitrogen": sum(values[n] for n in cons["nitrogen"])}
+    if "carbon" in cons:
+        out["carbon"] = sum(values[n] * f for n, f in zip(cons["carbon"]["tracers"], cons["carbon"]["scalefactors"]))
+    return out
+
+
+@pytest.fixture(scope="module")
+def one(oracle):
+    g = ob.RectilinearGrid(size=(1, 1, 1), extent=(1, 1, 2), device="cpu")
+    return oracle.Grid.like(g)
+
+
+@pytest.mark.parametrize("det,oxy,car,nut", VARIANTS)
+def test_names_match_reference_order(oracle, det, oxy, car, nut):
+    bgc = make(det, oxy, car, nut)
+    assert oracle.npd_tracer_names(bgc.c_params()) == bgc.required_biogeochemical_tracers()
+
+
+@pytest.mark.parametrize("det,oxy,car,nut", VARIANTS)
+def test_zero_state_has_zero_tendencies(oracle, one, det, oxy, car, nut):
+    # test_NutrientsPlanktonDetritus.jl:101-112 — this is what the eps(0.0) guards are for (no 0/0 NaN)
+    bgc = make(det, oxy, car, nut)
+    G = tendencies(oracle, one, bgc, {n: 0.0 for n in bgc.required_biogeochemical_tracers()})
+    assert all(v == 0.0 for v in G.values()), G
+
+
+@pytest.mark.parametrize("det,oxy,car,nut", VARIANTS)
+def test_instantaneous_conservation(oracle, one, det, oxy, car, nut):
+    bgc = make(det, oxy, car, nut)
+    rng = np.random.default_rng(42)
+    for _ in range(5):
+        G = tendencies(oracle, one, bgc, random_state(bgc, rng))
+        cons = bgc.conserved_tracers(labeled=True)
+        sN = sum(G[n] for n in cons["nitrogen"])
+        aN = sum(abs(G[n]) for n in cons["nitrogen"])
+        assert abs(sN) <= 4e-16 * aN
+        if "carbon" in cons:
+            terms = [G[n] * f for n, f in zip(cons["carbon"]["tracers"], cons["carbon"]["scalefactors"])]
+            assert abs(sum(terms)) <= 4e-16 * sum(abs(t) for t in terms)
+
+
+@pytest.mark.parametrize("det,oxy,car,nut", VARIANTS[::5])
+def test_conservation_over_100_steps(oracle, one, det, oxy, car, nut):
+    # test_NutrientsPlanktonDetritus.jl:114-139 (forward Euler here; Δt = 1 s as in the reference)
+    bgc = make(det, oxy, car, nut)
+    state = random_state(bgc, np.random.default_rng(42))
+    t0 = totals(bgc, state)
+    for _ in range(100):
+        G = tendencies(oracle, one, bgc, state)
+        state = {n: state[n] + 1.0 * G[n] for n in state}
+    t1 = totals(bgc, state)
+    for k in t0:
+        assert abs(t1[k] - t0[k]) <= 1.5e-8 * abs(t0[k])
+
+
+def test_npzd_defaults_and_oxygen_dead_dispatch(oracle, one):
+    """NPZD(grid) tracer order (:N, :P, :Z, :T, :D) constructors.jl:169; with Oxygen the `<:Nutrient`
+    specialisation is unreachable, so ∂ₜO₂ = Rp μP exactly (SURVEY App. A bug 2)."""
+    g = ob.RectilinearGrid(size=(1, 1, 1), extent=(1, 1, 2), device="cpu")
+    bgc = ob.NPZD(g, oxygen=ob.Oxygen()).underlying_biogeochemistry
+    assert bgc.required_biogeochemical_tracers() == ("N", "P", "Z", "T", "D", "O₂")
+    state = {"N": 3.0, "P": 0.4, "Z": 0.2, "T": 12.0, "D": 0.3, "O₂": 200.0}
+    G = tendencies(oracle, one, bgc, state, PAR=60.0)
+    p = bgc.plankton
+    kPAR = p.light_half_saturation
+    mu = (p.phytoplankton_maximum_growth_rate * (60.0 / np.sqrt(60.0 ** 2 + kPAR ** 2))
+          * (3.0 / (3.0 + p.nitrate_half_saturation)) * 1.88 ** (12.0 / 10) * 0.4)
+    assert np.isclose(G["O₂"], 10.75 * mu, rtol=1e-14)
+    assert G["T"] == 0.0
+    assert abs(G["N"] + G["P"] + G["Z"] + G["D"]) <= 4e-16 * sum(abs(G[n]) for n in "NPZD")
