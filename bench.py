@@ -1,0 +1,451 @@
+#!/usr/bin/env python
+"""bench.py — BGC hot-path throughput (Gcell-updates/s) on N B200s, with roofline, CPU baseline,
+end-to-end (host-buffer) number and clock record.  Contract: see the task statement / DESIGN.md §5.
+
+One "step" = one Runge–Kutta stage of the biogeochemistry for the whole local grid, i.e. exactly what
+Oceananigans triggers per stage through the plugin hooks:
+    update_biogeochemical_state!(bgc, model)   → negative scaling, PAR scan, (PISCES: zₑᵤ, ML means, Ω)
+    update_tendencies!(bgc, model)             → fused tendencies of every tracer, Gⁿ += …
+A "cell-update" = all of that for one grid cell.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+Under torchrun (N > 1) every rank owns one x–y slab of the same size (weak scaling; no data-path
+collective — every kernel is pointwise or column-local), time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+
+# --------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs)
+# --------------------------------------------------------------------------------------------------
+def workload_table():
+    return {
+        # name: (description, builder)
+        "lobster_c3": ("LOBSTER + carbonates + O2, 3-D Eady-style grid 512x512x64 (BASELINE configs[2], no sediment)",
+                       dict(model="lobster", size=(512, 512, 64), extent=(1000.0, 1000.0, 140.0))),
+        "lobster_c2": ("LOBSTER + carbonates + O2, column ensemble 4096 columns x 64 levels (BASELINE configs[1])",
+                       dict(model="lobster", size=(4096, 1, 64), extent=(4096.0, 1.0, 200.0))),
+        "npzd_c1": ("NPZD + TwoBandPAR on the README grid 160x1x32 (BASELINE configs[0])",
+                    dict(model="npzd", size=(160, 1, 32), extent=(10e3, 1.0, 500.0))),
+        "pisces_c4": ("PISCES + 3-band PAR + calcite saturation, 1024x1024x128 (BASELINE configs[3], the headline)",
+                      dict(model="pisces", size=(1024, 1024, 128), extent=(1024e3, 1024e3, 400.0))),
+        "carbon_c5": ("CarbonChemistry pH solve sweep over 1e8 synthetic (T, S, DIC, Alk) cells (BASELINE configs[4])",
+                      dict(model="carbon", n=100_000_000)),
+    }
+
+
+def default_workload():
+    import oceanbiome_b200 as ob
+    return "pisces_c4" if hasattr(ob, "PISCES") else "lobster_c3"
+
+
+class Workload:
+    """Builds the model state on `device` (synthetic fields) and exposes step()."""
+
+    def __init__(self, name, device, scale=1.0):
+        import oceanbiome_b200 as ob
+        from oceanbiome_b200 import synthetic
+        self.ob, self.name, self.device = ob, name, device
+        desc, cfg = workload_table()[name]
+        self.description, self.cfg = desc, cfg
+        self.kind = cfg["model"]
+        self.launches_per_step = 0
+        if self.kind == "carbon":
+            self._build_carbon(int(cfg["n"] * scale))
+            return
+        Nx, Ny, Nz = cfg["size"]
+        if scale != 1.0:
+            Ny = max(1, int(Ny * scale))
+        topo = ("Periodic", "Periodic" if Ny > 1 else "Flat", "Bounded")
+        size = (Nx, Ny, Nz) if Ny > 1 else (Nx, Nz)
+        extent = cfg["extent"] if Ny > 1 else (cfg["extent"][0], cfg["extent"][2])
+        self.grid = ob.RectilinearGrid(size=size, extent=extent, topology=topo, device=device)
+        if self.kind == "lobster":
+            self.bgc = ob.LOBSTER(self.grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(),
+                                  scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
+            ranges = synthetic.lobster_range
+        elif self.kind == "npzd":
+            self.bgc = ob.NPZD(self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
+            ranges = lambda n: synthetic.RANGES_NPZD[n]  # noqa: E731
+        elif self.kind == "pisces":
+            self.bgc = ob.PISCES(grid=self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
+            ranges = ob.pisces.synthetic_range
+        self.model = ob.BiogeochemicalModel(self.grid, self.bgc)
+        for n, f in self.model.tracers.items():
+            lo, hi, log = ranges(n)
+            synthetic.fill_torch(f, n, lo, hi, log)
+        if self.kind == "pisces":
+            ob.pisces.fill_synthetic_auxiliary(self.bgc, self.model)
+        self.ranges = ranges
+        self.cells = self.grid.ncells
+        nt = len(self.model.tracers)
+        nG = sum(1 for n in self.model.tracers if n not in ("T", "S"))
+        self.nG = nG
+        self.tendency_bytes_per_cell = self._tendency_bytes()
+        self.step_kernels = self._kernel_names()
+
+    # ---- algorithmic bytes per cell of the dominant (tendency) kernel, accumulate mode ------------
+    def _tendency_bytes(self):
+        if self.kind == "lobster":
+            return 8 * (7 + 1) + 16 * 10      # read 7 active tracers + PAR, RMW 10 tendencies = 224 B
+        if self.kind == "npzd":
+            return 8 * (5 + 1) + 16 * 4       # N,P,Z,D,T + PAR, RMW 4 tendencies = 112 B
+        if self.kind == "pisces":
+            return 256 + 16 * 24              # 256 B in, 24 tendencies RMW = 640 B
+        return 40
+
+    def _kernel_names(self):
+        if self.kind in ("lobster", "npzd"):
+            return ["scale_negative_kernel", "par_twoband_kernel", "npd_tendency_kernel"]
+        return []
+
+    def _build_carbon(self, n):
+        from oceanbiome_b200 import synthetic
+        dev = self.device
+        self.n = n
+        self.cells = n
+        u = lambda name: synthetic.uniform_torch(synthetic.field_id(name), 0, n, dev)  # noqa: E731
+        self.T = -2.0 + 37.0 * u("T")
+        self.S = 20.0 + 20.0 * u("S")
+        self.DIC = 1800.0 + 600.0 * u("DIC")
+        lo = torch.maximum(self.DIC * 1.02, torch.full_like(self.DIC, 2000.0))
+        self.Alk = lo + (2600.0 - lo) * u("Alk")
+        self.out = torch.empty_like(self.DIC)
+        self.cc = self.ob.CarbonChemistry(newton_iterations=12)
+        self.tendency_bytes_per_cell = 40
+        self.launches_per_step = 1
+        self.step_kernels = ["carbon_sweep_kernel"]
+
+    # ---- one step of the hot path, inputs resident in HBM -------------------------------------------
+    def step(self, ev=None):
+        if self.kind == "carbon":
+            if ev:
+                ev[0].record()
+            self.cc(DIC=self.DIC, T=self.T, S=self.S, Alk=self.Alk, output="pHᶠ", out=self.out)
+            if ev:
+                ev[1].record()
+            return 1
+        m = self.model
+        m.biogeochemistry.update_biogeochemical_state(m)
+        if ev:
+            ev[0].record()
+        m.biogeochemistry.update_tendencies(m)
+        if ev:
+            ev[1].record()
+        return len(self.step_kernels)
+
+
+# --------------------------------------------------------------------------------------------------
+# end-to-end leg: host (pinned) buffers in, host buffers out, through the public API
+# --------------------------------------------------------------------------------------------------
+class HostStage:
+    """The call a user with HOST arrays makes: tracers live in pinned host memory, every step copies
+    them to the device, runs the stage through the plugin hooks, and reads every tendency back."""
+
+    def __init__(self, w: Workload):
+        self.w = w
+        if w.kind == "carbon":
+            self.h_in = [torch.empty(w.n, dtype=torch.float64).pin_memory() for _ in range(4)]
+            for h, d in zip(self.h_in, (w.T, w.S, w.DIC, w.Alk)):
+                h.copy_(d)
+            self.h_out = torch.empty(w.n, dtype=torch.float64).pin_memory()
+            self.h2d_bytes = 4 * 8 * w.n
+            self.d2h_bytes = 8 * w.n
+            return
+        m = w.model
+        self.names = list(m.tracers)
+        self.h_in = {n: torch.empty(m.tracers[n].data.shape, dtype=torch.float64).pin_memory() for n in self.names}
+        for n in self.names:
+            self.h_in[n].copy_(m.tracers[n].data)
+        self.gnames = [n for n in self.names if n not in ("T", "S")]
+        self.h_out = {n: torch.empty(m.Gn[n].data.shape, dtype=torch.float64).pin_memory() for n in self.gnames}
+        nb = m.tracers[self.names[0]].data.numel() * 8
+        self.h2d_bytes = nb * len(self.names)
+        self.d2h_bytes = nb * len(self.gnames)
+
+    def step(self):
+        w = self.w
+        if w.kind == "carbon":
+            for h, d in zip(self.h_in, (w.T, w.S, w.DIC, w.Alk)):
+                d.copy_(h, non_blocking=True)
+            w.step()
+            self.h_out.copy_(w.out, non_blocking=True)
+            return
+        m = w.model
+        for n in self.names:
+            m.tracers[n].data.copy_(self.h_in[n], non_blocking=True)
+        for n in self.gnames:
+            m.Gn[n].data.zero_()
+        w.step()
+        for n in self.gnames:
+            self.h_out[n].copy_(m.Gn[n].data, non_blocking=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(self.samples),
+                "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(workload)
+    return None
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU legs (the oracle = port of the reference algorithm and launch structure)
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(name, threads, budget_cells):
+    """Time the oracle (one pass per tracer, reference solver, serial-in-z PAR, one pass per group) on a
+    bounded sub-volume of the same workload.  Returns (cells/s, sample description)."""
+    import pyoracle
+    from oceanbiome_b200 import synthetic
+    import oceanbiome_b200 as ob
+    pyoracle.build()
+    pyoracle.set_threads(threads)
+    desc, cfg = workload_table()[name]
+    if cfg["model"] == "carbon":
+        n = int(budget_cells)
+        u = lambda nm: synthetic.uniform_numpy(synthetic.field_id(nm), 0, n)  # noqa: E731
+        T, S, DIC = -2.0 + 37.0 * u("T"), 20.0 + 20.0 * u("S"), 1800.0 + 600.0 * u("DIC")
+        lo = np.maximum(DIC * 1.02, 2000.0)
+        Alk = lo + (2600.0 - lo) * u("Alk")
+        t0 = time.perf_counter()
+        pyoracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=2)
+        dt = time.perf_counter() - t0
+        return n / dt, f"first {n} cells of the sweep, reference damped Newton (atol 1e-20, max 100 iterations)"
+    Nx, Ny, Nz = cfg["size"]
+    ny = max(1, min(Ny, int(budget_cells // (Nx * Nz))))
+    nx = Nx if ny >= 1 and Nx * Nz <= budget_cells else max(1, int(budget_cells // Nz))
+    topo = ("Periodic", "Periodic" if ny > 1 else "Flat", "Bounded")
+    size = (nx, ny, Nz) if ny > 1 else (nx, Nz)
+    ext = cfg["extent"]
+    extent = (ext[0] * nx / Nx, ext[1] * ny / Ny, ext[2]) if ny > 1 else (ext[0] * nx / Nx, ext[2])
+    grid = ob.RectilinearGrid(size=size, extent=extent, topology=topo, device="cpu")
+    og = pyoracle.Grid.like(grid)
+    if cfg["model"] in ("lobster", "npzd"):
+        if cfg["model"] == "lobster":
+            bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(), scale_negatives=True)
+            rng = synthetic.lobster_range
+        else:
+            bgc = ob.NPZD(grid, scale_negatives=True)
+            rng = lambda n: synthetic.RANGES_NPZD[n]  # noqa: E731
+        u = bgc.underlying_biogeochemistry
+        names = u.required_biogeochemical_tracers()
+        host = {n: synthetic.fill_numpy(np.zeros(og.parent_shape), og, n, *rng(n)) for n in names}
+        mods = bgc.modifiers if isinstance(bgc.modifiers, tuple) else (bgc.modifiers,)
+        groups = [(m.tracers, m.scalefactors) for m in mods]
+        snames = []
+        for tn, _ in groups:
+            snames += [t for t in tn if t not in snames]
+        cgroups = pyoracle.make_groups(snames, groups)
+        G = [np.zeros(og.parent_shape) for _ in names]
+        PAR = np.zeros(og.parent_shape)
+        t0 = time.perf_counter()
+        pyoracle.scale_negative_tracers(og, [host[n] for n in snames], cgroups)
+        pyoracle.par_twoband(og, bgc.light_attenuation.c_params(), host["P"], 100.0, PAR)
+        pyoracle.npd_tendencies(og, u.c_params(), [host[n] for n in names], PAR, G=G, accumulate=True)
+        dt = time.perf_counter() - t0
+    else:
+        dt, grid = ob.pisces.oracle_stage_seconds(pyoracle, grid, og)
+    return grid.ncells / dt, (f"{grid.Nx}x{grid.Ny}x{grid.Nz} sub-volume of the workload grid, reference launch structure "
+                             "(one pass per tracer / band / group, reference solver)")
+
+
+def run_reference_arm(args, name):
+    """--impl reference: the reference's CPU implementation of the path (here: its C restatement — Julia
+    is not in the image) with all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    desc, cfg = workload_table()[name]
+    budget = 4_000_000 if cfg["model"] != "pisces" else 400_000
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, sample = cpu_sample(name, threads, budget)
+        if s >= args.warmup:
+            vals.append(v)
+    value = float(np.mean(vals)) / 1e9
+    line = {
+        "impl": "reference", "metric": "BGC tendency Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * budget / (value * 1e9), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": {"workload": name, "description": desc},
+        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=None, choices=list(workload_table()))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink Ny (or n) for quick checks; not a bench number")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    name = args.workload or default_workload()
+    if args.impl == "reference":
+        run_reference_arm(args, name)
+        return
+
+    import oceanbiome_b200 as ob
+    from oceanbiome_b200.distributed import init_distributed
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: oceanbiome.jl_b200 has no CPU fallback")
+    ob.load_library()
+    rank, world, device = init_distributed()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    w = Workload(name, device, args.scale)
+    sampler = ClockSampler(device.index or 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for _ in range(args.warmup):
+        w.step()
+    barrier()
+    # ---- timed region: K steps, CUDA events on the launching stream --------------------------------
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    launches = 0
+    t0.record()
+    for s in range(args.steps):
+        launches += w.step(ev[s])
+    t1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = t0.elapsed_time(t1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    total_cells = w.cells * world
+    value = total_cells * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- end-to-end through the public API with host buffers ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hs = HostStage(w)
+        for _ in range(2):
+            hs.step()
+        barrier()
+        k = max(2, min(args.steps, 5))
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            hs.step()
+        b.record()
+        barrier()
+        ems = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ems], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = t.item()
+        e2e = {"value": total_cells * k / (ems * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+               "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    alg_bytes = w.tendency_bytes_per_cell * w.cells
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": w.step_kernels[-1] if w.step_kernels else None, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peak_src,
+                "algorithmic_bytes_per_cell": w.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
+                "kernel_share_of_step": kernel_ms / (ms / args.steps)}
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        desc, cfg = workload_table()[name]
+        budget = 2_000_000 if cfg["model"] != "pisces" else 200_000
+        v, sample = cpu_sample(name, 1, budget)
+        cpu = {"value": v / 1e9, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample}
+    line = {
+        "metric": "BGC tendency Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": name, "description": w.description, "cells_per_gpu": w.cells,
+                   "l2": "inputs larger than L2 (no flush needed)" if w.cells * w.tendency_bytes_per_cell > 4e8
+                         else "working set fits L2: reported as is, see DESIGN.md",
+                   "parallelism": f"xy-slab x{world}, no data-path collective"},
+        "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -264,6 +264,12 @@ int obm_inventory(const obm_grid* grid, int ntracers, const double* const* trace
                   const obm_scale_group* groups, const double* cell_volume /*nullable: 3-D field*/,
                   double uniform_volume, double* out, void* workspace, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Diagnostic (synchronises): measured FP64-pipe peak in DFMA instructions per second, the
+ * denominator of the FP64 roofline.  scratch: DEVICE buffer of >= 148*8*256 doubles.
+ * ------------------------------------------------------------------------------------ */
+double obm_fp64_peak_dfma_per_s(double* scratch, int iters, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 const char* obm_last_error(void);
 int obm_version(void);

@@ -1,0 +1,72 @@
+"""The C-ABI shared library loads on a machine without a GPU, exports every symbol that
+include/obm_b200.h declares, agrees with the ctypes mirror on struct sizes, and rejects bad
+arguments with the documented error codes before launching anything (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from oceanbiome_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "obm_b200.h"), encoding="utf-8").read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(obm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"libobm_b200.so does not export {n}"
+    assert sorted(_lib.PROTOTYPES) == names, "ctypes PROTOTYPES and the header disagree"
+    assert lib.obm_version() == 100
+
+
+def test_struct_sizes_match_ctypes_mirror():
+    lib = _lib.load()
+    for name, cls in _lib.STRUCTS.items():
+        assert lib.obm_sizeof(name.encode()) == C.sizeof(cls), name
+    assert lib.obm_sizeof(b"no_such_struct") == -3
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    g = _lib.obm_grid(4, 4, 4, 3, 3, 3, 0, 0, 0, 0, None, None)
+    p = _lib.obm_npd_params()
+    assert lib.obm_npd_tendencies(C.byref(g), C.byref(p), None, None, None, 0, None) == -1  # OBM_ENULL
+    assert b"NULL" in lib.obm_last_error()
+    p.nutrients = 7
+    assert lib.obm_npd_tracer_names(C.byref(p), None) == -3  # OBM_EENUM
+    p.nutrients, p.carbonate_replicates = 1, 99
+    assert lib.obm_npd_tracer_names(C.byref(p), None) == -4  # OBM_ENOTIMPL
+    tb = _lib.obm_twoband_params()
+    bad = _lib.obm_grid(0, 4, 4, 3, 3, 3, 0, 0, 0, 0, None, None)
+    dummy = C.c_void_p(8)
+    assert lib.obm_par_twoband(C.byref(bad), C.byref(tb), dummy, None, 1.0, dummy, None) == -2  # OBM_ESIZE
+    assert lib.obm_par_twoband(C.byref(g), C.byref(tb), dummy, None, 1.0, dummy, None) == -1  # zc/zf NULL
+    assert lib.obm_carbon_chemistry(-1, None, dummy, dummy, dummy, dummy, None, None, None, None, 0, dummy, None) == -2
+    assert lib.obm_carbon_chemistry(4, None, dummy, dummy, dummy, dummy, None, None, None, None, 42, dummy, None) == -3
+    assert lib.obm_carbon_chemistry(0, None, None, None, None, None, None, None, None, None, 0, None, None) == 0
+    assert lib.obm_inventory_workspace_bytes(5) == 5 * 148 * 4 * 8
+
+
+def test_tracer_names_from_the_library_match_reference_order():
+    lib = _lib.load()
+    p = _lib.obm_npd_params()
+    p.nutrients, p.detritus, p.carbonate_replicates, p.oxygen = _lib.NUT_NITRATE_AMMONIA, _lib.DET_TWO_PARTICLE, 2, 1
+    names = ((C.c_char * 16) * _lib.OBM_NPD_MAX_TRACERS)()
+    n = lib.obm_npd_tracer_names(C.byref(p), names)
+    got = [bytes(names[i]).split(b"\0")[0].decode() for i in range(n)]
+    assert got == ["NO₃", "NH₄", "P", "Z", "sPOM", "bPOM", "DOM", "DIC1", "DIC2", "Alk1", "Alk2", "O₂"]
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load(str(tmp_path / "nope.so"))

@@ -1,0 +1,106 @@
+"""GPU parity: the fixed-iteration ln[H⁺] Newton carbonate kernel against (i) the reference's
+16-digit docstring goldens, (ii) the oracle running the reference's own damped Newton, over the
+physical box, with pressure / silicate / phosphate, and over the reference's full validation box
+(validation/carbon_chemistry.jl:6-9).  Tolerances: |ΔpH| ≤ 1e-10, relative 1e-10 on fCO₂/pCO₂/CO₃²⁻/Ω."""
+import numpy as np
+import pytest
+import torch
+
+import oceanbiome_b200 as ob
+from oceanbiome_b200 import _lib as abi
+from helpers import ATOL_PH, RTOL_CARBON
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(x, cuda):
+    return torch.as_tensor(np.asarray(x, dtype=np.float64), device=cuda)
+
+
+def physical_box(n, seed=0):
+    rng = np.random.default_rng(seed)
+    T, S = rng.uniform(-2, 35, n), rng.uniform(20, 40, n)
+    DIC = rng.uniform(1800, 2400, n)
+    Alk = rng.uniform(np.maximum(DIC * 1.02, 2000), 2600)
+    return T, S, DIC, Alk
+
+
+def test_docstring_goldens(cuda):
+    cc = ob.CarbonChemistry()
+    one = lambda v: dev([v], cuda)  # noqa: E731
+    f = cc(DIC=one(2000.0), T=one(10.0), S=one(35.0), Alk=one(2000.0)).item()
+    pH = cc(DIC=one(2000.0), T=one(10.0), S=one(35.0), Alk=one(2000.0), output="pHᶠ").item()
+    f2 = cc(DIC=one(2000.0), T=one(10.0), S=one(35.0), pH=one(7.5)).item()
+    assert abs(f - 1308.1474527899106) <= RTOL_CARBON * 1308
+    assert abs(pH - 7.502532746463654) <= ATOL_PH
+    assert abs(f2 - 1315.7136384737507) <= RTOL_CARBON * 1315
+    p = cc(DIC=one(2136.242890518708), T=one(25.0), S=one(35.0), Alk=one(2500.0), output="pCO₂").item()
+    assert abs(p - 350) <= 0.1
+
+
+@pytest.mark.parametrize("output,tol", [("pHᶠ", ATOL_PH), ("pHᵗ", ATOL_PH), ("pHˢ", ATOL_PH), ("fCO₂", RTOL_CARBON),
+                                        ("pCO₂", RTOL_CARBON), ("CO₃²⁻", RTOL_CARBON), ("Ω", RTOL_CARBON)])
+@pytest.mark.parametrize("iters", [8, 12])
+def test_physical_box_matches_reference_solver(cuda, oracle, output, tol, iters):
+    n = 20000
+    T, S, DIC, Alk = physical_box(n)
+    kind = ob.carbon_chemistry.OUTPUTS[output]
+    want, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=kind)
+    got = ob.CarbonChemistry(newton_iterations=iters)(DIC=dev(DIC, cuda), T=dev(T, cuda), S=dev(S, cuda),
+                                                      Alk=dev(Alk, cuda), output=output).cpu().numpy()
+    err = np.abs(got - want) if output.startswith("pH") else np.abs(got - want) / np.abs(want)
+    assert err.max() <= tol, f"{output}: {err.max():.3e}"
+
+
+def test_pressure_silicate_phosphate(cuda, oracle):
+    n = 20000
+    T, S, DIC, Alk = physical_box(n, seed=3)
+    rng = np.random.default_rng(4)
+    P, Si, PO4 = rng.uniform(0, 400, n), rng.uniform(0, 150, n), rng.uniform(0, 3, n)
+    cc = ob.CarbonChemistry()
+    for output, tol in (("pHᶠ", ATOL_PH), ("Ω", RTOL_CARBON), ("pCO₂", RTOL_CARBON)):
+        kind = ob.carbon_chemistry.OUTPUTS[output]
+        want, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, P=P, silicate=Si, phosphate=PO4, output=kind)
+        got = cc(DIC=dev(DIC, cuda), T=dev(T, cuda), S=dev(S, cuda), Alk=dev(Alk, cuda), P=dev(P, cuda),
+                 silicate=dev(Si, cuda), phosphate=dev(PO4, cuda), output=output).cpu().numpy()
+        err = np.abs(got - want) if output.startswith("pH") else np.abs(got - want) / np.abs(want)
+        assert err.max() <= tol, f"{output}: {err.max():.3e}"
+
+
+def test_full_validation_box_robustness(cuda, oracle):
+    """validation/carbon_chemistry.jl:6-9: DIC, Alk ∈ [1000, 3000], S ∈ [1, 40], T ∈ [−5, 40] includes
+    unphysical corners.  Wherever the reference's solver converged to a positive root (residual at
+    its answer ≈ 0 ⇔ both agree), the 12-iteration clamped Newton must land on the same root."""
+    n = 20000
+    rng = np.random.default_rng(7)
+    T, S = rng.uniform(-5, 40, n), rng.uniform(1, 40, n)
+    DIC, Alk = rng.uniform(1000, 3000, n), rng.uniform(1000, 3000, n)
+    want, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=abi.CC_PH_FREE)
+    got = ob.CarbonChemistry(newton_iterations=12)(DIC=dev(DIC, cuda), T=dev(T, cuda), S=dev(S, cuda), Alk=dev(Alk, cuda),
+                                                   output="pHᶠ").cpu().numpy()
+    ok = np.isfinite(want)
+    err = np.abs(got[ok] - want[ok])
+    assert ok.mean() > 0.99
+    assert (err <= ATOL_PH).mean() > 0.999, f"{(err > ATOL_PH).sum()} of {ok.sum()} disagree, worst {err.max():.2e}"
+
+
+def test_nan_inputs_propagate(cuda):
+    cc = ob.CarbonChemistry()
+    T = dev([10.0, float("nan"), 10.0], cuda)
+    DIC = dev([2000.0, 2000.0, float("nan")], cuda)
+    out = cc(DIC=DIC, T=T, S=dev([35.0] * 3, cuda), Alk=dev([2200.0] * 3, cuda), output="pHᶠ").cpu().numpy()
+    assert np.isfinite(out[0]) and np.isnan(out[1]) and np.isnan(out[2])
+
+
+def test_gridded_calcite_saturation(cuda, oracle):
+    # PISCES/compute_calcite_saturation.jl:21-37: P = |z| g 1026 / 1e5 bar, silicate = Si
+    from helpers import synthetic_state
+    grid = ob.RectilinearGrid(size=(19, 6, 25), extent=(19, 6, 4000), device=cuda)
+    ranges = {"T": (2, 28, False), "S": (33, 37, False), "DIC": (1900, 2300, False), "Alk": (2300, 2500, False), "Si": (0, 150, False)}
+    devf, host, og = synthetic_state(grid, list(ranges), ranges)
+    Om = ob.CenterField(grid, "Ω")
+    ob.CarbonChemistry(newton_iterations=8).calcite_saturation(grid, devf["T"], devf["S"], devf["DIC"], devf["Alk"], devf["Si"], Om)
+    want = oracle.calcite_saturation(og, host["T"], host["S"], host["DIC"], host["Alk"], host["Si"])
+    got = Om.data.cpu().numpy()
+    err = np.abs(og.interior(got) - og.interior(want)) / np.abs(og.interior(want))
+    assert err.max() <= RTOL_CARBON

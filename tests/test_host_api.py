@@ -1,0 +1,96 @@
+"""Host-side mirror of the reference's plugin surface (CPU only, no compute): constructors, tracer
+lists, conserved groups and summaries behave like the reference's
+(test/test_NutrientsPlanktonDetritus.jl:141-152, docstrings constructors.jl:51-63,163-175)."""
+import ctypes as C
+import itertools
+
+import numpy as np
+import pytest
+
+import oceanbiome_b200 as ob
+from oceanbiome_b200 import _lib
+
+
+@pytest.fixture(scope="module")
+def grid():
+    return ob.RectilinearGrid(size=(3, 3, 30), extent=(10, 10, 200), device="cpu")
+
+
+def test_constructor_docstrings(grid):
+    # constructors.jl:56-61 and :168-173
+    assert repr(ob.LOBSTER(grid)) == ("LOBSTER model (:NO₃, :NH₄, :P, :Z, :sPOM, :bPOM, :DOM) \n"
+                                      " Light attenuation: Two-band light attenuation model (Float64)\n"
+                                      " Sediment: Nothing\n Particles: Nothing\n Modifiers: Nothing")
+    assert repr(ob.NPZD(grid)).startswith("NPZD model (:N, :P, :Z, :T, :D) \n")
+
+
+def test_constructor_types(grid):
+    lobster, npzd = ob.LOBSTER(grid), ob.NPZD(grid)
+    assert isinstance(lobster, ob.Biogeochemistry) and isinstance(npzd, ob.Biogeochemistry)
+    u = lobster.underlying_biogeochemistry
+    assert isinstance(u.nutrients, ob.NitrateAmmonia) and isinstance(u.plankton, ob.PhytoZoo)
+    assert isinstance(u.detritus, ob.TwoParticleAndDissolved)
+    u = npzd.underlying_biogeochemistry
+    assert isinstance(u.nutrients, ob.Nutrient) and isinstance(u.detritus, ob.Detritus)
+    assert u.plankton.temperature_coefficient == 1.88
+    assert lobster.required_biogeochemical_auxiliary_fields() == ("PAR",)
+    assert set(lobster.biogeochemical_auxiliary_fields()) == {"PAR"}
+
+
+@pytest.mark.parametrize("nut,det,car,oxy", list(itertools.product(
+    (ob.Nutrient, ob.NitrateAmmonia, ob.NitrateAmmoniaIron),
+    (None, ob.Detritus, ob.TwoParticleAndDissolved, ob.VariableRedfieldDetritus), (0, 1, 3), (False, True))))
+def test_tracer_lists_agree_with_the_library(nut, det, car, oxy):
+    bgc = ob.NutrientsPlanktonDetritus(nut(), ob.PhytoZoo(), det() if det else None,
+                                       ob.CarbonateSystem(car) if car else None, ob.Oxygen() if oxy else None)
+    p = bgc.c_params()
+    names = ((C.c_char * 16) * _lib.OBM_NPD_MAX_TRACERS)()
+    n = _lib.load().obm_npd_tracer_names(C.byref(p), names)
+    got = tuple(bytes(names[i]).split(b"\0")[0].decode() for i in range(n))
+    assert got == bgc.required_biogeochemical_tracers()
+
+
+def test_conserved_tracers_and_scalers(grid):
+    bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), scale_negatives=True)
+    nitrogen, carbon = bgc.conserved_tracers()
+    assert nitrogen == ("P", "Z", "NO₃", "NH₄", "sPOM", "bPOM", "DOM")
+    assert carbon["tracers"] == ("P", "Z", "DIC", "sPOM", "bPOM", "DOM")
+    R, rho = 6.56, 0.1
+    assert carbon["scalefactors"] == ((1 + rho) * R, R, 1, R, R, R)
+    assert isinstance(bgc.modifiers, tuple) and len(bgc.modifiers) == 2
+    assert all(isinstance(m, ob.ScaleNegativeTracers) for m in bgc.modifiers)
+    npzd = ob.NPZD(grid, scale_negatives=True)
+    assert isinstance(npzd.modifiers, ob.ScaleNegativeTracers)
+    assert npzd.modifiers.tracers == ("P", "Z", "N", "D")
+    with pytest.raises(ValueError, match="Incorrect number of scale factors"):
+        ob.ScaleNegativeTracers(("A", "B"), scalefactors=(1,))
+
+
+def test_drift_velocities(grid):
+    bgc = ob.LOBSTER(grid)
+    assert bgc.biogeochemical_drift_velocity("sPOM") == -3.47e-5
+    assert bgc.biogeochemical_drift_velocity("bPOM") == -200 / 86400
+    assert bgc.biogeochemical_drift_velocity("NO₃") is None
+    assert np.isclose(ob.NPZD(grid).biogeochemical_drift_velocity("D"), -2.7489 / 86400)
+
+
+def test_grid_layout_matches_oceananigans_parent_arrays():
+    g = ob.RectilinearGrid(size=(5, 4, 6), x=(0, 10), y=(0, 8), z=(-12, 0), device="cpu")
+    assert g.parent_shape == (12, 10, 11)
+    f = ob.CenterField(g)
+    assert f.data.stride() == (110, 11, 1)  # x fastest, then y, then z: Julia column-major (x, y, z)
+    np.testing.assert_allclose(g.zf, np.linspace(-12, 0, 7))
+    np.testing.assert_allclose(g.zc_host, np.arange(-17, 6, 2.0)[:12])
+    flat = ob.RectilinearGrid(size=(10,), extent=(100,), topology=("Flat", "Flat", "Bounded"), device="cpu")
+    assert (flat.Nx, flat.Ny, flat.Nz, flat.Hx, flat.Hy, flat.Hz) == (1, 1, 10, 0, 0, 3)
+    s = ob.RectilinearGrid(size=(8, 16, 4), extent=(8, 16, 4), device="cpu").slab(1, 4)
+    assert (s.Nx, s.Ny, s.Nz) == (8, 4, 4) and s.y == (4.0, 8.0)
+
+
+def test_compute_entry_points_refuse_cpu_tensors(grid):
+    bgc = ob.LOBSTER(grid)
+    model = ob.BiogeochemicalModel(grid, bgc)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.update_state()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.compute_tendencies()
