@@ -83,7 +83,7 @@ class Workload:
             self.bgc = ob.NPZD(self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
             ranges = lambda n: synthetic.RANGES_NPZD[n]  # noqa: E731
         elif self.kind == "pisces":
-            self.bgc = ob.PISCES(grid=self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
+            self.bgc = ob.PISCES(self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
             ranges = ob.pisces.synthetic_range
         self.model = ob.BiogeochemicalModel(self.grid, self.bgc)
         for n, f in self.model.tracers.items():
@@ -112,7 +112,8 @@ class Workload:
     def _kernel_names(self):
         if self.kind in ("lobster", "npzd"):
             return ["scale_negative_kernel", "par_twoband_kernel", "npd_tendency_kernel"]
-        return []
+        return ["scale_negative_kernel", "par_multiband_kernel", "euphotic_depth_kernel", "mixed_layer_mean_kernel",
+                "calcite_saturation_kernel", "pisces_tendency_kernel"]
 
     def _build_carbon(self, n):
         from oceanbiome_b200 import synthetic

@@ -229,6 +229,111 @@ int obm_calcite_saturation(const obm_grid* grid, const obm_carbchem_params* p, c
                            const double* Si, double* Omega, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (a3) PISCES — src/Models/AdvectedPopulations/PISCES/ (struct PISCES.jl:53-92), default
+ * component types: MixedMondo nano + diatoms, QualityDependant micro + meso zooplankton,
+ * DissolvedOrganicCarbon, TwoCompartmentCarbonIronParticles, NitrateAmmonia, SimpleIron,
+ * Silicate, Oxygen, Phosphate, InorganicCarbon.
+ * ------------------------------------------------------------------------------------ */
+enum { OBM_GROWTH_NUTRIENT_LIMITED = 0, OBM_GROWTH_RESPIRATION_LIMITED = 1 }; /* growth_rate.jl:69,107 */
+
+typedef struct obm_pisces_phyto { /* MixedMondo — phytoplankton/mixed_mondo.jl:23-93 */
+    int32_t growth_rate_kind;     /* OBM_GROWTH_*                                            */
+    int32_t silicate_limited;     /* nutrient_limitation.jl:15                               */
+    /* growth rate — growth_rate.jl:69-75,107-115 */
+    double base_growth_rate, temperature_sensitivity, dark_tolerance, initial_slope_of_PI_curve,
+        low_light_adaptation, basal_respiration_rate, reference_growth_rate;
+    /* NitrogenIronPhosphateSilicateLimitation — nutrient_limitation.jl:10-18 */
+    double minimum_ammonium_half_saturation, minimum_nitrate_half_saturation,
+        minimum_phosphate_half_saturation, optimal_iron_quota, minimum_silicate_half_saturation,
+        silicate_half_saturation_parameter;
+    /* MixedMondo */
+    double exudated_fraction, blue_light_absorption, green_light_absorption, red_light_absorption,
+        mortality_half_saturation, linear_mortality_rate, base_quadratic_mortality,
+        maximum_quadratic_mortality, minimum_chlorophyll_ratio, maximum_chlorophyll_ratio,
+        maximum_iron_ratio, silicate_half_saturation, enhanced_silicate_half_saturation,
+        optimal_silicate_ratio, half_saturation_for_iron_uptake, threshold_for_size_dependency,
+        size_ratio;
+} obm_pisces_phyto;
+
+typedef struct obm_pisces_zoo { /* QualityDependantZooplankton — zooplankton/food_quality_dependant.jl:11-35 */
+    double temperature_sensitivity, maximum_grazing_rate;
+    double food_preferences[4]; /* NamedTuple order (P, D, POC, Z) — zooplankton/defaults.jl:4,12 */
+    double food_threshold_concentration, specific_food_threshold_concentration,
+        grazing_half_saturation, maximum_flux_feeding_rate, iron_ratio, minimum_growth_efficiency,
+        non_assimilated_fraction, mortality_half_saturation, quadratic_mortality, linear_mortality,
+        dissolved_excretion_fraction, undissolved_calcite_fraction;
+} obm_pisces_zoo;
+
+typedef struct obm_pisces_params {
+    obm_pisces_phyto nano, diatoms; /* mixed_mondo_nano_diatoms.jl:1-28                         */
+    double base_rain_ratio;         /* nano_and_diatoms.jl:4                                    */
+    obm_pisces_zoo micro, meso;     /* zooplankton/defaults.jl:2-21                             */
+    /* MicroAndMeso — zooplankton/micro_and_meso.jl:3-17 */
+    double microzooplankton_bacteria_concentration, mesozooplankton_bacteria_concentration,
+        maximum_bacteria_concentration, bacteria_concentration_depth_exponent,
+        doc_half_saturation_for_bacterial_activity, nitrate_half_saturation_for_bacterial_activity,
+        ammonia_half_saturation_for_bacterial_activity,
+        phosphate_half_saturation_for_bacterial_activity, iron_half_saturation_for_bacterial_activity;
+    /* DissolvedOrganicCarbon — dissolved_organic_matter/dissolved_organic_carbon.jl:9-35 */
+    double dom_remineralisation_rate, dom_reference_bacteria_concentration,
+        dom_temperature_sensitivity, dom_aggregation_parameters[5];
+    /* TwoCompartmentCarbonIronParticles — particulate_organic_matter/two_size_class.jl:17-84 */
+    double pom_temperature_sensitivity, pom_base_breakdown_rate, pom_aggregation_parameters[4],
+        minimum_iron_scavenging_rate, load_specific_iron_scavenging_rate,
+        bacterial_iron_uptake_efficiency, small_fraction_of_bacterially_consumed_iron,
+        large_fraction_of_bacterially_consumed_iron, base_liable_silicate_fraction,
+        fast_dissolution_rate_of_silicate, slow_dissolution_rate_of_silicate,
+        base_calcite_dissolution_rate, calcite_dissolution_exponent,
+        maximum_iron_ratio_in_bacteria, iron_half_saturation_for_bacteria,
+        maximum_bacterial_growth_rate;
+    /* NitrateAmmonia — nitrogen/nitrate_ammonia.jl:10-16 */
+    double maximum_nitrification_rate, maximum_fixation_rate, iron_half_saturation_for_fixation,
+        phosphate_half_saturation_for_fixation, light_saturation_for_fixation;
+    /* SimpleIron — iron/simple_iron.jl:9-13 */
+    double excess_scavenging_enhancement, maximum_ligand_concentration, dissolved_ligand_ratio;
+    /* Oxygen — oxygen.jl:21-24 */
+    double ratio_for_respiration, ratio_for_nitrification;
+    /* PISCES.jl:69-76 */
+    double first_anoxia_threshold, second_anoxia_threshold, nitrogen_redfield_ratio,
+        phosphate_redfield_ratio, mixed_layer_shear, background_shear;
+    /* Host-evaluated per launch (they depend on (clock.time, latitude) only; user callables cannot
+     * cross the ABI).  `latitude` = PrescribedLatitude (common.jl:20-25).  The reference calls
+     * `bgc.day_length(φ, clock.time)` with SWAPPED arguments in every growth rate
+     * (growth_rate.jl:30) and `bgc.day_length(clock.time, φ)` in chlorophyll synthesis
+     * (growth_rate.jl:143); both are reproduced: */
+    double latitude;
+    double day_length_growth;      /* = day_length(φ, t)  — the swapped call                     */
+    double day_length_chlorophyll; /* = day_length(t, φ)                                         */
+    double silicate_climatology;   /* Si′ = ConstantField(7.5) (PISCES.jl:319)                   */
+} obm_pisces_params;
+
+#define OBM_PISCES_NTRACERS 26 /* 24 prognostic + T, S — order of PISCES.jl:94-105:
+   P PChl PFe D DChl DFe DSi Z M DOC POC GOC SFe BFe PSi CaCO₃ NO₃ NH₄ PO₄ Fe Si DIC Alk O₂ T S */
+
+typedef struct obm_pisces_fields { /* biogeochemical_auxiliary_fields — PISCES.jl:107-118 + light */
+    const double* PAR1;            /* 3-D centre fields                                           */
+    const double* PAR2;
+    const double* PAR3;
+    const double* PAR;             /* total (multi_band.jl:120)                                   */
+    const double* Omega;           /* calcite saturation Ω                                        */
+    const double* wPOC;            /* z-FACE fields (Nz+1 levels, face k at parent level k+Hz)    */
+    const double* wGOC;
+    const double* mixed_layer_depth_xy;  /* 2-D fields, parent x-y layout                         */
+    const double* euphotic_depth_xy;
+    const double* mean_mixed_layer_vertical_diffusivity_xy;
+    const double* mean_mixed_layer_light_xy;
+} obm_pisces_fields;
+
+/* Fused replacement of the 24 per-tracer callables of PISCES (files listed in SURVEY §8 a3):
+ * every tracer of a cell is read once, all shared sub-models (nutrient limitation, growth rates,
+ * grazing, mortalities, bacteria, aggregation, iron chemistry) are evaluated once in registers
+ * and all 24 tendencies are written in one pass.  tracers[n] / G[n] in OBM_PISCES_NTRACERS
+ * order; G[n] == NULL is skipped (T, S have no tendency, PISCES.jl:120). */
+int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_params* p,
+                          const double* const* tracers, const obm_pisces_fields* aux,
+                          double* const* G, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (a9) ScaleNegativeTracers — src/Utils/negative_tracers.jl:137-276.  All groups of a model
  * in ONE launch, applied sequentially in the given order (PISCES: carbon, iron, phosphate,
  * silicon, nitrogen — PISCES/coupling_utils.jl:31).

@@ -6,7 +6,7 @@ There is no CPU fallback: compute entry points raise if the CUDA library or a CU
 """
 from . import _lib
 from ._lib import ObmError, load as load_library
-from .grids import CenterField, Field, Field2D, RectilinearGrid
+from .grids import CenterField, Field, Field2D, RectilinearGrid, ZFaceField
 from .light import (MultiBandPhotosyntheticallyActiveRadiation, PrescribedPhotosyntheticallyActiveRadiation,
                     TwoBandPhotosyntheticallyActiveRadiation, compute_euphotic_depth, compute_mixed_layer_mean,
                     default_surface_PAR)
@@ -15,6 +15,8 @@ from .negative_tracers import ScaleNegativeTracers, ZeroNegativeTracers
 from .npd import (LOBSTER, NPZD, AnalyticalLightLimitation, CarbonateSystem, Detritus, Linear, MondoLightLimitation,
                   NitrateAmmonia, NitrateAmmoniaIron, Nutrient, NutrientsPlanktonDetritus, Oxygen, PhytoZoo, Quadratic,
                   TwoParticleAndDissolved, VariableRedfieldDetritus)
+from . import pisces
+from .pisces import PISCES, CBMDayLength, DepthDependantSinkingSpeed, PrescribedLatitude
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
 
 __version__ = "0.1.0"

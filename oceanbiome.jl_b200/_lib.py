@@ -96,7 +96,75 @@ class obm_scale_group(C.Structure):
     ]
 
 
+_PHYTO_DOUBLES = [
+    "base_growth_rate", "temperature_sensitivity", "dark_tolerance", "initial_slope_of_PI_curve",
+    "low_light_adaptation", "basal_respiration_rate", "reference_growth_rate",
+    "minimum_ammonium_half_saturation", "minimum_nitrate_half_saturation", "minimum_phosphate_half_saturation",
+    "optimal_iron_quota", "minimum_silicate_half_saturation", "silicate_half_saturation_parameter",
+    "exudated_fraction", "blue_light_absorption", "green_light_absorption", "red_light_absorption",
+    "mortality_half_saturation", "linear_mortality_rate", "base_quadratic_mortality", "maximum_quadratic_mortality",
+    "minimum_chlorophyll_ratio", "maximum_chlorophyll_ratio", "maximum_iron_ratio", "silicate_half_saturation",
+    "enhanced_silicate_half_saturation", "optimal_silicate_ratio", "half_saturation_for_iron_uptake",
+    "threshold_for_size_dependency", "size_ratio",
+]
+
+
+class obm_pisces_phyto(C.Structure):
+    _fields_ = [("growth_rate_kind", C.c_int32), ("silicate_limited", C.c_int32)] + [(n, C.c_double) for n in _PHYTO_DOUBLES]
+
+
+class obm_pisces_zoo(C.Structure):
+    _fields_ = ([("temperature_sensitivity", C.c_double), ("maximum_grazing_rate", C.c_double),
+                 ("food_preferences", C.c_double * 4)]
+                + [(n, C.c_double) for n in (
+                    "food_threshold_concentration", "specific_food_threshold_concentration", "grazing_half_saturation",
+                    "maximum_flux_feeding_rate", "iron_ratio", "minimum_growth_efficiency", "non_assimilated_fraction",
+                    "mortality_half_saturation", "quadratic_mortality", "linear_mortality",
+                    "dissolved_excretion_fraction", "undissolved_calcite_fraction")])
+
+
+class obm_pisces_params(C.Structure):
+    _fields_ = (
+        [("nano", obm_pisces_phyto), ("diatoms", obm_pisces_phyto), ("base_rain_ratio", C.c_double),
+         ("micro", obm_pisces_zoo), ("meso", obm_pisces_zoo)]
+        + [(n, C.c_double) for n in (
+            "microzooplankton_bacteria_concentration", "mesozooplankton_bacteria_concentration",
+            "maximum_bacteria_concentration", "bacteria_concentration_depth_exponent",
+            "doc_half_saturation_for_bacterial_activity", "nitrate_half_saturation_for_bacterial_activity",
+            "ammonia_half_saturation_for_bacterial_activity", "phosphate_half_saturation_for_bacterial_activity",
+            "iron_half_saturation_for_bacterial_activity",
+            "dom_remineralisation_rate", "dom_reference_bacteria_concentration", "dom_temperature_sensitivity")]
+        + [("dom_aggregation_parameters", C.c_double * 5),
+           ("pom_temperature_sensitivity", C.c_double), ("pom_base_breakdown_rate", C.c_double),
+           ("pom_aggregation_parameters", C.c_double * 4)]
+        + [(n, C.c_double) for n in (
+            "minimum_iron_scavenging_rate", "load_specific_iron_scavenging_rate", "bacterial_iron_uptake_efficiency",
+            "small_fraction_of_bacterially_consumed_iron", "large_fraction_of_bacterially_consumed_iron",
+            "base_liable_silicate_fraction", "fast_dissolution_rate_of_silicate", "slow_dissolution_rate_of_silicate",
+            "base_calcite_dissolution_rate", "calcite_dissolution_exponent", "maximum_iron_ratio_in_bacteria",
+            "iron_half_saturation_for_bacteria", "maximum_bacterial_growth_rate",
+            "maximum_nitrification_rate", "maximum_fixation_rate", "iron_half_saturation_for_fixation",
+            "phosphate_half_saturation_for_fixation", "light_saturation_for_fixation",
+            "excess_scavenging_enhancement", "maximum_ligand_concentration", "dissolved_ligand_ratio",
+            "ratio_for_respiration", "ratio_for_nitrification",
+            "first_anoxia_threshold", "second_anoxia_threshold", "nitrogen_redfield_ratio", "phosphate_redfield_ratio",
+            "mixed_layer_shear", "background_shear",
+            "latitude", "day_length_growth", "day_length_chlorophyll", "silicate_climatology")])
+
+
+class obm_pisces_fields(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "PAR1", "PAR2", "PAR3", "PAR", "Omega", "wPOC", "wGOC", "mixed_layer_depth_xy", "euphotic_depth_xy",
+        "mean_mixed_layer_vertical_diffusivity_xy", "mean_mixed_layer_light_xy")]
+
+
+OBM_PISCES_NTRACERS = 26
+
 STRUCTS = {
+    "obm_pisces_phyto": obm_pisces_phyto,
+    "obm_pisces_zoo": obm_pisces_zoo,
+    "obm_pisces_params": obm_pisces_params,
+    "obm_pisces_fields": obm_pisces_fields,
     "obm_grid": obm_grid,
     "obm_npd_params": obm_npd_params,
     "obm_twoband_params": obm_twoband_params,
@@ -110,6 +178,8 @@ PROTOTYPES = {
     "obm_npd_tracer_names": (C.c_int, [C.POINTER(obm_npd_params), C.c_void_p]),
     "obm_npd_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_pisces_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p,
+                                        C.POINTER(obm_pisces_fields), C.c_void_p, C.c_int, C.c_void_p]),
     "obm_par_twoband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_twoband_params), C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_void_p, C.c_void_p]),
     "obm_par_multiband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_multiband_params), C.c_void_p, C.c_void_p,

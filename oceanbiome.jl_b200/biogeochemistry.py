@@ -67,7 +67,7 @@ class Biogeochemistry:
         then the sediment adds its bottom fluxes (Sediments/tracer_coupling.jl:3-28)."""
         self.underlying_biogeochemistry.compute_tendencies(model.grid, model.tracers,
                                                            self.biogeochemical_auxiliary_fields(), model.Gn,
-                                                           accumulate=True, stream=stream)
+                                                           accumulate=True, stream=stream, time=model.clock.time)
         if self.sediment is not None:
             self.sediment.update_tendencies(self, model, stream)
 
@@ -125,7 +125,7 @@ class BiogeochemicalModel:
         names += [t for t in extra_tracers if t not in names]
         self.tracers = {n: CenterField(grid, n) for n in names}
         self.Gn = {n: CenterField(grid, "G" + n) for n in names}
-        self.Gm = {n: CenterField(grid, "G⁻" + n) for n in names}
+        self.Gm = None  # G⁻, allocated on first RK3 step
         self.timestepper = timestepper
 
     @property
@@ -153,6 +153,8 @@ class BiogeochemicalModel:
                 c.data.add_(self.Gn[n].data, alpha=dt)
             self.clock.time += dt
         else:
+            if self.Gm is None:
+                self.Gm = {n: CenterField(self.grid, "G⁻" + n) for n in self.tracers}
             for stage, (gamma, zeta) in enumerate(self.RK3):
                 self.update_state()
                 self.compute_tendencies()

@@ -37,10 +37,10 @@ extern "C" int obm_sizeof(const char* name) {
     S(obm_multiband_params);
     S(obm_carbchem_params);
     S(obm_scale_group);
-#ifdef OBM_HAVE_PISCES
+    S(obm_pisces_phyto);
+    S(obm_pisces_zoo);
     S(obm_pisces_params);
     S(obm_pisces_fields);
-#endif
 #ifdef OBM_HAVE_SEDIMENT
     S(obm_sediment_params);
     S(obm_sediment_fields);

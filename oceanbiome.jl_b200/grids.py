@@ -160,6 +160,12 @@ class Field:
     def is_2d(self) -> bool:
         return self.data.shape[0] == 1
 
+    @property
+    def face_interior(self) -> torch.Tensor:
+        """Interior of a z-FACE field: Nz + 1 faces (face k, 0-based, at parent level k + Hz)."""
+        g = self.grid
+        return self.data[g.Hz:g.Hz + g.Nz + 1, g.Hy:g.Hy + g.Ny, g.Hx:g.Hx + g.Nx]
+
     def set(self, value):
         """`set!(field, value)`: scalar, array of interior shape (Nz, Ny, Nx) or (Ny, Nx), torch or numpy."""
         if not torch.is_tensor(value):
@@ -184,6 +190,12 @@ class Field:
 
 def CenterField(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Field:
     return Field(grid, torch.full(grid.parent_shape, fill, dtype=torch.float64, device=grid.device), name)
+
+
+def ZFaceField(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Field:
+    """`ZFaceField(grid)` — (Center, Center, Face): parent has Nz + 1 + 2Hz levels."""
+    shape = (grid.Nz + 1 + 2 * grid.Hz, grid.Ny + 2 * grid.Hy, grid.Nx + 2 * grid.Hx)
+    return Field(grid, torch.full(shape, fill, dtype=torch.float64, device=grid.device), name)
 
 
 def Field2D(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Field:

@@ -258,7 +258,7 @@ class NutrientsPlanktonDetritus:
 
     # -- the fused tendency pass ---------------------------------------------------------------------
     def compute_tendencies(self, grid: RectilinearGrid, tracers: dict, auxiliary_fields: dict, G: dict,
-                           accumulate: bool = True, stream: Optional[int] = None):
+                           accumulate: bool = True, stream: Optional[int] = None, time: float = 0.0):
         """All per-tracer callables `bgc(i, j, k, grid, Val(name), clock, fields, aux)` for every
         cell in one launch; G[name] (+)= tendency."""
         names = self.required_biogeochemical_tracers()

@@ -61,9 +61,9 @@ def _shape(u, lo, hi, log):
     if log:
         if isinstance(u, np.ndarray):
             return np.exp(np.log(lo) + (np.log(hi) - np.log(lo)) * u)
-        # exp/log on the device could differ from libm by an ulp; keep log-uniform fields bit-identical
-        # by evaluating the transform on the host in every case
-        return torch.from_numpy(np.exp(np.log(lo) + (np.log(hi) - np.log(lo)) * u.cpu().numpy())).to(u.device)
+        # device exp may differ from libm by an ulp: parity tests that need bit-identical host copies
+        # either fill on the host (fill_numpy) and upload, or download the device field
+        return torch.exp(float(np.log(lo)) + float(np.log(hi) - np.log(lo)) * u)
     return lo + (hi - lo) * u
 
 

@@ -262,3 +262,44 @@ def inventory(grid: Grid, tracers, groups, cell_volume=None, uniform_volume=1.0)
                              C.c_void_p(_ptr(cell_volume)), C.c_double(uniform_volume), C.c_void_p(_ptr(out)))
     assert rc == 0
     return out
+
+
+# ---- PISCES -------------------------------------------------------------------------------------------
+def pisces_fields(aux: dict):
+    """aux: dict of numpy parent arrays keyed like obm_pisces_fields members."""
+    f = abi.obm_pisces_fields()
+    for k in ("PAR1", "PAR2", "PAR3", "PAR", "Omega", "wPOC", "wGOC", "mixed_layer_depth_xy", "euphotic_depth_xy",
+              "mean_mixed_layer_vertical_diffusivity_xy", "mean_mixed_layer_light_xy"):
+        _check([aux[k]])
+        setattr(f, k, aux[k].ctypes.data)
+    return f
+
+
+def pisces_tendencies(grid: Grid, params, tracers, aux: dict, G=None, accumulate=False, skip=("T", "S")):
+    """One full-grid pass per tracer (reference launch structure).  tracers: list of 26 parent arrays."""
+    _check(tracers)
+    if G is None:
+        G = [np.zeros(grid.parent_shape) if n < 24 else None for n in range(abi.OBM_PISCES_NTRACERS)]
+    f = pisces_fields(aux)
+    cg = grid.c_grid()
+    rc = lib().orc_pisces_tendencies(C.byref(cg), C.byref(params), _table(tracers), C.byref(f), _table(G),
+                                     1 if accumulate else 0)
+    assert rc == 0, f"orc_pisces_tendencies → {rc}"
+    return G
+
+
+def pisces_point(params, values, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z):
+    vals = (C.c_double * abi.OBM_PISCES_NTRACERS)(*values)
+    out = (C.c_double * abi.OBM_PISCES_NTRACERS)()
+    fn = lib().orc_pisces_point
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 12 + [C.c_void_p]
+    fn(C.byref(params), vals, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z, out)
+    return list(out)
+
+
+def cbm_day_length(t, phi):
+    fn = lib().orc_cbm_day_length
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_double, C.c_double]
+    return fn(t, phi)

@@ -97,7 +97,7 @@ def test_euphotic_depth_and_mixed_layer_means(cuda, oracle):
     grid = ob.RectilinearGrid(size=(10,), extent=(100,), topology=("Flat", "Flat", "Bounded"), device=cuda)
     light = lambda z: math.exp(z / 10) if z <= 0 else 2 - math.exp(-z / 10)  # noqa: E731
     PAR = ob.CenterField(grid, "PAR")
-    PAR.data[:, 0, 0] = torch.tensor([3 * light(z) for z in grid.zc_host])
+    PAR.data[:, 0, 0] = torch.tensor([3 * light(z) for z in grid.zc_host], dtype=torch.float64)
     zeu, mean = ob.Field2D(grid), ob.Field2D(grid)
     ob.compute_euphotic_depth(zeu, PAR)
     assert math.isclose(zeu.data.item(), -10 * math.log(1000), rel_tol=1e-12)

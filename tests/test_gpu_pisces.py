@@ -1,0 +1,151 @@
+"""GPU parity: the fused PISCES tendency kernel (C ABI) against the oracle on identical seeded inputs,
+the reference's conservation / zero-state test through the device path, and the whole PISCES state update
+(3-band PAR → zₑᵤ → mixed-layer means → Ω) against the oracle.  Tolerance 1e-12 scale-aware."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oceanbiome_b200 as ob
+from oceanbiome_b200 import pisces, synthetic
+from helpers import RTOL_CARBON, RTOL_TENDENCY, scale_aware_error, synthetic_state
+
+pytestmark = pytest.mark.gpu
+
+
+def build(cuda, size, extent, **kw):
+    grid = ob.RectilinearGrid(size=size, extent=extent, device=cuda)
+    bgc = ob.PISCES(grid, surface_photosynthetically_active_radiation=120.0, **kw)
+    model = ob.BiogeochemicalModel(grid, bgc)
+    return grid, bgc, model
+
+
+def host_aux(og, grid, bgc):
+    a = bgc.biogeochemical_auxiliary_fields()
+    h = lambda f: np.ascontiguousarray(f.data.cpu().numpy())  # noqa: E731
+    return {"PAR1": h(a["PAR₁"]), "PAR2": h(a["PAR₂"]), "PAR3": h(a["PAR₃"]), "PAR": h(a["PAR"]), "Omega": h(a["Ω"]),
+            "wPOC": h(a["wPOC"]), "wGOC": h(a["wGOC"]), "mixed_layer_depth_xy": h(a["zₘₓₗ"]),
+            "euphotic_depth_xy": h(a["zₑᵤ"]), "mean_mixed_layer_vertical_diffusivity_xy": h(a["κ"]),
+            "mean_mixed_layer_light_xy": h(a["mixed_layer_PAR"])}
+
+
+def fill(model, bgc):
+    host = {}
+    for n, f in model.tracers.items():
+        lo, hi, log = pisces.synthetic_range(n)
+        synthetic.fill_torch(f, n, lo, hi, log)
+        host[n] = np.ascontiguousarray(f.data.cpu().numpy())
+    pisces.fill_synthetic_auxiliary(bgc, model)
+    return host
+
+
+def compare(oracle, og, u, host, aux, G, t, accumulate=False, g0=0.0):
+    Go = oracle.pisces_tendencies(og, u.c_params(t), [host[n] for n in pisces.TRACERS], aux,
+                                  G=[np.full(og.parent_shape, g0) if n < 24 else None for n in range(26)] if accumulate else None,
+                                  accumulate=accumulate)
+    want = {n: og.interior(g) for n, g in zip(pisces.TRACERS, Go) if g is not None}
+    got = {n: og.interior(G[n].data.cpu().numpy()) for n in want}
+    # scale: the largest un-cancelled flux of the element family the tendency belongs to
+    S = np.maximum.reduce([np.abs(want[n] - g0) for n in want]) + abs(g0)
+    worst = {n: scale_aware_error(got[n], want[n], S) for n in want}
+    rel = {n: float(np.max(np.abs(got[n] - want[n]) / np.maximum(np.abs(want[n]), 1e-300))) for n in want}
+    return worst, rel
+
+
+@pytest.mark.parametrize("size,t", [((33, 7, 19), 0.37 * 365 * 86400.0), ((128, 2, 40), 1.6)])
+def test_fused_tendencies_match_oracle(cuda, oracle, size, t):
+    grid, bgc, model = build(cuda, size, (1e4, 1e3, 400.0))
+    u = bgc.underlying_biogeochemistry
+    host = fill(model, bgc)
+    model.clock.time = t
+    model.update_state()  # PAR bands, zeu, ML means, Ω on the device
+    og = oracle.Grid.like(grid)
+    aux = host_aux(og, grid, bgc)
+    G = {n: ob.CenterField(grid, fill=3.0) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G, accumulate=False, time=t)
+    worst, rel = compare(oracle, og, u, host, aux, G, t)
+    assert max(worst.values()) <= RTOL_TENDENCY, worst
+    # T and S receive nothing; halos untouched
+    for n in ("T", "S"):
+        assert bool((G[n].data == 3.0).all())
+    full = G["P"].data.cpu().numpy().copy()
+    og.interior(full)[...] = 3.0
+    assert np.all(full == 3.0)
+
+
+def test_accumulate_into_existing_tendencies(cuda, oracle):
+    grid, bgc, model = build(cuda, (20, 5, 12), (1e4, 1e3, 300.0))
+    u = bgc.underlying_biogeochemistry
+    host = fill(model, bgc)
+    model.update_state()
+    og = oracle.Grid.like(grid)
+    aux = host_aux(og, grid, bgc)
+    G = {n: ob.CenterField(grid, fill=1e-7) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G, accumulate=True, time=0.0)
+    worst, _ = compare(oracle, og, u, host, aux, G, 0.0, accumulate=True, g0=1e-7)
+    assert max(worst.values()) <= RTOL_TENDENCY, worst
+
+
+def test_reference_conservation_test_on_device(cuda):
+    """test/test_PISCES.jl:32-92 through the device path (prescribed PAR, w = 0, Ω from the state update)."""
+    grid = ob.RectilinearGrid(size=(1,), z=(-10, 0), topology=("Flat", "Flat", "Bounded"), device=cuda)
+    PAR = {n: ob.CenterField(grid, n, 100.0) for n in ("PAR₁", "PAR₂", "PAR₃")}
+    PAR["PAR"] = ob.CenterField(grid, "PAR", 300.0)
+    bgc = ob.PISCES(grid, sinking_speeds={"POC": 0.0, "GOC": 0.0},
+                    light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR),
+                    mixed_layer_depth=ob.Field2D(grid, fill=-10.0), euphotic_depth=ob.Field2D(grid, fill=-10.0),
+                    mean_mixed_layer_light=ob.Field2D(grid, fill=300.0),
+                    iron=pisces.SimpleIron(excess_scavenging_enhancement=0.0),
+                    nitrogen=pisces.NitrateAmmonia(maximum_fixation_rate=0.0))
+    u = bgc.underlying_biogeochemistry
+    model = ob.BiogeochemicalModel(grid, bgc)
+    aux = bgc.biogeochemical_auxiliary_fields()
+    # zero state → zero tendencies
+    u.compute_tendencies(grid, model.tracers, aux, model.Gn, accumulate=False, time=0.0)
+    assert all(bool((model.Gn[n].interior == 0).all()) for n in pisces.TRACERS[:24])
+    model.set(**{n: v for n, v in pisces.PISCES_INITIAL_VALUES.items()})
+    u.compute_tendencies(grid, model.tracers, aux, model.Gn, accumulate=False, time=1.0)
+    G = {n: model.Gn[n].interior.item() for n in pisces.TRACERS}
+    cons = u.conserved_tracers(ntuple=True)
+    # the fused kernel contracts a·b + c into FMAs, so budgets close to rounding of the LARGEST term rather
+    # than to the reference's absolute 1e-20 (which the un-contracted oracle meets exactly)
+    for key in ("carbon", "silicon"):
+        terms = [G[n] for n in cons[key]]
+        assert abs(sum(terms)) <= 4e-16 * sum(abs(x) for x in terms)
+    for key in ("iron", "phosphate", "nitrogen"):
+        terms = [G[n] * f for n, f in zip(cons[key]["tracers"], cons[key]["scalefactors"])]
+        assert abs(sum(terms)) <= 4e-16 * sum(abs(x) for x in terms)
+
+
+def test_state_update_matches_oracle(cuda, oracle):
+    """update_biogeochemical_state!: 3-band PAR from PChl + DChl, zₑᵤ, PAR̄ₘₓₗ, Ω (update_state.jl:1-17)."""
+    grid, bgc, model = build(cuda, (40, 6, 30), (1e4, 1e3, 500.0))
+    u = bgc.underlying_biogeochemistry
+    host = fill(model, bgc)
+    model.update_state()
+    og = oracle.Grid.like(grid)
+    la = bgc.light_attenuation
+    bands, total = oracle.par_multiband(og, la.c_params(), host["PChl"], host["DChl"], 1.0, 120.0)
+    rel = lambda a, b: float(np.max(np.abs(og.interior(a) - og.interior(b)) / np.abs(og.interior(b))))  # noqa: E731
+    for n, name in enumerate(la.field_names):
+        assert rel(la.fields[name].data.cpu().numpy(), bands[n]) <= RTOL_TENDENCY
+    PARd = la.total.data.cpu().numpy()
+    assert rel(PARd, total) <= RTOL_TENDENCY
+    zeu = oracle.euphotic_depth(og, PARd)
+    assert rel(u.euphotic_depth.data.cpu().numpy(), zeu) <= RTOL_TENDENCY
+    mean = oracle.mixed_layer_mean(og, u.mixed_layer_depth.data.cpu().numpy(), PARd)
+    assert rel(u.mean_mixed_layer_light.data.cpu().numpy(), mean) <= RTOL_TENDENCY
+    Om = oracle.calcite_saturation(og, host["T"], host["S"], host["DIC"], host["Alk"], host["Si"])
+    assert rel(u.calcite_saturation.data.cpu().numpy(), Om) <= RTOL_CARBON
+
+
+def test_full_stage_runs_with_negative_scaling(cuda):
+    grid = ob.RectilinearGrid(size=(16, 4, 10), extent=(1e3, 1e2, 100.0), device=cuda)
+    bgc = ob.PISCES(grid, scale_negatives=True, surface_photosynthetically_active_radiation=80.0)
+    model = ob.BiogeochemicalModel(grid, bgc)
+    fill(model, bgc)
+    model.tracers["P"].interior[0, 0, :4] = -0.1
+    model.time_step(60.0)
+    assert all(bool(torch.isfinite(f.interior).all()) for f in model.tracers.values())
+    assert bool((model.tracers["P"].interior >= 0).all())

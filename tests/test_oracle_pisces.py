@@ -1,0 +1,110 @@
+"""Pin the ORACLE's PISCES on what the reference's own test asserts (test/test_PISCES.jl:32-92): at
+PISCES_INITIAL_VALUES (box model, z = −5, PAR₁₂₃ = 100, PAR = 300, zₘₓₗ = zₑᵤ = −10, κ̄ = 1, PAR̄ = 300, w = 0,
+iron scavenging enhancement and N-fixation off) the carbon, iron, silicon, phosphate and nitrogen budgets of
+the 24 tendencies close to atol 1e-20 … 1e-22, and the all-zero state has exactly zero tendencies.
+Cross-check: the 24 smoke values derived independently in SURVEY §8c (Ω = 3, t = 1.6 s)."""
+import math
+
+import numpy as np
+import pytest
+
+import oceanbiome_b200 as ob
+from oceanbiome_b200 import pisces
+
+SURVEY_SMOKE = {  # SURVEY.md §8c "Readings already validated", mmol m⁻³ s⁻¹ (Fe in μmol)
+    "P": 1.683697e-06, "PChl": 9.841187e-08, "PFe": 6.841848e-08, "D": 1.121333e-07, "DChl": 5.410023e-09,
+    "DFe": 4.426870e-09, "DSi": 4.689823e-08, "Z": 3.130033e-08, "M": 4.732613e-08, "DOC": 3.978079e-07,
+    "POC": 1.017150e-06, "GOC": -1.586144e-06, "SFe": 8.212952e-08, "BFe": -8.313395e-08, "PSi": -2.725922e-08,
+    "CaCO₃": 3.631553e-09, "NO₃": -4.978455e-08, "NH₄": -1.735952e-07, "PO₄": -1.396123e-08, "Fe": -7.286382e-08,
+    "Si": -1.963901e-08, "DIC": -1.706902e-06, "Alk": -1.310737e-07, "O₂": 1.956413e-06}
+
+
+@pytest.fixture(scope="module")
+def box():
+    g = ob.RectilinearGrid(size=(1,), z=(-10, 0), topology=("Flat", "Flat", "Bounded"), device="cpu")
+    bgc = ob.PISCES(g, sinking_speeds={"POC": 0.0, "GOC": 0.0}, iron=pisces.SimpleIron(excess_scavenging_enhancement=0.0),
+                    nitrogen=pisces.NitrateAmmonia(maximum_fixation_rate=0.0))
+    return bgc.underlying_biogeochemistry
+
+
+def point(oracle, u, values, t=1.0, Omega=0.0):
+    G = oracle.pisces_point(u.c_params(t), [values[n] for n in pisces.TRACERS], 100.0, 100.0, 100.0, 300.0, Omega, 0.0, 0.0,
+                            -10.0, -10.0, 1.0, 300.0, -5.0)
+    return dict(zip(pisces.TRACERS, G))
+
+
+def test_tracer_and_auxiliary_lists(box):
+    assert box.required_biogeochemical_tracers() == (
+        "P", "PChl", "PFe", "D", "DChl", "DFe", "DSi", "Z", "M", "DOC", "POC", "GOC", "SFe", "BFe", "PSi", "CaCO₃", "NO₃",
+        "NH₄", "PO₄", "Fe", "Si", "DIC", "Alk", "O₂", "T", "S")
+    assert box.required_biogeochemical_auxiliary_fields() == (
+        "zₘₓₗ", "zₑᵤ", "Si′", "Ω", "κ", "mixed_layer_PAR", "wPOC", "wGOC", "PAR", "PAR₁", "PAR₂", "PAR₃")
+
+
+def test_zero_state_is_exactly_zero(oracle, box):
+    # test_PISCES.jl:66-69
+    G = point(oracle, box, {n: 0.0 for n in pisces.TRACERS})
+    assert all(v == 0.0 for v in G.values()), {k: v for k, v in G.items() if v != 0}
+
+
+@pytest.mark.parametrize("Omega,t", [(0.0, 1.0), (3.0, 1.6), (0.7, 86400.0 * 200)])
+def test_element_budgets_close(oracle, box, Omega, t):
+    # test_PISCES.jl:71-90 with the reference's own tolerances
+    G = point(oracle, box, pisces.PISCES_INITIAL_VALUES, t=t, Omega=Omega)
+    cons = box.conserved_tracers(ntuple=True)
+    assert abs(sum(G[n] for n in cons["carbon"])) <= 1e-20
+    assert abs(sum(G[n] * f for n, f in zip(cons["iron"]["tracers"], cons["iron"]["scalefactors"]))) <= 1e-21
+    assert abs(sum(G[n] for n in cons["silicon"])) <= 1e-21
+    assert abs(sum(G[n] * f for n, f in zip(cons["phosphate"]["tracers"], cons["phosphate"]["scalefactors"]))) <= 1e-22
+    assert abs(sum(G[n] * f for n, f in zip(cons["nitrogen"]["tracers"], cons["nitrogen"]["scalefactors"]))) <= 1e-21
+    assert G["T"] == 0.0 and G["S"] == 0.0
+
+
+def test_agrees_with_independently_derived_smoke_values(oracle, box):
+    G = point(oracle, box, pisces.PISCES_INITIAL_VALUES, t=1.6, Omega=3.0)
+    for n, v in SURVEY_SMOKE.items():
+        assert math.isclose(G[n], v, rel_tol=1e-6), (n, G[n], v)
+
+
+def test_budgets_close_on_random_states(oracle, box):
+    rng = np.random.default_rng(11)
+    cons = box.conserved_tracers(ntuple=True)
+    for _ in range(50):
+        vals = {n: v * math.exp(rng.uniform(-1, 1)) for n, v in pisces.PISCES_INITIAL_VALUES.items()}
+        vals["T"] = rng.uniform(0, 30)
+        G = oracle.pisces_point(box.c_params(rng.uniform(0, 3e7)), [vals[n] for n in pisces.TRACERS], *rng.uniform(0, 80, 3), 90.0,
+                                rng.uniform(0.3, 4), -2 / 86400, -40 / 86400, rng.uniform(-100, -5), rng.uniform(-100, -5),
+                                10 ** rng.uniform(-4, 0), rng.uniform(0, 100), rng.uniform(-200, -1))
+        G = dict(zip(pisces.TRACERS, G))
+        for key in ("carbon", "silicon"):
+            terms = [G[n] for n in cons[key]]
+            assert abs(sum(terms)) <= 1e-15 * sum(abs(x) for x in terms)
+        for key in ("iron", "phosphate", "nitrogen"):
+            terms = [G[n] * f for n, f in zip(cons[key]["tracers"], cons[key]["scalefactors"])]
+            assert abs(sum(terms)) <= 1e-15 * sum(abs(x) for x in terms)
+
+
+def test_day_length_call_orders(oracle, box):
+    """The reference calls day_length(φ, t) in growth rates and day_length(t, φ) in chlorophyll synthesis
+    (growth_rate.jl:30 vs :143); both must differ and match the C restatement of Utils.jl:13-34."""
+    for t in (0.0, 1.6, 86400.0 * 100.5):
+        p = box.c_params(t)
+        assert math.isclose(p.day_length_growth, oracle.cbm_day_length(45.0, t), rel_tol=1e-14)
+        assert math.isclose(p.day_length_chlorophyll, oracle.cbm_day_length(t, 45.0), rel_tol=1e-14)
+        assert abs(p.day_length_growth - p.day_length_chlorophyll) > 1000
+    # Forsythe et al. 1995: ~12 h at the equinoxes, longer in summer at 45°N
+    assert abs(oracle.cbm_day_length(86400.0 * 80, 45.0) / 3600 - 12.2) < 0.3
+    assert oracle.cbm_day_length(86400.0 * 172, 45.0) / 3600 > 15
+
+
+def test_conserved_groups_and_scalers(box):
+    g = ob.RectilinearGrid(size=(1,), z=(-10, 0), topology=("Flat", "Flat", "Bounded"), device="cpu")
+    bgc = ob.PISCES(g, scale_negatives=True)
+    assert len(bgc.modifiers) == 5
+    assert bgc.modifiers[1].tracers == ("PFe", "DFe", "Z", "M", "SFe", "BFe", "Fe")
+    assert bgc.modifiers[1].scalefactors == (1, 1, 0.01, 0.015, 1, 1, 1)
+    assert bgc.modifiers[3].tracers == ("DSi", "Si", "PSi")
+    assert list(bgc.biogeochemical_auxiliary_fields())[:4] == ["zₘₓₗ", "zₑᵤ", "Si′", "Ω"]
+    # wPOC: faces 1…Nz = −2/day, top face 0 (sinking_velocity_fields.jl:15-17)
+    w = bgc.underlying_biogeochemistry.sinking_velocities["POC"].face_interior[:, 0, 0]
+    assert float(w[0]) == -2 / 86400 and float(w[-1]) == 0.0
