@@ -80,7 +80,6 @@ extern "C" int obm_calcite_saturation(const obm_grid* grid, const obm_carbchem_p
     if (rc) return rc;
     a.T = T; a.S = S; a.DIC = DIC; a.Alk = Alk; a.Si = Si; a.Omega = Omega;
     defaults(p, &a.iterations, &a.initial_pH);
-    const long long cells = cell_count(a.d);
-    calcite_saturation_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    calcite_saturation_kernel<<<cell_grid(a.d, 128), 128, 0, (cudaStream_t)stream>>>(a);
     return launch_status("calcite_saturation_kernel");
 }

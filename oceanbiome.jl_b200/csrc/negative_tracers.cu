@@ -171,9 +171,8 @@ extern "C" int obm_scale_negative_tracers(const obm_grid* grid, int ntracers, do
         a.tracers[t] = tracers[t];
     }
     for (int q = 0; q < ngroups; q++) a.groups[q] = groups[q];
-    const long long cells = cell_count(a.d);
     const size_t smem = (size_t)ntracers * SN_BLOCK * sizeof(double);
-    scale_negative_kernel<<<(unsigned)((cells + SN_BLOCK - 1) / SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
+    scale_negative_kernel<<<cell_grid(a.d, SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
     return launch_status("scale_negative_kernel");
 }
 

@@ -237,7 +237,7 @@ static int npd_layout(const obm_npd_params* p, int* roles, char (*names)[16]) {
 }
 
 template <int NUT>
-static void launch_det(const NpdArgs& a, int det, unsigned blocks, cudaStream_t s) {
+static void launch_det(const NpdArgs& a, int det, dim3 blocks, cudaStream_t s) {
     switch (det) {
         case OBM_DET_NONE: npd_tendency_kernel<NUT, OBM_DET_NONE><<<blocks, 256, 0, s>>>(a); break;
         case OBM_DET_DETRITUS: npd_tendency_kernel<NUT, OBM_DET_DETRITUS><<<blocks, 256, 0, s>>>(a); break;
@@ -296,8 +296,7 @@ extern "C" int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p,
         }
     }
     a.nrep = nd;
-    const long long cells = cell_count(a.d);
-    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    const dim3 blocks = cell_grid(a.d, 256);
     cudaStream_t s = (cudaStream_t)stream;
     switch (p->nutrients) {
         case OBM_NUT_NUTRIENT: launch_det<OBM_NUT_NUTRIENT>(a, p->detritus, blocks, s); break;

@@ -81,17 +81,28 @@ __device__ __forceinline__ long long plane_index(const GridDims& d, int i, int j
 }
 
 // One thread per interior cell of the sub-range, x fastest (coalesced along the contiguous axis).
-// Returns false for out-of-range threads.
+// 3-D launch without any integer division: blockIdx.x ↔ x chunk, blockIdx.y ↔ j, blockIdx.z ↔ k
+// (when Ny exceeds the 65535 limit of gridDim.y, j is folded into blockIdx.x).
 __device__ __forceinline__ bool thread_cell(const GridDims& d, int& i, int& j, int& k) {
-    const int nx = d.i1 - d.i0, ny = d.j1 - d.j0;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)nx * ny * d.Nz;
-    if (t >= total) return false;
-    long long row = t / nx;
-    i = d.i0 + (int)(t - row * nx);
-    k = (int)(row / ny);
-    j = d.j0 + (int)(row - (long long)k * ny);
+    const int nx = d.i1 - d.i0;
+    const unsigned chunks = (nx + blockDim.x - 1) / blockDim.x;
+    unsigned bx = blockIdx.x, by = blockIdx.y;
+    if (gridDim.y == 1 && (d.j1 - d.j0) > 1) {  // folded layout
+        by = bx / chunks;
+        bx = bx - by * chunks;
+    }
+    const int ii = (int)(bx * blockDim.x + threadIdx.x);
+    if (ii >= nx) return false;
+    i = d.i0 + ii;
+    j = d.j0 + (int)by;
+    k = (int)blockIdx.z;
     return true;
+}
+inline dim3 cell_grid(const GridDims& d, int block) {
+    const unsigned chunks = (unsigned)((d.i1 - d.i0 + block - 1) / block);
+    const unsigned ny = (unsigned)(d.j1 - d.j0);
+    if (ny <= 65535u) return dim3(chunks, ny, (unsigned)d.Nz);
+    return dim3(chunks * ny, 1, (unsigned)d.Nz);
 }
 inline long long cell_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0) * d.Nz; }
 inline long long column_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0); }

@@ -36,9 +36,45 @@ struct PiscesArgs {
 };
 
 constexpr double DAY = 86400.0;
+constexpr int PB = 128;   // threads per block
+constexpr int NOUT = 24;  // tendencies staged in shared memory
 
-__device__ __forceinline__ double min3(double a, double b, double c) { return jl_min(jl_min(a, b), c); }
-__device__ __forceinline__ double min4(double a, double b, double c, double d) { return jl_min(jl_min(jl_min(a, b), c), d); }
+// ---- arithmetic policy -------------------------------------------------------------------------------
+// EXACT: IEEE division, NaN-propagating min/max — the reference's semantics operation by operation.
+// FAST (default path): a lean branch-free division (MUFU.RCP64H seed + 2 Newton steps + one residual
+// correction: ≤ 1 ulp, 8 FP64 instructions instead of the ≈ 30-instruction IEEE sequence with its
+// slow-path call scaffolding), `x / (y + eps(0.0))` with the reference's exact y == 0 behaviour
+// (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and plain
+// fmin/fmax.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
+// by fmin/fmax) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
+__device__ __forceinline__ double rcp_fast(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    return r;
+}
+template <bool EXACT>
+struct Ar {
+    static __device__ __forceinline__ double div(double a, double b) {
+        if (EXACT) return a / b;
+        const double r = rcp_fast(b);
+        const double q = a * r;
+        return fma(fma(-b, q, a), r, q);
+    }
+    // a / (y + eps(0.0))
+    static __device__ __forceinline__ double gdiv(double a, double y) {
+        if (EXACT) return a / (y + eps0());
+        const bool z = (y == 0.0);
+        const double q = div(a, z ? 1.0 : y);
+        const double q0 = (a * 0x1p537) * 0x1p537;  // a / 2⁻¹⁰⁷⁴, exact incl. overflow to ±Inf
+        return z ? q0 : q;
+    }
+    static __device__ __forceinline__ double mx(double a, double b) { return EXACT ? jl_max(a, b) : fmax(a, b); }
+    static __device__ __forceinline__ double mn(double a, double b) { return EXACT ? jl_min(a, b) : fmin(a, b); }
+    static __device__ __forceinline__ double mn3(double a, double b, double c) { return mn(mn(a, b), c); }
+    static __device__ __forceinline__ double mn4(double a, double b, double c, double d) { return mn(mn(mn(a, b), c), d); }
+};
 
 struct Cell {
     double NO3, NH4, PO4, Fe, Si, T, O2;
@@ -52,169 +88,161 @@ struct Phyto {  // everything the rest of the model needs from one phytoplankton
 };
 
 // nutrient_limitation.jl:20-73 + growth_rate.jl:3-47 + mixed_mondo.jl:137-175, evaluated ONCE per class
+template <class A>
 __device__ __forceinline__ Phyto phytoplankton(const obm_pisces_params& p, const obm_pisces_phyto& ph, const Cell& c,
                                                double I, double IChl, double IFe, double fT, double shear) {
     Phyto r;
     // quotas
-    r.tFe = IFe / (I + eps0());
-    r.tChl = IChl / (12 * I + eps0());
+    r.tFe = A::gdiv(IFe, I);
+    r.tChl = A::gdiv(IChl, 12 * I);
     const double tFe_l = I == 0 ? 0.0 : r.tFe;
     const double tChl_l = I == 0 ? 0.0 : r.tChl;
     // size_factor mixed_mondo.jl:207-215
-    const double I1 = jl_min(I, ph.threshold_for_size_dependency);
-    const double I2 = jl_max(0.0, I - ph.threshold_for_size_dependency);
-    const double Kbar = (I1 + ph.size_ratio * I2) / (I1 + I2 + eps0());
+    const double I1 = A::mn(I, ph.threshold_for_size_dependency);
+    const double I2 = A::mx(0.0, I - ph.threshold_for_size_dependency);
+    const double Kbar = A::gdiv(I1 + ph.size_ratio * I2, I1 + I2);
     const double Kno = ph.minimum_nitrate_half_saturation * Kbar, Knh = ph.minimum_ammonium_half_saturation * Kbar;
     const double Kp = ph.minimum_phosphate_half_saturation * Kbar, Ksi = ph.minimum_silicate_half_saturation * Kbar;
     // nitrogen_limitation(N₁, N₂, K₁, K₂) nutrient_limitation.jl:73
-    r.LNO3 = (Knh * c.NO3) / (Kno * Knh + Kno * c.NH4 + Knh * c.NO3 + eps0());
-    r.LNH4 = (Kno * c.NH4) / (Knh * Kno + Knh * c.NO3 + Kno * c.NH4 + eps0());
+    r.LNO3 = A::gdiv(Knh * c.NO3, Kno * Knh + Kno * c.NH4 + Knh * c.NO3);
+    r.LNH4 = A::gdiv(Kno * c.NH4, Knh * Kno + Knh * c.NO3 + Kno * c.NH4);
     r.LN = r.LNO3 + r.LNH4;
-    r.LPO4 = c.PO4 / (c.PO4 + Kp + eps0());
+    r.LPO4 = A::gdiv(c.PO4, c.PO4 + Kp);
     const double tm = 1000 * (0.0016 / 55.85 * 12 * tChl_l + 1.5 * 1.21e-5 * 14 / (55.85 * 7.625) * r.LN
                               + 1.15e-4 * 14 / (55.85 * 7.625) * r.LNO3);
-    r.LFe = jl_min(1.0, jl_max(0.0, (tFe_l - tm) / ph.optimal_iron_quota));
+    r.LFe = A::mn(1.0, A::mx(0.0, A::div(tFe_l - tm, ph.optimal_iron_quota)));
     const double Sip = p.silicate_climatology, pk = ph.silicate_half_saturation_parameter;
-    const double KSi = Ksi + 7 * (Sip * Sip) / (pk * pk + Sip * Sip);
-    double LSi = c.Si / (c.Si + KSi);
+    const double KSi = Ksi + 7 * (Sip * Sip) / (pk * pk + Sip * Sip);  // parameters only: hoisted by the compiler
+    double LSi = A::div(c.Si, c.Si + KSi);
     LSi = ph.silicate_limited ? LSi : __longlong_as_double(0x7ff0000000000000LL);
-    r.L = min4(r.LN, r.LPO4, r.LFe, LSi);
+    r.L = A::mn4(r.LN, r.LPO4, r.LFe, LSi);
 
     // growth rate (μ::BaseProduction)(…, L) with the SWAPPED day length — growth_rate.jl:3-47
     const double PAR = ph.blue_light_absorption * c.PAR1 + ph.green_light_absorption * c.PAR2 + ph.red_light_absorption * c.PAR3;
     const double dl = p.day_length_growth;
-    const double dd = jl_max(0.0, c.zeu - c.zmxl);
-    const double drt = dd * dd / c.kappa;
+    const double dd = A::mx(0.0, c.zeu - c.zmxl);
+    const double drt = A::div(dd * dd, c.kappa);
     r.mui = ph.base_growth_rate * fT;
-    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);
-    const double f2 = 1 - drt / (drt + ph.dark_tolerance);
+    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);  // parameters only
+    const double f2 = 1 - A::div(drt, drt + ph.dark_tolerance);
     double alpha = ph.initial_slope_of_PI_curve;
     if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
     else alpha = alpha * (1 + 0.0);
     double fl;
     if (ph.growth_rate_kind == OBM_GROWTH_NUTRIENT_LIMITED)
-        fl = 1 - exp(-alpha * r.tChl * PAR / (dl * r.mui * r.L + eps0()));
+        fl = 1 - exp(A::gdiv(-alpha * r.tChl * PAR, dl * r.mui * r.L));
     else
-        fl = 1 - exp(-alpha * r.tChl * PAR / (dl * (ph.basal_respiration_rate + ph.reference_growth_rate)));
+        fl = 1 - exp(A::div(-alpha * r.tChl * PAR, dl * (ph.basal_respiration_rate + ph.reference_growth_rate)));
     r.mu = r.mui * f1 * f2 * fl * r.L;
     r.muI = r.mu * I;
 
     // mortality mixed_mondo.jl:137-167
-    r.lin = ph.linear_mortality_rate * I / (I + ph.mortality_half_saturation) * I;
-    const double w = ph.base_quadratic_mortality + ph.maximum_quadratic_mortality * 0.25 * (1 - r.L * r.L) / (0.25 + r.L * r.L);
+    r.lin = A::div(ph.linear_mortality_rate * I, I + ph.mortality_half_saturation) * I;
+    const double w = ph.base_quadratic_mortality
+                     + A::div(ph.maximum_quadratic_mortality * 0.25 * (1 - r.L * r.L), 0.25 + r.L * r.L);
     r.quad = shear * w * (I * I);
     return r;
 }
 
 // chlorophyll synthesis: production_and_energy_assimilation_absorption_ratio (growth_rate.jl:126-156)
 // + chlorophyll_growth (mixed_mondo.jl:112-124); CORRECT day-length order here
+template <class A>
 __device__ __forceinline__ double chlorophyll_growth(const obm_pisces_params& p, const obm_pisces_phyto& ph, const Cell& c,
                                                      const Phyto& r, double I, double IChl) {
     const double PAR = ph.blue_light_absorption * c.PAR1 + ph.green_light_absorption * c.PAR2 + ph.red_light_absorption * c.PAR3;
     const double dl = p.day_length_chlorophyll;
-    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);
-    const double mucheck = r.mu / f1 * dl;
+    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);  // parameters only
+    const double mucheck = A::div(r.mu, f1) * dl;
     double alpha = ph.initial_slope_of_PI_curve;
     if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
     else alpha = alpha * (1 + 0.0);
-    const double rho = 12 * mucheck * I / (alpha * IChl * PAR + eps0()) * r.L;
+    const double rho = A::gdiv(12 * mucheck * I, alpha * IChl * PAR) * r.L;
     const double t0 = ph.minimum_chlorophyll_ratio, t1 = ph.maximum_chlorophyll_ratio;
     return (1 - ph.exudated_fraction) * 12 * (t0 + (t1 - t0) * rho) * r.mu * I;
 }
 
 // iron_uptake mixed_mondo.jl:177-205
+template <class A>
 __device__ __forceinline__ double iron_uptake(const obm_pisces_phyto& ph, const Cell& c, const Phyto& r, double I) {
-    const double I1 = jl_min(I, ph.threshold_for_size_dependency);
-    const double I2 = jl_max(0.0, I - ph.threshold_for_size_dependency);
-    const double K = ph.half_saturation_for_iron_uptake * ((I1 + ph.size_ratio * I2) / (I1 + I2 + eps0()));
-    const double L1 = c.Fe / (c.Fe + K + eps0());
-    const double L2 = 4 - 4.5 * r.LFe / (r.LFe + 1);
-    const double q = r.tFe / ph.maximum_iron_ratio;
-    return (1 - ph.exudated_fraction) * ph.maximum_iron_ratio * L1 * L2 * jl_max(0.0, (1 - q) / (1.05 - q)) * r.mui * I;
+    const double I1 = A::mn(I, ph.threshold_for_size_dependency);
+    const double I2 = A::mx(0.0, I - ph.threshold_for_size_dependency);
+    const double K = ph.half_saturation_for_iron_uptake * A::gdiv(I1 + ph.size_ratio * I2, I1 + I2);
+    const double L1 = A::gdiv(c.Fe, c.Fe + K);
+    const double L2 = 4 - A::div(4.5 * r.LFe, r.LFe + 1);
+    const double q = A::div(r.tFe, ph.maximum_iron_ratio);
+    return (1 - ph.exudated_fraction) * ph.maximum_iron_ratio * L1 * L2 * A::mx(0.0, A::div(1 - q, 1.05 - q)) * r.mui * I;
 }
 
 struct Zoo {
-    double tsg, avail, ge, gI, gfI, base_ff, inv_avail_I;  // inv_avail_I: tsg / (avail + eps) handled per use
+    double tsg, avail, ge, gI, gfI, base_ff;
     double mort, lin_mort, iron_graze, iron_ff;
 };
 
 // food_quality_dependant.jl:126-220, iron_grazing.jl:2-51 — evaluated ONCE per class
-template <int N>
-__device__ __forceinline__ Zoo zooplankton(const obm_pisces_params& p, const obm_pisces_zoo& z, const double (&food)[4],
-                                           const double (&iron)[4], double I, double fT, double dO2, double flux_C,
-                                           double flux_Fe) {
+template <class A, int N>
+__device__ __forceinline__ Zoo zooplankton(const obm_pisces_zoo& z, const double (&food)[4], const double (&iron)[4],
+                                           double I, double fT, double dO2, double flux_C, double flux_Fe) {
     Zoo r;
     const double J = z.specific_food_threshold_concentration;
     const double base = z.maximum_grazing_rate * fT;
     double total_food = food[0] * z.food_preferences[0];
-    double avail = jl_max(0.0, (food[0] - J)) * z.food_preferences[0];
+    double avail = A::mx(0.0, (food[0] - J)) * z.food_preferences[0];
     double total_iron = iron[0] * z.food_preferences[0];
-    double s = jl_max(0.0, (food[0] - J)) * z.food_preferences[0] * iron[0];
+    double s = A::mx(0.0, (food[0] - J)) * z.food_preferences[0] * iron[0];
 #pragma unroll
     for (int n = 1; n < N; n++) {
         total_food += food[n] * z.food_preferences[n];
-        const double a = jl_max(0.0, (food[n] - J)) * z.food_preferences[n];
+        const double a = A::mx(0.0, (food[n] - J)) * z.food_preferences[n];
         avail += a;
         total_iron += iron[n] * z.food_preferences[n];
         s += a * iron[n];
     }
-    const double clg = jl_max(0.0, avail - jl_min(avail / 2, z.food_threshold_concentration));
-    r.tsg = base * clg / (z.grazing_half_saturation + total_food);
+    const double clg = A::mx(0.0, avail - A::mn(avail / 2, z.food_threshold_concentration));
+    r.tsg = A::div(base * clg, z.grazing_half_saturation + total_food);
     r.avail = avail;
-    const double igr = total_iron / (z.iron_ratio * r.tsg + eps0());
-    r.ge = jl_min(1.0, igr) * jl_min(z.minimum_growth_efficiency, (1 - z.non_assimilated_fraction) * igr);
+    const double igr = A::gdiv(total_iron, z.iron_ratio * r.tsg);
+    r.ge = A::mn(1.0, igr) * A::mn(z.minimum_growth_efficiency, (1 - z.non_assimilated_fraction) * igr);
     r.gI = r.tsg * I;
     r.base_ff = z.maximum_flux_feeding_rate * fT;
     r.gfI = r.base_ff * flux_C * I;
-    const double cf = I / (I + z.mortality_half_saturation);
+    const double cf = A::div(I, I + z.mortality_half_saturation);
     r.mort = fT * I * (z.quadratic_mortality * I + z.linear_mortality * (cf + 3 * dO2));
     r.lin_mort = fT * z.linear_mortality * (cf + 3 * dO2) * I;
-    r.iron_graze = s * r.tsg / (avail + eps0()) * I;
+    r.iron_graze = A::gdiv(s * r.tsg, avail) * I;
     r.iron_ff = r.base_ff * flux_Fe * I;
     return r;
 }
 // grazing on one prey — food_quality_dependant.jl:226-255
+template <class A>
 __device__ __forceinline__ double graze_on(const obm_pisces_zoo& z, const Zoo& r, double pref, double prey, double I) {
-    return pref * jl_max(0.0, prey - z.specific_food_threshold_concentration) * r.tsg / (r.avail + eps0()) * I;
+    return A::gdiv(pref * A::mx(0.0, prey - z.specific_food_threshold_concentration) * r.tsg, r.avail) * I;
 }
 
-__device__ __forceinline__ void put(double* g, long long idx, double t, int accumulate) {
-    if (g == nullptr) return;
-    if (accumulate) t += g[idx];
-    g[idx] = t;
-}
-
-__global__ void __launch_bounds__(128) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
-    int i, j, k;
-    if (!thread_cell(a.d, i, j, k)) return;
-    const long long idx = cell_index(a.d, i, j, k);
-    const long long pl = plane_index(a.d, i, j);
-    const obm_pisces_params& p = a.p;
-    const int acc = a.accumulate;
-
-    // ---- one coalesced read of the cell ------------------------------------------------------------
-    const double P = a.c[T_P][idx], PChl = a.c[T_PChl][idx], PFe = a.c[T_PFe][idx];
-    const double D = a.c[T_D][idx], DChl = a.c[T_DChl][idx], DFe = a.c[T_DFe][idx], DSi = a.c[T_DSi][idx];
-    const double Z = a.c[T_Z][idx], M = a.c[T_M][idx], DOC = a.c[T_DOC][idx];
-    const double POC = a.c[T_POC][idx], GOC = a.c[T_GOC][idx], SFe = a.c[T_SFe][idx], BFe = a.c[T_BFe][idx];
-    const double PSi = a.c[T_PSi][idx], CaCO3 = a.c[T_CaCO3][idx];
+struct Inputs {
+    double P, PChl, PFe, D, DChl, DFe, DSi, Z, M, DOC, POC, GOC, SFe, BFe, PSi, CaCO3;
     Cell c;
-    c.NO3 = a.c[T_NO3][idx]; c.NH4 = a.c[T_NH4][idx]; c.PO4 = a.c[T_PO4][idx]; c.Fe = a.c[T_Fe][idx];
-    c.Si = a.c[T_Si][idx]; c.O2 = a.c[T_O2][idx]; c.T = a.c[T_T][idx];
-    c.PAR1 = a.f.PAR1[idx]; c.PAR2 = a.f.PAR2[idx]; c.PAR3 = a.f.PAR3[idx];
-    const double PARt = a.f.PAR[idx], Omega = a.f.Omega[idx];
-    // ℑzᵃᵃᶜ(i, j, k, grid, w) = (w[k] + w[k+1]) / 2 — two_size_class.jl:95-98
-    const double wPOC = (a.f.wPOC[idx] + a.f.wPOC[idx + a.d.sz]) / 2;
-    const double wGOC = (a.f.wGOC[idx] + a.f.wGOC[idx + a.d.sz]) / 2;
-    c.zmxl = a.f.mixed_layer_depth_xy[pl];
-    c.zeu = a.f.euphotic_depth_xy[pl];
-    c.kappa = a.f.mean_mixed_layer_vertical_diffusivity_xy[pl];
-    const double mlPAR = a.f.mean_mixed_layer_light_xy[pl];
-    c.z = a.d.zc[k];
+    double PARt, Omega, wPOC, wGOC, mlPAR;
+};
+
+// All 24 tendencies of one cell → out[n * PB] (shared memory).  Returns true when any result is
+// non-finite (⇒ the caller recomputes the cell with the EXACT policy).
+template <bool EXACT>
+__device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& in, double* out) {
+    using A = Ar<EXACT>;
+    const obm_pisces_params& p = a.p;
+    const Cell& c = in.c;
+    const double P = in.P, PChl = in.PChl, PFe = in.PFe, D = in.D, DChl = in.DChl, DFe = in.DFe, DSi = in.DSi;
+    const double Z = in.Z, M = in.M, DOC = in.DOC, POC = in.POC, GOC = in.GOC, SFe = in.SFe, BFe = in.BFe;
+    const double PSi = in.PSi, CaCO3 = in.CaCO3, PARt = in.PARt, Omega = in.Omega, wPOC = in.wPOC, wGOC = in.wGOC;
+    unsigned bad = 0;  // OR of the high words' exponent test
+    auto put = [&](int n, double t) {
+        out[n * PB] = t;
+        bad |= ((unsigned)(__double2hiint(t)) & 0x7ff00000u) == 0x7ff00000u;
+    };
 
     // ---- shared scalars --------------------------------------------------------------------------------
     const double shear = c.z < c.zmxl ? p.background_shear : p.mixed_layer_shear;
-    const double dO2 = jl_min(1.0, jl_max(0.0, 0.4 * (p.first_anoxia_threshold - c.O2) / (p.second_anoxia_threshold + c.O2)));
+    const double dO2 = A::mn(1.0, A::mx(0.0, A::div(0.4 * (p.first_anoxia_threshold - c.O2), p.second_anoxia_threshold + c.O2)));
     // b^T once per distinct base (exp(T ln b); bases are parameters, ln b is host-evaluated)
     double fT[6];
 #pragma unroll
@@ -228,51 +256,51 @@ __global__ void __launch_bounds__(128) pisces_tendency_kernel(const __grid_const
     }
 
     // ---- phytoplankton ------------------------------------------------------------------------------------
-    const Phyto n = phytoplankton(p, p.nano, c, P, PChl, PFe, fT[0], shear);
-    const Phyto d = phytoplankton(p, p.diatoms, c, D, DChl, DFe, fT[1], shear);
+    const Phyto n = phytoplankton<A>(p, p.nano, c, P, PChl, PFe, fT[0], shear);
+    const Phyto d = phytoplankton<A>(p, p.diatoms, c, D, DChl, DFe, fT[1], shear);
 
     // ---- zooplankton ----------------------------------------------------------------------------------------
     const double fluxPOC = POC * wPOC, fluxGOC = GOC * wGOC, fluxSFe = SFe * wPOC, fluxBFe = BFe * wGOC;
-    const double tSFe = SFe / (POC + eps0());
+    const double tSFe = A::gdiv(SFe, POC);
     const double food[4] = {P, D, POC, Z};
     const double iron[4] = {n.tFe, d.tFe, tSFe, p.micro.iron_ratio};
-    const Zoo zz = zooplankton<3>(p, p.micro, food, iron, Z, fT[2], dO2, fluxPOC + fluxGOC, fluxSFe + fluxBFe);
-    const Zoo zm = zooplankton<4>(p, p.meso, food, iron, M, fT[3], dO2, fluxPOC + fluxGOC, fluxSFe + fluxBFe);
+    const Zoo zz = zooplankton<A, 3>(p.micro, food, iron, Z, fT[2], dO2, fluxPOC + fluxGOC, fluxSFe + fluxBFe);
+    const Zoo zm = zooplankton<A, 4>(p.meso, food, iron, M, fT[3], dO2, fluxPOC + fluxGOC, fluxSFe + fluxBFe);
     // grazing(zoo::MicroAndMeso, prey) = micro + meso (micro_and_meso.jl:50-52)
-    const double gP_micro = graze_on(p.micro, zz, p.micro.food_preferences[0], P, Z);
-    const double gP_meso = graze_on(p.meso, zm, p.meso.food_preferences[0], P, M);
+    const double gP_micro = graze_on<A>(p.micro, zz, p.micro.food_preferences[0], P, Z);
+    const double gP_meso = graze_on<A>(p.meso, zm, p.meso.food_preferences[0], P, M);
     const double gP = gP_micro + gP_meso;
-    const double gD = graze_on(p.micro, zz, p.micro.food_preferences[1], D, Z) + graze_on(p.meso, zm, p.meso.food_preferences[1], D, M);
-    const double gPOC = graze_on(p.micro, zz, p.micro.food_preferences[2], POC, Z) + graze_on(p.meso, zm, p.meso.food_preferences[2], POC, M);
-    const double gZ_meso = graze_on(p.meso, zm, p.meso.food_preferences[3], Z, M);
+    const double gD = graze_on<A>(p.micro, zz, p.micro.food_preferences[1], D, Z) + graze_on<A>(p.meso, zm, p.meso.food_preferences[1], D, M);
+    const double gPOC = graze_on<A>(p.micro, zz, p.micro.food_preferences[2], POC, Z) + graze_on<A>(p.meso, zm, p.meso.food_preferences[2], POC, M);
+    const double gZ_meso = graze_on<A>(p.meso, zm, p.meso.food_preferences[3], Z, M);
 
     // ---- P, D, chlorophyll, iron, silicon quotas: mixed_mondo_nano_diatoms.jl:45-112 -----------------
     const double deathP = (n.lin + n.quad), deathD = (d.lin + d.quad);
-    put(a.g[T_P], idx, (1 - p.nano.exudated_fraction) * n.muI - deathP - gP, acc);
-    put(a.g[T_D], idx, (1 - p.diatoms.exudated_fraction) * d.muI - deathD - gD, acc);
-    put(a.g[T_PChl], idx, chlorophyll_growth(p, p.nano, c, n, P, PChl) - (deathP + gP) * n.tChl * 12, acc);
-    put(a.g[T_DChl], idx, chlorophyll_growth(p, p.diatoms, c, d, D, DChl) - (deathD + gD) * d.tChl * 12, acc);
-    const double upFe_n = iron_uptake(p.nano, c, n, P), upFe_d = iron_uptake(p.diatoms, c, d, D);
-    put(a.g[T_PFe], idx, upFe_n - (deathP + gP) * n.tFe, acc);
-    put(a.g[T_DFe], idx, upFe_d - (deathD + gD) * d.tFe, acc);
+    put(T_P, (1 - p.nano.exudated_fraction) * n.muI - deathP - gP);
+    put(T_D, (1 - p.diatoms.exudated_fraction) * d.muI - deathD - gD);
+    put(T_PChl, chlorophyll_growth<A>(p, p.nano, c, n, P, PChl) - (deathP + gP) * n.tChl * 12);
+    put(T_DChl, chlorophyll_growth<A>(p, p.diatoms, c, d, D, DChl) - (deathD + gD) * d.tChl * 12);
+    const double upFe_n = iron_uptake<A>(p.nano, c, n, P), upFe_d = iron_uptake<A>(p.diatoms, c, d, D);
+    put(T_PFe, upFe_n - (deathP + gP) * n.tFe);
+    put(T_DFe, upFe_d - (deathD + gD) * d.tFe);
     // silicate_uptake (diatoms) mixed_mondo.jl:217-248
     double upSi;
     {
         const obm_pisces_phyto& ph = p.diatoms;
         const double Si = c.Si, K2 = ph.enhanced_silicate_half_saturation;
-        const double L1 = Si / (Si + ph.silicate_half_saturation + eps0());
-        const double L2 = p.latitude < 0 ? (Si * Si * Si) / (Si * Si * Si + K2 * K2 * K2) : 0.0;
-        const double F1 = min4(d.mu / (d.mui * d.L + eps0()), d.LFe, d.LPO4, d.LN);
-        const double F2 = jl_min(1.0, 2.2 * jl_max(0.0, L1 - 0.5));
-        const double t1 = ph.optimal_silicate_ratio * L1 * jl_min(5.4, (4.4 * exp(-4.23 * F1) * F2 + 1) * (1 + 2 * L2));
+        const double L1 = A::gdiv(Si, Si + ph.silicate_half_saturation);
+        const double L2 = p.latitude < 0 ? A::div(Si * Si * Si, Si * Si * Si + K2 * K2 * K2) : 0.0;
+        const double F1 = A::mn4(A::gdiv(d.mu, d.mui * d.L), d.LFe, d.LPO4, d.LN);
+        const double F2 = A::mn(1.0, 2.2 * A::mx(0.0, L1 - 0.5));
+        const double t1 = ph.optimal_silicate_ratio * L1 * A::mn(5.4, (4.4 * exp(-4.23 * F1) * F2 + 1) * (1 + 2 * L2));
         upSi = (1 - ph.exudated_fraction) * t1 * d.mu * D;
     }
-    const double tSi = DSi / (D + eps0());
-    put(a.g[T_DSi], idx, upSi - (deathD + gD) * tSi, acc);
+    const double tSi = A::gdiv(DSi, D);
+    put(T_DSi, upSi - (deathD + gD) * tSi);
 
     // ---- Z, M: micro_and_meso.jl:36-48 -----------------------------------------------------------------------
-    put(a.g[T_Z], idx, (zz.ge * (zz.gI + zz.gfI) - zz.mort) - gZ_meso, acc);
-    put(a.g[T_M], idx, (zm.ge * (zm.gI + zm.gfI) - zm.mort) - 0.0, acc);
+    put(T_Z, (zz.ge * (zz.gI + zz.gfI) - zz.mort) - gZ_meso);
+    put(T_M, (zm.ge * (zm.gI + zm.gfI) - zm.mort) - 0.0);
 
     // ---- zooplankton wastes: grazing_waste.jl, mortality_waste.jl -------------------------------------------
     const double exc_z = (1 - p.micro.non_assimilated_fraction - zz.ge) * (zz.gI + zz.gfI);
@@ -286,71 +314,70 @@ __global__ void __launch_bounds__(128) pisces_tendency_kernel(const __grid_const
     const double ut_fecal = p.meso.non_assimilated_fraction * ut_waste;
 
     // ---- bacteria: micro_and_meso.jl:85-132 ------------------------------------------------------------------
-    const double zmin = jl_min(c.zmxl, c.zeu);
+    const double zmin = A::mn(c.zmxl, c.zeu);
     double Bact;
     {
-        const double surface = jl_min(4.0, p.microzooplankton_bacteria_concentration * Z + p.mesozooplankton_bacteria_concentration * M);
+        const double surface = A::mn(4.0, p.microzooplankton_bacteria_concentration * Z + p.mesozooplankton_bacteria_concentration * M);
         // ifelse(z >= zₘ, 1, (zₘ / z)^a): the discarded arm has no side effect, so it is only evaluated when selected
-        const double factor = c.z >= zmin ? 1.0 : pow(zmin / c.z, p.bacteria_concentration_depth_exponent);
+        const double factor = c.z >= zmin ? 1.0 : pow(A::div(zmin, c.z), p.bacteria_concentration_depth_exponent);
         Bact = factor * surface;
     }
     double LBact;
     {
         const double K_NO3 = p.nitrate_half_saturation_for_bacterial_activity, K_NH4 = p.ammonia_half_saturation_for_bacterial_activity;
-        const double DOC_limit = DOC / (DOC + p.doc_half_saturation_for_bacterial_activity);
-        const double L_N = (K_NO3 * c.NH4 + K_NH4 * c.NO3) / (K_NO3 * K_NH4 + K_NO3 * c.NH4 + K_NH4 * c.NO3);
-        const double L_PO4 = c.PO4 / (c.PO4 + p.phosphate_half_saturation_for_bacterial_activity);
-        const double L_Fe = c.Fe / (c.Fe + p.iron_half_saturation_for_bacterial_activity);
-        LBact = min3(L_N, L_PO4, L_Fe) * DOC_limit;
+        const double DOC_limit = A::div(DOC, DOC + p.doc_half_saturation_for_bacterial_activity);
+        const double L_N = A::div(K_NO3 * c.NH4 + K_NH4 * c.NO3, K_NO3 * K_NH4 + K_NO3 * c.NH4 + K_NH4 * c.NO3);
+        const double L_PO4 = A::div(c.PO4, c.PO4 + p.phosphate_half_saturation_for_bacterial_activity);
+        const double L_Fe = A::div(c.Fe, c.Fe + p.iron_half_saturation_for_bacterial_activity);
+        LBact = A::mn3(L_N, L_PO4, L_Fe) * DOC_limit;
     }
 
     // ---- dissolved organic matter: dissolved_organic_carbon.jl:39-130 ---------------------------------------
-    const double dom_deg = p.dom_remineralisation_rate * fT[4] * LBact * Bact / p.dom_reference_bacteria_concentration * DOC;
+    const double dom_deg = A::div(p.dom_remineralisation_rate * fT[4] * LBact * Bact, p.dom_reference_bacteria_concentration) * DOC;
     const double Phi1 = shear * (p.dom_aggregation_parameters[0] * DOC + p.dom_aggregation_parameters[1] * POC) * DOC;
     const double Phi2 = shear * (p.dom_aggregation_parameters[2] * GOC) * DOC;
     const double Phi3 = (p.dom_aggregation_parameters[3] * POC + p.dom_aggregation_parameters[4] * DOC) * DOC;
     const double spec_deg = p.pom_base_breakdown_rate * fT[5] * (1 - 0.45 * dO2);  // two_size_class.jl:127-137
-    put(a.g[T_DOC], idx,
-        ((p.nano.exudated_fraction * n.muI + p.diatoms.exudated_fraction * d.muI) + ut_excretion + org_exc + spec_deg * POC
-         - dom_deg - (Phi1 + Phi2 + Phi3)), acc);
+    put(T_DOC, ((p.nano.exudated_fraction * n.muI + p.diatoms.exudated_fraction * d.muI) + ut_excretion + org_exc + spec_deg * POC
+                - dom_deg - (Phi1 + Phi2 + Phi3)));
 
     // ---- iron chemistry: iron/iron.jl:25-37, particulate_organic_matter/iron.jl:97-126 ------------------------
     double Fep;
     {
-        const double ligands = jl_max(0.6, 0.09 * (DOC + 40) - 3);
-        const double K = exp(16.27 - 1565.7 / jl_max(c.T + 273.15, 5.0));
+        const double ligands = A::mx(0.6, 0.09 * (DOC + 40) - 3);
+        const double K = exp(16.27 - A::div(1565.7, A::mx(c.T + 273.15, 5.0)));
         const double Dl = 1 + K * ligands - K * c.Fe;
-        Fep = (-Dl + sqrt(Dl * Dl + 4 * K * c.Fe)) / (2 * K);
+        Fep = A::div(-Dl + sqrt(Dl * Dl + 4 * K * c.Fe), 2 * K);
     }
     const double lFe = p.minimum_iron_scavenging_rate + p.load_specific_iron_scavenging_rate * (POC + GOC + CaCO3 + PSi);
-    const double BactFe = p.maximum_bacterial_growth_rate * fT[5] * LBact * p.maximum_iron_ratio_in_bacteria * c.Fe
-                          / (c.Fe + p.iron_half_saturation_for_bacteria) * Bact * p.bacterial_iron_uptake_efficiency;
+    const double BactFe = A::div(p.maximum_bacterial_growth_rate * fT[5] * LBact * p.maximum_iron_ratio_in_bacteria * c.Fe,
+                                 c.Fe + p.iron_half_saturation_for_bacteria) * Bact * p.bacterial_iron_uptake_efficiency;
     const double colloidal = 0.5 * (c.Fe - Fep);
-    const double CgFe1 = (Phi1 + Phi3) * colloidal / (DOC + eps0());
-    const double CgFe2 = Phi2 * colloidal / (DOC + eps0());
+    const double CgFe1 = A::gdiv((Phi1 + Phi3) * colloidal, DOC);
+    const double CgFe2 = A::gdiv(Phi2 * colloidal, DOC);
 
     // ---- rain ratio & calcite: nano_diatom_coupling.jl:57-124, calcite.jl:9-19 -------------------------------
     double R;
     {
-        const double L_CaCO3 = min3(n.LN, c.Fe / (c.Fe + 0.05), n.LPO4);
-        const double pcf = jl_max(1.0, P / 2);
-        const double low_light = jl_max(0.0, PARt - 1) / (4 + PARt);
-        const double high_light = 30 / (30 + PARt);
-        const double low_T = jl_max(0.0, c.T / (c.T + 0.1));
+        const double L_CaCO3 = A::mn3(n.LN, A::div(c.Fe, c.Fe + 0.05), n.LPO4);
+        const double pcf = A::mx(1.0, P / 2);
+        const double low_light = A::div(A::mx(0.0, PARt - 1), 4 + PARt);
+        const double high_light = A::div(30.0, 30 + PARt);
+        const double low_T = A::mx(0.0, A::div(c.T, c.T + 0.1));
         const double high_T = 1 + exp(-((c.T - 10) * (c.T - 10)) / 25);
-        const double depth = jl_min(1.0, -50 / c.zmxl);
+        const double depth = A::mn(1.0, A::div(-50.0, c.zmxl));
         R = (p.base_rain_ratio * L_CaCO3 * pcf * low_light * high_light * low_T * high_T * depth);
     }
     const double calcite_loss = p.micro.undissolved_calcite_fraction * gP_micro + p.meso.undissolved_calcite_fraction * gP_meso;
     const double calcite_prod = R * (calcite_loss + (n.lin + n.quad) / 2);
     double calcite_diss;
     {
-        const double dCa = jl_max(0.0, 1 - Omega);
+        const double dCa = A::mx(0.0, 1 - Omega);
         const double e = p.calcite_dissolution_exponent;
         calcite_diss = p.base_calcite_dissolution_rate * (e == 1.0 ? dCa : pow(dCa, e)) * CaCO3;  // x^1.0 ≡ x
     }
     const double tCaCO3 = calcite_prod - calcite_diss;
-    put(a.g[T_CaCO3], idx, tCaCO3, acc);
+    put(T_CaCO3, tCaCO3);
 
     // ---- POC, GOC: particulate_organic_matter/carbon.jl:3-50 --------------------------------------------------
     const double* ap = p.pom_aggregation_parameters;
@@ -360,36 +387,32 @@ __global__ void __launch_bounds__(128) pisces_tendency_kernel(const __grid_const
     const double tg_POC = gPOC + ff_POC;                                      // micro_meso_zoo_coupling.jl:27-32
     const double sm_phyto = (1 - R / 2) * (n.lin + n.quad) + d.lin / 2;         // nano_diatom_coupling.jl:1-9
     const double lm_phyto = R / 2 * (n.lin + n.quad) + d.lin / 2 + d.quad;      // :11-19
-    put(a.g[T_POC], idx,
-        (p.micro.non_assimilated_fraction * (zz.gI + zz.gfI) + sm_phyto + zz.mort + (Phi1 + Phi3) + spec_deg * GOC
-         - tg_POC - pom_agg - spec_deg * POC), acc);
-    put(a.g[T_GOC], idx,
-        (p.meso.non_assimilated_fraction * (zm.gI + zm.gfI) + lm_phyto + zm.lin_mort + ut_fecal + pom_agg + Phi2
-         - ff_GOC - spec_deg * GOC), acc);
+    put(T_POC, (p.micro.non_assimilated_fraction * (zz.gI + zz.gfI) + sm_phyto + zz.mort + (Phi1 + Phi3) + spec_deg * GOC
+                - tg_POC - pom_agg - spec_deg * POC));
+    put(T_GOC, (p.meso.non_assimilated_fraction * (zm.gI + zm.gfI) + lm_phyto + zm.lin_mort + ut_fecal + pom_agg + Phi2
+                - ff_GOC - spec_deg * GOC));
 
     // ---- SFe, BFe: particulate_organic_matter/iron.jl:2-89 ------------------------------------------------------
     {
         const double smi = (1 - R / 2) * (n.lin + n.quad) * n.tFe + d.lin * d.tFe / 2;           // nano_diatom_coupling.jl:21-37
         const double lmi = R / 2 * (n.lin + n.quad) * n.tFe + (d.lin / 2 + d.quad) * d.tFe;       // :39-55
-        const double tB = BFe / (GOC + eps0());
-        put(a.g[T_SFe], idx,
-            (p.micro.non_assimilated_fraction * (zz.iron_graze + zz.iron_ff) + smi + zz.mort * p.micro.iron_ratio + spec_deg * BFe
-             + lFe * POC * Fep + p.small_fraction_of_bacterially_consumed_iron * BactFe + CgFe1
-             - tg_POC * tSFe - pom_agg * tSFe - spec_deg * SFe), acc);
-        put(a.g[T_BFe], idx,
-            (p.meso.non_assimilated_fraction * (zm.iron_graze + zm.iron_ff) + lmi + zm.lin_mort * p.meso.iron_ratio
-             + ut_fecal * p.meso.iron_ratio + lFe * GOC * Fep + p.large_fraction_of_bacterially_consumed_iron * BactFe + CgFe2
-             + pom_agg * tSFe - ff_GOC * tB - spec_deg * BFe), acc);
+        const double tB = A::gdiv(BFe, GOC);
+        put(T_SFe, (p.micro.non_assimilated_fraction * (zz.iron_graze + zz.iron_ff) + smi + zz.mort * p.micro.iron_ratio + spec_deg * BFe
+                    + lFe * POC * Fep + p.small_fraction_of_bacterially_consumed_iron * BactFe + CgFe1
+                    - tg_POC * tSFe - pom_agg * tSFe - spec_deg * SFe));
+        put(T_BFe, (p.meso.non_assimilated_fraction * (zm.iron_graze + zm.iron_ff) + lmi + zm.lin_mort * p.meso.iron_ratio
+                    + ut_fecal * p.meso.iron_ratio + lFe * GOC * Fep + p.large_fraction_of_bacterially_consumed_iron * BactFe + CgFe2
+                    + pom_agg * tSFe - ff_GOC * tB - spec_deg * BFe));
     }
 
     // ---- PSi, Si: particulate_organic_matter/silicate.jl:1-48, silicate.jl:20-26 -------------------------------
     double psi_diss;
     {
         const double ll = p.fast_dissolution_rate_of_silicate, lr = p.slow_dissolution_rate_of_silicate;
-        const double chi = p.base_liable_silicate_fraction * (c.z >= zmin ? 1.0 : exp((ll - lr) * (zmin - c.z) / wGOC));
+        const double chi = p.base_liable_silicate_fraction * (c.z >= zmin ? 1.0 : exp(A::div((ll - lr) * (zmin - c.z), wGOC)));
         const double l0 = chi * ll + (1 - chi) * lr;
-        const double eq = exp10(6.44 - 968 / (c.T + 273.15));
-        const double sat = (eq - c.Si) / eq;
+        const double eq = exp10(6.44 - A::div(968.0, c.T + 273.15));
+        const double sat = A::div(eq - c.Si, eq);
         const double q = 1 + c.T / 400;
         const double q2 = q * q;
         const double b = (q2 * q2) * sat;  // ((1 + T/400)^4 * saturation)
@@ -397,51 +420,101 @@ __global__ void __launch_bounds__(128) pisces_tendency_kernel(const __grid_const
         const double l = l0 * (0.225 * (1 + c.T / 15) * sat + 0.775 * (b4 * b4 * b));  // (…)^9
         psi_diss = l * PSi;
     }
-    put(a.g[T_PSi], idx, (gD + d.lin + d.quad) * tSi - psi_diss, acc);
-    put(a.g[T_Si], idx, psi_diss - upSi, acc);
+    put(T_PSi, (gD + d.lin + d.quad) * tSi - psi_diss);
+    put(T_Si, psi_diss - upSi);
 
     // ---- nitrogen: nitrogen/nitrate_ammonia.jl:22-89 ------------------------------------------------------------
-    const double nitrif = p.maximum_nitrification_rate * c.NH4 / (1 + mlPAR) * (1 - dO2);
+    const double nitrif = A::div(p.maximum_nitrification_rate * c.NH4, 1 + in.mlPAR) * (1 - dO2);
     double fixation;
     {
         const double limit = n.LN >= 0.8 ? 0.01 : 1 - n.LN;
-        const double growth_requirement = jl_max(0.0, n.mui - 2.15);
-        const double nutrient = jl_min(c.Fe / (c.Fe + p.iron_half_saturation_for_fixation),
-                                       c.PO4 / (c.PO4 + p.phosphate_half_saturation_for_fixation));
+        const double growth_requirement = A::mx(0.0, n.mui - 2.15);
+        const double nutrient = A::mn(A::div(c.Fe, c.Fe + p.iron_half_saturation_for_fixation),
+                                      A::div(c.PO4, c.PO4 + p.phosphate_half_saturation_for_fixation));
         const double light = 1 - exp(-PARt / p.light_saturation_for_fixation);
         fixation = p.maximum_fixation_rate * growth_requirement * limit * nutrient * light;
     }
-    const double upNO3 = n.muI * n.LNO3 / (n.LN + eps0()) + d.muI * d.LNO3 / (d.LN + eps0());
-    const double upNH4 = n.muI * n.LNH4 / (n.LN + eps0()) + d.muI * d.LNH4 / (d.LN + eps0());
+    const double upNO3 = A::gdiv(n.muI * n.LNO3, n.LN) + A::gdiv(d.muI * d.LNO3, d.LN);
+    const double upNH4 = A::gdiv(n.muI * n.LNH4, n.LN) + A::gdiv(d.muI * d.LNH4, d.LN);
     const double oxic = (1 - dO2) * dom_deg, anoxic = dO2 * dom_deg;
     const double tN = p.nitrogen_redfield_ratio;
     const double tNO3 = nitrif + tN * (oxic - upNO3);
     const double tNH4 = fixation + tN * (anoxic + inorg_exc + ut_respiration - upNH4) - nitrif;
-    put(a.g[T_NO3], idx, tNO3, acc);
-    put(a.g[T_NH4], idx, tNH4, acc);
+    put(T_NO3, tNO3);
+    put(T_NH4, tNH4);
 
     // ---- PO₄, Fe, DIC, Alk, O₂ ---------------------------------------------------------------------------------------
     const double prod = n.muI + d.muI;
-    put(a.g[T_PO4], idx, p.phosphate_redfield_ratio * (inorg_exc + ut_respiration + dom_deg - prod), acc);  // phosphate.jl:21-33
+    put(T_PO4, p.phosphate_redfield_ratio * (inorg_exc + ut_respiration + dom_deg - prod));  // phosphate.jl:21-33
     {   // iron/simple_iron.jl:19-62
         const double Lt = p.dissolved_ligand_ratio * DOC - p.maximum_ligand_concentration;
-        const double ligand_agg = p.excess_scavenging_enhancement * lFe * jl_max(0.0, c.Fe - jl_max(p.maximum_ligand_concentration, Lt)) * Fep;
+        const double ligand_agg = p.excess_scavenging_enhancement * lFe * A::mx(0.0, c.Fe - A::mx(p.maximum_ligand_concentration, Lt)) * Fep;
         // non_assimilated_iron grazing_waste.jl:45-63, per class
         const double fz = zz.iron_graze + zz.iron_ff, fm = zm.iron_graze + zm.iron_ff;
         const double nai = (fz - p.micro.non_assimilated_fraction * fz - p.micro.iron_ratio * zz.ge * (zz.gI + zz.gfI))
                            + (fm - p.meso.non_assimilated_fraction * fm - p.meso.iron_ratio * zm.ge * (zm.gI + zm.gfI));
-        put(a.g[T_Fe], idx,
-            (spec_deg * SFe + nai + p.meso.iron_ratio * ut_R - (upFe_n + upFe_d) - ligand_agg - (CgFe1 + CgFe2)
-             - lFe * (POC + GOC) * Fep - BactFe), acc);
+        put(T_Fe, (spec_deg * SFe + nai + p.meso.iron_ratio * ut_R - (upFe_n + upFe_d) - ligand_agg - (CgFe1 + CgFe2)
+                   - lFe * (POC + GOC) * Fep - BactFe));
     }
-    put(a.g[T_DIC], idx, (inorg_exc + ut_respiration + dom_deg + calcite_diss - calcite_prod - prod), acc);  // inorganic_carbon.jl:32-47
-    put(a.g[T_Alk], idx, tNH4 - tNO3 - 2 * tCaCO3, acc);                                                   // :49-58
+    put(T_DIC, (inorg_exc + ut_respiration + dom_deg + calcite_diss - calcite_prod - prod));  // inorganic_carbon.jl:32-47
+    put(T_Alk, tNH4 - tNO3 - 2 * tCaCO3);                                                   // :49-58
     {   // oxygen.jl:30-51
         const double tr = p.ratio_for_respiration, tn = p.ratio_for_nitrification;
         const double remin = ((tr + tn) * oxic + tr * anoxic);
-        put(a.g[T_O2], idx,
-            (tr * upNH4 + (tr + tn) * upNO3 + tn * fixation / tN - remin - tr * inorg_exc - tr * ut_respiration
-             - tn * nitrif / tN), acc);
+        put(T_O2, (tr * upNH4 + (tr + tn) * upNO3 + tn * fixation / tN - remin - tr * inorg_exc - tr * ut_respiration
+                   - tn * nitrif / tN));
+    }
+    // NaN inputs that only flow through min/max would be swallowed by fmin/fmax: force the EXACT path
+    bad |= (c.zeu != c.zeu) | (c.O2 != c.O2) | (Omega != Omega) | (c.zmxl != c.zmxl) | (c.kappa != c.kappa);
+    return bad != 0;
+}
+
+#ifndef OBM_PISCES_MIN_BLOCKS
+#define OBM_PISCES_MIN_BLOCKS 4
+#endif
+
+__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
+    __shared__ double sm[NOUT * PB];
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    const long long pl = plane_index(a.d, i, j);
+
+    // ---- one coalesced read of the cell ------------------------------------------------------------
+    Inputs in;
+    in.P = a.c[T_P][idx]; in.PChl = a.c[T_PChl][idx]; in.PFe = a.c[T_PFe][idx];
+    in.D = a.c[T_D][idx]; in.DChl = a.c[T_DChl][idx]; in.DFe = a.c[T_DFe][idx]; in.DSi = a.c[T_DSi][idx];
+    in.Z = a.c[T_Z][idx]; in.M = a.c[T_M][idx]; in.DOC = a.c[T_DOC][idx];
+    in.POC = a.c[T_POC][idx]; in.GOC = a.c[T_GOC][idx]; in.SFe = a.c[T_SFe][idx]; in.BFe = a.c[T_BFe][idx];
+    in.PSi = a.c[T_PSi][idx]; in.CaCO3 = a.c[T_CaCO3][idx];
+    in.c.NO3 = a.c[T_NO3][idx]; in.c.NH4 = a.c[T_NH4][idx]; in.c.PO4 = a.c[T_PO4][idx]; in.c.Fe = a.c[T_Fe][idx];
+    in.c.Si = a.c[T_Si][idx]; in.c.O2 = a.c[T_O2][idx]; in.c.T = a.c[T_T][idx];
+    in.c.PAR1 = a.f.PAR1[idx]; in.c.PAR2 = a.f.PAR2[idx]; in.c.PAR3 = a.f.PAR3[idx];
+    in.PARt = a.f.PAR[idx]; in.Omega = a.f.Omega[idx];
+    // ℑzᵃᵃᶜ(i, j, k, grid, w) = (w[k] + w[k+1]) / 2 — two_size_class.jl:95-98
+    in.wPOC = (a.f.wPOC[idx] + a.f.wPOC[idx + a.d.sz]) / 2;
+    in.wGOC = (a.f.wGOC[idx] + a.f.wGOC[idx + a.d.sz]) / 2;
+    in.c.zmxl = a.f.mixed_layer_depth_xy[pl];
+    in.c.zeu = a.f.euphotic_depth_xy[pl];
+    in.c.kappa = a.f.mean_mixed_layer_vertical_diffusivity_xy[pl];
+    in.mlPAR = a.f.mean_mixed_layer_light_xy[pl];
+    in.c.z = a.d.zc[k];
+
+    double* out = sm + threadIdx.x;
+    if (cell_tendencies<false>(a, in, out)) cell_tendencies<true>(a, in, out);  // rare: non-finite results
+
+    // ---- write-out: all loads of the accumulate RMW are issued together ------------------------------
+    if (a.accumulate) {
+        double old[NOUT];
+#pragma unroll
+        for (int n = 0; n < NOUT; n++) old[n] = a.g[n] ? a.g[n][idx] : 0.0;
+#pragma unroll
+        for (int n = 0; n < NOUT; n++)
+            if (a.g[n]) a.g[n][idx] = old[n] + out[n * PB];
+    } else {
+#pragma unroll
+        for (int n = 0; n < NOUT; n++)
+            if (a.g[n]) a.g[n][idx] = out[n * PB];
     }
 }
 
@@ -482,7 +555,6 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
             if (bases[q] == bases[u]) { A.same_as[u] = q; break; }
     }
     A.accumulate = accumulate ? 1 : 0;
-    const long long cells = cell_count(A.d);
-    pisces_tendency_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, (cudaStream_t)stream>>>(A);
+    pisces_tendency_kernel<<<cell_grid(A.d, PB), PB, 0, (cudaStream_t)stream>>>(A);
     return launch_status("pisces_tendency_kernel");
 }
