@@ -33,6 +33,22 @@ struct PiscesArgs {
     double ln_base[6];
     int same_as[6];  // index of an earlier user with an identical base, or -1
     int accumulate;
+    unsigned out_mask;  // bit n set ⇔ g[n] != NULL
+    // parameter-only sub-expressions, evaluated once on the host in double precision
+    // (the reference re-evaluates them per cell per tracer; results agree to ≤ 1 ulp)
+    struct Derived {
+        double f1_growth;         // 1.5 dl / (dl + 0.5day), dl = day_length_growth       growth_rate.jl:38
+        double dl_over_f1_chl;    // day_length_chlorophyll / f1(day_length_chlorophyll)  growth_rate.jl:145,151
+        double inv_resp[2];       // 1 / (dl (bᵣ + μᵣ))                                   growth_rate.jl:123
+        double KSi_add[2];        // 7 Si′² / (pk² + Si′²)                                nutrient_limitation.jl:65
+        double inv_theta_o[2];    // 1 / optimal_iron_quota
+        double inv_theta_Fem[2];  // 1 / maximum_iron_ratio
+        double inv_bact_ref;      // 1 / reference_bacteria_concentration
+        double ut_coeff;          // 1 / (1 − e₀) · m₀ (meso)                             mortality_waste.jl:40
+        double inv_E;             // 1 / light_saturation_for_fixation
+        double inv_tN;            // 1 / nitrogen_redfield_ratio
+        double K2_cubed;          // enhanced_silicate_half_saturation³
+    } dv;
 };
 
 constexpr double DAY = 86400.0;
@@ -41,9 +57,9 @@ constexpr int NOUT = 24;  // tendencies staged in shared memory
 
 // ---- arithmetic policy -------------------------------------------------------------------------------
 // EXACT: IEEE division, NaN-propagating min/max — the reference's semantics operation by operation.
-// FAST (default path): a lean branch-free division (MUFU.RCP64H seed + 2 Newton steps + one residual
-// correction: ≤ 1 ulp, 8 FP64 instructions instead of the ≈ 30-instruction IEEE sequence with its
-// slow-path call scaffolding), `x / (y + eps(0.0))` with the reference's exact y == 0 behaviour
+// FAST (default path): a lean branch-free division (MUFU.RCP64H seed + 2 Newton steps, ≤ 1.5 ulp:
+// 5 FP64 instructions instead of the ≈ 30-instruction IEEE sequence with its slow-path call
+// scaffolding), `x / (y + eps(0.0))` with the reference's exact y == 0 behaviour
 // (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and plain
 // fmin/fmax.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
 // by fmin/fmax) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
@@ -56,11 +72,10 @@ __device__ __forceinline__ double rcp_fast(double b) {
 }
 template <bool EXACT>
 struct Ar {
+    static constexpr bool EX = EXACT;
     static __device__ __forceinline__ double div(double a, double b) {
         if (EXACT) return a / b;
-        const double r = rcp_fast(b);
-        const double q = a * r;
-        return fma(fma(-b, q, a), r, q);
+        return a * rcp_fast(b);  // ≤ 1.5 ulp
     }
     // a / (y + eps(0.0))
     static __device__ __forceinline__ double gdiv(double a, double y) {
@@ -89,8 +104,9 @@ struct Phyto {  // everything the rest of the model needs from one phytoplankton
 
 // nutrient_limitation.jl:20-73 + growth_rate.jl:3-47 + mixed_mondo.jl:137-175, evaluated ONCE per class
 template <class A>
-__device__ __forceinline__ Phyto phytoplankton(const obm_pisces_params& p, const obm_pisces_phyto& ph, const Cell& c,
+__device__ __forceinline__ Phyto phytoplankton(const PiscesArgs& a, const int cls, const Cell& c,
                                                double I, double IChl, double IFe, double fT, double shear) {
+    const obm_pisces_phyto& ph = cls == 0 ? a.p.nano : a.p.diatoms;
     Phyto r;
     // quotas
     r.tFe = A::gdiv(IFe, I);
@@ -110,20 +126,19 @@ __device__ __forceinline__ Phyto phytoplankton(const obm_pisces_params& p, const
     r.LPO4 = A::gdiv(c.PO4, c.PO4 + Kp);
     const double tm = 1000 * (0.0016 / 55.85 * 12 * tChl_l + 1.5 * 1.21e-5 * 14 / (55.85 * 7.625) * r.LN
                               + 1.15e-4 * 14 / (55.85 * 7.625) * r.LNO3);
-    r.LFe = A::mn(1.0, A::mx(0.0, A::div(tFe_l - tm, ph.optimal_iron_quota)));
-    const double Sip = p.silicate_climatology, pk = ph.silicate_half_saturation_parameter;
-    const double KSi = Ksi + 7 * (Sip * Sip) / (pk * pk + Sip * Sip);  // parameters only: hoisted by the compiler
+    r.LFe = A::mn(1.0, A::mx(0.0, A::EX ? (tFe_l - tm) / ph.optimal_iron_quota : (tFe_l - tm) * a.dv.inv_theta_o[cls]));
+    const double KSi = Ksi + a.dv.KSi_add[cls];
     double LSi = A::div(c.Si, c.Si + KSi);
     LSi = ph.silicate_limited ? LSi : __longlong_as_double(0x7ff0000000000000LL);
     r.L = A::mn4(r.LN, r.LPO4, r.LFe, LSi);
 
     // growth rate (μ::BaseProduction)(…, L) with the SWAPPED day length — growth_rate.jl:3-47
     const double PAR = ph.blue_light_absorption * c.PAR1 + ph.green_light_absorption * c.PAR2 + ph.red_light_absorption * c.PAR3;
-    const double dl = p.day_length_growth;
+    const double dl = a.p.day_length_growth;
     const double dd = A::mx(0.0, c.zeu - c.zmxl);
     const double drt = A::div(dd * dd, c.kappa);
     r.mui = ph.base_growth_rate * fT;
-    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);  // parameters only
+    const double f1 = a.dv.f1_growth;
     const double f2 = 1 - A::div(drt, drt + ph.dark_tolerance);
     double alpha = ph.initial_slope_of_PI_curve;
     if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
@@ -132,7 +147,8 @@ __device__ __forceinline__ Phyto phytoplankton(const obm_pisces_params& p, const
     if (ph.growth_rate_kind == OBM_GROWTH_NUTRIENT_LIMITED)
         fl = 1 - exp(A::gdiv(-alpha * r.tChl * PAR, dl * r.mui * r.L));
     else
-        fl = 1 - exp(A::div(-alpha * r.tChl * PAR, dl * (ph.basal_respiration_rate + ph.reference_growth_rate)));
+        fl = 1 - exp(A::EX ? -alpha * r.tChl * PAR / (dl * (ph.basal_respiration_rate + ph.reference_growth_rate))
+                           : -alpha * r.tChl * PAR * a.dv.inv_resp[cls]);
     r.mu = r.mui * f1 * f2 * fl * r.L;
     r.muI = r.mu * I;
 
@@ -147,12 +163,12 @@ __device__ __forceinline__ Phyto phytoplankton(const obm_pisces_params& p, const
 // chlorophyll synthesis: production_and_energy_assimilation_absorption_ratio (growth_rate.jl:126-156)
 // + chlorophyll_growth (mixed_mondo.jl:112-124); CORRECT day-length order here
 template <class A>
-__device__ __forceinline__ double chlorophyll_growth(const obm_pisces_params& p, const obm_pisces_phyto& ph, const Cell& c,
+__device__ __forceinline__ double chlorophyll_growth(const PiscesArgs& a, const int cls, const Cell& c,
                                                      const Phyto& r, double I, double IChl) {
+    const obm_pisces_phyto& ph = cls == 0 ? a.p.nano : a.p.diatoms;
     const double PAR = ph.blue_light_absorption * c.PAR1 + ph.green_light_absorption * c.PAR2 + ph.red_light_absorption * c.PAR3;
-    const double dl = p.day_length_chlorophyll;
-    const double f1 = 1.5 * dl / (dl + 0.5 * DAY);  // parameters only
-    const double mucheck = A::div(r.mu, f1) * dl;
+    const double dl = a.p.day_length_chlorophyll;
+    const double mucheck = A::EX ? r.mu / (1.5 * dl / (dl + 0.5 * DAY)) * dl : r.mu * a.dv.dl_over_f1_chl;
     double alpha = ph.initial_slope_of_PI_curve;
     if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
     else alpha = alpha * (1 + 0.0);
@@ -163,13 +179,14 @@ __device__ __forceinline__ double chlorophyll_growth(const obm_pisces_params& p,
 
 // iron_uptake mixed_mondo.jl:177-205
 template <class A>
-__device__ __forceinline__ double iron_uptake(const obm_pisces_phyto& ph, const Cell& c, const Phyto& r, double I) {
+__device__ __forceinline__ double iron_uptake(const PiscesArgs& a, const int cls, const Cell& c, const Phyto& r, double I) {
+    const obm_pisces_phyto& ph = cls == 0 ? a.p.nano : a.p.diatoms;
     const double I1 = A::mn(I, ph.threshold_for_size_dependency);
     const double I2 = A::mx(0.0, I - ph.threshold_for_size_dependency);
     const double K = ph.half_saturation_for_iron_uptake * A::gdiv(I1 + ph.size_ratio * I2, I1 + I2);
     const double L1 = A::gdiv(c.Fe, c.Fe + K);
     const double L2 = 4 - A::div(4.5 * r.LFe, r.LFe + 1);
-    const double q = A::div(r.tFe, ph.maximum_iron_ratio);
+    const double q = A::EX ? r.tFe / ph.maximum_iron_ratio : r.tFe * a.dv.inv_theta_Fem[cls];
     return (1 - ph.exudated_fraction) * ph.maximum_iron_ratio * L1 * L2 * A::mx(0.0, A::div(1 - q, 1.05 - q)) * r.mui * I;
 }
 
@@ -227,7 +244,7 @@ struct Inputs {
 // All 24 tendencies of one cell → out[n * PB] (shared memory).  Returns true when any result is
 // non-finite (⇒ the caller recomputes the cell with the EXACT policy).
 template <bool EXACT>
-__device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& in, double* out) {
+__device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& in, double* out) {
     using A = Ar<EXACT>;
     const obm_pisces_params& p = a.p;
     const Cell& c = in.c;
@@ -256,8 +273,8 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
     }
 
     // ---- phytoplankton ------------------------------------------------------------------------------------
-    const Phyto n = phytoplankton<A>(p, p.nano, c, P, PChl, PFe, fT[0], shear);
-    const Phyto d = phytoplankton<A>(p, p.diatoms, c, D, DChl, DFe, fT[1], shear);
+    const Phyto n = phytoplankton<A>(a, 0, c, P, PChl, PFe, fT[0], shear);
+    const Phyto d = phytoplankton<A>(a, 1, c, D, DChl, DFe, fT[1], shear);
 
     // ---- zooplankton ----------------------------------------------------------------------------------------
     const double fluxPOC = POC * wPOC, fluxGOC = GOC * wGOC, fluxSFe = SFe * wPOC, fluxBFe = BFe * wGOC;
@@ -278,9 +295,9 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
     const double deathP = (n.lin + n.quad), deathD = (d.lin + d.quad);
     put(T_P, (1 - p.nano.exudated_fraction) * n.muI - deathP - gP);
     put(T_D, (1 - p.diatoms.exudated_fraction) * d.muI - deathD - gD);
-    put(T_PChl, chlorophyll_growth<A>(p, p.nano, c, n, P, PChl) - (deathP + gP) * n.tChl * 12);
-    put(T_DChl, chlorophyll_growth<A>(p, p.diatoms, c, d, D, DChl) - (deathD + gD) * d.tChl * 12);
-    const double upFe_n = iron_uptake<A>(p.nano, c, n, P), upFe_d = iron_uptake<A>(p.diatoms, c, d, D);
+    put(T_PChl, chlorophyll_growth<A>(a, 0, c, n, P, PChl) - (deathP + gP) * n.tChl * 12);
+    put(T_DChl, chlorophyll_growth<A>(a, 1, c, d, D, DChl) - (deathD + gD) * d.tChl * 12);
+    const double upFe_n = iron_uptake<A>(a, 0, c, n, P), upFe_d = iron_uptake<A>(a, 1, c, d, D);
     put(T_PFe, upFe_n - (deathP + gP) * n.tFe);
     put(T_DFe, upFe_d - (deathD + gD) * d.tFe);
     // silicate_uptake (diatoms) mixed_mondo.jl:217-248
@@ -289,7 +306,7 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
         const obm_pisces_phyto& ph = p.diatoms;
         const double Si = c.Si, K2 = ph.enhanced_silicate_half_saturation;
         const double L1 = A::gdiv(Si, Si + ph.silicate_half_saturation);
-        const double L2 = p.latitude < 0 ? A::div(Si * Si * Si, Si * Si * Si + K2 * K2 * K2) : 0.0;
+        const double L2 = p.latitude < 0 ? A::div(Si * Si * Si, Si * Si * Si + (A::EX ? K2 * K2 * K2 : a.dv.K2_cubed)) : 0.0;
         const double F1 = A::mn4(A::gdiv(d.mu, d.mui * d.L), d.LFe, d.LPO4, d.LN);
         const double F2 = A::mn(1.0, 2.2 * A::mx(0.0, L1 - 0.5));
         const double t1 = ph.optimal_silicate_ratio * L1 * A::mn(5.4, (4.4 * exp(-4.23 * F1) * F2 + 1) * (1 + 2 * L2));
@@ -307,7 +324,7 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
     const double exc_m = (1 - p.meso.non_assimilated_fraction - zm.ge) * (zm.gI + zm.gfI);
     const double inorg_exc = p.micro.dissolved_excretion_fraction * exc_z + p.meso.dissolved_excretion_fraction * exc_m;
     const double org_exc = (1 - p.micro.dissolved_excretion_fraction) * exc_z + (1 - p.meso.dissolved_excretion_fraction) * exc_m;
-    const double ut_waste = 1 / (1 - p.meso.minimum_growth_efficiency) * p.meso.quadratic_mortality * fT[3] * (M * M);
+    const double ut_waste = (A::EX ? 1 / (1 - p.meso.minimum_growth_efficiency) * p.meso.quadratic_mortality : a.dv.ut_coeff) * fT[3] * (M * M);
     const double ut_R = (1 - p.meso.minimum_growth_efficiency - p.meso.non_assimilated_fraction) * ut_waste;
     const double ut_excretion = (1 - p.meso.dissolved_excretion_fraction) * ut_R;
     const double ut_respiration = p.meso.dissolved_excretion_fraction * ut_R;
@@ -333,7 +350,8 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
     }
 
     // ---- dissolved organic matter: dissolved_organic_carbon.jl:39-130 ---------------------------------------
-    const double dom_deg = A::div(p.dom_remineralisation_rate * fT[4] * LBact * Bact, p.dom_reference_bacteria_concentration) * DOC;
+    const double dom_deg = (A::EX ? p.dom_remineralisation_rate * fT[4] * LBact * Bact / p.dom_reference_bacteria_concentration
+                                  : p.dom_remineralisation_rate * fT[4] * LBact * Bact * a.dv.inv_bact_ref) * DOC;
     const double Phi1 = shear * (p.dom_aggregation_parameters[0] * DOC + p.dom_aggregation_parameters[1] * POC) * DOC;
     const double Phi2 = shear * (p.dom_aggregation_parameters[2] * GOC) * DOC;
     const double Phi3 = (p.dom_aggregation_parameters[3] * POC + p.dom_aggregation_parameters[4] * DOC) * DOC;
@@ -364,7 +382,7 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
         const double low_light = A::div(A::mx(0.0, PARt - 1), 4 + PARt);
         const double high_light = A::div(30.0, 30 + PARt);
         const double low_T = A::mx(0.0, A::div(c.T, c.T + 0.1));
-        const double high_T = 1 + exp(-((c.T - 10) * (c.T - 10)) / 25);
+        const double high_T = 1 + exp(A::EX ? -((c.T - 10) * (c.T - 10)) / 25 : -((c.T - 10) * (c.T - 10)) * 0.04);
         const double depth = A::mn(1.0, A::div(-50.0, c.zmxl));
         R = (p.base_rain_ratio * L_CaCO3 * pcf * low_light * high_light * low_T * high_T * depth);
     }
@@ -431,7 +449,7 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
         const double growth_requirement = A::mx(0.0, n.mui - 2.15);
         const double nutrient = A::mn(A::div(c.Fe, c.Fe + p.iron_half_saturation_for_fixation),
                                       A::div(c.PO4, c.PO4 + p.phosphate_half_saturation_for_fixation));
-        const double light = 1 - exp(-PARt / p.light_saturation_for_fixation);
+        const double light = 1 - exp(A::EX ? -PARt / p.light_saturation_for_fixation : -PARt * a.dv.inv_E);
         fixation = p.maximum_fixation_rate * growth_requirement * limit * nutrient * light;
     }
     const double upNO3 = A::gdiv(n.muI * n.LNO3, n.LN) + A::gdiv(d.muI * d.LNO3, d.LN);
@@ -461,8 +479,9 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
     {   // oxygen.jl:30-51
         const double tr = p.ratio_for_respiration, tn = p.ratio_for_nitrification;
         const double remin = ((tr + tn) * oxic + tr * anoxic);
-        put(T_O2, (tr * upNH4 + (tr + tn) * upNO3 + tn * fixation / tN - remin - tr * inorg_exc - tr * ut_respiration
-                   - tn * nitrif / tN));
+        const double fix_c = A::EX ? tn * fixation / tN : tn * fixation * a.dv.inv_tN;
+        const double nit_c = A::EX ? tn * nitrif / tN : tn * nitrif * a.dv.inv_tN;
+        put(T_O2, (tr * upNH4 + (tr + tn) * upNO3 + fix_c - remin - tr * inorg_exc - tr * ut_respiration - nit_c));
     }
     // NaN inputs that only flow through min/max would be swallowed by fmin/fmax: force the EXACT path
     bad |= (c.zeu != c.zeu) | (c.O2 != c.O2) | (Omega != Omega) | (c.zmxl != c.zmxl) | (c.kappa != c.kappa);
@@ -473,14 +492,7 @@ __device__ __noinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& 
 #define OBM_PISCES_MIN_BLOCKS 4
 #endif
 
-__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
-    __shared__ double sm[NOUT * PB];
-    int i, j, k;
-    if (!thread_cell(a.d, i, j, k)) return;
-    const long long idx = cell_index(a.d, i, j, k);
-    const long long pl = plane_index(a.d, i, j);
-
-    // ---- one coalesced read of the cell ------------------------------------------------------------
+__device__ __forceinline__ Inputs load_inputs(const PiscesArgs& a, long long idx, long long pl, int k) {
     Inputs in;
     in.P = a.c[T_P][idx]; in.PChl = a.c[T_PChl][idx]; in.PFe = a.c[T_PFe][idx];
     in.D = a.c[T_D][idx]; in.DChl = a.c[T_DChl][idx]; in.DFe = a.c[T_DFe][idx]; in.DSi = a.c[T_DSi][idx];
@@ -499,22 +511,42 @@ __global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_ker
     in.c.kappa = a.f.mean_mixed_layer_vertical_diffusivity_xy[pl];
     in.mlPAR = a.f.mean_mixed_layer_light_xy[pl];
     in.c.z = a.d.zc[k];
+    return in;
+}
+
+// The rare path (non-finite results): re-reads the cell and evaluates it with the reference's exact
+// operation semantics.  Kept out of line so that it does not weigh on the fast path's registers.
+__device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long long pl, int k, double* out) {
+    const Inputs in = load_inputs(a, idx, pl, k);
+    cell_tendencies<true>(a, in, out);
+}
+
+__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
+    __shared__ double sm[NOUT * PB];
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    const long long pl = plane_index(a.d, i, j);
+
+    // ---- one coalesced read of the cell ------------------------------------------------------------
+    const Inputs in = load_inputs(a, idx, pl, k);
 
     double* out = sm + threadIdx.x;
-    if (cell_tendencies<false>(a, in, out)) cell_tendencies<true>(a, in, out);  // rare: non-finite results
+    if (cell_tendencies<false>(a, in, out)) cell_exact(a, idx, pl, k, out);  // rare: non-finite results
 
     // ---- write-out: all loads of the accumulate RMW are issued together ------------------------------
+    const unsigned mask = a.out_mask;
     if (a.accumulate) {
         double old[NOUT];
 #pragma unroll
-        for (int n = 0; n < NOUT; n++) old[n] = a.g[n] ? a.g[n][idx] : 0.0;
+        for (int n = 0; n < NOUT; n++) old[n] = (mask >> n) & 1u ? a.g[n][idx] : 0.0;
 #pragma unroll
         for (int n = 0; n < NOUT; n++)
-            if (a.g[n]) a.g[n][idx] = old[n] + out[n * PB];
+            if ((mask >> n) & 1u) a.g[n][idx] = old[n] + out[n * PB];
     } else {
 #pragma unroll
         for (int n = 0; n < NOUT; n++)
-            if (a.g[n]) a.g[n][idx] = out[n * PB];
+            if ((mask >> n) & 1u) a.g[n][idx] = out[n * PB];
     }
 }
 
@@ -555,6 +587,30 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
             if (bases[q] == bases[u]) { A.same_as[u] = q; break; }
     }
     A.accumulate = accumulate ? 1 : 0;
+    A.out_mask = 0;
+    for (int n = 0; n < NOUT; n++)
+        if (A.g[n]) A.out_mask |= 1u << n;
+    {
+        PiscesArgs::Derived& dv = A.dv;
+        const double dlg = p->day_length_growth, dlc = p->day_length_chlorophyll;
+        dv.f1_growth = 1.5 * dlg / (dlg + 0.5 * DAY);
+        dv.dl_over_f1_chl = dlc / (1.5 * dlc / (dlc + 0.5 * DAY));
+        const obm_pisces_phyto* cls[2] = {&p->nano, &p->diatoms};
+        const double Sip = p->silicate_climatology;
+        for (int q = 0; q < 2; q++) {
+            dv.inv_resp[q] = 1.0 / (dlg * (cls[q]->basal_respiration_rate + cls[q]->reference_growth_rate));
+            const double pk = cls[q]->silicate_half_saturation_parameter;
+            dv.KSi_add[q] = 7 * (Sip * Sip) / (pk * pk + Sip * Sip);
+            dv.inv_theta_o[q] = 1.0 / cls[q]->optimal_iron_quota;
+            dv.inv_theta_Fem[q] = 1.0 / cls[q]->maximum_iron_ratio;
+        }
+        dv.inv_bact_ref = 1.0 / p->dom_reference_bacteria_concentration;
+        dv.ut_coeff = 1 / (1 - p->meso.minimum_growth_efficiency) * p->meso.quadratic_mortality;
+        dv.inv_E = 1.0 / p->light_saturation_for_fixation;
+        dv.inv_tN = 1.0 / p->nitrogen_redfield_ratio;
+        const double K2 = p->diatoms.enhanced_silicate_half_saturation;
+        dv.K2_cubed = K2 * K2 * K2;
+    }
     pisces_tendency_kernel<<<cell_grid(A.d, PB), PB, 0, (cudaStream_t)stream>>>(A);
     return launch_status("pisces_tendency_kernel");
 }
