@@ -25,9 +25,9 @@ namespace cc {
 
 // ---- TEOS-10 55-term polynomial (Roquet et al. 2015) as used through SeawaterPolynomials 0.3 ----
 __device__ __forceinline__ double teos10_rho(double T, double Sp, double Pbar) {
-    const double t = T / 40.0;
-    const double s = sqrt((Sp + 32.0) / (40.0 * 35.16504 / 35.0));
-    const double z = -(10.0 * Pbar) / 1e4;
+    const double t = T * 0.025;
+    const double s = sqrt((Sp + 32.0) * (1.0 / (40.0 * 35.16504 / 35.0)));
+    const double z = -(10.0 * Pbar) * 1e-4;
     const double r0 = (((((-1.7243708991e-03 * z + 1.5616995503e-02) * z + 6.4326772569e-02) * z + 2.2601900708e-01) * z
                         + -5.2099962525e+00) * z + 4.6494977072e+01) * z;
     const double rp3 = 3.7969820455e-01 * t + -1.8507636718e-02 * s + -2.3342758797e-02;
@@ -62,6 +62,7 @@ __device__ __forceinline__ double ln_pc(double a0, double a1, double a2, double 
 struct Constants {
     double K1, K2, KB, KW, KS, KF, KP1, KP2, KP3, KSi;
     double Tk, Is, sqrtS, logT;
+    double isd, KSsd;  // H-independent sulfate terms: 1 / (1 + ST/KS), KS (1 + ST/KS)
 };
 
 // all equilibrium constants of carbon_chemistry.jl:140-149 (defaults of :66-87)
@@ -70,18 +71,18 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
                                           Constants& c) {
     constexpr double LN10 = 2.302585092994045684;
     const double T = Tc_in + 273.15;
-    const double invT = 1.0 / T;
+    const double invT = rcp_fast(T);
     const double logT = log(T);
     const double sqS = sqrt(S);
     const double S15 = S * sqS;
-    const double Is = 19.924 * S / (1000.0 + -1.005 * S);  // :341
+    const double Is = 19.924 * S * rcp_fast(1000.0 + -1.005 * S);  // :341
     const double sqIs = sqrt(Is);
     const double Is15 = Is * sqIs;
     const double logS1 = log(1 + -0.001005 * S);
     double Tc = 0, inv_RT = 0;
     if (HAS_P) {
         Tc = T - 273.15;
-        inv_RT = 1.0 / (83.14472 * T);
+        inv_RT = invT * (1.0 / 83.14472);
     }
     // K1 :124-126, K2 :170-172 (10^x)
     double e1 = 61.2172 + -3633.86 * invT + -9.67770 * logT + 0.011555 * S + -0.0001152 * (S * S);
@@ -145,30 +146,30 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
                                          bool need_silicate, double& f, double& Hdf) {
     const double K1K2 = c.K1 * c.K2;
     const double cd = H * H + c.K1 * H + K1K2;
-    const double icd = 1.0 / cd;
+    const double icd = rcp_fast(cd);
     // bicarbonate + carbonate
     f = c.K1 * t.DIC * (H + 2 * c.K2) * icd;
     double df = c.K1 * t.DIC * ((K1K2 - H * H) - 2 * c.K2 * (2 * H + c.K1)) * (icd * icd);
     // borate
-    const double ib = 1.0 / (c.KB + H);
+    const double ib = rcp_fast(c.KB + H);
     f += t.boron * c.KB * ib;
     df -= t.boron * c.KB * (ib * ib);
     // hydroxide − free hydrogen
-    const double iH = 1.0 / H;
-    const double isd = 1.0 / (1 + t.sulfate / c.KS);
+    const double iH = rcp_fast(H);
+    const double isd = c.isd;
     f += c.KW * iH - H * isd;
     df -= c.KW * (iH * iH) + isd;
     // hydrogen sulfate: −ST·H / (H + KS·sd)
-    const double KSsd = c.KS * (1 + t.sulfate / c.KS);
-    const double ihs = 1.0 / (H + KSsd);
+    const double KSsd = c.KSsd;
+    const double ihs = rcp_fast(H + KSsd);
     f -= t.sulfate * H * ihs;
     df -= t.sulfate * KSsd * (ihs * ihs);
     // hydrogen fluoride: −FT·H / (H + KF)
-    const double ihf = 1.0 / (H + c.KF);
+    const double ihf = rcp_fast(H + c.KF);
     f -= t.fluoride * H * ihf;
     df -= t.fluoride * c.KF * (ihf * ihf);
     if (need_silicate) {
-        const double isi = 1.0 / (c.KSi + H);
+        const double isi = rcp_fast(c.KSi + H);
         f += t.silicate * c.KSi * isi;
         df -= t.silicate * c.KSi * (isi * isi);
     }
@@ -177,7 +178,7 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
         const double H2 = H * H, H3 = H2 * H;
         const double pd = H3 + c.KP1 * H2 + k12 * H + k123;
         const double dpd = 3 * H2 + 2 * c.KP1 * H + k12;
-        const double ipd = 1.0 / pd;
+        const double ipd = rcp_fast(pd);
         const double num = k12 * H + 2 * k123 - H3;  // [HPO₄²⁻] + 2[PO₄³⁻] − [H₃PO₄] numerator
         f += t.phosphate * num * ipd;
         df += t.phosphate * ((k12 - 3 * H2) * pd - num * dpd) * (ipd * ipd);
@@ -196,7 +197,7 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
     for (int n = 0; n < iterations; n++) {
         double f, Hdf;
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
-        double dx = f / Hdf;
+        double dx = f * rcp_fast(Hdf);
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
         x -= dx;
         H = exp(x);
@@ -206,7 +207,7 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
 
 // K0 — equilibrium_constants.jl:65-80
 __device__ __forceinline__ double K0(double T, double logT, double S) {
-    return exp(-60.2409 + (93.4517 * 100) / T + 23.3585 * (logT - 4.605170185988092) + 0.0 * (T * T)
+    return exp(-60.2409 + (93.4517 * 100) * rcp_fast(T) + 23.3585 * (logT - 4.605170185988092) + 0.0 * (T * T)
                + (0.023517 + (-0.023656 / 100) * T + (0.0047036 / (100.0 * 100.0)) * (T * T)) * S);
 }
 
@@ -214,10 +215,11 @@ __device__ __forceinline__ double K0(double T, double logT, double S) {
 template <bool HAS_P>
 __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P) {
     constexpr double LN10 = 2.302585092994045684;
-    const double therm = -171.9065 + -0.077993 * T + 2839.319 / T + 71.595 * (logT / LN10);
-    const double sea = ((-0.77712 + 0.0028426 * T + 178.34 / T) * sqS + -0.07711 * S + 0.0041249 * (S * sqS));
+    const double iT = rcp_fast(T);
+    const double therm = -171.9065 + -0.077993 * T + 2839.319 * iT + 71.595 * (logT * (1.0 / LN10));
+    const double sea = ((-0.77712 + 0.0028426 * T + 178.34 * iT) * sqS + -0.07711 * S + 0.0041249 * (S * sqS));
     double e = (therm + sea) * LN10;
-    if (HAS_P) e += ln_pc(-48.76, 0.5304, -0.0, -0.01176, 0.0003692, T - 273.15, P, 1.0 / (83.14472 * T));
+    if (HAS_P) e += ln_pc(-48.76, 0.5304, -0.0, -0.01176, 0.0003692, T - 273.15, P, iT * (1.0 / 83.14472));
     return exp(e);
 }
 
@@ -233,35 +235,43 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     const double rho = teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
     Constants c;
     constants<HAS_P>(T, S, P, has_phos, has_sil, c);
-    const double scale = 1e-3 / rho;
+    const double scale = 1e-3 * rcp_fast(rho);
     Totals t;
     t.DIC = DIC * scale;
     t.Alk = Alk * scale;
     t.phosphate = phosphate * scale;
     t.silicate = silicate * scale;
-    t.boron = 0.000232 / 10.811 * S / 1.80655;
-    t.sulfate = 0.14 / 96.06 * S / 1.80655;
-    t.fluoride = 0.000067 / 18.9984 * S / 1.80655;
+    t.boron = 0.000232 / 10.811 * S * (1.0 / 1.80655);
+    t.sulfate = 0.14 / 96.06 * S * (1.0 / 1.80655);
+    t.fluoride = 0.000067 / 18.9984 * S * (1.0 / 1.80655);
 
+    {
+        const double sd = 1 + t.sulfate * rcp_fast(c.KS);
+        c.isd = rcp_fast(sd);
+        c.KSsd = c.KS * sd;
+    }
     const double H = has_pH ? exp(-pH * LN10) : solve_H(c, t, has_phos, has_sil, initial_pH, iterations);
 
     switch (output_kind) {
         case OBM_CC_PH_FREE: return -log10(H);
-        case OBM_CC_PH_TOTAL: return -log10(H + t.sulfate / (1 + c.KS / H));
-        case OBM_CC_PH_SEAWATER: return -log10(H + t.sulfate / (1 + c.KS / H) + t.fluoride / (1 + c.KF / H));
+        case OBM_CC_PH_TOTAL: return -log10(H + t.sulfate * rcp_fast(1 + c.KS * rcp_fast(H)));
+        case OBM_CC_PH_SEAWATER: {
+            const double iH = rcp_fast(H);
+            return -log10(H + t.sulfate * rcp_fast(1 + c.KS * iH) + t.fluoride * rcp_fast(1 + c.KF * iH));
+        }
         case OBM_CC_CO3:
         case OBM_CC_OMEGA_CALCITE: {
             const double denom1 = (H * (H + c.K1));
-            const double denom2 = (1.0 + c.K1 * c.K2 / denom1);
-            const double CO3 = t.DIC * c.K1 * c.K2 / denom1 / denom2;
+            const double denom2 = (1.0 + c.K1 * c.K2 * rcp_fast(denom1));
+            const double CO3 = t.DIC * c.K1 * c.K2 * rcp_fast(denom1 * denom2);
             if (output_kind == OBM_CC_CO3) return CO3;
-            const double calcium = 0.0103 * S / 35;
-            return calcium * CO3 / KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P);
+            const double calcium = 0.0103 * S * (1.0 / 35);
+            return calcium * CO3 * rcp_fast(KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P));
         }
         default: break;
     }
-    const double CO2 = t.DIC * (H * H) / (H * H + c.K1 * H + c.K1 * c.K2);
-    double fCO2 = (CO2 / K0(c.Tk, c.logT, S)) * 1000000.0;
+    const double CO2 = t.DIC * (H * H) * rcp_fast(H * H + c.K1 * H + c.K1 * c.K2);
+    double fCO2 = (CO2 * rcp_fast(K0(c.Tk, c.logT, S))) * 1000000.0;
     if (output_kind == OBM_CC_FCO2) return fCO2;
     // pCO₂: carbon_chemistry.jl:170-193 (3 fixed-point virial iterations)
     const double Pp = (HAS_P ? P : 1.0) * 101325.0;
@@ -270,14 +280,16 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     const double dl = (57.7 + -0.118 * Tk) * 1e-6;
     fCO2 *= 0.09807;
     double phi = 1.0;
-    double x = fCO2 / (phi * Pp);
+    const double iPp = rcp_fast(Pp);
+    const double iRT = rcp_fast(8.31446261815324 * Tk);
+    double x = fCO2 * iPp;
 #pragma unroll
     for (int n = 0; n < 3; n++) {
         const double om = 1.0 - x;
-        phi = exp((B + 2.0 * (om * om) * dl) * Pp / (8.31446261815324 * Tk));
-        x = fCO2 / (phi * Pp);
+        phi = exp((B + 2.0 * (om * om) * dl) * Pp * iRT);
+        x = fCO2 * rcp_fast(phi) * iPp;
     }
-    return fCO2 / phi / 0.09807;
+    return fCO2 * rcp_fast(phi) * (1.0 / 0.09807);
 }
 
 }  // namespace cc

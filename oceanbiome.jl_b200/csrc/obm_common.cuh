@@ -40,6 +40,17 @@ __device__ __forceinline__ double jl_eps(double x) {
     return __longlong_as_double(__double_as_longlong(ax) + 1) - ax;  // Inf: NaN-pattern − Inf = NaN
 }
 
+// Lean reciprocal: MUFU.RCP64H seed (2⁻²³) + 2 Newton steps → ≤ 1 ulp, 4 DFMA, no branches, no
+// slow-path call.  Valid for normal, finite b (0 → Inf → NaN, NaN → NaN: garbage in, NaN out);
+// callers that need the IEEE special cases use `/`.
+__device__ __forceinline__ double rcp_fast(double b) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    return r;
+}
+
 // ---- grid indexing -----------------------------------------------------------------------------
 struct GridDims {
     int Nx, Ny, Nz, Hx, Hy, Hz;

@@ -63,13 +63,6 @@ constexpr int NOUT = 24;  // tendencies staged in shared memory
 // (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and plain
 // fmin/fmax.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
 // by fmin/fmax) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
-__device__ __forceinline__ double rcp_fast(double b) {
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-    r = fma(fma(-b, r, 1.0), r, r);
-    r = fma(fma(-b, r, 1.0), r, r);
-    return r;
-}
 template <bool EXACT>
 struct Ar {
     static constexpr bool EX = EXACT;
