@@ -155,8 +155,10 @@ class Workload:
 # end-to-end leg: host (pinned) buffers in, host buffers out, through the public API
 # --------------------------------------------------------------------------------------------------
 class HostStage:
-    """The call a user with HOST arrays makes: tracers live in pinned host memory, every step copies
-    them to the device, runs the stage through the plugin hooks, and reads every tendency back."""
+    """The call a user with HOST arrays makes: tracers live in pinned host memory; every step copies them to
+    the device, runs the stage through the plugin hooks and reads every tendency back — as a 3-stream slab
+    pipeline (oceanbiome_b200.host_stage.HostStagedStage).  The flat carbonate sweep copies its 4 inputs in and
+    its output back."""
 
     def __init__(self, w: Workload):
         self.w = w
@@ -168,16 +170,10 @@ class HostStage:
             self.h2d_bytes = 4 * 8 * w.n
             self.d2h_bytes = 8 * w.n
             return
-        m = w.model
-        self.names = list(m.tracers)
-        self.h_in = {n: torch.empty(m.tracers[n].data.shape, dtype=torch.float64).pin_memory() for n in self.names}
-        for n in self.names:
-            self.h_in[n].copy_(m.tracers[n].data)
-        self.gnames = [n for n in self.names if n not in ("T", "S")]
-        self.h_out = {n: torch.empty(m.Gn[n].data.shape, dtype=torch.float64).pin_memory() for n in self.gnames}
-        nb = m.tracers[self.names[0]].data.numel() * 8
-        self.h2d_bytes = nb * len(self.names)
-        self.d2h_bytes = nb * len(self.gnames)
+        from oceanbiome_b200.host_stage import HostStagedStage
+        self.stage = HostStagedStage(w.model, nslabs=8 if w.grid.Ny >= 64 else 1)
+        self.stage.upload_from_device()
+        self.h2d_bytes, self.d2h_bytes = self.stage.h2d_bytes, self.stage.d2h_bytes
 
     def step(self):
         w = self.w
@@ -187,14 +183,7 @@ class HostStage:
             w.step()
             self.h_out.copy_(w.out, non_blocking=True)
             return
-        m = w.model
-        for n in self.names:
-            m.tracers[n].data.copy_(self.h_in[n], non_blocking=True)
-        for n in self.gnames:
-            m.Gn[n].data.zero_()
-        w.step()
-        for n in self.gnames:
-            self.h_out[n].copy_(m.Gn[n].data, non_blocking=True)
+        self.stage.step()
 
 
 # --------------------------------------------------------------------------------------------------

@@ -370,6 +370,17 @@ int obm_inventory(const obm_grid* grid, int ntracers, const double* const* trace
                   double uniform_volume, double* out, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Host-buffer staging (for callers whose fields live in pinned HOST memory): copies interior
+ * rows j ∈ [grid.j0, grid.j1) of `nplanes` k-planes of each field, host → device (direction 0)
+ * or device → host (1), as one strided 2-D copy per field on `stream`.  Because every hot
+ * kernel is pointwise or column-local, a stage can be pipelined slab by slab with these copies
+ * (oceanbiome.jl_b200/host_stage.py).  Oceananigans fields are device-resident, so the Julia
+ * glue does not need this; it is the end-to-end path of bench.py.
+ * ------------------------------------------------------------------------------------ */
+int obm_copy_slab(const obm_grid* grid, int nfields, void* const* dst, const void* const* src,
+                  int nplanes, int direction, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Diagnostic (synchronises): measured FP64-pipe peak in DFMA instructions per second, the
  * denominator of the FP64 roofline.  scratch: DEVICE buffer of >= 148*8*256 doubles.
  * ------------------------------------------------------------------------------------ */

@@ -196,6 +196,7 @@ PROTOTYPES = {
     "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),
     "obm_inventory": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.POINTER(obm_scale_group),
                                 C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
     "obm_last_error": (C.c_char_p, []),
     "obm_version": (C.c_int, []),

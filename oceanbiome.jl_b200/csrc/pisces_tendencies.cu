@@ -253,17 +253,17 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
     // ---- shared scalars --------------------------------------------------------------------------------
     const double shear = c.z < c.zmxl ? p.background_shear : p.mixed_layer_shear;
     const double dO2 = A::mn(1.0, A::mx(0.0, A::div(0.4 * (p.first_anoxia_threshold - c.O2), p.second_anoxia_threshold + c.O2)));
-    // b^T once per distinct base (exp(T ln b); bases are parameters, ln b is host-evaluated)
-    double fT[6];
-#pragma unroll
-    for (int u = 0; u < 6; u++) {
-        double v = 0.0;
-        bool found = false;
-#pragma unroll
-        for (int q = 0; q < u; q++)
-            if (a.same_as[u] == q) { v = fT[q]; found = true; }
-        fT[u] = found ? v : exp(c.T * a.ln_base[u]);
-    }
+    // b^T once per distinct base (exp(T ln b); bases are parameters, ln b is host-evaluated; `same_as`
+    // is uniform, so these are uniform branches / selects on scalars — no local array)
+    const int s1 = a.same_as[1], s2 = a.same_as[2], s3 = a.same_as[3], s4 = a.same_as[4], s5 = a.same_as[5];
+    const double fT0 = exp(c.T * a.ln_base[0]);
+    double fT1, fT2, fT3, fT4, fT5;
+    if (s1 < 0) fT1 = exp(c.T * a.ln_base[1]); else fT1 = fT0;
+    if (s2 < 0) fT2 = exp(c.T * a.ln_base[2]); else fT2 = s2 == 0 ? fT0 : fT1;
+    if (s3 < 0) fT3 = exp(c.T * a.ln_base[3]); else fT3 = s3 == 0 ? fT0 : (s3 == 1 ? fT1 : fT2);
+    if (s4 < 0) fT4 = exp(c.T * a.ln_base[4]); else fT4 = s4 == 0 ? fT0 : (s4 == 1 ? fT1 : (s4 == 2 ? fT2 : fT3));
+    if (s5 < 0) fT5 = exp(c.T * a.ln_base[5]); else fT5 = s5 == 0 ? fT0 : (s5 == 1 ? fT1 : (s5 == 2 ? fT2 : (s5 == 3 ? fT3 : fT4)));
+    const double fT[6] = {fT0, fT1, fT2, fT3, fT4, fT5};
 
     // ---- phytoplankton ------------------------------------------------------------------------------------
     const Phyto n = phytoplankton<A>(a, 0, c, P, PChl, PFe, fT[0], shear);

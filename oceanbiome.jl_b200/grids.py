@@ -7,6 +7,7 @@ non-Flat side) so that the pointers handed to the C ABI here are interchangeable
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 
@@ -117,9 +118,22 @@ class RectilinearGrid:
         """Interior cell volumes, shape (Nz, 1, 1) broadcastable against `interior(...)`."""
         return torch.from_numpy(self.dz * self.dx * self.dy).to(self.device).reshape(-1, 1, 1)
 
-    def c_grid(self, i0=0, i1=0, j0=0, j1=0) -> _lib.obm_grid:
+    def c_grid(self, i0=None, i1=None, j0=None, j1=None) -> _lib.obm_grid:
+        r = getattr(self, "_subrange", (0, 0, 0, 0))
+        i0, i1, j0, j1 = (r[n] if v is None else v for n, v in enumerate((i0, i1, j0, j1)))
         return _lib.obm_grid(self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz, i0, i1, j0, j1,
                              self.zc_dev.data_ptr(), self.zf_dev.data_ptr())
+
+    @contextlib.contextmanager
+    def restrict(self, j0: int, j1: int, i0: int = 0, i1: int = 0):
+        """Every kernel launched inside the block processes only the interior sub-range
+        i ∈ [i0, i1), j ∈ [j0, j1) (partial launches: slab pipelining, multi-stream execution)."""
+        old = getattr(self, "_subrange", (0, 0, 0, 0))
+        self._subrange = (i0, i1, j0, j1)
+        try:
+            yield self
+        finally:
+            self._subrange = old
 
     def slab(self, rank: int, world: int) -> "RectilinearGrid":
         """x–y slab decomposition for multi-GPU runs: split y (the slower horizontal axis, so

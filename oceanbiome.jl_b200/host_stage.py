@@ -1,0 +1,82 @@
+"""Host-resident stage: the call a user whose tracer fields live in HOST memory makes.
+
+`HostStagedStage(model)` keeps every tracer and every tendency in pinned host arrays (same halo'd parent
+layout) and runs one biogeochemical stage — `update_biogeochemical_state!` + all tendencies — for the whole
+grid as a 3-stream pipeline over x–y slabs:
+
+        H2D(slab s+1)   ∥   kernels(slab s)   ∥   D2H(slab s−1)
+
+which is legal because every hot kernel is pointwise or column-local.  The PCIe copies, not the
+kernels, bound this path; pipelining overlaps the two copy directions and hides the kernels entirely.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+class HostStagedStage:
+    def __init__(self, model, nslabs: int = 8, pin: bool = True):
+        self.model = model
+        self.grid = model.grid
+        g = self.grid
+        self.names = list(model.tracers)
+        self.gnames = [n for n in self.names if n not in ("T", "S")]
+        alloc = (lambda t: torch.empty(t.shape, dtype=torch.float64).pin_memory()) if pin else \
+                (lambda t: torch.empty(t.shape, dtype=torch.float64))
+        self.host_tracers = {n: alloc(model.tracers[n].data) for n in self.names}
+        self.host_G = {n: alloc(model.Gn[n].data) for n in self.gnames}
+        nslabs = max(1, min(nslabs, g.Ny))
+        edges = [round(s * g.Ny / nslabs) for s in range(nslabs + 1)]
+        self.slabs = [(edges[s], edges[s + 1]) for s in range(nslabs) if edges[s + 1] > edges[s]]
+        dev = g.device
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.nplanes = g.Nz + 2 * g.Hz
+        plane_bytes = (g.Nx + 2 * g.Hx) * 8 * self.nplanes
+        self.h2d_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * len(self.names)
+        self.d2h_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * len(self.gnames)
+        self._src_in = _lib.pointer_table([self.host_tracers[n].data_ptr() for n in self.names])
+        self._dst_in = _lib.pointer_table([model.tracers[n].ptr for n in self.names])
+        self._src_out = _lib.pointer_table([model.Gn[n].ptr for n in self.gnames])
+        self._dst_out = _lib.pointer_table([self.host_G[n].data_ptr() for n in self.gnames])
+
+    def upload_from_device(self):
+        """Initialise the host copies from the model's current device state."""
+        for n in self.names:
+            self.host_tracers[n].copy_(self.model.tracers[n].data)
+
+    def step(self):
+        """One stage, host → host.  Returns after all work is enqueued; `synchronize()` to wait."""
+        lib = _lib.load()
+        m, g = self.model, self.grid
+        bgc = m.biogeochemistry
+        cur = torch.cuda.current_stream(g.device)
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.wait_stream(cur)
+        for j0, j1 in self.slabs:
+            cg = g.c_grid(j0=j0, j1=j1)
+            rc = lib.obm_copy_slab(C.byref(cg), len(self.names), self._dst_in, self._src_in, self.nplanes, 0,
+                                   self.s_in.cuda_stream)
+            _lib.check(rc, "obm_copy_slab(H2D)")
+            ready = self.s_in.record_event()
+            self.s_run.wait_event(ready)
+            with torch.cuda.stream(self.s_run), g.restrict(j0, j1):
+                bgc.update_biogeochemical_state(m)
+                bgc.underlying_biogeochemistry.compute_tendencies(g, m.tracers, bgc.biogeochemical_auxiliary_fields(), m.Gn,
+                                                                 accumulate=False, time=m.clock.time)
+                if bgc.sediment is not None:
+                    bgc.sediment.update_tendencies(bgc, m, None)
+            done = self.s_run.record_event()
+            self.s_out.wait_event(done)
+            rc = lib.obm_copy_slab(C.byref(cg), len(self.gnames), self._dst_out, self._src_out, self.nplanes, 1,
+                                   self.s_out.cuda_stream)
+            _lib.check(rc, "obm_copy_slab(D2H)")
+        for s in (self.s_in, self.s_run, self.s_out):
+            cur.wait_stream(s)
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.grid.device).synchronize()

@@ -4,7 +4,7 @@
 set -u
 W=${1:-lobster_c3}; KS=${2:-tendency}; shift 2 || true
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:obm -c 400 --csv --log-file gpurun_out/launches_$W.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"pisces_|calcite_|euphotic_|mixed_layer_|par_|scale_negative|zero_negative|npd_|carbon_sweep|inventory_|sediment_|gas_" -c 400 --csv --log-file gpurun_out/launches_$W.csv \
     python bench.py --workload $W --steps 3 --warmup 3 --no-e2e --no-cpu-baseline "$@" > gpurun_out/ncu_bench_$W.log 2>&1
 for K in $KS; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o gpurun_out/prof_${W}_$K -f \
