@@ -357,6 +357,78 @@ int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tra
                               void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (a8) Bottom sediments — src/Sediments/ (driver) + src/Models/Sediments/ (equations).
+ * The reference runs ≈ 15 tiny :xy launches per stage (K7–K11 of SURVEY §2.2); here there are
+ * two fused :xy launches, one per hook:
+ *   obm_sediment_update_state      ↔ update_biogeochemical_state!(model, ::BiogeochemicalSediment)
+ *                                    (Sediments/update_state.jl:6-16): gather bottom-cell tracers
+ *                                    (tracked_fields.jl:43-51), sinking fluxes (:60-71), step the
+ *                                    sediment pools with the stored tendencies (timesteppers.jl:15-73),
+ *                                    cache G⁻ ← Gⁿ (:78-94), recompute Gⁿ (compute_tendencies.jl:5-50);
+ *   obm_sediment_update_tendencies ↔ update_tendencies!(bgc, sediment, model)
+ *                                    (Sediments/tracer_coupling.jl:3-39): G[i,j,k_bottom] += flux / Δz.
+ * PARITY UNPINNED: the reference's sediment tests are commented out (test/test_sediments.jl:106-163)
+ * and the stepping order / flux operator live in Oceananigans (not in the tree) — see DESIGN.md.
+ * ------------------------------------------------------------------------------------ */
+enum { OBM_SED_INSTANT_REMINERALISATION = 0, OBM_SED_SIMPLE_MULTI_G = 1 };
+enum { OBM_ADV_UPWIND1 = 0, OBM_ADV_CENTERED2 = 1 }; /* face reconstruction of advective_tracer_flux_z */
+enum { OBM_TS_AB2 = 0, OBM_TS_RK3 = 1 };             /* Sediments.jl:48: timestepper                   */
+#define OBM_SED_MAX_SINKING 4
+#define OBM_SED_MAX_POOLS 6
+#define OBM_SED_MAX_COUPLED 4
+
+typedef struct obm_sediment_params {
+    int32_t model;             /* OBM_SED_*                                                          */
+    int32_t carbon;            /* SimpleMultiG{Nothing}: separate C pools + sinking carbon tracers   */
+    int32_t nsinking_nitrogen; /* length(sinking_nitrogen) (InstantRemineralisation: sinking_tracers) */
+    int32_t nsinking_carbon;
+    int32_t advection;         /* OBM_ADV_*                                                          */
+    int32_t timestepper;       /* OBM_TS_*                                                           */
+    /* InstantRemineralisation — Models/Sediments/instant_remineralisation.jl:13-19,83-96 */
+    double burial_efficiency_constant1, burial_efficiency_constant2, burial_efficiency_half_saturation;
+    /* SimpleMultiG — Models/Sediments/simple_multi_G.jl:15-38,104-132 */
+    double sinking_redfield, fast_decay_rate, slow_decay_rate, fast_redfield, slow_redfield,
+        fast_fraction, slow_fraction, refactory_fraction, sedimentation_rate, anoxia_half_saturation;
+    double nitrate_oxidation_params[6], denitrification_params[6], anoxic_params[6],
+        solid_dep_params[4];
+} obm_sediment_params;
+
+typedef struct obm_sediment_fields {
+    const int64_t* bottom_indices_xy; /* 2-D Int field, 1-based k of the bottom cell
+                                         (bottom_indices.jl:19-26); NULL ⇒ OneField ⇒ k = 1      */
+    /* water-column side (3-D parents) */
+    const double* NO3;                /* tracked tracers of SimpleMultiG (simple_multi_G.jl:42)    */
+    const double* NH4;
+    const double* O2;
+    const double* sinking[2 * OBM_SED_MAX_SINKING];   /* sinking tracers: nitrogen…, then carbon… */
+    const double* sinking_w[2 * OBM_SED_MAX_SINKING]; /* their w: z-FACE fields                    */
+    /* sediment side (2-D parents): pools in required_sediment_fields order
+       (InstantRemineralisation: storage; SimpleMultiG: Ns Nf Nr [Cs Cf Cr]) */
+    double* pools[OBM_SED_MAX_POOLS];
+    double* Gn[OBM_SED_MAX_POOLS];    /* timestepper.Gⁿ / G⁻ of the pools                         */
+    double* Gm[OBM_SED_MAX_POOLS];
+    double* tracked_xy[3 + 2 * OBM_SED_MAX_SINKING]; /* tracked_fields (tracers…, fluxes…), written every call */
+    /* tendencies of the coupled tracers (3-D): InstantRemineralisation: the receiver;
+       SimpleMultiG: NO₃ NH₄ O₂ [DIC] (simple_multi_G.jl:45-46) */
+    double* G_coupled[OBM_SED_MAX_COUPLED];
+} obm_sediment_fields;
+
+/* dt = model.clock.last_stage_Δt (non-finite ⇒ pools are not stepped, update_state.jl:11-13).
+ * AB2: chi (χ = −0.5 ⇒ Euler; timesteppers.jl:29-42).  RK3: gamma, zeta (zeta = NaN ⇒ the
+ * first-stage method without G⁻, :67-73). */
+int obm_sediment_update_state(const obm_grid* grid, const obm_sediment_params* p,
+                              const obm_sediment_fields* f, double dt, double chi, double gamma,
+                              double zeta, void* stream);
+int obm_sediment_update_tendencies(const obm_grid* grid, const obm_sediment_params* p,
+                                   const obm_sediment_fields* f, void* stream);
+
+/* K12 `find_bottom_cell!` (bottom_indices.jl:7-17) for a grid-fitted bottom: k_bottom = first
+ * (1-based) k whose centre is NOT immersed, i.e. not (z_c[k] <= bottom_height[i,j]), capped at Nz.
+ * Integer work: bit-exact. */
+int obm_find_bottom_cells(const obm_grid* grid, const double* bottom_height_xy,
+                          int64_t* bottom_indices_xy, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
  * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
  * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics
