@@ -17,6 +17,8 @@ from .npd import (LOBSTER, NPZD, AnalyticalLightLimitation, CarbonateSystem, Det
                   TwoParticleAndDissolved, VariableRedfieldDetritus)
 from . import pisces
 from .pisces import PISCES, CBMDayLength, DepthDependantSinkingSpeed, PrescribedLatitude
+from .sediments import (BiogeochemicalSediment, InstantRemineralisation, InstantRemineralisationSediment, SimpleMultiG,
+                        SimpleMultiGSediment, calculate_bottom_indices)
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
 
 __version__ = "0.1.0"

@@ -160,7 +160,33 @@ class obm_pisces_fields(C.Structure):
 
 OBM_PISCES_NTRACERS = 26
 
+SED_INSTANT_REMINERALISATION, SED_SIMPLE_MULTI_G = 0, 1
+ADV_UPWIND1, ADV_CENTERED2 = 0, 1
+TS_AB2, TS_RK3 = 0, 1
+OBM_SED_MAX_SINKING, OBM_SED_MAX_POOLS, OBM_SED_MAX_COUPLED = 4, 6, 4
+
+
+class obm_sediment_params(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("model", "carbon", "nsinking_nitrogen", "nsinking_carbon", "advection", "timestepper")]
+                + [(n, C.c_double) for n in (
+                    "burial_efficiency_constant1", "burial_efficiency_constant2", "burial_efficiency_half_saturation",
+                    "sinking_redfield", "fast_decay_rate", "slow_decay_rate", "fast_redfield", "slow_redfield",
+                    "fast_fraction", "slow_fraction", "refactory_fraction", "sedimentation_rate", "anoxia_half_saturation")]
+                + [("nitrate_oxidation_params", C.c_double * 6), ("denitrification_params", C.c_double * 6),
+                   ("anoxic_params", C.c_double * 6), ("solid_dep_params", C.c_double * 4)])
+
+
+class obm_sediment_fields(C.Structure):
+    _fields_ = [("bottom_indices_xy", C.c_void_p), ("NO3", C.c_void_p), ("NH4", C.c_void_p), ("O2", C.c_void_p),
+                ("sinking", C.c_void_p * (2 * OBM_SED_MAX_SINKING)), ("sinking_w", C.c_void_p * (2 * OBM_SED_MAX_SINKING)),
+                ("pools", C.c_void_p * OBM_SED_MAX_POOLS), ("Gn", C.c_void_p * OBM_SED_MAX_POOLS),
+                ("Gm", C.c_void_p * OBM_SED_MAX_POOLS), ("tracked_xy", C.c_void_p * (3 + 2 * OBM_SED_MAX_SINKING)),
+                ("G_coupled", C.c_void_p * OBM_SED_MAX_COUPLED)]
+
+
 STRUCTS = {
+    "obm_sediment_params": obm_sediment_params,
+    "obm_sediment_fields": obm_sediment_fields,
     "obm_pisces_phyto": obm_pisces_phyto,
     "obm_pisces_zoo": obm_pisces_zoo,
     "obm_pisces_params": obm_pisces_params,
@@ -196,6 +222,11 @@ PROTOTYPES = {
     "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),
     "obm_inventory": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.POINTER(obm_scale_group),
                                 C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_sediment_update_state": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sediment_params), C.POINTER(obm_sediment_fields),
+                                            C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]),
+    "obm_sediment_update_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sediment_params),
+                                                 C.POINTER(obm_sediment_fields), C.c_void_p]),
+    "obm_find_bottom_cells": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_void_p, C.c_void_p]),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
     "obm_last_error": (C.c_char_p, []),

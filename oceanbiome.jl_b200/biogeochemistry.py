@@ -108,6 +108,9 @@ def _update_modifiers(model, modifiers, stream):
 class Clock:
     time: float = 0.0
     iteration: int = 0
+    last_stage_dt: float = float("inf")  # `clock.last_stage_Δt` (read by the sediment hook)
+    rk3_gamma: float = 1.0
+    rk3_zeta: float = float("nan")
 
 
 class BiogeochemicalModel:
@@ -152,10 +155,12 @@ class BiogeochemicalModel:
             for n, c in self.tracers.items():
                 c.data.add_(self.Gn[n].data, alpha=dt)
             self.clock.time += dt
+            self.clock.last_stage_dt = dt
         else:
             if self.Gm is None:
                 self.Gm = {n: CenterField(self.grid, "G⁻" + n) for n in self.tracers}
             for stage, (gamma, zeta) in enumerate(self.RK3):
+                self.clock.rk3_gamma, self.clock.rk3_zeta = gamma, (zeta if zeta else float("nan"))
                 self.update_state()
                 self.compute_tendencies()
                 for n, c in self.tracers.items():
@@ -164,4 +169,5 @@ class BiogeochemicalModel:
                         c.data.add_(self.Gm[n].data, alpha=dt * zeta)
                     self.Gm[n].data.copy_(self.Gn[n].data)
                 self.clock.time += dt * (gamma + zeta)
+                self.clock.last_stage_dt = dt * (gamma + zeta)
         self.clock.iteration += 1

@@ -41,10 +41,8 @@ extern "C" int obm_sizeof(const char* name) {
     S(obm_pisces_zoo);
     S(obm_pisces_params);
     S(obm_pisces_fields);
-#ifdef OBM_HAVE_SEDIMENT
     S(obm_sediment_params);
     S(obm_sediment_fields);
-#endif
 #undef S
     return OBM_EENUM;
 }

@@ -303,3 +303,58 @@ def cbm_day_length(t, phi):
     fn.restype = C.c_double
     fn.argtypes = [C.c_double, C.c_double]
     return fn(t, phi)
+
+
+# ---- sediments ----------------------------------------------------------------------------------------
+def sediment_fields(**ptrs):
+    """Build an obm_sediment_fields from numpy arrays: NO3, NH4, O2, sinking=[…], sinking_w=[…], pools=[…], Gn=[…],
+    Gm=[…], tracked=[…], G_coupled=[…], bottom_indices=int64 array."""
+    f = abi.obm_sediment_fields()
+    keep = []
+    for k in ("NO3", "NH4", "O2"):
+        if ptrs.get(k) is not None:
+            setattr(f, k, ptrs[k].ctypes.data)
+            keep.append(ptrs[k])
+    if ptrs.get("bottom_indices") is not None:
+        f.bottom_indices_xy = ptrs["bottom_indices"].ctypes.data
+    for name, member in (("sinking", "sinking"), ("sinking_w", "sinking_w"), ("pools", "pools"), ("Gn", "Gn"), ("Gm", "Gm"),
+                         ("tracked", "tracked_xy"), ("G_coupled", "G_coupled")):
+        for n, a in enumerate(ptrs.get(name) or []):
+            if a is not None:
+                getattr(f, member)[n] = a.ctypes.data
+    return f
+
+
+def sediment_update_state(grid: Grid, params, fields, dt, chi=0.1, gamma=1.0, zeta=float("nan")):
+    cg = grid.c_grid()
+    rc = lib().orc_sediment_update_state(C.byref(cg), C.byref(params), C.byref(fields), C.c_double(dt), C.c_double(chi),
+                                         C.c_double(gamma), C.c_double(zeta))
+    assert rc == 0
+
+
+def sediment_update_tendencies(grid: Grid, params, fields):
+    cg = grid.c_grid()
+    rc = lib().orc_sediment_update_tendencies(C.byref(cg), C.byref(params), C.byref(fields))
+    assert rc == 0
+
+
+def find_bottom_cells(grid: Grid, bottom_height):
+    out = np.ones(grid.plane_shape, dtype=np.int64)
+    cg = grid.c_grid()
+    rc = lib().orc_find_bottom_cells(C.byref(cg), C.c_void_p(_ptr(bottom_height)), C.c_void_p(out.ctypes.data))
+    assert rc == 0
+    return out
+
+
+def sediment_point(params, pools, NO3, NH4, O2, fN, fC=0.0):
+    """→ (pool tendencies, coupled fluxes) at one point."""
+    L = lib()
+    for fn in (L.orc_sediment_pool_tendency, L.orc_sediment_coupled_flux):
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 5 + [C.c_int]
+    pl = (C.c_double * 6)(*(list(pools) + [0.0] * (6 - len(pools))))
+    smg = params.model == abi.SED_SIMPLE_MULTI_G
+    npool = (6 if params.carbon else 3) if smg else 1
+    nc = (4 if params.carbon else 3) if smg else 1
+    return ([L.orc_sediment_pool_tendency(C.byref(params), pl, NO3, NH4, O2, fN, fC, n) for n in range(npool)],
+            [L.orc_sediment_coupled_flux(C.byref(params), pl, NO3, NH4, O2, fN, fC, n) for n in range(nc)])
