@@ -113,23 +113,25 @@ def test_total_nitrogen_is_conserved_with_sinking_into_the_sediment(cuda):
         sediment = sum(f.interior.sum().item() for f in sed.fields.values()) * A
         return water + sediment
 
-    def sink(dt):  # upwind-1 sinking: flux through face k = −w·C[k] (w < 0), zero through the surface
-        for n in ("sPOM", "bPOM"):
-            w = -bgc.biogeochemical_drift_velocity(n)
+    def sinking_fluxes():  # upwind-1: downward flux through the lower face of every cell, from the CURRENT state
+        return {n: -bgc.biogeochemical_drift_velocity(n) * model.tracers[n].interior.clone() for n in ("sPOM", "bPOM")}
+
+    def sink(fluxes, dt):  # flux divergence; nothing enters through the surface, the bottom face feeds the sediment
+        for n, flux in fluxes.items():
             c = model.tracers[n].interior
-            flux = w * c                      # downward flux leaving each cell through its lower face
             c -= dt * flux / dz
             c[:-1] += dt * flux[1:] / dz
 
     N0 = total()
     dt = 20.0
     for _ in range(50):
-        # order of one step: state update (sediment pools stepped with the PREVIOUS flux-based Gⁿ), tendencies, tracers
-        model.update_state()
+        # one step: state update (sediment pools stepped with the PREVIOUS flux-based Gⁿ), tendencies, tracers
+        model.update_state()          # the sediment tracks the bottom flux of THIS state …
+        fluxes = sinking_fluxes()     # … and the water column loses exactly the same flux
         model.compute_tendencies()
         for n, c in model.tracers.items():
             c.data.add_(model.Gn[n].data, alpha=dt)
-        sink(dt)
+        sink(fluxes, dt)
         model.clock.last_stage_dt = dt
     # one more state update applies the last stored sediment tendency so both sides have seen 50 fluxes … the
     # sediment lags the water column by exactly one step (it integrates the flux computed at the previous call)
