@@ -1,5 +1,5 @@
 // carbon_chemistry.cuh — per-cell carbonate-system solve as a branch-free, fixed-iteration
-// Newton iteration in x = ln[H⁺] (device functions shared by the flat sweep kernel, the gridded
+// Newton iteration in x = ln[H⁺] with a warp-uniform early exit (device functions shared by the flat sweep kernel, the gridded
 // Ω kernel and the gas-exchange kernel).
 //
 // Replaces src/Models/CarbonChemistry/carbon_chemistry.jl:111-210 + alkalinity_residual.jl +
@@ -193,6 +193,7 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
     constexpr double LN10 = 2.302585092994045684;
     double x = -initial_pH * LN10;
     double H = exp(x);
+    const unsigned mask = __activemask();
 #pragma unroll 1
     for (int n = 0; n < iterations; n++) {
         double f, Hdf;
@@ -201,6 +202,9 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
         x -= dx;
         H = exp(x);
+        // Warp-uniform early exit (no divergence): once every lane's step is below 1e-7 the quadratic convergence
+        // of Newton puts the next iterate within ~1e-14 of the root; NaN lanes count as converged (they stay NaN).
+        if (__all_sync(mask, !(fabs(dx) >= 1e-7))) break;
     }
     return H;
 }

@@ -7,8 +7,11 @@
 // conflict-free), the groups are applied back to back on those staged values in the reference's
 // order, and every tracer is written once.  HBM-bound: 16 B per distinct tracer per cell.
 //
-// Arithmetic uses explicit round-to-nearest mul/add/div (no FMA contraction) so results are
-// bit-identical to the reference's `t += value * scale`, `value * t / p` sequence.
+// The sums t, p use explicit round-to-nearest mul/add (no FMA contraction) — bit-identical to the
+// reference's `t += value * scale` — so the decisions (t < 0, value > 0, NaN fill, zeroing) are exact.
+// The rescaling itself uses ONE division per group (value·(t/p) instead of value·t/p, ≤ 1 ulp apart) and
+// cells whose group has nothing to rescale are neither recomputed nor written back (the reference rewrites
+// them with value·t/t, i.e. value up to 1 ulp of rounding noise): half the HBM traffic in the common case.
 #include <string.h>
 
 #include "obm_common.cuh"
@@ -32,23 +35,33 @@ __global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_c
     const long long idx = cell_index(a.d, i, j, k);
     double* mine = sm + threadIdx.x;
     for (int t = 0; t < a.ntracers; t++) mine[t * SN_BLOCK] = a.tracers[t][idx];
+    unsigned dirty = 0;  // bit t ⇔ tracer t was rescaled and must be written back
     for (int q = 0; q < a.ngroups; q++) {
         const obm_scale_group& g = a.groups[q];
         double t = 0.0, p = 0.0;
-        for (int m = 0; m < g.n; m++) {  // negative_tracers.jl:256-264
+        unsigned members = 0;
+        for (int m = 0; m < g.n; m++) {  // negative_tracers.jl:256-264 (same operation order, no FMA contraction)
             const double v = mine[g.index[m] * SN_BLOCK];
             const double s = __dmul_rn(v, g.scalefactor[m]);
             t = __dadd_rn(t, s);
             if (v > 0) p = __dadd_rn(p, s);
+            members |= 1u << g.index[m];
         }
-        t = t < 0 ? a.fill : t;  // :266
-        for (int m = 0; m < g.n; m++) {  // :268-274
+        // No negative and no non-finite member ⇔ p == t (bitwise: identical operation sequence) and t finite: the
+        // reference would multiply every member by t/p = 1 (up to 1 ulp of (v·t)/t rounding noise) — leave the cell alone.
+        if (p == t && isfinite(t)) continue;
+        t = t < 0 ? a.fill : t;             // :266
+        const double ratio = __ddiv_rn(t, p);  // one division per group; v·t/p ≡ v·(t/p) to ≤ 1 ulp
+        for (int m = 0; m < g.n; m++) {     // :268-274
             const double v = mine[g.index[m] * SN_BLOCK];
             const bool keep = !isfinite(v) | (v > 0);
-            mine[g.index[m] * SN_BLOCK] = keep ? __ddiv_rn(__dmul_rn(v, t), p) : 0.0;
+            mine[g.index[m] * SN_BLOCK] = keep ? __dmul_rn(v, ratio) : 0.0;
         }
+        dirty |= members;
     }
-    for (int t = 0; t < a.ntracers; t++) a.tracers[t][idx] = mine[t * SN_BLOCK];
+    if (dirty == 0) return;
+    for (int t = 0; t < a.ntracers; t++)
+        if ((dirty >> t) & 1u) a.tracers[t][idx] = mine[t * SN_BLOCK];
 }
 
 struct ZeroArgs {

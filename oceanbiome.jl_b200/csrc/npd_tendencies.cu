@@ -35,6 +35,13 @@ __device__ __forceinline__ void put(double* g, long long idx, double t, int accu
     if (accumulate) t += g[idx];
     g[idx] = t;
 }
+// `accumulate` read issued up front (with the tracer loads) so that no store waits on a late, dependent load
+__device__ __forceinline__ double old_value(const double* g, long long idx, int accumulate) {
+    return (accumulate && g != nullptr) ? g[idx] : 0.0;
+}
+__device__ __forceinline__ void put(double* g, long long idx, double t, double old) {
+    if (g != nullptr) g[idx] = t + old;
+}
 
 // plankton.jl:86-90
 __device__ __forceinline__ double mortality(int form, double X, double m) { return form == OBM_LINEAR ? m * X : m * (X * X); }
@@ -59,6 +66,14 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
     if constexpr (DET == OBM_DET_DETRITUS) D = a.D[idx];
     if constexpr (TWO_SIZE) { sPOM = a.sPOM[idx]; bPOM = a.bPOM[idx]; DOM = a.DOM[idx]; }
     if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) { sPOC = a.sPOC[idx]; bPOC = a.bPOC[idx]; DOC = a.DOC[idx]; }
+
+    const int acc = a.accumulate;
+    const double oP = old_value(a.gP, idx, acc), oZ = old_value(a.gZ, idx, acc), oNO3 = old_value(a.gNO3, idx, acc),
+                 oNH4 = old_value(a.gNH4, idx, acc), oFe = old_value(a.gFe, idx, acc), oN = old_value(a.gN, idx, acc),
+                 oD = old_value(a.gD, idx, acc), osPOM = old_value(a.gsPOM, idx, acc), obPOM = old_value(a.gbPOM, idx, acc),
+                 oDOM = old_value(a.gDOM, idx, acc), osPOC = old_value(a.gsPOC, idx, acc), obPOC = old_value(a.gbPOC, idx, acc),
+                 oDOC = old_value(a.gDOC, idx, acc), oO2 = old_value(a.gO2, idx, acc),
+                 oDIC = a.nrep ? old_value(a.gDIC[0], idx, acc) : 0.0, oAlk = a.nrep ? old_value(a.gAlk[0], idx, acc) : 0.0;
 
     // ---- growth: plankton.jl:150-220 -----------------------------------------------------------
     double nl = 0, al = 0, Ln;
@@ -108,8 +123,8 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
     else dinw = ponw + sw;
 
     // ---- plankton: plankton.jl:92-116 -----------------------------------------------------------
-    put(a.gP, idx, (1 - p.phytoplankton_exudation_fraction) * muP - Gp - nuP, a.accumulate);
-    put(a.gZ, idx, p.zooplankton_assimilation_fraction * Gtot - mZZ - exc * Z, a.accumulate);
+    put(a.gP, idx, (1 - p.phytoplankton_exudation_fraction) * muP - Gp - nuP, oP);
+    put(a.gZ, idx, p.zooplankton_assimilation_fraction * Gtot - mZZ - exc * Z, oZ);
 
     // ---- nutrients: nutrients.jl:22-64, uptake plankton.jl:223-278 --------------------------
     double tNO3 = 0, tNH4 = 0, tN = 0, nitrif = 0;
@@ -119,31 +134,31 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
         const double lim = nl + al + eps0();
         tNO3 = nitrif - muP * nl / lim;
         tNH4 = pinw + dinw - nitrif - (muP * al / lim - ag * muP);
-        put(a.gNO3, idx, tNO3, a.accumulate);
-        put(a.gNH4, idx, tNH4, a.accumulate);
-        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) put(a.gFe, idx, -(p.iron_ratio * muP), a.accumulate);
+        put(a.gNO3, idx, tNO3, oNO3);
+        put(a.gNH4, idx, tNH4, oNH4);
+        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) put(a.gFe, idx, -(p.iron_ratio * muP), oFe);
     } else {
         tN = pinw + dinw - muP * (1 - ag);
-        put(a.gN, idx, tN, a.accumulate);
+        put(a.gN, idx, tN, oN);
     }
 
     // ---- detritus: detritus.jl:85-101, 143-158, 282-288 --------------------------------------
     const double R = p.redfield_ratio;
     if constexpr (DET == OBM_DET_DETRITUS) {
-        put(a.gD, idx, ponw + sw - Gd - p.remineralisation_rate * D, a.accumulate);
+        put(a.gD, idx, ponw + sw - Gd - p.remineralisation_rate * D, oD);
     }
     if constexpr (TWO_SIZE) {
         const double ssf = p.small_solid_waste_fraction;
-        put(a.gsPOM, idx, ssf * sw - Gd - sm * sPOM, a.accumulate);
-        put(a.gbPOM, idx, (1 - ssf) * sw - bm * bPOM, a.accumulate);
-        put(a.gDOM, idx, ponw + (1 - af) * (sm * sPOM + bm * bPOM) - dm * DOM, a.accumulate);
+        put(a.gsPOM, idx, ssf * sw - Gd - sm * sPOM, osPOM);
+        put(a.gbPOM, idx, (1 - ssf) * sw - bm * bPOM, obPOM);
+        put(a.gDOM, idx, ponw + (1 - af) * (sm * sPOM + bm * bPOM) - dm * DOM, oDOM);
         if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) {
             const double scw = sw * R;  // solid_carbon_waste plankton.jl:348
             // calcite_production plankton.jl:399-412
             const double cprod = (Gp * (1 - p.zooplankton_gut_calcite_dissolution) + nuP) * p.carbon_calcite_ratio * R;
-            put(a.gsPOC, idx, ssf * scw - Gd * R - sm * sPOC, a.accumulate);
-            put(a.gbPOC, idx, (1 - ssf) * scw + cprod - bm * bPOC, a.accumulate);
-            put(a.gDOC, idx, R * ponw + (1 - af) * (sm * sPOC + bm * bPOC) - dm * DOC, a.accumulate);
+            put(a.gsPOC, idx, ssf * scw - Gd * R - sm * sPOC, osPOC);
+            put(a.gbPOC, idx, (1 - ssf) * scw + cprod - bm * bPOC, obPOC);
+            put(a.gDOC, idx, R * ponw + (1 - af) * (sm * sPOC + bm * bPOC) - dm * DOC, oDOC);
         }
     }
 
@@ -174,7 +189,10 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
         if constexpr (HAS_NA) tAlk = tNH4 * (1 - 1.0 / 16) - tNO3 * (1 + 1.0 / 16) - 2.0 * cupt + 2.0 * cdis;
         else tAlk = tN - 2.0 * cupt + 2.0 * cdis;
 #pragma unroll 1
-        for (int r = 0; r < a.nrep; r++) {  // CarbonateSystem(N): every replicate gets the same tendency (:70-83)
+        put(a.gDIC[0], idx, tDIC, oDIC);
+        put(a.gAlk[0], idx, tAlk, oAlk);
+#pragma unroll 1
+        for (int r = 1; r < a.nrep; r++) {  // CarbonateSystem(N): every replicate gets the same tendency (:70-83)
             put(a.gDIC[r], idx, tDIC, a.accumulate);
             put(a.gAlk[r], idx, tAlk, a.accumulate);
         }
@@ -183,7 +201,7 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
     // ---- oxygen: oxygen.jl:21-31 (Nutrient models: bgc(Val(:NH₄)) = 0, nitrification = 0) -------
     if (a.gO2 != nullptr) {
         const double Rp = p.respiration_oxygen_nitrogen_ratio, Rn = p.nitrification_oxygen_nitrogen_ratio;
-        put(a.gO2, idx, Rp * muP - (Rp - Rn) * tNH4 - Rp * nitrif, a.accumulate);
+        put(a.gO2, idx, Rp * muP - (Rp - Rn) * tNH4 - Rp * nitrif, oO2);
     }
 }
 
