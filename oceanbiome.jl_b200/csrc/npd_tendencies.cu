@@ -188,7 +188,6 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
         double tAlk;
         if constexpr (HAS_NA) tAlk = tNH4 * (1 - 1.0 / 16) - tNO3 * (1 + 1.0 / 16) - 2.0 * cupt + 2.0 * cdis;
         else tAlk = tN - 2.0 * cupt + 2.0 * cdis;
-#pragma unroll 1
         put(a.gDIC[0], idx, tDIC, oDIC);
         put(a.gAlk[0], idx, tAlk, oAlk);
 #pragma unroll 1
