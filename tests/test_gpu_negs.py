@@ -51,7 +51,9 @@ def test_pisces_groups_match_oracle(cuda, oracle):
         assert np.array_equal(got == 0, host[n] == 0), n                    # zero pattern: exact
         assert np.array_equal(np.isinf(got), np.isinf(host[n])), n
         fin = np.isfinite(host[n])
-        assert np.all(np.abs(got[fin] - host[n][fin]) <= 1e-14 * np.abs(host[n][fin])), n   # ≤ 2 ulp per group, ≤ 5 overlapping groups
+        # ≤ 2 ulp per applied group; a later group whose total is a near-cancellation (t ≈ 0 from O(1) terms) amplifies
+        # those ulps, so the bound is scale-aware like the tendency metric: 1e-12 of max(|value|, magnitude of the inputs = 1)
+        assert np.all(np.abs(got[fin] - host[n][fin]) <= 1e-12 * np.maximum(np.abs(host[n][fin]), 1.0)), n
         full = got.copy()
         og.interior(full)[...] = og.interior(before[n])
         assert np.array_equal(full, before[n], equal_nan=True), n           # halos untouched
