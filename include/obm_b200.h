@@ -429,6 +429,59 @@ int obm_find_bottom_cells(const obm_grid* grid, const double* bottom_height_xy,
                           int64_t* bottom_indices_xy, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-1) Air–sea gas exchange — src/Models/GasExchange/: the `GasExchange` callable
+ * (gas_exchange.jl:26-38) evaluated for every surface column in one x–y launch:
+ *     flux[i,j] = k(u₁₀, T, S) · (water − air),
+ *     k = k₆₆₀(u₁₀) / √(Sc(T)/660) · solubility(T, S)          (gas_transfer_velocity.jl:32-33)
+ * with T, S (and every tracer) read at the top cell k = Nz.  Positive = out of the ocean
+ * (Oceananigans top-flux convention).  The result is the plain 2-D field Oceananigans reads as
+ * a flux boundary condition; if `G_top` is given the kernel also applies it to the tendency of
+ * the top cell, G[i,j,Nz] -= flux / Δzᶜ(Nz), which is what Oceananigans' `apply_z_bcs!` does
+ * with the boundary value.
+ * ------------------------------------------------------------------------------------ */
+enum {
+    OBM_GE_WATER_TRACER = 0, /* OxygenConcentration / any tracer: surface value, GasExchange.jl:37 */
+    OBM_GE_WATER_PCO2 = 1    /* CarbonDioxideConcentration: carbon-chemistry pCO₂ of the surface
+                                cell, carbon_dioxide_concentration.jl:48-60 */
+};
+enum {
+    OBM_GE_AIR_PLAIN = 0,        /* number / field as is, surface_values.jl:4,33-34 */
+    OBM_GE_AIR_WANNINKHOF92 = 1  /* PartiallySolubleGas: air · β(T,S)/Tk, gas_solubility.jl:24-49 */
+};
+enum {
+    OBM_GE_SOLUBILITY_ONE = 0,     /* default `(T, S) -> 1`, gas_transfer_velocity.jl:29 */
+    OBM_GE_SOLUBILITY_K0_RHO = 1   /* MolPerKgPerAtmToMMolPerCubicMPerMicroAtm: K0(T+273.15,S)·ρ(T,S)/10³,
+                                      gas_solubility.jl:65 (CO₂ default, GasExchange.jl:105-106) */
+};
+
+typedef struct obm_gas_exchange_params {
+    int32_t water_kind;      /* OBM_GE_WATER_*      */
+    int32_t air_kind;        /* OBM_GE_AIR_*        */
+    int32_t solubility_kind; /* OBM_GE_SOLUBILITY_* */
+    int32_t k660_order;      /* order (0…3) of the base transfer velocity polynomial in u₁₀ */
+    int32_t use_silicate_phosphate; /* 0: `nothing` → (0, 0); 1: fields if given else the two values below */
+    int32_t _pad;
+    double k660[4];          /* k₆₆₀ coefficients c₀…c₃ (Ho06: (0, 0, 0.266/hour/100)), gas_transfer_velocity.jl:52-135 */
+    double schmidt[5];       /* order-4 Schmidt-number polynomial in T °C, schmidt_number.jl:6-16 */
+    double w92[6];           /* A1 A2 A3 B1 B2 B3 of Wanninkhof92Solubility, gas_solubility.jl:46-47 */
+    double air_concentration; /* used when the air field is NULL (CO₂ default 413 ppmv, O₂ 9352.7 mmol/m³) */
+    double wind_speed;        /* used when the wind field is NULL (default 2 m/s) */
+    double silicate, phosphate; /* constant values (NamedTuple form), carbon_dioxide_concentration.jl:63 */
+    obm_carbchem_params carbon_chemistry;
+} obm_gas_exchange_params;
+
+/* T, S, tracer, DIC, Alk, silicate_f, phosphate_f: 3-D parents (surface level read).
+ * wind_speed_xy, air_concentration_xy: 2-D planes in parent x–y layout, or NULL → the scalars.
+ * tracer is needed for OBM_GE_WATER_TRACER, DIC/Alk for OBM_GE_WATER_PCO2.
+ * flux_xy (2-D plane) and/or G_top (3-D parent) receive the result; at least one is required. */
+int obm_gas_exchange_flux(const obm_grid* grid, const obm_gas_exchange_params* p,
+                          const double* T, const double* S, const double* tracer,
+                          const double* DIC, const double* Alk,
+                          const double* silicate_f, const double* phosphate_f,
+                          const double* wind_speed_xy, const double* air_concentration_xy,
+                          double* flux_xy, double* G_top, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
  * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
  * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics

@@ -19,6 +19,10 @@ from . import pisces
 from .pisces import PISCES, CBMDayLength, DepthDependantSinkingSpeed, PrescribedLatitude
 from .sediments import (BiogeochemicalSediment, InstantRemineralisation, InstantRemineralisationSediment, SimpleMultiG,
                         SimpleMultiGSediment, calculate_bottom_indices)
+from .gas_exchange import (CarbonDioxideConcentration, CarbonDioxideGasExchangeBoundaryCondition,
+                           CarbonDioxidePolynomialSchmidtNumber, GasExchange, GasExchangeBoundaryCondition,
+                           OxygenConcentration, OxygenGasExchangeBoundaryCondition, OxygenPolynomialSchmidtNumber,
+                           PartiallySolubleGas, PolynomialParameterisation, SchmidtScaledTransferVelocity)
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
 
 __version__ = "0.1.0"

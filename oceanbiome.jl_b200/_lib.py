@@ -184,7 +184,20 @@ class obm_sediment_fields(C.Structure):
                 ("G_coupled", C.c_void_p * OBM_SED_MAX_COUPLED)]
 
 
+class obm_gas_exchange_params(C.Structure):
+    _fields_ = ([(n, C.c_int32) for n in ("water_kind", "air_kind", "solubility_kind", "k660_order",
+                                          "use_silicate_phosphate", "_pad")]
+                + [("k660", C.c_double * 4), ("schmidt", C.c_double * 5), ("w92", C.c_double * 6)]
+                + [(n, C.c_double) for n in ("air_concentration", "wind_speed", "silicate", "phosphate")]
+                + [("carbon_chemistry", obm_carbchem_params)])
+
+
+OBM_GE_WATER_TRACER, OBM_GE_WATER_PCO2 = 0, 1
+OBM_GE_AIR_PLAIN, OBM_GE_AIR_WANNINKHOF92 = 0, 1
+OBM_GE_SOLUBILITY_ONE, OBM_GE_SOLUBILITY_K0_RHO = 0, 1
+
 STRUCTS = {
+    "obm_gas_exchange_params": obm_gas_exchange_params,
     "obm_sediment_params": obm_sediment_params,
     "obm_sediment_fields": obm_sediment_fields,
     "obm_pisces_phyto": obm_pisces_phyto,
@@ -227,6 +240,7 @@ PROTOTYPES = {
     "obm_sediment_update_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sediment_params),
                                                  C.POINTER(obm_sediment_fields), C.c_void_p]),
     "obm_find_bottom_cells": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_gas_exchange_flux": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_gas_exchange_params)] + [C.c_void_p] * 12),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
     "obm_last_error": (C.c_char_p, []),

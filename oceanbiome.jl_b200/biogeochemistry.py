@@ -120,8 +120,11 @@ class BiogeochemicalModel:
 
     RK3 = ((8 / 15, 0.0), (5 / 12, -17 / 60), (3 / 4, -5 / 12))  # (γⁿ, ζⁿ) of Oceananigans' RK3
 
-    def __init__(self, grid: RectilinearGrid, biogeochemistry, extra_tracers=(), timestepper="RungeKutta3"):
+    def __init__(self, grid: RectilinearGrid, biogeochemistry, extra_tracers=(), timestepper="RungeKutta3",
+                 boundary_conditions=None):
         self.grid = grid
+        # {tracer: top flux boundary condition} — e.g. DIC=CarbonDioxideGasExchangeBoundaryCondition()
+        self.boundary_conditions = dict(boundary_conditions or {})
         self.biogeochemistry = biogeochemistry
         self.clock = Clock()
         names = list(biogeochemistry.required_biogeochemical_tracers())
@@ -147,6 +150,8 @@ class BiogeochemicalModel:
         for g in self.Gn.values():
             g.data.zero_()
         self.biogeochemistry.update_tendencies(self)
+        for name, bc in self.boundary_conditions.items():
+            bc.apply_top(self, name)  # G[i, j, Nz] -= flux / Δz, as Oceananigans' apply_z_bcs! does
 
     def time_step(self, dt: float):
         if self.timestepper == "Euler":

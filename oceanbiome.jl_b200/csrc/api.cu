@@ -43,6 +43,7 @@ extern "C" int obm_sizeof(const char* name) {
     S(obm_pisces_fields);
     S(obm_sediment_params);
     S(obm_sediment_fields);
+    S(obm_gas_exchange_params);
 #undef S
     return OBM_EENUM;
 }

@@ -358,3 +358,47 @@ def sediment_point(params, pools, NO3, NH4, O2, fN, fC=0.0):
     nc = (4 if params.carbon else 3) if smg else 1
     return ([L.orc_sediment_pool_tendency(C.byref(params), pl, NO3, NH4, O2, fN, fC, n) for n in range(npool)],
             [L.orc_sediment_coupled_flux(C.byref(params), pl, NO3, NH4, O2, fN, fC, n) for n in range(nc)])
+
+
+# ---- gas exchange ---------------------------------------------------------------------------------------
+def gas_exchange_flux(grid: Grid, params, T, S, tracer=None, DIC=None, Alk=None, silicate=None, phosphate=None,
+                      wind_speed=None, air_concentration=None, G_top=None):
+    """→ flux plane (grid.plane_shape); G_top (3-D parent) is updated in place when given."""
+    arrs = [T, S, tracer, DIC, Alk, silicate, phosphate, wind_speed, air_concentration]
+    _check(arrs + [G_top])
+    flux = np.zeros(grid.plane_shape)
+    cg = grid.c_grid()
+    rc = lib().orc_gas_exchange_flux(C.byref(cg), C.byref(params), *[C.c_void_p(_ptr(a)) for a in arrs],
+                                     C.c_void_p(_ptr(flux)), C.c_void_p(_ptr(G_top)))
+    assert rc == 0
+    return flux
+
+
+def gas_exchange_point(params, T, S, tracer=0.0, DIC=0.0, Alk=0.0, silicate=0.0, phosphate=0.0, u10=None, air=None):
+    fn = lib().orc_gas_exchange_point
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_void_p] + [C.c_double] * 9
+    return fn(C.byref(params), T, S, tracer, DIC, Alk, silicate, phosphate,
+              params.wind_speed if u10 is None else u10, params.air_concentration if air is None else air)
+
+
+def polynomial(coefficients, x):
+    fn = lib().orc_polynomial
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_int, dp, C.c_double]
+    c = (C.c_double * len(coefficients))(*coefficients)
+    return fn(len(coefficients) - 1, c, x)
+
+
+def transfer_velocity(params, u10, T, S):
+    fn = lib().orc_transfer_velocity
+    fn.restype = C.c_double
+    fn.argtypes = [C.c_void_p] + [C.c_double] * 3
+    return fn(C.byref(params), u10, T, S)
+
+
+def w92_solubility(coefficients, T, S):
+    fn = lib().orc_w92_solubility
+    fn.restype = C.c_double
+    fn.argtypes = [dp, C.c_double, C.c_double]
+    return fn((C.c_double * 6)(*coefficients), T, S)
