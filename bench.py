@@ -231,11 +231,15 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
+def ncu_traffic(workload, cells):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch from the committed
+    `ncu --set full` capture (profiles/traffic.json), scaled to this run's cell count → (bytes | None, note)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
-        return json.load(open(p)).get(workload)
-    return None
+        d = json.load(open(p)).get(workload)
+        if d:
+            return d["bytes_per_launch"] * cells / d["cells"], f'{d["source"]}: {d["note"]}'
+    return None, None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -427,8 +431,9 @@ def main():
     peak, peak_src = measured_peaks()
     alg_bytes = w.tendency_bytes_per_cell * w.cells
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(name, w.cells)
     roofline = {"bound": "hbm", "kernel": w.step_kernels[-1] if w.step_kernels else None, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(name), "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": w.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
                 "kernel_share_of_step": kernel_ms / (ms / args.steps)}
     cpu = None

@@ -52,7 +52,10 @@ struct PiscesArgs {
 };
 
 constexpr double DAY = 86400.0;
-constexpr int PB = 128;   // threads per block
+#ifndef OBM_PISCES_BLOCK
+#define OBM_PISCES_BLOCK 128
+#endif
+constexpr int PB = OBM_PISCES_BLOCK;   // threads per block
 constexpr int NOUT = 24;  // tendencies staged in shared memory
 
 // ---- arithmetic policy -------------------------------------------------------------------------------
@@ -514,7 +517,12 @@ __device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long
     cell_tendencies<true>(a, in, out);
 }
 
-__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
+#ifdef OBM_PISCES_MAXNREG
+#define OBM_PISCES_BOUNDS __maxnreg__(OBM_PISCES_MAXNREG)
+#else
+#define OBM_PISCES_BOUNDS __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS)
+#endif
+__global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
     __shared__ double sm[NOUT * PB];
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
