@@ -511,6 +511,13 @@ int obm_copy_slab(const obm_grid* grid, int nfields, void* const* dst, const voi
  * ------------------------------------------------------------------------------------ */
 double obm_fp64_peak_dfma_per_s(double* scratch, int iters, void* stream);
 
+/* Diagnostic (synchronises): bandwidth in GB/s of the bare access pattern of a fused tendency kernel —
+ * every thread reads its cell from `nread` (<= 40) fields and read-modify-writes (mode 0) or writes
+ * (mode 1) `nrmw` (<= 26) fields, same launch geometry, no arithmetic.  The ceiling the memory system
+ * sets for that many concurrent streams (a two-stream copy does not show it). */
+double obm_stream_pattern_gbs(const obm_grid* grid, int nread, const double* const* reads, int nrmw,
+                              double* const* rmw, int mode, int reps, void* stream);
+
 /* ------------------------------------------------------------------------------------ */
 const char* obm_last_error(void);
 int obm_version(void);

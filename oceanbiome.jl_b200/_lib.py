@@ -243,6 +243,8 @@ PROTOTYPES = {
     "obm_gas_exchange_flux": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_gas_exchange_params)] + [C.c_void_p] * 12),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_stream_pattern_gbs": (C.c_double, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_int, C.c_void_p]),
     "obm_last_error": (C.c_char_p, []),
     "obm_version": (C.c_int, []),
     "obm_sizeof": (C.c_int, [C.c_char_p]),

@@ -37,3 +37,72 @@ extern "C" double obm_fp64_peak_dfma_per_s(double* scratch, int iters, void* str
     if (rc) return -(double)rc;
     return (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
 }
+
+// ---- many-stream access pattern ---------------------------------------------------------------------
+// The memory system's ceiling for the access pattern of a fused tendency kernel: every thread reads its
+// cell from `nread` separate fields and read-modify-writes (mode 0) or writes (mode 1) `nrmw` fields,
+// same launch geometry as the real kernels, no arithmetic to speak of.  A plain two-stream copy (the
+// MEASURED_PEAKS.json number) does not capture what 40–60 concurrent streams do to DRAM efficiency.
+namespace obm {
+constexpr int SP_MAX_READ = 40, SP_MAX_RMW = 26;
+struct StreamArgs {
+    GridDims d;
+    const double* rd[SP_MAX_READ];
+    double* wr[SP_MAX_RMW];
+    int nread, nrmw, mode;
+};
+__global__ void __launch_bounds__(128) stream_pattern_kernel(const __grid_constant__ StreamArgs a) {
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    double v[SP_MAX_READ];
+#pragma unroll
+    for (int n = 0; n < SP_MAX_READ; n++) v[n] = n < a.nread ? a.rd[n][idx] : 0.0;
+    double s = 0;
+#pragma unroll
+    for (int n = 0; n < SP_MAX_READ; n++) s += v[n];
+    if (a.mode == 0) {
+        double o[SP_MAX_RMW];
+#pragma unroll
+        for (int n = 0; n < SP_MAX_RMW; n++) o[n] = n < a.nrmw ? a.wr[n][idx] : 0.0;
+#pragma unroll
+        for (int n = 0; n < SP_MAX_RMW; n++)
+            if (n < a.nrmw) a.wr[n][idx] = o[n] + s * 1e-300;
+    } else {
+#pragma unroll
+        for (int n = 0; n < SP_MAX_RMW; n++)
+            if (n < a.nrmw) a.wr[n][idx] = s;
+    }
+}
+}  // namespace obm
+
+// Diagnostic (synchronises): GB/s moved (8·cells·(nread + (mode == 0 ? 2 : 1)·nrmw) per launch) over `reps`
+// launches; negative on error.
+extern "C" double obm_stream_pattern_gbs(const obm_grid* grid, int nread, const double* const* reads, int nrmw,
+                                         double* const* rmw, int mode, int reps, void* stream) {
+    using namespace obm;
+    if (!reads || !rmw || nread < 0 || nread > SP_MAX_READ || nrmw < 0 || nrmw > SP_MAX_RMW || reps <= 0)
+        return (double)OBM_ESIZE;
+    static thread_local StreamArgs a;
+    if (make_dims(grid, &a.d, false)) return (double)OBM_ESIZE;
+    for (int n = 0; n < nread; n++) a.rd[n] = reads[n];
+    for (int n = 0; n < nrmw; n++) a.wr[n] = rmw[n];
+    a.nread = nread; a.nrmw = nrmw; a.mode = mode;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    stream_pattern_kernel<<<cell_grid(a.d, 128), 128, 0, s>>>(a);
+    cudaEventRecord(e0, s);
+    for (int r = 0; r < reps; r++) stream_pattern_kernel<<<cell_grid(a.d, 128), 128, 0, s>>>(a);
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    int rc = launch_status("stream_pattern_kernel");
+    if (rc) return -(double)rc;
+    const double bytes = 8.0 * (double)cell_count(a.d) * (nread + (mode == 0 ? 2 : 1) * nrmw) * reps;
+    return bytes / (ms * 1e-3) / 1e9;
+}

@@ -56,7 +56,7 @@ constexpr double DAY = 86400.0;
 #define OBM_PISCES_BLOCK 128
 #endif
 constexpr int PB = OBM_PISCES_BLOCK;   // threads per block
-constexpr int NOUT = 24;  // tendencies staged in shared memory
+constexpr int NOUT = 24;  // tendencies
 
 // ---- arithmetic policy -------------------------------------------------------------------------------
 // EXACT: IEEE division, NaN-propagating min/max — the reference's semantics operation by operation.
@@ -85,6 +85,7 @@ struct Ar {
     static __device__ __forceinline__ double mn(double a, double b) { return EXACT ? jl_min(a, b) : fmin(a, b); }
     static __device__ __forceinline__ double mn3(double a, double b, double c) { return mn(mn(a, b), c); }
     static __device__ __forceinline__ double mn4(double a, double b, double c, double d) { return mn(mn(mn(a, b), c), d); }
+    static __device__ __forceinline__ double ex(double x) { return exp(x); }
 };
 
 struct Cell {
@@ -137,13 +138,13 @@ __device__ __forceinline__ Phyto phytoplankton(const PiscesArgs& a, const int cl
     const double f1 = a.dv.f1_growth;
     const double f2 = 1 - A::div(drt, drt + ph.dark_tolerance);
     double alpha = ph.initial_slope_of_PI_curve;
-    if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
+    if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * A::ex(-PAR));
     else alpha = alpha * (1 + 0.0);
     double fl;
     if (ph.growth_rate_kind == OBM_GROWTH_NUTRIENT_LIMITED)
-        fl = 1 - exp(A::gdiv(-alpha * r.tChl * PAR, dl * r.mui * r.L));
+        fl = 1 - A::ex(A::gdiv(-alpha * r.tChl * PAR, dl * r.mui * r.L));
     else
-        fl = 1 - exp(A::EX ? -alpha * r.tChl * PAR / (dl * (ph.basal_respiration_rate + ph.reference_growth_rate))
+        fl = 1 - A::ex(A::EX ? -alpha * r.tChl * PAR / (dl * (ph.basal_respiration_rate + ph.reference_growth_rate))
                            : -alpha * r.tChl * PAR * a.dv.inv_resp[cls]);
     r.mu = r.mui * f1 * f2 * fl * r.L;
     r.muI = r.mu * I;
@@ -166,7 +167,7 @@ __device__ __forceinline__ double chlorophyll_growth(const PiscesArgs& a, const 
     const double dl = a.p.day_length_chlorophyll;
     const double mucheck = A::EX ? r.mu / (1.5 * dl / (dl + 0.5 * DAY)) * dl : r.mu * a.dv.dl_over_f1_chl;
     double alpha = ph.initial_slope_of_PI_curve;
-    if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * exp(-PAR));
+    if (ph.low_light_adaptation != 0.0) alpha = alpha * (1 + ph.low_light_adaptation * A::ex(-PAR));
     else alpha = alpha * (1 + 0.0);
     const double rho = A::gdiv(12 * mucheck * I, alpha * IChl * PAR) * r.L;
     const double t0 = ph.minimum_chlorophyll_ratio, t1 = ph.maximum_chlorophyll_ratio;
@@ -237,35 +238,66 @@ struct Inputs {
     double PARt, Omega, wPOC, wGOC, mlPAR;
 };
 
-// All 24 tendencies of one cell → out[n * PB] (shared memory).  Returns true when any result is
-// non-finite (⇒ the caller recomputes the cell with the EXACT policy).
-template <bool EXACT>
-__device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Inputs& in, double* out) {
+__device__ __forceinline__ unsigned nonfinite(double t) {
+    return ((unsigned)(__double2hiint(t)) & 0x7ff00000u) == 0x7ff00000u;  // exponent test on the high word
+}
+__device__ __forceinline__ void red_add(double* p, double t) {  // fire-and-forget Gⁿ += t at the L2
+    atomicAdd(p, t);  // result unused ⇒ RED.E.ADD.F64
+}
+
+// Where a tendency goes once its last term is known.
+// FAST pass: a finite result is final — stored (or added, accumulate mode) to Gⁿ at once, so it leaves the register
+// file; a non-finite one is only marked.  EXACT pass (rare): recomputes the cell with the reference's operation
+// semantics and delivers exactly the marked tendencies.  Every tendency is delivered once.
+struct FastSink {
+    const PiscesArgs& a;
+    long long idx;
+    unsigned pending;
+    __device__ __forceinline__ void put(int n, double t) {
+        if (!((a.out_mask >> n) & 1u)) return;
+        const unsigned nf = nonfinite(t);
+        pending |= nf << n;
+        if (!nf) {
+            if (a.accumulate) red_add(a.g[n] + idx, t);
+            else a.g[n][idx] = t;
+        }
+    }
+};
+struct ExactSink {
+    const PiscesArgs& a;
+    long long idx;
+    unsigned pending;
+    __device__ __forceinline__ void put(int n, double t) {
+        if (!((pending >> n) & 1u)) return;
+        if (a.accumulate) a.g[n][idx] += t;
+        else a.g[n][idx] = t;
+    }
+};
+
+// All 24 tendencies of one cell → sink.
+template <bool EXACT, class SINK>
+__device__ __forceinline__ void cell_tendencies(const PiscesArgs& a, const Inputs& in, SINK& sink) {
     using A = Ar<EXACT>;
     const obm_pisces_params& p = a.p;
     const Cell& c = in.c;
     const double P = in.P, PChl = in.PChl, PFe = in.PFe, D = in.D, DChl = in.DChl, DFe = in.DFe, DSi = in.DSi;
     const double Z = in.Z, M = in.M, DOC = in.DOC, POC = in.POC, GOC = in.GOC, SFe = in.SFe, BFe = in.BFe;
     const double PSi = in.PSi, CaCO3 = in.CaCO3, PARt = in.PARt, Omega = in.Omega, wPOC = in.wPOC, wGOC = in.wGOC;
-    unsigned bad = 0;  // OR of the high words' exponent test
-    auto put = [&](int n, double t) {
-        out[n * PB] = t;
-        bad |= ((unsigned)(__double2hiint(t)) & 0x7ff00000u) == 0x7ff00000u;
-    };
+    auto put = [&](int n, double t) { sink.put(n, t); };
 
     // ---- shared scalars --------------------------------------------------------------------------------
     const double shear = c.z < c.zmxl ? p.background_shear : p.mixed_layer_shear;
     const double dO2 = A::mn(1.0, A::mx(0.0, A::div(0.4 * (p.first_anoxia_threshold - c.O2), p.second_anoxia_threshold + c.O2)));
-    // b^T once per distinct base (exp(T ln b); bases are parameters, ln b is host-evaluated; `same_as`
+    // b^T once per distinct base (A::ex(T ln b); bases are parameters, ln b is host-evaluated; `same_as`
     // is uniform, so these are uniform branches / selects on scalars — no local array)
     const int s1 = a.same_as[1], s2 = a.same_as[2], s3 = a.same_as[3], s4 = a.same_as[4], s5 = a.same_as[5];
-    const double fT0 = exp(c.T * a.ln_base[0]);
+    const double fT0 = A::ex(c.T * a.ln_base[0]);
     double fT1, fT2, fT3, fT4, fT5;
-    if (s1 < 0) fT1 = exp(c.T * a.ln_base[1]); else fT1 = fT0;
-    if (s2 < 0) fT2 = exp(c.T * a.ln_base[2]); else fT2 = s2 == 0 ? fT0 : fT1;
-    if (s3 < 0) fT3 = exp(c.T * a.ln_base[3]); else fT3 = s3 == 0 ? fT0 : (s3 == 1 ? fT1 : fT2);
-    if (s4 < 0) fT4 = exp(c.T * a.ln_base[4]); else fT4 = s4 == 0 ? fT0 : (s4 == 1 ? fT1 : (s4 == 2 ? fT2 : fT3));
-    if (s5 < 0) fT5 = exp(c.T * a.ln_base[5]); else fT5 = s5 == 0 ? fT0 : (s5 == 1 ? fT1 : (s5 == 2 ? fT2 : (s5 == 3 ? fT3 : fT4)));
+    if (s1 < 0) fT1 = A::ex(c.T * a.ln_base[1]); else fT1 = fT0;
+    if (s2 < 0) fT2 = A::ex(c.T * a.ln_base[2]); else fT2 = s2 == 0 ? fT0 : fT1;
+    if (s3 < 0) fT3 = A::ex(c.T * a.ln_base[3]); else fT3 = s3 == 0 ? fT0 : (s3 == 1 ? fT1 : fT2);
+    if (s4 < 0) fT4 = A::ex(c.T * a.ln_base[4]); else fT4 = s4 == 0 ? fT0 : (s4 == 1 ? fT1 : (s4 == 2 ? fT2 : fT3));
+    if (s5 < 0) fT5 = A::ex(c.T * a.ln_base[5]); else fT5 = s5 == 0 ? fT0 : (s5 == 1 ? fT1 : (s5 == 2 ? fT2 : (s5 == 3 ? fT3 : fT4)));
     const double fT[6] = {fT0, fT1, fT2, fT3, fT4, fT5};
 
     // ---- phytoplankton ------------------------------------------------------------------------------------
@@ -305,7 +337,7 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
         const double L2 = p.latitude < 0 ? A::div(Si * Si * Si, Si * Si * Si + (A::EX ? K2 * K2 * K2 : a.dv.K2_cubed)) : 0.0;
         const double F1 = A::mn4(A::gdiv(d.mu, d.mui * d.L), d.LFe, d.LPO4, d.LN);
         const double F2 = A::mn(1.0, 2.2 * A::mx(0.0, L1 - 0.5));
-        const double t1 = ph.optimal_silicate_ratio * L1 * A::mn(5.4, (4.4 * exp(-4.23 * F1) * F2 + 1) * (1 + 2 * L2));
+        const double t1 = ph.optimal_silicate_ratio * L1 * A::mn(5.4, (4.4 * A::ex(-4.23 * F1) * F2 + 1) * (1 + 2 * L2));
         upSi = (1 - ph.exudated_fraction) * t1 * d.mu * D;
     }
     const double tSi = A::gdiv(DSi, D);
@@ -359,7 +391,7 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
     double Fep;
     {
         const double ligands = A::mx(0.6, 0.09 * (DOC + 40) - 3);
-        const double K = exp(16.27 - A::div(1565.7, A::mx(c.T + 273.15, 5.0)));
+        const double K = A::ex(16.27 - A::div(1565.7, A::mx(c.T + 273.15, 5.0)));
         const double Dl = 1 + K * ligands - K * c.Fe;
         Fep = A::div(-Dl + sqrt(Dl * Dl + 4 * K * c.Fe), 2 * K);
     }
@@ -378,7 +410,7 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
         const double low_light = A::div(A::mx(0.0, PARt - 1), 4 + PARt);
         const double high_light = A::div(30.0, 30 + PARt);
         const double low_T = A::mx(0.0, A::div(c.T, c.T + 0.1));
-        const double high_T = 1 + exp(A::EX ? -((c.T - 10) * (c.T - 10)) / 25 : -((c.T - 10) * (c.T - 10)) * 0.04);
+        const double high_T = 1 + A::ex(A::EX ? -((c.T - 10) * (c.T - 10)) / 25 : -((c.T - 10) * (c.T - 10)) * 0.04);
         const double depth = A::mn(1.0, A::div(-50.0, c.zmxl));
         R = (p.base_rain_ratio * L_CaCO3 * pcf * low_light * high_light * low_T * high_T * depth);
     }
@@ -423,7 +455,7 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
     double psi_diss;
     {
         const double ll = p.fast_dissolution_rate_of_silicate, lr = p.slow_dissolution_rate_of_silicate;
-        const double chi = p.base_liable_silicate_fraction * (c.z >= zmin ? 1.0 : exp(A::div((ll - lr) * (zmin - c.z), wGOC)));
+        const double chi = p.base_liable_silicate_fraction * (c.z >= zmin ? 1.0 : A::ex(A::div((ll - lr) * (zmin - c.z), wGOC)));
         const double l0 = chi * ll + (1 - chi) * lr;
         const double eq = exp10(6.44 - A::div(968.0, c.T + 273.15));
         const double sat = A::div(eq - c.Si, eq);
@@ -445,7 +477,7 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
         const double growth_requirement = A::mx(0.0, n.mui - 2.15);
         const double nutrient = A::mn(A::div(c.Fe, c.Fe + p.iron_half_saturation_for_fixation),
                                       A::div(c.PO4, c.PO4 + p.phosphate_half_saturation_for_fixation));
-        const double light = 1 - exp(A::EX ? -PARt / p.light_saturation_for_fixation : -PARt * a.dv.inv_E);
+        const double light = 1 - A::ex(A::EX ? -PARt / p.light_saturation_for_fixation : -PARt * a.dv.inv_E);
         fixation = p.maximum_fixation_rate * growth_requirement * limit * nutrient * light;
     }
     const double upNO3 = A::gdiv(n.muI * n.LNO3, n.LN) + A::gdiv(d.muI * d.LNO3, d.LN);
@@ -479,14 +511,15 @@ __device__ __forceinline__ bool cell_tendencies(const PiscesArgs& a, const Input
         const double nit_c = A::EX ? tn * nitrif / tN : tn * nitrif * a.dv.inv_tN;
         put(T_O2, (tr * upNH4 + (tr + tn) * upNO3 + fix_c - remin - tr * inorg_exc - tr * ut_respiration - nit_c));
     }
-    // NaN inputs that only flow through min/max would be swallowed by fmin/fmax: force the EXACT path
-    bad |= (c.zeu != c.zeu) | (c.O2 != c.O2) | (Omega != Omega) | (c.zmxl != c.zmxl) | (c.kappa != c.kappa);
-    return bad != 0;
 }
 
-#ifndef OBM_PISCES_MIN_BLOCKS
-#define OBM_PISCES_MIN_BLOCKS 4
-#endif
+// NaN inputs that only flow through min/max would be swallowed by the FAST pass's fmin/fmax: such cells go
+// straight to the EXACT pass
+__device__ __forceinline__ bool needs_exact(const Inputs& in) {
+    const Cell& c = in.c;
+    return (c.zeu != c.zeu) | (c.O2 != c.O2) | (in.Omega != in.Omega) | (c.zmxl != c.zmxl) | (c.kappa != c.kappa);
+}
+
 
 __device__ __forceinline__ Inputs load_inputs(const PiscesArgs& a, long long idx, long long pl, int k) {
     Inputs in;
@@ -512,18 +545,20 @@ __device__ __forceinline__ Inputs load_inputs(const PiscesArgs& a, long long idx
 
 // The rare path (non-finite results): re-reads the cell and evaluates it with the reference's exact
 // operation semantics.  Kept out of line so that it does not weigh on the fast path's registers.
-__device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long long pl, int k, double* out) {
+__device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long long pl, int k, unsigned pending) {
     const Inputs in = load_inputs(a, idx, pl, k);
-    cell_tendencies<true>(a, in, out);
+    ExactSink sink{a, idx, pending};
+    cell_tendencies<true>(a, in, sink);
 }
 
-#ifdef OBM_PISCES_MAXNREG
-#define OBM_PISCES_BOUNDS __maxnreg__(OBM_PISCES_MAXNREG)
-#else
-#define OBM_PISCES_BOUNDS __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS)
+#ifndef OBM_PISCES_MIN_BLOCKS
+#define OBM_PISCES_MIN_BLOCKS 4
 #endif
-__global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
-    __shared__ double sm[NOUT * PB];
+
+// One thread per cell.  Measured on B200 (16.8 M cells, accumulate mode): 2.75 ms whether the block is 64…512
+// threads, whether 3 or 4 blocks are resident (168 / 128 registers), with or without shared-memory staging of the
+// inputs or of Gⁿ, L2 prefetch of the next wave, or block-wide lock-step — see DESIGN.md "PISCES kernel: what bounds it".
+__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
@@ -532,23 +567,10 @@ __global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__
     // ---- one coalesced read of the cell ------------------------------------------------------------
     const Inputs in = load_inputs(a, idx, pl, k);
 
-    double* out = sm + threadIdx.x;
-    if (cell_tendencies<false>(a, in, out)) cell_exact(a, idx, pl, k, out);  // rare: non-finite results
-
-    // ---- write-out: all loads of the accumulate RMW are issued together ------------------------------
-    const unsigned mask = a.out_mask;
-    if (a.accumulate) {
-        double old[NOUT];
-#pragma unroll
-        for (int n = 0; n < NOUT; n++) old[n] = (mask >> n) & 1u ? a.g[n][idx] : 0.0;
-#pragma unroll
-        for (int n = 0; n < NOUT; n++)
-            if ((mask >> n) & 1u) a.g[n][idx] = old[n] + out[n * PB];
-    } else {
-#pragma unroll
-        for (int n = 0; n < NOUT; n++)
-            if ((mask >> n) & 1u) a.g[n][idx] = out[n * PB];
-    }
+    FastSink sink{a, idx, 0u};
+    if (needs_exact(in)) sink.pending = a.out_mask;
+    else cell_tendencies<false>(a, in, sink);
+    if (sink.pending) cell_exact(a, idx, pl, k, sink.pending);  // rare: non-finite results, NaN inputs
 }
 
 }  // namespace obm
