@@ -199,6 +199,8 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self.stop_flag = index, [], False
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
@@ -208,6 +210,31 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.1)
+
+    def _run_nvml(self):
+        """Same quantities through NVML (≈ 5 ms per sample instead of ≈ 100 ms per nvidia-smi process)."""
+        try:
+            import pynvml as N
+            import torch
+            N.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            h = N.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode() if not uuid.startswith("GPU-") else uuid.encode())
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        act = lambda bit: "Active" if bit else "Not Active"  # noqa: E731
+        while not self.stop_flag:
+            try:
+                r = reasons(h)
+                self.samples.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx),
+                                     str(N.nvmlDeviceGetPowerUsage(h) / 1000.0), act(r & 0x8), act(r & 0x40), act(r & 0x20),
+                                     act(r & 0x4)])
+            except Exception:
+                pass
+            time.sleep(0.01)
+        return True
 
     def summary(self):
         if not self.samples:

@@ -482,6 +482,18 @@ int obm_gas_exchange_flux(const obm_grid* grid, const obm_gas_exchange_params* p
                           double* flux_xy, double* G_top, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-2 / f-3) The tracer update either side of the tendency pass, every tracer in one launch:
+ *     U[f] += Δt·(γ·Gⁿ[f] + ζ·G⁻[f])   (has_zeta = 0, the first stage: U[f] += Δt·γ·Gⁿ[f])
+ *     G⁻[f] ← Gⁿ[f]                     (cache_previous != 0)
+ * `rk3_substep!` src/BoxModel/timesteppers.jl:66-93 and `cache_previous_tendencies!` :20-28 (the
+ * box model's copies of Oceananigans' per-tracer launches); γ = 1, has_zeta = 0 is forward Euler.
+ * U, Gn, Gm: host tables of nfields device parents.  Operation order as written (no FMA).
+ * ------------------------------------------------------------------------------------ */
+int obm_rk3_substep(const obm_grid* grid, int nfields, double* const* U, const double* const* Gn,
+                    double* const* Gm, double dt, double gamma, double zeta, int has_zeta,
+                    int cache_previous, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
  * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
  * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics

@@ -24,5 +24,6 @@ from .gas_exchange import (CarbonDioxideConcentration, CarbonDioxideGasExchangeB
                            OxygenConcentration, OxygenGasExchangeBoundaryCondition, OxygenPolynomialSchmidtNumber,
                            PartiallySolubleGas, PolynomialParameterisation, SchmidtScaledTransferVelocity)
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
+from .box_model import BoxModel, BoxModelGrid
 
 __version__ = "0.1.0"

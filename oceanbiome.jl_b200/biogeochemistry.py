@@ -10,9 +10,12 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Optional
 
+import ctypes as C
+
 import torch
 
-from .grids import CenterField, Field, RectilinearGrid
+from . import _lib
+from .grids import CenterField, Field, RectilinearGrid, current_stream_ptr
 from .negative_tracers import ScaleNegativeTracers, apply_scalers
 
 
@@ -153,12 +156,22 @@ class BiogeochemicalModel:
         for name, bc in self.boundary_conditions.items():
             bc.apply_top(self, name)  # G[i, j, Nz] -= flux / Δz, as Oceananigans' apply_z_bcs! does
 
+    def _substep(self, dt, gamma, zeta):
+        """U += Δt(γGⁿ + ζG⁻), G⁻ ← Gⁿ for every tracer in one launch (csrc/timestepping.cu)."""
+        names = list(self.tracers)
+        tab = lambda d: _lib.pointer_table([d[n].ptr for n in names])  # noqa: E731
+        cg = self.grid.c_grid()
+        rc = _lib.load().obm_rk3_substep(C.byref(cg), len(names), tab(self.tracers), tab(self.Gn),
+                                         tab(self.Gm) if self.Gm is not None else None, float(dt), float(gamma),
+                                         float(zeta or 0.0), int(bool(zeta)), int(self.Gm is not None),
+                                         current_stream_ptr(self.grid.device))
+        _lib.check(rc, "obm_rk3_substep")
+
     def time_step(self, dt: float):
         if self.timestepper == "Euler":
             self.update_state()
             self.compute_tendencies()
-            for n, c in self.tracers.items():
-                c.data.add_(self.Gn[n].data, alpha=dt)
+            self._substep(dt, 1.0, None)
             self.clock.time += dt
             self.clock.last_stage_dt = dt
         else:
@@ -168,11 +181,7 @@ class BiogeochemicalModel:
                 self.clock.rk3_gamma, self.clock.rk3_zeta = gamma, (zeta if zeta else float("nan"))
                 self.update_state()
                 self.compute_tendencies()
-                for n, c in self.tracers.items():
-                    c.data.add_(self.Gn[n].data, alpha=dt * gamma)
-                    if zeta:
-                        c.data.add_(self.Gm[n].data, alpha=dt * zeta)
-                    self.Gm[n].data.copy_(self.Gn[n].data)
+                self._substep(dt, gamma, zeta)
                 self.clock.time += dt * (gamma + zeta)
                 self.clock.last_stage_dt = dt * (gamma + zeta)
         self.clock.iteration += 1

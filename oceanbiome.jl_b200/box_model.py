@@ -1,0 +1,239 @@
+"""`BoxModel` — host-side mirror of src/BoxModel/boxmodel.jl:35-160 and timesteppers.jl:1-95, re-designed as a
+device-resident ENSEMBLE driver.
+
+The reference integrates one 0-D box at a time on the CPU (`BoxModelGrid()` = a `(Flat, Flat, Flat)` grid,
+≈ 8 µs per RK stage, benchmark/box_model.jl:67).  Here `BoxModelGrid(n)` is n independent boxes laid along x, and
+one time step is a handful of launches whatever n is: the same fused kernels as the 3-D models evaluate all
+tendencies of all boxes (`update_biogeochemical_state`, `update_tendencies`), `obm_rk3_substep` updates every
+tracer and caches G⁻ in one launch, and — when nothing but the tabulated time series depends on time — the whole
+step is captured once in a CUDA graph and replayed (`run(..., graph=True)`), so parameter / initial-condition
+sweeps and calibration ensembles run entirely on the device.
+
+Same keyword surface as the reference: `BoxModel(biogeochemistry=…, grid=…, forcing=…, timestepper=…,
+clock=…, prescribed_tracers=…)`, `set(model, **values)` (`set!`), `time_step(Δt)` (`time_step!`), `run` (`run!`).
+`forcing[name]` and `prescribed_tracers[name]` are functions of time `f(t)` (numbers or per-box tensors).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .biogeochemistry import Clock
+from .grids import CenterField, Field, RectilinearGrid, current_stream_ptr
+
+
+def BoxModelGrid(n: int = 1, device="cuda") -> RectilinearGrid:
+    """`BoxModelGrid()` (src/OceanBioME.jl:171) for `n` independent boxes: x is the ensemble axis, y and z are Flat
+    (the single level spans z ∈ [−1, 0] so that kernels reading z see a finite node)."""
+    return RectilinearGrid(size=(int(n),), x=(0.0, float(n)), topology=("Periodic", "Flat", "Flat"), halo=(0,),
+                           device=device)
+
+
+class BoxModel:
+    """`BoxModel(; biogeochemistry, grid, forcing, timestepper, clock, prescribed_tracers)` — boxmodel.jl:35-90."""
+
+    RK3 = ((8 / 15, None), (5 / 12, -17 / 60), (3 / 4, -5 / 12))  # (γⁿ, ζⁿ), Oceananigans' RungeKutta3TimeStepper
+
+    def __init__(self, biogeochemistry, grid: Optional[RectilinearGrid] = None, forcing: Optional[dict] = None,
+                 timestepper: str = "RungeKutta3", clock: Optional[Clock] = None,
+                 prescribed_tracers: Optional[Dict[str, Callable]] = None):
+        self.biogeochemistry = biogeochemistry
+        self.grid = grid if grid is not None else BoxModelGrid()
+        self.clock = clock or Clock()
+        self.prescribed_tracers = dict(prescribed_tracers or {})
+        names = list(biogeochemistry.required_biogeochemical_tracers())
+        aux = biogeochemistry.biogeochemical_auxiliary_fields()
+        # a prescribed name is a tracer (e.g. T) or an auxiliary field the biogeochemistry reads (e.g. PAR)
+        names += [n for n in self.prescribed_tracers if n not in names and n not in aux]
+        self.fields = {n: CenterField(self.grid, n) for n in names}
+        self.forcing = {n: (forcing or {}).get(n) for n in names}
+        unknown = set(forcing or {}) - set(names)
+        if unknown:
+            raise ValueError(f"forcing for unknown tracers {sorted(unknown)}")
+        if timestepper not in ("RungeKutta3", "Euler"):
+            raise ValueError("timestepper must be 'RungeKutta3' or 'Euler'")
+        self.timestepper = timestepper
+        # prognostic = everything the biogeochemistry steps; prescribed tracers are overwritten every stage
+        self.prognostic = [n for n in names if n not in self.prescribed_tracers]
+        self.Gn = {n: CenterField(self.grid, "Gⁿ" + n) for n in names}
+        self.Gm = {n: CenterField(self.grid, "G⁻" + n) for n in names}
+        self._tables = None
+        self._graph = None
+        self._needs_initial_update = True
+
+    # the hooks read `model.tracers` (an Oceananigans model's NamedTuple of tracer fields)
+    @property
+    def tracers(self):
+        return self.fields
+
+    @property
+    def auxiliary_fields(self):
+        return self.biogeochemistry.biogeochemical_auxiliary_fields()
+
+    def set(self, **values):
+        """`set!(model; kwargs...)` — boxmodel.jl:131-141 (scalars or one value per box)."""
+        for n, v in values.items():
+            if n not in self.fields:
+                raise ValueError(f"name {n} not found in model.fields.")
+            self.fields[n].set(v)
+        self._needs_initial_update = True
+        return self
+
+    # ---- update_state!(model) — boxmodel.jl:92-110 ---------------------------------------------------------
+    def _prescribed_target(self, n) -> Field:
+        return self.fields[n] if n in self.fields else self.auxiliary_fields[n]
+
+    def _apply_prescribed(self, t):
+        for n, f in self.prescribed_tracers.items():
+            self._prescribed_target(n).set(f(t))
+
+    def update_state(self, compute_tendencies: bool = True):
+        self._apply_prescribed(self.clock.time)
+        self.biogeochemistry.update_biogeochemical_state(self)
+        if compute_tendencies:
+            self.compute_tendencies()
+
+    # ---- compute_tendencies!(model) — timesteppers.jl:30-55 --------------------------------------------------
+    def compute_tendencies(self):
+        for n in self.prognostic:
+            f = self.forcing.get(n)
+            if f is None:
+                self.Gn[n].data.zero_()  # the per-point callable returns zero(grid), `no_func` forcing
+            else:
+                self.Gn[n].set(f(self.clock.time))
+        self.biogeochemistry.update_tendencies(self)
+
+    # ---- rk3_substep! + cache_previous_tendencies! in one launch — timesteppers.jl:20-28,66-93 -------------------
+    def _substep(self, dt, gamma, zeta, stream=None):
+        names = self.prognostic
+        U = _lib.pointer_table([self.fields[n].ptr for n in names])
+        Gn = _lib.pointer_table([self.Gn[n].ptr for n in names])
+        Gm = _lib.pointer_table([self.Gm[n].ptr for n in names])
+        cg = self.grid.c_grid()
+        s = stream if stream is not None else current_stream_ptr(self.grid.device)
+        rc = _lib.load().obm_rk3_substep(C.byref(cg), len(names), U, Gn, Gm, float(dt), float(gamma),
+                                         0.0 if zeta is None else float(zeta), int(zeta is not None), 1, s)
+        _lib.check(rc, "obm_rk3_substep")
+
+    def time_step(self, dt: float):
+        """`time_step!(model, Δt)`: Oceananigans' RK3 (or forward Euler) over the box-model methods above."""
+        if self._needs_initial_update:  # what `run!` / the first `time_step!` do at iteration 0
+            self.update_state()
+            self._needs_initial_update = False
+        stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
+        for gamma, zeta in stages:
+            self.clock.rk3_gamma, self.clock.rk3_zeta = gamma, (zeta if zeta is not None else float("nan"))
+            self._substep(dt, gamma, zeta)
+            stage_dt = dt * (gamma + (zeta or 0.0))
+            self.clock.time += stage_dt
+            self.clock.last_stage_dt = stage_dt
+            self.update_state()
+        self.clock.iteration += 1
+
+    # ---- run!(simulation) --------------------------------------------------------------------------------------
+    def run(self, dt: float, steps: int, graph: bool = False, output_every: int = 0, output_names=None):
+        """Integrate `steps` time steps.  Returns a dict name → tensor (n_outputs, n_boxes) of snapshots taken
+        every `output_every` steps (device-resident; the reference's `SpeedyOutput` keeps them on the host).
+
+        `graph=True`: prescribed tracers and forcings are tabulated for every stage of the run, uploaded once,
+        and ONE captured time step is replayed `steps` times; requires a biogeochemistry whose kernel parameters do
+        not depend on the clock (NPZD / LOBSTER family with prescribed or computed PAR)."""
+        names = list(output_names or self.prognostic)
+        nout = steps // output_every if output_every else 0
+        out = {n: torch.empty((nout, self.grid.Nx), dtype=torch.float64, device=self.grid.device) for n in names}
+        if not graph:
+            for it in range(steps):
+                self.time_step(dt)
+                if output_every and (it + 1) % output_every == 0:
+                    for n in names:
+                        out[n][(it + 1) // output_every - 1].copy_(self.fields[n].interior.reshape(-1))
+            return out
+        return self._run_graph(dt, steps, output_every, names, out)
+
+    # .. graph mode ...............................................................................................
+    def _tabulate(self, dt, steps):
+        """Stage times of the whole run and the time series evaluated at them: row r = step·nstages + stage holds the
+        values `update_state!` sees after that stage's substep."""
+        stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
+        t, times = self.clock.time, []
+        for _ in range(steps):
+            for gamma, zeta in stages:
+                t += dt * (gamma + (zeta or 0.0))
+                times.append(t)
+        dev, nx = self.grid.device, self.grid.Nx
+
+        def table(fn):
+            rows = [torch.as_tensor(fn(tt), dtype=torch.float64).reshape(-1).expand(nx) if not torch.is_tensor(fn(tt))
+                    else fn(tt).to(torch.float64).reshape(-1).expand(nx) for tt in times]
+            return torch.stack([r.to(dev) for r in rows]).contiguous()
+
+        tabs = {("prescribed", n): table(f) for n, f in self.prescribed_tracers.items()}
+        tabs.update({("forcing", n): table(f) for n, f in self.forcing.items() if f is not None and n in self.prognostic})
+        return times, tabs
+
+    def _run_graph(self, dt, steps, output_every, names, out):
+        if getattr(self.biogeochemistry.underlying_biogeochemistry, "clock_dependent_parameters", False):
+            raise ValueError("graph=True needs kernel parameters that do not depend on the clock (not PISCES)")
+        if callable(getattr(self.biogeochemistry.light_attenuation, "surface_PAR", None)):
+            raise ValueError("graph=True: a surface PAR function of time is evaluated on the host; prescribe PAR "
+                             "(prescribed_tracers={'PAR': f}) or use a constant surface PAR")
+        if self._needs_initial_update:
+            self.update_state()
+            self._needs_initial_update = False
+        stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
+        times, tabs = self._tabulate(dt, steps)
+        dev = self.grid.device
+        row = torch.zeros(1, dtype=torch.long, device=dev)  # device-side cursor into the tables
+
+        def one_step():
+            for gamma, zeta in stages:
+                self._substep(dt, gamma, zeta)
+                for (kind, n), tab in tabs.items():
+                    if kind == "prescribed":
+                        self._prescribed_target(n).interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
+                self.biogeochemistry.update_biogeochemical_state(self)
+                for n in self.prognostic:
+                    tab = tabs.get(("forcing", n))
+                    if tab is None:
+                        self.Gn[n].data.zero_()
+                    else:
+                        self.Gn[n].interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
+                self.biogeochemistry.update_tendencies(self)
+                row.add_(1)
+
+        # warm-up on a side stream (allocator, lazy module loads), with the state restored afterwards
+        saved = [(f, f.data.clone()) for d in (self.fields, self.Gn, self.Gm, self.auxiliary_fields) for f in d.values()]
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            one_step()
+        torch.cuda.current_stream(dev).wait_stream(s)
+        for f, v in saved:
+            f.data.copy_(v)
+        row.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            one_step()
+        # the capture itself does not execute: state and cursor are still those of step 0
+        for it in range(steps):
+            g.replay()
+            if output_every and (it + 1) % output_every == 0:
+                for n in names:
+                    out[n][(it + 1) // output_every - 1].copy_(self.fields[n].interior.reshape(-1))
+        self._graph = g
+        self.clock.time = times[-1] if times else self.clock.time
+        self.clock.iteration += steps
+        self.clock.last_stage_dt = dt * (stages[-1][0] + (stages[-1][1] or 0.0))
+        return out
+
+    def summary(self):
+        return "Biogeochemical box model"
+
+    def __repr__(self):
+        return (f"{self.summary()}\n  Biogeochemical model: \n    └── {self.biogeochemistry.summary()}\n"
+                f"  Time-stepper:\n    └── {self.timestepper}TimeStepper\n  Boxes: {self.grid.Nx}\n"
+                f"  Time:\n    └── {self.clock.time} s")

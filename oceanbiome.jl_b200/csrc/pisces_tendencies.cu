@@ -249,16 +249,17 @@ __device__ __forceinline__ void red_add(double* p, double t) {  // fire-and-forg
 // FAST pass: a finite result is final — stored (or added, accumulate mode) to Gⁿ at once, so it leaves the register
 // file; a non-finite one is only marked.  EXACT pass (rare): recomputes the cell with the reference's operation
 // semantics and delivers exactly the marked tendencies.  Every tendency is delivered once.
+template <bool ACC, bool FULL>  // ACC: Gⁿ += t; FULL: every tendency has a destination (no per-tendency mask test)
 struct FastSink {
     const PiscesArgs& a;
     long long idx;
     unsigned pending;
     __device__ __forceinline__ void put(int n, double t) {
-        if (!((a.out_mask >> n) & 1u)) return;
+        if (!FULL && !((a.out_mask >> n) & 1u)) return;
         const unsigned nf = nonfinite(t);
         pending |= nf << n;
         if (!nf) {
-            if (a.accumulate) red_add(a.g[n] + idx, t);
+            if (ACC) red_add(a.g[n] + idx, t);
             else a.g[n][idx] = t;
         }
     }
@@ -558,6 +559,7 @@ __device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long
 // One thread per cell.  Measured on B200 (16.8 M cells, accumulate mode): 2.75 ms whether the block is 64…512
 // threads, whether 3 or 4 blocks are resident (168 / 128 registers), with or without shared-memory staging of the
 // inputs or of Gⁿ, L2 prefetch of the next wave, or block-wide lock-step — see DESIGN.md "PISCES kernel: what bounds it".
+template <bool ACC, bool FULL>
 __global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
@@ -567,7 +569,7 @@ __global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_ker
     // ---- one coalesced read of the cell ------------------------------------------------------------
     const Inputs in = load_inputs(a, idx, pl, k);
 
-    FastSink sink{a, idx, 0u};
+    FastSink<ACC, FULL> sink{a, idx, 0u};
     if (needs_exact(in)) sink.pending = a.out_mask;
     else cell_tendencies<false>(a, in, sink);
     if (sink.pending) cell_exact(a, idx, pl, k, sink.pending);  // rare: non-finite results, NaN inputs
@@ -634,6 +636,15 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
         const double K2 = p->diatoms.enhanced_silicate_half_saturation;
         dv.K2_cubed = K2 * K2 * K2;
     }
-    pisces_tendency_kernel<<<cell_grid(A.d, PB), PB, 0, (cudaStream_t)stream>>>(A);
+    const dim3 gr = cell_grid(A.d, PB);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool full = A.out_mask == (1u << NOUT) - 1u;
+    if (A.accumulate) {
+        if (full) pisces_tendency_kernel<true, true><<<gr, PB, 0, st>>>(A);
+        else pisces_tendency_kernel<true, false><<<gr, PB, 0, st>>>(A);
+    } else {
+        if (full) pisces_tendency_kernel<false, true><<<gr, PB, 0, st>>>(A);
+        else pisces_tendency_kernel<false, false><<<gr, PB, 0, st>>>(A);
+    }
     return launch_status("pisces_tendency_kernel");
 }

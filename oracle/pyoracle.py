@@ -402,3 +402,13 @@ def w92_solubility(coefficients, T, S):
     fn.restype = C.c_double
     fn.argtypes = [dp, C.c_double, C.c_double]
     return fn((C.c_double * 6)(*coefficients), T, S)
+
+
+# ---- time stepping ----------------------------------------------------------------------------------------
+def rk3_substep(grid: Grid, U, Gn, Gm, dt, gamma, zeta=None, cache_previous=True):
+    """In place on the lists of parent arrays U, Gm."""
+    _check(list(U) + list(Gn) + list(Gm))
+    cg = grid.c_grid()
+    rc = lib().orc_rk3_substep(C.byref(cg), len(U), _table(U), _table(Gn), _table(Gm), C.c_double(dt), C.c_double(gamma),
+                               C.c_double(0.0 if zeta is None else zeta), int(zeta is not None), int(cache_previous))
+    assert rc == 0

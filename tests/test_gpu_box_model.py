@@ -1,0 +1,174 @@
+"""GPU: the fused tracer update (obm_rk3_substep, bit-exact vs the oracle) and the device-resident BoxModel
+ensemble driver — against a CPU loop assembled from the oracle in the reference's call order
+(boxmodel.jl:92-110, timesteppers.jl:30-93), the behaviour the reference's own test checks
+(test/test_boxmodel.jl:38-53: 10 steps of 20 minutes change every field), ensemble members ≡ single boxes,
+and CUDA-graph replay ≡ eager stepping bit for bit."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oceanbiome_b200 as ob
+from helpers import RTOL_TENDENCY
+
+pytestmark = pytest.mark.gpu
+
+day = 86400.0
+minutes = 60.0
+
+
+def PAR_fn(t):  # test/test_boxmodel.jl:9
+    return (60 * (1 - math.cos((t + 15 * day) * 2 * math.pi / (365 * day)))
+            * (1 / (1 + 0.2 * math.exp(-(((t % (365 * day)) - 200 * day) / (50 * day)) ** 2))) + 2) * math.exp(-2)
+
+
+DEFAULTS = {"NO₃": 10.0, "NH₄": 0.1, "P": 0.1, "Z": 0.01}
+
+
+def simple_box_model(cuda, n=1, **kw):
+    grid = ob.BoxModelGrid(n, device=cuda)
+    PAR = ob.CenterField(grid, "PAR")
+    bgc = ob.LOBSTER(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR), **kw)
+    return ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_fn}), PAR
+
+
+def host(f):
+    return np.ascontiguousarray(f.data.cpu().numpy())
+
+
+def test_substep_bit_exact(cuda, oracle):
+    grid = ob.RectilinearGrid(size=(70, 5, 6), extent=(1, 1, 1), device=cuda)
+    og = oracle.Grid.like(grid)
+    rng = np.random.default_rng(0)
+    nf = 7
+    hU, hGn, hGm = ([rng.normal(size=og.parent_shape) for _ in range(nf)] for _ in range(3))
+    mk = lambda hs: [ob.CenterField(grid).set(og.interior(h)) for h in hs]  # noqa: E731
+    from oceanbiome_b200 import _lib
+    import ctypes as C
+    lib = _lib.load()
+    for gamma, zeta, cache in ((8 / 15, None, 1), (5 / 12, -17 / 60, 1), (1.0, None, 0)):
+        dU, dGn, dGm = mk(hU), mk(hGn), mk(hGm)
+        for d, h in zip(dU + dGn + dGm, hU + hGn + hGm):
+            d.data.copy_(torch.from_numpy(h))  # halos too
+        cg = grid.c_grid()
+        tab = lambda fs: _lib.pointer_table([f.ptr for f in fs])  # noqa: E731
+        rc = lib.obm_rk3_substep(C.byref(cg), nf, tab(dU), tab(dGn), tab(dGm), 1200.0, gamma, zeta or 0.0,
+                                 int(zeta is not None), cache, None)
+        assert rc == 0
+        wU, wGm = [u.copy() for u in hU], [m.copy() for m in hGm]
+        oracle.rk3_substep(og, wU, hGn, wGm, 1200.0, gamma, zeta, cache_previous=bool(cache))
+        for f in range(nf):
+            assert np.array_equal(host(dU[f]), wU[f]) and np.array_equal(host(dGm[f]), wGm[f])
+    # argument errors
+    assert lib.obm_rk3_substep(C.byref(cg), 3, None, None, None, 1.0, 1.0, 0.0, 0, 0, None) == -1
+    assert lib.obm_rk3_substep(C.byref(cg), -1, None, None, None, 1.0, 1.0, 0.0, 0, 0, None) == -2
+    assert lib.obm_rk3_substep(C.byref(cg), 0, None, None, None, 1.0, 1.0, 0.0, 0, 0, None) == 0
+
+
+def test_reference_behaviour_ten_steps(cuda):
+    # test/test_boxmodel.jl:38-53
+    model, _ = simple_box_model(cuda)
+    model.set(**DEFAULTS)
+    for _ in range(10):
+        model.time_step(20 * minutes)
+    for name, f in model.fields.items():
+        assert f.interior.item() != DEFAULTS.get(name, 0.0), name
+        assert math.isfinite(f.interior.item())
+    assert model.clock.iteration == 10 and abs(model.clock.time - 10 * 20 * minutes) < 1e-6
+    assert "box model" in model.summary()
+    with pytest.raises(ValueError):
+        model.set(nope=1.0)
+
+
+def test_matches_cpu_loop_built_from_the_oracle(cuda, oracle):
+    model, _ = simple_box_model(cuda, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen())
+    ic = dict(DEFAULTS, sPOM=0.2, bPOM=0.1, DOM=0.3, DIC=2200.0, Alk=2400.0, **{"O₂": 240.0})
+    model.set(**ic)
+    names = list(model.biogeochemistry.required_biogeochemical_tracers())
+    og = oracle.Grid.like(model.grid)
+    params = model.biogeochemistry.underlying_biogeochemistry.c_params()
+    U = [np.full(og.parent_shape, ic.get(n, 0.0)) for n in names]
+    Gn = [np.zeros(og.parent_shape) for _ in names]
+    Gm = [np.zeros(og.parent_shape) for _ in names]
+    dt, t = 20 * minutes, 0.0
+
+    def tendencies(tt):
+        return oracle.npd_tendencies(og, params, U, np.full(og.parent_shape, PAR_fn(tt)))
+
+    Gn = tendencies(t)  # update_state! at iteration 0
+    for _ in range(25):
+        for gamma, zeta in ob.BoxModel.RK3:
+            oracle.rk3_substep(og, U, Gn, Gm, dt, gamma, zeta, cache_previous=True)
+            t += dt * (gamma + (zeta or 0.0))
+            Gn = tendencies(t)
+        model.time_step(dt)
+    for n, u in zip(names, U):
+        got, want = model.fields[n].interior.item(), og.interior(u).item()
+        assert abs(got - want) <= 50 * RTOL_TENDENCY * max(abs(want), 1e-3), (n, got, want)
+
+
+def test_ensemble_members_are_independent_boxes(cuda):
+    n = 257
+    rng = np.random.default_rng(3)
+    ics = {k: v * rng.uniform(0.5, 1.5, n) for k, v in DEFAULTS.items()}
+    ens, _ = simple_box_model(cuda, n)
+    ens.set(**{k: torch.from_numpy(v) for k, v in ics.items()})
+    for _ in range(5):
+        ens.time_step(20 * minutes)
+    for m in (0, 100, 256):
+        one, _ = simple_box_model(cuda)
+        one.set(**{k: float(v[m]) for k, v in ics.items()})
+        for _ in range(5):
+            one.time_step(20 * minutes)
+        for name in ens.fields:
+            assert ens.fields[name].interior.reshape(-1)[m].item() == one.fields[name].interior.item(), (m, name)
+
+
+@pytest.mark.parametrize("timestepper", ["RungeKutta3", "Euler"])
+def test_graph_replay_is_bit_identical_to_eager(cuda, timestepper):
+    n, steps = 4096, 30
+    rng = np.random.default_rng(4)
+    ics = {k: torch.from_numpy(v * rng.uniform(0.5, 1.5, n)) for k, v in DEFAULTS.items()}
+    T_fn = lambda t: 12.0 + 3.0 * math.sin(2 * math.pi * t / day)  # noqa: E731
+    src = lambda t: 1e-7 * (1 + math.cos(2 * math.pi * t / day))  # noqa: E731
+
+    def build():
+        grid = ob.BoxModelGrid(n, device=cuda)
+        PAR = ob.CenterField(grid, "PAR")
+        bgc = ob.NPZD(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR)) if False else \
+            ob.LOBSTER(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR), scale_negatives=True)
+        m = ob.BoxModel(biogeochemistry=bgc, grid=grid, timestepper=timestepper, forcing={"NO₃": src},
+                        prescribed_tracers={"PAR": PAR_fn, "T": T_fn})
+        m.set(**ics)
+        return m
+
+    eager, graph = build(), build()
+    oe = eager.run(20 * minutes, steps, graph=False, output_every=10)
+    og_ = graph.run(20 * minutes, steps, graph=True, output_every=10)
+    torch.cuda.synchronize()
+    for name in eager.prognostic:
+        assert torch.equal(eager.fields[name].data, graph.fields[name].data), name
+        assert torch.equal(oe[name], og_[name]) and oe[name].shape == (3, n)
+    assert graph.clock.iteration == steps and abs(graph.clock.time - eager.clock.time) < 1e-6
+    assert not torch.equal(oe["P"][0], oe["P"][-1])  # something is happening (test_boxmodel.jl:81)
+
+
+def test_box_nitrogen_is_conserved(cuda):
+    model, _ = simple_box_model(cuda, 64)
+    rng = np.random.default_rng(5)
+    model.set(**{k: torch.from_numpy(v * rng.uniform(0.5, 1.5, 64)) for k, v in DEFAULTS.items()},
+              sPOM=0.1, bPOM=0.1, DOM=0.2)
+    N = lambda: sum(model.fields[k].interior.reshape(-1) for k in ("NO₃", "NH₄", "P", "Z", "sPOM", "bPOM", "DOM"))  # noqa: E731
+    n0 = N().clone()
+    model.run(20 * minutes, 100)
+    assert torch.max(torch.abs(N() - n0) / n0).item() < 1e-13 * 100
+
+
+def test_graph_mode_refuses_host_evaluated_time_dependence(cuda):
+    grid = ob.BoxModelGrid(4, device=cuda)
+    bgc = ob.LOBSTER(grid)  # default surface PAR is a function of time evaluated on the host
+    m = ob.BoxModel(biogeochemistry=bgc, grid=grid)
+    m.set(**DEFAULTS)
+    with pytest.raises(ValueError):
+        m.run(60.0, 3, graph=True)
