@@ -523,19 +523,24 @@ __device__ __forceinline__ bool needs_exact(const Inputs& in) {
 
 
 __device__ __forceinline__ Inputs load_inputs(const PiscesArgs& a, long long idx, long long pl, int k) {
+    // 3-D inputs are read exactly once: keep them out of L1 (ld.global.cg), which is left to the spill slots
+#ifndef OBM_PISCES_LD
+#define OBM_PISCES_LD __ldcg
+#endif
+    auto ld = [](const double* p) { return OBM_PISCES_LD(p); };
     Inputs in;
-    in.P = a.c[T_P][idx]; in.PChl = a.c[T_PChl][idx]; in.PFe = a.c[T_PFe][idx];
-    in.D = a.c[T_D][idx]; in.DChl = a.c[T_DChl][idx]; in.DFe = a.c[T_DFe][idx]; in.DSi = a.c[T_DSi][idx];
-    in.Z = a.c[T_Z][idx]; in.M = a.c[T_M][idx]; in.DOC = a.c[T_DOC][idx];
-    in.POC = a.c[T_POC][idx]; in.GOC = a.c[T_GOC][idx]; in.SFe = a.c[T_SFe][idx]; in.BFe = a.c[T_BFe][idx];
-    in.PSi = a.c[T_PSi][idx]; in.CaCO3 = a.c[T_CaCO3][idx];
-    in.c.NO3 = a.c[T_NO3][idx]; in.c.NH4 = a.c[T_NH4][idx]; in.c.PO4 = a.c[T_PO4][idx]; in.c.Fe = a.c[T_Fe][idx];
-    in.c.Si = a.c[T_Si][idx]; in.c.O2 = a.c[T_O2][idx]; in.c.T = a.c[T_T][idx];
-    in.c.PAR1 = a.f.PAR1[idx]; in.c.PAR2 = a.f.PAR2[idx]; in.c.PAR3 = a.f.PAR3[idx];
-    in.PARt = a.f.PAR[idx]; in.Omega = a.f.Omega[idx];
+    in.P = ld(a.c[T_P] + idx); in.PChl = ld(a.c[T_PChl] + idx); in.PFe = ld(a.c[T_PFe] + idx);
+    in.D = ld(a.c[T_D] + idx); in.DChl = ld(a.c[T_DChl] + idx); in.DFe = ld(a.c[T_DFe] + idx); in.DSi = ld(a.c[T_DSi] + idx);
+    in.Z = ld(a.c[T_Z] + idx); in.M = ld(a.c[T_M] + idx); in.DOC = ld(a.c[T_DOC] + idx);
+    in.POC = ld(a.c[T_POC] + idx); in.GOC = ld(a.c[T_GOC] + idx); in.SFe = ld(a.c[T_SFe] + idx); in.BFe = ld(a.c[T_BFe] + idx);
+    in.PSi = ld(a.c[T_PSi] + idx); in.CaCO3 = ld(a.c[T_CaCO3] + idx);
+    in.c.NO3 = ld(a.c[T_NO3] + idx); in.c.NH4 = ld(a.c[T_NH4] + idx); in.c.PO4 = ld(a.c[T_PO4] + idx); in.c.Fe = ld(a.c[T_Fe] + idx);
+    in.c.Si = ld(a.c[T_Si] + idx); in.c.O2 = ld(a.c[T_O2] + idx); in.c.T = ld(a.c[T_T] + idx);
+    in.c.PAR1 = ld(a.f.PAR1 + idx); in.c.PAR2 = ld(a.f.PAR2 + idx); in.c.PAR3 = ld(a.f.PAR3 + idx);
+    in.PARt = ld(a.f.PAR + idx); in.Omega = ld(a.f.Omega + idx);
     // ℑzᵃᵃᶜ(i, j, k, grid, w) = (w[k] + w[k+1]) / 2 — two_size_class.jl:95-98
-    in.wPOC = (a.f.wPOC[idx] + a.f.wPOC[idx + a.d.sz]) / 2;
-    in.wGOC = (a.f.wGOC[idx] + a.f.wGOC[idx + a.d.sz]) / 2;
+    in.wPOC = (ld(a.f.wPOC + idx) + ld(a.f.wPOC + idx + a.d.sz)) / 2;
+    in.wGOC = (ld(a.f.wGOC + idx) + ld(a.f.wGOC + idx + a.d.sz)) / 2;
     in.c.zmxl = a.f.mixed_layer_depth_xy[pl];
     in.c.zeu = a.f.euphotic_depth_xy[pl];
     in.c.kappa = a.f.mean_mixed_layer_vertical_diffusivity_xy[pl];
@@ -552,15 +557,23 @@ __device__ __noinline__ void cell_exact(const PiscesArgs& a, long long idx, long
     cell_tendencies<true>(a, in, sink);
 }
 
+// 3 blocks of 128 threads per SM (168 registers, ≈ 116 B of spill per thread): the spill slots of all resident
+// threads then stay inside L1, which the input loads bypass (ld.global.cg).  4 blocks (128 registers, ≈ 410 B of
+// spill) is 2 % slower, 5 blocks thrashes L1.
 #ifndef OBM_PISCES_MIN_BLOCKS
-#define OBM_PISCES_MIN_BLOCKS 4
+#define OBM_PISCES_MIN_BLOCKS 3
+#endif
+#ifdef OBM_PISCES_MAXNREG
+#define OBM_PISCES_BOUNDS __maxnreg__(OBM_PISCES_MAXNREG)
+#else
+#define OBM_PISCES_BOUNDS __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS)
 #endif
 
 // One thread per cell.  Measured on B200 (16.8 M cells, accumulate mode): 2.75 ms whether the block is 64…512
 // threads, whether 3 or 4 blocks are resident (168 / 128 registers), with or without shared-memory staging of the
 // inputs or of Gⁿ, L2 prefetch of the next wave, or block-wide lock-step — see DESIGN.md "PISCES kernel: what bounds it".
 template <bool ACC, bool FULL>
-__global__ void __launch_bounds__(PB, OBM_PISCES_MIN_BLOCKS) pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
+__global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__ PiscesArgs a) {
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
@@ -638,6 +651,14 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
     }
     const dim3 gr = cell_grid(A.d, PB);
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool carveout_set = [] {  // no shared memory is used: give the whole array to L1 (spill slots)
+        cudaFuncSetAttribute(pisces_tendency_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(pisces_tendency_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(pisces_tendency_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        cudaFuncSetAttribute(pisces_tendency_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 0);
+        return true;
+    }();
+    (void)carveout_set;
     const bool full = A.out_mask == (1u << NOUT) - 1u;
     if (A.accumulate) {
         if (full) pisces_tendency_kernel<true, true><<<gr, PB, 0, st>>>(A);
