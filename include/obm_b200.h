@@ -212,7 +212,7 @@ enum {
 typedef struct obm_carbchem_params {
     int32_t newton_iterations; /* fixed iteration count of the branch-free ln[H] Newton (default 12 when <= 0) */
     int32_t _pad;
-    double initial_pH_guess;   /* default 8 (carbon_chemistry.jl:121) when <= 0 */
+    double initial_pH_guess;   /* default 8 (carbon_chemistry.jl:121) when <= 0: fallback start and borate term of the analytic start */
 } obm_carbchem_params;
 
 /* Flat sweep over n cells.  T °C, S PSU, DIC mmol/m³, Alk meq/m³; optional (nullable)
@@ -223,10 +223,14 @@ int obm_carbon_chemistry(int64_t n, const obm_carbchem_params* p, const double* 
                          const double* pH, int output_kind, double* out, void* stream);
 
 /* Gridded Ω for PISCES — `compute_calcite_saturation!`
- * (PISCES/compute_calcite_saturation.jl:9-37): P = |z|·g·1026/1e5 bar, silicate = Si. */
+ * (PISCES/compute_calcite_saturation.jl:9-37): P = |z|·g·1026/1e5 bar, silicate = Si.
+ * H_state (nullable, 3-D parent, in/out): [H⁺] (mol/kg) of each cell as left by the previous call; a
+ * plausible value (pH 2 … 13) warm-starts the Newton iteration — 1–3 steps per stage — anything else
+ * (e.g. a zero-filled field on the first call) falls back to the analytic starting point every solve
+ * uses.  The root found is the same to ≈ 1e-14 either way. */
 int obm_calcite_saturation(const obm_grid* grid, const obm_carbchem_params* p, const double* T,
                            const double* S, const double* DIC, const double* Alk,
-                           const double* Si, double* Omega, void* stream);
+                           const double* Si, double* Omega, double* H_state, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * (a3) PISCES — src/Models/AdvectedPopulations/PISCES/ (struct PISCES.jl:53-92), default

@@ -228,7 +228,7 @@ PROTOTYPES = {
                                        C.c_void_p]),
     "obm_carbon_chemistry": (C.c_int, [C.c_int64, C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8
                              + [C.c_int, C.c_void_p, C.c_void_p]),
-    "obm_calcite_saturation": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 7),
+    "obm_calcite_saturation": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8),
     "obm_scale_negative_tracers": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int,
                                              C.POINTER(obm_scale_group), C.c_double, C.c_void_p]),
     "obm_zero_negative_tracers": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),

@@ -65,12 +65,13 @@ class CarbonChemistry:
         return out
 
     def calcite_saturation(self, grid: RectilinearGrid, T: Field, S: Field, DIC: Field, Alk: Field, Si: Field,
-                           Omega: Field, stream: Optional[int] = None):
-        """`compute_calcite_saturation!` — PISCES/compute_calcite_saturation.jl:9-37."""
+                           Omega: Field, stream: Optional[int] = None, state: Optional[Field] = None):
+        """`compute_calcite_saturation!` — PISCES/compute_calcite_saturation.jl:9-37.
+        `state`: optional field carrying [H⁺] from call to call (Newton warm start)."""
         cg, p = grid.c_grid(), self.c_params()
         s = stream if stream is not None else current_stream_ptr(grid.device)
         rc = _lib.load().obm_calcite_saturation(C.byref(cg), C.byref(p), T.ptr, S.ptr, DIC.ptr, Alk.ptr, Si.ptr,
-                                                Omega.ptr, s)
+                                                Omega.ptr, state.ptr if state is not None else None, s)
         _lib.check(rc, "obm_calcite_saturation")
 
     def summary(self):

@@ -10,7 +10,7 @@ struct SweepArgs {
     const double *T, *S, *DIC, *Alk, *P, *sil, *phos, *pH;
     double* out;
     int output_kind, iterations;
-    double initial_pH;
+    double H_init;  // 10^(−initial_pH_guess), host-evaluated
 };
 
 template <bool HAS_P>
@@ -20,15 +20,15 @@ __global__ void __launch_bounds__(128) carbon_sweep_kernel(const __grid_constant
     const double P = HAS_P ? a.P[c] : 0.0;
     a.out[c] = cc::solve<HAS_P>(a.output_kind, a.T[c], a.S[c], a.DIC[c], a.Alk ? a.Alk[c] : 0.0, P, a.sil != nullptr,
                                 a.sil ? a.sil[c] : 0.0, a.phos != nullptr, a.phos ? a.phos[c] : 0.0, a.pH != nullptr,
-                                a.pH ? a.pH[c] : 0.0, a.initial_pH, a.iterations);
+                                a.pH ? a.pH[c] : 0.0, a.H_init, a.iterations);
 }
 
 struct OmegaArgs {
     GridDims d;
     const double *T, *S, *DIC, *Alk, *Si;
-    double* Omega;
+    double *Omega, *Hst;
     int iterations;
-    double initial_pH;
+    double H_init;  // 10^(−initial_pH_guess), host-evaluated
 };
 
 __global__ void __launch_bounds__(128) calcite_saturation_kernel(const __grid_constant__ OmegaArgs a) {
@@ -38,12 +38,12 @@ __global__ void __launch_bounds__(128) calcite_saturation_kernel(const __grid_co
     // P = abs(z) * g * 1026 / 100000 with g = Oceananigans.defaults.gravitational_acceleration
     const double P = fabs(a.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;
     a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, a.T[idx], a.S[idx], a.DIC[idx], a.Alk[idx], P, true, a.Si[idx],
-                                   false, 0.0, false, 0.0, a.initial_pH, a.iterations);
+                                   false, 0.0, false, 0.0, a.H_init, a.iterations, a.Hst ? a.Hst + idx : nullptr);
 }
 
 static void defaults(const obm_carbchem_params* p, int* iterations, double* pH0) {
     *iterations = (p && p->newton_iterations > 0) ? p->newton_iterations : 12;
-    *pH0 = (p && p->initial_pH_guess > 0) ? p->initial_pH_guess : 8.0;
+    *pH0 = pow(10.0, -((p && p->initial_pH_guess > 0) ? p->initial_pH_guess : 8.0));
 }
 
 }  // namespace obm
@@ -64,7 +64,7 @@ extern "C" int obm_carbon_chemistry(int64_t n, const obm_carbchem_params* p, con
     a.n = n; a.T = T; a.S = S; a.DIC = DIC; a.Alk = Alk; a.P = P_bar; a.sil = silicate; a.phos = phosphate; a.pH = pH;
     a.out = out;
     a.output_kind = output_kind;
-    defaults(p, &a.iterations, &a.initial_pH);
+    defaults(p, &a.iterations, &a.H_init);
     const unsigned blocks = (unsigned)((n + 127) / 128);
     if (P_bar) carbon_sweep_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
     else carbon_sweep_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(a);
@@ -73,13 +73,13 @@ extern "C" int obm_carbon_chemistry(int64_t n, const obm_carbchem_params* p, con
 
 extern "C" int obm_calcite_saturation(const obm_grid* grid, const obm_carbchem_params* p, const double* T,
                                       const double* S, const double* DIC, const double* Alk, const double* Si,
-                                      double* Omega, void* stream) {
+                                      double* Omega, double* H_state, void* stream) {
     OBM_REQUIRE(T && S && DIC && Alk && Si && Omega, OBM_ENULL, "obm_calcite_saturation: a field pointer is NULL");
     OmegaArgs a;
     int rc = make_dims(grid, &a.d, true);
     if (rc) return rc;
-    a.T = T; a.S = S; a.DIC = DIC; a.Alk = Alk; a.Si = Si; a.Omega = Omega;
-    defaults(p, &a.iterations, &a.initial_pH);
+    a.T = T; a.S = S; a.DIC = DIC; a.Alk = Alk; a.Si = Si; a.Omega = Omega; a.Hst = H_state;
+    defaults(p, &a.iterations, &a.H_init);
     calcite_saturation_kernel<<<cell_grid(a.d, 128), 128, 0, (cudaStream_t)stream>>>(a);
     return launch_status("calcite_saturation_kernel");
 }

@@ -187,12 +187,12 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
     Hdf = H * df;
 }
 
-// solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]; fixed iteration count, step clamped to one pH unit
+// solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]: Newton on x = ln[H⁺] carried multiplicatively (H ← H·e^(−Δx)),
+// step clamped to one pH unit, at most `iterations` steps from H0.
 __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, bool need_phosphate, bool need_silicate,
-                                          double initial_pH, int iterations) {
+                                          double H0, int iterations) {
     constexpr double LN10 = 2.302585092994045684;
-    double x = -initial_pH * LN10;
-    double H = exp(x);
+    double H = H0;
     const unsigned mask = __activemask();
 #pragma unroll 1
     for (int n = 0; n < iterations; n++) {
@@ -200,13 +200,25 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
         double dx = f * rcp_fast(Hdf);
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
-        x -= dx;
-        H = exp(x);
+        H *= exp(-dx);
         // Warp-uniform early exit (no divergence): once every lane's step is below 1e-7 the quadratic convergence
         // of Newton puts the next iterate within ~1e-14 of the root; NaN lanes count as converged (they stay NaN).
         if (__all_sync(mask, !(fabs(dx) >= 1e-7))) break;
     }
     return H;
+}
+
+// Where the iteration starts when there is no stored [H⁺]: the positive root of the carbonate-alkalinity quadratic
+//   A_C H² + K1 (A_C − DIC) H + K1 K2 (A_C − 2 DIC) = 0,   A_C = Alk − B_T K_B / (K_B + H_init)
+// (bicarbonate + carbonate only, borate evaluated at the reference's initial guess H_init = 10⁻⁸), which is within a
+// few hundredths of a pH unit of the root for sea water: ≈ 3 Newton steps instead of ≈ 5–6 from pH 8.  The reference
+// starts every solve at pH 8 (carbon_chemistry.jl:121); only the starting point differs, not the root.
+__device__ __forceinline__ double initial_H(const Constants& c, const Totals& t, double H_init) {
+    const double AC = t.Alk - t.boron * c.KB * rcp_fast(c.KB + H_init);
+    const double b = c.K1 * (AC - t.DIC);
+    const double disc = b * b - 4.0 * AC * (c.K1 * c.K2) * (AC - 2.0 * t.DIC);
+    const double H0 = (sqrt(disc) - b) * rcp_fast(2.0 * AC);
+    return (H0 > 1e-12 && H0 < 1e-3) ? H0 : H_init;  // NaN (disc < 0, AC ≤ 0 …) fails both comparisons
 }
 
 // K0 — equilibrium_constants.jl:65-80
@@ -231,7 +243,7 @@ __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, do
 template <bool HAS_P>
 __device__ __forceinline__ double solve(int output_kind, double T, double S, double DIC, double Alk, double P,
                                         bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
-                                        double pH, double initial_pH, int iterations) {
+                                        double pH, double H_init, int iterations, double* H_io = nullptr) {
     constexpr double LN10 = 2.302585092994045684;
     const bool calcite_path = (output_kind == OBM_CC_CO3 || output_kind == OBM_CC_OMEGA_CALCITE);
     // density: P|1 for the main call (carbon_chemistry.jl:123), P|0 for carbonate_concentration
@@ -254,7 +266,16 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
         c.isd = rcp_fast(sd);
         c.KSsd = c.KS * sd;
     }
-    const double H = has_pH ? exp(-pH * LN10) : solve_H(c, t, has_phos, has_sil, initial_pH, iterations);
+    double H;
+    if (has_pH) {
+        H = exp(-pH * LN10);
+    } else {
+        // warm start: [H⁺] kept from the previous call on this cell, if it is a plausible value (pH 2 … 13)
+        double H0 = H_io ? *H_io : 0.0;
+        if (!(H0 > 1e-13 && H0 < 1e-2)) H0 = initial_H(c, t, H_init);
+        H = solve_H(c, t, has_phos, has_sil, H0, iterations);
+        if (H_io) *H_io = H;
+    }
 
     switch (output_kind) {
         case OBM_CC_PH_FREE: return -log10(H);

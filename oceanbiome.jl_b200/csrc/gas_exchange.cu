@@ -13,7 +13,7 @@ struct GasArgs {
     const double *T, *S, *tracer, *DIC, *Alk, *sil, *phos, *wind, *air;
     double *flux, *G;
     int iterations;
-    double initial_pH;
+    double H_init;  // 10^(−initial_pH_guess), host-evaluated
 };
 
 // Base.Math.pow_body(x, 4): compensated squaring (what Julia's `x^4` evaluates for Float64)
@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(128) gas_exchange_kernel(const __grid_constant
         const double sil = sp ? (a.sil ? a.sil[idx] : p.silicate) : 0.0;
         const double phos = sp ? (a.phos ? a.phos[idx] : p.phosphate) : 0.0;
         water = cc::solve<false>(OBM_CC_PCO2, T, S, a.DIC[idx], a.Alk[idx], 0.0, sp, sil, sp, phos, false, 0.0,
-                                 a.initial_pH, a.iterations);
+                                 a.H_init, a.iterations);
     } else {
         water = a.tracer[idx];
     }
@@ -108,7 +108,7 @@ extern "C" int obm_gas_exchange_flux(const obm_grid* grid, const obm_gas_exchang
     a.T = T; a.S = S; a.tracer = tracer; a.DIC = DIC; a.Alk = Alk; a.sil = silicate_f; a.phos = phosphate_f;
     a.wind = wind_speed_xy; a.air = air_concentration_xy; a.flux = flux_xy; a.G = G_top;
     a.iterations = p->carbon_chemistry.newton_iterations > 0 ? p->carbon_chemistry.newton_iterations : 12;
-    a.initial_pH = p->carbon_chemistry.initial_pH_guess > 0 ? p->carbon_chemistry.initial_pH_guess : 8.0;
+    a.H_init = pow(10.0, -(p->carbon_chemistry.initial_pH_guess > 0 ? p->carbon_chemistry.initial_pH_guess : 8.0));
     const unsigned chunks = (unsigned)((a.d.i1 - a.d.i0 + 127) / 128);
     const unsigned ny = (unsigned)(a.d.j1 - a.d.j0);
     OBM_REQUIRE(ny <= 65535u, OBM_ESIZE, "obm_gas_exchange_flux: more than 65535 rows per launch (%u); restrict j", ny);

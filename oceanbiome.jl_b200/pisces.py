@@ -290,6 +290,8 @@ class PISCESModel:
         self.mean_mixed_layer_vertical_diffusivity = mean_mixed_layer_vertical_diffusivity
         self.mean_mixed_layer_light = mean_mixed_layer_light
         self.carbon_chemistry, self.calcite_saturation = carbon_chemistry, calcite_saturation
+        # [H⁺] of every cell kept between stages: the Ω solve of the next stage starts from it (1–2 Newton steps)
+        self.warm_start_carbonate_solve, self.carbonate_state = True, None
         self.sinking_velocities = sinking_velocities
 
     # ---- plugin surface -------------------------------------------------------------------------------
@@ -398,8 +400,10 @@ class PISCESModel:
             compute_mixed_layer_mean(self.mean_mixed_layer_vertical_diffusivity, self.mixed_layer_depth, kappa, model.grid, stream)
         compute_mixed_layer_mean(self.mean_mixed_layer_light, self.mixed_layer_depth, PAR, model.grid, stream)
         t = model.tracers
+        if self.carbonate_state is None and self.warm_start_carbonate_solve:
+            self.carbonate_state = CenterField(model.grid, "[H⁺]")  # zero-filled ⇒ first call starts from pH 8
         self.carbon_chemistry.calcite_saturation(model.grid, t["T"], t["S"], t["DIC"], t["Alk"], t["Si"],
-                                                 self.calcite_saturation, stream)
+                                                 self.calcite_saturation, stream, state=self.carbonate_state)
 
     # ---- fused tendencies ------------------------------------------------------------------------------------
     def compute_tendencies(self, grid, tracers, auxiliary_fields, G, accumulate=True, stream=None, time=0.0):

@@ -104,3 +104,44 @@ def test_gridded_calcite_saturation(cuda, oracle):
     got = Om.data.cpu().numpy()
     err = np.abs(og.interior(got) - og.interior(want)) / np.abs(og.interior(want))
     assert err.max() <= RTOL_CARBON
+
+
+def test_gridded_omega_warm_start_finds_the_same_root(cuda, oracle):
+    """obm_calcite_saturation with a [H⁺] state field: first call (zero-filled state) ≡ cold start bit for bit,
+    later calls start from the stored value and land on the same root (≤ 1e-12 relative on Ω) also after the
+    tracers have drifted; implausible stored values (NaN, 0, +5) fall back to the default guess."""
+    grid = ob.RectilinearGrid(size=(33, 4, 10), extent=(33.0, 4.0, 3000.0), device=cuda)
+    og = oracle.Grid.like(grid)
+    rng = np.random.default_rng(11)
+    shp = og.parent_shape
+    h = {"T": rng.uniform(-1, 30, shp), "S": rng.uniform(30, 38, shp), "DIC": rng.uniform(1900, 2300, shp),
+         "Si": rng.uniform(0, 120, shp)}
+    h["Alk"] = h["DIC"] * rng.uniform(1.03, 1.15, shp)
+    f = {n: ob.CenterField(grid, n) for n in h}
+    for n in h:
+        f[n].data.copy_(torch.from_numpy(h[n]))
+    cc = ob.CarbonChemistry(newton_iterations=12)
+    cold, warm, state = ob.CenterField(grid), ob.CenterField(grid), ob.CenterField(grid)
+    args = lambda: (grid, f["T"], f["S"], f["DIC"], f["Alk"], f["Si"])  # noqa: E731
+    cc.calcite_saturation(*args(), cold)
+    cc.calcite_saturation(*args(), warm, state=state)
+    assert torch.equal(cold.data, warm.data)
+    x = grid.interior(state.data)
+    assert ((x > 1e-13) & (x < 1e-2)).all()  # [H⁺] stored
+    cc.calcite_saturation(*args(), warm, state=state)
+    ic, iw = grid.interior(cold.data), grid.interior(warm.data)
+    assert ((iw - ic).abs() / ic.abs()).max().item() <= 1e-12
+    # drifted tracers, warm start vs oracle
+    f["DIC"].data.mul_(1.002)
+    h["DIC"] = h["DIC"] * 1.002
+    f["DIC"].data.copy_(torch.from_numpy(h["DIC"]))
+    cc.calcite_saturation(*args(), warm, state=state)
+    want = og.interior(oracle.calcite_saturation(og, h["T"], h["S"], h["DIC"], h["Alk"], h["Si"]))
+    got = og.interior(warm.data.cpu().numpy())
+    assert np.max(np.abs(got - want) / np.abs(want)) <= RTOL_CARBON
+    # garbage in the state field is ignored
+    state.data[...] = float("nan")
+    state.data[:, :, ::2] = 5.0
+    cc.calcite_saturation(*args(), warm, state=state)
+    got2 = og.interior(warm.data.cpu().numpy())
+    assert np.max(np.abs(got2 - want) / np.abs(want)) <= RTOL_CARBON
