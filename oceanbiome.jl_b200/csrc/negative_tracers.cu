@@ -34,7 +34,13 @@ __global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_c
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
     double* mine = sm + threadIdx.x;
-    for (int t = 0; t < a.ntracers; t++) mine[t * SN_BLOCK] = a.tracers[t][idx];
+    bool touched = false;  // some value is negative or non-finite: only then can any group have p ≠ t
+    for (int t = 0; t < a.ntracers; t++) {
+        const double v = a.tracers[t][idx];
+        mine[t * SN_BLOCK] = v;
+        touched |= !(v >= 0.0 && v < __longlong_as_double(0x7ff0000000000000LL));
+    }
+    if (!__any_sync(__activemask(), touched)) return;  // warp-uniform: the common case reads its cells and leaves
     unsigned dirty = 0;  // bit t ⇔ tracer t was rescaled and must be written back
     for (int q = 0; q < a.ngroups; q++) {
         const obm_scale_group& g = a.groups[q];
