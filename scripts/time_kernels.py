@@ -28,4 +28,7 @@ res["light_ms"] = timeit(lambda: bgc.light_attenuation.update_biogeochemical_sta
 res["underlying_state_ms"] = timeit(lambda: bgc.underlying_biogeochemistry.update_biogeochemical_state(m))
 res["tendencies_ms"] = timeit(lambda: bgc.update_tendencies(m))
 res["tendency_Gcell_s"] = w.cells / res["tendencies_ms"] / 1e6
+u = bgc.underlying_biogeochemistry
+res["tendencies_overwrite_ms"] = timeit(lambda: u.compute_tendencies(m.grid, m.tracers, bgc.biogeochemical_auxiliary_fields(), m.Gn,
+                                                                      accumulate=False, time=m.clock.time))
 print(json.dumps(res))
