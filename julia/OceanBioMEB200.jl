@@ -11,13 +11,9 @@ import Oceananigans.Biogeochemistry: update_biogeochemical_state!, update_tenden
 
 const libobm = get(ENV, "OBM_B200_LIB", "libobm_b200.so")
 
-# ---- struct mirrors (isbits; field order = include/obm_b200.h) -------------------------------------------
-struct ObmGrid
-    Nx::Int32; Ny::Int32; Nz::Int32
-    Hx::Int32; Hy::Int32; Hz::Int32
-    i0::Int32; i1::Int32; j0::Int32; j1::Int32
-    zc::CuPtr{Float64}; zf::CuPtr{Float64}
-end
+# ---- struct mirrors: generated from the ctypes definitions the test-suite checks against the compiled library ----
+include("obm_structs.jl")   # ObmGrid, ObmNpdParams, ObmTwobandParams, ObmMultibandParams, ObmCarbchemParams, ObmScaleGroup,
+                            # ObmPiscesPhyto/Zoo/Params/Fields, ObmSedimentParams/Fields, ObmGasExchangeParams
 
 function ObmGrid(grid)
     Nx, Ny, Nz = size(grid)
@@ -25,13 +21,6 @@ function ObmGrid(grid)
     Hx, Hy = (Nx == 1 ? 0 : Hx), (Ny == 1 ? 0 : Hy)                      # Flat dimensions
     zc = parent(grid.z.cᵃᵃᶜ); zf = parent(grid.z.cᵃᵃᶠ)                     # device OffsetVectors incl. halos
     return ObmGrid(Nx, Ny, Nz, Hx, Hy, Hz, 0, 0, 0, 0, pointer(zc), pointer(zf))
-end
-
-struct ObmNpdParams                                                       # obm_npd_params
-    nutrients::Int32; detritus::Int32; carbonate_replicates::Int32; oxygen::Int32
-    light_limitation::Int32; phytoplankton_mortality_formulation::Int32
-    grazing_concentration_formulation::Int32; has_temperature_coefficient::Int32
-    doubles::NTuple{35, Float64}                                          # plankton.jl:19-58 … oxygen.jl:14-17, header order
 end
 
 check(rc, what) = rc == 0 || error("$what failed ($rc): " * unsafe_string(ccall((:obm_last_error, libobm), Cstring, ())))
@@ -63,8 +52,37 @@ function update_biogeochemical_state!(bgc::B200Biogeochemistry, model)
                 (Ref{ObmGrid}, Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
                 g, tb, pointer(parent(model.tracers.P)), CU_NULL, surface, pointer(parent(PAR.field)), s),
           "obm_par_twoband")
-    # 3. underlying (PISCES: obm_euphotic_depth, obm_mixed_layer_mean, obm_calcite_saturation)   4. sediment
+    # 3. underlying — PISCES (PISCES/update_state.jl:1-17): zₑᵤ, mixed-layer means, Ω with the per-cell [H⁺] warm start
+    if ref.underlying_biogeochemistry isa OceanBioME.Models.PISCESModel.PISCES
+        u, t = ref.underlying_biogeochemistry, model.tracers
+        check(ccall((:obm_euphotic_depth, libobm), Cint, (Ref{ObmGrid}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
+                    g, pointer(parent(PAR.total)), 1 / 1000, pointer(parent(u.euphotic_depth)), s), "obm_euphotic_depth")
+        check(ccall((:obm_mixed_layer_mean, libobm), Cint,
+                    (Ref{ObmGrid}, CuPtr{Float64}, CuPtr{Float64}, Cdouble, CuPtr{Float64}, Ptr{Cvoid}),
+                    g, pointer(parent(u.mixed_layer_depth)), pointer(parent(PAR.total)), 0.0,
+                    pointer(parent(u.mean_mixed_layer_light)), s), "obm_mixed_layer_mean")
+        check(ccall((:obm_calcite_saturation, libobm), Cint,
+                    (Ref{ObmGrid}, Ref{ObmCarbchemParams}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64},
+                     CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+                    g, Ref(ObmCarbchemParams(8, 0, 8.0)), pointer(parent(t.T)), pointer(parent(t.S)), pointer(parent(t.DIC)),
+                    pointer(parent(t.Alk)), pointer(parent(t.Si)), pointer(parent(u.calcite_saturation)),
+                    pointer(parent(bgc.hydrogen_ion_state)), s), "obm_calcite_saturation")
+    end
+    # 4. sediment: obm_sediment_update_state (src/Sediments/update_state.jl:6-16)
+    # 5. gas-exchange boundary conditions: obm_gas_exchange_flux into the flux field of each FluxBoundaryCondition
     return nothing
+end
+
+# PISCES: the 24 tendencies in one launch (replaces 26 compute_Gc! launches); `params` is an ObmPiscesParams filled once
+# from the @kwdef structs, with the two clock-dependent day lengths refreshed here (growth_rate.jl:20-22,142-143)
+function update_pisces_tendencies!(bgc::B200Biogeochemistry, model, params::ObmPiscesParams, fields::ObmPiscesFields)
+    names   = Oceananigans.Biogeochemistry.required_biogeochemical_tracers(bgc.reference)   # PISCES.jl:94-105 order
+    tracers = parents(model.tracers, names)
+    G       = [n in (:T, :S) ? CU_NULL : pointer(parent(model.timestepper.Gⁿ[n])) for n in names]
+    check(ccall((:obm_pisces_tendencies, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmPiscesParams}, Ptr{CuPtr{Float64}}, Ref{ObmPiscesFields}, Ptr{CuPtr{Float64}}, Cint, Ptr{Cvoid}),
+                Ref(ObmGrid(model.grid)), Ref(params), tracers, Ref(fields), G, 1, CUDA.stream().handle),
+          "obm_pisces_tendencies")
 end
 
 function update_tendencies!(bgc::B200Biogeochemistry, model)

@@ -70,3 +70,13 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     with pytest.raises(ImportError, match="no CPU fallback"):
         _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_generated_julia_structs_are_in_sync():
+    """julia/obm_structs.jl is generated from the ctypes mirrors; regenerate it when a struct changes."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_julia_structs.py")], capture_output=True,
+                         text=True, check=True).stdout
+    assert out == open(os.path.join(root, "julia", "obm_structs.jl")).read()
