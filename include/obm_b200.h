@@ -531,6 +531,11 @@ double obm_fp64_peak_dfma_per_s(double* scratch, int iters, void* stream);
  * every thread reads its cell from `nread` (<= 40) fields and read-modify-writes (mode 0) or writes
  * (mode 1) `nrmw` (<= 26) fields, same launch geometry, no arithmetic.  The ceiling the memory system
  * sets for that many concurrent streams (a two-stream copy does not show it). */
+/* Diagnostic (synchronises): run time in ms of `blocks` blocks x 128 threads x 4 096 DFMA executed as one
+ * straight-line instruction stream (straight != 0) or as a 64-instruction loop body — what a single pass over
+ * a long instruction stream costs on this device.  scratch: DEVICE buffer of >= blocks*128 doubles. */
+double obm_fetch_ceiling_ms(double* scratch, int blocks, int straight, void* stream);
+
 double obm_stream_pattern_gbs(const obm_grid* grid, int nread, const double* const* reads, int nrmw,
                               double* const* rmw, int mode, int reps, void* stream);
 

@@ -245,6 +245,7 @@ PROTOTYPES = {
                                   C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_fetch_ceiling_ms": (C.c_double, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_stream_pattern_gbs": (C.c_double, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                             C.c_int, C.c_void_p]),
     "obm_last_error": (C.c_char_p, []),

@@ -106,3 +106,54 @@ extern "C" double obm_stream_pattern_gbs(const obm_grid* grid, int nread, const 
     const double bytes = 8.0 * (double)cell_count(a.d) * (nread + (mode == 0 ? 2 : 1) * nrmw) * reps;
     return bytes / (ms * 1e-3) / 1e9;
 }
+
+// ---- instruction-fetch ceiling ------------------------------------------------------------------------
+// The PISCES tendency kernel is ≈ 3 200 straight-line instructions that every warp executes once.  This pair of kernels
+// does the same FP64 work (3 072 DFMA per thread, 8 independent chains) once as straight-line code and once as a
+// 48-instruction loop body: the ratio of their run times is what a single pass over a long instruction stream costs
+// on this device, independent of memory traffic and register pressure.
+namespace obm {
+#define OBM_R8(x) x x x x x x x x
+#define OBM_STEP                                                                                  \
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);               \
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+template <bool STRAIGHT>
+__global__ void __launch_bounds__(128) fetch_kernel(double* out, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    if (STRAIGHT) {
+        OBM_R8(OBM_R8(OBM_R8(OBM_STEP)) ) /* 512 steps … */
+        x0 += 0;
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 64; i++) { OBM_R8(OBM_STEP) }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+#undef OBM_STEP
+#undef OBM_R8
+}  // namespace obm
+
+// Diagnostic (synchronises): ms for `blocks` blocks of 128 threads, each thread 4 096 DFMA, as straight-line code
+// (straight != 0) or as a loop.  scratch: DEVICE buffer of >= blocks*128 doubles.
+extern "C" double obm_fetch_ceiling_ms(double* scratch, int blocks, int straight, void* stream) {
+    using namespace obm;
+    if (!scratch || blocks <= 0) return (double)OBM_ENULL;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int rep = 0; rep < 2; rep++) {
+        if (rep == 1) cudaEventRecord(e0, s);
+        if (straight) fetch_kernel<true><<<blocks, 128, 0, s>>>(scratch, 0.999999, 1e-9);
+        else fetch_kernel<false><<<blocks, 128, 0, s>>>(scratch, 0.999999, 1e-9);
+    }
+    cudaEventRecord(e1, s);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    int rc = launch_status("fetch_kernel");
+    if (rc) return -(double)rc;
+    return (double)ms;
+}
