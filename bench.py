@@ -228,7 +228,9 @@ class ClockSampler(threading.Thread):
         except Exception:
             return False
         act = lambda bit: "Active" if bit else "Not Active"  # noqa: E731
-        while not self.stop_flag:
+        first = True
+        while first or not self.stop_flag:  # at least one sample, however short the timed region
+            first = False
             try:
                 r = reasons(h)
                 self.samples.append([str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx),
