@@ -355,6 +355,24 @@ int obm_scale_negative_tracers(const obm_grid* grid, int ntracers, double* const
                                int ngroups, const obm_scale_group* groups,
                                double invalid_fill_value, void* stream);
 
+/* The PISCES stage prologue in ONE launch: the modifiers' negative scaling (above) followed by
+ * `compute_calcite_saturation!` (PISCES/compute_calcite_saturation.jl:9-37, see obm_calcite_saturation)
+ * on the same cell.  Replaces the pair  update_biogeochemical_state!(model, modifiers)
+ * (OceanBioME.jl:169) … compute_calcite_saturation! (PISCES/update_state.jl:13): both are pointwise
+ * and nothing between them writes DIC, Alk, Si, T or S, so Ω is solved from the cell's rescaled
+ * values while they are on chip; the bandwidth-bound scaling pass is hidden under the FP64-bound
+ * solve.  DIC / Alk / Si are matched against `tracers` by pointer (a match uses the rescaled
+ * value); T and S must not be rescaled tracers (OBM_ESIZE).  Results are those of the two
+ * separate calls. */
+int obm_scale_negative_tracers_calcite_saturation(const obm_grid* grid, int ntracers,
+                                                  double* const* tracers, int ngroups,
+                                                  const obm_scale_group* groups,
+                                                  double invalid_fill_value,
+                                                  const obm_carbchem_params* p, const double* T,
+                                                  const double* S, const double* DIC,
+                                                  const double* Alk, const double* Si,
+                                                  double* Omega, double* H_state, void* stream);
+
 /* `ZeroNegativeTracers` negative_tracers.jl:22-32: parent .= max.(0, parent) over the whole
  * parent array (halos included, as the reference does). n = parent element count. */
 int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tracers,

@@ -231,6 +231,9 @@ PROTOTYPES = {
     "obm_calcite_saturation": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8),
     "obm_scale_negative_tracers": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int,
                                              C.POINTER(obm_scale_group), C.c_double, C.c_void_p]),
+    "obm_scale_negative_tracers_calcite_saturation": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int,
+                                                                C.POINTER(obm_scale_group), C.c_double,
+                                                                C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8),
     "obm_zero_negative_tracers": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
     "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),
     "obm_inventory": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.POINTER(obm_scale_group),

@@ -31,6 +31,7 @@ class Biogeochemistry:
         self.sediment = sediment
         self.particles = particles
         self.modifiers = modifiers
+        self.fuse_state_update = True  # False: one launch per reference step, in the reference's order
 
     # ---- forwarding (OceanBioME.jl:122-131) -------------------------------------------------------
     def required_biogeochemical_tracers(self):
@@ -56,10 +57,17 @@ class Biogeochemistry:
 
     # ---- update_biogeochemical_state!(bgc, model) — OceanBioME.jl:161-167, fixed order ----------
     def update_biogeochemical_state(self, model, stream: Optional[int] = None):
-        _update_modifiers(model, self.modifiers, stream)
+        # PISCES: its pointwise calcite-saturation solve rides in the launch of the last negative scaling (nothing
+        # between the two writes DIC, Alk, Si, T or S — see obm_scale_negative_tracers_calcite_saturation)
+        u = self.underlying_biogeochemistry
+        epilogue = u.calcite_saturation_arguments(model) if (self.fuse_state_update and hasattr(u, "calcite_saturation_arguments")) else None
+        fused = _update_modifiers(model, self.modifiers, stream, epilogue)
         if self.light_attenuation is not None:
             self.light_attenuation.update_biogeochemical_state(model, stream)
-        self.underlying_biogeochemistry.update_biogeochemical_state(model)
+        if fused:
+            u.update_biogeochemical_state(model, stream, calcite_saturation_done=True)
+        else:
+            u.update_biogeochemical_state(model, stream)
         if self.sediment is not None:
             self.sediment.update_biogeochemical_state(model, stream)
 
@@ -88,11 +96,12 @@ class Biogeochemistry:
                 f" Sediment: {s(self.sediment)}\n Particles: {s(self.particles)}\n Modifiers: {s(self.modifiers)}")
 
 
-def _update_modifiers(model, modifiers, stream):
+def _update_modifiers(model, modifiers, stream, calcite=None) -> bool:
     """update_biogeochemical_state!(model, modifiers) with tuple broadcast (OceanBioME.jl:169);
-    consecutive ScaleNegativeTracers are fused into one launch, order preserved."""
+    consecutive ScaleNegativeTracers are fused into one launch, order preserved.  `calcite` (PISCES) is handed to the
+    LAST launch when that is a negative scaling; returns whether it was consumed."""
     if modifiers is None:
-        return
+        return False
     mods = modifiers if isinstance(modifiers, tuple) else (modifiers,)
     run = []
     for m in mods:
@@ -104,7 +113,8 @@ def _update_modifiers(model, modifiers, stream):
             run = []
         m.update_biogeochemical_state(model, stream)
     if run:
-        apply_scalers(model, run, stream)
+        return apply_scalers(model, run, stream, calcite)
+    return False
 
 
 @dataclass

@@ -14,6 +14,7 @@
 // them with value·t/t, i.e. value up to 1 ulp of rounding noise): half the HBM traffic in the common case.
 #include <string.h>
 
+#include "carbon_chemistry.cuh"
 #include "obm_common.cuh"
 
 namespace obm {
@@ -28,12 +29,9 @@ struct ScaleArgs {
     obm_scale_group groups[OBM_MAX_SCALE_GROUPS];
 };
 
-__global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_constant__ ScaleArgs a) {
-    extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
-    int i, j, k;
-    if (!thread_cell(a.d, i, j, k)) return;
-    const long long idx = cell_index(a.d, i, j, k);
-    double* mine = sm + threadIdx.x;
+// One cell: stage its distinct tracers in `mine` (stride SN_BLOCK), apply the groups in order, write back what changed.
+// On return `mine` holds the cell's tracers as the rest of the stage will see them.
+__device__ __forceinline__ void scale_cell(const ScaleArgs& a, double* mine, long long idx) {
     bool touched = false;  // some value is negative or non-finite: only then can any group have p ≠ t
     for (int t = 0; t < a.ntracers; t++) {
         const double v = a.tracers[t][idx];
@@ -68,6 +66,44 @@ __global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_c
     if (dirty == 0) return;
     for (int t = 0; t < a.ntracers; t++)
         if ((dirty >> t) & 1u) a.tracers[t][idx] = mine[t * SN_BLOCK];
+}
+
+__global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_constant__ ScaleArgs a) {
+    extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
+    int i, j, k;
+    if (!thread_cell(a.d, i, j, k)) return;
+    scale_cell(a, sm + threadIdx.x, cell_index(a.d, i, j, k));
+}
+
+// ---- negative scaling + calcite saturation of the same cell in one pass (PISCES stage prologue) ----------------------
+// `update_biogeochemical_state!` runs the modifiers (OceanBioME.jl:161-169) and, for PISCES, later
+// `compute_calcite_saturation!` (PISCES/update_state.jl:13) on the rescaled DIC, Alk, Si.  Both are pointwise, nothing
+// in between writes those tracers, T or S, so the Ω solve can consume the staged, already rescaled values of the cell:
+// the HBM-bound scaling pass (8 B × distinct tracers per cell) disappears under the FP64-bound carbonate solve, and
+// DIC, Alk, Si are read once instead of twice.  Same device functions as the separate kernels ⇒ same results.
+struct ScaleOmegaArgs {
+    ScaleArgs s;
+    const double *T, *S, *DIC, *Alk, *Si;  // used directly when the field is not one of s.tracers
+    int iDIC, iAlk, iSi;                  // index in s.tracers, or −1
+    double *Omega, *Hst;
+    int iterations;
+    double H_init;
+};
+
+__global__ void __launch_bounds__(SN_BLOCK) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
+    extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
+    int i, j, k;
+    if (!thread_cell(a.s.d, i, j, k)) return;
+    const long long idx = cell_index(a.s.d, i, j, k);
+    double* mine = sm + threadIdx.x;
+    const double T = a.T[idx], S = a.S[idx];  // never rescaled (not members of any conserved group)
+    scale_cell(a.s, mine, idx);
+    const double DIC = a.iDIC >= 0 ? mine[a.iDIC * SN_BLOCK] : a.DIC[idx];
+    const double Alk = a.iAlk >= 0 ? mine[a.iAlk * SN_BLOCK] : a.Alk[idx];
+    const double Si = a.iSi >= 0 ? mine[a.iSi * SN_BLOCK] : a.Si[idx];
+    const double P = fabs(a.s.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;  // compute_calcite_saturation.jl:27
+    a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, T, S, DIC, Alk, P, true, Si, false, 0.0, false, 0.0, a.H_init,
+                                   a.iterations, a.Hst ? a.Hst + idx : nullptr);
 }
 
 struct ZeroArgs {
@@ -193,6 +229,42 @@ extern "C" int obm_scale_negative_tracers(const obm_grid* grid, int ntracers, do
     const size_t smem = (size_t)ntracers * SN_BLOCK * sizeof(double);
     scale_negative_kernel<<<cell_grid(a.d, SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
     return launch_status("scale_negative_kernel");
+}
+
+extern "C" int obm_scale_negative_tracers_calcite_saturation(const obm_grid* grid, int ntracers, double* const* tracers,
+                                                             int ngroups, const obm_scale_group* groups,
+                                                             double invalid_fill_value, const obm_carbchem_params* p,
+                                                             const double* T, const double* S, const double* DIC,
+                                                             const double* Alk, const double* Si, double* Omega,
+                                                             double* H_state, void* stream) {
+    const char* who = "obm_scale_negative_tracers_calcite_saturation";
+    OBM_REQUIRE(tracers != nullptr, OBM_ENULL, "%s: tracers is NULL", who);
+    OBM_REQUIRE(T && S && DIC && Alk && Si && Omega, OBM_ENULL, "%s: a field pointer is NULL", who);
+    int rc = check_groups(who, ntracers, ngroups, groups);
+    if (rc) return rc;
+    static thread_local ScaleOmegaArgs a;
+    memset(&a, 0, sizeof(a));
+    rc = make_dims(grid, &a.s.d, true);
+    if (rc) return rc;
+    a.s.ntracers = ntracers;
+    a.s.ngroups = ngroups;
+    a.s.fill = invalid_fill_value;
+    a.iDIC = a.iAlk = a.iSi = -1;
+    for (int t = 0; t < ntracers; t++) {
+        OBM_REQUIRE(tracers[t] != nullptr, OBM_ENULL, "%s: tracers[%d] is NULL", who, t);
+        OBM_REQUIRE(tracers[t] != T && tracers[t] != S, OBM_ESIZE, "%s: T and S may not be rescaled tracers", who);
+        a.s.tracers[t] = tracers[t];
+        if (tracers[t] == DIC) a.iDIC = t;
+        if (tracers[t] == Alk) a.iAlk = t;
+        if (tracers[t] == Si) a.iSi = t;
+    }
+    for (int q = 0; q < ngroups; q++) a.s.groups[q] = groups[q];
+    a.T = T; a.S = S; a.DIC = DIC; a.Alk = Alk; a.Si = Si; a.Omega = Omega; a.Hst = H_state;
+    a.iterations = (p && p->newton_iterations > 0) ? p->newton_iterations : 12;
+    a.H_init = pow(10.0, -((p && p->initial_pH_guess > 0) ? p->initial_pH_guess : 8.0));
+    const size_t smem = (size_t)ntracers * SN_BLOCK * sizeof(double);
+    scale_negative_calcite_kernel<<<cell_grid(a.s.d, SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
+    return launch_status("scale_negative_calcite_kernel");
 }
 
 extern "C" int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tracers, void* stream) {

@@ -47,8 +47,11 @@ class ScaleNegativeTracers:
         return f"Mass conserving negative scaling of {self.tracers}"
 
 
-def apply_scalers(model, scalers: Sequence[ScaleNegativeTracers], stream: Optional[int] = None):
-    """All groups in one launch, applied in order (OceanBioME.jl:169 applies modifiers in tuple order)."""
+def apply_scalers(model, scalers: Sequence[ScaleNegativeTracers], stream: Optional[int] = None, calcite=None) -> bool:
+    """All groups in one launch, applied in order (OceanBioME.jl:169 applies modifiers in tuple order).
+    `calcite`: optional `(carbon_chemistry, T, S, DIC, Alk, Si, Ω, [H⁺] state or None)` — the PISCES calcite-saturation
+    solve of the same cells rides in the same launch (obm_scale_negative_tracers_calcite_saturation).  Returns
+    whether it did."""
     names = []
     for sc in scalers:
         for t in sc.tracers:
@@ -60,7 +63,7 @@ def apply_scalers(model, scalers: Sequence[ScaleNegativeTracers], stream: Option
     if len(fills) > 1:  # different fill values cannot share a launch: fall back to one launch per group
         for sc in scalers:
             apply_scalers(model, (sc,), stream)
-        return
+        return False
     fields = [model.tracers[n] for n in names]
     require_cuda(*fields)
     groups = (_lib.obm_scale_group * len(scalers))()
@@ -72,9 +75,20 @@ def apply_scalers(model, scalers: Sequence[ScaleNegativeTracers], stream: Option
     grid = model.grid
     cg = grid.c_grid()
     s = stream if stream is not None else current_stream_ptr(grid.device)
+    if calcite is not None:
+        cc, T, S, DIC, Alk, Si, Omega, state = calcite
+        require_cuda(T, S, DIC, Alk, Si, Omega)
+        p = cc.c_params()
+        rc = _lib.load().obm_scale_negative_tracers_calcite_saturation(
+            C.byref(cg), len(names), _lib.pointer_table([f.ptr for f in fields]), len(scalers), groups,
+            scalers[0].invalid_fill_value, C.byref(p), T.ptr, S.ptr, DIC.ptr, Alk.ptr, Si.ptr, Omega.ptr,
+            state.ptr if state is not None else None, s)
+        _lib.check(rc, "obm_scale_negative_tracers_calcite_saturation")
+        return True
     rc = _lib.load().obm_scale_negative_tracers(C.byref(cg), len(names), _lib.pointer_table([f.ptr for f in fields]),
                                                 len(scalers), groups, scalers[0].invalid_fill_value, s)
     _lib.check(rc, "obm_scale_negative_tracers")
+    return False
 
 
 class ZeroNegativeTracers:

@@ -253,7 +253,7 @@ class NutrientsPlanktonDetritus:
         """coupling_utils.jl:54 — (chl_a, chl_b, scale) for the multi-band light model."""
         return model.tracers["P"], None, self.plankton.phytoplankton_chlorophyll_ratio
 
-    def update_biogeochemical_state(self, model):
+    def update_biogeochemical_state(self, model, stream=None):
         return None  # no method in the reference: Oceananigans' no-op fallback (SURVEY §3A step 3)
 
     # -- the fused tendency pass ---------------------------------------------------------------------

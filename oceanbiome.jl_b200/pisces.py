@@ -392,18 +392,29 @@ class PISCESModel:
         return f
 
     # ---- update_biogeochemical_state!(model, bgc::PISCES) — update_state.jl:1-17 --------------------
-    def update_biogeochemical_state(self, model, stream: Optional[int] = None):
+    def _carbonate_state(self, model):
+        if self.carbonate_state is None and self.warm_start_carbonate_solve:
+            self.carbonate_state = CenterField(model.grid, "[H⁺]")  # zero-filled ⇒ first call starts from pH 8
+        return self.carbonate_state
+
+    def calcite_saturation_arguments(self, model):
+        """What `apply_scalers(…, calcite=…)` needs to solve Ω in the negative-scaling launch."""
+        t = model.tracers
+        return (self.carbon_chemistry, t["T"], t["S"], t["DIC"], t["Alk"], t["Si"], self.calcite_saturation,
+                self._carbonate_state(model))
+
+    def update_biogeochemical_state(self, model, stream: Optional[int] = None, calcite_saturation_done: bool = False):
         PAR = model.biogeochemistry.light_attenuation.biogeochemical_auxiliary_fields()["PAR"]
         compute_euphotic_depth(self.euphotic_depth, PAR, stream=stream)
         kappa = getattr(model, "vertical_diffusivity", None)  # closure = nothing ⇒ pre-set κ̄ is kept (:64-67)
         if kappa is not None:
             compute_mixed_layer_mean(self.mean_mixed_layer_vertical_diffusivity, self.mixed_layer_depth, kappa, model.grid, stream)
         compute_mixed_layer_mean(self.mean_mixed_layer_light, self.mixed_layer_depth, PAR, model.grid, stream)
+        if calcite_saturation_done:  # solved in the negative-scaling launch (Biogeochemistry.update_biogeochemical_state)
+            return
         t = model.tracers
-        if self.carbonate_state is None and self.warm_start_carbonate_solve:
-            self.carbonate_state = CenterField(model.grid, "[H⁺]")  # zero-filled ⇒ first call starts from pH 8
         self.carbon_chemistry.calcite_saturation(model.grid, t["T"], t["S"], t["DIC"], t["Alk"], t["Si"],
-                                                 self.calcite_saturation, stream, state=self.carbonate_state)
+                                                 self.calcite_saturation, stream, state=self._carbonate_state(model))
 
     # ---- fused tendencies ------------------------------------------------------------------------------------
     def compute_tendencies(self, grid, tracers, auxiliary_fields, G, accumulate=True, stream=None, time=0.0):

@@ -24,6 +24,9 @@ def timeit(fn, n=10):
 res = {"lib": os.environ.get("OBM_B200_LIB", "default"), "cells": w.cells}
 from oceanbiome_b200.biogeochemistry import _update_modifiers
 res["scale_negative_ms"] = timeit(lambda: _update_modifiers(m, bgc.modifiers, None))
+if hasattr(bgc.underlying_biogeochemistry, "calcite_saturation_arguments"):
+    u0 = bgc.underlying_biogeochemistry
+    res["scale_negative_calcite_fused_ms"] = timeit(lambda: _update_modifiers(m, bgc.modifiers, None, u0.calcite_saturation_arguments(m)))
 res["light_ms"] = timeit(lambda: bgc.light_attenuation.update_biogeochemical_state(m))
 res["underlying_state_ms"] = timeit(lambda: bgc.underlying_biogeochemistry.update_biogeochemical_state(m))
 res["tendencies_ms"] = timeit(lambda: bgc.update_tendencies(m))

@@ -151,3 +151,43 @@ def test_full_stage_runs_with_negative_scaling(cuda):
     model.time_step(60.0)
     assert all(bool(torch.isfinite(f.interior).all()) for f in model.tracers.values())
     assert bool((model.tracers["NO₃"].interior >= 0).all())
+
+
+@pytest.mark.parametrize("warm", [False, True])
+def test_fused_scaling_and_calcite_saturation_equals_separate_launches(cuda, oracle, warm):
+    """obm_scale_negative_tracers_calcite_saturation ≡ obm_scale_negative_tracers → obm_calcite_saturation: tracers bit
+    for bit (incl. zeroed / NaN-filled cells), Ω from the RESCALED DIC, Alk, Si to rounding, and Ω ≡ oracle."""
+    out = []
+    for fuse in (True, False):
+        grid = ob.RectilinearGrid(size=(37, 5, 21), extent=(1e4, 1e3, 2000.0), device=cuda)
+        bgc = ob.PISCES(grid, scale_negatives=True, surface_photosynthetically_active_radiation=90.0)
+        bgc.fuse_state_update = fuse
+        bgc.underlying_biogeochemistry.warm_start_carbonate_solve = warm
+        model = ob.BiogeochemicalModel(grid, bgc)
+        fill(model, bgc)
+        t = model.tracers
+        t["DOC"].interior[3, 1, :7] = -5.0        # carbon group: DIC is rescaled (by ≈ 1e-3) in these cells
+        t["Si"].interior[5:9, 2, 4] = -0.3        # silicon group: Si → 0, DSi / PSi rescaled
+        t["NO₃"].interior[0, 0, 10:] = -0.1
+        t["Fe"].interior[11, 3, 2] = float("nan")  # iron group only
+        t["PSi"].interior[20, 4, 20] = -1e9       # group total < 0 ⇒ invalid_fill_value (NaN) on DSi, Si
+        for _ in range(2 if warm else 1):          # second pass: the stored [H⁺] is used
+            model.update_state()
+        torch.cuda.synchronize()
+        out.append((model, bgc))
+    (mf, bf), (ms, bs) = out
+    for n in pisces.TRACERS:
+        a, b = mf.tracers[n].data, ms.tracers[n].data
+        assert bool(((a == b) | (a.isnan() & b.isnan())).all()), n
+    of, os_ = bf.underlying_biogeochemistry.calcite_saturation.interior, bs.underlying_biogeochemistry.calcite_saturation.interior
+    both_nan = of.isnan() & os_.isnan()
+    assert int(both_nan.sum()) == 1  # the NaN-filled Si cell; a NaN Fe does not reach Ω
+    assert bool((((of - os_).abs() <= 1e-13 * os_.abs()) | both_nan).all())
+    og = oracle.Grid.like(mf.grid)
+    h = {n: np.ascontiguousarray(mf.tracers[n].data.cpu().numpy()) for n in ("T", "S", "DIC", "Alk", "Si")}
+    Om = og.interior(oracle.calcite_saturation(og, h["T"], h["S"], h["DIC"], h["Alk"], h["Si"]))
+    got = of.cpu().numpy()
+    ok = np.isfinite(Om)
+    assert float(np.max(np.abs(got[ok] - Om[ok]) / np.abs(Om[ok]))) <= RTOL_CARBON
+    for n in ("PAR", "PAR₁"):
+        assert torch.equal(bf.biogeochemical_auxiliary_fields()[n].data, bs.biogeochemical_auxiliary_fields()[n].data)
