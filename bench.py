@@ -163,7 +163,7 @@ class HostStage:
     pipeline (oceanbiome_b200.host_stage.HostStagedStage).  The flat carbonate sweep copies its 4 inputs in and
     its output back."""
 
-    def __init__(self, w: Workload):
+    def __init__(self, w: Workload, copy_engine: str = "dma", nslabs: int = 0):
         self.w = w
         if w.kind == "carbon":
             self.h_in = [torch.empty(w.n, dtype=torch.float64).pin_memory() for _ in range(4)]
@@ -174,7 +174,8 @@ class HostStage:
             self.d2h_bytes = 8 * w.n
             return
         from oceanbiome_b200.host_stage import HostStagedStage
-        self.stage = HostStagedStage(w.model, nslabs=8 if w.grid.Ny >= 64 else 1)
+        self.stage = HostStagedStage(w.model, nslabs=nslabs or ((32 if w.grid.Ny >= 256 else 8) if w.grid.Ny >= 64 else 1),
+                                     copy_engine=copy_engine)
         self.stage.upload_from_device()
         self.h2d_bytes, self.d2h_bytes = self.stage.h2d_bytes, self.stage.d2h_bytes
 
@@ -371,6 +372,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink Ny (or n) for quick checks; not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-slabs", type=int, default=0, help="x-y slabs of the e2e pipeline (0: default)")
+    ap.add_argument("--copy-engine", default="dma", choices=["sm", "dma", "sm_h2d", "sm_d2h"],
+                    help="host<->device slab copies of the e2e leg: persistent copy kernel (sm) or cudaMemcpy2DAsync (dma)")
     args = ap.parse_args()
     name = args.workload or default_workload()
     if args.impl == "reference":
@@ -433,7 +437,7 @@ def main():
                 scale_e2e = max(1.0 / w.grid.Ny, budget / need) * args.scale
                 we = Workload(name, device, scale_e2e)
                 note = f"host RAM limits pinned buffers: e2e grid reduced to {we.grid.Nx}x{we.grid.Ny}x{we.grid.Nz} per GPU"
-        hs = HostStage(we)
+        hs = HostStage(we, args.copy_engine, args.e2e_slabs)
         for _ in range(2):
             hs.step()
         barrier()
@@ -451,7 +455,8 @@ def main():
             ems = t.item()
         e2e = {"value": we.cells * world * k / (ems * 1e-3) / 1e9, "unit": "Gcell-updates/s",
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k,
-               "cells_per_gpu": we.cells}
+               "cells_per_gpu": we.cells, "copy_engine": args.copy_engine,
+               "pcie_GBs_each_direction": max(hs.h2d_bytes, hs.d2h_bytes) * k / (ems * 1e-3) / 1e9}
         if note:
             e2e["note"] = note
 

@@ -393,7 +393,7 @@ int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tra
  * and the stepping order / flux operator live in Oceananigans (not in the tree) — see DESIGN.md.
  * ------------------------------------------------------------------------------------ */
 enum { OBM_SED_INSTANT_REMINERALISATION = 0, OBM_SED_SIMPLE_MULTI_G = 1 };
-enum { OBM_ADV_UPWIND1 = 0, OBM_ADV_CENTERED2 = 1 }; /* face reconstruction of advective_tracer_flux_z */
+enum { OBM_ADV_UPWIND1 = 0, OBM_ADV_CENTERED2 = 1, OBM_ADV_UPWIND3 = 2 }; /* face reconstruction of advective_tracer_flux_z (UPWIND3: obm_sinking_tendencies only) */
 enum { OBM_TS_AB2 = 0, OBM_TS_RK3 = 1 };             /* Sediments.jl:48: timestepper                   */
 #define OBM_SED_MAX_SINKING 4
 #define OBM_SED_MAX_POOLS 6
@@ -435,12 +435,13 @@ typedef struct obm_sediment_fields {
     double* G_coupled[OBM_SED_MAX_COUPLED];
 } obm_sediment_fields;
 
-/* dt = model.clock.last_stage_Δt (non-finite ⇒ pools are not stepped, update_state.jl:11-13).
- * AB2: chi (χ = −0.5 ⇒ Euler; timesteppers.jl:29-42).  RK3: gamma, zeta (zeta = NaN ⇒ the
- * first-stage method without G⁻, :67-73). */
+/* dt = model.clock.last_stage_Δt (non-finite ⇒ pools are not stepped, update_state.jl:11-13):
+ * `time_step!(sediment_model, dt)` in one launch.  AB2: one ab2_step! with chi (χ = −0.5 ⇒ Euler;
+ * timesteppers.jl:16-42).  RK3: the sediment's whole three-stage step (rk3_substep! :46-73,
+ * cache_previous_tendencies! :84-96 and the tendency recompute per stage) with the tracked
+ * tracers and fluxes held fixed; chi is ignored. */
 int obm_sediment_update_state(const obm_grid* grid, const obm_sediment_params* p,
-                              const obm_sediment_fields* f, double dt, double chi, double gamma,
-                              double zeta, void* stream);
+                              const obm_sediment_fields* f, double dt, double chi, void* stream);
 int obm_sediment_update_tendencies(const obm_grid* grid, const obm_sediment_params* p,
                                    const obm_sediment_fields* f, void* stream);
 
@@ -504,6 +505,22 @@ int obm_gas_exchange_flux(const obm_grid* grid, const obm_gas_exchange_params* p
                           double* flux_xy, double* G_top, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-2) Sinking: Gⁿ[c] (+)= −∂z(w c) for every tracer with a biogeochemical drift velocity, all in
+ * one launch.  w_faces[t]: the z-face field `biogeochemical_drift_velocity(bgc, Val(c)).w`
+ * (`setup_velocity_fields` src/Utils/sinking_velocity_fields.jl:10-35, `DepthDependantSinkingSpeed`
+ * PISCES/common.jl:39-55; face k at plane k, Nz + 1 faces).  Flux form  F_k = w_k·c̃_k,
+ * G_k −= (F_{k+1} − F_k)/Δz_k  with c̃ by `advection` (OBM_ADV_UPWIND1 | CENTERED2 | UPWIND3; UPWIND3
+ * falls back to first order where its stencil would leave the interior).  This is the
+ * `div_Uc(…, total_velocities, c)` term of Oceananigans' tracer tendency for models without a
+ * resolved vertical velocity (column / box ensembles, the reference's sediment tests); the
+ * bottom-face flux is the one obm_sediment_update_state reads.  Tracer z-halos are read as found.
+ * ------------------------------------------------------------------------------------ */
+#define OBM_MAX_SINKING_TRACERS 8
+int obm_sinking_tendencies(const obm_grid* grid, int ntracers, const double* const* tracers,
+                           const double* const* w_faces, double* const* G, int advection,
+                           int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (f-2 / f-3) The tracer update either side of the tendency pass, every tracer in one launch:
  *     U[f] += Δt·(γ·Gⁿ[f] + ζ·G⁻[f])   (has_zeta = 0, the first stage: U[f] += Δt·γ·Gⁿ[f])
  *     G⁻[f] ← Gⁿ[f]                     (cache_previous != 0)
@@ -538,6 +555,13 @@ int obm_inventory(const obm_grid* grid, int ntracers, const double* const* trace
  * ------------------------------------------------------------------------------------ */
 int obm_copy_slab(const obm_grid* grid, int nfields, void* const* dst, const void* const* src,
                   int nplanes, int direction, void* stream);
+
+/* The same copy driven by a small persistent kernel (one block per SM, 16-byte accesses over PCIe)
+ * instead of one DMA descriptor per (field, k-plane) row: ≈ 10⁵ descriptors per direction per stage
+ * at 32 slabs cost ≈ 15 % of the PCIe bandwidth.  Host pointers must be pinned memory (mapped for
+ * the device by UVA).  Same arguments and result as obm_copy_slab. */
+int obm_copy_slab_sm(const obm_grid* grid, int nfields, void* const* dst, const void* const* src,
+                     int nplanes, int direction, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Diagnostic (synchronises): measured FP64-pipe peak in DFMA instructions per second, the

@@ -161,7 +161,8 @@ class obm_pisces_fields(C.Structure):
 OBM_PISCES_NTRACERS = 26
 
 SED_INSTANT_REMINERALISATION, SED_SIMPLE_MULTI_G = 0, 1
-ADV_UPWIND1, ADV_CENTERED2 = 0, 1
+ADV_UPWIND1, ADV_CENTERED2, ADV_UPWIND3 = 0, 1, 2
+OBM_MAX_SINKING_TRACERS = 8
 TS_AB2, TS_RK3 = 0, 1
 OBM_SED_MAX_SINKING, OBM_SED_MAX_POOLS, OBM_SED_MAX_COUPLED = 4, 6, 4
 
@@ -235,11 +236,13 @@ PROTOTYPES = {
                                                                 C.POINTER(obm_scale_group), C.c_double,
                                                                 C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8),
     "obm_zero_negative_tracers": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "obm_sinking_tendencies": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p]),
     "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),
     "obm_inventory": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.POINTER(obm_scale_group),
                                 C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "obm_sediment_update_state": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sediment_params), C.POINTER(obm_sediment_fields),
-                                            C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]),
+                                            C.c_double, C.c_double, C.c_void_p]),
     "obm_sediment_update_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sediment_params),
                                                  C.POINTER(obm_sediment_fields), C.c_void_p]),
     "obm_find_bottom_cells": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -247,6 +250,7 @@ PROTOTYPES = {
     "obm_rk3_substep": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                   C.c_double, C.c_int, C.c_int, C.c_void_p]),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "obm_copy_slab_sm": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),
     "obm_fetch_ceiling_ms": (C.c_double, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_stream_pattern_gbs": (C.c_double, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,

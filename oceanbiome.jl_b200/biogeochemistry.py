@@ -15,7 +15,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from .grids import CenterField, Field, RectilinearGrid, current_stream_ptr
+from .grids import CenterField, Field, RectilinearGrid, ZFaceField, current_stream_ptr
 from .negative_tracers import ScaleNegativeTracers, apply_scalers
 
 
@@ -133,9 +133,17 @@ class BiogeochemicalModel:
 
     RK3 = ((8 / 15, 0.0), (5 / 12, -17 / 60), (3 / 4, -5 / 12))  # (γⁿ, ζⁿ) of Oceananigans' RK3
 
+    ADVECTION = {"UpwindBiased1": _lib.ADV_UPWIND1, "Centered2": _lib.ADV_CENTERED2, "UpwindBiased3": _lib.ADV_UPWIND3}
+
     def __init__(self, grid: RectilinearGrid, biogeochemistry, extra_tracers=(), timestepper="RungeKutta3",
-                 boundary_conditions=None):
+                 boundary_conditions=None, sinking_advection: Optional[str] = None):
         self.grid = grid
+        # advection scheme applied to the biogeochemical drift velocities (Oceananigans' `advection` keyword restricted
+        # to what a model without resolved flow needs); None = the host model advects the sinking tracers itself
+        if sinking_advection is not None and sinking_advection not in self.ADVECTION:
+            raise ValueError(f"sinking_advection must be one of {tuple(self.ADVECTION)} or None")
+        self.sinking_advection = sinking_advection
+        self._drift = {}
         # {tracer: top flux boundary condition} — e.g. DIC=CarbonDioxideGasExchangeBoundaryCondition()
         self.boundary_conditions = dict(boundary_conditions or {})
         self.biogeochemistry = biogeochemistry
@@ -163,8 +171,37 @@ class BiogeochemicalModel:
         for g in self.Gn.values():
             g.data.zero_()
         self.biogeochemistry.update_tendencies(self)
+        if self.sinking_advection is not None:
+            self.add_sinking_tendencies()
         for name, bc in self.boundary_conditions.items():
             bc.apply_top(self, name)  # G[i, j, Nz] -= flux / Δz, as Oceananigans' apply_z_bcs! does
+
+    def drift_velocity_field(self, name) -> Optional[Field]:
+        """`biogeochemical_drift_velocity(bgc, Val(name)).w` as a z-face field, or None for a tracer that does not sink
+        (constant speeds are materialised once, like `setup_velocity_fields`, sinking_velocity_fields.jl:10-35:
+        every face but the closed top one)."""
+        if name not in self._drift:
+            w = self.biogeochemistry.biogeochemical_drift_velocity(name)
+            if w is None or isinstance(w, Field):
+                self._drift[name] = w
+            else:
+                f = ZFaceField(self.grid, "w" + name)
+                f.face_interior[:self.grid.Nz] = float(w)
+                self._drift[name] = f
+        return self._drift[name]
+
+    def add_sinking_tendencies(self, stream: Optional[int] = None):
+        """Gⁿ[c] += −∂z(w c) for every sinking tracer, one launch (csrc/sinking.cu)."""
+        names = [n for n in self.tracers if n not in ("T", "S") and self.drift_velocity_field(n) is not None]
+        cg = self.grid.c_grid()
+        s = stream if stream is not None else current_stream_ptr(self.grid.device)
+        for c0 in range(0, len(names), _lib.OBM_MAX_SINKING_TRACERS):
+            chunk = names[c0:c0 + _lib.OBM_MAX_SINKING_TRACERS]
+            rc = _lib.load().obm_sinking_tendencies(
+                C.byref(cg), len(chunk), _lib.pointer_table([self.tracers[n].ptr for n in chunk]),
+                _lib.pointer_table([self.drift_velocity_field(n).ptr for n in chunk]),
+                _lib.pointer_table([self.Gn[n].ptr for n in chunk]), self.ADVECTION[self.sinking_advection], 1, s)
+            _lib.check(rc, "obm_sinking_tendencies")
 
     def _substep(self, dt, gamma, zeta):
         """U += Δt(γGⁿ + ζG⁻), G⁻ ← Gⁿ for every tracer in one launch (csrc/timestepping.cu)."""

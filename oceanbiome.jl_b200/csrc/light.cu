@@ -20,6 +20,19 @@
 
 namespace obm {
 
+// exp of the scans: the lean even/odd-Horner exp of obm_common.cuh (≈ 26 instructions, ≤ 2 ulp, library call for
+// |x| ≥ 700 / NaN) — these kernels are issue-bound on their 4 (two-band) / 2·bands (N-band) exps per cell.
+#ifndef OBM_LIGHT_EXP
+#define OBM_LIGHT_EXP 2
+#endif
+__device__ __forceinline__ double lexp(double x) {
+#if OBM_LIGHT_EXP == 0
+    return exp(x);
+#else
+    return exp_lean<OBM_LIGHT_EXP>(x);
+#endif
+}
+
 constexpr int TC = 32;        // columns per block tile
 constexpr int TZ = 32;        // levels per z-tile (= warp width)
 constexpr int NWARP = 8;      // warps per block
@@ -112,8 +125,8 @@ __global__ void __launch_bounds__(TC* NWARP) par_twoband_kernel(const __grid_con
             // (P Rᶜₚ / r)^e for both bands from ONE logarithm: x^e = exp(e ln x)  (x = 0 → 0, x < 0 → NaN like pow;
             // |e ln x| ≲ 10 ⇒ ≤ 2e-15 relative, inside the 1e-12 tolerance; saves two ≈ 130-instruction pow calls)
             const double lp = log(tile[lane][c] * Rcp / r);
-            const double pr = live ? (er == 0.0 ? 1.0 : exp(er * lp)) : 0.0;  // x^0 ≡ 1
-            const double pb = live ? (eb == 0.0 ? 1.0 : exp(eb * lp)) : 0.0;
+            const double pr = live ? (er == 0.0 ? 1.0 : lexp(er * lp)) : 0.0;  // x^0 ≡ 1
+            const double pb = live ? (eb == 0.0 ? 1.0 : lexp(eb * lp)) : 0.0;
             double pr_up = __shfl_up_sync(0xffffffffu, pr, 1);
             double pb_up = __shfl_up_sync(0xffffffffu, pb, 1);
             if (lane == 0) { pr_up = prev_pr[q]; pb_up = prev_pb[q]; }
@@ -123,7 +136,7 @@ __global__ void __launch_bounds__(TC* NWARP) par_twoband_kernel(const __grid_con
             const double db = w_above * pb_up + w_here * pb;
             const double ir = carry_r[q] + warp_inclusive_sum(dr, lane);
             const double ib = carry_b[q] + warp_inclusive_sum(db, lane);
-            const double par = col_par0[c] * (exp(kr * zck - xr * ir) + exp(kb * zck - xb * ib)) / 2;
+            const double par = col_par0[c] * (lexp(kr * zck - xr * ir) + lexp(kb * zck - xb * ib)) / 2;
             carry_r[q] = __shfl_sync(0xffffffffu, ir, 31);
             carry_b[q] = __shfl_sync(0xffffffffu, ib, 31);
             prev_pr[q] = __shfl_sync(0xffffffffu, pr, 31);
@@ -205,8 +218,8 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
             for (int n = 0; n < NB; n++) {
                 const double kw = a.m.water_attenuation_coefficient[n], e = a.m.chlorophyll_exponent[n];
                 const double chi = a.m.chlorophyll_attenuation_coefficient[n];
-                const double chle = e == 0.0 ? 1.0 : exp(e * lchl);  // x^0 ≡ 1 (also for x = 0)
-                double t = live ? exp(dz * (kw + chi * chle)) : 1.0;
+                const double chle = e == 0.0 ? 1.0 : lexp(e * lchl);  // x^0 ≡ 1 (also for x = 0)
+                double t = live ? lexp(dz * (kw + chi * chle)) : 1.0;
                 if (ktop == Nz - 1 && lane == 0) t = col_par0[c] * a.m.surface_PAR_division[n] * t;
                 const double f = carry[q][n] * warp_inclusive_prod(t, lane);
                 carry[q][n] = __shfl_sync(0xffffffffu, f, 31);

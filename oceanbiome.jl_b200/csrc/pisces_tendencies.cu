@@ -63,33 +63,18 @@ constexpr int NOUT = 24;  // tendencies
 // FAST (default path): a lean branch-free division (MUFU.RCP64H seed + 2 Newton steps, ≤ 1.5 ulp:
 // 5 FP64 instructions instead of the ≈ 30-instruction IEEE sequence with its slow-path call
 // scaffolding), `x / (y + eps(0.0))` with the reference's exact y == 0 behaviour
-// (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and plain
-// fmin/fmax.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
-// by fmin/fmax) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
+// (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and min/max as
+// compare + select.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
+// by a min/max) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
 #ifndef OBM_PISCES_EXP
-#define OBM_PISCES_EXP 2  // 0: library exp, 1: exp_lean Estrin, 2: exp_lean even/odd Horner
-#endif
-#ifndef OBM_PISCES_DIV
-#define OBM_PISCES_DIV 1  // 0: a·rcp_fast(b), 1: product folded into the refinement
-#endif
-#ifndef OBM_PISCES_MINMAX
-#define OBM_PISCES_MINMAX 1  // 0: fmin/fmax, 1: compare + select
+#define OBM_PISCES_EXP 0  // 0: library exp; 1 / 2: exp_lean schemes of obm_common.cuh (measured: no gain here, r02)
 #endif
 template <bool EXACT>
 struct Ar {
     static constexpr bool EX = EXACT;
     static __device__ __forceinline__ double div(double a, double b) {
         if (EXACT) return a / b;
-#if OBM_PISCES_DIV == 0
-        return a * rcp_fast(b);
-#endif
-        // a·(1/b) with the product folded into the refinement: q₀ = a·r₀ is formed beside e = 1 − b·r₀, then
-        // q = q₀ + q₀(e + e²) — dependent depth MUFU → DFMA → DFMA → DFMA (one less than a·rcp_fast(b)), ≤ 1.5 ulp
-        double r;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
-        const double e = fma(-b, r, 1.0);
-        const double q0 = a * r;
-        return fma(fma(e, e, e), q0, q0);
+        return a * rcp_fast(b);  // ≤ 1.5 ulp
     }
     // a / (y + eps(0.0)).  y == 0 makes the quotient garbage (NaN), which the select discards.
     static __device__ __forceinline__ double gdiv(double a, double y) {
@@ -101,13 +86,8 @@ struct Ar {
     // FAST min/max are a compare + select (3 instructions; fmin/fmax on doubles expand to ≈ 7 with their NaN fix-up).
     // NaN: a NaN in `b` propagates, a NaN in `a` is swallowed — never more than fmin/fmax swallow, so the guard of
     // `needs_exact` (inputs that reach the tendencies only through min/max) still covers every such cell.
-#if OBM_PISCES_MINMAX == 0
-    static __device__ __forceinline__ double mx(double a, double b) { return EXACT ? jl_max(a, b) : fmax(a, b); }
-    static __device__ __forceinline__ double mn(double a, double b) { return EXACT ? jl_min(a, b) : fmin(a, b); }
-#else
     static __device__ __forceinline__ double mx(double a, double b) { return EXACT ? jl_max(a, b) : (a > b ? a : b); }
     static __device__ __forceinline__ double mn(double a, double b) { return EXACT ? jl_min(a, b) : (a < b ? a : b); }
-#endif
     static __device__ __forceinline__ double mn3(double a, double b, double c) { return mn(mn(a, b), c); }
     static __device__ __forceinline__ double mn4(double a, double b, double c, double d) { return mn(mn(mn(a, b), c), d); }
     static __device__ __forceinline__ double ex(double x) {

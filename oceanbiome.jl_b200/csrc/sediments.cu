@@ -21,7 +21,7 @@ struct SedArgs {
     GridDims d;
     obm_sediment_params p;
     obm_sediment_fields f;
-    double dt, chi, gamma, zeta;
+    double dt, chi;
     int np, nc, nt;  // pools, coupled tracers, tracked tracers
 };
 
@@ -138,20 +138,41 @@ __global__ void __launch_bounds__(128) sediment_state_kernel(const __grid_consta
         for (int n = 0; n < a.p.nsinking_nitrogen; n++) a.f.tracked_xy[q++][pl] = fluxes[n];
         for (int n = 0; n < a.p.nsinking_carbon; n++) a.f.tracked_xy[q++][pl] = fluxes[OBM_SED_MAX_SINKING + n];
     }
-    if (isfinite(a.dt)) {  // time_step!(sediment_model, Δt): K10 + tendency cache
+    if (isfinite(a.dt) && a.p.timestepper == OBM_TS_RK3) {
+        // time_step!(sediment_model::…{<:RungeKutta3TimeStepper}, Δt): the sediment takes a WHOLE three-stage step of
+        // length Δt (the parent's last stage) inside this hook — per stage rk3_substep! (timesteppers.jl:46-73),
+        // cache_previous_tendencies! (:84-96), update_state! → compute_sediment_tendencies! — with the tracked
+        // tracers / fluxes held at the values gathered above.  The pools are per-column scalars, so all three stages
+        // run in registers: one launch instead of 3 × (np step + np cache + np tendency) launches.
+        const double gam[3] = {8.0 / 15.0, 5.0 / 12.0, 3.0 / 4.0}, zet[3] = {0.0, -17.0 / 60.0, -5.0 / 12.0};
+        double Gn[OBM_SED_MAX_POOLS], Gm[OBM_SED_MAX_POOLS];
+#pragma unroll
+        for (int n = 0; n < OBM_SED_MAX_POOLS; n++)
+            if (n < a.np) { Gn[n] = a.f.Gn[n][pl]; Gm[n] = a.f.Gm[n][pl]; }
+#pragma unroll
+        for (int st = 0; st < 3; st++) {
+#pragma unroll
+            for (int n = 0; n < OBM_SED_MAX_POOLS; n++)
+                if (n < a.np) {
+                    c.pool[n] += st == 0 ? a.dt * gam[0] * Gn[n] : a.dt * (gam[st] * Gn[n] + zet[st] * Gm[n]);
+                    Gm[n] = Gn[n];
+                }
+#pragma unroll
+            for (int n = 0; n < OBM_SED_MAX_POOLS; n++)
+                if (n < a.np) Gn[n] = pool_tendency(a.p, c, n);
+        }
+#pragma unroll
+        for (int n = 0; n < OBM_SED_MAX_POOLS; n++)
+            if (n < a.np) { a.f.pools[n][pl] = c.pool[n]; a.f.Gm[n][pl] = Gm[n]; a.f.Gn[n][pl] = Gn[n]; }
+        return;
+    }
+    if (isfinite(a.dt)) {  // time_step!(sediment_model::…{<:QuasiAdamsBashforth2TimeStepper}, Δt): K10 + tendency cache
 #pragma unroll
         for (int n = 0; n < OBM_SED_MAX_POOLS; n++)
             if (n < a.np) {
                 const double Gn = a.f.Gn[n][pl], Gm = a.f.Gm[n][pl];
-                double u = c.pool[n];
-                if (a.p.timestepper == OBM_TS_AB2) {
-                    const double Gu = (1.5 + a.chi) * Gn - (a.chi != -0.5 ? (0.5 + a.chi) * Gm : 0.0);
-                    u += a.dt * Gu;
-                } else if (a.zeta != a.zeta) {
-                    u += a.dt * a.gamma * Gn;
-                } else {
-                    u += a.dt * (a.gamma * Gn + a.zeta * Gm);
-                }
+                const double Gu = (1.5 + a.chi) * Gn - (a.chi != -0.5 ? (0.5 + a.chi) * Gm : 0.0);
+                const double u = c.pool[n] + a.dt * Gu;
                 c.pool[n] = u;
                 a.f.pools[n][pl] = u;
                 a.f.Gm[n][pl] = Gn;
@@ -231,12 +252,12 @@ static int fill_args(SedArgs& a, const obm_grid* grid, const obm_sediment_params
 using namespace obm;
 
 extern "C" int obm_sediment_update_state(const obm_grid* grid, const obm_sediment_params* p, const obm_sediment_fields* f,
-                                         double dt, double chi, double gamma, double zeta, void* stream) {
+                                         double dt, double chi, void* stream) {
     SedArgs a;
     memset(&a, 0, sizeof(a));
     int rc = fill_args(a, grid, p, f, true);
     if (rc) return rc;
-    a.dt = dt; a.chi = chi; a.gamma = gamma; a.zeta = zeta;
+    a.dt = dt; a.chi = chi;
     const long long ncols = column_count(a.d);
     sediment_state_kernel<<<(unsigned)((ncols + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
     return launch_status("sediment_state_kernel");

@@ -172,9 +172,7 @@ class BiogeochemicalSediment:
         p, f, cg = self.c_params(), self.c_fields(model, bgc), self.grid.c_grid()
         chi = -0.5 if (dt != self.last_dt) else self.chi  # Oceananigans' AB2 takes an Euler step when Δt changed
         s = stream if stream is not None else current_stream_ptr(self.grid.device)
-        rc = _lib.load().obm_sediment_update_state(C.byref(cg), C.byref(p), C.byref(f), float(dt), chi,
-                                                   getattr(model.clock, "rk3_gamma", 1.0),
-                                                   getattr(model.clock, "rk3_zeta", float("nan")), s)
+        rc = _lib.load().obm_sediment_update_state(C.byref(cg), C.byref(p), C.byref(f), float(dt), chi, s)
         _lib.check(rc, "obm_sediment_update_state")
         if math.isfinite(dt):
             self.last_dt = dt
@@ -214,7 +212,7 @@ def InstantRemineralisationSediment(grid, sinking_tracers=("P", "D"), reminerali
 
 def SimpleMultiGSediment(grid, sinking_nitrogen=("sPOM", "bPOM"), sinking_carbon=None, sinking_redfield="default",
                          sedimentation_rate=None, timestepper="QuasiAdamsBashforth2", advection="UpwindBiased1",
-                         bottom_height=None, **params):
+                         bottom_height=None, chi=0.1, **params):
     """simple_multi_G.jl:104-132; sedimentation_rate defaults to 982 |z₁|^(−1.548) (cm/year)."""
     if sinking_redfield == "default":
         sinking_redfield = 6.56 if sinking_carbon is None else None
@@ -223,4 +221,4 @@ def SimpleMultiGSediment(grid, sinking_nitrogen=("sPOM", "bPOM"), sinking_carbon
     b = SimpleMultiG(sinking_redfield=sinking_redfield, sedimentation_rate=sedimentation_rate,
                      sinking_nitrogen=tuple(sinking_nitrogen), sinking_carbon=tuple(sinking_carbon) if sinking_carbon else None,
                      **params)
-    return BiogeochemicalSediment(grid, b, timestepper=timestepper, advection=advection, bottom_height=bottom_height)
+    return BiogeochemicalSediment(grid, b, timestepper=timestepper, advection=advection, bottom_height=bottom_height, chi=chi)

@@ -325,10 +325,9 @@ def sediment_fields(**ptrs):
     return f
 
 
-def sediment_update_state(grid: Grid, params, fields, dt, chi=0.1, gamma=1.0, zeta=float("nan")):
+def sediment_update_state(grid: Grid, params, fields, dt, chi=0.1):
     cg = grid.c_grid()
-    rc = lib().orc_sediment_update_state(C.byref(cg), C.byref(params), C.byref(fields), C.c_double(dt), C.c_double(chi),
-                                         C.c_double(gamma), C.c_double(zeta))
+    rc = lib().orc_sediment_update_state(C.byref(cg), C.byref(params), C.byref(fields), C.c_double(dt), C.c_double(chi))
     assert rc == 0
 
 
@@ -412,3 +411,14 @@ def rk3_substep(grid: Grid, U, Gn, Gm, dt, gamma, zeta=None, cache_previous=True
     rc = lib().orc_rk3_substep(C.byref(cg), len(U), _table(U), _table(Gn), _table(Gm), C.c_double(dt), C.c_double(gamma),
                                C.c_double(0.0 if zeta is None else zeta), int(zeta is not None), int(cache_previous))
     assert rc == 0
+
+
+# ---- sinking ------------------------------------------------------------------------------------------------
+def sinking_tendencies(grid: Grid, tracers, w_faces, G, advection=0, accumulate=True):
+    """G[t] (+)= −∂z(w c), in place on the list of parent arrays G (oracle_sinking.c)."""
+    _check(list(tracers) + list(w_faces) + list(G))
+    cg = grid.c_grid()
+    rc = lib().orc_sinking_tendencies(C.byref(cg), len(tracers), _table(tracers), _table(w_faces), _table(G),
+                                      int(advection), int(accumulate))
+    assert rc == 0
+    return G

@@ -154,7 +154,7 @@ static void gather(const obm_grid* g, SP s, const obm_sediment_fields* f, int i,
 
 /* update_biogeochemical_state!(model, sediment) — Sediments/update_state.jl:6-16 */
 int orc_sediment_update_state(const obm_grid* g, const obm_sediment_params* s, const obm_sediment_fields* f, double dt,
-                              double chi, double gamma, double zeta) {
+                              double chi) {
     int i0, i1, j0, j1;
     grid_range(g, &i0, &i1, &j0, &j1);
     const int np = npools(s), nt = ntracked_tracers(s);
@@ -170,18 +170,30 @@ int orc_sediment_update_state(const obm_grid* g, const obm_sediment_params* s, c
                 for (int n = 0; n < s->nsinking_nitrogen + s->nsinking_carbon; n++)
                     f->tracked_xy[q++][pl] = sinking_flux(g, s, f->sinking[n], f->sinking_w[n], i, j, k);
             }
-            if (isfinite(dt)) { /* time_step!(sediment_model, Δt) */
+            if (isfinite(dt) && s->timestepper == OBM_TS_RK3) {
+                /* time_step!(sediment_model, Δt) with a RungeKutta3TimeStepper: three stages inside the hook, each
+                 * rk3_substep! (Sediments/timesteppers.jl:46-73; first stage Δt * γ¹ * G¹) → cache_previous_tendencies!
+                 * (:84-96) → update_state! (compute_sediment_tendencies!), tracked fields held fixed.  γ, ζ are
+                 * Oceananigans' RungeKutta3TimeStepper constants (not in the tree): 8/15, 5/12, 3/4; −17/60, −5/12. */
+                const double gam[3] = {8.0 / 15.0, 5.0 / 12.0, 3.0 / 4.0}, zet[3] = {0.0, -17.0 / 60.0, -5.0 / 12.0};
+                for (int st = 0; st < 3; st++) {
+                    for (int n = 0; n < np; n++) { /* one launch per pool */
+                        double Gn = f->Gn[n][pl], Gm = f->Gm[n][pl];
+                        if (st == 0) f->pools[n][pl] += dt * gam[0] * Gn;
+                        else f->pools[n][pl] += dt * (gam[st] * Gn + zet[st] * Gm);
+                    }
+                    for (int n = 0; n < np; n++) f->Gm[n][pl] = f->Gn[n][pl];
+                    for (int n = 0; n < np; n++) c.pool[n] = f->pools[n][pl];
+                    for (int n = 0; n < np; n++) f->Gn[n][pl] = pool_tendency(s, &c, n);
+                }
+                continue;
+            }
+            if (isfinite(dt)) { /* time_step!(sediment_model, Δt), QuasiAdamsBashforth2 */
                 for (int n = 0; n < np; n++) { /* K10 */
                     double Gn = f->Gn[n][pl], Gm = f->Gm[n][pl], u = f->pools[n][pl];
-                    if (s->timestepper == OBM_TS_AB2) {
-                        int not_euler = chi != -0.5;
-                        double Gu = (1.5 + chi) * Gn - (not_euler ? (0.5 + chi) * Gm : 0.0);
-                        u += dt * Gu;
-                    } else if (isnan(zeta)) {
-                        u += dt * gamma * Gn;
-                    } else {
-                        u += dt * (gamma * Gn + zeta * Gm);
-                    }
+                    int not_euler = chi != -0.5;
+                    double Gu = (1.5 + chi) * Gn - (not_euler ? (0.5 + chi) * Gm : 0.0);
+                    u += dt * Gu;
                     f->pools[n][pl] = u;
                     c.pool[n] = u;
                     f->Gm[n][pl] = Gn; /* cache_previous_tendencies! */

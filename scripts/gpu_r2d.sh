@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_r2d.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu_r2d.log
+tail -5 gpurun_out/pytest_gpu_r2d.log
+python scripts/time_e2e.py pisces_c4 0.5 dma:8 dma:16 dma:32 dma:64 sm_h2d:32 sm_d2h:32 sm_d2h:8 2>&1 | grep -v Warn | tee gpurun_out/time_e2e_r2d.txt

@@ -23,10 +23,11 @@ def lobster(cuda, size=(48, 20, 12)):
     return grid, bgc, model
 
 
+@pytest.mark.parametrize("engine,Nx", [("sm", 48), ("sm", 47), ("dma", 48)])  # Nx = 47: rows are not 16-byte multiples
 @pytest.mark.parametrize("nslabs", [1, 3, 20])
-def test_host_staged_lobster_equals_resident(cuda, nslabs):
-    grid, bgc, model = lobster(cuda)
-    stage = HostStagedStage(model, nslabs=nslabs)
+def test_host_staged_lobster_equals_resident(cuda, nslabs, engine, Nx):
+    grid, bgc, model = lobster(cuda, size=(Nx, 20, 12))
+    stage = HostStagedStage(model, nslabs=nslabs, copy_engine=engine)
     stage.upload_from_device()
     before = {n: f.data.clone() for n, f in model.tracers.items()}
     # resident reference
@@ -45,7 +46,7 @@ def test_host_staged_lobster_equals_resident(cuda, nslabs):
     for n in stage.gnames:
         got = grid.interior(stage.host_G[n])
         assert torch.equal(got, grid.interior(want[n]).cpu()), n
-    assert stage.h2d_bytes == len(model.tracers) * grid.Ny * (grid.Nx + 6) * (grid.Nz + 6) * 8
+    assert stage.h2d_bytes == len(model.tracers) * grid.Ny * (grid.Nx + 6) * grid.Nz * 8  # interior k-planes only
 
 
 def test_host_staged_pisces_equals_resident(cuda):

@@ -181,13 +181,14 @@ def test_fused_scaling_and_calcite_saturation_equals_separate_launches(cuda, ora
         assert bool(((a == b) | (a.isnan() & b.isnan())).all()), n
     of, os_ = bf.underlying_biogeochemistry.calcite_saturation.interior, bs.underlying_biogeochemistry.calcite_saturation.interior
     both_nan = of.isnan() & os_.isnan()
-    assert int(both_nan.sum()) == 1  # the NaN-filled Si cell; a NaN Fe does not reach Ω
+    # the NaN-filled Si cell; a NaN Fe reaches Ω only on a second pass (iron group → NaN Z, M → carbon group → NaN DIC)
+    assert int(both_nan.sum()) == (2 if warm else 1)
     assert bool((((of - os_).abs() <= 1e-13 * os_.abs()) | both_nan).all())
     og = oracle.Grid.like(mf.grid)
     h = {n: np.ascontiguousarray(mf.tracers[n].data.cpu().numpy()) for n in ("T", "S", "DIC", "Alk", "Si")}
     Om = og.interior(oracle.calcite_saturation(og, h["T"], h["S"], h["DIC"], h["Alk"], h["Si"]))
     got = of.cpu().numpy()
-    ok = np.isfinite(Om)
+    ok = np.isfinite(Om) & np.isfinite(got)  # the NaN-filled cell is excluded (counted above)
     assert float(np.max(np.abs(got[ok] - Om[ok]) / np.abs(Om[ok]))) <= RTOL_CARBON
     for n in ("PAR", "PAR₁"):
         assert torch.equal(bf.biogeochemical_auxiliary_fields()[n].data, bs.biogeochemical_auxiliary_fields()[n].data)
