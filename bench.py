@@ -174,7 +174,7 @@ class HostStage:
             self.d2h_bytes = 8 * w.n
             return
         from oceanbiome_b200.host_stage import HostStagedStage
-        self.stage = HostStagedStage(w.model, nslabs=nslabs or ((32 if w.grid.Ny >= 256 else 8) if w.grid.Ny >= 64 else 1),
+        self.stage = HostStagedStage(w.model, nslabs=nslabs or ((16 if w.grid.Ny >= 256 else 8) if w.grid.Ny >= 64 else 1),
                                      copy_engine=copy_engine)
         self.stage.upload_from_device()
         self.h2d_bytes, self.d2h_bytes = self.stage.h2d_bytes, self.stage.d2h_bytes
@@ -188,6 +188,35 @@ class HostStage:
             self.h_out.copy_(w.out, non_blocking=True)
             return
         self.stage.step()
+
+
+def pcie_peak_gbs(device, nbytes=1 << 30, reps=3):
+    """Measured host<->device rate of this box with both directions busy (pinned memory, one large contiguous copy per
+    direction on its own stream): the roofline of the end-to-end leg, which moves every tracer in and every tendency
+    out.  GB/s per direction."""
+    n = nbytes // 8
+    h_in, h_out = (torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(2))
+    d_in = torch.empty(n, dtype=torch.float64, device=device)
+    d_out = torch.zeros(n, dtype=torch.float64, device=device)
+    s1, s2 = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    cur = torch.cuda.current_stream(device)
+
+    def run(r):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        s1.wait_stream(cur); s2.wait_stream(cur)
+        for _ in range(r):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        cur.wait_stream(s1); cur.wait_stream(s2)
+        b.record()
+        torch.cuda.synchronize(device)
+        return r * n * 8 / (a.elapsed_time(b) * 1e-3) / 1e9
+
+    run(1)
+    return run(reps)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -457,6 +486,10 @@ def main():
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k,
                "cells_per_gpu": we.cells, "copy_engine": args.copy_engine,
                "pcie_GBs_each_direction": max(hs.h2d_bytes, hs.d2h_bytes) * k / (ems * 1e-3) / 1e9}
+        if rank == 0:  # the leg's own roofline: both copy directions busy, measured here on this box
+            peak = pcie_peak_gbs(device)
+            e2e["pcie_peak_GBs_each_direction"] = peak
+            e2e["pcie_frac"] = e2e["pcie_GBs_each_direction"] / peak
         if note:
             e2e["note"] = note
 

@@ -69,7 +69,10 @@ def test_hooks_match_oracle(cuda, oracle, ctor, kw):
     for f, h in zip(sed.Gn.values(), h_Gn):
         close(host(f), h)
     for f, h in zip(sed.Gm.values(), h_Gm):
-        assert np.array_equal(host(f), h)  # cached tendency: a copy
+        if sed.timestepper == "RungeKutta3":
+            close(host(f), h)  # the tendency of the sediment's second stage, recomputed inside the hook
+        else:
+            assert np.array_equal(host(f), h)  # cached tendency: a copy
     for f, h in zip(sed.tracked_fields.values(), h_tracked):
         close(host(f), h)
     for n, h in zip(b.coupled_tracers(), h_Gc):
