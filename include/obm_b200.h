@@ -505,6 +505,76 @@ int obm_gas_exchange_flux(const obm_grid* grid, const obm_gas_exchange_params* p
                           double* flux_xy, double* G_top, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-4) Biologically active particles — src/Particles/ with the sugar-kelp individual model of
+ * src/Models/Individuals/SugarKelp/ (Broch & Slagstad 2012 as updated there).  The reference runs, per
+ * stage, one launch per coupled tracer (8) that re-evaluates the whole kelp model including the
+ * Newton solve for the light-inhibition parameter β, then 3 tendency + 3 Euler launches for the
+ * particle fields; here there are two: a scatter launch (all 8 uptake / release terms of a particle
+ * from ONE evaluation, atomically added into Gⁿ of the nearest cell) and a step launch (dA, dN, dC
+ * and the forward-Euler update).  A user-supplied particle biogeochemistry is a Julia callable and
+ * cannot cross the C ABI; SugarKelp is the one the reference ships.
+ * ------------------------------------------------------------------------------------ */
+enum { OBM_TOPO_PERIODIC = 0, OBM_TOPO_BOUNDED = 1, OBM_TOPO_FLAT = 2 };
+
+typedef struct obm_sugar_kelp_params { /* SugarKelp.jl:36-150, field order kept */
+    /* temperature_limit::LinearOptimalTemperatureRange — equations.jl:206-227 */
+    double lower_optimal, upper_optimal, lower_gradient, upper_gradient;
+    double growth_rate_adjustment, photosynthetic_efficiency, minimum_carbon_reserve, structural_carbon;
+    double exudation, erosion_exponent, base_erosion_rate, saturation_irradiance;
+    double structural_dry_weight_per_area, structural_dry_to_wet_weight;
+    double carbon_reserve_per_carbon, nitrogen_reserve_per_nitrogen;
+    double minimum_nitrogen_reserve, maximum_nitrogen_reserve;
+    double growth_adjustment_2, growth_adjustment_1, maximum_specific_growth_rate, structural_nitrogen;
+    double photosynthesis_at_ref_temp_1, photosynthesis_at_ref_temp_2;
+    double photosynthesis_ref_temp_1, photosynthesis_ref_temp_2, photoperiod_1, photoperiod_2;
+    double respiration_at_ref_temp_1, respiration_at_ref_temp_2, respiration_ref_temp_1, respiration_ref_temp_2;
+    double photosynthesis_arrhenius_temp, photosynthesis_low_temp, photosynthesis_high_temp;
+    double photosynthesis_high_arrhenius_temp, photosynthesis_low_arrhenius_temp, respiration_arrhenius_temp;
+    double current_speed_for_0p65_uptake, nitrate_half_saturation, ammonia_half_saturation;
+    double maximum_nitrate_uptake, maximum_ammonia_uptake, current_1, current_2, current_3;
+    double base_activity_respiration_rate, base_basal_respiration_rate, exudation_redfield_ratio;
+    double adapted_latitude;
+    int32_t newton_iterations; /* cap of the β solve (reference: 1000 with an unreachable atol); <= 0 ⇒ 100 */
+    int32_t _pad;
+} obm_sugar_kelp_params;
+
+typedef struct obm_particles { /* BiogeochemicalParticles — Particles.jl:25-41 (device arrays of length n) */
+    int64_t n;
+    const double *x, *y, *z;
+    double *A, *N, *C;            /* required_particle_fields(::SugarKelp) = (:A, :N, :C)           */
+    const double* scalefactors;   /* nullable ⇒ 1                                                   */
+    /* where the particles live horizontally (obm_grid carries only z): first cell CENTRE and spacing */
+    double x0, dx, y0, dy;
+    int32_t topology[3];          /* OBM_TOPO_* of x, y, z — get_node, tracer_interpolation.jl:5-7  */
+    int32_t _pad;
+} obm_particles;
+
+typedef struct obm_kelp_tracers { /* required_tracers(::SugarKelp) = (:u, :v, :w, :T, :NO₃, :NH₄, :PAR), 3-D parents */
+    const double *u, *v, *w;      /* nullable ⇒ 0 (read at the same (i, j, k) as the reference does)  */
+    const double *T, *NO3, *NH4, *PAR;
+} obm_kelp_tracers;
+
+#define OBM_KELP_NCOUPLED 8 /* coupled_tracers: NO₃ NH₄ DIC O₂ DOC DON bPOC bPON (SugarKelp.jl:164) */
+
+/* `update_tendencies!(bgc, particles, model)` — update_tracer_tendencies.jl:1-48 with NearestPoint
+ * (tracer_interpolation.jl:16-72): G[c][nearest cell] += scalefactor · kelp(Val(c), t, …) / volume
+ * for the 8 coupled tracers (G[c] == NULL ⇒ that tracer is not coupled in this model).  Atomic. */
+int obm_kelp_update_tendencies(const obm_grid* grid, const obm_sugar_kelp_params* p,
+                               const obm_particles* particles, const obm_kelp_tracers* tracers,
+                               double* const* G, double t, void* stream);
+
+/* `time_step_particle_fields!(::ForwardEuler, …)` — tendencies.jl:3-35 + time_stepping.jl:18-48:
+ * dA, dN, dC from the state as it is, then field += tendency · Δt.  tendencies_out (nullable): three
+ * device arrays of length n that receive dA, dN, dC (the reference's timestepper.tendencies). */
+int obm_kelp_step(const obm_grid* grid, const obm_sugar_kelp_params* p, const obm_particles* particles,
+                  const obm_kelp_tracers* tracers, double t, double dt, double* const* tendencies_out,
+                  void* stream);
+
+/* `seasonal_limitation(kelp, t)` (equations.jl:229-255) — a function of the clock only, evaluated on
+ * the host by the two calls above. */
+double obm_kelp_seasonal_limitation(const obm_sugar_kelp_params* p, double t);
+
+/* ------------------------------------------------------------------------------------
  * (f-2) Sinking: Gⁿ[c] (+)= −∂z(w c) for every tracer with a biogeochemical drift velocity, all in
  * one launch.  w_faces[t]: the z-face field `biogeochemical_drift_velocity(bgc, Val(c)).w`
  * (`setup_velocity_fields` src/Utils/sinking_velocity_fields.jl:10-35, `DepthDependantSinkingSpeed`

@@ -23,6 +23,7 @@ from .gas_exchange import (CarbonDioxideConcentration, CarbonDioxideGasExchangeB
                            CarbonDioxidePolynomialSchmidtNumber, GasExchange, GasExchangeBoundaryCondition,
                            OxygenConcentration, OxygenGasExchangeBoundaryCondition, OxygenPolynomialSchmidtNumber,
                            PartiallySolubleGas, PolynomialParameterisation, SchmidtScaledTransferVelocity)
+from .particles import BiogeochemicalParticles, LinearOptimalTemperatureRange, SugarKelp, SugarKelpParticles
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
 from .box_model import BoxModel, BoxModelGrid
 

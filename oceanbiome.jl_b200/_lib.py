@@ -197,7 +197,42 @@ OBM_GE_WATER_TRACER, OBM_GE_WATER_PCO2 = 0, 1
 OBM_GE_AIR_PLAIN, OBM_GE_AIR_WANNINKHOF92 = 0, 1
 OBM_GE_SOLUBILITY_ONE, OBM_GE_SOLUBILITY_K0_RHO = 0, 1
 
+KELP_DOUBLES = (
+    "lower_optimal", "upper_optimal", "lower_gradient", "upper_gradient",
+    "growth_rate_adjustment", "photosynthetic_efficiency", "minimum_carbon_reserve", "structural_carbon",
+    "exudation", "erosion_exponent", "base_erosion_rate", "saturation_irradiance",
+    "structural_dry_weight_per_area", "structural_dry_to_wet_weight", "carbon_reserve_per_carbon",
+    "nitrogen_reserve_per_nitrogen", "minimum_nitrogen_reserve", "maximum_nitrogen_reserve",
+    "growth_adjustment_2", "growth_adjustment_1", "maximum_specific_growth_rate", "structural_nitrogen",
+    "photosynthesis_at_ref_temp_1", "photosynthesis_at_ref_temp_2", "photosynthesis_ref_temp_1",
+    "photosynthesis_ref_temp_2", "photoperiod_1", "photoperiod_2",
+    "respiration_at_ref_temp_1", "respiration_at_ref_temp_2", "respiration_ref_temp_1", "respiration_ref_temp_2",
+    "photosynthesis_arrhenius_temp", "photosynthesis_low_temp", "photosynthesis_high_temp",
+    "photosynthesis_high_arrhenius_temp", "photosynthesis_low_arrhenius_temp", "respiration_arrhenius_temp",
+    "current_speed_for_0p65_uptake", "nitrate_half_saturation", "ammonia_half_saturation",
+    "maximum_nitrate_uptake", "maximum_ammonia_uptake", "current_1", "current_2", "current_3",
+    "base_activity_respiration_rate", "base_basal_respiration_rate", "exudation_redfield_ratio", "adapted_latitude")
+OBM_TOPO_PERIODIC, OBM_TOPO_BOUNDED, OBM_TOPO_FLAT = 0, 1, 2
+OBM_KELP_NCOUPLED = 8
+
+
+class obm_sugar_kelp_params(C.Structure):
+    _fields_ = [(n, C.c_double) for n in KELP_DOUBLES] + [("newton_iterations", C.c_int32), ("_pad", C.c_int32)]
+
+
+class obm_particles(C.Structure):
+    _fields_ = ([("n", C.c_int64)] + [(n, C.c_void_p) for n in ("x", "y", "z", "A", "N", "C", "scalefactors")]
+                + [(n, C.c_double) for n in ("x0", "dx", "y0", "dy")] + [("topology", C.c_int32 * 3), ("_pad", C.c_int32)])
+
+
+class obm_kelp_tracers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("u", "v", "w", "T", "NO3", "NH4", "PAR")]
+
+
 STRUCTS = {
+    "obm_sugar_kelp_params": obm_sugar_kelp_params,
+    "obm_particles": obm_particles,
+    "obm_kelp_tracers": obm_kelp_tracers,
     "obm_gas_exchange_params": obm_gas_exchange_params,
     "obm_sediment_params": obm_sediment_params,
     "obm_sediment_fields": obm_sediment_fields,
@@ -236,6 +271,11 @@ PROTOTYPES = {
                                                                 C.POINTER(obm_scale_group), C.c_double,
                                                                 C.POINTER(obm_carbchem_params)] + [C.c_void_p] * 8),
     "obm_zero_negative_tracers": (C.c_int, [C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
+    "obm_kelp_update_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sugar_kelp_params), C.POINTER(obm_particles),
+                                             C.POINTER(obm_kelp_tracers), C.c_void_p, C.c_double, C.c_void_p]),
+    "obm_kelp_step": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_sugar_kelp_params), C.POINTER(obm_particles),
+                                C.POINTER(obm_kelp_tracers), C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
+    "obm_kelp_seasonal_limitation": (C.c_double, [C.POINTER(obm_sugar_kelp_params), C.c_double]),
     "obm_sinking_tendencies": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p]),
     "obm_inventory_workspace_bytes": (C.c_int64, [C.c_int]),

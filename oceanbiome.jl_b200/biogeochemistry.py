@@ -24,8 +24,6 @@ class Biogeochemistry:
 
     def __init__(self, underlying_biogeochemistry, light_attenuation=None, sediment=None, particles=None,
                  modifiers=None):
-        if particles is not None:
-            raise NotImplementedError("BiogeochemicalParticles are outside the B200 hot path (SURVEY §2 row 9)")
         self.underlying_biogeochemistry = underlying_biogeochemistry
         self.light_attenuation = light_attenuation
         self.sediment = sediment
@@ -81,6 +79,8 @@ class Biogeochemistry:
                                                            accumulate=True, stream=stream, time=model.clock.time)
         if self.sediment is not None:
             self.sediment.update_tendencies(self, model, stream)
+        if self.particles is not None:  # OceanBioME.jl:150: update_tendencies!(bgc, bgc.particles, model)
+            self.particles.update_tendencies(self, model, stream)
 
     def __call__(self, *args):
         """Per-point callable `bgc(i, j, k, grid, Val(name), clock, fields)` — reduced to zero(grid)
@@ -214,10 +214,28 @@ class BiogeochemicalModel:
                                          current_stream_ptr(self.grid.device))
         _lib.check(rc, "obm_rk3_substep")
 
+    def step_lagrangian_particles(self):
+        """`step_lagrangian_particles!(model, Δt)` with Δt the stage just completed.  Oceananigans calls it at the END of
+        every stage, after `update_state!` has recomputed the tendencies; this stand-in calls `update_state` at the START
+        of a stage, so the same interleaving (substep → state → tendencies → particles → substep …) is obtained by
+        stepping the particles right after the tendencies — the last stage's particle step of a run is then pending
+        until the next stage, or `finish_particles()`."""
+        p = getattr(self.biogeochemistry, "particles", None)
+        if p is not None and self.clock.last_stage_dt != float("inf"):
+            p.step(self, self.clock.last_stage_dt)
+
+    def finish_particles(self):
+        """Bring the particles to the model time at the end of a run (state, tendencies, pending particle step)."""
+        self.update_state()
+        self.compute_tendencies()
+        self.step_lagrangian_particles()
+        self.clock.last_stage_dt = float("inf")
+
     def time_step(self, dt: float):
         if self.timestepper == "Euler":
             self.update_state()
             self.compute_tendencies()
+            self.step_lagrangian_particles()
             self._substep(dt, 1.0, None)
             self.clock.time += dt
             self.clock.last_stage_dt = dt
@@ -228,6 +246,7 @@ class BiogeochemicalModel:
                 self.clock.rk3_gamma, self.clock.rk3_zeta = gamma, (zeta if zeta else float("nan"))
                 self.update_state()
                 self.compute_tendencies()
+                self.step_lagrangian_particles()
                 self._substep(dt, gamma, zeta)
                 self.clock.time += dt * (gamma + zeta)
                 self.clock.last_stage_dt = dt * (gamma + zeta)

@@ -44,6 +44,9 @@ extern "C" int obm_sizeof(const char* name) {
     S(obm_sediment_params);
     S(obm_sediment_fields);
     S(obm_gas_exchange_params);
+    S(obm_sugar_kelp_params);
+    S(obm_particles);
+    S(obm_kelp_tracers);
 #undef S
     return OBM_EENUM;
 }

@@ -23,30 +23,43 @@
 namespace obm {
 namespace cc {
 
+// exp of the solve: the library exp.  (The lean exp of obm_common.cuh — OBM_CC_EXP = 1 / 2 — was measured here: its
+// four extra FP64 instructions and 8 more registers cost the fused scaling + Ω kernel 6 %, r02 profiles/.)
+#ifndef OBM_CC_EXP
+#define OBM_CC_EXP 0
+#endif
+__device__ __forceinline__ double cexp(double x) {
+#if OBM_CC_EXP == 0
+    return exp(x);
+#else
+    return exp_lean<OBM_CC_EXP>(x);
+#endif
+}
+
 // ---- TEOS-10 55-term polynomial (Roquet et al. 2015) as used through SeawaterPolynomials 0.3 ----
 __device__ __forceinline__ double teos10_rho(double T, double Sp, double Pbar) {
-    const double t = T * 0.025;
-    const double s = sqrt((Sp + 32.0) * (1.0 / (40.0 * 35.16504 / 35.0)));
-    const double z = -(10.0 * Pbar) * 1e-4;
-    const double r0 = (((((-1.7243708991e-03 * z + 1.5616995503e-02) * z + 6.4326772569e-02) * z + 2.2601900708e-01) * z
-                        + -5.2099962525e+00) * z + 4.6494977072e+01) * z;
-    const double rp3 = 3.7969820455e-01 * t + -1.8507636718e-02 * s + -2.3342758797e-02;
-    const double rp2 = (-1.2419983026e+00 * t + -2.1311365518e-01 * s + 2.0564311499e+00) * t
-                       + (2.5019633244e+00 * s + -4.9527603989e+00) * s + 2.0660924175e+00;
-    const double rp1 = (((5.5927935970e-01 * t + -5.5077101279e-01 * s + -2.4649669534e+00) * t
-                         + (-1.8795372996e+00 * s + 3.5063081279e+00) * s + 6.7080479603e+00) * t
-                        + ((-6.5399043664e-01 * s + 5.0042598061e+00) * s + -4.4870114575e+00) * s + -1.3336301113e+01) * t
-                       + (((6.6051753097e+00 * s + -3.0938076334e+01) * s + 5.0774768218e+01) * s + -4.2549998214e+01) * s
-                       + 1.9681925209e+01;
-    const double rp0 = (((((-1.9083568888e-01 * t + 4.8169980163e-01 * s + 5.4048723791e-01) * t
-                           + (-5.3563304045e+00 * s + 1.1311538584e+01) * s + -8.3627885467e+00) * t
-                          + ((-3.1742946532e+00 * s + 1.9717078466e+01) * s + -3.3449108469e+01) * s + 2.1661789529e+01) * t
-                         + (((-5.4723692739e+00 * s + 2.9130021253e+01) * s + -6.0362551501e+01) * s + 6.1548258127e+01) * s
-                         + -3.7074170417e+01) * t
-                        + ((((-1.9193502195e+00 * s + 1.7681814114e+01) * s + -5.6888046321e+01) * s + 8.1770425108e+01) * s
-                           + -6.5281885265e+01) * s + 2.6010145068e+01) * t
-                       + (((((-6.0579916612e+01 * s + 4.3227585684e+02) * s + -1.2849161071e+03) * s + 2.0375295546e+03) * s
-                           + -1.7864682637e+03) * s + 8.6672408165e+02) * s + 8.0189615746e+02;
+    const double t = T * KD(0.025);
+    const double s = sqrt((Sp + 32.0) * KD(1.0 / (40.0 * 35.16504 / 35.0)));
+    const double z = -(10.0 * Pbar) * KD(1e-4);
+    const double r0 = (((((KD(-1.7243708991e-03) * z + KD(1.5616995503e-02)) * z + KD(6.4326772569e-02)) * z + KD(2.2601900708e-01)) * z
+                        + KD(-5.2099962525e+00)) * z + KD(4.6494977072e+01)) * z;
+    const double rp3 = KD(3.7969820455e-01) * t + KD(-1.8507636718e-02) * s + KD(-2.3342758797e-02);
+    const double rp2 = (KD(-1.2419983026e+00) * t + KD(-2.1311365518e-01) * s + KD(2.0564311499e+00)) * t
+                       + (KD(2.5019633244e+00) * s + KD(-4.9527603989e+00)) * s + KD(2.0660924175e+00);
+    const double rp1 = (((KD(5.5927935970e-01) * t + KD(-5.5077101279e-01) * s + KD(-2.4649669534e+00)) * t
+                         + (KD(-1.8795372996e+00) * s + KD(3.5063081279e+00)) * s + KD(6.7080479603e+00)) * t
+                        + ((KD(-6.5399043664e-01) * s + KD(5.0042598061e+00)) * s + KD(-4.4870114575e+00)) * s + KD(-1.3336301113e+01)) * t
+                       + (((KD(6.6051753097e+00) * s + KD(-3.0938076334e+01)) * s + KD(5.0774768218e+01)) * s + KD(-4.2549998214e+01)) * s
+                       + KD(1.9681925209e+01);
+    const double rp0 = (((((KD(-1.9083568888e-01) * t + KD(4.8169980163e-01) * s + KD(5.4048723791e-01)) * t
+                           + (KD(-5.3563304045e+00) * s + KD(1.1311538584e+01)) * s + KD(-8.3627885467e+00)) * t
+                          + ((KD(-3.1742946532e+00) * s + KD(1.9717078466e+01)) * s + KD(-3.3449108469e+01)) * s + KD(2.1661789529e+01)) * t
+                         + (((KD(-5.4723692739e+00) * s + KD(2.9130021253e+01)) * s + KD(-6.0362551501e+01)) * s + KD(6.1548258127e+01)) * s
+                         + KD(-3.7074170417e+01)) * t
+                        + ((((KD(-1.9193502195e+00) * s + KD(1.7681814114e+01)) * s + KD(-5.6888046321e+01)) * s + KD(8.1770425108e+01)) * s
+                           + KD(-6.5281885265e+01)) * s + KD(2.6010145068e+01)) * t
+                       + (((((KD(-6.0579916612e+01) * s + KD(4.3227585684e+02)) * s + KD(-1.2849161071e+03)) * s + KD(2.0375295546e+03)) * s
+                           + KD(-1.7864682637e+03)) * s + KD(8.6672408165e+02)) * s + KD(8.0189615746e+02);
     return r0 + (((rp3 * z + rp2) * z + rp1) * z + rp0);
 }
 
@@ -70,67 +83,67 @@ template <bool HAS_P>
 __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool need_phosphate, bool need_silicate,
                                           Constants& c) {
     constexpr double LN10 = 2.302585092994045684;
-    const double T = Tc_in + 273.15;
+    const double T = Tc_in + KD(273.15);
     const double invT = rcp_fast(T);
     const double logT = log(T);
     const double sqS = sqrt(S);
     const double S15 = S * sqS;
-    const double Is = 19.924 * S * rcp_fast(1000.0 + -1.005 * S);  // :341
+    const double Is = KD(19.924) * S * rcp_fast(1000.0 + KD(-1.005) * S);  // :341
     const double sqIs = sqrt(Is);
     const double Is15 = Is * sqIs;
-    const double logS1 = log(1 + -0.001005 * S);
+    const double logS1 = log(1 + KD(-0.001005) * S);
     double Tc = 0, inv_RT = 0;
     if (HAS_P) {
-        Tc = T - 273.15;
-        inv_RT = invT * (1.0 / 83.14472);
+        Tc = T - KD(273.15);
+        inv_RT = invT * KD(1.0 / 83.14472);
     }
     // K1 :124-126, K2 :170-172 (10^x)
-    double e1 = 61.2172 + -3633.86 * invT + -9.67770 * logT + 0.011555 * S + -0.0001152 * (S * S);
-    double e2 = -25.9290 + -471.78 * invT + 0.01781 * S + -0.0001122 * (S * S) + 3.16967 * logT;
-    e1 *= LN10;
-    e2 *= LN10;
+    double e1 = KD(61.2172) + KD(-3633.86) * invT + KD(-9.67770) * logT + KD(0.011555) * S + KD(-0.0001152) * (S * S);
+    double e2 = KD(-25.9290) + KD(-471.78) * invT + KD(0.01781) * S + KD(-0.0001122) * (S * S) + KD(3.16967) * logT;
+    e1 *= KD(LN10);
+    e2 *= KD(LN10);
     // KB :243-250
-    double eB = 148.0248 + (-8966.90 + -2890.53 * sqS + -77.942 * S + 1.728 * S15 + -0.0996 * (S * S)) * invT
-                + 137.1942 * sqS + 1.62142 * S + (-24.4344 + -25.085 * sqS + -0.2474 * S) * logT + 0.053105 * sqS * T;
+    double eB = KD(148.0248) + (KD(-8966.90) + KD(-2890.53) * sqS + KD(-77.942) * S + KD(1.728) * S15 + KD(-0.0996) * (S * S)) * invT
+                + KD(137.1942) * sqS + KD(1.62142) * S + (KD(-24.4344) + KD(-25.085) * sqS + KD(-0.2474) * S) * logT + KD(0.053105) * sqS * T;
     // KW :307-313
-    double eW = 148.9652 + -13847.26 * invT + -23.6521 * logT + (-5.977 + 118.67 * invT + 1.0495 * logT) * sqS + -0.01615 * S;
+    double eW = KD(148.9652) + KD(-13847.26) * invT + KD(-23.6521) * logT + (KD(-5.977) + KD(118.67) * invT + KD(1.0495) * logT) * sqS + KD(-0.01615) * S;
     // KS :410-419
-    double eS = 141.328 + -4276.1 * invT + -23.093 * logT + (324.57 + -13856.0 * invT + -47.986 * logT) * sqIs
-                + (-771.54 + 35474.0 * invT + 114.723 * logT) * Is + -2698.0 * Is15 * invT + 1776.0 * (Is * Is) * invT + logS1;
+    double eS = KD(141.328) + KD(-4276.1) * invT + KD(-23.093) * logT + (KD(324.57) + -13856.0 * invT + KD(-47.986) * logT) * sqIs
+                + (KD(-771.54) + 35474.0 * invT + KD(114.723) * logT) * Is + -2698.0 * Is15 * invT + 1776.0 * (Is * Is) * invT + logS1;
     // KF :481-487 (log(1 + 0·S) terms are exactly 0)
-    double eF = -9.68 + 874.0 * invT + 0.111 * sqS;
+    double eF = KD(-9.68) + 874.0 * invT + KD(0.111) * sqS;
     if (HAS_P) {
-        e1 += ln_pc(-25.50, 0.1271, 0.0, -0.00308, 0.0000877, Tc, P, inv_RT);
-        e2 += ln_pc(-15.82, -0.0219, 0.0, 0.00113, -0.0001475, Tc, P, inv_RT);
-        eB += ln_pc(-29.48, 0.1622, -0.0026080, -0.00284, 0.0, Tc, P, inv_RT);
-        eW += ln_pc(-20.02, 0.1119, -0.001409, -0.00513, 0.0000794, Tc, P, inv_RT);
-        eS += ln_pc(-18.03, 0.0466, 0.000316, -0.00453, 0.00009, Tc, P, inv_RT);
-        eF += ln_pc(-9.78, -0.0090, -0.000942, -0.00391, 0.000054, Tc, P, inv_RT);
+        e1 += ln_pc(-25.50, KD(0.1271), 0.0, KD(-0.00308), KD(0.0000877), Tc, P, inv_RT);
+        e2 += ln_pc(KD(-15.82), KD(-0.0219), 0.0, KD(0.00113), KD(-0.0001475), Tc, P, inv_RT);
+        eB += ln_pc(KD(-29.48), KD(0.1622), KD(-0.0026080), KD(-0.00284), 0.0, Tc, P, inv_RT);
+        eW += ln_pc(KD(-20.02), KD(0.1119), KD(-0.001409), KD(-0.00513), KD(0.0000794), Tc, P, inv_RT);
+        eS += ln_pc(KD(-18.03), KD(0.0466), KD(0.000316), KD(-0.00453), KD(0.00009), Tc, P, inv_RT);
+        eF += ln_pc(KD(-9.78), KD(-0.0090), KD(-0.000942), KD(-0.00391), KD(0.000054), Tc, P, inv_RT);
     }
-    c.K1 = exp(e1);
-    c.K2 = exp(e2);
-    c.KB = exp(eB);
-    c.KW = exp(eW);
-    c.KS = exp(eS);
-    c.KF = exp(eF);
+    c.K1 = cexp(e1);
+    c.K2 = cexp(e2);
+    c.KB = cexp(eB);
+    c.KW = cexp(eW);
+    c.KS = cexp(eS);
+    c.KF = cexp(eF);
     c.KP1 = c.KP2 = c.KP3 = 1.0;
     if (need_phosphate) {  // KP1-3 :523-529, :558-651
-        double p1 = 115.525 + -4576.752 * invT + -18.453 * logT + (0.69171 + -106.736 * invT) * sqS + (-0.01844 + -0.65643 * invT) * S;
-        double p2 = 172.0883 + -8814.715 * invT + -27.927 * logT + (1.3566 + -160.340 * invT) * sqS + (-0.05778 + 0.37335 * invT) * S;
-        double p3 = -18.141 + -3070.75 * invT + 0.0 * logT + (2.81197 + 17.27039 * invT) * sqS + (-0.09984 + -44.99486 * invT) * S;
+        double p1 = KD(115.525) + KD(-4576.752) * invT + KD(-18.453) * logT + (KD(0.69171) + KD(-106.736) * invT) * sqS + (KD(-0.01844) + KD(-0.65643) * invT) * S;
+        double p2 = KD(172.0883) + KD(-8814.715) * invT + KD(-27.927) * logT + (KD(1.3566) + KD(-160.340) * invT) * sqS + (KD(-0.05778) + KD(0.37335) * invT) * S;
+        double p3 = KD(-18.141) + -3070.75 * invT + 0.0 * logT + (KD(2.81197) + KD(17.27039) * invT) * sqS + (KD(-0.09984) + KD(-44.99486) * invT) * S;
         if (HAS_P) {
-            p1 += ln_pc(-14.51, 0.1211, -0.000321, -0.00267, 0.0000427, Tc, P, inv_RT);
-            p2 += ln_pc(-23.12, 0.1758, -0.002647, -0.00515, 0.00009, Tc, P, inv_RT);
-            p3 += ln_pc(-26.57, 0.2020, -0.0030420, -0.00408, 0.0000714, Tc, P, inv_RT);
+            p1 += ln_pc(KD(-14.51), KD(0.1211), KD(-0.000321), KD(-0.00267), KD(0.0000427), Tc, P, inv_RT);
+            p2 += ln_pc(KD(-23.12), KD(0.1758), KD(-0.002647), KD(-0.00515), KD(0.00009), Tc, P, inv_RT);
+            p3 += ln_pc(KD(-26.57), KD(0.2020), KD(-0.0030420), KD(-0.00408), KD(0.0000714), Tc, P, inv_RT);
         }
-        c.KP1 = exp(p1);
-        c.KP2 = exp(p2);
-        c.KP3 = exp(p3);
+        c.KP1 = cexp(p1);
+        c.KP2 = cexp(p2);
+        c.KP3 = cexp(p3);
     }
     c.KSi = 1.0;
     if (need_silicate)  // KSi :706-713 (no pressure correction)
-        c.KSi = exp(117.385 + -8904.2 * invT + -19.334 * logT + (3.5913 + -458.79 * invT) * sqIs + (-1.5998 + 188.74 * invT) * Is
-                    + (0.07871 + -12.1652 * invT) * (Is * Is) + logS1);
+        c.KSi = cexp(KD(117.385) + KD(-8904.2) * invT + KD(-19.334) * logT + (KD(3.5913) + KD(-458.79) * invT) * sqIs + (KD(-1.5998) + KD(188.74) * invT) * Is
+                    + (KD(0.07871) + KD(-12.1652) * invT) * (Is * Is) + logS1);
     c.Tk = T;
     c.Is = Is;
     c.sqrtS = sqS;
@@ -200,10 +213,10 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
         double dx = f * rcp_fast(Hdf);
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
-        H *= exp(-dx);
+        H *= cexp(-dx);
         // Warp-uniform early exit (no divergence): once every lane's step is below 1e-7 the quadratic convergence
         // of Newton puts the next iterate within ~1e-14 of the root; NaN lanes count as converged (they stay NaN).
-        if (__all_sync(mask, !(fabs(dx) >= 1e-7))) break;
+        if (__all_sync(mask, !(fabs(dx) >= KD(1e-7)))) break;
     }
     return H;
 }
@@ -218,13 +231,13 @@ __device__ __forceinline__ double initial_H(const Constants& c, const Totals& t,
     const double b = c.K1 * (AC - t.DIC);
     const double disc = b * b - 4.0 * AC * (c.K1 * c.K2) * (AC - 2.0 * t.DIC);
     const double H0 = (sqrt(disc) - b) * rcp_fast(2.0 * AC);
-    return (H0 > 1e-12 && H0 < 1e-3) ? H0 : H_init;  // NaN (disc < 0, AC ≤ 0 …) fails both comparisons
+    return (H0 > KD(1e-12) && H0 < KD(1e-3)) ? H0 : H_init;  // NaN (disc < 0, AC ≤ 0 …) fails both comparisons
 }
 
 // K0 — equilibrium_constants.jl:65-80
 __device__ __forceinline__ double K0(double T, double logT, double S) {
-    return exp(-60.2409 + (93.4517 * 100) * rcp_fast(T) + 23.3585 * (logT - 4.605170185988092) + 0.0 * (T * T)
-               + (0.023517 + (-0.023656 / 100) * T + (0.0047036 / (100.0 * 100.0)) * (T * T)) * S);
+    return cexp(KD(-60.2409) + KD(93.4517 * 100) * rcp_fast(T) + KD(23.3585) * (logT - KD(4.605170185988092)) + 0.0 * (T * T)
+               + (KD(0.023517) + KD(-0.023656 / 100) * T + KD(0.0047036 / (100.0 * 100.0)) * (T * T)) * S);
 }
 
 // KSP calcite — equilibrium_constants.jl:754-764, :789-810 (the log10(T) in a "ln K" is the reference's, :758)
@@ -232,11 +245,11 @@ template <bool HAS_P>
 __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P) {
     constexpr double LN10 = 2.302585092994045684;
     const double iT = rcp_fast(T);
-    const double therm = -171.9065 + -0.077993 * T + 2839.319 * iT + 71.595 * (logT * (1.0 / LN10));
-    const double sea = ((-0.77712 + 0.0028426 * T + 178.34 * iT) * sqS + -0.07711 * S + 0.0041249 * (S * sqS));
-    double e = (therm + sea) * LN10;
-    if (HAS_P) e += ln_pc(-48.76, 0.5304, -0.0, -0.01176, 0.0003692, T - 273.15, P, iT * (1.0 / 83.14472));
-    return exp(e);
+    const double therm = KD(-171.9065) + KD(-0.077993) * T + KD(2839.319) * iT + KD(71.595) * (logT * KD(1.0 / LN10));
+    const double sea = ((KD(-0.77712) + KD(0.0028426) * T + KD(178.34) * iT) * sqS + KD(-0.07711) * S + KD(0.0041249) * (S * sqS));
+    double e = (therm + sea) * KD(LN10);
+    if (HAS_P) e += ln_pc(KD(-48.76), KD(0.5304), -0.0, KD(-0.01176), KD(0.0003692), T - KD(273.15), P, iT * KD(1.0 / 83.14472));
+    return cexp(e);
 }
 
 // The whole `(p::CarbonChemistry)(; DIC, T, S, Alk, pH, P, output, silicate, phosphate)` call.
@@ -251,15 +264,15 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     const double rho = teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
     Constants c;
     constants<HAS_P>(T, S, P, has_phos, has_sil, c);
-    const double scale = 1e-3 * rcp_fast(rho);
+    const double scale = KD(1e-3) * rcp_fast(rho);
     Totals t;
     t.DIC = DIC * scale;
     t.Alk = Alk * scale;
     t.phosphate = phosphate * scale;
     t.silicate = silicate * scale;
-    t.boron = 0.000232 / 10.811 * S * (1.0 / 1.80655);
-    t.sulfate = 0.14 / 96.06 * S * (1.0 / 1.80655);
-    t.fluoride = 0.000067 / 18.9984 * S * (1.0 / 1.80655);
+    t.boron = KD(0.000232 / 10.811) * S * KD(1.0 / 1.80655);
+    t.sulfate = KD(0.14 / 96.06) * S * KD(1.0 / 1.80655);
+    t.fluoride = KD(0.000067 / 18.9984) * S * KD(1.0 / 1.80655);
 
     {
         const double sd = 1 + t.sulfate * rcp_fast(c.KS);
@@ -268,11 +281,11 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     }
     double H;
     if (has_pH) {
-        H = exp(-pH * LN10);
+        H = cexp(-pH * KD(LN10));
     } else {
         // warm start: [H⁺] kept from the previous call on this cell, if it is a plausible value (pH 2 … 13)
         double H0 = H_io ? *H_io : 0.0;
-        if (!(H0 > 1e-13 && H0 < 1e-2)) H0 = initial_H(c, t, H_init);
+        if (!(H0 > KD(1e-13) && H0 < KD(1e-2))) H0 = initial_H(c, t, H_init);
         H = solve_H(c, t, has_phos, has_sil, H0, iterations);
         if (H_io) *H_io = H;
     }
@@ -290,7 +303,7 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
             const double denom2 = (1.0 + c.K1 * c.K2 * rcp_fast(denom1));
             const double CO3 = t.DIC * c.K1 * c.K2 * rcp_fast(denom1 * denom2);
             if (output_kind == OBM_CC_CO3) return CO3;
-            const double calcium = 0.0103 * S * (1.0 / 35);
+            const double calcium = KD(0.0103) * S * KD(1.0 / 35);
             return calcium * CO3 * rcp_fast(KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P));
         }
         default: break;
@@ -301,20 +314,20 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     // pCO₂: carbon_chemistry.jl:170-193 (3 fixed-point virial iterations)
     const double Pp = (HAS_P ? P : 1.0) * 101325.0;
     const double Tk = c.Tk;
-    const double B = (-1636.75 + 12.0408 * Tk + -3.27957e-2 * (Tk * Tk) + 3.16528e-5 * (Tk * Tk * Tk)) * 1e-6;
-    const double dl = (57.7 + -0.118 * Tk) * 1e-6;
-    fCO2 *= 0.09807;
+    const double B = (-1636.75 + KD(12.0408) * Tk + KD(-3.27957e-2) * (Tk * Tk) + KD(3.16528e-5) * (Tk * Tk * Tk)) * KD(1e-6);
+    const double dl = (KD(57.7) + KD(-0.118) * Tk) * KD(1e-6);
+    fCO2 *= KD(0.09807);
     double phi = 1.0;
     const double iPp = rcp_fast(Pp);
-    const double iRT = rcp_fast(8.31446261815324 * Tk);
+    const double iRT = rcp_fast(KD(8.31446261815324) * Tk);
     double x = fCO2 * iPp;
 #pragma unroll
     for (int n = 0; n < 3; n++) {
         const double om = 1.0 - x;
-        phi = exp((B + 2.0 * (om * om) * dl) * Pp * iRT);
+        phi = cexp((B + 2.0 * (om * om) * dl) * Pp * iRT);
         x = fCO2 * rcp_fast(phi) * iPp;
     }
-    return fCO2 * rcp_fast(phi) * (1.0 / 0.09807);
+    return fCO2 * rcp_fast(phi) * KD(1.0 / 0.09807);
 }
 
 }  // namespace cc

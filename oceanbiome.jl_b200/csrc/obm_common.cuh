@@ -51,6 +51,15 @@ __device__ __forceinline__ double rcp_fast(double b) {
     return fma(fma(e, e, e), r, r);
 }
 
+// KD(x): the double literal x as a constant-bank operand.  ptxas materialises a 64-bit FP immediate with TWO moves
+// (UMOV lo / UMOV hi) in front of every use — in the carbonate solve (≈ 150 literals: TEOS-10, the equilibrium
+// constants, their pressure corrections) that was more issue slots than the arithmetic itself (805 moves vs 693 FP64
+// instructions, static).  A variable template keyed by the bit pattern puts each distinct literal in bank 3 once; it is
+// then fetched by one LDC(U).64 — or two neighbours by one LDCU.128 — and the value is bit-identical.
+template <unsigned long long BITS>
+static __constant__ double CONST_BANK_DOUBLE = __builtin_bit_cast(double, BITS);
+#define KD(x) (::obm::CONST_BANK_DOUBLE<__builtin_bit_cast(unsigned long long, (double)(x))>)
+
 // Lean exp for latency-bound kernels: k = round(x·log₂e) by the 1.5·2⁵² shift, r = x − k·ln2 (two-term Cody–Waite),
 // e^r = (1 + r) + r²·Q(r) with Q the degree-11 Taylor tail Σ r^m/(m+2)! (|r| ≤ ln2/2 ⇒ truncation < 2⁻⁵⁷), then the
 // exponent of the result is advanced by k.  ≤ 2 ulp for |x| < 700; anything else (overflow, underflow to subnormals
@@ -65,12 +74,12 @@ static __device__ __noinline__ double exp_library(double x) { return exp(x); }  
 template <int SCHEME>
 __device__ __forceinline__ double exp_lean(double x) {
     if (!(fabs(x) < 700.0)) return exp_library(x);
-    const double SHIFT = 6755399441055744.0;
-    const double t = fma(x, 1.4426950408889634, SHIFT);
+    const double SHIFT = KD(6755399441055744.0);
+    const double t = fma(x, KD(1.4426950408889634), SHIFT);
     const int k = __double2loint(t);
     const double kf = t - SHIFT;
-    double r = fma(kf, -6.93147180559945286e-01, x);
-    r = fma(kf, -2.31904681384629956e-17, r);
+    double r = fma(kf, KD(-6.93147180559945286e-01), x);
+    r = fma(kf, KD(-2.31904681384629956e-17), r);
     const double r2 = r * r;
     const double a0 = 1.0 + r;
     double Q;

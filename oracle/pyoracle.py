@@ -422,3 +422,89 @@ def sinking_tendencies(grid: Grid, tracers, w_faces, G, advection=0, accumulate=
                                       int(advection), int(accumulate))
     assert rc == 0
     return G
+
+
+# ---- particles / sugar kelp -------------------------------------------------------------------------------------
+KELP_NAMES = ("A", "N", "C", "NO₃", "NH₄", "DIC", "O₂", "DOC", "DON", "bPOC", "bPON")
+
+
+def _kelp_protos():
+    L = lib()
+    if getattr(L, "_kelp_ready", False):
+        return L
+    L.orc_kelp.restype = C.c_double
+    L.orc_kelp.argtypes = [C.POINTER(abi.obm_sugar_kelp_params), C.c_int] + [C.c_double] * 11
+    L.orc_kelp_seasonal_limitation.restype = C.c_double
+    L.orc_kelp_seasonal_limitation.argtypes = [C.POINTER(abi.obm_sugar_kelp_params), C.c_double]
+    L.orc_kelp_light_inhibition.restype = C.c_double
+    L.orc_kelp_light_inhibition.argtypes = [C.POINTER(abi.obm_sugar_kelp_params), C.c_double, C.POINTER(C.c_int)]
+    L.orc_particle_cell.restype = C.c_int64
+    L.orc_particle_cell.argtypes = [C.POINTER(abi.obm_grid), C.POINTER(abi.obm_particles), C.c_int64]
+    L.orc_kelp_update_tendencies.restype = C.c_int
+    L.orc_kelp_update_tendencies.argtypes = [C.POINTER(abi.obm_grid), C.POINTER(abi.obm_sugar_kelp_params),
+                                             C.POINTER(abi.obm_particles), C.POINTER(abi.obm_kelp_tracers), C.c_void_p, C.c_double]
+    L.orc_kelp_step.restype = C.c_int
+    L.orc_kelp_step.argtypes = [C.POINTER(abi.obm_grid), C.POINTER(abi.obm_sugar_kelp_params), C.POINTER(abi.obm_particles),
+                                C.POINTER(abi.obm_kelp_tracers), C.c_double, C.c_double, C.c_void_p]
+    L._kelp_ready = True
+    return L
+
+
+def kelp(params, name, t, A, N, Cr, T, NO3, NH4, PAR, u=0.0, v=0.0, w=0.0):
+    """`kelp(Val(name), t, A, N, C, u, v, w, T, NO₃, NH₄, PAR)` for name in KELP_NAMES (equations.jl, coupling.jl)."""
+    return _kelp_protos().orc_kelp(C.byref(params), KELP_NAMES.index(name), t, A, N, Cr, u, v, w, T, NO3, NH4, PAR)
+
+
+def kelp_seasonal_limitation(params, t):
+    return _kelp_protos().orc_kelp_seasonal_limitation(C.byref(params), t)
+
+
+def kelp_light_inhibition(params, Pm):
+    """β of solve_for_light_inhibition with the reference's solver; returns (β, iterations taken)."""
+    n = C.c_int(0)
+    b = _kelp_protos().orc_kelp_light_inhibition(C.byref(params), Pm, C.byref(n))
+    return b, n.value
+
+
+def make_particles(x, y, z, A, N, Cr, scalefactors, x0, dx, y0, dy, topology):
+    """obm_particles over host arrays (kept alive by the returned tuple)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (x, y, z, A, N, Cr, scalefactors)]
+    q = abi.obm_particles()
+    q.n = len(arrs[0])
+    for name, a in zip(("x", "y", "z", "A", "N", "C", "scalefactors"), arrs):
+        setattr(q, name, a.ctypes.data if a is not None else None)
+    q.x0, q.dx, q.y0, q.dy = x0, dx, y0, dy
+    for c in range(3):
+        q.topology[c] = topology[c]
+    return q, arrs
+
+
+def make_kelp_tracers(T, NO3, NH4, PAR, u=None, v=None, w=None):
+    f = abi.obm_kelp_tracers()
+    keep = []
+    for name, a in (("T", T), ("NO3", NO3), ("NH4", NH4), ("PAR", PAR), ("u", u), ("v", v), ("w", w)):
+        if a is not None:
+            _check([a])
+            keep.append(a)
+            setattr(f, name, a.ctypes.data)
+    return f, keep
+
+
+def particle_cell(grid: Grid, q, n):
+    cg = grid.c_grid()
+    return _kelp_protos().orc_particle_cell(C.byref(cg), C.byref(q), n)
+
+
+def kelp_update_tendencies(grid: Grid, params, q, f, G, t):
+    """G: list of 8 parent arrays (or None) in coupled_tracers order; updated in place."""
+    _check([g for g in G if g is not None])
+    cg = grid.c_grid()
+    rc = _kelp_protos().orc_kelp_update_tendencies(C.byref(cg), C.byref(params), C.byref(q), C.byref(f), _table(G), t)
+    assert rc == 0
+
+
+def kelp_step(grid: Grid, params, q, f, t, dt, tendencies_out=None):
+    cg = grid.c_grid()
+    rc = _kelp_protos().orc_kelp_step(C.byref(cg), C.byref(params), C.byref(q), C.byref(f), t, dt,
+                                      _table(tendencies_out) if tendencies_out is not None else None)
+    assert rc == 0

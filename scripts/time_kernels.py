@@ -34,4 +34,7 @@ res["tendency_Gcell_s"] = w.cells / res["tendencies_ms"] / 1e6
 u = bgc.underlying_biogeochemistry
 res["tendencies_overwrite_ms"] = timeit(lambda: u.compute_tendencies(m.grid, m.tracers, bgc.biogeochemical_auxiliary_fields(), m.Gn,
                                                                       accumulate=False, time=m.clock.time))
+if len(sys.argv) > 3 and sys.argv[3] == "carbon":
+    wc = bench.Workload("carbon_c5", dev, 0.25)
+    res["carbon_sweep_ms_25M"] = timeit(lambda: wc.step())
 print(json.dumps(res))
