@@ -135,6 +135,20 @@ class Workload:
         self.launches_per_step = 1
         self.step_kernels = ["carbon_sweep_kernel"]
 
+    def capture(self):
+        """One stage (all hooks) as a CUDA graph on the current stream; parameters evaluated on the host (day length,
+        surface PAR) are frozen at their capture-time values, which is what a static synthetic bench state has anyway."""
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self.step()
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.step()
+        return self.graph
+
     # ---- one step of the hot path, inputs resident in HBM -------------------------------------------
     def step(self, ev=None):
         if self.kind == "carbon":
@@ -401,6 +415,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink Ny (or n) for quick checks; not a bench number")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the stage as one CUDA graph (auto: when the working set fits L2, i.e. the stage is launch-bound)")
     ap.add_argument("--e2e-slabs", type=int, default=0, help="x-y slabs of the e2e pipeline (0: default)")
     ap.add_argument("--copy-engine", default="dma", choices=["sm", "dma", "sm_h2d", "sm_d2h"],
                     help="host<->device slab copies of the e2e leg: persistent copy kernel (sm) or cudaMemcpy2DAsync (dma)")
@@ -431,18 +447,42 @@ def main():
     for _ in range(args.warmup):
         w.step()
     barrier()
+    # A working set that fits the 126 MB L2 (configs C1, C2) is (a) evicted before every step by a 256 MB write that
+    # is left out of the timing, and (b) launch-bound: its stage — three tiny launches — is replayed as ONE CUDA
+    # graph, which removes the host's per-launch cost (≈ 35 µs per hook call from Python) the way the box-model driver
+    # does.  Large workloads keep one event pair around all K steps, as before.
+    small = w.cells * w.tendency_bytes_per_cell <= 4e8
+    use_graph = args.graph == "on" or (args.graph == "auto" and small and w.kind != "carbon")
+    if use_graph:
+        w.capture()
+    flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device=device) if small else None
     # ---- timed region: K steps, CUDA events on the launching stream --------------------------------
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.start()
     launches = 0
     t0.record()
     for s in range(args.steps):
-        launches += w.step(ev[s])
+        if small:
+            flush.fill_(float(s))
+            sev[s][0].record()
+        if use_graph:
+            w.graph.replay()
+            launches += len(w.step_kernels)
+        else:
+            launches += w.step(ev[s])
+        if small:
+            sev[s][1].record()
     t1.record()
     barrier()
     sampler.stop_flag = True
-    ms = t0.elapsed_time(t1)
+    ms = sum(a.elapsed_time(b) for a, b in sev) if small else t0.elapsed_time(t1)
+    if use_graph:  # the tendency kernel's own time: a few eager steps with an event pair around it
+        for s in range(args.steps):
+            flush.fill_(float(s)) if small else None
+            w.step(ev[s])
+        torch.cuda.synchronize(device)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
@@ -517,8 +557,9 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "description": w.description, "cells_per_gpu": w.cells,
-                   "l2": "inputs larger than L2 (no flush needed)" if w.cells * w.tendency_bytes_per_cell > 4e8
-                         else "working set fits L2: reported as is, see DESIGN.md",
+                   "l2": "inputs larger than L2 (no flush needed)" if not small
+                         else "working set fits L2: evicted by a 256 MB write before every step (not timed); time = sum of per-step event pairs",
+                   "cuda_graph": bool(use_graph),
                    "parallelism": f"xy-slab x{world}, no data-path collective",
                    "carbonate_solve": "cold start from pH 8 every step (warm start disabled: static synthetic state)"},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
