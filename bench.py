@@ -545,7 +545,9 @@ def main():
     roofline = {"bound": "hbm", "kernel": w.step_kernels[-1] if w.step_kernels else None, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_cell": w.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
-                "kernel_share_of_step": kernel_ms / (ms / args.steps)}
+                # graph mode: kernel_ms comes from separate eager launches (it includes their launch latency, which the
+                # graphed stage does not pay), so a share of the graphed step would be meaningless
+                "kernel_share_of_step": None if use_graph else kernel_ms / (ms / args.steps)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         desc, cfg = workload_table()[name]
