@@ -44,6 +44,11 @@ function update_biogeochemical_state!(bgc::B200Biogeochemistry, model)
     ref = bgc.reference
     # 1. modifiers — all ScaleNegativeTracers groups in ONE launch (src/Utils/negative_tracers.jl:137-176)
     #    check(ccall((:obm_scale_negative_tracers, libobm), Cint, (Ref{ObmGrid}, Cint, Ptr{CuPtr{Float64}}, Cint, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}), …))
+    #    PISCES: the same launch also leaves Ω (step 3's obm_calcite_saturation is then skipped) —
+    #    check(ccall((:obm_scale_negative_tracers_calcite_saturation, libobm), Cint,
+    #                (Ref{ObmGrid}, Cint, Ptr{CuPtr{Float64}}, Cint, Ptr{Cvoid}, Cdouble, Ref{ObmCarbchemParams},
+    #                 CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Ptr{Cvoid}),
+    #                g, ntracers, tracer_table, ngroups, groups, NaN, carbchem, T, S, DIC, Alk, Si, Ω, H_state, s))
     # 2. light (src/Light/2band.jl:148-155): surface_PAR evaluated here into a scalar / 2-D field, then
     PAR = ref.light_attenuation
     surface = Float64(OceanBioME.Light.default_surface_PAR(model.clock.time))
@@ -68,7 +73,8 @@ function update_biogeochemical_state!(bgc::B200Biogeochemistry, model)
                     pointer(parent(t.Alk)), pointer(parent(t.Si)), pointer(parent(u.calcite_saturation)),
                     pointer(parent(bgc.hydrogen_ion_state)), s), "obm_calcite_saturation")
     end
-    # 4. sediment: obm_sediment_update_state (src/Sediments/update_state.jl:6-16)
+    # 4. sediment: obm_sediment_update_state(g, params, fields, model.clock.last_stage_Δt, χ, s) — the sediment's whole
+    #    time_step! (AB2 step, or all three RK3 stages) in one launch (src/Sediments/update_state.jl:6-16)
     # 5. gas-exchange boundary conditions: obm_gas_exchange_flux into the flux field of each FluxBoundaryCondition
     return nothing
 end
@@ -96,5 +102,13 @@ function update_tendencies!(bgc::B200Biogeochemistry, model)
           "obm_npd_tendencies")
     return nothing
 end
+
+# Particles (src/Particles): `update_tendencies!(bgc, particles::BiogeochemicalParticles{<:SugarKelp}, model)` →
+# obm_kelp_update_tendencies (all 8 coupled tracers, one launch);  `time_step_particle_fields!(::ForwardEuler, …)` →
+# obm_kelp_step.  ObmParticles carries pointer(particles.x), …, pointer(particles.fields.A), …, the first cell centre
+# and spacing in x and y, and the topology codes; ObmKelpTracers the parents of u, v, w, T, NO₃, NH₄ and PAR.
+#
+# Column / box models without resolved flow: `obm_sinking_tendencies(g, n, tracers, w_faces, Gⁿ, scheme, 1, s)` adds
+# −∂z(w c) of every sinking tracer (w = biogeochemical_drift_velocity(bgc, Val(c)).w) in one launch.
 
 end # module

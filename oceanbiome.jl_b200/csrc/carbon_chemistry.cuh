@@ -23,8 +23,8 @@
 namespace obm {
 namespace cc {
 
-// exp of the solve: the library exp.  (The lean exp of obm_common.cuh — OBM_CC_EXP = 1 / 2 — was measured here: its
-// four extra FP64 instructions and 8 more registers cost the fused scaling + Ω kernel 6 %, r02 profiles/.)
+// exp of the solve: the library exp.  (The lean exp of obm_common.cuh, -DOBM_CC_EXP=1, was measured here: its four
+// extra FP64 instructions and 8 more registers cost the fused scaling + Ω kernel 6 %, profiles/r02_kernel_variants.txt.)
 #ifndef OBM_CC_EXP
 #define OBM_CC_EXP 0
 #endif
@@ -32,7 +32,7 @@ __device__ __forceinline__ double cexp(double x) {
 #if OBM_CC_EXP == 0
     return exp(x);
 #else
-    return exp_lean<OBM_CC_EXP>(x);
+    return exp_lean(x);
 #endif
 }
 

@@ -20,16 +20,17 @@
 
 namespace obm {
 
-// exp of the scans: the lean even/odd-Horner exp of obm_common.cuh (≈ 26 instructions, ≤ 2 ulp, library call for
-// |x| ≥ 700 / NaN) — these kernels are issue-bound on their 4 (two-band) / 2·bands (N-band) exps per cell.
+// exp of the scans: the lean exp of obm_common.cuh (≈ 26 instructions, ≤ 2 ulp, library call for |x| ≥ 700 / NaN) —
+// these kernels are issue-bound on their 4 (two-band) / 2·bands (N-band) exps per cell: 3-band PAR 3.2 → 2.65 ms.
+// -DOBM_LIGHT_EXP=0 restores the library exp.
 #ifndef OBM_LIGHT_EXP
-#define OBM_LIGHT_EXP 2
+#define OBM_LIGHT_EXP 1
 #endif
 __device__ __forceinline__ double lexp(double x) {
 #if OBM_LIGHT_EXP == 0
     return exp(x);
 #else
-    return exp_lean<OBM_LIGHT_EXP>(x);
+    return exp_lean(x);
 #endif
 }
 

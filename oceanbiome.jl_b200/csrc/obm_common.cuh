@@ -60,18 +60,18 @@ template <unsigned long long BITS>
 static __constant__ double CONST_BANK_DOUBLE = __builtin_bit_cast(double, BITS);
 #define KD(x) (::obm::CONST_BANK_DOUBLE<__builtin_bit_cast(unsigned long long, (double)(x))>)
 
-// Lean exp for latency-bound kernels: k = round(x·log₂e) by the 1.5·2⁵² shift, r = x − k·ln2 (two-term Cody–Waite),
-// e^r = (1 + r) + r²·Q(r) with Q the degree-11 Taylor tail Σ r^m/(m+2)! (|r| ≤ ln2/2 ⇒ truncation < 2⁻⁵⁷), then the
-// exponent of the result is advanced by k.  ≤ 2 ulp for |x| < 700; anything else (overflow, underflow to subnormals
-// or 0, NaN) takes the library call, out of line behind a rarely taken branch.
-//   SCHEME 1: Estrin (pairs, r², r⁴ blocks) — dependent depth 5 after r, but two constants per pair FMA (12 LDC);
-//   SCHEME 2: even/odd Horner chains in r² — depth 7, ONE constant per FMA, which rides as a constant-bank operand:
-//             ≈ 26 instructions against ≈ 45 for the library exp (whose 64-bit immediates cost two moves each).
+// Lean exp: k = round(x·log₂e) by the 1.5·2⁵² shift, r = x − k·ln2 (two-term Cody–Waite), e^r = (1 + r) + r²·Q(r) with Q
+// the degree-11 Taylor tail Σ r^m/(m+2)! (|r| ≤ ln2/2 ⇒ truncation < 2⁻⁵⁷) as even / odd Horner chains in r² — ONE
+// constant per FMA, fetched from the constant bank — then the exponent of the result is advanced by k.  ≈ 26
+// instructions against ≈ 45 for the library exp (whose 64-bit immediates cost two moves each); ≤ 2 ulp for |x| < 700;
+// anything else (overflow, underflow to subnormals or 0, NaN) takes the library call, out of line behind a rarely
+// taken branch.  Used by the PAR scans (issue-bound); measured and NOT adopted in the PISCES tendency kernel (± 0) and
+// the carbonate solve (+6 %: 4 more FP64 instructions per call) — an Estrin variant was slower everywhere (two
+// constants per pair FMA) and is gone.
 static __constant__ double EXP_C[12] = {  // 1/n!, n = 2 … 13
     0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
     1.0 / 479001600, 1.0 / 6227020800.0};
 static __device__ __noinline__ double exp_library(double x) { return exp(x); }  // out of line: keeps the hot code short
-template <int SCHEME>
 __device__ __forceinline__ double exp_lean(double x) {
     if (!(fabs(x) < 700.0)) return exp_library(x);
     const double SHIFT = KD(6755399441055744.0);
@@ -82,33 +82,17 @@ __device__ __forceinline__ double exp_lean(double x) {
     r = fma(kf, KD(-2.31904681384629956e-17), r);
     const double r2 = r * r;
     const double a0 = 1.0 + r;
-    double Q;
-    if (SCHEME == 1) {
-        const double a1 = fma(EXP_C[1], r, EXP_C[0]);
-        const double a2 = fma(EXP_C[3], r, EXP_C[2]);
-        const double a3 = fma(EXP_C[5], r, EXP_C[4]);
-        const double a4 = fma(EXP_C[7], r, EXP_C[6]);
-        const double a5 = fma(EXP_C[9], r, EXP_C[8]);
-        const double a6 = fma(EXP_C[11], r, EXP_C[10]);
-        const double r4 = r2 * r2;
-        const double b0 = fma(a2, r2, a1);
-        const double b1 = fma(a4, r2, a3);
-        const double b2 = fma(a6, r2, a5);
-        Q = fma(fma(b2, r4, b1), r4, b0);
-    } else {
-        double e = fma(EXP_C[10], r2, EXP_C[8]);
-        double o = fma(EXP_C[11], r2, EXP_C[9]);
-        e = fma(e, r2, EXP_C[6]);
-        o = fma(o, r2, EXP_C[7]);
-        e = fma(e, r2, EXP_C[4]);
-        o = fma(o, r2, EXP_C[5]);
-        e = fma(e, r2, EXP_C[2]);
-        o = fma(o, r2, EXP_C[3]);
-        e = fma(e, r2, EXP_C[0]);
-        o = fma(o, r2, EXP_C[1]);
-        Q = fma(o, r, e);
-    }
-    const double p = fma(Q, r2, a0);
+    double e = fma(EXP_C[10], r2, EXP_C[8]);
+    double o = fma(EXP_C[11], r2, EXP_C[9]);
+    e = fma(e, r2, EXP_C[6]);
+    o = fma(o, r2, EXP_C[7]);
+    e = fma(e, r2, EXP_C[4]);
+    o = fma(o, r2, EXP_C[5]);
+    e = fma(e, r2, EXP_C[2]);
+    o = fma(o, r2, EXP_C[3]);
+    e = fma(e, r2, EXP_C[0]);
+    o = fma(o, r2, EXP_C[1]);
+    const double p = fma(fma(o, r, e), r2, a0);
     return __hiloint2double(__double2hiint(p) + (int)((unsigned)k << 20), __double2loint(p));
 }
 

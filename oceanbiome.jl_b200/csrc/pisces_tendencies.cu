@@ -67,7 +67,7 @@ constexpr int NOUT = 24;  // tendencies
 // compare + select.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
 // by a min/max) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
 #ifndef OBM_PISCES_EXP
-#define OBM_PISCES_EXP 0  // 0: library exp; 1 / 2: exp_lean schemes of obm_common.cuh (measured: no gain here, r02)
+#define OBM_PISCES_EXP 0  // 0: library exp; 1: exp_lean of obm_common.cuh (measured: no gain here, r02)
 #endif
 template <bool EXACT>
 struct Ar {
@@ -94,7 +94,7 @@ struct Ar {
 #if OBM_PISCES_EXP == 0
         return exp(x);
 #else
-        return EXACT ? exp(x) : exp_lean<OBM_PISCES_EXP>(x);
+        return EXACT ? exp(x) : exp_lean(x);
 #endif
     }
 };
