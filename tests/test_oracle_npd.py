@@ -113,3 +113,37 @@ def test_npzd_defaults_and_oxygen_dead_dispatch(oracle, one):
     assert np.isclose(G["O₂"], 10.75 * mu, rtol=1e-14)
     assert G["T"] == 0.0
     assert abs(G["N"] + G["P"] + G["Z"] + G["D"]) <= 4e-16 * sum(abs(G[n]) for n in "NPZD")
+
+
+# ---- absolute values: the C oracle against an independent transliteration of the reference ------------------------
+def _golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "npd_tendencies.json"), encoding="utf-8"))["cases"]
+
+
+GOLDEN_MODELS = {
+    "lobster": lambda: ob.NutrientsPlanktonDetritus(ob.NitrateAmmonia(), ob.PhytoZoo(), ob.TwoParticleAndDissolved()),
+    "lobster_carbonate_oxygen": lambda: ob.NutrientsPlanktonDetritus(ob.NitrateAmmonia(), ob.PhytoZoo(), ob.TwoParticleAndDissolved(),
+                                                                     ob.CarbonateSystem(), ob.Oxygen()),
+    "lobster_iron_variable_redfield_carbonate_oxygen": lambda: ob.NutrientsPlanktonDetritus(
+        ob.NitrateAmmoniaIron(), ob.PhytoZoo(), ob.VariableRedfieldDetritus(), ob.CarbonateSystem(), ob.Oxygen()),
+    "npzd": lambda: ob.NPZD(ob.RectilinearGrid(size=(1, 1, 1), extent=(1, 1, 2), device="cpu")).underlying_biogeochemistry,
+    "npzd_carbonate_oxygen": lambda: ob.NPZD(ob.RectilinearGrid(size=(1, 1, 1), extent=(1, 1, 2), device="cpu"),
+                                             carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen()).underlying_biogeochemistry,
+}
+
+
+@pytest.mark.parametrize("case", sorted(GOLDEN_MODELS))
+def test_c_oracle_matches_independent_restatement(oracle, one, case):
+    """tests/golden/npd_tendencies.json holds tendencies computed by oracle/pyref_npd.py, a method-by-method Python
+    transliteration of the reference that shares no code with oracle_npd.c (scripts/make_npd_golden.py).  Two
+    independent readings of the same source must agree to rounding: 1e-15 of the largest term of the model."""
+    g = _golden()[case]
+    bgc = GOLDEN_MODELS[case]()
+    assert list(bgc.required_biogeochemical_tracers()) == g["tracers"]
+    for row in g["rows"]:
+        got = tendencies(oracle, one, bgc, row["state"], PAR=row["state"]["PAR"])
+        scale = max(abs(v) for v in row["tendencies"].values())
+        for n, want in row["tendencies"].items():
+            assert abs(got[n] - want) <= 2e-15 * scale, (case, n, got[n], want)
