@@ -27,6 +27,39 @@ TRACERS = ("P", "PChl", "PFe", "D", "DChl", "DFe", "DSi", "Z", "M", "DOC", "POC"
 
 
 # ---- day length (src/Utils/Utils.jl:13-34) ----------------------------------------------------------
+def _sind(x: float) -> float:
+    """Julia's `sind`: the argument is reduced in DEGREES first (`rem(x, 360)` is exact), then folded to |angle| ≤ 45° —
+    `math.sin(math.radians(x))` would carry the rounding of x·π/180 (2e-11 absolute at x = 10⁷, which is what the
+    reference's swapped `day_length(φ, t)` passes as the latitude: the clock time in seconds)."""
+    r = math.fmod(x, 360.0)
+    a = abs(r)
+    if a < 45.0:
+        v = math.sin(math.radians(a))
+    elif a <= 135.0:
+        v = math.cos(math.radians(90.0 - a))
+    elif a < 225.0:
+        v = math.sin(math.radians(180.0 - a))
+    elif a <= 315.0:
+        v = -math.cos(math.radians(270.0 - a))
+    else:
+        v = math.sin(math.radians(a - 360.0))
+    return math.copysign(v, r) if v >= 0 else -math.copysign(-v, r)
+
+
+def _cosd(x: float) -> float:
+    """Julia's `cosd` (degree-exact reduction, see `_sind`)."""
+    a = abs(math.fmod(x, 360.0))
+    if a <= 45.0:
+        return math.cos(math.radians(a))
+    if a < 135.0:
+        return math.sin(math.radians(90.0 - a))
+    if a <= 225.0:
+        return -math.cos(math.radians(180.0 - a))
+    if a < 315.0:
+        return math.sin(math.radians(a - 270.0))
+    return math.cos(math.radians(360.0 - a))
+
+
 @dataclass
 class CBMDayLength:
     day_length_coefficient: float = 0.833
@@ -37,8 +70,7 @@ class CBMDayLength:
         θ = 0.216310 + 2 * math.atan(0.9671396 * math.tan(0.00860 * (J - 186)))
         # NB: Python NFKC-normalises identifiers, so the reference's ϕ (declination) and φ (latitude) would collide
         decl = math.degrees(math.asin(0.39795 * math.cos(θ)))
-        sind, cosd = (lambda x: math.sin(math.radians(x))), (lambda x: math.cos(math.radians(x)))
-        L = max(-1.0, min(1.0, (sind(p) + sind(φ) * sind(decl)) / (cosd(φ) * cosd(decl))))
+        L = max(-1.0, min(1.0, (_sind(p) + _sind(φ) * _sind(decl)) / (_cosd(φ) * _cosd(decl))))
         return (24 - 24 / 180 * math.degrees(math.acos(L))) * hour
 
 

@@ -108,3 +108,34 @@ def test_conserved_groups_and_scalers(box):
     # wPOC: faces 1…Nz = −2/day, top face 0 (sinking_velocity_fields.jl:15-17)
     w = bgc.underlying_biogeochemistry.sinking_velocities["POC"].face_interior[:, 0, 0]
     assert float(w[0]) == -2 / 86400 and float(w[-1]) == 0.0
+
+
+# ---- absolute values: the C oracle against an independent transliteration of the reference ------------------------
+def _golden_rows():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pisces_tendencies.json"), encoding="utf-8"))["rows"]
+
+
+@pytest.mark.parametrize("row", range(14))
+def test_c_oracle_matches_independent_restatement(oracle, row):
+    """tests/golden/pisces_tendencies.json holds the 24 tendencies computed by oracle/pyref_pisces.py — a
+    method-by-method Python transliteration of the reference that shares no code with oracle_pisces.c
+    (scripts/make_pisces_golden.py) — at 14 states that take both sides of every branch.  Two independent readings of
+    the same source agree to rounding: 1e-13 of the largest un-cancelled flux of the cell."""
+    r = _golden_rows()[row]
+    f = r["state"]
+    g = ob.RectilinearGrid(size=(1,), z=(-10, 0), topology=("Flat", "Flat", "Bounded"), device="cpu")
+    u = ob.PISCES(g, latitude=pisces.PrescribedLatitude(r["latitude"])).underlying_biogeochemistry
+    p = u.c_params(f["t"])
+    # the host-evaluated day lengths (both argument orders of the reference) agree with the transliteration's
+    assert math.isclose(p.day_length_growth, r["day_length_growth"], rel_tol=1e-13)
+    assert math.isclose(p.day_length_chlorophyll, r["day_length_chlorophyll"], rel_tol=1e-13)
+    vals = [f.get(n, 0.0) for n in pisces.TRACERS]
+    G = dict(zip(pisces.TRACERS, oracle.pisces_point(p, vals, f["PAR₁"], f["PAR₂"], f["PAR₃"], f["PAR"], f["Ω"], f["wPOC"], f["wGOC"],
+                                                     f["zₘₓₗ"], f["zₑᵤ"], f["κ"], f["mixed_layer_PAR"], f["z"])))
+    want = r["tendencies"]
+    carbon = max(abs(want[n]) for n in ("P", "D", "Z", "M", "DOC", "POC", "GOC", "DIC"))
+    for n, v in want.items():
+        scale = max(abs(v), 1e-3 * carbon if n not in ("PChl", "DChl", "PFe", "DFe", "SFe", "BFe", "Fe") else 0.0)
+        assert abs(G[n] - v) <= 1e-13 * max(scale, 1e-300) + 1e-30, (row, n, G[n], v)
