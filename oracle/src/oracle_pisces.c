@@ -820,6 +820,29 @@ void orc_pisces_point(const obm_pisces_params* p, const double* values, double P
     for (int n = 0; n < OBM_PISCES_NTRACERS; n++) out[n] = tendency(p, &c, n);
 }
 
+/* Julia's sind / cosd reduce the argument in DEGREES (rem(x, 360) is exact) and fold it to |angle| <= 45° before the
+ * radian conversion; sin(x·π/180) would carry the rounding of x·π/180, 2e-11 at the x ~ 1e7 that the reference's
+ * swapped day_length(φ, t) passes as the latitude. */
+static double jl_sind(double x) {
+    double r = fmod(x, 360.0), a = fabs(r), v;
+    const double D2R = 3.14159265358979323846 / 180.0;
+    if (a < 45.0) v = sin(a * D2R);
+    else if (a <= 135.0) v = cos((90.0 - a) * D2R);
+    else if (a < 225.0) v = sin((180.0 - a) * D2R);
+    else if (a <= 315.0) v = -cos((270.0 - a) * D2R);
+    else v = sin((a - 360.0) * D2R);
+    return r < 0 ? -v : v;
+}
+static double jl_cosd(double x) {
+    double a = fabs(fmod(x, 360.0));
+    const double D2R = 3.14159265358979323846 / 180.0;
+    if (a <= 45.0) return cos(a * D2R);
+    if (a < 135.0) return sin((90.0 - a) * D2R);
+    if (a <= 225.0) return -cos((180.0 - a) * D2R);
+    if (a < 315.0) return sin((a - 270.0) * D2R);
+    return cos((360.0 - a) * D2R);
+}
+
 /* (day_length::CBMDayLength)(t, φ) — src/Utils/Utils.jl:13-34 */
 double orc_cbm_day_length(double t, double phi) {
     const double pcoef = 0.833;
@@ -828,6 +851,6 @@ double orc_cbm_day_length(double t, double phi) {
     if (fmod(t, 365 * DAY) < 0) J = floor((fmod(t, 365 * DAY) + 365 * DAY) / DAY);
     double theta = 0.216310 + 2 * atan(0.9671396 * tan(0.00860 * (J - 186)));
     double decl = asin(0.39795 * cos(theta)) / D2R; /* asind */
-    double L = jl_max(-1.0, jl_min(1.0, (sin(pcoef * D2R) + sin(phi * D2R) * sin(decl * D2R)) / (cos(phi * D2R) * cos(decl * D2R))));
+    double L = jl_max(-1.0, jl_min(1.0, (jl_sind(pcoef) + jl_sind(phi) * jl_sind(decl)) / (jl_cosd(phi) * jl_cosd(decl))));
     return (24 - 24.0 / 180 * (acos(L) / D2R)) * 3600.0;
 }
