@@ -86,3 +86,34 @@ def test_constructors(oracle):
         ob.BiogeochemicalSediment(g, ob.InstantRemineralisation(), timestepper="Euler")
     bgc = ob.LOBSTER(g, sediment=ir)
     assert "instant remineralisation" in repr(bgc)
+
+
+@pytest.mark.parametrize("carbon", [False, True])
+def test_c_oracle_matches_independent_restatement(oracle, carbon):
+    """oracle/pyref_sediment.py transliterates simple_multi_G.jl method by method (no code shared with
+    oracle_sediment.c, reference default parameters typed in again): pool tendencies and the NO₃ / NH₄ / O₂ / DIC return
+    fluxes agree to rounding at seeded states, including the guard for an exactly empty sediment."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import pyref_sediment as ref
+    g = ob.RectilinearGrid(size=(2, 2, 4), extent=(2, 2, 400), device="cpu")
+    kw = dict(sinking_carbon=("sPOC", "bPOC"), sinking_nitrogen=("sPON", "bPON")) if carbon else {}
+    p = params(ob.SimpleMultiGSediment, grid=g, **kw)
+    model = ref.SimpleMultiG(float(g.zc[0]), carbon=carbon)
+    rng = np.random.default_rng(17)
+    names = ("Ns", "Nf", "Nr") + (("Cs", "Cf", "Cr") if carbon else ())
+    coupled = ("NO₃", "NH₄", "O₂") + (("DIC",) if carbon else ())
+    for case in range(12):
+        pools = list(10 ** rng.uniform(-3, 1, len(names)))
+        NO3, NH4, O2 = rng.uniform(0.5, 30), rng.uniform(0.05, 5), rng.uniform(2, 400)
+        fN, fC = 10 ** rng.uniform(-8, -4), 10 ** rng.uniform(-7, -3)
+        if case == 0:
+            pools = [0.0] * len(names)  # log(0) ⇒ non-finite fractions ⇒ ifelse(isfinite(p), p, 0)
+        dP, cf = oracle.sediment_point(p, pools, NO3, NH4, O2, fN, *([fC] if carbon else []))
+        for n, got in zip(names, dP):
+            want = model(n, pools, NO3, NH4, O2, fN, fC)
+            assert math.isclose(got, want, rel_tol=1e-14, abs_tol=1e-300), (case, n, got, want)
+        for n, got in zip(coupled, cf):
+            want = model(n, pools, NO3, NH4, O2, fN, fC)
+            assert math.isclose(got, want, rel_tol=1e-11, abs_tol=1e-300), (case, n, got, want)  # exp of ≈ 10 log-products
