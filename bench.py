@@ -115,8 +115,7 @@ class Workload:
     def _kernel_names(self):
         if self.kind in ("lobster", "npzd"):
             return ["scale_negative_kernel", "par_twoband_kernel", "npd_tendency_kernel"]
-        return ["scale_negative_calcite_kernel", "par_multiband_kernel", "euphotic_depth_kernel", "mixed_layer_mean_kernel",
-                "pisces_tendency_kernel"]
+        return ["scale_negative_calcite_kernel", "par_multiband_kernel", "pisces_tendency_kernel"]
 
     def _build_carbon(self, n):
         from oceanbiome_b200 import synthetic

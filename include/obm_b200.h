@@ -181,6 +181,19 @@ int obm_par_multiband(const obm_grid* grid, const obm_multiband_params* p, const
                       double surface_PAR_const, double* const* PAR_bands, double* PAR_total,
                       void* stream);
 
+/* obm_par_multiband that also leaves the two column diagnostics PISCES derives from the total PAR in
+ * the same stage — `compute_euphotic_depth!` (compute_euphotic_depth.jl:3-40, below) and
+ * `compute_mixed_layer_mean!` of PAR (PISCES/mean_mixed_layer_properties.jl:10-49; PISCES/update_state.jl:7,11)
+ * — while each level's total is on chip: one launch instead of three, PAR is not re-read.  Same results
+ * as the three calls (the mean is summed pairwise instead of top-down: ≤ 1e-15 relative apart).
+ * PAR_total is required (its top halo cell is read as found, like obm_euphotic_depth). */
+int obm_par_multiband_column_state(const obm_grid* grid, const obm_multiband_params* p,
+                                   const double* chl_a, const double* chl_b, double chl_scale,
+                                   const double* surface_PAR_xy, double surface_PAR_const,
+                                   double* const* PAR_bands, double* PAR_total,
+                                   const double* mixed_layer_depth_xy, double cutoff,
+                                   double* zeu_xy, double* mean_mixed_layer_PAR_xy, void* stream);
+
 /* `compute_euphotic_depth!(euphotic_depth, PAR, cutoff)` compute_euphotic_depth.jl:31-40.
  * Reads PAR[i,j,Nz+1] — a halo cell — exactly as the reference does (:6). zeu_xy is a 2-D
  * field in parent x-y layout. */

@@ -259,6 +259,9 @@ PROTOTYPES = {
                                   C.c_double, C.c_void_p, C.c_void_p]),
     "obm_par_multiband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_multiband_params), C.c_void_p, C.c_void_p,
                                     C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "obm_par_multiband_column_state": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_multiband_params), C.c_void_p, C.c_void_p,
+                                                 C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "obm_euphotic_depth": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "obm_mixed_layer_mean": (C.c_int, [C.POINTER(obm_grid), C.c_void_p, C.c_void_p, C.c_double, C.c_void_p,
                                        C.c_void_p]),

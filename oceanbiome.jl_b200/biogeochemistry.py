@@ -60,10 +60,20 @@ class Biogeochemistry:
         u = self.underlying_biogeochemistry
         epilogue = u.calcite_saturation_arguments(model) if (self.fuse_state_update and hasattr(u, "calcite_saturation_arguments")) else None
         fused = _update_modifiers(model, self.modifiers, stream, epilogue)
+        # PISCES: zₑᵤ and the mixed-layer mean PAR ride in the launch of the multi-band PAR scan
+        light_done = False
         if self.light_attenuation is not None:
-            self.light_attenuation.update_biogeochemical_state(model, stream)
-        if fused:
-            u.update_biogeochemical_state(model, stream, calcite_saturation_done=True)
+            cs = None
+            if (self.fuse_state_update and getattr(self.light_attenuation, "supports_column_state", False)
+                    and hasattr(u, "column_light_state")):
+                cs = u.column_light_state(model)
+            if cs is not None:
+                self.light_attenuation.update_biogeochemical_state(model, stream, column_state=cs)
+                light_done = True
+            else:
+                self.light_attenuation.update_biogeochemical_state(model, stream)
+        if fused or light_done:
+            u.update_biogeochemical_state(model, stream, calcite_saturation_done=fused, light_state_done=light_done)
         else:
             u.update_biogeochemical_state(model, stream)
         if self.sediment is not None:

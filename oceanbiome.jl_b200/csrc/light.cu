@@ -166,15 +166,40 @@ struct MultiBandArgs {
     double sPAR_const;
     double* bands[OBM_MAX_BANDS];
     double* total;
+    // DIAG variant: the two column diagnostics PISCES derives from the total PAR (PISCES/update_state.jl:7,11)
+    const double* zmxl;  // 2-D mixed-layer depth
+    double cutoff;       // euphotic depth = where PAR falls to cutoff × surface PAR
+    double* zeu;         // 2-D out
+    double* mlmean;      // 2-D out: mixed-layer mean of the total PAR
 };
 
-// NB = number of bands (compile-time so the per-band carries live in registers)
-template <int NB>
-__global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_constant__ MultiBandArgs a) {
+#ifndef OBM_PAR_DIAG_BLOCKS
+#define OBM_PAR_DIAG_BLOCKS 5
+#endif
+// compute_euphotic_depth.jl:20: log-space interpolation between level k (`here`, at or below the threshold) and the
+// level above it.  Out of line: it runs a few times per column and carries four logs.
+__device__ __noinline__ double euphotic_depth_between(double zk, double zk1, double here, double above, double thr) {
+    return zk + (log(thr) - log(here)) * (zk - zk1) / (log(here) - log(above));
+}
+
+// NB = number of bands (compile-time so the per-band carries live in registers).
+// DIAG: the launch also produces PISCES' euphotic depth (compute_euphotic_depth.jl:3-29) and mixed-layer mean PAR
+// (mean_mixed_layer_properties.jl:25-49) of each column while the total PAR of a level is on chip — the two extra column
+// launches and their re-read of the PAR field go away.  Both ride in the store phase (thread ↔ column, warp ↔ 4 levels):
+// a thread adds its levels to its own partial sums (reduced across the 8 warps once, at the end: pairwise instead of the
+// reference's top-down order, ≤ 1e-15 relative apart), flags the first level of the tile at or below the threshold
+// with a shared-memory atomicMin, and warp 0 resolves the flagged level (log-space interpolation with the level above)
+// between two barriers that are there anyway.
+template <int NB, bool DIAG>
+__global__ void __launch_bounds__(TC* NWARP, DIAG ? OBM_PAR_DIAG_BLOCKS : 5) par_multiband_kernel(const __grid_constant__ MultiBandArgs a) {
     __shared__ double tile[TZ][TC + 1];
     __shared__ double out[NB][TZ][TC + 1];
     __shared__ long long col_base[TC];
     __shared__ double col_par0[TC];
+    constexpr int DT = DIAG ? TC : 1;
+    __shared__ long long col_plane[DT];
+    __shared__ double col_zmxl[DT], col_halo[DT], col_thr[DT], col_prev[DT], col_zeu[DT];
+    __shared__ int col_first[DT], col_found[DT];
 
     const GridDims& d = a.d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -184,6 +209,16 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
         long long b = column_base(d, (long long)blockIdx.x * TC + lane, ncols, &plane);
         col_base[lane] = b;
         col_par0[lane] = b < 0 ? 0.0 : (a.sPAR ? a.sPAR[plane] : a.sPAR_const);
+        if (DIAG) {
+            col_plane[lane] = plane;
+            col_zmxl[lane] = b < 0 ? 0.0 : a.zmxl[plane];
+            // PAR[i, j, Nz + 1]: the (unfilled) top halo cell, read as found — compute_euphotic_depth.jl:6
+            col_halo[lane] = b < 0 ? 0.0 : a.total[b + d.sz * d.Nz];
+            col_thr[lane] = col_prev[lane] = 0.0;
+            col_zeu[lane] = -INFINITY;
+            col_first[lane] = TZ;
+            col_found[lane] = 0;
+        }
     }
     __syncthreads();
     const int Nz = d.Nz;
@@ -193,6 +228,7 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
     for (int q = 0; q < CPW; q++)
 #pragma unroll
         for (int n = 0; n < NB; n++) carry[q][n] = 1.0;
+    double ml_acc = 0.0, ml_depth = 0.0;  // DIAG: this thread's share of Σ PAR·Δz and Σ Δz above zₘₓₗ (column = lane)
 
     for (int ktop = Nz - 1; ktop >= 0; ktop -= TZ) {
 #pragma unroll
@@ -215,6 +251,7 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
         for (int q = 0; q < CPW; q++) {
             const int c = warp * CPW + q;
             const double lchl = log(tile[lane][c]);  // Chl^e = exp(e ln Chl): one log shared by all bands
+            double top = 0.0;
 #pragma unroll
             for (int n = 0; n < NB; n++) {
                 const double kw = a.m.water_attenuation_coefficient[n], e = a.m.chlorophyll_exponent[n];
@@ -225,16 +262,19 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
                 const double f = carry[q][n] * warp_inclusive_prod(t, lane);
                 carry[q][n] = __shfl_sync(0xffffffffu, f, 31);
                 out[n][lane][c] = f;
+                if (DIAG) top = (n == 0) ? f : top + f;
             }
+            // threshold of the column from its top level: PAR[Nz] (+ the halo cell above it) — compute_euphotic_depth.jl:6
+            if (DIAG && ktop == Nz - 1 && lane == 0) col_thr[c] = (top + col_halo[c]) / 2 * a.cutoff;
         }
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < TZ / NWARP; q++) {
             const int l = warp * (TZ / NWARP) + q, kk = ktop - l;
             const long long b = col_base[lane];
+            double s = 0.0;
             if (kk >= 0 && b >= 0) {
                 const long long idx = b + d.sz * kk;
-                double s = 0.0;
 #pragma unroll
                 for (int n = 0; n < NB; n++) {
                     const double f = out[n][l][lane];
@@ -242,9 +282,55 @@ __global__ void __launch_bounds__(TC* NWARP) par_multiband_kernel(const __grid_c
                     s = (n == 0) ? f : s + f;  // sum(fields): ((PAR₁ + PAR₂) + PAR₃) multi_band.jl:120
                 }
                 if (a.total) a.total[idx] = s;
+                if (DIAG) {
+                    const double zk = d.zf[kk], zk1 = d.zf[kk + 1], zm = col_zmxl[lane];  // mean_mixed_layer_properties.jl:33-45
+                    const double dzk1 = zk1 > zm ? zk1 - zm : 0.0;
+                    const double dzm = zk >= zm ? zk1 - zk : dzk1;
+                    ml_acc += s * dzm;
+                    ml_depth += dzm;
+                    if (kk <= Nz - 2 && s <= col_thr[lane]) atomicMin(&col_first[lane], l);
+                }
             }
+            // the total PAR of (l, lane) replaces band 0 of the same element, which only this thread reads in this phase
+            if (DIAG) out[0][l][lane] = s;
         }
         __syncthreads();
+        if (DIAG && warp == 0) {  // compute_euphotic_depth.jl:14-24 for the levels of this tile, column = lane
+            const double thr = col_thr[lane];
+            if (!col_found[lane]) {
+                for (int l = col_first[lane]; l < TZ; l++) {
+                    const int kk = ktop - l;
+                    if (kk < 0) break;
+                    const double here = out[0][l][lane];
+                    if (!(kk <= Nz - 2 && here <= thr)) continue;
+                    const double above = l > 0 ? out[0][l - 1][lane] : col_prev[lane];
+                    const double z = euphotic_depth_between(d.zc[kk], d.zc[kk + 1], here, above, thr);
+                    if (!isinf(z)) {  // `isinf(zₑᵤ)` keeps the search going after an infinite candidate
+                        col_zeu[lane] = z;
+                        col_found[lane] = 1;
+                        break;
+                    }
+                }
+            }
+            col_first[lane] = TZ;
+            col_prev[lane] = out[0][TZ - 1][lane];
+        }
+    }
+    if (DIAG) {
+        // Σ over the 8 warps' partial sums per column, fixed order; `out` is free after the last barrier of the loop
+        __syncthreads();  // warp 0 has finished reading the last tile's totals
+        double (*red)[2][TC] = reinterpret_cast<double (*)[2][TC]>(&out[0][0][0]);
+        red[warp][0][lane] = ml_acc;
+        red[warp][1][lane] = ml_depth;
+        __syncthreads();
+        if (warp == 0 && col_base[lane] >= 0) {
+            double acc = 0.0, dep = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; w++) { acc += red[w][0][lane]; dep += red[w][1][lane]; }
+            a.mlmean[col_plane[lane]] = acc / dep;
+            const double z = col_zeu[lane];
+            a.zeu[col_plane[lane]] = isfinite(z) ? z : d.zc[-1];  // znode(i, j, 0, grid, …) :28
+        }
     }
 }
 
@@ -326,15 +412,20 @@ extern "C" int obm_par_twoband(const obm_grid* grid, const obm_twoband_params* p
     return launch_status("par_twoband_kernel");
 }
 
-extern "C" int obm_par_multiband(const obm_grid* grid, const obm_multiband_params* p, const double* chl_a,
-                                 const double* chl_b, double chl_scale, const double* surface_PAR_xy,
-                                 double surface_PAR_const, double* const* PAR_bands, double* PAR_total, void* stream) {
-    OBM_REQUIRE(p && chl_a && PAR_bands, OBM_ENULL, "obm_par_multiband: params / chl_a / PAR_bands is NULL");
+static int launch_multiband(const char* who, const obm_grid* grid, const obm_multiband_params* p, const double* chl_a,
+                            const double* chl_b, double chl_scale, const double* surface_PAR_xy, double surface_PAR_const,
+                            double* const* PAR_bands, double* PAR_total, const double* zmxl, double cutoff, double* zeu,
+                            double* mlmean, bool diag, void* stream) {
+    OBM_REQUIRE(p && chl_a && PAR_bands, OBM_ENULL, "%s: params / chl_a / PAR_bands is NULL", who);
     OBM_REQUIRE(p->nbands >= 1 && p->nbands <= 4, p->nbands >= 1 && p->nbands <= OBM_MAX_BANDS ? OBM_ENOTIMPL : OBM_ESIZE,
-                "obm_par_multiband: nbands = %d (this build supports 1..4)", p->nbands);
+                "%s: nbands = %d (this build supports 1..4)", who, p->nbands);
     MultiBandArgs a;
     int rc = make_dims(grid, &a.d, true);
     if (rc) return rc;
+    if (diag) {
+        OBM_REQUIRE(PAR_total && zmxl && zeu && mlmean, OBM_ENULL, "%s: PAR_total / zmxl / zeu / mean is NULL", who);
+        OBM_REQUIRE(a.d.Hz >= 1, OBM_ESIZE, "%s needs Hz >= 1 (reads PAR[i,j,Nz+1] and znode(k=0))", who);
+    }
     a.m = *p;
     a.chl_a = chl_a;
     a.chl_b = chl_b;
@@ -343,16 +434,37 @@ extern "C" int obm_par_multiband(const obm_grid* grid, const obm_multiband_param
     a.sPAR_const = surface_PAR_const;
     for (int n = 0; n < OBM_MAX_BANDS; n++) a.bands[n] = n < p->nbands ? PAR_bands[n] : nullptr;
     a.total = PAR_total;
+    a.zmxl = zmxl; a.cutoff = cutoff; a.zeu = zeu; a.mlmean = mlmean;
     const long long ncols = column_count(a.d);
     const unsigned blocks = (unsigned)((ncols + TC - 1) / TC);
     cudaStream_t s = (cudaStream_t)stream;
+#define OBM_MB(NB)                                                                   \
+    if (diag) par_multiband_kernel<NB, true><<<blocks, TC * NWARP, 0, s>>>(a);       \
+    else par_multiband_kernel<NB, false><<<blocks, TC * NWARP, 0, s>>>(a)
     switch (p->nbands) {
-        case 1: par_multiband_kernel<1><<<blocks, TC * NWARP, 0, s>>>(a); break;
-        case 2: par_multiband_kernel<2><<<blocks, TC * NWARP, 0, s>>>(a); break;
-        case 3: par_multiband_kernel<3><<<blocks, TC * NWARP, 0, s>>>(a); break;
-        default: par_multiband_kernel<4><<<blocks, TC * NWARP, 0, s>>>(a); break;
+        case 1: OBM_MB(1); break;
+        case 2: OBM_MB(2); break;
+        case 3: OBM_MB(3); break;
+        default: OBM_MB(4); break;
     }
+#undef OBM_MB
     return launch_status("par_multiband_kernel");
+}
+
+extern "C" int obm_par_multiband(const obm_grid* grid, const obm_multiband_params* p, const double* chl_a,
+                                 const double* chl_b, double chl_scale, const double* surface_PAR_xy,
+                                 double surface_PAR_const, double* const* PAR_bands, double* PAR_total, void* stream) {
+    return launch_multiband("obm_par_multiband", grid, p, chl_a, chl_b, chl_scale, surface_PAR_xy, surface_PAR_const, PAR_bands,
+                            PAR_total, nullptr, 0.0, nullptr, nullptr, false, stream);
+}
+
+extern "C" int obm_par_multiband_column_state(const obm_grid* grid, const obm_multiband_params* p, const double* chl_a,
+                                              const double* chl_b, double chl_scale, const double* surface_PAR_xy,
+                                              double surface_PAR_const, double* const* PAR_bands, double* PAR_total,
+                                              const double* mixed_layer_depth_xy, double cutoff, double* zeu_xy,
+                                              double* mean_mixed_layer_PAR_xy, void* stream) {
+    return launch_multiband("obm_par_multiband_column_state", grid, p, chl_a, chl_b, chl_scale, surface_PAR_xy, surface_PAR_const,
+                            PAR_bands, PAR_total, mixed_layer_depth_xy, cutoff, zeu_xy, mean_mixed_layer_PAR_xy, true, stream);
 }
 
 extern "C" int obm_euphotic_depth(const obm_grid* grid, const double* PAR, double cutoff, double* zeu_xy, void* stream) {

@@ -186,8 +186,12 @@ class MultiBandPhotosyntheticallyActiveRadiation:
             p.surface_PAR_division[n] = self.surface_PAR_division[n]
         return p
 
-    def update_biogeochemical_state(self, model, stream: Optional[int] = None):
-        """multi_band.jl:165-185 — all bands in one launch; Chl = `chlorophyll(bgc, model)`."""
+    supports_column_state = True  # can produce PISCES' zₑᵤ and mixed-layer mean PAR in the same launch
+
+    def update_biogeochemical_state(self, model, stream: Optional[int] = None, column_state=None):
+        """multi_band.jl:165-185 — all bands in one launch; Chl = `chlorophyll(bgc, model)`.
+        `column_state = (mixed_layer_depth, cutoff, euphotic_depth, mean_mixed_layer_light)`: also leave PISCES' two
+        column diagnostics of the total PAR (obm_par_multiband_column_state)."""
         chl_a, chl_b, scale = model.biogeochemistry.chlorophyll(model)
         require_cuda(chl_a, chl_b, self.total)
         sfield, sconst = evaluate_surface_PAR(self.surface_PAR, self.grid, model.clock, self.discrete_form,
@@ -195,6 +199,14 @@ class MultiBandPhotosyntheticallyActiveRadiation:
         cg, p = self.grid.c_grid(), self.c_params()
         bands = _lib.pointer_table([self.fields[n].ptr for n in self.field_names])
         s = stream if stream is not None else current_stream_ptr(self.grid.device)
+        if column_state is not None:
+            zmxl, cutoff, zeu, mean = column_state
+            require_cuda(zmxl, zeu, mean)
+            rc = _lib.load().obm_par_multiband_column_state(
+                C.byref(cg), C.byref(p), chl_a.ptr, chl_b.ptr if chl_b else None, float(scale), sfield.ptr if sfield else None,
+                sconst, bands, self.total.ptr, zmxl.ptr, float(cutoff), zeu.ptr, mean.ptr, s)
+            _lib.check(rc, "obm_par_multiband_column_state")
+            return
         rc = _lib.load().obm_par_multiband(C.byref(cg), C.byref(p), chl_a.ptr, chl_b.ptr if chl_b else None,
                                            float(scale), sfield.ptr if sfield else None, sconst, bands,
                                            self.total.ptr, s)

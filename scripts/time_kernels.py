@@ -28,6 +28,8 @@ if hasattr(bgc.underlying_biogeochemistry, "calcite_saturation_arguments"):
     u0 = bgc.underlying_biogeochemistry
     res["scale_negative_calcite_fused_ms"] = timeit(lambda: _update_modifiers(m, bgc.modifiers, None, u0.calcite_saturation_arguments(m)))
 res["light_ms"] = timeit(lambda: bgc.light_attenuation.update_biogeochemical_state(m))
+if hasattr(bgc.underlying_biogeochemistry, "column_light_state"):
+    res["light_with_column_state_ms"] = timeit(lambda: bgc.light_attenuation.update_biogeochemical_state(m, column_state=bgc.underlying_biogeochemistry.column_light_state(m)))
 res["underlying_state_ms"] = timeit(lambda: bgc.underlying_biogeochemistry.update_biogeochemical_state(m))
 res["tendencies_ms"] = timeit(lambda: bgc.update_tendencies(m))
 res["tendency_Gcell_s"] = w.cells / res["tendencies_ms"] / 1e6

@@ -192,3 +192,31 @@ def test_fused_scaling_and_calcite_saturation_equals_separate_launches(cuda, ora
     assert float(np.max(np.abs(got[ok] - Om[ok]) / np.abs(Om[ok]))) <= RTOL_CARBON
     for n in ("PAR", "PAR₁"):
         assert torch.equal(bf.biogeochemical_auxiliary_fields()[n].data, bs.biogeochemical_auxiliary_fields()[n].data)
+    # obm_par_multiband_column_state ≡ obm_par_multiband → obm_euphotic_depth → obm_mixed_layer_mean
+    uf, us = bf.underlying_biogeochemistry, bs.underlying_biogeochemistry
+    zf_, zs_ = uf.euphotic_depth.interior, us.euphotic_depth.interior
+    assert bool(((zf_ - zs_).abs() <= 1e-13 * zs_.abs()).all()) and bool((zs_ < -1.0).all())
+    mf_, ms_ = uf.mean_mixed_layer_light.interior, us.mean_mixed_layer_light.interior
+    assert bool(((mf_ - ms_).abs() <= 1e-13 * ms_.abs()).all()) and bool((ms_ > 0).all())
+
+
+@pytest.mark.parametrize("size,extent", [((40, 6, 30), (1e4, 1e3, 500.0)), ((33, 3, 70), (1e3, 1e2, 4000.0)), ((5, 2, 7), (10.0, 4.0, 30.0))])
+def test_par_scan_with_column_state_matches_oracle(cuda, oracle, size, extent):
+    """The fused PAR launch: zₑᵤ and PAR̄ₘₓₗ against the oracle's top-down column loops, on columns where the euphotic
+    depth falls in the first z-tile, in a later tile (70 levels, 4 km) and nowhere (7 shallow levels ⇒ znode(k = 0))."""
+    grid, bgc, model = build(cuda, size, extent)
+    assert bgc.fuse_state_update
+    u = bgc.underlying_biogeochemistry
+    fill(model, bgc)
+    synthetic.fill_torch(u.mixed_layer_depth, "zₘₓₗ", -0.9 * extent[2], -0.02 * extent[2])
+    model.update_state()
+    og = oracle.Grid.like(grid)
+    PARd = bgc.light_attenuation.total.data.cpu().numpy()
+    zeu = oracle.euphotic_depth(og, PARd)
+    got = u.euphotic_depth.data.cpu().numpy()
+    assert float(np.max(np.abs(og.interior(got) - og.interior(zeu)) / np.abs(og.interior(zeu)))) <= RTOL_TENDENCY
+    if size[2] == 7:
+        assert np.all(og.interior(got) == grid.zc_host[grid.Hz - 1])  # never dark enough: znode(i, j, 0, grid, …)
+    mean = oracle.mixed_layer_mean(og, u.mixed_layer_depth.data.cpu().numpy(), PARd)
+    gm = u.mean_mixed_layer_light.data.cpu().numpy()
+    assert float(np.max(np.abs(og.interior(gm) - og.interior(mean)) / np.abs(og.interior(mean)))) <= RTOL_TENDENCY
