@@ -7,12 +7,11 @@ Julia's `f!(…)` names are spelled `f(…)` here; argument order follows the re
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional
 
 import ctypes as C
 
-import torch
 
 from . import _lib
 from .grids import CenterField, Field, RectilinearGrid, ZFaceField, current_stream_ptr

@@ -8,7 +8,6 @@ non-Flat side) so that the pointers handed to the C ABI here are interchangeable
 from __future__ import annotations
 
 import contextlib
-import ctypes as C
 from dataclasses import dataclass
 
 import numpy as np

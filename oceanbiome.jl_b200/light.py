@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Callable, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 import torch

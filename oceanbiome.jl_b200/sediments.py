@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Optional, Sequence
 
 import torch

@@ -9,7 +9,7 @@ import torch
 
 import oceanbiome_b200 as ob
 from oceanbiome_b200 import pisces, synthetic
-from helpers import RTOL_CARBON, RTOL_TENDENCY, scale_aware_error, synthetic_state
+from helpers import RTOL_CARBON, RTOL_TENDENCY, scale_aware_error
 
 pytestmark = pytest.mark.gpu
 
