@@ -25,6 +25,6 @@ from .gas_exchange import (CarbonDioxideConcentration, CarbonDioxideGasExchangeB
                            PartiallySolubleGas, PolynomialParameterisation, SchmidtScaledTransferVelocity)
 from .particles import BiogeochemicalParticles, LinearOptimalTemperatureRange, SugarKelp, SugarKelpParticles
 from .biogeochemistry import Biogeochemistry, BiogeochemicalModel, Clock
-from .box_model import BoxModel, BoxModelGrid
+from .box_model import BoxModel, BoxModelGrid, SpeedyOutput, load_output
 
 __version__ = "0.1.0"

@@ -25,6 +25,44 @@ from .biogeochemistry import Clock
 from .grids import CenterField, Field, RectilinearGrid, current_stream_ptr
 
 
+class SpeedyOutput:
+    """`SpeedyOutput(filename; overwrite_existing = true)` — src/BoxModel/output_writer.jl:1-56: the time series of
+    every model field, one entry per output, appended while the model runs and read back with `load_output`.
+    The reference writes a JLD2 file (`timeseries/<name>/<iteration>`); this mirror writes a NumPy `.npz` with the same
+    content — `t` and one array (n_outputs, n_boxes) per field — because JLD2 is a Julia serialisation format.
+    Snapshots are gathered on the device and copied to the host once, when the file is written."""
+
+    def __init__(self, filename: str, overwrite_existing: bool = True):
+        import os
+        if os.path.exists(filename) and not overwrite_existing:
+            raise FileExistsError(filename)
+        self.filename, self.overwrite_existing = filename, overwrite_existing
+        self._t, self._series = [], {}
+
+    def __call__(self, model):
+        """One output: the reference's `(save::SpeedyOutput)(simulation)`."""
+        self._t.append(float(model.clock.time))
+        for n, f in model.fields.items():
+            self._series.setdefault(n, []).append(f.interior.reshape(-1).clone())
+
+    def flush(self):
+        import numpy as np
+        data = {n: torch.stack(v).cpu().numpy() for n, v in self._series.items()}
+        data["t"] = np.asarray(self._t, dtype=np.float64)
+        with open(self.filename, "wb") as fh:  # np.savez would append ".npz" to a bare name
+            np.savez(fh, **data)
+
+
+def load_output(save: SpeedyOutput, name=None):
+    """`load_output(save)` / `load_output(save, name)` — output_writer.jl:34-56: dict name → array sorted by time."""
+    import numpy as np
+    with np.load(save.filename) as z:
+        order = np.argsort(z["t"])
+        if name is not None:
+            return z[str(name)][order]
+        return {n: z[n][order] for n in z.files}
+
+
 def BoxModelGrid(n: int = 1, device="cuda") -> RectilinearGrid:
     """`BoxModelGrid()` (src/OceanBioME.jl:171) for `n` independent boxes: x is the ensemble axis, y and z are Flat
     (the single level spans z ∈ [−1, 0] so that kernels reading z see a finite node)."""
@@ -134,9 +172,12 @@ class BoxModel:
         self.clock.iteration += 1
 
     # ---- run!(simulation) --------------------------------------------------------------------------------------
-    def run(self, dt: float, steps: int, graph: bool = False, output_every: int = 0, output_names=None):
+    def run(self, dt: float, steps: int, graph: bool = False, output_every: int = 0, output_names=None,
+            output: Optional[SpeedyOutput] = None):
         """Integrate `steps` time steps.  Returns a dict name → tensor (n_outputs, n_boxes) of snapshots taken
-        every `output_every` steps (device-resident; the reference's `SpeedyOutput` keeps them on the host).
+        every `output_every` steps (device-resident).  `output`: a `SpeedyOutput` called at iteration 0 and every
+        `output_every` steps like `simulation.callbacks[:output] = Callback(SpeedyOutput(f), IterationInterval(n))`
+        (eager mode), and written to disk at the end of the run.
 
         `graph=True`: prescribed tracers and forcings are tabulated for every stage of the run, uploaded once,
         and ONE captured time step is replayed `steps` times; requires a biogeochemistry whose kernel parameters do
@@ -144,12 +185,20 @@ class BoxModel:
         names = list(output_names or self.prognostic)
         nout = steps // output_every if output_every else 0
         out = {n: torch.empty((nout, self.grid.Nx), dtype=torch.float64, device=self.grid.device) for n in names}
+        if output is not None and graph:
+            raise ValueError("SpeedyOutput is an eager-mode callback; graph=True returns the snapshots as tensors")
         if not graph:
+            if output is not None and output_every:
+                output(self)  # IterationInterval fires at iteration 0 too
             for it in range(steps):
                 self.time_step(dt)
                 if output_every and (it + 1) % output_every == 0:
                     for n in names:
                         out[n][(it + 1) // output_every - 1].copy_(self.fields[n].interior.reshape(-1))
+                    if output is not None:
+                        output(self)
+            if output is not None:
+                output.flush()
             return out
         return self._run_graph(dt, steps, output_every, names, out)
 

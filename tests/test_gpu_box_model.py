@@ -172,3 +172,19 @@ def test_graph_mode_refuses_host_evaluated_time_dependence(cuda):
     m.set(**DEFAULTS)
     with pytest.raises(ValueError):
         m.run(60.0, 3, graph=True)
+
+
+def test_reference_simulation_with_speedy_output(cuda, tmp_path):
+    """test/test_boxmodel.jl:55-79: 1000 steps of 20 minutes, `SpeedyOutput` every 20 iterations — every model field
+    plus `t` is written, 1000/20 + 1 entries each (iteration 0 included), and every series moves."""
+    model, _ = simple_box_model(cuda)
+    model.set(**DEFAULTS)
+    fname = str(tmp_path / "box_model_test.jld2")  # the reference's file name; the content is .npz (see SpeedyOutput)
+    fast_output = ob.SpeedyOutput(fname)
+    model.run(dt=20 * minutes, steps=1000, output_every=20, output=fast_output)
+    results = ob.load_output(fast_output)
+    assert len(results) == len(model.fields) + 1
+    assert len(results["t"]) == 1000 // 20 + 1
+    assert results["t"][0] == 0.0 and math.isclose(results["t"][-1], 1000 * 20 * minutes, rel_tol=1e-12)
+    assert all(r[0].tolist() != r[-1].tolist() for r in results.values())
+    assert np.array_equal(ob.load_output(fast_output, "P"), results["P"])
