@@ -555,39 +555,3 @@ def fill_synthetic_auxiliary(bgc, model):
     synthetic.fill_torch(u.mean_mixed_layer_vertical_diffusivity, "κ̄", 1e-4, 1e-2, log=True)
     u.euphotic_depth.data.fill_(-60.0)
     u.sinking_velocities["GOC"] = DepthDependantSinkingSpeed().face_field(model.grid, u.mixed_layer_depth, u.euphotic_depth)
-
-
-def oracle_stage_seconds(pyoracle, grid, og):
-    """CPU-baseline leg of bench.py for the PISCES workload: one stage in the reference's launch structure
-    (5 scaling passes, 3 PAR passes, zₑᵤ, PAR̄, Ω with the reference's damped Newton, 24 tendency passes) on the
-    host twin `og` of `grid`.  TEST/BENCH INFRASTRUCTURE: the oracle is passed in by the caller."""
-    import time as _time
-
-    from . import synthetic
-    bgc = PISCES(grid, scale_negatives=True)
-    u = bgc.underlying_biogeochemistry
-    host = {n: synthetic.fill_numpy(np.zeros(og.parent_shape), og, n, *synthetic_range(n)) for n in TRACERS}
-    zmxl = synthetic.fill_numpy(np.zeros(og.plane_shape), og, "zₘₓₗ", -150.0, -10.0)
-    kappa = synthetic.fill_numpy(np.zeros(og.plane_shape), og, "κ̄", 1e-4, 1e-2, True)
-    wPOC = np.ascontiguousarray(u.sinking_velocities["POC"].data.numpy())
-    u.mixed_layer_depth.data.copy_(torch.from_numpy(zmxl))
-    u.euphotic_depth.data.fill_(-60.0)
-    wGOC = np.ascontiguousarray(DepthDependantSinkingSpeed().face_field(grid, u.mixed_layer_depth, u.euphotic_depth).data.numpy())
-    groups = [(m.tracers, m.scalefactors) for m in bgc.modifiers]
-    snames = []
-    for tn, _ in groups:
-        snames += [t for t in tn if t not in snames]
-    cgroups = pyoracle.make_groups(snames, groups)
-    la = bgc.light_attenuation
-    G = [np.zeros(og.parent_shape) if n < 24 else None for n in range(26)]
-    t0 = _time.perf_counter()
-    pyoracle.scale_negative_tracers(og, [host[n] for n in snames], cgroups)
-    bands, total = pyoracle.par_multiband(og, la.c_params(), host["PChl"], host["DChl"], 1.0, 100.0)
-    zeu = pyoracle.euphotic_depth(og, total)
-    mean = pyoracle.mixed_layer_mean(og, zmxl, total)
-    Om = pyoracle.calcite_saturation(og, host["T"], host["S"], host["DIC"], host["Alk"], host["Si"])
-    aux = {"PAR1": bands[0], "PAR2": bands[1], "PAR3": bands[2], "PAR": total, "Omega": Om, "wPOC": wPOC, "wGOC": wGOC,
-           "mixed_layer_depth_xy": zmxl, "euphotic_depth_xy": zeu, "mean_mixed_layer_vertical_diffusivity_xy": kappa,
-           "mean_mixed_layer_light_xy": mean}
-    pyoracle.pisces_tendencies(og, u.c_params(0.0), [host[n] for n in TRACERS], aux, G=G, accumulate=True)
-    return _time.perf_counter() - t0, grid
