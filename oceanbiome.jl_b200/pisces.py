@@ -10,7 +10,6 @@ import math
 from dataclasses import dataclass, field
 from typing import Optional
 
-import numpy as np
 import torch
 
 from . import _lib
