@@ -463,6 +463,12 @@ def main():
         run_reference_arm(args, name)
         return
 
+    # stdout carries exactly ONE line — the JSON — so everything libraries print there while the job runs (NCCL's
+    # "NCCL version …" banner at communicator creation, for one) is sent to stderr until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import oceanbiome_b200 as ob
     from oceanbiome_b200.distributed import init_distributed
     import torch.distributed as dist
@@ -603,7 +609,10 @@ def main():
                    "carbonate_solve": "cold start from pH 8 every step (warm start disabled: static synthetic state)"},
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
