@@ -1,0 +1,128 @@
+"""CPU: which C entry points the hooks call, and in which order — the reference's fixed order
+`update_biogeochemical_state!`: modifiers → light → underlying → sediment (src/OceanBioME.jl:161-167) and
+`update_tendencies!`: underlying → sediment → particles (:148-152) — for every fusion the host layer can choose.
+The library is replaced by a recorder (no kernel runs, no GPU needed); argument COUNTS are checked against the ctypes
+prototypes so a drifted call site fails here rather than on the GPU box."""
+import importlib
+
+import pytest
+
+import oceanbiome_b200 as ob
+from oceanbiome_b200 import _lib
+
+MODULES = ["biogeochemistry", "negative_tracers", "light", "pisces", "carbon_chemistry", "sediments", "npd", "particles",
+           "gas_exchange", "box_model"]
+
+
+class Recorder:
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        if name not in _lib.PROTOTYPES:
+            raise AttributeError(name)
+        nargs = len(_lib.PROTOTYPES[name][1])
+
+        def fn(*args):
+            assert len(args) == nargs, f"{name}: {len(args)} arguments, prototype has {nargs}"
+            self.calls.append(name)
+            return 0
+        return fn
+
+
+@pytest.fixture
+def lib(monkeypatch):
+    rec = Recorder()
+    monkeypatch.setattr(_lib, "load", lambda path=None: rec)
+    for m in MODULES:
+        mod = importlib.import_module(f"oceanbiome_b200.{m}")
+        if hasattr(mod, "require_cuda"):
+            monkeypatch.setattr(mod, "require_cuda", lambda *a, **k: None)
+        if hasattr(mod, "current_stream_ptr"):
+            monkeypatch.setattr(mod, "current_stream_ptr", lambda device: None)
+    return rec
+
+
+def grid3():
+    return ob.RectilinearGrid(size=(4, 3, 8), extent=(4.0, 3.0, 80.0), device="cpu")
+
+
+def test_pisces_stage_is_three_launches(lib):
+    g = grid3()
+    bgc = ob.PISCES(g, scale_negatives=True)
+    model = ob.BiogeochemicalModel(g, bgc)
+    model.update_state()
+    assert lib.calls == ["obm_scale_negative_tracers_calcite_saturation", "obm_par_multiband_column_state"]
+    lib.calls.clear()
+    bgc.update_tendencies(model)
+    assert lib.calls == ["obm_pisces_tendencies"]
+
+
+def test_pisces_unfused_follows_the_reference_launch_by_launch(lib):
+    g = grid3()
+    bgc = ob.PISCES(g, scale_negatives=True)
+    bgc.fuse_state_update = False
+    ob.BiogeochemicalModel(g, bgc).update_state()
+    assert lib.calls == ["obm_scale_negative_tracers", "obm_par_multiband", "obm_euphotic_depth", "obm_mixed_layer_mean",
+                         "obm_calcite_saturation"]
+
+
+def test_pisces_without_modifiers_keeps_the_omega_launch(lib):
+    g = grid3()
+    ob.BiogeochemicalModel(g, ob.PISCES(g)).update_state()
+    assert lib.calls == ["obm_par_multiband_column_state", "obm_calcite_saturation"]
+
+
+def test_pisces_with_prescribed_light_uses_the_standalone_column_kernels(lib):
+    g = grid3()
+    PAR = {n: ob.CenterField(g, n, 10.0) for n in ("PAR₁", "PAR₂", "PAR₃", "PAR")}
+    bgc = ob.PISCES(g, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR), scale_negatives=True)
+    ob.BiogeochemicalModel(g, bgc).update_state()
+    assert lib.calls == ["obm_scale_negative_tracers_calcite_saturation", "obm_euphotic_depth", "obm_mixed_layer_mean"]
+
+
+def test_a_modifier_after_the_scalers_blocks_the_omega_fusion(lib):
+    g = grid3()
+    bgc = ob.PISCES(g, scale_negatives=True)
+    bgc.modifiers = (*bgc.modifiers, ob.ZeroNegativeTracers())  # the last launch is no longer a negative scaling
+    ob.BiogeochemicalModel(g, bgc).update_state()
+    assert lib.calls == ["obm_scale_negative_tracers", "obm_zero_negative_tracers", "obm_par_multiband_column_state",
+                         "obm_calcite_saturation"]
+
+
+def test_lobster_with_sediment_order(lib):
+    g = grid3()
+    sed = ob.SimpleMultiGSediment(g)
+    bgc = ob.LOBSTER(g, oxygen=ob.Oxygen(), sediment=sed, scale_negatives=True)
+    model = ob.BiogeochemicalModel(g, bgc)
+    model.update_state()
+    assert lib.calls == ["obm_scale_negative_tracers", "obm_par_twoband", "obm_sediment_update_state"]
+    lib.calls.clear()
+    model.compute_tendencies()
+    assert lib.calls == ["obm_npd_tendencies", "obm_sediment_update_tendencies"]
+
+
+def test_particles_and_sinking_in_a_time_step(lib):
+    g = grid3()
+    kelp = ob.SugarKelpParticles(5, g, coupled_tracers={"NO₃": "NO₃", "NH₄": "NH₄", "DON": "DOM", "bPON": "bPOM"})
+    bgc = ob.LOBSTER(g, particles=kelp)
+    model = ob.BiogeochemicalModel(g, bgc, extra_tracers=("T",), timestepper="Euler", sinking_advection="UpwindBiased1")
+    model.time_step(10.0)
+    # first step: no particle step yet (Oceananigans steps particles at the END of a stage, with that stage's Δt)
+    assert lib.calls == ["obm_par_twoband", "obm_npd_tendencies", "obm_kelp_update_tendencies", "obm_sinking_tendencies",
+                         "obm_rk3_substep"]
+    lib.calls.clear()
+    model.time_step(10.0)
+    assert lib.calls == ["obm_par_twoband", "obm_npd_tendencies", "obm_kelp_update_tendencies", "obm_sinking_tendencies",
+                         "obm_kelp_step", "obm_rk3_substep"]
+    lib.calls.clear()
+    model.finish_particles()
+    assert lib.calls[-1] == "obm_kelp_step" and model.clock.last_stage_dt == float("inf")
+
+
+def test_rk3_model_calls_the_hooks_once_per_stage(lib):
+    g = grid3()
+    model = ob.BiogeochemicalModel(g, ob.NPZD(g))
+    model.time_step(60.0)
+    assert lib.calls == ["obm_par_twoband", "obm_npd_tendencies", "obm_rk3_substep"] * 3
+    assert model.clock.iteration == 1 and abs(model.clock.time - 60.0) < 1e-9
