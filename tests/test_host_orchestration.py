@@ -126,3 +126,28 @@ def test_rk3_model_calls_the_hooks_once_per_stage(lib):
     model.time_step(60.0)
     assert lib.calls == ["obm_par_twoband", "obm_npd_tendencies", "obm_rk3_substep"] * 3
     assert model.clock.iteration == 1 and abs(model.clock.time - 60.0) < 1e-9
+
+
+def test_box_model_follows_oceananigans_rk3_order(lib):
+    """boxmodel.jl:92-110 + Oceananigans' RK3 `time_step!`: state and tendencies at iteration 0, then per stage
+    substep → update_state! (state hooks, then tendencies)."""
+    g = ob.BoxModelGrid(3, device="cpu")
+    PAR = ob.CenterField(g, "PAR")
+    bgc = ob.LOBSTER(g, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR))
+    box = ob.BoxModel(biogeochemistry=bgc, grid=g, prescribed_tracers={"PAR": lambda t: 50.0})
+    box.set(P=0.1, Z=0.01)
+    box.time_step(1200.0)
+    assert lib.calls == ["obm_npd_tendencies"] + ["obm_rk3_substep", "obm_npd_tendencies"] * 3
+    lib.calls.clear()
+    box.time_step(1200.0)  # no initial update the second time
+    assert lib.calls == ["obm_rk3_substep", "obm_npd_tendencies"] * 3
+    assert float(PAR.interior[0, 0, 0]) == 50.0
+
+
+def test_gas_exchange_boundary_condition_is_applied_after_the_tendencies(lib):
+    g = grid3()
+    co2 = ob.CarbonDioxideGasExchangeBoundaryCondition(air_concentration=413.0, wind_speed=2.0)
+    bgc = ob.LOBSTER(g, carbonate_system=ob.CarbonateSystem())
+    model = ob.BiogeochemicalModel(g, bgc, extra_tracers=("T", "S"), boundary_conditions={"DIC": co2})
+    model.compute_tendencies()
+    assert lib.calls == ["obm_npd_tendencies", "obm_gas_exchange_flux"]
