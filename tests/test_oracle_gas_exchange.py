@@ -169,3 +169,34 @@ def test_constructor_structure():
                                                             abi.OBM_GE_SOLUBILITY_ONE)
     two = ob.CarbonDioxideConcentration(DIC="DIC2", Alk="Alk2")
     assert (two.DIC, two.Alk) == ("DIC2", "Alk2")
+
+
+def test_oxygen_flux_against_an_independent_restatement(oracle):
+    """The whole O₂ exchange retyped from the reference in plain Python (gas_exchange.jl:26-38,
+    gas_transfer_velocity.jl:32-33 with Ho06, schmidt_number.jl:13-16, gas_solubility.jl:34-47 incl. its B2-used-twice
+    quadratic term, GasExchange.jl: air 9352.7 mmol O₂ m⁻³, wind 2 m/s): no coefficient is taken from the package."""
+    p = o2_params()
+    hour = 3600.0
+    for T, S, O2, u in ((25.0, 35.0, 200.0, 2.0), (4.0, 33.1, 330.0, 9.5), (15.5, 36.7, 260.0, 0.3)):
+        Sc = 1920.4 + -135.6 * T + 5.2122 * T ** 2 + -0.10939 * T ** 3 + 0.00093777 * T ** 4
+        k = (0.266 / hour / 100) * u ** 2 / math.sqrt(Sc / 660)
+        Tk = T + 273.15
+        Tk100 = Tk / 100
+        beta = math.exp(-58.3877 + 85.8079 / Tk100 + 23.8439 * math.log(Tk100) + S * (-0.034892 + 0.015578 * Tk100 + 0.015578 * Tk100 ** 2))
+        want = k * (O2 - 9352.7 * (beta / Tk))
+        got = oracle.gas_exchange_point(p, T, S, tracer=O2, u10=u)
+        assert math.isclose(got, want, rel_tol=1e-13), (T, S, got, want)
+
+
+def test_carbon_dioxide_flux_composition_against_an_independent_restatement(oracle):
+    """CO₂: k₆₆₀(u) / √(Sc(T)/660) · K₀(T, S) ρ(T, S) / 10³ · (pCO₂ − air) with the Schmidt polynomial (Wanninkhof 2014)
+    and Ho06 retyped here; pCO₂, K₀ and ρ come from the carbonate oracle, which the reference's docstring goldens pin
+    bit for bit (tests/test_oracle_carbon.py)."""
+    p = co2_params(air_concentration=413.0)
+    L = oracle.lib()
+    for T, S, DIC, Alk, u in ((15.0, 35.0, 2220.0, 2500.0, 2.0), (3.0, 34.0, 2150.0, 2300.0, 11.0), (27.0, 36.5, 1950.0, 2350.0, 6.0)):
+        Sc = 2116.8 + -136.25 * T + 4.7353 * T ** 2 + -0.092307 * T ** 3 + 0.0007555 * T ** 4
+        k = (0.266 / 3600.0 / 100) * u ** 2 / math.sqrt(Sc / 660) * (L.orc_K0(T + 273.15, S) * L.orc_teos10_polynomial_approximation(T, S, 0.0) / 10 ** 3)
+        pCO2 = oracle.carbon_chemistry(DIC=DIC, T=T, S=S, Alk=Alk, output=abi.CC_PCO2)
+        got = oracle.gas_exchange_point(p, T, S, DIC=DIC, Alk=Alk, u10=u)
+        assert math.isclose(got, k * (pCO2 - 413.0), rel_tol=1e-12), (T, got, k * (pCO2 - 413.0))
