@@ -136,6 +136,21 @@ int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p,
                        const double* const* tracers, const double* PAR,
                        double* const* G, int accumulate, void* stream);
 
+/* Parameter-sweep ensembles.  The reference calibrates by building one box model per parameter vector
+ * and running them one after the other on the CPU (examples/data_assimilation.jl:26-52, 118-130: NPZD with five
+ * PhytoZoo parameters per ensemble member).  Here every horizontal column (i, j) of the grid is a member: the same fused
+ * kernel evaluates all members in one launch, member m = i + Nx·j reading its own value of each varied parameter.
+ *   which[v]  (host, nvary ≤ OBM_NPD_MAX_VARIED) — the varied parameter, as its position among the `double` members of
+ *             obm_npd_params in declaration order (obm_npd_param_index("phytoplankton_maximum_growth_rate") …);
+ *   values    (DEVICE, [nvary][Nx·Ny], member fastest) — the member's value of parameter which[v].
+ * Everything not named in `which` — and the structure of the model, i.e. the int32 members — comes from `p`.
+ * With nvary = 0 the result is obm_npd_tendencies' bit for bit. */
+#define OBM_NPD_MAX_VARIED 16
+int obm_npd_param_index(const char* name); /* ≥ 0, or OBM_EENUM when obm_npd_params has no such double member */
+int obm_npd_tendencies_ensemble(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
+                                const double* values, const double* const* tracers, const double* PAR,
+                                double* const* G, int accumulate, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (a4) Two-band PAR — src/Light/2band.jl:1-33 (kernel), :35-70 (struct), :106-117 (defaults)
  * ------------------------------------------------------------------------------------ */

@@ -103,6 +103,23 @@ function update_tendencies!(bgc::B200Biogeochemistry, model)
     return nothing
 end
 
+# Parameter-sweep ensembles (examples/data_assimilation.jl builds one NPZD box model per parameter vector): one model
+# whose columns are the members.  `which` = Int32[obm_npd_param_index("phytoplankton_maximum_growth_rate"), …],
+# `values` = CuArray{Float64}(n_members, n_varied) (member fastest); everything else comes from bgc.params.
+function update_tendencies!(bgc::B200Biogeochemistry, model, which::Vector{Int32}, values::CuMatrix{Float64})
+    names   = Oceananigans.Biogeochemistry.required_biogeochemical_tracers(bgc.reference)
+    tracers = parents(model.tracers, names)
+    G       = [n === :T ? CU_NULL : pointer(parent(model.timestepper.Gⁿ[n])) for n in names]
+    PAR     = pointer(parent(Oceananigans.Biogeochemistry.biogeochemical_auxiliary_fields(bgc.reference).PAR))
+    check(ccall((:obm_npd_tendencies_ensemble, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmNpdParams}, Cint, Ptr{Int32}, CuPtr{Float64}, Ptr{CuPtr{Float64}}, CuPtr{Float64},
+                 Ptr{CuPtr{Float64}}, Cint, Ptr{Cvoid}),
+                Ref(ObmGrid(model.grid)), Ref(bgc.params), length(which), which, pointer(values), tracers, PAR, G, 1,
+                CUDA.stream().handle),
+          "obm_npd_tendencies_ensemble")
+    return nothing
+end
+
 # Particles (src/Particles): `update_tendencies!(bgc, particles::BiogeochemicalParticles{<:SugarKelp}, model)` →
 # obm_kelp_update_tendencies (all 8 coupled tracers, one launch);  `time_step_particle_fields!(::ForwardEuler, …)` →
 # obm_kelp_step.  ObmParticles carries pointer(particles.x), …, pointer(particles.fields.A), …, the first cell centre

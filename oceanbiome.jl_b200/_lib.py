@@ -20,6 +20,7 @@ OBM_MAX_SCALE_TRACERS = 32
 OBM_MAX_SCALE_GROUPS = 8
 OBM_MAX_GROUP_SIZE = 16
 OBM_NPD_MAX_TRACERS = 32
+OBM_NPD_MAX_VARIED = 16
 
 # enums (include/obm_b200.h)
 NUT_NUTRIENT, NUT_NITRATE_AMMONIA, NUT_NITRATE_AMMONIA_IRON = 0, 1, 2
@@ -253,6 +254,9 @@ PROTOTYPES = {
     "obm_npd_tracer_names": (C.c_int, [C.POINTER(obm_npd_params), C.c_void_p]),
     "obm_npd_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_npd_param_index": (C.c_int, [C.c_char_p]),
+    "obm_npd_tendencies_ensemble": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "obm_pisces_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p,
                                         C.POINTER(obm_pisces_fields), C.c_void_p, C.c_int, C.c_void_p]),
     "obm_par_twoband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_twoband_params), C.c_void_p, C.c_void_p,

@@ -28,7 +28,48 @@ struct NpdArgs {
     double* gAlk[MAX_REPLICATES];
     int nrep;
     int accumulate;
+    // parameter-sweep ensembles: member = horizontal column (i + Nx·j); values[v·members + member] replaces parameter which[v]
+    int nvary;
+    int which[OBM_NPD_MAX_VARIED];
+    const double* values;
 };
+
+// The double members of obm_npd_params in declaration order = the OBM_NPD_PARAM index space of the ensemble entry point.
+#define OBM_NPD_DOUBLE_PARAMS(X)                                                                                       \
+    X(nitrate_half_saturation) X(ammonia_half_saturation) X(iron_half_saturation) X(nitrate_ammonia_inhibition)        \
+    X(light_half_saturation) X(phytoplankton_maximum_growth_rate) X(iron_ratio) X(phytoplankton_exudation_fraction)    \
+    X(ammonia_fraction_of_exudate) X(temperature_coefficient) X(phytoplankton_mortality_rate)                          \
+    X(zooplankton_mortality_rate) X(zooplankton_excretion_rate) X(phytoplankton_solid_waste_fraction)                  \
+    X(excretion_inorganic_fraction) X(preference_for_phytoplankton) X(maximum_grazing_rate) X(grazing_half_saturation) \
+    X(zooplankton_assimilation_fraction) X(zooplankton_calcite_dissolution) X(redfield_ratio) X(carbon_calcite_ratio)  \
+    X(zooplankton_gut_calcite_dissolution) X(phytoplankton_chlorophyll_ratio) X(nitrification_rate)                    \
+    X(remineralisation_inorganic_fraction) X(small_remineralisation_rate) X(large_remineralisation_rate)               \
+    X(dissolved_remineralisation_rate) X(small_solid_waste_fraction) X(detritus_redfield_ratio)                        \
+    X(remineralisation_rate) X(small_particle_fraction) X(respiration_oxygen_nitrogen_ratio)                           \
+    X(nitrification_oxygen_nitrogen_ratio)
+
+enum NpdParamIndex {
+#define X(name) NPD_PARAM_##name,
+    OBM_NPD_DOUBLE_PARAMS(X)
+#undef X
+    NPD_PARAM_COUNT
+};
+#define X(name) static_assert(offsetof(obm_npd_params, name) == offsetof(obm_npd_params, nitrate_half_saturation) + 8 * NPD_PARAM_##name, \
+                              "OBM_NPD_DOUBLE_PARAMS out of step with obm_npd_params: " #name);
+OBM_NPD_DOUBLE_PARAMS(X)
+#undef X
+static_assert(sizeof(obm_npd_params) == offsetof(obm_npd_params, nitrate_half_saturation) + 8 * NPD_PARAM_COUNT,
+              "obm_npd_params has a member the ensemble index space does not name");
+
+// `which` is uniform over the launch: a uniform jump, and the block stays in registers (no dynamically indexed struct).
+__device__ __forceinline__ void set_param(obm_npd_params& p, int which, double v) {
+    switch (which) {
+#define X(name) case NPD_PARAM_##name: p.name = v; break;
+        OBM_NPD_DOUBLE_PARAMS(X)
+#undef X
+        default: break;
+    }
+}
 
 __device__ __forceinline__ void put(double* g, long long idx, double t, int accumulate) {
     if (g == nullptr) return;
@@ -49,12 +90,19 @@ __device__ __forceinline__ double concentration_limit(int form, double X, double
     return form == OBM_LINEAR ? X / (X + k) : (X * X) / (X * X + k * k);
 }
 
-template <int NUT, int DET>
+template <int NUT, int DET, bool ENSEMBLE>
 __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant__ NpdArgs a) {
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
-    const obm_npd_params& p = a.p;
+    obm_npd_params member;  // dead unless ENSEMBLE
+    if constexpr (ENSEMBLE) {
+        member = a.p;
+        const long long members = (long long)a.d.Nx * a.d.Ny, m = i + (long long)a.d.Nx * j;
+#pragma unroll 1
+        for (int v = 0; v < a.nvary; v++) set_param(member, a.which[v], a.values[v * members + m]);
+    }
+    const obm_npd_params& p = ENSEMBLE ? member : a.p;
     constexpr bool HAS_NA = (NUT != OBM_NUT_NUTRIENT);
     constexpr bool TWO_SIZE = (DET == OBM_DET_TWO_PARTICLE || DET == OBM_DET_VARIABLE_REDFIELD);
 
@@ -253,13 +301,21 @@ static int npd_layout(const obm_npd_params* p, int* roles, char (*names)[16]) {
     return n;
 }
 
-template <int NUT>
+template <int NUT, bool ENSEMBLE>
 static void launch_det(const NpdArgs& a, int det, dim3 blocks, cudaStream_t s) {
     switch (det) {
-        case OBM_DET_NONE: npd_tendency_kernel<NUT, OBM_DET_NONE><<<blocks, 256, 0, s>>>(a); break;
-        case OBM_DET_DETRITUS: npd_tendency_kernel<NUT, OBM_DET_DETRITUS><<<blocks, 256, 0, s>>>(a); break;
-        case OBM_DET_TWO_PARTICLE: npd_tendency_kernel<NUT, OBM_DET_TWO_PARTICLE><<<blocks, 256, 0, s>>>(a); break;
-        default: npd_tendency_kernel<NUT, OBM_DET_VARIABLE_REDFIELD><<<blocks, 256, 0, s>>>(a); break;
+        case OBM_DET_NONE: npd_tendency_kernel<NUT, OBM_DET_NONE, ENSEMBLE><<<blocks, 256, 0, s>>>(a); break;
+        case OBM_DET_DETRITUS: npd_tendency_kernel<NUT, OBM_DET_DETRITUS, ENSEMBLE><<<blocks, 256, 0, s>>>(a); break;
+        case OBM_DET_TWO_PARTICLE: npd_tendency_kernel<NUT, OBM_DET_TWO_PARTICLE, ENSEMBLE><<<blocks, 256, 0, s>>>(a); break;
+        default: npd_tendency_kernel<NUT, OBM_DET_VARIABLE_REDFIELD, ENSEMBLE><<<blocks, 256, 0, s>>>(a); break;
+    }
+}
+template <bool ENSEMBLE>
+static void launch_nut(const NpdArgs& a, int nut, int det, dim3 blocks, cudaStream_t s) {
+    switch (nut) {
+        case OBM_NUT_NUTRIENT: launch_det<OBM_NUT_NUTRIENT, ENSEMBLE>(a, det, blocks, s); break;
+        case OBM_NUT_NITRATE_AMMONIA: launch_det<OBM_NUT_NITRATE_AMMONIA, ENSEMBLE>(a, det, blocks, s); break;
+        default: launch_det<OBM_NUT_NITRATE_AMMONIA_IRON, ENSEMBLE>(a, det, blocks, s); break;
     }
 }
 
@@ -272,14 +328,39 @@ extern "C" int obm_npd_tracer_names(const obm_npd_params* p, char (*names)[16]) 
     return npd_layout(p, nullptr, names);
 }
 
-extern "C" int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p, const double* const* tracers,
-                                  const double* PAR, double* const* G, int accumulate, void* stream) {
+extern "C" int obm_npd_param_index(const char* name) {
+    OBM_REQUIRE(name != nullptr, OBM_ENULL, "obm_npd_param_index: name is NULL");
+#define X(n) if (strcmp(name, #n) == 0) return NPD_PARAM_##n;
+    OBM_NPD_DOUBLE_PARAMS(X)
+#undef X
+    set_error("obm_npd_param_index: obm_npd_params has no double member '%s'", name);
+    return OBM_EENUM;
+}
+
+static int npd_launch(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which, const double* values,
+                      const double* const* tracers, const double* PAR, double* const* G, int accumulate, void* stream,
+                      bool ensemble) {
     OBM_REQUIRE(p != nullptr && tracers != nullptr && G != nullptr && PAR != nullptr, OBM_ENULL,
                 "obm_npd_tendencies: params / tracers / G / PAR is NULL");
     NpdArgs a;
     memset(&a, 0, sizeof(a));
     int rc = make_dims(grid, &a.d, false);
     if (rc) return rc;
+    if (ensemble) {
+        OBM_REQUIRE(nvary >= 0 && nvary <= OBM_NPD_MAX_VARIED, OBM_ESIZE, "obm_npd_tendencies_ensemble: nvary = %d outside [0, %d]",
+                    nvary, OBM_NPD_MAX_VARIED);
+        OBM_REQUIRE(nvary == 0 || (which != nullptr && values != nullptr), OBM_ENULL,
+                    "obm_npd_tendencies_ensemble: which / values is NULL");
+        for (int v = 0; v < nvary; v++) {
+            OBM_REQUIRE(which[v] >= 0 && which[v] < NPD_PARAM_COUNT, OBM_EENUM,
+                        "obm_npd_tendencies_ensemble: which[%d] = %d is not a parameter index (0 … %d)", v, which[v],
+                        NPD_PARAM_COUNT - 1);
+            // temperature_coefficient changes the tracer list through has_temperature_coefficient only; its value may vary
+            a.which[v] = which[v];
+        }
+        a.nvary = nvary;
+        a.values = values;
+    }
     int roles[OBM_NPD_MAX_TRACERS];
     const int nt = npd_layout(p, roles, nullptr);
     if (nt < 0) return nt;
@@ -315,10 +396,18 @@ extern "C" int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p,
     a.nrep = nd;
     const dim3 blocks = cell_grid(a.d, 256);
     cudaStream_t s = (cudaStream_t)stream;
-    switch (p->nutrients) {
-        case OBM_NUT_NUTRIENT: launch_det<OBM_NUT_NUTRIENT>(a, p->detritus, blocks, s); break;
-        case OBM_NUT_NITRATE_AMMONIA: launch_det<OBM_NUT_NITRATE_AMMONIA>(a, p->detritus, blocks, s); break;
-        default: launch_det<OBM_NUT_NITRATE_AMMONIA_IRON>(a, p->detritus, blocks, s); break;
-    }
+    if (ensemble) launch_nut<true>(a, p->nutrients, p->detritus, blocks, s);
+    else launch_nut<false>(a, p->nutrients, p->detritus, blocks, s);
     return launch_status("npd_tendency_kernel");
+}
+
+extern "C" int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p, const double* const* tracers,
+                                  const double* PAR, double* const* G, int accumulate, void* stream) {
+    return npd_launch(grid, p, 0, nullptr, nullptr, tracers, PAR, G, accumulate, stream, false);
+}
+
+extern "C" int obm_npd_tendencies_ensemble(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
+                                           const double* values, const double* const* tracers, const double* PAR,
+                                           double* const* G, int accumulate, void* stream) {
+    return npd_launch(grid, p, nvary, which, values, tracers, PAR, G, accumulate, stream, true);
 }

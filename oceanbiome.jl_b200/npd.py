@@ -9,6 +9,8 @@ import ctypes as C
 from dataclasses import dataclass, field
 from typing import Optional
 
+import torch
+
 from . import _lib
 from .grids import RectilinearGrid, current_stream_ptr, require_cuda
 from .light import TwoBandPhotosyntheticallyActiveRadiation, default_surface_PAR
@@ -140,6 +142,37 @@ class NutrientsPlanktonDetritus:
             carbonate_system = CarbonateSystem(carbonate_system)
         self.nutrients, self.plankton, self.detritus = nutrients, plankton, detritus
         self.carbonate_system, self.oxygen = carbonate_system, oxygen
+        self.parameter_ensemble = None
+
+    # -- parameter-sweep ensembles ---------------------------------------------------
+    @staticmethod
+    def parameter_index(name: str) -> int:
+        """Position of `name` among the double members of `obm_npd_params` (= `obm_npd_param_index`)."""
+        doubles = [n for n, t in _lib.obm_npd_params._fields_ if t is C.c_double]
+        if name not in doubles:
+            raise KeyError(f"obm_npd_params has no double member '{name}'; choose from {doubles}")
+        return doubles.index(name)
+
+    def set_parameter_ensemble(self, device=None, **values):
+        """One value per ensemble member for each named parameter (`obm_npd_params` member names); a member is a
+        horizontal column of the grid (box i of `BoxModelGrid(n)`).  The reference builds and runs one model per
+        parameter vector (examples/data_assimilation.jl:26-52); here all members share every launch.  Structural
+        choices (components, formulations, whether T is a tracer) are common to the ensemble.  No arguments: back
+        to one parameter set."""
+        if not values:
+            self.parameter_ensemble = None
+            return self
+        if len(values) > _lib.OBM_NPD_MAX_VARIED:
+            raise ValueError(f"at most {_lib.OBM_NPD_MAX_VARIED} varied parameters")
+        which = [self.parameter_index(n) for n in values]
+        cols = [torch.as_tensor(v, dtype=torch.float64).reshape(-1) for v in values.values()]
+        if len({c.numel() for c in cols}) != 1:
+            raise ValueError("every varied parameter needs one value per member")
+        table = torch.stack(cols).contiguous()
+        if device is not None:
+            table = table.to(device)
+        self.parameter_ensemble = ((C.c_int32 * len(which))(*which), table, tuple(values))
+        return self
 
     # -- C parameter block -------------------------------------------------------------------------
     def c_params(self) -> _lib.obm_npd_params:
@@ -270,8 +303,20 @@ class NutrientsPlanktonDetritus:
         tptr = _lib.pointer_table([tracers[n].ptr for n in names])
         gptr = _lib.pointer_table([G[n].ptr if (n in G and G[n] is not None and n != "T") else None for n in names])
         s = stream if stream is not None else current_stream_ptr(grid.device)
-        rc = lib.obm_npd_tendencies(C.byref(cg), C.byref(p), tptr, PAR.ptr, gptr, 1 if accumulate else 0, s)
-        _lib.check(rc, "obm_npd_tendencies")
+        if self.parameter_ensemble is None:
+            rc = lib.obm_npd_tendencies(C.byref(cg), C.byref(p), tptr, PAR.ptr, gptr, 1 if accumulate else 0, s)
+            _lib.check(rc, "obm_npd_tendencies")
+            return
+        which, table, _ = self.parameter_ensemble
+        members = grid.Nx * grid.Ny
+        if table.shape[1] != members:
+            raise ValueError(f"parameter ensemble has {table.shape[1]} members, the grid has {members} columns")
+        if table.device != PAR.data.device:
+            table = table.to(PAR.data.device)
+            self.parameter_ensemble = (which, table, self.parameter_ensemble[2])
+        rc = lib.obm_npd_tendencies_ensemble(C.byref(cg), C.byref(p), len(which), which, table.data_ptr(), tptr, PAR.ptr,
+                                             gptr, 1 if accumulate else 0, s)
+        _lib.check(rc, "obm_npd_tendencies_ensemble")
 
     def summary(self):
         kind = "NPZD" if isinstance(self.nutrients, Nutrient) else "LOBSTER"
@@ -300,8 +345,10 @@ _DEFAULT = object()
 
 def LOBSTER(grid, nutrients=None, plankton=None, detritus=_DEFAULT, carbonate_system=None, oxygen=None,
             surface_photosynthetically_active_radiation=default_surface_PAR, light_attenuation=_DEFAULT,
-            sediment=None, scale_negatives=False, invalid_fill_value=float("nan"), particles=None, modifiers=None):
-    """`LOBSTER(grid; …)` — constructors.jl:65-96."""
+            sediment=None, scale_negatives=False, invalid_fill_value=float("nan"), particles=None, modifiers=None,
+            parameter_ensemble=None):
+    """`LOBSTER(grid; …)` — constructors.jl:65-96.  `parameter_ensemble = {name: one value per column}` (not in the
+    reference) makes every horizontal column its own parameter set, see `set_parameter_ensemble`."""
     nutrients = nutrients if nutrients is not None else NitrateAmmonia()
     plankton = plankton if plankton is not None else PhytoZoo()
     detritus = TwoParticleAndDissolved() if detritus is _DEFAULT else detritus
@@ -309,14 +356,17 @@ def LOBSTER(grid, nutrients=None, plankton=None, detritus=_DEFAULT, carbonate_sy
         light_attenuation = TwoBandPhotosyntheticallyActiveRadiation(
             grid=grid, surface_PAR=surface_photosynthetically_active_radiation)
     underlying = NutrientsPlanktonDetritus(nutrients, plankton, detritus, carbonate_system, oxygen)
+    if parameter_ensemble:
+        underlying.set_parameter_ensemble(device=grid.device, **parameter_ensemble)
     return _assemble(grid, underlying, light_attenuation, sediment, scale_negatives, invalid_fill_value, particles,
                      modifiers)
 
 
 def NPZD(grid, nutrients=None, plankton=None, detritus=_DEFAULT, carbonate_system=None, oxygen=None,
          surface_photosynthetically_active_radiation=default_surface_PAR, light_attenuation=_DEFAULT,
-         sediment=None, scale_negatives=False, invalid_fill_value=float("nan"), particles=None, modifiers=None):
-    """`NPZD(grid; …)` — constructors.jl:177-227 (Kuhn et al. 2015 parameters)."""
+         sediment=None, scale_negatives=False, invalid_fill_value=float("nan"), particles=None, modifiers=None,
+         parameter_ensemble=None):
+    """`NPZD(grid; …)` — constructors.jl:177-227 (Kuhn et al. 2015 parameters); `parameter_ensemble` as in `LOBSTER`."""
     nutrients = nutrients if nutrients is not None else Nutrient()
     if plankton is None:
         plankton = PhytoZoo(
@@ -343,5 +393,7 @@ def NPZD(grid, nutrients=None, plankton=None, detritus=_DEFAULT, carbonate_syste
         light_attenuation = TwoBandPhotosyntheticallyActiveRadiation(
             grid=grid, surface_PAR=surface_photosynthetically_active_radiation)
     underlying = NutrientsPlanktonDetritus(nutrients, plankton, detritus, carbonate_system, oxygen)
+    if parameter_ensemble:
+        underlying.set_parameter_ensemble(device=grid.device, **parameter_ensemble)
     return _assemble(grid, underlying, light_attenuation, sediment, scale_negatives, invalid_fill_value, particles,
                      modifiers)

@@ -80,3 +80,16 @@ def test_generated_julia_structs_are_in_sync():
     out = subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_julia_structs.py")], capture_output=True,
                          text=True, check=True).stdout
     assert out == open(os.path.join(root, "julia", "obm_structs.jl")).read()
+
+
+def test_npd_parameter_index_space_matches_the_library():
+    """`NutrientsPlanktonDetritus.parameter_index` (from the ctypes struct) ≡ `obm_npd_param_index` (from the C struct)."""
+    import ctypes as C
+    import oceanbiome_b200 as ob
+    lib = _lib.load()
+    doubles = [n for n, t in _lib.obm_npd_params._fields_ if t is C.c_double]
+    assert len(doubles) == 35
+    for n in doubles:
+        assert lib.obm_npd_param_index(n.encode()) == ob.NutrientsPlanktonDetritus.parameter_index(n)
+    assert lib.obm_npd_param_index(b"nutrients") == -3  # structural members cannot vary per member
+    assert lib.obm_npd_param_index(b"bogus") == -3

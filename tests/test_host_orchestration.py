@@ -151,3 +151,28 @@ def test_gas_exchange_boundary_condition_is_applied_after_the_tendencies(lib):
     model = ob.BiogeochemicalModel(g, bgc, extra_tracers=("T", "S"), boundary_conditions={"DIC": co2})
     model.compute_tendencies()
     assert lib.calls == ["obm_npd_tendencies", "obm_gas_exchange_flux"]
+
+
+def test_parameter_ensemble_routes_to_the_ensemble_entry_point(lib):
+    g = grid3()
+    growth = [1e-5 * (1 + m) for m in range(g.Nx * g.Ny)]
+    bgc = ob.NPZD(g, parameter_ensemble={"phytoplankton_maximum_growth_rate": growth})
+    model = ob.BiogeochemicalModel(g, bgc)
+    bgc.update_tendencies(model)
+    assert lib.calls == ["obm_npd_tendencies_ensemble"]
+    lib.calls.clear()
+    bgc.underlying_biogeochemistry.set_parameter_ensemble()  # back to one parameter set
+    bgc.update_tendencies(model)
+    assert lib.calls == ["obm_npd_tendencies"]
+
+
+def test_parameter_ensemble_checks_names_and_member_count(lib):
+    g = grid3()
+    u = ob.NPZD(g).underlying_biogeochemistry
+    with pytest.raises(KeyError):
+        u.set_parameter_ensemble(no_such_rate=[1.0] * 12)
+    with pytest.raises(ValueError):
+        u.set_parameter_ensemble(maximum_grazing_rate=[1.0] * 12, grazing_half_saturation=[1.0] * 11)
+    bgc = ob.NPZD(g, parameter_ensemble={"maximum_grazing_rate": [1.0] * 5})
+    with pytest.raises(ValueError, match="5 members"):
+        bgc.update_tendencies(ob.BiogeochemicalModel(g, bgc))
