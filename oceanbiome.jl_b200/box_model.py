@@ -96,7 +96,10 @@ class BoxModel:
         self.timestepper = timestepper
         # prognostic = everything the biogeochemistry steps; prescribed tracers are overwritten every stage
         self.prognostic = [n for n in names if n not in self.prescribed_tracers]
-        self.Gn = {n: CenterField(self.grid, "Gⁿ" + n) for n in names}
+        # Gⁿ of every field in one allocation: a step without forcing clears all of them with one memset
+        self._Gn_slab = torch.zeros((len(names),) + tuple(self.grid.parent_shape), dtype=torch.float64,
+                                    device=self.grid.device)
+        self.Gn = {n: Field(self.grid, self._Gn_slab[i], "Gⁿ" + n) for i, n in enumerate(names)}
         self.Gm = {n: CenterField(self.grid, "G⁻" + n) for n in names}
         self._tables = None
         self._graph = None
@@ -215,9 +218,12 @@ class BoxModel:
         dev, nx = self.grid.device, self.grid.Nx
 
         def table(fn):
-            rows = [torch.as_tensor(fn(tt), dtype=torch.float64).reshape(-1).expand(nx) if not torch.is_tensor(fn(tt))
-                    else fn(tt).to(torch.float64).reshape(-1).expand(nx) for tt in times]
-            return torch.stack([r.to(dev) for r in rows]).contiguous()
+            """(rows, 1) when the series is the same for every box (one upload, broadcast on the device), else (rows, nx)."""
+            vals = [fn(tt) for tt in times]
+            if not any(torch.is_tensor(v) or getattr(v, "shape", ()) not in ((), (1,)) for v in vals):
+                return torch.tensor([float(v) for v in vals], dtype=torch.float64).reshape(-1, 1).to(dev)
+            rows = [torch.as_tensor(v, dtype=torch.float64).reshape(-1).expand(nx) for v in vals]
+            return torch.stack(rows).contiguous().to(dev)
 
         tabs = {("prescribed", n): table(f) for n, f in self.prescribed_tracers.items()}
         tabs.update({("forcing", n): table(f) for n, f in self.forcing.items() if f is not None and n in self.prognostic})
@@ -244,11 +250,10 @@ class BoxModel:
                     if kind == "prescribed":
                         self._prescribed_target(n).interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
                 self.biogeochemistry.update_biogeochemical_state(self)
+                self._Gn_slab.zero_()
                 for n in self.prognostic:
                     tab = tabs.get(("forcing", n))
-                    if tab is None:
-                        self.Gn[n].data.zero_()
-                    else:
+                    if tab is not None:
                         self.Gn[n].interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
                 self.biogeochemistry.update_tendencies(self)
                 row.add_(1)
@@ -267,12 +272,15 @@ class BoxModel:
         with torch.cuda.graph(g):
             one_step()
         # the capture itself does not execute: state and cursor are still those of step 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         for it in range(steps):
             g.replay()
             if output_every and (it + 1) % output_every == 0:
                 for n in names:
                     out[n][(it + 1) // output_every - 1].copy_(self.fields[n].interior.reshape(-1))
-        self._graph = g
+        e1.record()
+        self._graph, self.replay_events = g, (e0, e1)  # elapsed_time after a synchronize = the replays alone
         self.clock.time = times[-1] if times else self.clock.time
         self.clock.iteration += steps
         self.clock.last_stage_dt = dt * (stages[-1][0] + (stages[-1][1] or 0.0))
