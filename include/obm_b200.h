@@ -144,7 +144,8 @@ int obm_npd_tendencies(const obm_grid* grid, const obm_npd_params* p,
  *             obm_npd_params in declaration order (obm_npd_param_index("phytoplankton_maximum_growth_rate") …);
  *   values    (DEVICE, [nvary][Nx·Ny], member fastest) — the member's value of parameter which[v].
  * Everything not named in `which` — and the structure of the model, i.e. the int32 members — comes from `p`.
- * With nvary = 0 the result is obm_npd_tendencies' bit for bit. */
+ * A member's result does not depend on the other members (bit for bit); against obm_npd_tendencies run with that member's
+ * block it agrees to rounding — the two kernel instantiations may contract different multiply-adds. */
 #define OBM_NPD_MAX_VARIED 16
 int obm_npd_param_index(const char* name); /* ≥ 0, or OBM_EENUM when obm_npd_params has no such double member */
 int obm_npd_tendencies_ensemble(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
