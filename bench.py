@@ -450,6 +450,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(workload_table()))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink Ny (or n) for quick checks; not a bench number")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): one full slab per GPU; strong: the N=1 grid split into N y-slabs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
@@ -479,6 +481,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if args.scaling == "strong":  # SURVEY §8d asks for both: the global grid stays that of N = 1, each rank owns Ny / N rows
+        args.scale = args.scale / world
     w = Workload(name, device, args.scale)
     sampler = ClockSampler(device.index or 0)
 
@@ -600,7 +604,7 @@ def main():
     line = {
         "metric": "BGC tendency Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": name, "description": w.description, "cells_per_gpu": w.cells,
                    "l2": "inputs larger than L2 (no flush needed)" if not small
                          else "working set fits L2: evicted by a 256 MB write before every step (not timed); time = sum of per-step event pairs",
