@@ -317,6 +317,23 @@ def ncu_traffic(workload, cells):
     return None, None
 
 
+def fp64_roofline(workload, cells, kernel_ms):
+    """The dominant kernel against the OTHER roof BASELINE.json's metric names: FP64-pipe instructions per cell counted by
+    ncu in the committed capture (profiles/traffic.json) × this run's cells ÷ this run's kernel time, against the DFMA
+    rate measured on this pool's B200s.  None when the capture holds no count for this workload."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    d = t.get(workload) or {}
+    if "fp64_instr_per_cell" not in d or "fp64_peak_instr_per_s" not in t:
+        return None
+    achieved = d["fp64_instr_per_cell"] * cells / (kernel_ms * 1e-3) / 1e12
+    peak = t["fp64_peak_instr_per_s"] / 1e12
+    return {"instr_per_cell": d["fp64_instr_per_cell"], "achieved": achieved, "peak": peak, "unit": "T FP64 instr/s",
+            "frac": achieved / peak, "source": d["fp64_source"], "peak_source": t["fp64_peak_source"]}
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU legs (the oracle = port of the reference algorithm and launch structure)
 # --------------------------------------------------------------------------------------------------
@@ -594,7 +611,8 @@ def main():
                 "algorithmic_bytes_per_cell": w.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
                 # graph mode: kernel_ms comes from separate eager launches (it includes their launch latency, which the
                 # graphed stage does not pay), so a share of the graphed step would be meaningless
-                "kernel_share_of_step": None if use_graph else kernel_ms / (ms / args.steps)}
+                "kernel_share_of_step": None if use_graph else kernel_ms / (ms / args.steps),
+                "fp64": fp64_roofline(name, w.cells, kernel_ms)}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         desc, cfg = workload_table()[name]
