@@ -318,6 +318,36 @@ class NutrientsPlanktonDetritus:
                                              gptr, 1 if accumulate else 0, s)
         _lib.check(rc, "obm_npd_tendencies_ensemble")
 
+    def __call__(self, name: str, *, PAR, device="cuda", **tracers):
+        """The per-tracer form `bgc(Val(name), x, y, z, t, tracers..., PAR)` of the plugin API
+        (docs/src/model_implementation.md:34-75; the built-in models' discrete form
+        `bgc(i, j, k, grid, Val(name), clock, fields, aux)`, NutrientsPlanktonDetritus.jl:88): the tendency of ONE tracer
+        at the given state — scalars, or arrays of states evaluated side by side.  The fused kernel runs on a row of
+        boxes and the named tendency is returned (a float for scalar input, else a device tensor), so any single
+        tendency can be inspected without assembling a model."""
+        from .grids import CenterField
+        names = self.required_biogeochemical_tracers()
+        if name not in names:
+            raise KeyError(f"{name} is not a tracer of this model {names}")
+        vals = {n: torch.as_tensor(tracers.get(n, 0.0), dtype=torch.float64).reshape(-1) for n in names}
+        unknown = set(tracers) - set(names)
+        if unknown:
+            raise KeyError(f"unknown tracers {sorted(unknown)}; this model carries {names}")
+        vals["PAR"] = torch.as_tensor(PAR, dtype=torch.float64).reshape(-1)
+        n = max(v.numel() for v in vals.values())
+        grid = RectilinearGrid(size=(n,), x=(0.0, float(n)), topology=("Periodic", "Flat", "Flat"), halo=(0,), device=device)
+        f = {k: CenterField(grid, k).set(v.expand(n).reshape(1, 1, n)) for k, v in vals.items()}
+        G = {k: CenterField(grid, "G" + k) for k in names}
+        saved = self.parameter_ensemble  # a parameter sweep applies when one state per member is given
+        if saved is not None and saved[1].shape[1] != n:
+            self.parameter_ensemble = None
+        try:
+            self.compute_tendencies(grid, f, {"PAR": f["PAR"]}, G, accumulate=False)
+        finally:
+            self.parameter_ensemble = saved
+        out = G[name].interior.reshape(-1)
+        return out.item() if n == 1 and all(v.numel() == 1 for v in vals.values()) and not torch.is_tensor(PAR) else out
+
     def summary(self):
         kind = "NPZD" if isinstance(self.nutrients, Nutrient) else "LOBSTER"
         return f"{kind} model ({', '.join(':' + t for t in self.required_biogeochemical_tracers())})"

@@ -130,3 +130,33 @@ def test_conservation_over_100_steps_on_device(cuda):
     N1, C1 = total()
     assert abs(N1 - N0) <= 1.5e-8 * abs(N0) and abs(C1 - C0) <= 1.5e-8 * abs(C0)
     assert model.clock.iteration == 100 and abs(model.clock.time - 100.0) < 1e-9
+
+
+def test_per_tracer_call_form(cuda, oracle):
+    """`bgc(Val(name), …)` — one tracer's tendency at a state — is the fused kernel evaluated on boxes."""
+    bgc = ob.LOBSTER(ob.BoxModelGrid(1, device=cuda), carbonate_system=ob.CarbonateSystem(),
+                     oxygen=ob.Oxygen()).underlying_biogeochemistry
+    state = {"NO₃": 10.0, "NH₄": 0.1, "P": 0.1, "Z": 0.01, "sPOM": 0.2, "bPOM": 0.1, "DOM": 0.3, "DIC": 2200.0,
+             "Alk": 2400.0, "O₂": 250.0}
+    names = bgc.required_biogeochemical_tracers()
+    # the oracle on the same single cell
+    grid = ob.BoxModelGrid(1, device=cuda)
+    _, host, og = synthetic_state(grid, names, synthetic.lobster_range)
+    for n in names:
+        og.interior(host[n])[...] = state.get(n, 0.0)
+    PARh = np.zeros(og.parent_shape)
+    og.interior(PARh)[...] = 40.0
+    Go = oracle.npd_tendencies(og, bgc.c_params(), [host[n] for n in names], PARh)
+    want = {n: og.interior(g).item() for n, g in zip(names, Go)}
+    S = max(abs(v) for v in want.values())
+    for n in names:
+        got = bgc(n, PAR=40.0, device=cuda, **state)
+        assert isinstance(got, float) and abs(got - want[n]) <= RTOL_TENDENCY * S, (n, got, want[n])
+    # arrays of states side by side
+    PAR = torch.linspace(0.0, 100.0, 7, dtype=torch.float64)
+    gP = bgc("P", PAR=PAR, device=cuda, **state)
+    assert gP.shape == (7,) and bool((gP[1:] > gP[:-1]).all())  # growth increases with light
+    with pytest.raises(KeyError):
+        bgc("Q", PAR=1.0, device=cuda)
+    with pytest.raises(KeyError):
+        bgc("P", PAR=1.0, device=cuda, Q=1.0)
