@@ -63,10 +63,12 @@ def load_output(save: SpeedyOutput, name=None):
         return {n: z[n][order] for n in z.files}
 
 
-def BoxModelGrid(n: int = 1, device="cuda") -> RectilinearGrid:
-    """`BoxModelGrid()` (src/OceanBioME.jl:171) for `n` independent boxes: x is the ensemble axis, y and z are Flat
-    (the single level spans z ∈ [−1, 0] so that kernels reading z see a finite node)."""
-    return RectilinearGrid(size=(int(n),), x=(0.0, float(n)), topology=("Periodic", "Flat", "Flat"), halo=(0,),
+def BoxModelGrid(n: int = 1, device="cuda", z: Optional[float] = None) -> RectilinearGrid:
+    """`BoxModelGrid(; z)` (src/OceanBioME.jl:171) for `n` independent boxes: x is the ensemble axis, y and z are Flat.
+    The single level is centred on `z` (the reference's Flat z-node, e.g. `BoxModelGrid(; z = -5)` in test_PISCES.jl:37);
+    without it the level spans z ∈ [−1, 0] so that kernels reading z see a finite node."""
+    span = (-1.0, 0.0) if z is None else (float(z) - 0.5, float(z) + 0.5)
+    return RectilinearGrid(size=(int(n),), x=(0.0, float(n)), z=span, topology=("Periodic", "Flat", "Flat"), halo=(0,),
                            device=device)
 
 

@@ -160,6 +160,7 @@ class Field:
     grid: RectilinearGrid
     data: torch.Tensor
     name: str = ""
+    constant: bool = False  # Oceananigans' ConstantField: prescribed by the user, never recomputed by a hook
 
     @property
     def ptr(self) -> int:
@@ -209,6 +210,14 @@ def ZFaceField(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Fiel
     """`ZFaceField(grid)` — (Center, Center, Face): parent has Nz + 1 + 2Hz levels."""
     shape = (grid.Nz + 1 + 2 * grid.Hz, grid.Ny + 2 * grid.Hy, grid.Nx + 2 * grid.Hx)
     return Field(grid, torch.full(shape, fill, dtype=torch.float64, device=grid.device), name)
+
+
+def ConstantField(grid: RectilinearGrid, value: float, name: str = "") -> Field:
+    """`ConstantField(value)` where the reference prescribes a column quantity (zₘₓₗ, zₑᵤ, κ̄, PAR̄ₘₓₗ of a box model,
+    test_PISCES.jl:44-48): an x–y field holding `value` that the state update leaves alone, like the reference's
+    `compute_euphotic_depth!(::ConstantField, args...) = nothing` (compute_euphotic_depth.jl:44-46) and
+    `compute_mixed_layer_mean!(::ConstantField, …) = nothing` (mean_mixed_layer_properties.jl:21)."""
+    return Field(grid, torch.full(grid.plane_shape, float(value), dtype=torch.float64, device=grid.device), name, True)
 
 
 def Field2D(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Field:

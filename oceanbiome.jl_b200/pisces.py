@@ -435,18 +435,21 @@ class PISCESModel:
                 self._carbonate_state(model))
 
     def column_light_state(self, model):
-        """What the multi-band PAR launch needs to also leave zₑᵤ and the mixed-layer mean PAR (update_state.jl:7,11)."""
+        """What the multi-band PAR launch needs to also leave zₑᵤ and the mixed-layer mean PAR (update_state.jl:7,11);
+        None when either is a prescribed `ConstantField` (then nothing may overwrite it)."""
+        if self.euphotic_depth.constant or self.mean_mixed_layer_light.constant:
+            return None
         return (self.mixed_layer_depth, 1 / 1000, self.euphotic_depth, self.mean_mixed_layer_light)
 
     def update_biogeochemical_state(self, model, stream: Optional[int] = None, calcite_saturation_done: bool = False,
                                     light_state_done: bool = False):
         PAR = model.biogeochemistry.light_attenuation.biogeochemical_auxiliary_fields()["PAR"]
-        if not light_state_done:
+        if not light_state_done and not self.euphotic_depth.constant:
             compute_euphotic_depth(self.euphotic_depth, PAR, stream=stream)
         kappa = getattr(model, "vertical_diffusivity", None)  # closure = nothing ⇒ pre-set κ̄ is kept (:64-67)
-        if kappa is not None:
+        if kappa is not None and not self.mean_mixed_layer_vertical_diffusivity.constant:
             compute_mixed_layer_mean(self.mean_mixed_layer_vertical_diffusivity, self.mixed_layer_depth, kappa, model.grid, stream)
-        if not light_state_done:
+        if not light_state_done and not self.mean_mixed_layer_light.constant:
             compute_mixed_layer_mean(self.mean_mixed_layer_light, self.mixed_layer_depth, PAR, model.grid, stream)
         if calcite_saturation_done:  # solved in the negative-scaling launch (Biogeochemistry.update_biogeochemical_state)
             return

@@ -118,6 +118,39 @@ def test_reference_conservation_test_on_device(cuda):
         assert abs(sum(terms)) <= 2e-15 * sum(abs(x) for x in terms)
 
 
+def test_reference_conservation_test_as_a_box_model(cuda):
+    """test/test_PISCES.jl:32-92 as written there: `BoxModelGrid(; z = -5)`, ConstantFields for zₘₓₗ, zₑᵤ, κ̄ and
+    PAR̄ₘₓₗ, one `time_step!` from the zero state (everything but T, S stays 0), then the initial values, another
+    `time_step!`, and the element budgets of `model.timestepper.Gⁿ`."""
+    grid = ob.BoxModelGrid(1, device=cuda, z=-5)
+    PAR = {n: ob.CenterField(grid, n, 100.0) for n in ("PAR₁", "PAR₂", "PAR₃")}
+    PAR["PAR"] = ob.CenterField(grid, "PAR", 300.0)
+    bgc = ob.PISCES(grid, sinking_speeds={"POC": 0.0, "GOC": 0.0},
+                    light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR),
+                    mixed_layer_depth=ob.ConstantField(grid, -10.0), euphotic_depth=ob.ConstantField(grid, -10.0),
+                    mean_mixed_layer_vertical_diffusivity=ob.ConstantField(grid, 1.0),
+                    mean_mixed_layer_light=ob.ConstantField(grid, 300.0),
+                    iron=pisces.SimpleIron(excess_scavenging_enhancement=0.0),
+                    nitrogen=pisces.NitrateAmmonia(maximum_fixation_rate=0.0))
+    model = ob.BoxModel(biogeochemistry=bgc, grid=grid)
+    model.time_step(1.0)
+    assert all(f.interior.item() == 0.0 for n, f in model.fields.items() if n not in ("T", "S"))
+    model.set(**pisces.PISCES_INITIAL_VALUES)
+    before = {n: f.interior.item() for n, f in model.fields.items()}
+    model.time_step(1.0)
+    assert any(model.fields[n].interior.item() != before[n] for n in ("P", "NO₃", "DIC"))
+    u = bgc.underlying_biogeochemistry
+    assert u.euphotic_depth.data.item() == -10.0 and u.mean_mixed_layer_light.data.item() == 300.0  # left alone
+    G = {n: model.Gn[n].interior.item() for n in pisces.TRACERS}
+    cons = u.conserved_tracers(ntuple=True)
+    for key in ("carbon", "silicon"):
+        terms = [G[n] for n in cons[key]]
+        assert abs(sum(terms)) <= 2e-15 * sum(abs(x) for x in terms), key
+    for key in ("iron", "phosphate", "nitrogen"):
+        terms = [G[n] * f for n, f in zip(cons[key]["tracers"], cons[key]["scalefactors"])]
+        assert abs(sum(terms)) <= 2e-15 * sum(abs(x) for x in terms), key
+
+
 def test_state_update_matches_oracle(cuda, oracle):
     """update_biogeochemical_state!: 3-band PAR from PChl + DChl, zₑᵤ, PAR̄ₘₓₗ, Ω (update_state.jl:1-17)."""
     grid, bgc, model = build(cuda, (40, 6, 30), (1e4, 1e3, 500.0))

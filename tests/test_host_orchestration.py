@@ -176,3 +176,47 @@ def test_parameter_ensemble_checks_names_and_member_count(lib):
     bgc = ob.NPZD(g, parameter_ensemble={"maximum_grazing_rate": [1.0] * 5})
     with pytest.raises(ValueError, match="5 members"):
         bgc.update_tendencies(ob.BiogeochemicalModel(g, bgc))
+
+
+def pisces_box(constant_zeu=True, constant_mean_light=True):
+    from oceanbiome_b200 import pisces
+    grid = ob.BoxModelGrid(1, device="cpu", z=-5)
+    PAR = {n: ob.CenterField(grid, n, 100.0) for n in ("PAR₁", "PAR₂", "PAR₃")}
+    PAR["PAR"] = ob.CenterField(grid, "PAR", 300.0)
+    bgc = ob.PISCES(grid, sinking_speeds={"POC": 0.0, "GOC": 0.0},
+                    light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR),
+                    mixed_layer_depth=ob.ConstantField(grid, -10.0),
+                    euphotic_depth=ob.ConstantField(grid, -10.0) if constant_zeu else None,
+                    mean_mixed_layer_vertical_diffusivity=ob.ConstantField(grid, 1.0),
+                    mean_mixed_layer_light=ob.ConstantField(grid, 300.0) if constant_mean_light else None,
+                    iron=pisces.SimpleIron(excess_scavenging_enhancement=0.0),
+                    nitrogen=pisces.NitrateAmmonia(maximum_fixation_rate=0.0))
+    return ob.BoxModel(biogeochemistry=bgc, grid=grid), bgc
+
+
+def test_pisces_box_model_leaves_constant_fields_alone(lib):
+    """test/test_PISCES.jl:32-60: a PISCES box model prescribes zₑᵤ, κ̄ and PAR̄ₘₓₗ as ConstantFields, for which the
+    reference's state update does nothing (compute_euphotic_depth.jl:44-46, mean_mixed_layer_properties.jl:21,59)."""
+    model, bgc = pisces_box()
+    model.time_step(1.0)
+    stage = ["obm_calcite_saturation", "obm_pisces_tendencies"]
+    assert lib.calls == stage + 3 * (["obm_rk3_substep"] + stage)
+    u = bgc.underlying_biogeochemistry
+    assert u.euphotic_depth.data.unique().tolist() == [-10.0] and u.mean_mixed_layer_light.data.unique().tolist() == [300.0]
+
+
+def test_pisces_recomputes_only_what_is_not_constant(lib):
+    model, _ = pisces_box(constant_zeu=False)
+    model.update_state()
+    assert lib.calls == ["obm_euphotic_depth", "obm_calcite_saturation", "obm_pisces_tendencies"]
+    lib.calls.clear()
+    model, _ = pisces_box(constant_mean_light=False)
+    model.update_state()
+    assert lib.calls == ["obm_mixed_layer_mean", "obm_calcite_saturation", "obm_pisces_tendencies"]
+
+
+def test_computed_light_with_a_constant_column_field_takes_the_plain_scan(lib):
+    g = grid3()
+    bgc = ob.PISCES(g, euphotic_depth=ob.ConstantField(g, -50.0))
+    ob.BiogeochemicalModel(g, bgc).update_state()
+    assert lib.calls == ["obm_par_multiband", "obm_mixed_layer_mean", "obm_calcite_saturation"]
