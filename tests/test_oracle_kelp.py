@@ -2,7 +2,9 @@
 restatement is (a) the bookkeeping between the particle equations (equations.jl:1-36) and the tracer coupling
 (coupling.jl:3-57) that makes test/test_sugar_kelp.jl's nitrogen and carbon conservation hold, (b) the defining equation
 of the light-inhibition parameter, (c) the documented parameter values, (d) the nearest-node deposit rule the reference's
-particle tests state (test/test_particles.jl:97-114)."""
+particle tests state (test/test_particles.jl:97-114), and — r02 — (e) an independent plain-Python transliteration of
+equations.jl / coupling.jl (oracle/pyref_kelp.py, no code shared with oracle_kelp.c) through committed golden vectors
+(tests/golden/kelp_rates.json by scripts/make_kelp_golden.py): absolute rates, all eleven of them."""
 import math
 
 import numpy as np
@@ -149,3 +151,57 @@ def test_scatter_and_step_drivers(oracle):
                                   PAR.ravel()[cells[i]]) for i in range(n)])
         assert np.array_equal(out[j], d)
         assert np.array_equal(keep[3 + j], (A, N, Cr)[j] + d * 30.0)
+
+
+# ---- independent restatement ------------------------------------------------------------------------------------------
+
+def _golden():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "kelp_rates.json")) as fh:
+        return json.load(fh)
+
+
+def test_golden_vectors_are_what_the_restatement_produces():
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import pyref_kelp as ref
+    g = _golden()
+    assert tuple(g["names"]) == ref.NAMES and len(g["cases"]) == 36
+    for case in g["cases"][::5]:
+        kelp, s = ref.SugarKelp(**case["parameters"]), case["state"]
+        rates = [kelp(n, s["t"], s["A"], s["N"], s["C"], s["u"], s["v"], s["w"], s["T"], s["NO3"], s["NH4"], s["PAR"])
+                 for n in ref.NAMES]
+        assert rates == case["rates"]
+
+
+def test_c_oracle_matches_independent_restatement(oracle):
+    """All eleven rates at 12 states × 3 parameter sets, relative 1e-13 (measured: identical to the last bit)."""
+    g = _golden()
+    assert tuple(g["names"]) == tuple(oracle.KELP_NAMES)
+    worst = 0.0
+    for case in g["cases"]:
+        p, s = ob.SugarKelp(**case["parameters"]).c_params(), case["state"]
+        for name, want in zip(g["names"], case["rates"]):
+            got = oracle.kelp(p, name, s["t"], s["A"], s["N"], s["C"], s["T"], s["NO3"], s["NH4"], s["PAR"], s["u"], s["v"], s["w"])
+            worst = max(worst, abs(got - want) / abs(want) if want else abs(got))
+    assert worst <= 1e-13, worst
+
+
+def test_host_parameter_defaults_match_the_restatement():
+    """Every keyword default of SugarKelp.jl:88-139 as the host mirror holds it ≡ as the restatement derives it."""
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import pyref_kelp as ref
+    mine, theirs = ob.SugarKelp(), ref.SugarKelp()
+    checked = 0
+    for name, want in vars(theirs).items():
+        if name == "temperature_limit":
+            for f in ("lower_optimal", "upper_optimal", "lower_gradient", "upper_gradient"):
+                assert getattr(mine.temperature_limit, f) == pytest.approx(getattr(want, f), rel=1e-15)
+            continue
+        assert getattr(mine, name) == pytest.approx(want, rel=1e-15), name
+        checked += 1
+    assert checked >= 40
