@@ -54,6 +54,15 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.obm_carbon_chemistry(4, None, dummy, dummy, dummy, dummy, None, None, None, None, 42, dummy, None) == -3
     assert lib.obm_carbon_chemistry(0, None, None, None, None, None, None, None, None, None, 0, None, None) == 0
     assert lib.obm_inventory_workspace_bytes(5) == 5 * 148 * 4 * 8
+    # the ensemble entry point refuses a bad sweep description before it touches the device
+    p = _lib.obm_npd_params()
+    ens = lambda nvary, which, values: lib.obm_npd_tendencies_ensemble(  # noqa: E731
+        C.byref(g), C.byref(p), nvary, which, values, dummy, dummy, dummy, 0, None)
+    assert ens(_lib.OBM_NPD_MAX_VARIED + 1, (C.c_int32 * 17)(), dummy) == -2 and b"nvary" in lib.obm_last_error()
+    assert ens(-1, None, None) == -2
+    assert ens(1, None, dummy) == -1 and ens(1, (C.c_int32 * 1)(0), None) == -1
+    assert ens(1, (C.c_int32 * 1)(35), dummy) == -3 and b"not a parameter index" in lib.obm_last_error()
+    assert ens(1, (C.c_int32 * 1)(-1), dummy) == -3
 
 
 def test_tracer_names_from_the_library_match_reference_order():
