@@ -616,7 +616,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         desc, cfg = workload_table()[name]
-        budget = 2_000_000 if cfg["model"] != "pisces" else 200_000
+        # ≈ 10 s of one host core on the GPU box: PISCES ≈ 0.13, LOBSTER ≈ 2, the carbonate solve ≈ 0.4 Mcell/s
+        budget = {"pisces": 1_500_000, "carbon": 4_000_000}.get(cfg["model"], 8_000_000)
         v, sample = cpu_sample(name, 1, budget)
         cpu = {"value": v / 1e9, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample}
     line = {
