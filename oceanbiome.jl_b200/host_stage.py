@@ -52,8 +52,13 @@ def bind_to_gpu_numa_node(device) -> bool:
 
 
 class HostStagedStage:
-    def __init__(self, model, nslabs: int = 16, pin: bool = True, copy_engine: str = "dma", host_buffers=None):
+    def __init__(self, model, nslabs: int = 16, pin: bool = True, copy_engine: str = "dma", host_buffers=None,
+                 return_tracers: bool = False):
+        """`return_tracers`: also copy the tracers back after the stage (the state update may have rescaled them —
+        `ScaleNegativeTracers` works in place).  Off by default: in the drop-in the tracer arrays live on the device
+        (Julia hands over CuArrays) and what a stage produces for its caller is the tendencies."""
         self.model = model
+        self.return_tracers = bool(return_tracers)
         self.grid = model.grid
         if copy_engine not in ("sm", "dma", "sm_h2d", "sm_d2h"):
             raise ValueError("copy_engine: 'dma' (cudaMemcpy2DAsync), 'sm' (persistent copy kernel) or 'sm_h2d' / 'sm_d2h' "
@@ -82,7 +87,8 @@ class HostStagedStage:
         skip = g.Hz * (g.Nx + 2 * g.Hx) * (g.Ny + 2 * g.Hy) * 8  # bytes of the bottom halo planes
         plane_bytes = (g.Nx + 2 * g.Hx) * 8 * self.nplanes
         self.h2d_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * len(self.names)
-        self.d2h_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * len(self.gnames)
+        self.d2h_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * (
+            len(self.gnames) + (len(self.names) if self.return_tracers else 0))
         self._src_in = _lib.pointer_table([self.host_tracers[n].data_ptr() + skip for n in self.names])
         self._dst_in = _lib.pointer_table([model.tracers[n].ptr + skip for n in self.names])
         self._src_out = _lib.pointer_table([model.Gn[n].ptr + skip for n in self.gnames])
@@ -121,6 +127,10 @@ class HostStagedStage:
             rc = copy_out(C.byref(cg), len(self.gnames), self._dst_out, self._src_out, self.nplanes, 1,
                                    self.s_out.cuda_stream)
             _lib.check(rc, "obm_copy_slab(D2H)")
+            if self.return_tracers:  # src / dst swapped: device tracers → host tracers
+                rc = copy_out(C.byref(cg), len(self.names), self._src_in, self._dst_in, self.nplanes, 1,
+                              self.s_out.cuda_stream)
+                _lib.check(rc, "obm_copy_slab(D2H, tracers)")
         for s in (self.s_in, self.s_run, self.s_out):
             cur.wait_stream(s)
 

@@ -49,6 +49,27 @@ def test_host_staged_lobster_equals_resident(cuda, nslabs, engine, Nx):
     assert stage.h2d_bytes == len(model.tracers) * grid.Ny * (grid.Nx + 6) * grid.Nz * 8  # interior k-planes only
 
 
+@pytest.mark.parametrize("engine", ["dma", "sm"])
+def test_host_staged_stage_can_return_the_rescaled_tracers(cuda, engine):
+    """`return_tracers=True`: what `ScaleNegativeTracers` did to the state in place comes back to the host arrays too."""
+    grid, bgc, model = lobster(cuda)
+    stage = HostStagedStage(model, nslabs=3, copy_engine=engine, return_tracers=True)
+    stage.upload_from_device()
+    sent = {n: t.clone() for n, t in stage.host_tracers.items()}
+    model.update_state()  # resident reference: the state update rescales in place
+    want = {n: f.data.clone() for n, f in model.tracers.items()}
+    for f in model.tracers.values():
+        f.data.fill_(float("nan"))
+    stage.step()
+    stage.synchronize()
+    for n in stage.names:
+        assert torch.equal(grid.interior(stage.host_tracers[n]), grid.interior(want[n]).cpu()), n
+    assert bool((grid.interior(sent["NO₃"]) < 0).any()) and bool((grid.interior(stage.host_tracers["NO₃"]) >= 0).all())
+    assert not torch.equal(grid.interior(stage.host_tracers["NH₄"]), grid.interior(sent["NH₄"]))  # its group was rescaled
+    per_field = grid.Ny * (grid.Nx + 6) * grid.Nz * 8
+    assert stage.d2h_bytes == (len(stage.gnames) + len(stage.names)) * per_field
+
+
 def test_host_staged_pisces_equals_resident(cuda):
     grid = ob.RectilinearGrid(size=(40, 16, 10), extent=(4e3, 1.6e3, 200.0), device=cuda)
     bgc = ob.PISCES(grid, scale_negatives=True, surface_photosynthetically_active_radiation=75.0)
