@@ -70,6 +70,8 @@ class RectilinearGrid:
                 zf = z.copy()
         if zf.size != self.Nz + 1:
             raise ValueError(f"need {self.Nz + 1} z faces, got {zf.size}")
+        if not np.all(np.diff(zf) > 0):  # Oceananigans: "z faces must be strictly increasing" (bottom first)
+            raise ValueError("z faces must be strictly increasing, from the bottom face to the surface")
         # … extended into the halos with the end-cell spacing, like Oceananigans does
         Hz = self.Hz
         lo = zf[0] - (zf[1] - zf[0]) * np.arange(Hz, 0, -1)

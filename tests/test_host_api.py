@@ -94,3 +94,14 @@ def test_compute_entry_points_refuse_cpu_tensors(grid):
         model.update_state()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.compute_tendencies()
+
+
+def test_z_faces_must_increase():
+    import pytest
+    import oceanbiome_b200 as ob
+    with pytest.raises(ValueError, match="strictly increasing"):
+        ob.RectilinearGrid(size=(2, 2, 3), x=(0, 1), y=(0, 1), z=[0.0, -1.0, -2.0, -3.0], device="cpu")
+    with pytest.raises(ValueError, match="strictly increasing"):
+        ob.RectilinearGrid(size=(2, 2, 2), x=(0, 1), y=(0, 1), z=[-2.0, -1.0, -1.0], device="cpu")
+    g = ob.RectilinearGrid(size=(2, 2, 3), x=(0, 1), y=(0, 1), z=[-3.0, -2.0, -0.5, 0.0], device="cpu")
+    assert list(g.zc) == [-2.5, -1.25, -0.25]

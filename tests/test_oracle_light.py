@@ -106,3 +106,89 @@ def test_euphotic_depth_never_reached_returns_znode_zero(oracle):
     PAR = np.full(og.parent_shape, 50.0)
     zeu = oracle.euphotic_depth(og, PAR)
     assert zeu[0, 0, 0] == og.zc_parent[og.Hz - 1] == -17.0
+
+
+# ---- independent restatement (oracle/pyref_light.py: plain Python, one column at a time, no code shared with the C) ----
+
+def _pyref():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    import pyref_light
+    return pyref_light
+
+
+def _stretched_column(oracle, rng, Nz, Lz, nx=3):
+    faces = -Lz * (1 - np.linspace(0, 1, Nz + 1)) ** 1.7  # faces[0] = −Lz … faces[-1] = 0, fine near the surface
+    faces[1:-1] += rng.uniform(-0.2, 0.2, Nz - 1) * np.diff(faces).min()
+    g = ob.RectilinearGrid(size=(nx, Nz), x=(0, nx), z=faces, topology=("Periodic", "Flat", "Bounded"), device="cpu")
+    return g, oracle.Grid.like(g)
+
+
+def _cols(ref, g):
+    """1-based zc[0 … Nz + 1], zf[1 … Nz + 1] views of the grid's host z arrays."""
+    zc = ref.Col(g.zc_host[g.Hz - 1:g.Hz + g.Nz + 1], lo=0)
+    zf = ref.Col(g.zf_host[g.Hz:g.Hz + g.Nz + 1], lo=1)
+    return zc, zf
+
+
+def test_c_oracle_matches_independent_two_band(oracle):
+    ref, rng = _pyref(), np.random.default_rng(5)
+    for Nz, Lz in ((1, 10.0), (7, 80.0), (40, 300.0)):
+        g, og = _stretched_column(oracle, rng, Nz, Lz)
+        par = ob.TwoBandPhotosyntheticallyActiveRadiation(grid=g, surface_PAR=100.0)
+        P = np.zeros(og.parent_shape)
+        og.interior(P)[...] = rng.uniform(0.0, 2.0, og.interior(P).shape)
+        og.interior(P)[Nz // 2, 0, 1] = 0.0  # a level without phytoplankton
+        S = np.zeros(og.plane_shape)
+        S[...] = rng.uniform(5.0, 200.0, S.shape)
+        PAR = oracle.par_twoband(og, par.c_params(), P, S)
+        zc, zf = _cols(ref, g)
+        for i in range(g.Nx):
+            want = ref.two_band(Nz, zc, zf, ref.Col(og.interior(P)[:, 0, i]), float(og.interior(S)[0, 0, i]),
+                                par.water_red_attenuation, par.water_blue_attenuation, par.chlorophyll_red_attenuation,
+                                par.chlorophyll_blue_attenuation, par.chlorophyll_red_exponent, par.chlorophyll_blue_exponent,
+                                par.pigment_ratio, par.phytoplankton_chlorophyll_ratio)
+            np.testing.assert_allclose(og.interior(PAR)[:, 0, i], want.v, rtol=2e-14)
+
+
+def test_c_oracle_matches_independent_multi_band_and_column_diagnostics(oracle):
+    ref, rng = _pyref(), np.random.default_rng(6)
+    from oceanbiome_b200.light import MOREL_e, MOREL_kʷ, MOREL_λ, MOREL_χ
+    bands = ((400, 500), (500, 600), (600, 700))
+    for Nz, Lz in ((2, 20.0), (9, 120.0), (64, 400.0)):
+        g, og = _stretched_column(oracle, rng, Nz, Lz)
+        m = ob.MultiBandPhotosyntheticallyActiveRadiation(grid=g, surface_PAR=100.0, surface_PAR_division=[0.5, 0.25, 0.25])
+        # the three Morel means, derived independently from the base tables
+        for mine, base in ((m.water_attenuation_coefficient, MOREL_kʷ), (m.chlorophyll_exponent, MOREL_e),
+                           (m.chlorophyll_attenuation_coefficient, MOREL_χ)):
+            np.testing.assert_allclose(mine, ref.band_coefficients(bands, list(MOREL_λ), list(base)), rtol=1e-15)
+        a, b = np.zeros(og.parent_shape), np.zeros(og.parent_shape)
+        og.interior(a)[...] = rng.uniform(0.0, 1.5, og.interior(a).shape)
+        og.interior(b)[...] = rng.uniform(0.0, 0.5, og.interior(b).shape)
+        PAR0 = 80.0
+        fields, total = oracle.par_multiband(og, m.c_params(), a, b, 1.0, PAR0)
+        zc, zf = _cols(ref, g)
+        zmxl = np.zeros(og.plane_shape)
+        zmxl[...] = rng.uniform(-0.9 * Lz, -0.02 * Lz, zmxl.shape)
+        # level above the surface as the value boundary condition would leave it (2·surface − top)
+        for f, d in zip(fields + [total], m.surface_PAR_division + [1.0]):
+            f[og.Hz + Nz] = 2 * PAR0 * d - f[og.Hz + Nz - 1]
+        cutoff = 0.3  # reached inside even the shallow columns
+        zeu = oracle.euphotic_depth(og, total, cutoff)
+        mean = oracle.mixed_layer_mean(og, zmxl, total)
+        for i in range(g.Nx):
+            chl = ref.Col(og.interior(a)[:, 0, i] + og.interior(b)[:, 0, i])
+            want_total = np.zeros(Nz)
+            for n in range(3):
+                w = ref.multi_band(Nz, zc, chl, PAR0, m.surface_PAR_division[n], m.water_attenuation_coefficient[n],
+                                   m.chlorophyll_exponent[n], m.chlorophyll_attenuation_coefficient[n])
+                np.testing.assert_allclose(og.interior(fields[n])[:, 0, i], w.v, rtol=2e-14)
+                want_total += np.array(w.v)
+            np.testing.assert_allclose(og.interior(total)[:, 0, i], want_total, rtol=2e-14)
+            col = ref.Col(list(og.interior(total)[:, 0, i]) + [float(total[og.Hz + Nz, og.Hy, og.Hx + i])])
+            got_zeu = float(og.interior(zeu)[0, 0, i])
+            assert abs(got_zeu - ref.euphotic_depth(Nz, zc, col, cutoff)) <= 1e-12 * Lz
+            got_mean = float(og.interior(mean)[0, 0, i])
+            want_mean = ref.mixed_layer_mean(Nz, zf, float(og.interior(zmxl)[0, 0, i]), col)
+            assert abs(got_mean - want_mean) <= 1e-13 * abs(want_mean)
