@@ -265,9 +265,10 @@ struct FastSink {
     const PiscesArgs& a;
     long long idx;
     unsigned pending;
+    unsigned hold;  // 1: deliver nothing, mark everything (a cell whose NaN inputs min/max would swallow)
     __device__ __forceinline__ void put(int n, double t) {
         if (!FULL && !((a.out_mask >> n) & 1u)) return;
-        const unsigned nf = nonfinite(t);
+        const unsigned nf = nonfinite(t) | hold;
         pending |= nf << n;
         if (!nf) {
             if (ACC) red_add(a.g[n] + idx, t);
@@ -525,11 +526,17 @@ __device__ __forceinline__ void cell_tendencies(const PiscesArgs& a, const Input
     }
 }
 
-// NaN inputs that only flow through min/max would be swallowed by the FAST pass's fmin/fmax: such cells go
-// straight to the EXACT pass
+// A NaN that only flows through min/max would be swallowed by the FAST pass's selects — an input NaN directly, an
+// input ±Inf through Inf − Inf or Inf / Inf on the way: a cell with ANY non-finite input goes straight to the EXACT
+// pass.  Integer test on the high words (exponent all ones), min-reduced: ≈ 70 ALU-pipe instructions per cell.
 __device__ __forceinline__ bool needs_exact(const Inputs& in) {
-    const Cell& c = in.c;
-    return (c.zeu != c.zeu) | (c.O2 != c.O2) | (in.Omega != in.Omega) | (c.zmxl != c.zmxl) | (c.kappa != c.kappa);
+    static_assert(sizeof(Inputs) % sizeof(double) == 0, "Inputs is all doubles");
+    const double* v = reinterpret_cast<const double*>(&in);
+    unsigned gap = 0x7ff00000u;
+#pragma unroll
+    for (int n = 0; n < (int)(sizeof(Inputs) / sizeof(double)); n++)
+        gap = min(gap, ~(unsigned)__double2hiint(v[n]) & 0x7ff00000u);  // 0 ⇔ NaN or ±Inf
+    return gap == 0u;
 }
 
 
@@ -593,9 +600,11 @@ __global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__
     // ---- one coalesced read of the cell ------------------------------------------------------------
     const Inputs in = load_inputs(a, idx, pl, k);
 
-    FastSink<ACC, FULL> sink{a, idx, 0u};
-    if (needs_exact(in)) sink.pending = a.out_mask;
-    else cell_tendencies<false>(a, in, sink);
+    // The NaN-input guard is a data dependency of the stores, not a branch ahead of the arithmetic: a branch on
+    // loaded values here made the compiler sink two thirds of the input loads below it, i.e. two DRAM round trips
+    // per cell instead of one (profiles/r02_pisces_tendency_hot_lines.txt: 24 % of the samples on three waits).
+    FastSink<ACC, FULL> sink{a, idx, 0u, needs_exact(in) ? 1u : 0u};
+    cell_tendencies<false>(a, in, sink);
     if (sink.pending) cell_exact(a, idx, pl, k, sink.pending);  // rare: non-finite results, NaN inputs
 }
 

@@ -74,6 +74,52 @@ def test_fused_tendencies_match_oracle(cuda, oracle, size, t):
     assert np.all(full == 3.0)
 
 
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_nan_inputs_propagate_like_the_reference(cuda, oracle, accumulate):
+    """NaN in an input that the fast path's select-based min / max could swallow (O₂, Ω, zₘₓₗ, zₑᵤ, κ̄: the
+    `needs_exact` guard) or that makes a result non-finite (a tracer, PAR): every tendency of such a cell comes from
+    the exact pass, NaN exactly where the reference's NaN-propagating `min` / `max` put them, and — accumulate mode —
+    nothing is added twice.  All other cells are untouched by the detour."""
+    grid, bgc, model = build(cuda, (24, 6, 10), (1e4, 1e3, 300.0))
+    u = bgc.underlying_biogeochemistry
+    fill(model, bgc)
+    model.update_state()
+    aux_dev = bgc.biogeochemical_auxiliary_fields()
+    nan = float("nan")
+    model.tracers["O₂"].interior[3, 1, 2] = nan
+    aux_dev["Ω"].interior[4, 2, 5] = nan
+    aux_dev["zₘₓₗ"].interior[0, 3, 7] = nan          # a whole column
+    aux_dev["zₑᵤ"].interior[0, 4, 9] = nan
+    aux_dev["κ"].interior[0, 5, 11] = nan
+    model.tracers["P"].interior[6, 0, 13] = nan
+    model.tracers["Fe"].interior[7, 1, 15] = float("inf")
+    aux_dev["PAR₂"].interior[8, 2, 17] = nan
+    model.tracers["T"].interior[2, 3, 19] = nan
+    og = oracle.Grid.like(grid)
+    host = {n: np.ascontiguousarray(f.data.cpu().numpy()) for n, f in model.tracers.items()}
+    aux = host_aux(og, grid, bgc)
+    g0 = 1e-7 if accumulate else 3.0
+    G = {n: ob.CenterField(grid, fill=g0) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, aux_dev, G, accumulate=accumulate, time=0.0)
+    torch.cuda.synchronize()
+    Go = oracle.pisces_tendencies(og, u.c_params(0.0), [host[n] for n in pisces.TRACERS], aux,
+                                  G=[np.full(og.parent_shape, g0) if n < 24 else None for n in range(26)] if accumulate else None,
+                                  accumulate=accumulate)
+    want = {n: og.interior(g) for n, g in zip(pisces.TRACERS, Go) if g is not None}
+    got = {n: og.interior(G[n].data.cpu().numpy()) for n in want}
+    off = g0 if accumulate else 0.0
+    S = np.maximum.reduce([np.nan_to_num(np.abs(want[n] - off), nan=0.0, posinf=0.0) for n in want]) + off
+    poisoned = 0
+    for n in want:
+        bad_w, bad_g = ~np.isfinite(want[n]), ~np.isfinite(got[n])
+        assert np.array_equal(np.isnan(want[n]), np.isnan(got[n])), n
+        assert np.array_equal(bad_w, bad_g) and np.array_equal(want[n][bad_w & ~np.isnan(want[n])], got[n][bad_g & ~np.isnan(got[n])]), n
+        ok = ~bad_w
+        assert np.max(np.abs(got[n][ok] - want[n][ok]) / S[ok]) <= RTOL_TENDENCY, n
+        poisoned += int(bad_w.sum())
+    assert poisoned >= 9 * 3  # every injected NaN reaches several tendencies
+
+
 def test_accumulate_into_existing_tendencies(cuda, oracle):
     grid, bgc, model = build(cuda, (20, 5, 12), (1e4, 1e3, 300.0))
     u = bgc.underlying_biogeochemistry
