@@ -288,10 +288,25 @@ def pisces_tendencies(grid: Grid, params, tracers, aux: dict, G=None, accumulate
     return G
 
 
-def pisces_point(params, values, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z):
+_select_lib = None
+
+
+def select_lib():
+    """The same oracle built with -DORC_SELECT_MINMAX: Julia's NaN-propagating min / max replaced by compare + select,
+    i.e. the arithmetic of the kernels' fast pass (used to show where that pass could swallow a NaN)."""
+    global _select_lib
+    if _select_lib is None:
+        path = os.path.join(_HERE, "_build", "liboracle_select.so")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(LIB_PATH):
+            subprocess.run(["make", "-C", _HERE, "all"], check=True, stdout=subprocess.DEVNULL)
+        _select_lib = C.CDLL(path)
+    return _select_lib
+
+
+def pisces_point(params, values, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z, select=False):
     vals = (C.c_double * abi.OBM_PISCES_NTRACERS)(*values)
     out = (C.c_double * abi.OBM_PISCES_NTRACERS)()
-    fn = lib().orc_pisces_point
+    fn = (select_lib() if select else lib()).orc_pisces_point
     fn.restype = None
     fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 12 + [C.c_void_p]
     fn(C.byref(params), vals, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z, out)

@@ -25,11 +25,15 @@
 
 /* Julia `max`/`min` propagate NaN; C fmax/fmin do not. */
 static inline double jl_max(double a, double b) {
+#ifndef ORC_SELECT_MINMAX /* defined only for _build/liboracle_select.so: compare + select, what the kernels' fast pass does */
     if (isnan(a) || isnan(b)) return NAN;
+#endif
     return a > b ? a : b;
 }
 static inline double jl_min(double a, double b) {
+#ifndef ORC_SELECT_MINMAX
     if (isnan(a) || isnan(b)) return NAN;
+#endif
     return a < b ? a : b;
 }
 /* Julia `eps(x)` = ulp(x): 5e-324 at 0, NaN at NaN/Inf. */

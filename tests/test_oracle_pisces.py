@@ -139,3 +139,76 @@ def test_c_oracle_matches_independent_restatement(oracle, row):
     for n, v in want.items():
         scale = max(abs(v), 1e-3 * carbon if n not in ("PChl", "DChl", "PFe", "DFe", "SFe", "BFe", "Fe") else 0.0)
         assert abs(G[n] - v) <= 1e-13 * max(scale, 1e-300) + 1e-30, (row, n, G[n], v)
+
+
+# ---- what the kernels' fast pass may and may not do with min / max --------------------------------------------------
+
+def _random_point(rng, extreme):
+    """A state with finite inputs: ordinary (factor e^{±2} around the reference test's state) or extreme (zeros,
+    denormals, huge values — what a blown-up simulation hands over just before it produces its first NaN; the four
+    plankton biomasses are 0 or ≥ 1e-30, see the next test but one for why)."""
+    if not extreme:
+        vals = {n: v * math.exp(rng.uniform(-2, 2)) for n, v in pisces.PISCES_INITIAL_VALUES.items()}
+        vals["T"], vals["S"] = rng.uniform(-2, 32), rng.uniform(20, 40)
+    else:
+        pick = lambda: rng.choice([0.0, 5e-324, 1e-300, 1e-30, 1e-6, 1.0, 1e6, 1e30, 1e150])  # noqa: E731
+        vals = {n: pick() for n in pisces.PISCES_INITIAL_VALUES}
+        for biomass in ("P", "D", "Z", "M"):
+            vals[biomass] = rng.choice([0.0, 1e-30, 1e-6, 1.0, 1e6])
+        vals["T"], vals["S"] = rng.choice([-2.0, 0.0, 40.0, 1e3]), rng.choice([0.0, 35.0, 1e3])
+    aux = [rng.uniform(0, 80), rng.uniform(0, 80), rng.uniform(0, 80), 0.0, rng.choice([0.0, 0.5, 1.0, 3.0, 1e6]),
+           -rng.choice([0.0, 2.0, 50.0]) / 86400, -rng.choice([1e-9, 30.0, 200.0]) / 86400, -rng.uniform(1, 300),
+           -rng.uniform(1, 300), rng.choice([1e-12, 1e-4, 1.0, 1e6]), rng.uniform(0, 300), -rng.uniform(0.5, 400)]
+    aux[3] = aux[0] + aux[1] + aux[2]
+    return vals, aux
+
+
+def _lost_nans(oracle, box, vals, aux, t):
+    """Tendencies that are finite under select semantics but differ from the reference's (NaN there)."""
+    p = box.c_params(t)
+    v = [vals.get(n, 0.0) for n in pisces.TRACERS]
+    exact = oracle.pisces_point(p, v, *aux)
+    fast = oracle.pisces_point(p, v, *aux, select=True)
+    return [pisces.TRACERS[n] for n in range(24) if math.isfinite(fast[n]) and not (exact[n] == fast[n])]
+
+
+@pytest.mark.parametrize("extreme", [False, True])
+def test_select_min_max_equals_propagating_min_max_for_finite_inputs(oracle, box, extreme):
+    """The kernels' fast pass takes min / max by compare + select, which swallows a NaN operand; cells with a non-finite
+    INPUT are routed to the exact pass.  What remains to show is that no NaN is born mid-way from finite inputs and then
+    meets ONLY selects.  The oracle rebuilt with select semantics (-DORC_SELECT_MINMAX) is the fast pass's arithmetic:
+    over ordinary and extreme finite states, wherever its result is finite it is the reference's bit for bit — a
+    non-finite result is recomputed by the exact pass anyway."""
+    rng = np.random.default_rng(20261017 + extreme)
+    for _ in range(1500):
+        vals, aux = _random_point(rng, extreme)
+        lost = _lost_nans(oracle, box, vals, aux, rng.uniform(0, 3e7))
+        assert not lost, (lost, vals, aux)
+
+
+def test_known_limit_of_the_fast_pass_quota_overflow(oracle, box):
+    """Where the statement above stops: a POSITIVE plankton biomass below ≈ 1e-290 carrying ordinary pigment makes the
+    chlorophyll quota θ = Chl / (12 I + eps(0)) overflow to Inf; Inf · 0 is then a NaN born mid-way, which the reference's
+    `min` / `max` propagate into a dozen tendencies and a select drops.  Exactly zero biomass is guarded (in the reference
+    too), so this needs a concentration no simulation reaches with its pigment intact; recorded here so that the parity
+    claim in DESIGN.md §3.1 is stated with its edge."""
+    vals = dict(pisces.PISCES_INITIAL_VALUES)
+    vals["D"] = 5e-324
+    aux = [30.0, 30.0, 30.0, 90.0, 0.8, -2 / 86400, -30 / 86400, -50.0, -80.0, 1e-3, 40.0, -20.0]
+    assert "D" in _lost_nans(oracle, box, vals, aux, 1e6)
+    vals["D"] = 0.0  # the guarded case: nothing is lost
+    assert not _lost_nans(oracle, box, vals, aux, 1e6)
+
+
+def test_select_min_max_swallows_what_the_input_guard_catches(oracle, box):
+    """The counter-example that motivates the guard over ALL inputs: Fe = +Inf gives Inf / Inf = NaN inside a min, which a
+    select drops — three tendencies come out finite where the reference has NaN."""
+    vals = dict(pisces.PISCES_INITIAL_VALUES)
+    vals["Fe"] = math.inf
+    v = [vals.get(n, 0.0) for n in pisces.TRACERS]
+    aux = [30.0, 30.0, 30.0, 90.0, 0.8, -2 / 86400, -30 / 86400, -50.0, -80.0, 1e-3, 40.0, -20.0]
+    p = box.c_params(1e6)
+    exact = oracle.pisces_point(p, v, *aux)
+    fast = oracle.pisces_point(p, v, *aux, select=True)
+    lost = [pisces.TRACERS[n] for n in range(24) if math.isnan(exact[n]) and math.isfinite(fast[n])]
+    assert lost, "expected the select arithmetic to lose NaNs for an infinite input"
