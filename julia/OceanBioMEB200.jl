@@ -128,4 +128,79 @@ end
 # Column / box models without resolved flow: `obm_sinking_tendencies(g, n, tracers, w_faces, Gⁿ, scheme, 1, s)` adds
 # −∂z(w c) of every sinking tracer (w = biogeochemical_drift_velocity(bgc, Val(c)).w) in one launch.
 
+# ---- raw bindings of the remaining entry points (include/obm_b200.h), one thin method each ---------------------------
+# Device arrays are passed as CuPtr{Float64} (`pointer(parent(field))`), tables of them as host Vector{CuPtr{Float64}},
+# parameter blocks by Ref; `s` is `CUDA.stream().handle`.  tests/test_abi.py checks every signature's arity against the header.
+const F64 = CuPtr{Float64}
+
+par_multiband!(g, p, chl_a, chl_b, chl_scale, surface_xy, surface_const, bands, total, s) =
+    check(ccall((:obm_par_multiband, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmMultibandParams}, F64, F64, Cdouble, F64, Cdouble, Ptr{F64}, F64, Ptr{Cvoid}),
+                g, p, chl_a, chl_b, chl_scale, surface_xy, surface_const, bands, total, s), "obm_par_multiband")
+
+# PISCES: the PAR scan that also leaves zₑᵤ and the mixed-layer mean PAR (replaces three of the reference's launches)
+par_multiband_column_state!(g, p, chl_a, chl_b, chl_scale, surface_xy, surface_const, bands, total, zmxl, cutoff, zeu, mean_par, s) =
+    check(ccall((:obm_par_multiband_column_state, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmMultibandParams}, F64, F64, Cdouble, F64, Cdouble, Ptr{F64}, F64, F64, Cdouble, F64, F64, Ptr{Cvoid}),
+                g, p, chl_a, chl_b, chl_scale, surface_xy, surface_const, bands, total, zmxl, cutoff, zeu, mean_par, s),
+          "obm_par_multiband_column_state")
+
+sediment_update_state!(g, p, f, Δt, χ, s) =
+    check(ccall((:obm_sediment_update_state, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmSedimentParams}, Ref{ObmSedimentFields}, Cdouble, Cdouble, Ptr{Cvoid}), g, p, f, Δt, χ, s),
+          "obm_sediment_update_state")
+
+sediment_update_tendencies!(g, p, f, s) =
+    check(ccall((:obm_sediment_update_tendencies, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmSedimentParams}, Ref{ObmSedimentFields}, Ptr{Cvoid}), g, p, f, s),
+          "obm_sediment_update_tendencies")
+
+find_bottom_cells!(g, bottom_height_xy, bottom_indices_xy::CuPtr{Int64}, s) =
+    check(ccall((:obm_find_bottom_cells, libobm), Cint, (Ref{ObmGrid}, F64, CuPtr{Int64}, Ptr{Cvoid}),
+                g, bottom_height_xy, bottom_indices_xy, s), "obm_find_bottom_cells")
+
+# gas exchange: the flux field a FluxBoundaryCondition then reads; DIC / Alk only for CO₂, silicate / phosphate optional
+gas_exchange_flux!(g, p, T, S, tracer, DIC, Alk, silicate, phosphate, wind_xy, air_xy, flux_xy, G_top, s) =
+    check(ccall((:obm_gas_exchange_flux, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmGasExchangeParams}, F64, F64, F64, F64, F64, F64, F64, F64, F64, F64, F64, Ptr{Cvoid}),
+                g, p, T, S, tracer, DIC, Alk, silicate, phosphate, wind_xy, air_xy, flux_xy, G_top, s), "obm_gas_exchange_flux")
+
+kelp_update_tendencies!(g, p, particles, tracers, G, t, s) =
+    check(ccall((:obm_kelp_update_tendencies, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmSugarKelpParams}, Ref{ObmParticles}, Ref{ObmKelpTracers}, Ptr{F64}, Cdouble, Ptr{Cvoid}),
+                g, p, particles, tracers, G, t, s), "obm_kelp_update_tendencies")
+
+kelp_step!(g, p, particles, tracers, t, Δt, tendencies_out, s) =
+    check(ccall((:obm_kelp_step, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmSugarKelpParams}, Ref{ObmParticles}, Ref{ObmKelpTracers}, Cdouble, Cdouble, Ptr{F64}, Ptr{Cvoid}),
+                g, p, particles, tracers, t, Δt, tendencies_out, s), "obm_kelp_step")
+
+sinking_tendencies!(g, tracers, w_faces, G, advection, accumulate, s) =
+    check(ccall((:obm_sinking_tendencies, libobm), Cint,
+                (Ref{ObmGrid}, Cint, Ptr{F64}, Ptr{F64}, Ptr{F64}, Cint, Cint, Ptr{Cvoid}),
+                g, length(tracers), tracers, w_faces, G, advection, accumulate, s), "obm_sinking_tendencies")
+
+# box / column models: U += Δt (γ Gⁿ + ζ G⁻) and G⁻ ← Gⁿ for every field in one launch (src/BoxModel/timesteppers.jl:66-93)
+rk3_substep!(g, U, Gⁿ, G⁻, Δt, γ, ζ, has_ζ, cache_previous, s) =
+    check(ccall((:obm_rk3_substep, libobm), Cint,
+                (Ref{ObmGrid}, Cint, Ptr{F64}, Ptr{F64}, Ptr{F64}, Cdouble, Cdouble, Cdouble, Cint, Cint, Ptr{Cvoid}),
+                g, length(U), U, Gⁿ, G⁻, Δt, γ, ζ, has_ζ, cache_previous, s), "obm_rk3_substep")
+
+# CarbonChemistry()(; DIC, Alk, T, S, …) over flat device arrays (src/Models/CarbonChemistry/carbon_chemistry.jl:84-181)
+carbon_chemistry!(out, p, T, S, DIC, Alk, P_bar, silicate, phosphate, pH, output_kind, n, s) =
+    check(ccall((:obm_carbon_chemistry, libobm), Cint,
+                (Int64, Ref{ObmCarbchemParams}, F64, F64, F64, F64, F64, F64, F64, F64, Cint, F64, Ptr{Cvoid}),
+                n, p, T, S, DIC, Alk, P_bar, silicate, phosphate, pH, output_kind, out, s), "obm_carbon_chemistry")
+
+zero_negative_tracers!(n_parent, tracers, s) =
+    check(ccall((:obm_zero_negative_tracers, libobm), Cint, (Int64, Cint, Ptr{F64}, Ptr{Cvoid}),
+                n_parent, length(tracers), tracers, s), "obm_zero_negative_tracers")
+
+# conservation diagnostics: Σ sf·c·V per conserved group on this GPU; follow with an all-reduce over the ranks
+inventory!(out, g, tracers, groups, cell_volume, uniform_volume, workspace, s) =
+    check(ccall((:obm_inventory, libobm), Cint,
+                (Ref{ObmGrid}, Cint, Ptr{F64}, Cint, Ptr{ObmScaleGroup}, F64, Cdouble, F64, CuPtr{Cvoid}, Ptr{Cvoid}),
+                g, length(tracers), tracers, length(groups), groups, cell_volume, uniform_volume, out, workspace, s),
+          "obm_inventory")
+
 end # module

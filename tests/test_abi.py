@@ -102,3 +102,25 @@ def test_npd_parameter_index_space_matches_the_library():
         assert lib.obm_npd_param_index(n.encode()) == ob.NutrientsPlanktonDetritus.parameter_index(n)
     assert lib.obm_npd_param_index(b"nutrients") == -3  # structural members cannot vary per member
     assert lib.obm_npd_param_index(b"bogus") == -3
+
+
+def test_julia_ccall_signatures_have_the_prototypes_arity():
+    """julia/OceanBioMEB200.jl cannot run here (no Julia in the image): at least every `ccall((:name, libobm), Cint,
+    (types…), …)` in it — commented sketches included — names an exported symbol and lists as many argument types as the
+    C prototype has parameters."""
+    src = open(os.path.join(os.path.dirname(__file__), "..", "julia", "OceanBioMEB200.jl"), encoding="utf-8").read()
+    src = "\n".join(line.lstrip().lstrip("#") for line in src.splitlines())  # the commented call sketches count too
+    calls = re.findall(r"ccall\(\(:(\w+),\s*libobm\),\s*(\w+),\s*\(([^()]*)\)", src, flags=re.S)
+    assert len(calls) >= 8
+    for name, ret, types in calls:
+        assert name in _lib.PROTOTYPES, name
+        n = len([t for t in types.split(",") if t.strip()])
+        assert n == len(_lib.PROTOTYPES[name][1]), f"{name}: Julia lists {n} argument types, the C prototype has {len(_lib.PROTOTYPES[name][1])}"
+        assert ret == {C.c_int: "Cint", C.c_char_p: "Cstring", C.c_double: "Cdouble"}.get(_lib.PROTOTYPES[name][0], ret), name
+        # scalars where C has scalars, pointers where C has pointers
+        for pos, (jt, ct) in enumerate(zip([t.strip() for t in types.split(",") if t.strip()], _lib.PROTOTYPES[name][1])):
+            scalar = {C.c_double: "Cdouble", C.c_int: "Cint", C.c_int64: "Int64", C.c_longlong: "Int64"}.get(ct)
+            if scalar is not None:
+                assert jt == scalar, f"{name} argument {pos}: Julia {jt}, C {ct.__name__}"
+            else:
+                assert any(k in jt for k in ("Ptr", "Ref", "F64", "Cstring")), f"{name} argument {pos}: Julia {jt} for a C pointer"
