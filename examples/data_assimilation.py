@@ -30,7 +30,8 @@ def PAR_func(t):  # data_assimilation.jl:22-25
 
 
 def phytozoo_parameters(u):
-    """(α, μ₀, k_N, m_P), one column per member → the PhytoZoo keywords `run_box_simulation` sets (:39-43)."""
+    """(α, μ₀, k_N, m_P), one column per member → the PhytoZoo keywords `run_box_simulation` sets (:39-43), written as
+    they are there (m_P, a rate per second, is divided by `day` once more in the mortality rate)."""
     alpha, mu, kN, mP = u
     return {"phytoplankton_maximum_growth_rate": mu, "nitrate_half_saturation": kN, "light_half_saturation": mu / alpha,
             "phytoplankton_mortality_rate": 0.066 / day + mP / day,
