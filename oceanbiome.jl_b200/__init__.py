@@ -6,7 +6,7 @@ There is no CPU fallback: compute entry points raise if the CUDA library or a CU
 """
 from . import _lib
 from ._lib import ObmError, load as load_library
-from .grids import CenterField, ConstantField, Field, Field2D, RectilinearGrid, ZFaceField
+from .grids import CenterField, ConstantField, Field, Field2D, LatitudeLongitudeGrid, RectilinearGrid, ZFaceField
 from .light import (MultiBandPhotosyntheticallyActiveRadiation, PrescribedPhotosyntheticallyActiveRadiation,
                     TwoBandPhotosyntheticallyActiveRadiation, compute_euphotic_depth, compute_mixed_layer_mean,
                     default_surface_PAR)

@@ -144,7 +144,7 @@ class RectilinearGrid:
             raise ValueError(f"Ny = {self.Ny} is not divisible by {world} ranks")
         ny = self.Ny // world
         y0 = (self.y[0] if self.y is not None else 0.0) + rank * ny * self.dy
-        g = RectilinearGrid.__new__(RectilinearGrid)
+        g = type(self).__new__(type(self))
         g.__dict__.update(self.__dict__)
         g.Ny = ny
         g.y = (y0, y0 + ny * self.dy)
@@ -154,6 +154,41 @@ class RectilinearGrid:
     def __repr__(self):
         return (f"RectilinearGrid(size=({self.Nx}, {self.Ny}, {self.Nz}), halo=({self.Hx}, {self.Hy}, {self.Hz}), "
                 f"topology={self.topology}, device={self.device})")
+
+
+class LatitudeLongitudeGrid(RectilinearGrid):
+    """`LatitudeLongitudeGrid(size = (Nλ, Nφ, Nz), longitude = (λ₀, λ₁), latitude = (φ₀, φ₁), z = …)` in degrees — the
+    second grid of the reference's light tests (test/test_light.jl:113-114).  Every hot kernel is pointwise or local to
+    one column, so on the device this is the same arrays and the same launches as a `RectilinearGrid` of that size;
+    what the sphere changes is host-side: cell areas (tracer inventories) and the latitude of each row of columns."""
+
+    def __init__(self, size, longitude, latitude, z, topology=("Periodic", "Bounded", "Bounded"), halo=None,
+                 radius: float = 6371e3, device="cuda"):
+        if not (-90.0 <= latitude[0] < latitude[1] <= 90.0):
+            raise ValueError("latitude must satisfy −90 ≤ φ₀ < φ₁ ≤ 90")
+        super().__init__(size, x=tuple(longitude), y=tuple(latitude), z=z, topology=topology, halo=halo, device=device)
+        self.radius = float(radius)
+
+    @property
+    def latitude_faces(self):
+        return self.y[0] + self.dy * np.arange(self.Ny + 1)
+
+    @property
+    def latitude_centers(self):
+        return self.y[0] + self.dy * (np.arange(self.Ny) + 0.5)
+
+    def cell_area(self) -> np.ndarray:
+        """Area of the cells of each latitude row, R² Δλ (sin φⱼ₊₁ − sin φⱼ), shape (Ny,)."""
+        phi = np.radians(self.latitude_faces)
+        return self.radius ** 2 * np.radians(self.dx) * np.diff(np.sin(phi))
+
+    def cell_volume(self) -> torch.Tensor:
+        v = self.dz.reshape(-1, 1, 1) * self.cell_area().reshape(1, -1, 1)
+        return torch.from_numpy(v).to(self.device)
+
+    def __repr__(self):
+        return (f"LatitudeLongitudeGrid(size=({self.Nx}, {self.Ny}, {self.Nz}), longitude={self.x}, latitude={self.y}, "
+                f"halo=({self.Hx}, {self.Hy}, {self.Hz}), device={self.device})")
 
 
 @dataclass

@@ -56,6 +56,19 @@ def test_two_band_reference_closed_form(cuda):
         np.testing.assert_allclose(got[::-1], [87.99032377900511, 70.00421099730072], rtol=1e-13)
 
 
+def test_two_band_on_the_reference_latitude_longitude_grid(cuda):
+    # test_light.jl:113-122: the same closed form on LatitudeLongitudeGrid(size = (5, 5, 2), …, z = (-2, 0)) — the scan
+    # sees sizes, halos and z only, so every column carries the rectilinear answer
+    grid = ob.LatitudeLongitudeGrid(size=(5, 5, 2), longitude=(-180, 180), latitude=(-85, 85), z=(-2, 0), device=cuda)
+    bgc = ob.NPZD(grid, light_attenuation=ob.TwoBandPhotosyntheticallyActiveRadiation(grid=grid, surface_PAR=100.0))
+    model = ob.BiogeochemicalModel(grid, bgc, extra_tracers=("T", "S"))
+    model.set(P=torch.tensor(2.5 + grid.zc).reshape(-1, 1, 1))
+    model.update_state()
+    got = model.auxiliary_fields["PAR"].interior.cpu().numpy()
+    np.testing.assert_allclose(got[::-1, 0, 0], [87.99032377900511, 70.00421099730072], rtol=1e-13)
+    assert np.all(got == got[:, :1, :1])
+
+
 @pytest.mark.parametrize("nbands", [1, 2, 3, 4])
 def test_multi_band_matches_oracle(cuda, oracle, nbands):
     grid = ob.RectilinearGrid(size=(70, 3, 45), extent=(70, 3, 400), device=cuda)

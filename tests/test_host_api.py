@@ -105,3 +105,29 @@ def test_z_faces_must_increase():
         ob.RectilinearGrid(size=(2, 2, 2), x=(0, 1), y=(0, 1), z=[-2.0, -1.0, -1.0], device="cpu")
     g = ob.RectilinearGrid(size=(2, 2, 3), x=(0, 1), y=(0, 1), z=[-3.0, -2.0, -0.5, 0.0], device="cpu")
     assert list(g.zc) == [-2.5, -1.25, -0.25]
+
+
+def test_latitude_longitude_grid_geometry():
+    import math
+    import numpy as np
+    import pytest
+    import oceanbiome_b200 as ob
+    R = 6371e3
+    g = ob.LatitudeLongitudeGrid(size=(36, 18, 2), longitude=(-180, 180), latitude=(-90, 90), z=(-2, 0), device="cpu")
+    assert (g.Nx, g.Ny, g.Nz) == (36, 18, 2) and g.topology == ("Periodic", "Bounded", "Bounded")
+    assert math.isclose(g.cell_area().sum() * g.Nx, 4 * math.pi * R ** 2, rel_tol=1e-14)
+    v = g.cell_volume()
+    assert tuple(v.shape) == (2, 18, 1) and math.isclose(float(v.sum()) * g.Nx, 4 * math.pi * R ** 2 * 2.0, rel_tol=1e-13)
+    assert np.allclose(g.latitude_centers[[0, -1]], [-85.0, 85.0])
+    # areas shrink towards the poles and are symmetric about the equator
+    a = g.cell_area()
+    assert np.allclose(a, a[::-1], rtol=1e-13) and a[0] < a[4] < a[8]
+    # slabs keep the class and their own rows; together they are the whole grid
+    parts = [g.slab(r, 2) for r in range(2)]
+    assert all(isinstance(p, ob.LatitudeLongitudeGrid) for p in parts)
+    assert np.allclose(np.concatenate([p.cell_area() for p in parts]), a, rtol=1e-13)
+    # the reference's light-test grid (test/test_light.jl:113-114) and argument checking
+    t = ob.LatitudeLongitudeGrid(size=(5, 5, 2), longitude=(-180, 180), latitude=(-85, 85), z=(-2, 0), device="cpu")
+    assert t.parent_shape == (2 + 6, 5 + 6, 5 + 6) and list(t.zc) == [-1.5, -0.5]
+    with pytest.raises(ValueError):
+        ob.LatitudeLongitudeGrid(size=(5, 5, 2), longitude=(-180, 180), latitude=(-95, 85), z=(-2, 0), device="cpu")
