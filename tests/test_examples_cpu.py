@@ -65,3 +65,18 @@ def test_parameter_mapping_of_the_example():
     import oceanbiome_b200 as ob
     for k in p:
         assert ob.NutrientsPlanktonDetritus.parameter_index(k) >= 0
+
+
+def test_box_example_builds_the_reference_setup():
+    """examples/box.py (the reference's examples/box.jl): construction, initial values and the PAR cycle; the run itself
+    is the graph-replay path of tests/test_gpu_box_model.py."""
+    spec = importlib.util.spec_from_file_location("box", os.path.join(os.path.dirname(__file__), "..", "examples", "box.py"))
+    box = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(box)
+    model = box.build(3, device="cpu")
+    assert model.prognostic == ["NO₃", "NH₄", "P", "Z", "sPOM", "bPOM", "DOM"] and model.grid.Nx == 3
+    assert model.fields["NO₃"].interior.unique().tolist() == [10.0] and model.fields["Z"].interior.unique().tolist() == [0.01]
+    # box.jl:24-28: PAR⁰ between 2 and ≈ 122 W m⁻², attenuated by exp(0.2 · (−10 m))
+    vals = [box.PAR_func(d * box.day) for d in range(0, 365, 5)]
+    assert min(vals) >= 2 * math.exp(-2) and max(vals) <= 122 * math.exp(-2) and vals.index(max(vals)) * 5 in range(140, 200)
+    assert math.isclose(box.PAR_func(0.0), box.PAR_func(box.year))  # one-year period
