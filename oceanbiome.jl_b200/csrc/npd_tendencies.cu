@@ -261,7 +261,7 @@ static int npd_layout(const obm_npd_params* p, int* roles, char (*names)[16]) {
         if (roles) roles[n] = role;
         if (names) {
             memset(names[n], 0, 16);
-            strncpy(names[n], nm, 15);
+            memcpy(names[n], nm, strnlen(nm, 15));  // ≤ 15 bytes of UTF-8, NUL-terminated by the memset
         }
         n++;
     };
