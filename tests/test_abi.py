@@ -108,7 +108,9 @@ def test_julia_ccall_signatures_have_the_prototypes_arity():
     """julia/OceanBioMEB200.jl cannot run here (no Julia in the image): at least every `ccall((:name, libobm), Cint,
     (types…), …)` in it — commented sketches included — names an exported symbol and lists as many argument types as the
     C prototype has parameters."""
-    src = open(os.path.join(os.path.dirname(__file__), "..", "julia", "OceanBioMEB200.jl"), encoding="utf-8").read()
+    root = os.path.join(os.path.dirname(__file__), "..")
+    src = open(os.path.join(root, "julia", "OceanBioMEB200.jl"), encoding="utf-8").read()
+    src += open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()  # the binding sketches shown to maintainers
     src = "\n".join(line.lstrip().lstrip("#") for line in src.splitlines())  # the commented call sketches count too
     calls = re.findall(r"ccall\(\(:(\w+),\s*libobm\),\s*(\w+),\s*\(([^()]*)\)", src, flags=re.S)
     assert len(calls) >= 8
