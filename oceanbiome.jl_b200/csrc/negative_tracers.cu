@@ -38,7 +38,7 @@ __device__ __forceinline__ void scale_cell(const ScaleArgs& a, double* mine, lon
         mine[t * SN_BLOCK] = v;
         // negative, −0.0, ±Inf or NaN ⇔ sign bit set or exponent all ones ⇔ high word ≥ 0x7ff00000 as unsigned: one
         // integer compare (the FP64 form `!(v >= 0 && v < Inf)` compiled to ≈ 14 integer instructions per value).
-        // −0.0 is flagged too; such a cell then finds p == t in every group below and is left as it is.
+        // −0.0 is flagged too; its group then runs with t / p = 1 and writes +0.0, as the reference's `ifelse(…, 0)` does.
         touched |= (unsigned)__double2hiint(v) >= 0x7ff00000u;
     }
     if (!__any_sync(__activemask(), touched)) return;  // warp-uniform: the common case reads its cells and leaves
@@ -47,16 +47,20 @@ __device__ __forceinline__ void scale_cell(const ScaleArgs& a, double* mine, lon
         const obm_scale_group& g = a.groups[q];
         double t = 0.0, p = 0.0;
         unsigned members = 0;
+        bool bad = false;  // some member is negative (−0.0 included) or non-finite
         for (int m = 0; m < g.n; m++) {  // negative_tracers.jl:256-264 (same operation order, no FMA contraction)
             const double v = mine[g.index[m] * SN_BLOCK];
             const double s = __dmul_rn(v, g.scalefactor[m]);
             t = __dadd_rn(t, s);
             if (v > 0) p = __dadd_rn(p, s);
+            bad |= (unsigned)__double2hiint(v) >= 0x7ff00000u;
             members |= 1u << g.index[m];
         }
-        // No negative and no non-finite member ⇔ p == t (bitwise: identical operation sequence) and t finite: the
-        // reference would multiply every member by t/p = 1 (up to 1 ulp of (v·t)/t rounding noise) — leave the cell alone.
-        if (p == t && isfinite(t)) continue;
+        // No negative and no non-finite member: the reference would multiply every member by t/p = 1 (up to 1 ulp of
+        // (v·t)/t rounding noise) — leave the cell alone.  The decision is taken from the members themselves, not from
+        // p == t: a negative member far below the ulp of the positive sum (DIC = 2000, P = −1e-14) is absorbed by the
+        // rounding of t, yet the reference still zeroes it (:268-274).
+        if (!bad) continue;
         t = t < 0 ? a.fill : t;             // :266
         const double ratio = __ddiv_rn(t, p);  // one division per group; v·t/p ≡ v·(t/p) to ≤ 1 ulp
         for (int m = 0; m < g.n; m++) {     // :268-274

@@ -138,7 +138,10 @@ __device__ __forceinline__ Phyto phytoplankton(const PiscesArgs& a, const int cl
     const double KSi = Ksi + a.dv.KSi_add[cls];
     double LSi = A::div(c.Si, c.Si + KSi);
     LSi = ph.silicate_limited ? LSi : __longlong_as_double(0x7ff0000000000000LL);
-    r.L = A::mn4(r.LN, r.LPO4, r.LFe, LSi);
+    // min(L_N, L_PO₄, L_Fe, L_Si) nutrient_limitation.jl:69.  FAST: a select propagates a NaN in its SECOND operand only, and
+    // L_Fe is the one limitation a finite state can turn into NaN (a positive biomass far below its pigment makes both
+    // quotas overflow: Inf − Inf) — it goes last, so that such a cell reaches the exact pass through a non-finite result.
+    r.L = A::EX ? A::mn4(r.LN, r.LPO4, r.LFe, LSi) : A::mn4(LSi, r.LN, r.LPO4, r.LFe);
 
     // growth rate (μ::BaseProduction)(…, L) with the SWAPPED day length — growth_rate.jl:3-47
     const double PAR = ph.blue_light_absorption * c.PAR1 + ph.green_light_absorption * c.PAR2 + ph.red_light_absorption * c.PAR3;

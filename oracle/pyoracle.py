@@ -143,6 +143,16 @@ def npd_tendencies(grid: Grid, params, tracers, PAR, G=None, accumulate=False):
     return G
 
 
+def npd_tendency_scales(grid: Grid, params, tracers, PAR):
+    """Σ|additive terms| of every tendency — the S of the parity metric |a − b| ≤ 1e-12·max(|b|, S)."""
+    _check(list(tracers) + [PAR])
+    S = [np.zeros(grid.parent_shape) for _ in tracers]
+    cg = grid.c_grid()
+    rc = lib().orc_npd_tendency_scales(C.byref(cg), C.byref(params), _table(tracers), C.c_void_p(_ptr(PAR)), _table(S))
+    assert rc == 0, f"orc_npd_tendency_scales → {rc}"
+    return S
+
+
 # ---- light ------------------------------------------------------------------------------------------
 def par_twoband(grid: Grid, params, P, surface_PAR, PAR=None):
     PAR = np.zeros(grid.parent_shape) if PAR is None else PAR
@@ -288,6 +298,17 @@ def pisces_tendencies(grid: Grid, params, tracers, aux: dict, G=None, accumulate
     return G
 
 
+def pisces_tendency_scales(grid: Grid, params, tracers, aux: dict):
+    """Σ|additive terms| of each of the 24 tendencies — the S of the parity metric."""
+    _check(tracers)
+    S = [np.zeros(grid.parent_shape) if n < 24 else None for n in range(abi.OBM_PISCES_NTRACERS)]
+    f = pisces_fields(aux)
+    cg = grid.c_grid()
+    rc = lib().orc_pisces_tendency_scales(C.byref(cg), C.byref(params), _table(tracers), C.byref(f), _table(S))
+    assert rc == 0, f"orc_pisces_tendency_scales → {rc}"
+    return S
+
+
 _select_lib = None
 
 
@@ -311,6 +332,18 @@ def pisces_point(params, values, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl,
     fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 12 + [C.c_void_p]
     fn(C.byref(params), vals, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z, out)
     return list(out)
+
+
+def pisces_point_terms(params, values, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z):
+    """(tendencies, Σ|terms| per tendency) of one point."""
+    vals = (C.c_double * abi.OBM_PISCES_NTRACERS)(*values)
+    out = (C.c_double * abi.OBM_PISCES_NTRACERS)()
+    sc = (C.c_double * abi.OBM_PISCES_NTRACERS)()
+    fn = lib().orc_pisces_point_terms
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_void_p] + [C.c_double] * 12 + [C.c_void_p, C.c_void_p]
+    fn(C.byref(params), vals, PAR1, PAR2, PAR3, PAR, Omega, wPOC, wGOC, zmxl, zeu, kappa, mlPAR, z, out, sc)
+    return list(out), list(sc)
 
 
 def cbm_day_length(t, phi):

@@ -62,4 +62,17 @@ static inline void grid_range(const obm_grid* g, int* i0, int* i1, int* j0, int*
     *j1 = g->j1 > 0 ? g->j1 : g->Ny;
 }
 
+/* Parity metric scale: S = Σ |additive terms| of the tendency this thread evaluated last.  Every per-tracer
+ * callable of oracle_pisces.c / oracle_npd.c records it next to its return statement through ORC_TERMS (the return
+ * expression itself is untouched: same operations, same order).  A term that is itself a difference of fluxes
+ * contributes its own Σ|terms| (read back from orc_term_scale right after the call). */
+extern __thread double orc_term_scale;
+static inline double orc_abs_sum(const double* v, int n) {
+    double s = 0;
+    for (int i = 0; i < n; i++) s += fabs(v[i]);
+    return s;
+}
+#define ORC_TERMS(...) \
+    (orc_term_scale = orc_abs_sum((const double[]){__VA_ARGS__}, (int)(sizeof((const double[]){__VA_ARGS__}) / sizeof(double))))
+
 #endif

@@ -183,6 +183,7 @@ static double nutrient_uptake_NH4(P_ p, C_ c) {
     double nl = NO3 * exp(-p->nitrate_ammonia_inhibition * NH4) / (NO3 + p->nitrate_half_saturation);
     double al = jl_max(0.0, NH4 / (p->ammonia_half_saturation + NH4));
     double waste = alpha * gamma * mu;
+    ORC_TERMS(mu * al / (nl + al + EPS0), waste);
     return mu * al / (nl + al + EPS0) - waste;
 }
 static double nutrient_uptake_Fe(P_ p, C_ c) { return p->iron_ratio * phytoplankton_growth(p, c); }
@@ -334,17 +335,32 @@ static int has_NA(P_ p) { return p->nutrients != OBM_NUT_NUTRIENT; }
  * (NutrientsPlanktonDetritus.jl:88). */
 static double tendency(P_ p, C_ c, int role) {
     switch (role) {
-        case R_FE: /* nutrients.jl:22-23 */
-            return p->nutrients == OBM_NUT_NITRATE_AMMONIA_IRON ? -nutrient_uptake_Fe(p, c) : 0.0;
+        case R_FE: { /* nutrients.jl:22-23 */
+            double t = p->nutrients == OBM_NUT_NITRATE_AMMONIA_IRON ? -nutrient_uptake_Fe(p, c) : 0.0;
+            ORC_TERMS(t);
+            return t;
+        }
         case R_NO3: /* nutrients.jl:31-34 */
             if (!has_NA(p)) return 0.0;
+            ORC_TERMS(nitrification(p, c), nutrient_uptake_NO3(p, c));
             return (nitrification(p, c) - nutrient_uptake_NO3(p, c));
         case R_NH4: /* nutrients.jl:36-41 */
             if (!has_NA(p)) return 0.0;
-            return (plankton_inorganic_nitrogen_waste(p, c) + detritus_inorganic_nitrogen_waste(p, c)
-                    - nitrification(p, c) - nutrient_uptake_NH4(p, c));
+            {
+                (void)nutrient_uptake_NH4(p, c);
+                double s_up = orc_term_scale; /* uptake − exuded ammonia: its own Σ|terms| */
+                ORC_TERMS(plankton_inorganic_nitrogen_waste(p, c), detritus_inorganic_nitrogen_waste(p, c), nitrification(p, c), s_up);
+            }
+            {
+                double s_all = orc_term_scale; /* the uptake call below records its own scale again */
+                double t = (plankton_inorganic_nitrogen_waste(p, c) + detritus_inorganic_nitrogen_waste(p, c)
+                            - nitrification(p, c) - nutrient_uptake_NH4(p, c));
+                orc_term_scale = s_all;
+                return t;
+            }
         case R_N: /* nutrients.jl:60-64 */
             if (has_NA(p)) return 0.0;
+            ORC_TERMS(plankton_inorganic_nitrogen_waste(p, c), detritus_inorganic_nitrogen_waste(p, c), nutrient_uptake_N(p, c));
             return (plankton_inorganic_nitrogen_waste(p, c) + detritus_inorganic_nitrogen_waste(p, c)
                     - nutrient_uptake_N(p, c));
         case R_P: { /* plankton.jl:92-105 */
@@ -353,54 +369,90 @@ static double tendency(P_ p, C_ c, int role) {
             double muP = phytoplankton_growth(p, c);
             double Gp = grazing_P(p, c);
             double nu = mortality(p->phytoplankton_mortality_formulation, P, m);
+            ORC_TERMS((1 - gamma) * muP, Gp, nu);
             return (1 - gamma) * muP - Gp - nu;
         }
         case R_Z: { /* plankton.jl:107-116 */
             double a = p->zooplankton_assimilation_fraction, m = p->zooplankton_mortality_rate, mu = p->zooplankton_excretion_rate;
             double Z = c->v[R_Z];
             double G = total_grazing(p, c);
+            ORC_TERMS(a * G, m * (Z * Z), mu * Z);
             return a * G - m * (Z * Z) - mu * Z;
         }
         case R_D: /* detritus.jl:282-288 */
             if (p->detritus != OBM_DET_DETRITUS) return 0.0;
+            ORC_TERMS(plankton_organic_nitrogen_waste(p, c), solid_waste(p, c), grazing_sPOM(p, c), p->remineralisation_rate * c->v[R_D]);
             return (plankton_organic_nitrogen_waste(p, c) + solid_waste(p, c) - grazing_sPOM(p, c)
                     - p->remineralisation_rate * c->v[R_D]);
         case R_SPOM: /* detritus.jl:149-153 */
+            ORC_TERMS(p->small_solid_waste_fraction * solid_waste(p, c), grazing_sPOM(p, c),
+                      p->small_remineralisation_rate * small_particulate_concentration(p, c));
             return (p->small_solid_waste_fraction * solid_waste(p, c) - grazing_sPOM(p, c)
                     - p->small_remineralisation_rate * small_particulate_concentration(p, c));
         case R_BPOM: /* detritus.jl:155-158 */
+            ORC_TERMS((1 - p->small_solid_waste_fraction) * solid_waste(p, c), p->large_remineralisation_rate * large_particulate_concentration(p, c));
             return ((1 - p->small_solid_waste_fraction) * solid_waste(p, c)
                     - p->large_remineralisation_rate * large_particulate_concentration(p, c));
         case R_DOM: /* detritus.jl:143-147 */
+            ORC_TERMS(plankton_organic_nitrogen_waste(p, c), detritus_organic_nitrogen_waste(p, c),
+                      p->dissolved_remineralisation_rate * dissolved_organic_nitrogen(p, c));
             return (plankton_organic_nitrogen_waste(p, c) + detritus_organic_nitrogen_waste(p, c)
                     - p->dissolved_remineralisation_rate * dissolved_organic_nitrogen(p, c));
         case R_SPOC: /* detritus.jl:85-89 */
+            ORC_TERMS(p->small_solid_waste_fraction * solid_carbon_waste(p, c), grazing_sPOC(p, c),
+                      p->small_remineralisation_rate * small_particulate_carbon_concentration(p, c));
             return (p->small_solid_waste_fraction * solid_carbon_waste(p, c) - grazing_sPOC(p, c)
                     - p->small_remineralisation_rate * small_particulate_carbon_concentration(p, c));
         case R_BPOC: /* detritus.jl:91-95 */
+            ORC_TERMS((1 - p->small_solid_waste_fraction) * solid_carbon_waste(p, c), calcite_production(p, c),
+                      p->large_remineralisation_rate * large_particulate_carbon_concentration(p, c));
             return ((1 - p->small_solid_waste_fraction) * solid_carbon_waste(p, c) + calcite_production(p, c)
                     - p->large_remineralisation_rate * large_particulate_carbon_concentration(p, c));
         case R_DOC: /* detritus.jl:97-101 */
+            ORC_TERMS(plankton_organic_carbon_waste(p, c), detritus_organic_carbon_waste(p, c),
+                      p->dissolved_remineralisation_rate * dissolved_organic_carbon(p, c));
             return (plankton_organic_carbon_waste(p, c) + detritus_organic_carbon_waste(p, c)
                     - p->dissolved_remineralisation_rate * dissolved_organic_carbon(p, c));
         case R_DIC: /* carbonate_system.jl:50-55 */
+            ORC_TERMS(phytoplankton_primary_production(p, c), plankton_inorganic_carbon_waste(p, c),
+                      detritus_inorganic_carbon_waste(p, c), calcite_dissolution(p, c));
             return (-phytoplankton_primary_production(p, c) + plankton_inorganic_carbon_waste(p, c)
                     + detritus_inorganic_carbon_waste(p, c) + calcite_dissolution(p, c));
-        case R_ALK: /* carbonate_system.jl:57-68 */
-            if (has_NA(p))
-                return (tendency(p, c, R_NH4) * (1 - 1.0 / 16) - tendency(p, c, R_NO3) * (1 + 1.0 / 16)
-                        - 2.0 * calcite_uptake(p, c) + 2.0 * calcite_dissolution(p, c));
-            return (tendency(p, c, R_N) - 2.0 * calcite_uptake(p, c) + 2.0 * calcite_dissolution(p, c));
+        case R_ALK: /* carbonate_system.jl:57-68 — a sum of tendencies: the un-cancelled scale is the sum of theirs */
+            if (has_NA(p)) {
+                (void)tendency(p, c, R_NH4);
+                double s_nh4 = orc_term_scale;
+                (void)tendency(p, c, R_NO3);
+                double s_no3 = orc_term_scale;
+                ORC_TERMS(s_nh4 * (1 - 1.0 / 16), s_no3 * (1 + 1.0 / 16), 2.0 * calcite_uptake(p, c), 2.0 * calcite_dissolution(p, c));
+            } else {
+                (void)tendency(p, c, R_N);
+                double s_n = orc_term_scale;
+                ORC_TERMS(s_n, 2.0 * calcite_uptake(p, c), 2.0 * calcite_dissolution(p, c));
+            }
+            {
+                double s_all = orc_term_scale; /* the tendency calls below record their own scales again */
+                double t;
+                if (has_NA(p))
+                    t = (tendency(p, c, R_NH4) * (1 - 1.0 / 16) - tendency(p, c, R_NO3) * (1 + 1.0 / 16)
+                         - 2.0 * calcite_uptake(p, c) + 2.0 * calcite_dissolution(p, c));
+                else
+                    t = (tendency(p, c, R_N) - 2.0 * calcite_uptake(p, c) + 2.0 * calcite_dissolution(p, c));
+                orc_term_scale = s_all;
+                return t;
+            }
         case R_O2: { /* oxygen.jl:21-31.  The `<:Nutrient` specialisation :33-43 dispatches on the
                         PLANKTON slot and is unreachable (SURVEY App. A bug 2), so Nutrient models use
                         the generic method with bgc(Val(:NH₄)) = 0 and nitrification = 0. */
             double Rp = p->respiration_oxygen_nitrogen_ratio, Rn = p->nitrification_oxygen_nitrogen_ratio;
             double muP = phytoplankton_growth(p, c);
             double nitrate_production = tendency(p, c, R_NH4);
+            double s_nh4 = has_NA(p) ? orc_term_scale : 0.0;
             double muNH4 = nitrification(p, c);
+            ORC_TERMS(Rp * muP, (Rp - Rn) * s_nh4, Rp * muNH4);
             return Rp * muP - (Rp - Rn) * nitrate_production - Rp * muNH4;
         }
-        default: return 0.0; /* T etc.: zero(grid) */
+        default: orc_term_scale = 0.0; return 0.0; /* T etc.: zero(grid) */
     }
 }
 
@@ -432,6 +484,31 @@ int orc_npd_tendency(const obm_grid* g, const obm_npd_params* p, const double* c
                 double t = tendency(p, &c, role);
                 int64_t idx = cell_index(g, i, j, k);
                 if (accumulate) G[idx] += t; else G[idx] = t;
+            }
+    return 0;
+}
+
+/* Σ|additive terms| of every tendency (the parity metric's S): S[n] parent arrays in layout order, NULL skips */
+int orc_npd_tendency_scales(const obm_grid* g, const obm_npd_params* p, const double* const* tracers, const double* PAR,
+                            double* const* S) {
+    int roles[OBM_NPD_MAX_TRACERS];
+    int nt = orc_npd_layout(p, roles, NULL);
+    if (nt < 0) return nt;
+    int i0, i1, j0, j1;
+    grid_range(g, &i0, &i1, &j0, &j1);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < g->Nz; k++)
+        for (int j = j0; j < j1; j++)
+            for (int i = i0; i < i1; i++) {
+                cell_t c;
+                load_cell(g, roles, nt, tracers, PAR, i, j, k, &c);
+                int64_t idx = cell_index(g, i, j, k);
+                for (int n = 0; n < nt; n++) {
+                    if (!S[n]) continue;
+                    orc_term_scale = 0.0;
+                    (void)tendency(p, &c, roles[n]);
+                    S[n][idx] = orc_term_scale;
+                }
             }
     return 0;
 }

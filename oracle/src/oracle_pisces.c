@@ -41,6 +41,8 @@ typedef const pcell* PC;
 
 #define DAY 86400.0
 
+__thread double orc_term_scale = 0.0; /* oracle_common.h: Σ|terms| of the tendency evaluated last */
+
 static double jl_min3(double a, double b, double c) { return jl_min(jl_min(a, b), c); }
 static double jl_min4(double a, double b, double c, double d) { return jl_min(jl_min(jl_min(a, b), c), d); }
 
@@ -84,7 +86,12 @@ static nlim_t nutrient_limitation(PP p, PH ph, PC c, double I, double IChl, doub
     double KSi = Ksi + 7 * (Sip * Sip) / (pk * pk + Sip * Sip);
     double LSi = c->Si / (c->Si + KSi);
     LSi = ph->silicate_limited ? LSi : INFINITY;
+#ifdef ORC_SELECT_MINMAX /* the fast pass's operand order: a select propagates a NaN in its SECOND operand, and L_Fe is the
+                          * only limitation a finite state can turn into NaN (Inf − Inf of overflowed quotas) */
+    r.L = jl_min4(LSi, r.LN, r.LPO4, r.LFe);
+#else
     r.L = jl_min4(r.LN, r.LPO4, r.LFe, LSi);
+#endif
     return r;
 }
 
@@ -278,6 +285,7 @@ static double growth_death(PP p, ZO zoo, PC c, int is_meso) {
     double gI = zoo_grazing(p, zoo, c, is_meso, &e);
     double gfI = zoo_flux_feeding(p, zoo, c, is_meso);
     double mI = zoo_mortality(p, zoo, c, is_meso);
+    ORC_TERMS(e * gI, e * gfI, mI);
     return e * (gI + gfI) - mI;
 }
 /* micro_and_meso.jl:50-52: grazing(zoo::MicroAndMeso, prey) = micro + meso */
@@ -338,9 +346,16 @@ static double non_assimilated_iron1(PP p, ZO zoo, PC c, int is_meso) {
     double gfIFe = iron_flux_feeding(zoo, c, is_meso);
     double lost_to_particles = zoo->non_assimilated_fraction * (gIFe + gfIFe);
     double total_iron_grazed = gIFe + gfIFe;
+    ORC_TERMS(total_iron_grazed, lost_to_particles, zoo_assimilated_iron);
     return total_iron_grazed - lost_to_particles - zoo_assimilated_iron;
 }
-static double non_assimilated_iron(PP p, PC c) { return non_assimilated_iron1(p, &p->micro, c, 0) + non_assimilated_iron1(p, &p->meso, c, 1); }
+static double non_assimilated_iron(PP p, PC c) {
+    double micro = non_assimilated_iron1(p, &p->micro, c, 0);
+    double s_micro = orc_term_scale;
+    double meso = non_assimilated_iron1(p, &p->meso, c, 1);
+    orc_term_scale += s_micro;
+    return micro + meso;
+}
 /* grazing_waste.jl:65-71; micro_and_meso.jl:134-136 */
 static double calcite_loss(PP p, PC c, int prey) {
     return p->micro.undissolved_calcite_fraction * zoo_grazing_on(p, &p->micro, c, 0, prey)
@@ -573,6 +588,7 @@ static double phyto_carbon(PP p, PH ph, PC c, double I, double IChl, double IFe,
     phyto_mortality(p, ph, c, I, IChl, IFe, &l, &q);
     double death = (l + q);
     double grazed = grazing_both(p, c, prey);
+    ORC_TERMS(growth, death, grazed);
     return growth - death - grazed;
 }
 static double phyto_chl(PP p, PH ph, PC c, double I, double IChl, double IFe, int prey) { /* :59-75, mixed_mondo.jl:112-124 */
@@ -585,6 +601,7 @@ static double phyto_chl(PP p, PH ph, PC c, double I, double IChl, double IFe, in
     phyto_mortality(p, ph, c, I, IChl, IFe, &l, &q);
     double death = (l + q);
     double grazed = grazing_both(p, c, prey);
+    ORC_TERMS(growth, death * tChl * 12, grazed * tChl * 12);
     return growth - (death + grazed) * tChl * 12;
 }
 static double phyto_iron(PP p, PH ph, PC c, double I, double IChl, double IFe, int prey) { /* :77-93 */
@@ -594,6 +611,7 @@ static double phyto_iron(PP p, PH ph, PC c, double I, double IChl, double IFe, i
     phyto_mortality(p, ph, c, I, IChl, IFe, &l, &q);
     double death = (l + q);
     double grazed = grazing_both(p, c, prey);
+    ORC_TERMS(growth, death * tFe, grazed * tFe);
     return growth - (death + grazed) * tFe;
 }
 
@@ -612,14 +630,17 @@ static double tendency(PP p, PC c, int name) {
             phyto_mortality(p, DIAT, &l, &q);
             double death = (l + q);
             double grazed = grazing_both(p, c, 1);
+            ORC_TERMS(growth, death * tSi, grazed * tSi);
             return growth - (death + grazed) * tSi;
         }
         case T_Z: { /* micro_and_meso.jl:36-48: M preys on Z */
             double net = growth_death(p, &p->micro, c, 0);
+            double s_net = orc_term_scale;
             double predatory = zoo_grazing_on(p, &p->meso, c, 1, 3);
+            ORC_TERMS(s_net, predatory);
             return net - predatory;
         }
-        case T_M: return growth_death(p, &p->meso, c, 1) - 0.0;
+        case T_M: return growth_death(p, &p->meso, c, 1) - 0.0; /* scale: growth_death's */
         case T_DOC: { /* dissolved_organic_carbon.jl:39-54 */
             double exud = p->nano.exudated_fraction * total_production(p, NANO) + p->diatoms.exudated_fraction * total_production(p, DIAT);
             double ute = upper_trophic_excretion(p, c);
@@ -628,6 +649,7 @@ static double tendency(PP p, PC c, int name) {
             double db = dom_degradation(p, c);
             double agg;
             dom_aggregation(p, c, &agg, NULL, NULL, NULL);
+            ORC_TERMS(exud, ute, gw, pb, db, agg);
             return (exud + ute + gw + pb - db - agg);
         }
         case T_POC: { /* particulate_organic_matter/carbon.jl:3-26 */
@@ -641,6 +663,7 @@ static double tendency(PP p, PC c, int name) {
             double gr = total_grazing_POC(p, c);
             double atl = pom_aggregation(p, c);
             double sb = specific_degradation_rate(p, c) * c->POC;
+            ORC_TERMS(gw, pm, zm, da, lb, gr, atl, sb);
             return (gw + pm + zm + da + lb - gr - atl - sb);
         }
         case T_GOC: { /* carbon.jl:28-50 */
@@ -653,6 +676,7 @@ static double tendency(PP p, PC c, int name) {
             dom_aggregation(p, c, NULL, NULL, &F2, NULL);
             double gr = total_grazing_GOC(p, c);
             double lb = specific_degradation_rate(p, c) * c->GOC;
+            ORC_TERMS(gw, pm, zm, utf, atl, F2, gr, lb);
             return (gw + pm + zm + utf + atl + F2 - gr - lb);
         }
         case T_SFe: { /* particulate_organic_matter/iron.jl:2-45 */
@@ -670,6 +694,7 @@ static double tendency(PP p, PC c, int name) {
             double gr = total_grazing_POC(p, c) * theta;
             double atl = pom_aggregation(p, c) * theta;
             double sb = specific_degradation_rate(p, c) * c->SFe;
+            ORC_TERMS(gw, pm, zm, lb, scav, ba, ca, gr, atl, sb);
             return (gw + pm + zm + lb + scav + ba + ca - gr - atl - sb);
         }
         case T_BFe: { /* iron.jl:47-89 */
@@ -687,16 +712,24 @@ static double tendency(PP p, PC c, int name) {
             aggregation_of_colloidal_iron(p, c, NULL, NULL, &ca);
             double gr = total_grazing_GOC(p, c) * tB;
             double lb = specific_degradation_rate(p, c) * c->BFe;
+            ORC_TERMS(gw, pm, zm, utf, scav, ba, ca, atl, gr, lb);
             return (gw + pm + zm + utf + scav + ba + ca + atl - gr - lb);
         }
-        case T_PSi: /* particulate_organic_matter/silicate.jl:1-9 */
-            return particulate_silicate_production(p, c) - particulate_silicate_dissolution(p, c);
-        case T_CaCO3: /* particulate_organic_matter/calcite.jl:1-7 */
-            return calcite_production(p, c) - calcite_dissolution(p, c);
+        case T_PSi: { /* particulate_organic_matter/silicate.jl:1-9 */
+            double prod = particulate_silicate_production(p, c), diss = particulate_silicate_dissolution(p, c);
+            ORC_TERMS(prod, diss);
+            return prod - diss;
+        }
+        case T_CaCO3: { /* particulate_organic_matter/calcite.jl:1-7 */
+            double prod = calcite_production(p, c), diss = calcite_dissolution(p, c);
+            ORC_TERMS(prod, diss);
+            return prod - diss;
+        }
         case T_NO3: { /* nitrate_ammonia.jl:22-32 */
             double nitrif = nitrification(p, c);
             double remin = oxic_remineralisation(p, c);
             double consumption = uptake_NO3(p, NANO) + uptake_NO3(p, DIAT);
+            ORC_TERMS(nitrif, p->nitrogen_redfield_ratio * remin, p->nitrogen_redfield_ratio * consumption);
             return nitrif + p->nitrogen_redfield_ratio * (remin - consumption);
         }
         case T_NH4: { /* nitrate_ammonia.jl:34-50 */
@@ -706,6 +739,8 @@ static double tendency(PP p, PC c, int name) {
             double gw = inorganic_excretion(p, c);
             double utw = upper_trophic_respiration(p, c);
             double fix = nitrogen_fixation(p, c);
+            ORC_TERMS(fix, p->nitrogen_redfield_ratio * remin, p->nitrogen_redfield_ratio * gw, p->nitrogen_redfield_ratio * utw,
+                      p->nitrogen_redfield_ratio * consumption, nitrif);
             return fix + p->nitrogen_redfield_ratio * (remin + gw + utw - consumption) - nitrif;
         }
         case T_PO4: { /* phosphate.jl:21-33 */
@@ -713,6 +748,8 @@ static double tendency(PP p, PC c, int name) {
             double gw = inorganic_excretion(p, c);
             double rp = upper_trophic_respiration(p, c);
             double remin = dom_degradation(p, c);
+            ORC_TERMS(p->phosphate_redfield_ratio * gw, p->phosphate_redfield_ratio * rp, p->phosphate_redfield_ratio * remin,
+                      p->phosphate_redfield_ratio * up);
             return p->phosphate_redfield_ratio * (gw + rp + remin - up);
         }
         case T_Fe: { /* iron/simple_iron.jl:19-53 */
@@ -728,11 +765,16 @@ static double tendency(PP p, PC c, int name) {
             double small_particles = specific_degradation_rate(p, c) * c->SFe;
             double consumption = iron_uptake(p, NANO) + iron_uptake(p, DIAT);
             double gw = non_assimilated_iron(p, c);
+            double s_gw = orc_term_scale; /* itself intake − waste − growth: its own Σ|terms| */
             double utw = upper_trophic_dissolved_iron(p, c);
+            ORC_TERMS(small_particles, s_gw, utw, consumption, ligand_aggregation, colloidal, scav, BactFe);
             return (small_particles + gw + utw - consumption - ligand_aggregation - colloidal - scav - BactFe);
         }
-        case T_Si: /* silicate.jl:20-26 */
-            return particulate_silicate_dissolution(p, c) - silicate_uptake(p, DIAT);
+        case T_Si: { /* silicate.jl:20-26 */
+            double diss = particulate_silicate_dissolution(p, c), up = silicate_uptake(p, DIAT);
+            ORC_TERMS(diss, up);
+            return diss - up;
+        }
         case T_DIC: { /* inorganic_carbon.jl:32-47 */
             double zr = inorganic_excretion(p, c);
             double ut = upper_trophic_respiration(p, c);
@@ -740,12 +782,17 @@ static double tendency(PP p, PC c, int name) {
             double cd = calcite_dissolution(p, c);
             double cp = calcite_production(p, c);
             double consumption = total_production(p, NANO) + total_production(p, DIAT);
+            ORC_TERMS(zr, ut, remin, cd, cp, consumption);
             return (zr + ut + remin + cd - cp - consumption);
         }
         case T_Alk: { /* inorganic_carbon.jl:49-58 */
             double nitrate_production = tendency(p, c, T_NO3);
+            double s_no3 = orc_term_scale;
             double ammonia_production = tendency(p, c, T_NH4);
+            double s_nh4 = orc_term_scale;
             double calcite_prod = tendency(p, c, T_CaCO3);
+            double s_ca = orc_term_scale;
+            ORC_TERMS(s_nh4, s_no3, 2 * s_ca); /* a sum of three tendencies: the un-cancelled scale is the sum of theirs */
             return ammonia_production - nitrate_production - 2 * calcite_prod;
         }
         case T_O2: { /* oxygen.jl:30-51 */
@@ -757,9 +804,10 @@ static double tendency(PP p, PC c, int name) {
             double np = (tr + tn) * (uptake_NO3(p, NANO) + uptake_NO3(p, DIAT));
             double nitrif = tn * nitrification(p, c) / p->nitrogen_redfield_ratio;
             double fix = tn * nitrogen_fixation(p, c) / p->nitrogen_redfield_ratio;
+            ORC_TERMS(ap, np, fix, remin, zoo, ut, nitrif);
             return (ap + np + fix - remin - zoo - ut - nitrif);
         }
-        default: return 0.0; /* T, S: zero(grid) PISCES.jl:120 */
+        default: orc_term_scale = 0.0; return 0.0; /* T, S: zero(grid) PISCES.jl:120 */
     }
 }
 
@@ -808,6 +856,28 @@ int orc_pisces_tendencies(const obm_grid* g, const obm_pisces_params* p, const d
     return 0;
 }
 
+/* Σ|additive terms| of every tendency (the parity metric's S) on the grid: S[n] parent arrays, NULL skips */
+int orc_pisces_tendency_scales(const obm_grid* g, const obm_pisces_params* p, const double* const* tracers,
+                               const obm_pisces_fields* aux, double* const* S) {
+    int i0, i1, j0, j1;
+    grid_range(g, &i0, &i1, &j0, &j1);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < g->Nz; k++)
+        for (int j = j0; j < j1; j++)
+            for (int i = i0; i < i1; i++) {
+                pcell c;
+                load_pcell(g, tracers, aux, i, j, k, &c);
+                int64_t idx = cell_index(g, i, j, k);
+                for (int n = 0; n < OBM_PISCES_NTRACERS; n++) {
+                    if (!S[n]) continue;
+                    orc_term_scale = 0.0;
+                    (void)tendency(p, &c, n);
+                    S[n][idx] = orc_term_scale;
+                }
+            }
+    return 0;
+}
+
 /* scalar entry for box-model style checks: values[26] tracers, aux scalars → tendencies[26] */
 void orc_pisces_point(const obm_pisces_params* p, const double* values, double PAR1, double PAR2, double PAR3, double PAR,
                       double Omega, double wPOC, double wGOC, double zmxl, double zeu, double kappa, double mlPAR, double z,
@@ -818,6 +888,21 @@ void orc_pisces_point(const obm_pisces_params* p, const double* values, double P
     c.PAR1 = PAR1; c.PAR2 = PAR2; c.PAR3 = PAR3; c.PAR = PAR; c.Omega = Omega; c.wPOC = wPOC; c.wGOC = wGOC;
     c.zmxl = zmxl; c.zeu = zeu; c.kappa = kappa; c.mlPAR = mlPAR; c.z = z;
     for (int n = 0; n < OBM_PISCES_NTRACERS; n++) out[n] = tendency(p, &c, n);
+}
+/* the same point, also returning Σ|terms| per tendency */
+void orc_pisces_point_terms(const obm_pisces_params* p, const double* values, double PAR1, double PAR2, double PAR3, double PAR,
+                            double Omega, double wPOC, double wGOC, double zmxl, double zeu, double kappa, double mlPAR, double z,
+                            double* out, double* scale) {
+    pcell c;
+    double* v = &c.P;
+    for (int n = 0; n < OBM_PISCES_NTRACERS; n++) v[n] = values[n];
+    c.PAR1 = PAR1; c.PAR2 = PAR2; c.PAR3 = PAR3; c.PAR = PAR; c.Omega = Omega; c.wPOC = wPOC; c.wGOC = wGOC;
+    c.zmxl = zmxl; c.zeu = zeu; c.kappa = kappa; c.mlPAR = mlPAR; c.z = z;
+    for (int n = 0; n < OBM_PISCES_NTRACERS; n++) {
+        orc_term_scale = 0.0;
+        out[n] = tendency(p, &c, n);
+        scale[n] = orc_term_scale;
+    }
 }
 
 /* Julia's sind / cosd reduce the argument in DEGREES (rem(x, 360) is exact) and fold it to |angle| <= 45° before the

@@ -9,7 +9,7 @@ import torch
 
 import oceanbiome_b200 as ob
 from oceanbiome_b200 import pisces, synthetic
-from helpers import RTOL_TENDENCY
+from helpers import RTOL_TENDENCY, assert_tendency_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -64,11 +64,10 @@ def test_lobster_c3_full_size(cuda, oracle):
     og = oracle.Grid(3000, 1, 1, 0, 0, 0, np.array([-0.5]), np.array([-1.0, 0.0]))
     vals = [np.ascontiguousarray(at(model.tracers[n], k, j, i).reshape(og.parent_shape)) for n in names]
     PAR = np.ascontiguousarray(at(bgc.biogeochemical_auxiliary_fields()["PAR"], k, j, i).reshape(og.parent_shape))
-    want = oracle.npd_tendencies(og, u.c_params(), vals, PAR)
-    S = np.maximum.reduce([np.abs(w) for w in want])
-    for n, w in zip(names, want):
-        got = at(model.Gn[n], k, j, i).reshape(og.parent_shape)
-        assert np.max(np.abs(got - w) / np.maximum(np.abs(w), S)) <= RTOL_TENDENCY, n
+    want = dict(zip(names, oracle.npd_tendencies(og, u.c_params(), vals, PAR)))
+    S = dict(zip(names, oracle.npd_tendency_scales(og, u.c_params(), vals, PAR)))  # Σ|terms| per tendency
+    got = {n: at(model.Gn[n], k, j, i).reshape(og.parent_shape) for n in names}
+    assert_tendency_parity("lobster_c3_full_size_3000_cells", names, got, want, S)
     # … and 24 drawn columns of the two-band PAR scan
     rng = np.random.default_rng(2)
     cj, ci = rng.integers(0, grid.Ny, 24), rng.integers(0, grid.Nx, 24)
@@ -121,15 +120,17 @@ def test_pisces_c4_full_size(cuda, oracle):
     wP, wG = wmean(aux["wPOC"]), wmean(aux["wGOC"])
     G = {n: at(model.Gn[n], k, j, i) for n in pisces.TRACERS[:24]}
     params = u.c_params(model.clock.time)
-    worst = 0.0
+    names24 = pisces.TRACERS[:24]
+    want = {n: np.zeros(len(k)) for n in names24}
+    S = {n: np.zeros(len(k)) for n in names24}
     for c in range(len(k)):
-        want = oracle.pisces_point(params, [T[n][c] for n in pisces.TRACERS], A["PAR₁"][c], A["PAR₂"][c], A["PAR₃"][c],
-                                   A["PAR"][c], A["Ω"][c], wP[c], wG[c], A["zₘₓₗ"][c], A["zₑᵤ"][c], A["κ"][c],
-                                   A["mixed_layer_PAR"][c], grid.zc[k[c]])
-        S = max(abs(w) for w in want[:24])
-        for n, w in zip(pisces.TRACERS[:24], want):
-            worst = max(worst, abs(G[n][c] - w) / max(abs(w), S))
-    assert worst <= RTOL_TENDENCY, worst
+        w, sc = oracle.pisces_point_terms(params, [T[n][c] for n in pisces.TRACERS], A["PAR₁"][c], A["PAR₂"][c], A["PAR₃"][c],
+                                          A["PAR"][c], A["Ω"][c], wP[c], wG[c], A["zₘₓₗ"][c], A["zₑᵤ"][c], A["κ"][c],
+                                          A["mixed_layer_PAR"][c], grid.zc[k[c]])
+        for q, n in enumerate(names24):
+            want[n][c], S[n][c] = w[q], sc[q]
+    # the stated metric: |Δ| ≤ 1e-12·max(|want|, S) with S = Σ|additive terms| of THAT tendency; pure relative error too
+    assert_tendency_parity("pisces_c4_full_size_4000_cells", names24, G, want, S)
     # Ω of the drawn cells against the reference's own damped Newton (oracle), P = |z|·g·1026/1e5 bar
     om = np.array([oracle.carbon_chemistry(T["DIC"][c], T["T"][c], T["S"][c], T["Alk"][c],
                                            P=abs(grid.zc[k[c]]) * 9.80665 * 1026.0 / 100000.0, silicate=T["Si"][c],

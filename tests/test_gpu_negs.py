@@ -97,6 +97,31 @@ def test_reference_expected_outcomes(cuda):
     assert tr["Fe"].interior.item() == 0 and math.isclose(tr["Z"].interior.item(), 900, rel_tol=1e-8)
 
 
+def test_absorbed_negative_member_is_still_zeroed(cuda, oracle):
+    """A negative member far below the ulp of the group's positive sum (the usual overshoot: DIC ≈ 2e3, plankton ≈ −1e-15)
+    leaves t == p bit for bit; the reference still writes 0 for every non-positive member (negative_tracers.jl:268-274)
+    and leaves the positives as they are (t / p = 1).  Also −0.0 → +0.0, as `ifelse(…, 0)` gives."""
+    grid = ob.RectilinearGrid(size=(8, 2, 3), extent=(8, 2, 3), device=cuda)
+    names = ("P", "Z", "DIC")
+    dev, host, og = synthetic_state(grid, names, {"P": (0.01, 0.5, False), "Z": (0.01, 0.5, False), "DIC": (2000.0, 2300.0, False)})
+    for (k, j, i), v in {(0, 0, 1): -1e-14, (1, 1, 3): -5e-324, (2, 0, 5): -0.0, (2, 1, 7): -1e-13}.items():
+        host["P"][og.Hz + k, og.Hy + j, og.Hx + i] = v
+    dev["P"].data.copy_(torch.from_numpy(host["P"]))
+    groups = [(names, (6.56, 6.56, 1.0))]
+    before = {n: host[n].copy() for n in names}
+    scalers = tuple(ob.ScaleNegativeTracers(t, s) for t, s in groups)
+    ob.biogeochemistry._update_modifiers(M(grid, dev), scalers, None)
+    oracle.scale_negative_tracers(og, [host[n] for n in names], oracle.make_groups(names, groups))
+    gotP = og.interior(dev["P"].data.cpu().numpy())
+    assert bool((gotP >= 0).all()) and int((gotP == 0).sum()) == 4 and not np.signbit(gotP).any()
+    for n in names:
+        got = dev[n].data.cpu().numpy()
+        assert np.array_equal(got == 0, host[n] == 0), n
+        assert np.all(np.abs(got - host[n]) <= 5e-16 * np.abs(host[n])), n  # (v·t)/p vs v·(t/p): ≤ 2 ulp
+        touched = og.interior(before["P"]) <= 0
+        assert np.array_equal(og.interior(got)[~touched], og.interior(before[n])[~touched]), n  # clean cells: bit for bit
+
+
 def test_zero_negative_bit_exact(cuda, oracle):
     grid = ob.RectilinearGrid(size=(13, 5, 7), extent=(13, 5, 7), device=cuda)
     dev, host, og = synthetic_state(grid, ["A", "B", "C"], {n: (-1.0, 1.0, False) for n in "ABC"})

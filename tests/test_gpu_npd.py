@@ -10,7 +10,7 @@ import torch
 
 import oceanbiome_b200 as ob
 from oceanbiome_b200 import synthetic
-from helpers import RTOL_TENDENCY, scale_aware_error, synthetic_state
+from helpers import RTOL_TENDENCY, assert_tendency_parity, synthetic_state
 
 pytestmark = pytest.mark.gpu
 
@@ -30,20 +30,16 @@ def run_both(oracle, grid, bgc, PAR_range=(0.0, 150.0), accumulate=False, g0=0.2
                                accumulate=accumulate)
     got = {n: og.interior(G[n].data.cpu().numpy()) for n in names}
     want = {n: og.interior(g) for n, g in zip(names, Go)}
-    return names, got, want, G, og
+    So = oracle.npd_tendency_scales(og, bgc.c_params(), [host[n] for n in names], phost["PAR"])
+    scales = {n: og.interior(s) for n, s in zip(names, So)}
+    return names, got, (want, scales), G, og
 
 
-def assert_parity(names, got, want, offset=0.0):
-    # S: the largest un-cancelled flux of the cell — every additive term of every tendency appears
-    # (times an O(1–10) stoichiometric factor) in at least one of the tendencies
-    S = np.maximum.reduce([np.abs(want[n] - offset) for n in names if n != "T"]) + abs(offset)
-    worst = 0.0
-    for n in names:
-        if n == "T":
-            continue
-        worst = max(worst, scale_aware_error(got[n], want[n], S))
-    assert worst <= RTOL_TENDENCY, f"scale-aware error {worst:.3e}"
-    return worst
+def assert_parity(names, got, want_scales, offset=0.0, label="npd"):
+    """|Δ| ≤ 1e-12·max(|want|, S) per tendency, S = Σ|additive terms| of that tendency (oracle.npd_tendency_scales);
+    pure relative error asserted where the tendency is not a near-total cancellation (helpers.assert_tendency_parity)."""
+    want, S = want_scales
+    return assert_tendency_parity(label, [n for n in names if n != "T"], got, want, S, offset)[0]
 
 
 @pytest.mark.parametrize("nut,det,car,oxy", list(itertools.product(NUTRIENTS, DETRITUS, (0, 1), (False, True))))
@@ -52,7 +48,7 @@ def test_every_variant_matches_oracle(cuda, oracle, nut, det, car, oxy):
     bgc = ob.NutrientsPlanktonDetritus(nut(), ob.PhytoZoo(), det() if det else None,
                                        ob.CarbonateSystem(car) if car else None, ob.Oxygen() if oxy else None)
     names, got, want, G, og = run_both(oracle, grid, bgc)
-    assert_parity(names, got, want)
+    assert_parity(names, got, want, label=f"npd[{nut.__name__},{det.__name__ if det else None},{car},{oxy}]")
     # halos of G are never written
     for n in names:
         full = G[n].data.cpu().numpy().copy()
@@ -70,9 +66,10 @@ def test_npzd_readme_grid_C1(cuda, oracle):
     G = {n: ob.CenterField(grid) for n in names}
     bgc.compute_tendencies(grid, dev, pdev, G, accumulate=False)
     Go = oracle.npd_tendencies(og, bgc.c_params(), [host[n] for n in names], phost["PAR"])
+    So = oracle.npd_tendency_scales(og, bgc.c_params(), [host[n] for n in names], phost["PAR"])
     got = {n: og.interior(G[n].data.cpu().numpy()) for n in names}
     want = {n: og.interior(g) for n, g in zip(names, Go)}
-    assert_parity(names, got, want)
+    assert_parity(names, got, (want, {n: og.interior(x) for n, x in zip(names, So)}), label="npzd_c1")
     assert np.all(got["T"] == 0.0)
 
 
@@ -83,7 +80,7 @@ def test_lobster_columns_C2_accumulate(cuda, oracle):
                               device=cuda)
     bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen()).underlying_biogeochemistry
     names, got, want, _, _ = run_both(oracle, grid, bgc, accumulate=True, g0=1e-7)
-    assert_parity(names, got, want, offset=1e-7)
+    assert_parity(names, got, want, offset=1e-7, label="lobster_c2_accumulate")
 
 
 def test_carbonate_replicates_share_one_tendency(cuda, oracle):
@@ -92,7 +89,7 @@ def test_carbonate_replicates_share_one_tendency(cuda, oracle):
     bgc = ob.NutrientsPlanktonDetritus(ob.NitrateAmmonia(), ob.PhytoZoo(), ob.TwoParticleAndDissolved(),
                                        ob.CarbonateSystem(3), None)
     names, got, want, _, _ = run_both(oracle, grid, bgc)
-    assert_parity(names, got, want)
+    assert_parity(names, got, want, label="npd_carbonate_replicates")
     assert np.array_equal(got["DIC1"], got["DIC3"]) and np.array_equal(got["Alk1"], got["Alk2"])
 
 

@@ -9,7 +9,7 @@ import torch
 
 import oceanbiome_b200 as ob
 from oceanbiome_b200 import pisces, synthetic
-from helpers import RTOL_CARBON, RTOL_TENDENCY, scale_aware_error
+from helpers import RTOL_CARBON, RTOL_TENDENCY, assert_tendency_parity, scale_aware_error
 
 pytestmark = pytest.mark.gpu
 
@@ -40,17 +40,23 @@ def fill(model, bgc):
     return host
 
 
-def compare(oracle, og, u, host, aux, G, t, accumulate=False, g0=0.0):
-    Go = oracle.pisces_tendencies(og, u.c_params(t), [host[n] for n in pisces.TRACERS], aux,
+def compare(oracle, og, u, host, aux, G, t, accumulate=False, g0=0.0, label="pisces"):
+    """CUDA vs oracle with the stated per-tendency metric: |Δ| ≤ 1e-12·max(|want|, S), S = Σ|additive terms| of that
+    tendency (oracle.pisces_tendency_scales); the pure relative error is asserted too (helpers.assert_tendency_parity).
+    Returns ({tracer: scale-aware error}, {tracer: pure relative max})."""
+    from helpers import tendency_parity
+    params = u.c_params(t)
+    tr = [host[n] for n in pisces.TRACERS]
+    Go = oracle.pisces_tendencies(og, params, tr, aux,
                                   G=[np.full(og.parent_shape, g0) if n < 24 else None for n in range(26)] if accumulate else None,
                                   accumulate=accumulate)
+    So = oracle.pisces_tendency_scales(og, params, tr, aux)
     want = {n: og.interior(g) for n, g in zip(pisces.TRACERS, Go) if g is not None}
+    S = {n: og.interior(s) for n, s in zip(pisces.TRACERS, So) if s is not None}
     got = {n: og.interior(G[n].data.cpu().numpy()) for n in want}
-    # scale: the largest un-cancelled flux of the element family the tendency belongs to
-    S = np.maximum.reduce([np.abs(want[n] - g0) for n in want]) + abs(g0)
-    worst = {n: scale_aware_error(got[n], want[n], S) for n in want}
-    rel = {n: float(np.max(np.abs(got[n] - want[n]) / np.maximum(np.abs(want[n]), 1e-300))) for n in want}
-    return worst, rel
+    assert_tendency_parity(label, list(want), got, want, S, offset=g0 if accumulate else 0.0)
+    rows = {n: tendency_parity(got[n], want[n], S[n], g0 if accumulate else 0.0) for n in want}
+    return {n: r[0] for n, r in rows.items()}, {n: r[1] for n, r in rows.items()}
 
 
 @pytest.mark.parametrize("size,t", [((33, 7, 19), 0.37 * 365 * 86400.0), ((128, 2, 40), 1.6)])
@@ -64,7 +70,7 @@ def test_fused_tendencies_match_oracle(cuda, oracle, size, t):
     aux = host_aux(og, grid, bgc)
     G = {n: ob.CenterField(grid, fill=3.0) for n in pisces.TRACERS}
     u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G, accumulate=False, time=t)
-    worst, rel = compare(oracle, og, u, host, aux, G, t)
+    worst, rel = compare(oracle, og, u, host, aux, G, t, label=f"pisces{size}")
     assert max(worst.values()) <= RTOL_TENDENCY, worst
     # T and S receive nothing; halos untouched
     for n in ("T", "S"):
@@ -108,14 +114,15 @@ def test_nan_inputs_propagate_like_the_reference(cuda, oracle, accumulate):
     want = {n: og.interior(g) for n, g in zip(pisces.TRACERS, Go) if g is not None}
     got = {n: og.interior(G[n].data.cpu().numpy()) for n in want}
     off = g0 if accumulate else 0.0
-    S = np.maximum.reduce([np.nan_to_num(np.abs(want[n] - off), nan=0.0, posinf=0.0) for n in want]) + off
+    So = oracle.pisces_tendency_scales(og, u.c_params(0.0), [host[n] for n in pisces.TRACERS], aux)
+    Sn = {n: og.interior(s) + off for n, s in zip(pisces.TRACERS, So) if s is not None}
     poisoned = 0
     for n in want:
         bad_w, bad_g = ~np.isfinite(want[n]), ~np.isfinite(got[n])
         assert np.array_equal(np.isnan(want[n]), np.isnan(got[n])), n
         assert np.array_equal(bad_w, bad_g) and np.array_equal(want[n][bad_w & ~np.isnan(want[n])], got[n][bad_g & ~np.isnan(got[n])]), n
-        ok = ~bad_w
-        assert np.max(np.abs(got[n][ok] - want[n][ok]) / S[ok]) <= RTOL_TENDENCY, n
+        ok = ~bad_w & np.isfinite(Sn[n])
+        assert np.max(np.abs(got[n][ok] - want[n][ok]) / np.maximum(np.abs(want[n][ok]), Sn[n][ok])) <= RTOL_TENDENCY, n
         poisoned += int(bad_w.sum())
     assert poisoned >= 9 * 3  # every injected NaN reaches several tendencies
 
@@ -129,7 +136,7 @@ def test_accumulate_into_existing_tendencies(cuda, oracle):
     aux = host_aux(og, grid, bgc)
     G = {n: ob.CenterField(grid, fill=1e-7) for n in pisces.TRACERS}
     u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G, accumulate=True, time=0.0)
-    worst, _ = compare(oracle, og, u, host, aux, G, 0.0, accumulate=True, g0=1e-7)
+    worst, _ = compare(oracle, og, u, host, aux, G, 0.0, accumulate=True, g0=1e-7, label="pisces_accumulate")
     assert max(worst.values()) <= RTOL_TENDENCY, worst
 
 

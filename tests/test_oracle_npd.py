@@ -147,3 +147,27 @@ def test_c_oracle_matches_independent_restatement(oracle, one, case):
         scale = max(abs(v) for v in row["tendencies"].values())
         for n, want in row["tendencies"].items():
             assert abs(got[n] - want) <= 2e-15 * scale, (case, n, got[n], want)
+
+
+@pytest.mark.parametrize("det,oxy,car,nut", VARIANTS[::5])
+def test_term_scales_bound_the_tendencies(oracle, one, det, oxy, car, nut):
+    """`orc_npd_tendency_scales` — the S of the parity metric |a − b| ≤ 1e-12·max(|b|, S): Σ|additive terms| of
+    each tendency bounds the tendency itself, and is 0 exactly where the model gives the tracer no method (`zero(grid)`)."""
+    bgc = make(det, oxy, car, nut)
+    rng = np.random.default_rng(3)
+    names = bgc.required_biogeochemical_tracers()
+    for _ in range(20):
+        state = random_state(bgc, rng)
+        tr = []
+        for n in names:
+            a = np.zeros(one.parent_shape)
+            one.interior(a)[...] = state[n]
+            tr.append(a)
+        par = np.full(one.parent_shape, 100.0 * rng.random())
+        G = oracle.npd_tendencies(one, bgc.c_params(), tr, par)
+        S = oracle.npd_tendency_scales(one, bgc.c_params(), tr, par)
+        for n, g, s in zip(names, G, S):
+            t, sc = float(one.interior(g)[0, 0, 0]), float(one.interior(s)[0, 0, 0])
+            assert sc >= 0 and abs(t) <= sc * (1 + 1e-14), (n, t, sc)
+            if n == "T":
+                assert sc == 0 and t == 0

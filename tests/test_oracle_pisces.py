@@ -145,16 +145,15 @@ def test_c_oracle_matches_independent_restatement(oracle, row):
 
 def _random_point(rng, extreme):
     """A state with finite inputs: ordinary (factor e^{±2} around the reference test's state) or extreme (zeros,
-    denormals, huge values — what a blown-up simulation hands over just before it produces its first NaN; the four
-    plankton biomasses are 0 or ≥ 1e-30, see the next test but one for why)."""
+    denormals, huge values — what a blown-up simulation hands over just before it produces its first NaN)."""
     if not extreme:
         vals = {n: v * math.exp(rng.uniform(-2, 2)) for n, v in pisces.PISCES_INITIAL_VALUES.items()}
         vals["T"], vals["S"] = rng.uniform(-2, 32), rng.uniform(20, 40)
     else:
         pick = lambda: rng.choice([0.0, 5e-324, 1e-300, 1e-30, 1e-6, 1.0, 1e6, 1e30, 1e150])  # noqa: E731
         vals = {n: pick() for n in pisces.PISCES_INITIAL_VALUES}
-        for biomass in ("P", "D", "Z", "M"):
-            vals[biomass] = rng.choice([0.0, 1e-30, 1e-6, 1.0, 1e6])
+        for biomass in ("P", "D", "Z", "M"):  # incl. positive biomasses far below their pigment (quota overflow, see below)
+            vals[biomass] = rng.choice([0.0, 5e-324, 1e-310, 1e-280, 1e-200, 1e-30, 1e-6, 1.0, 1e6])
         vals["T"], vals["S"] = rng.choice([-2.0, 0.0, 40.0, 1e3]), rng.choice([0.0, 35.0, 1e3])
     aux = [rng.uniform(0, 80), rng.uniform(0, 80), rng.uniform(0, 80), 0.0, rng.choice([0.0, 0.5, 1.0, 3.0, 1e6]),
            -rng.choice([0.0, 2.0, 50.0]) / 86400, -rng.choice([1e-9, 30.0, 200.0]) / 86400, -rng.uniform(1, 300),
@@ -186,17 +185,25 @@ def test_select_min_max_equals_propagating_min_max_for_finite_inputs(oracle, box
         assert not lost, (lost, vals, aux)
 
 
-def test_known_limit_of_the_fast_pass_quota_overflow(oracle, box):
-    """Where the statement above stops: a POSITIVE plankton biomass below ≈ 1e-290 carrying ordinary pigment makes the
-    chlorophyll quota θ = Chl / (12 I + eps(0)) overflow to Inf; Inf · 0 is then a NaN born mid-way, which the reference's
-    `min` / `max` propagate into a dozen tendencies and a select drops.  Exactly zero biomass is guarded (in the reference
-    too), so this needs a concentration no simulation reaches with its pigment intact; recorded here so that the parity
-    claim in DESIGN.md §3.1 is stated with its edge."""
+def test_quota_overflow_reaches_the_exact_pass(oracle, box):
+    """A POSITIVE plankton biomass far below its pigment (here a denormal) makes the iron and chlorophyll quotas overflow:
+    θ = Chl / (12 I + eps(0)) = Inf, and L_Fe = min(1, max(0, (θFe − θFe_min) / θopt)) = Inf − Inf = NaN — a NaN born
+    mid-way from finite inputs, which the reference's `min` / `max` propagate into a dozen tendencies.  With the
+    reference's operand order min(L_N, L_PO₄, L_Fe, L_Si) a compare + select drops it for diatoms (L_Si is finite there);
+    the fast pass therefore takes L_Fe last (a select propagates a NaN in its second operand), and the oracle built with
+    select semantics does the same: nothing is lost, the cell comes out non-finite and is redone by the exact pass.
+    (r01 recorded this case as a known limit of the fast pass.)"""
     vals = dict(pisces.PISCES_INITIAL_VALUES)
-    vals["D"] = 5e-324
     aux = [30.0, 30.0, 30.0, 90.0, 0.8, -2 / 86400, -30 / 86400, -50.0, -80.0, 1e-3, 40.0, -20.0]
-    assert "D" in _lost_nans(oracle, box, vals, aux, 1e6)
-    vals["D"] = 0.0  # the guarded case: nothing is lost
+    for tiny in (5e-324, 1e-310, 1e-300, 1e-290):
+        for who in ("D", "P"):
+            v = dict(vals)
+            v[who] = tiny
+            exact = oracle.pisces_point(box.c_params(1e6), [v.get(n, 0.0) for n in pisces.TRACERS], *aux)
+            if tiny == 5e-324:
+                assert math.isnan(exact[pisces.TRACERS.index(who)])  # the reference's answer for such a cell
+            assert not _lost_nans(oracle, box, v, aux, 1e6), (who, tiny)
+    vals["D"] = 0.0  # exactly zero biomass is guarded in the reference itself: finite, nothing to lose
     assert not _lost_nans(oracle, box, vals, aux, 1e6)
 
 
@@ -212,3 +219,29 @@ def test_select_min_max_swallows_what_the_input_guard_catches(oracle, box):
     fast = oracle.pisces_point(p, v, *aux, select=True)
     lost = [pisces.TRACERS[n] for n in range(24) if math.isnan(exact[n]) and math.isfinite(fast[n])]
     assert lost, "expected the select arithmetic to lose NaNs for an infinite input"
+
+
+# ---- the parity metric's scale: S = Σ|additive terms| per tendency ------------------------------------
+
+def test_term_scales_bound_the_tendencies_and_compose(oracle, box):
+    """`orc_pisces_point_terms`: every tendency is bounded by the sum of the magnitudes of its own additive terms
+    (triangle inequality, to rounding); a tendency that is one flux has S = |t|; Alk = NH₄ − NO₃ − 2 CaCO₃
+    (inorganic_carbon.jl:49-58) carries S_NH₄ + S_NO₃ + 2 S_CaCO₃; the tendencies are those of `orc_pisces_point` bit for
+    bit (recording S does not touch the arithmetic); T and S have no terms."""
+    rng = np.random.default_rng(77)
+    ix = {n: q for q, n in enumerate(pisces.TRACERS)}
+    saw_cancellation = False
+    for _ in range(200):
+        vals, aux = _random_point(rng, False)
+        v = [vals.get(n, 0.0) for n in pisces.TRACERS]
+        p = box.c_params(rng.uniform(0, 3e7))
+        t, S = oracle.pisces_point_terms(p, v, *aux)
+        assert t == oracle.pisces_point(p, v, *aux)
+        for n in range(24):
+            assert S[n] >= 0 and abs(t[n]) <= S[n] * (1 + 1e-14), (pisces.TRACERS[n], t[n], S[n])
+            saw_cancellation |= abs(t[n]) < 1e-2 * S[n]
+        assert S[ix["T"]] == 0 and S[ix["S"]] == 0
+        assert S[ix["Alk"]] == pytest.approx(S[ix["NH₄"]] + S[ix["NO₃"]] + 2 * S[ix["CaCO₃"]], rel=1e-15)
+        # a sum over disjoint positive fluxes: DIC's terms are ≥ each of the fluxes that also close the carbon budget
+        assert S[ix["DIC"]] >= abs(t[ix["DIC"]])
+    assert saw_cancellation  # the metric matters: some tendencies ARE near-cancelling differences of their terms
