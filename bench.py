@@ -1,16 +1,22 @@
 #!/usr/bin/env python
-"""bench.py — BGC hot-path throughput (Gcell-updates/s) on N B200s, with roofline, CPU baseline,
-end-to-end (host-buffer) number and clock record.  Contract: see the task statement / DESIGN.md §5.
+"""bench.py — BGC hot-path throughput (Gcell-updates/s) on N B200s, with per-kernel and whole-stage roofline, CPU
+baselines, end-to-end (host-buffer) number, the N-GPU inventory all-reduce and a clock record.
+Contract: the task statement / DESIGN.md §5.
 
-One "step" = one Runge–Kutta stage of the biogeochemistry for the whole local grid, i.e. exactly what
-Oceananigans triggers per stage through the plugin hooks:
-    update_biogeochemical_state!(bgc, model)   → negative scaling, PAR scan, (PISCES: zₑᵤ, ML means, Ω)
-    update_tendencies!(bgc, model)             → fused tendencies of every tracer, Gⁿ += …
+One "step" = one Runge–Kutta stage of the biogeochemistry for the whole grid, i.e. exactly what Oceananigans triggers
+per stage through the plugin hooks:
+    update_biogeochemical_state!(bgc, model)   → negative scaling (+ Ω for PISCES), PAR scan (+ zₑᵤ, PAR̄), sediment
+    update_tendencies!(bgc, model)             → fused tendencies of every tracer, Gⁿ += …, sediment ↔ tracer fluxes
 A "cell-update" = all of that for one grid cell.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
-Under torchrun (N > 1) every rank owns one x–y slab of the same size (weak scaling; no data-path
-collective — every kernel is pointwise or column-local), time = max over ranks.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference] [--scaling strong|weak]
+
+Under torchrun (N > 1) the ONE grid of the workload is split into N x–y slabs along y (BASELINE configs[3]: "1024×1024×128
+x-y slab-sharded across 1/2/4/8 B200") — `"scaling": "strong"`; there is no data-path collective (every kernel is
+pointwise or column-local), time = max over ranks.  The same run also reports, as sub-records: the weak-scaling number
+(one full-size grid per GPU), the tracer-inventory diagnostic executed every stage (obm_inventory + the path's only
+collective, an all-reduce of ≤ 8 doubles over NCCL) with its own time and a check against the oracle's serial sum, and
+the end-to-end leg with the PCIe peak measured while all N ranks copy concurrently.
 """
 from __future__ import annotations
 
@@ -33,11 +39,22 @@ import torch  # noqa: E402
 # --------------------------------------------------------------------------------------------------
 # workloads (BASELINE.json configs)
 # --------------------------------------------------------------------------------------------------
+def eady_z_faces(Nz=64, Lz=140.0, refinement=1.8, stretching=3.0):
+    """The stretched vertical grid of the reference's Eady case, paper/figures/eady.jl:11-27 (k = 1 … Nz + 1)."""
+    def z(k):
+        h = (k - 1) / Nz
+        zeta0 = 1 + (h - 1) / refinement
+        sigma = (1 - np.exp(-stretching * h)) / (1 - np.exp(-stretching))
+        return Lz * (zeta0 * sigma - 1)
+    return z
+
+
 def workload_table():
     return {
         # name: (description, builder)
-        "lobster_c3": ("LOBSTER + carbonates + O2, 3-D Eady-style grid 512x512x64 (BASELINE configs[2], no sediment)",
-                       dict(model="lobster", size=(512, 512, 64), extent=(1000.0, 1000.0, 140.0))),
+        "lobster_c3": ("LOBSTER + carbonates + O2 with SimpleMultiG sediment bottom boundary and sinking sPOM / bPOM, 3-D Eady grid "
+                       "512x512x64 on the stretched z of paper/figures/eady.jl (BASELINE configs[2])",
+                       dict(model="lobster", size=(512, 512, 64), extent=(1000.0, 1000.0, 140.0), sediment=True, z="eady")),
         "lobster_c2": ("LOBSTER + carbonates + O2, column ensemble 4096 columns x 64 levels (BASELINE configs[1])",
                        dict(model="lobster", size=(4096, 1, 64), extent=(4096.0, 1.0, 200.0))),
         "npzd_c1": ("NPZD + TwoBandPAR on the README grid 160x1x32 (BASELINE configs[0])",
@@ -50,33 +67,79 @@ def workload_table():
 
 
 def default_workload():
-    import oceanbiome_b200 as ob
-    return "pisces_c4" if hasattr(ob, "PISCES") else "lobster_c3"
+    return "pisces_c4"
+
+
+def shards(name, world, scaling):
+    """How the workload is split over `world` ranks: ("strong", rows per rank) when its grid divides along y, else
+    ("weak", None) — independent replicas (column ensembles and the flat sweep have no y to split)."""
+    cfg = workload_table()[name][1]
+    if scaling == "weak" or world == 1:
+        return ("weak" if world > 1 else scaling), None
+    if cfg["model"] == "carbon" or cfg["size"][1] % world or cfg["size"][1] // world < 1 or cfg["size"][1] == 1:
+        return "weak", None
+    return "strong", cfg["size"][1] // world
+
+
+def config_dict(name, world, scaling):
+    """The `config` of the JSON line — built by this one function for BOTH arms (`--impl b200` and `--impl reference`),
+    so the driver's same-config check compares like with like."""
+    desc, cfg = workload_table()[name]
+    mode, rows = shards(name, world, scaling)
+    if cfg["model"] == "carbon":
+        grid = f"flat n = {cfg['n']}"
+        small = False
+    else:
+        Nx, Ny, Nz = cfg["size"]
+        grid = f"{Nx}x{Ny}x{Nz}"
+        small = Nx * Ny * Nz * 640 <= 4e8
+    return {"workload": name, "description": desc, "grid": grid, "scaling": mode,
+            "parallelism": (f"one grid, {world} x-y slabs of {rows} rows along y" if mode == "strong" and world > 1
+                            else (f"{world} independent replicas of the grid" if world > 1 else "1 GPU")) + "; no data-path collective",
+            "l2": ("working set fits L2: evicted by a 256 MB write before every step (not timed); time = sum of per-step event pairs"
+                   if small else "inputs larger than L2 (no flush needed)"),
+            "state": "static synthetic fields (splitmix64, seed 20260117), all positive: the negative-scaling pass reads every "
+                     "scaled tracer and rewrites none",
+            "carbonate_solve": ("Newton in ln[H+] started every step from the analytic root of the carbonate-alkalinity quadratic "
+                                "(no stored [H+]: warm start disabled for the static state)" if cfg["model"] in ("pisces", "carbon") else None)}
 
 
 class Workload:
-    """Builds the model state on `device` (synthetic fields) and exposes step()."""
+    """Builds the model state on `device` (synthetic fields) and exposes step().
+    `rows = (j0, ny, Ny_global)`: this rank's y-slab of the global grid (strong scaling)."""
 
-    def __init__(self, name, device, scale=1.0):
+    def __init__(self, name, device, scale=1.0, rows=None):
         import oceanbiome_b200 as ob
         from oceanbiome_b200 import synthetic
         self.ob, self.name, self.device = ob, name, device
         desc, cfg = workload_table()[name]
         self.description, self.cfg = desc, cfg
         self.kind = cfg["model"]
-        self.launches_per_step = 0
+        self.marks = None
         if self.kind == "carbon":
             self._build_carbon(int(cfg["n"] * scale))
             return
         Nx, Ny, Nz = cfg["size"]
         if scale != 1.0:
             Ny = max(1, int(Ny * scale))
+        Lx, Ly, Lz = cfg["extent"]
+        fill_rows = None
+        if rows is not None:
+            j0, ny, nyg = rows
+            Ly, Ny = Ly * ny / Ny, ny
+            fill_rows = (j0, nyg)
         topo = ("Periodic", "Periodic" if Ny > 1 else "Flat", "Bounded")
         size = (Nx, Ny, Nz) if Ny > 1 else (Nx, Nz)
-        extent = cfg["extent"] if Ny > 1 else (cfg["extent"][0], cfg["extent"][2])
-        self.grid = ob.RectilinearGrid(size=size, extent=extent, topology=topo, device=device)
+        z = eady_z_faces(Nz, Lz) if cfg.get("z") == "eady" else (-Lz, 0.0)
+        kw = dict(x=(0.0, Lx), z=z) if Ny == 1 else dict(x=(0.0, Lx), y=(0.0, Ly), z=z)
+        self.grid = ob.RectilinearGrid(size=size, topology=topo, device=device, **kw)
+        sediment = None
+        if cfg.get("sediment"):
+            # configs[2] as named: SimpleMultiG sediment under sinking sPOM / bPOM (detritus.jl:35-36 speeds), the
+            # sediment's own AB2 stepper and its first-order upwind bottom flux (test_sediments.jl:37-80 setup)
+            sediment = ob.SimpleMultiGSediment(self.grid)
         if self.kind == "lobster":
-            self.bgc = ob.LOBSTER(self.grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(),
+            self.bgc = ob.LOBSTER(self.grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(), sediment=sediment,
                                   scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
             ranges = synthetic.lobster_range
         elif self.kind == "npzd":
@@ -85,37 +148,46 @@ class Workload:
         elif self.kind == "pisces":
             self.bgc = ob.PISCES(self.grid, scale_negatives=True, surface_photosynthetically_active_radiation=100.0)
             # the synthetic state does not change between steps: with the Newton warm start on, every Ω solve after the
-            # first would converge in one iteration, which no simulation sees ⇒ the bench always solves from pH 8
+            # first would converge in one iteration, which no simulation sees ⇒ the bench always solves cold
             self.bgc.underlying_biogeochemistry.warm_start_carbonate_solve = False
             ranges = ob.pisces.synthetic_range
         self.model = ob.BiogeochemicalModel(self.grid, self.bgc)
         for n, f in self.model.tracers.items():
             lo, hi, log = ranges(n)
-            synthetic.fill_torch(f, n, lo, hi, log)
+            synthetic.fill_torch(f, n, lo, hi, log, rows=fill_rows)
         if self.kind == "pisces":
             ob.pisces.fill_synthetic_auxiliary(self.bgc, self.model)
+        if sediment is not None:
+            for n, f in sediment.fields.items():  # pools Ns, Nf, Nr ∈ [1e-2, 10] (log), SURVEY §8d C3
+                synthetic.fill_torch(f, "sed" + n, 1e-2, 10.0, True)
+            self.model.clock.last_stage_dt = 60.0  # the sediment hook steps its pools with Δt of the last stage
         self.ranges = ranges
         self.cells = self.grid.ncells
-        nt = len(self.model.tracers)
-        nG = sum(1 for n in self.model.tracers if n not in ("T", "S"))
-        self.nG = nG
-        self.tendency_bytes_per_cell = self._tendency_bytes()
-        self.step_kernels = self._kernel_names()
+        self.nG = sum(1 for n in self.model.tracers if n not in ("T", "S"))
+        mods = self.bgc.modifiers if isinstance(self.bgc.modifiers, tuple) else (self.bgc.modifiers,)
+        self.groups = [(m.tracers, m.scalefactors) for m in mods]
+        scaled = []
+        for tn, _ in self.groups:
+            scaled += [t for t in tn if t not in scaled]
+        self.stage_kernels = self._stage_kernels(len(scaled), sediment is not None)
+        self.tendency_bytes_per_cell = self.stage_kernels["tendencies"][1]
+        self.stage_bytes_per_cell = sum(b for _, b, _ in self.stage_kernels.values())
+        self.step_kernels = [k for k, _, _ in self.stage_kernels.values()]
 
-    # ---- algorithmic bytes per cell of the dominant (tendency) kernel, accumulate mode ------------
-    def _tendency_bytes(self):
-        if self.kind == "lobster":
-            return 8 * (7 + 1) + 16 * 10      # read 7 active tracers + PAR, RMW 10 tendencies = 224 B
-        if self.kind == "npzd":
-            return 8 * (5 + 1) + 16 * 4       # N,P,Z,D,T + PAR, RMW 4 tendencies = 112 B
+    def _stage_kernels(self, nscaled, sediment):
+        """marker label → (kernel, ALGORITHMIC bytes per cell — SURVEY §8d's per-unit figures —, what bounds it)."""
         if self.kind == "pisces":
-            return 256 + 16 * 24              # 256 B in, 24 tendencies RMW = 640 B
-        return 40
-
-    def _kernel_names(self):
-        if self.kind in ("lobster", "npzd"):
-            return ["scale_negative_kernel", "par_twoband_kernel", "npd_tendency_kernel"]
-        return ["scale_negative_calcite_kernel", "par_multiband_kernel", "pisces_tendency_kernel"]
+            return {"modifiers": ("scale_negative_calcite_kernel", 8 * nscaled + 16 + 8, "issue / FP64 (Ω solve); HBM roof shown"),
+                    "light": ("par_multiband_kernel<3,DIAG>", 16 + 32, "issue / FP64 (1 log + 6 exp per cell); HBM roof shown"),
+                    "tendencies": ("pisces_tendency_kernel", 256 + 16 * 24, "latency of dependent FP64 chains; HBM roof shown")}
+        npd = {"lobster": 8 * (7 + 1) + 16 * 10, "npzd": 8 * (5 + 1) + 16 * 4}[self.kind]
+        k = {"modifiers": ("scale_negative_kernel", 8 * nscaled, "hbm"),
+             "light": ("par_twoband_kernel", 16, "issue / FP64 (2 pow + 2 exp per cell); HBM roof shown"),
+             "tendencies": ("npd_tendency_kernel", npd, "hbm")}
+        if sediment:  # per COLUMN ≈ 200 B (SURVEY §8d) = 200 / Nz per cell
+            k["sediment"] = ("sediment_state_kernel", 200.0 / self.grid.Nz, "latency (Nx·Ny threads)")
+            k["sediment_tendencies"] = ("sediment_tendency_kernel", 100.0 / self.grid.Nz, "latency (Nx·Ny threads)")
+        return k
 
     def _build_carbon(self, n):
         from oceanbiome_b200 import synthetic
@@ -130,9 +202,10 @@ class Workload:
         self.Alk = lo + (2600.0 - lo) * u("Alk")
         self.out = torch.empty_like(self.DIC)
         self.cc = self.ob.CarbonChemistry(newton_iterations=12)
-        self.tendency_bytes_per_cell = 40
-        self.launches_per_step = 1
+        self.tendency_bytes_per_cell = self.stage_bytes_per_cell = 40
+        self.stage_kernels = {"tendencies": ("carbon_sweep_kernel", 40, "FP64 pipe; HBM roof shown")}
         self.step_kernels = ["carbon_sweep_kernel"]
+        self.groups = []
 
     def capture(self):
         """One stage (all hooks) as a CUDA graph on the current stream; parameters evaluated on the host (day length,
@@ -149,22 +222,38 @@ class Workload:
         return self.graph
 
     # ---- one step of the hot path, inputs resident in HBM -------------------------------------------
-    def step(self, ev=None):
+    def step(self, marks=None):
+        """`marks`: list that receives (label, CUDA event) after every launch group of the stage (first entry: start)."""
+        def mark(label):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((label, e))
         if self.kind == "carbon":
-            if ev:
-                ev[0].record()
+            if marks is not None:
+                mark("start")
             self.cc(DIC=self.DIC, T=self.T, S=self.S, Alk=self.Alk, output="pHᶠ", out=self.out)
-            if ev:
-                ev[1].record()
+            if marks is not None:
+                mark("tendencies")
             return 1
         m = self.model
-        m.biogeochemistry.update_biogeochemical_state(m)
-        if ev:
-            ev[0].record()
-        m.biogeochemistry.update_tendencies(m)
-        if ev:
-            ev[1].record()
+        bgc = m.biogeochemistry
+        if marks is not None:
+            mark("start")
+            bgc.stage_marker = mark
+        bgc.update_biogeochemical_state(m)
+        bgc.update_tendencies(m)
+        bgc.stage_marker = None
         return len(self.step_kernels)
+
+
+def kernel_times(step_marks, table):
+    """Mean duration (ms) of every launch group over the steps, from the marker events recorded inside the timed region."""
+    acc = {}
+    for marks in step_marks:
+        for (_, e0), (label, e1) in zip(marks[:-1], marks[1:]):
+            if label in table:
+                acc.setdefault(label, []).append(e0.elapsed_time(e1))
+    return {k: float(np.mean(v)) for k, v in acc.items()}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -177,7 +266,10 @@ class HostStage:
     its output back."""
 
     def __init__(self, w: Workload, copy_engine: str = "dma", nslabs: int = 0):
+        from oceanbiome_b200.host_stage import HostStagedStage, bind_to_gpu_numa_node
         self.w = w
+        # first-touch the pinned buffers on the NUMA node the GPU hangs off (no-op on single-node hosts)
+        self.numa_bound = bind_to_gpu_numa_node(w.device)
         if w.kind == "carbon":
             self.h_in = [torch.empty(w.n, dtype=torch.float64).pin_memory() for _ in range(4)]
             for h, d in zip(self.h_in, (w.T, w.S, w.DIC, w.Alk)):
@@ -186,7 +278,6 @@ class HostStage:
             self.h2d_bytes = 4 * 8 * w.n
             self.d2h_bytes = 8 * w.n
             return
-        from oceanbiome_b200.host_stage import HostStagedStage
         self.stage = HostStagedStage(w.model, nslabs=nslabs or ((16 if w.grid.Ny >= 256 else 8) if w.grid.Ny >= 64 else 1),
                                      copy_engine=copy_engine)
         self.stage.upload_from_device()
@@ -230,6 +321,18 @@ def pcie_peak_gbs(device, nbytes=1 << 30, reps=3):
 
     run(1)
     return run(reps)
+
+
+def host_memcpy_gbs(nbytes=1 << 29, reps=3):
+    """Host DRAM copy rate of one core (numpy memcpy, read + write bytes): with all ranks running it at once it shows
+    what the shared host memory system leaves each rank."""
+    a = np.ones(nbytes // 8)
+    b = np.empty_like(a)
+    np.copyto(b, a)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        np.copyto(b, a)
+    return 2 * reps * nbytes / (time.perf_counter() - t0) / 1e9
 
 
 # --------------------------------------------------------------------------------------------------
@@ -339,7 +442,7 @@ def fp64_roofline(workload, cells, kernel_ms):
 # --------------------------------------------------------------------------------------------------
 def cpu_sample(name, threads, budget_cells):
     """Time the oracle (one pass per tracer, reference solver, serial-in-z PAR, one pass per group) on a
-    bounded sub-volume of the same workload.  Returns (cells/s, sample description)."""
+    bounded sub-volume of the same workload.  Returns (cells/s, sample description, seconds)."""
     import pyoracle
     from oceanbiome_b200 import synthetic
     import oceanbiome_b200 as ob
@@ -355,43 +458,77 @@ def cpu_sample(name, threads, budget_cells):
         t0 = time.perf_counter()
         pyoracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=2)
         dt = time.perf_counter() - t0
-        return n / dt, f"first {n} cells of the sweep, reference damped Newton (atol 1e-20, max 100 iterations)"
+        return n / dt, f"first {n} cells of the sweep ({n / cfg['n']:.4f} of it), reference damped Newton (atol 1e-20, max 100 iterations)", dt
     Nx, Ny, Nz = cfg["size"]
     ny = max(1, min(Ny, int(budget_cells // (Nx * Nz))))
     nx = Nx if ny >= 1 and Nx * Nz <= budget_cells else max(1, int(budget_cells // Nz))
     topo = ("Periodic", "Periodic" if ny > 1 else "Flat", "Bounded")
     size = (nx, ny, Nz) if ny > 1 else (nx, Nz)
-    ext = cfg["extent"]
-    extent = (ext[0] * nx / Nx, ext[1] * ny / Ny, ext[2]) if ny > 1 else (ext[0] * nx / Nx, ext[2])
-    grid = ob.RectilinearGrid(size=size, extent=extent, topology=topo, device="cpu")
+    Lx, Ly, Lz = cfg["extent"]
+    z = eady_z_faces(Nz, Lz) if cfg.get("z") == "eady" else (-Lz, 0.0)
+    kw = dict(x=(0.0, Lx * nx / Nx), z=z) if ny == 1 else dict(x=(0.0, Lx * nx / Nx), y=(0.0, Ly * ny / Ny), z=z)
+    grid = ob.RectilinearGrid(size=size, topology=topo, device="cpu", **kw)
     og = pyoracle.Grid.like(grid)
     if cfg["model"] in ("lobster", "npzd"):
-        if cfg["model"] == "lobster":
-            bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(), scale_negatives=True)
-            rng = synthetic.lobster_range
-        else:
-            bgc = ob.NPZD(grid, scale_negatives=True)
-            rng = lambda n: synthetic.RANGES_NPZD[n]  # noqa: E731
-        u = bgc.underlying_biogeochemistry
-        names = u.required_biogeochemical_tracers()
-        host = {n: synthetic.fill_numpy(np.zeros(og.parent_shape), og, n, *rng(n)) for n in names}
-        mods = bgc.modifiers if isinstance(bgc.modifiers, tuple) else (bgc.modifiers,)
-        groups = [(m.tracers, m.scalefactors) for m in mods]
-        snames = []
-        for tn, _ in groups:
-            snames += [t for t in tn if t not in snames]
-        cgroups = pyoracle.make_groups(snames, groups)
-        G = [np.zeros(og.parent_shape) for _ in names]
-        PAR = np.zeros(og.parent_shape)
-        t0 = time.perf_counter()
-        pyoracle.scale_negative_tracers(og, [host[n] for n in snames], cgroups)
-        pyoracle.par_twoband(og, bgc.light_attenuation.c_params(), host["P"], 100.0, PAR)
-        pyoracle.npd_tendencies(og, u.c_params(), [host[n] for n in names], PAR, G=G, accumulate=True)
-        dt = time.perf_counter() - t0
+        dt = npd_oracle_stage_seconds(pyoracle, grid, og, cfg)
     else:
         dt, grid = pisces_oracle_stage_seconds(pyoracle, grid, og)
-    return grid.ncells / dt, (f"{grid.Nx}x{grid.Ny}x{grid.Nz} sub-volume of the workload grid, reference launch structure "
-                             "(one pass per tracer / band / group, reference solver)")
+    frac = grid.ncells / (Nx * Ny * Nz)
+    return grid.ncells / dt, (f"{grid.Nx}x{grid.Ny}x{grid.Nz} sub-volume of the workload grid (1/{1 / frac:.0f} of it), reference launch "
+                             "structure (one pass per tracer / band / group, reference solver)"), dt
+
+
+def npd_oracle_stage_seconds(pyoracle, grid, og, cfg):
+    """CPU-baseline leg for the LOBSTER / NPZD workloads: one stage in the reference's launch structure (one scaling pass
+    per group, serial-in-z two-band PAR, the sediment's column passes, one tendency pass per tracer)."""
+    import oceanbiome_b200 as ob
+    from oceanbiome_b200 import synthetic
+    if cfg["model"] == "lobster":
+        bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(), scale_negatives=True)
+        rng = synthetic.lobster_range
+    else:
+        bgc = ob.NPZD(grid, scale_negatives=True)
+        rng = lambda n: synthetic.RANGES_NPZD[n]  # noqa: E731
+    u = bgc.underlying_biogeochemistry
+    names = u.required_biogeochemical_tracers()
+    host = {n: synthetic.fill_numpy(np.zeros(og.parent_shape), og, n, *rng(n)) for n in names}
+    mods = bgc.modifiers if isinstance(bgc.modifiers, tuple) else (bgc.modifiers,)
+    groups = [(m.tracers, m.scalefactors) for m in mods]
+    snames = []
+    for tn, _ in groups:
+        snames += [t for t in tn if t not in snames]
+    cgroups = pyoracle.make_groups(snames, groups)
+    G = [np.zeros(og.parent_shape) for _ in names]
+    PAR = np.zeros(og.parent_shape)
+    sed, keep = None, None
+    if cfg.get("sediment"):
+        sed = ob.SimpleMultiGSediment(grid)
+        pools = {n: synthetic.fill_numpy(np.zeros(og.plane_shape), og, "sed" + n, 1e-2, 10.0, True) for n in sed.fields}
+        plane = lambda: np.zeros(og.plane_shape)  # noqa: E731
+        wf = {}
+        for n in sed.biogeochemistry.sinking_fluxes():
+            w = np.zeros((og.parent_shape[0] + 1,) + og.parent_shape[1:])
+            w[og.Hz:og.Hz + og.Nz] = float(bgc.biogeochemical_drift_velocity(n))
+            wf[n] = w
+        sink = list(sed.biogeochemistry.sinking_fluxes())
+        keep = dict(pools=[pools[n] for n in sed.fields], Gn=[plane() for _ in sed.fields], Gm=[plane() for _ in sed.fields],
+                    tracked=[plane() for _ in sed.tracked_fields], sinking_w=[wf[n] for n in sink])  # referenced until the end
+        sf = pyoracle.sediment_fields(
+            NO3=host["NO₃"], NH4=host["NH₄"], O2=host["O₂"], sinking=[host[n] for n in sink], sinking_w=keep["sinking_w"],
+            pools=keep["pools"], Gn=keep["Gn"], Gm=keep["Gm"], tracked=keep["tracked"],
+            G_coupled=[G[names.index(n)] if n in names else None for n in sed.biogeochemistry.coupled_tracers()])
+        sp = sed.c_params()
+    t0 = time.perf_counter()
+    pyoracle.scale_negative_tracers(og, [host[n] for n in snames], cgroups)
+    pyoracle.par_twoband(og, bgc.light_attenuation.c_params(), host["P"], 100.0, PAR)
+    if sed is not None:
+        pyoracle.sediment_update_state(og, sp, sf, 60.0)
+    pyoracle.npd_tendencies(og, u.c_params(), [host[n] for n in names], PAR, G=G, accumulate=True)
+    if sed is not None:
+        pyoracle.sediment_update_tendencies(og, sp, sf)
+    dt = time.perf_counter() - t0
+    del keep
+    return dt
 
 
 def pisces_oracle_stage_seconds(pyoracle, grid, og):
@@ -400,7 +537,6 @@ def pisces_oracle_stage_seconds(pyoracle, grid, og):
     host twin `og` of `grid`.  TEST/BENCH INFRASTRUCTURE: the oracle is passed in by the caller."""
     import time as _time
 
-    import oceanbiome_b200 as ob
     from oceanbiome_b200 import synthetic
     from oceanbiome_b200.pisces import PISCES, TRACERS, DepthDependantSinkingSpeed, synthetic_range
     bgc = PISCES(grid, scale_negatives=True)
@@ -432,6 +568,35 @@ def pisces_oracle_stage_seconds(pyoracle, grid, og):
     return _time.perf_counter() - t0, grid
 
 
+def reference_budget(name):
+    """Cells of the bounded sample the reference arm times per step: ≥ 1/64 of the workload."""
+    cfg = workload_table()[name][1]
+    if cfg["model"] == "carbon":
+        return cfg["n"] // 32
+    Nx, Ny, Nz = cfg["size"]
+    total = Nx * Ny * Nz
+    if cfg["model"] == "pisces":
+        return max(total // 64, Nx * Nz)
+    return max(total // 8, Nx * Nz) if total > 4_000_000 else total
+
+
+def workload_cells(name):
+    cfg = workload_table()[name][1]
+    return cfg["n"] if cfg["model"] == "carbon" else int(np.prod(cfg["size"]))
+
+
+def fused_cpu_sample(name, threads, budget_cells):
+    """The second CPU column of BASELINE.md §3: the GPU kernels' FUSED algorithm (one pass over the cells, every shared
+    sub-model evaluated once, fixed-iteration Newton) compiled for the host — separates the algorithmic gain from the
+    hardware gain.  Needs bench_ref/libobm_fused_host.so (bench_ref/Makefile); None when it is not built."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "bench_ref"))
+        import fused_host
+    except Exception:
+        return None
+    return fused_host.sample(name, threads, budget_cells, workload_table()[name][1])
+
+
 def run_reference_arm(args, name):
     """--impl reference: the reference's CPU implementation of the path (here: its C restatement — Julia
     is not in the image) with all host threads, bounded sample per step."""
@@ -439,26 +604,71 @@ def run_reference_arm(args, name):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    desc, cfg = workload_table()[name]
-    budget = 4_000_000 if cfg["model"] != "pisces" else 400_000
-    vals = []
+    budget = reference_budget(name)
+    vals, secs = [], []
     for s in range(args.warmup + args.steps):
-        v, sample = cpu_sample(name, threads, budget)
+        v, sample, dt = cpu_sample(name, threads, budget)
         if s >= args.warmup:
             vals.append(v)
+            secs.append(dt)
     value = float(np.mean(vals)) / 1e9
+    world = max(1, args.gpus)
     line = {
         "impl": "reference", "metric": "BGC tendency Gcell-updates/s", "value": value, "unit": "Gcell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * budget / (value * 1e9), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic", "config": {"workload": name, "description": desc},
-        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": threads, "kind": "port", "sample": sample},
+        # the time ONE stage of the whole workload grid would take at the sampled rate (the sample's own time is below)
+        "ms_per_step": 1e3 * workload_cells(name) / (value * 1e9), "higher_is_better": True,
+        "scaling": config_dict(name, world, args.scaling)["scaling"], "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(name, world, args.scaling),
+        "cpu_baseline": {"value": value, "unit": "Gcell-updates/s", "cores": threads, "kind": "port", "sample": sample,
+                         "sample_ms": 1e3 * float(np.mean(secs)),
+                         "note": "C restatement of the reference algorithm and launch structure (oracle/): Julia is not in the image"},
         "e2e": {"value": value, "unit": "Gcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
+def inventory_check(w, diag, rank, world, rows_info):
+    """The inventory path (obm_inventory → all-reduce) against the oracle's serial sum, on a bounded set of cells: the
+    first R rows of every rank's slab.  The device side is the real thing — kernel on the sub-range, NCCL all-reduce —
+    and rank 0 regenerates exactly those rows of the global synthetic field on the host for the oracle."""
+    import torch.distributed as dist
+    g = w.grid
+    R = min(2, g.Ny)
+    with g.restrict(0, R):
+        got = diag.local().clone()
+    if world > 1:
+        dist.all_reduce(got, op=dist.ReduceOp.SUM)
+    got = got.cpu().numpy()
+    if rank != 0:
+        return None
+    import pyoracle
+    from oceanbiome_b200 import synthetic
+    import oceanbiome_b200 as ob
+    names = diag.names
+    cg = pyoracle.make_groups(names, diag.groups)
+    want = np.zeros(len(diag.groups))
+    mag = np.zeros(len(diag.groups))
+    ny_local = g.Ny
+    nyg = rows_info[2] if rows_info else g.Ny
+    for r in range(world if rows_info else 1):
+        sub = ob.RectilinearGrid(size=(g.Nx, R, g.Nz), x=(0.0, g.Lx), y=(0.0, g.dy * R), z=g.zf, device="cpu") if g.Ny > 1 else None
+        if sub is None:
+            return {"skipped": "flat y"}
+        og = pyoracle.Grid.like(sub)
+        fields = [synthetic.fill_numpy(np.zeros(og.parent_shape), og, n, *w.ranges(n), rows=(r * ny_local, nyg)) for n in names]
+        vol = np.zeros(og.parent_shape)
+        og.interior(vol)[...] = (g.dz * g.dx * g.dy).reshape(-1, 1, 1)
+        want += pyoracle.inventory(og, fields, cg, cell_volume=vol)
+        mag += pyoracle.inventory(og, [np.abs(f) for f in fields],
+                                  pyoracle.make_groups(names, [(tn, tuple(abs(x) for x in sf)) for tn, sf in diag.groups]), cell_volume=vol)
+    err = float(np.max(np.abs(got - want) / mag))
+    return {"cells": int(g.Nx * R * g.Nz * (world if rows_info else 1)), "rows_per_rank": R, "max_err_over_sum_abs_terms": err,
+            "tolerance": 1e-12, "ok": bool(err <= 1e-12),
+            "how": "obm_inventory on the first rows of every slab + all-reduce vs the oracle's serial (long double) sum of the same cells"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -467,10 +677,12 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(workload_table()))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink Ny (or n) for quick checks; not a bench number")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak (default, the driver's contract): one full slab per GPU; strong: the N=1 grid split into N y-slabs")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the workload's ONE grid split into N y-slabs (BASELINE configs[3]); weak: one full grid per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling sub-record of a multi-GPU run")
+    ap.add_argument("--no-inventory", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the stage as one CUDA graph (auto: when the working set fits L2, i.e. the stage is launch-bound)")
     ap.add_argument("--e2e-slabs", type=int, default=0, help="x-y slabs of the e2e pipeline (0: default)")
@@ -489,7 +701,7 @@ def main():
     os.dup2(2, 1)
 
     import oceanbiome_b200 as ob
-    from oceanbiome_b200.distributed import init_distributed
+    from oceanbiome_b200.distributed import InventoryDiagnostic, init_distributed
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: oceanbiome.jl_b200 has no CPU fallback")
@@ -498,9 +710,13 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
-    if args.scaling == "strong":  # SURVEY §8d asks for both: the global grid stays that of N = 1, each rank owns Ny / N rows
-        args.scale = args.scale / world
-    w = Workload(name, device, args.scale)
+    mode, nrows = shards(name, world, args.scaling)
+    cfg = workload_table()[name][1]
+    rows_info = None
+    if mode == "strong" and world > 1:
+        nyg = max(world, int(cfg["size"][1] * args.scale) // world * world)
+        rows_info = (rank * (nyg // world), nyg // world, nyg)
+    w = Workload(name, device, args.scale, rows=rows_info)
     sampler = ClockSampler(device.index or 0)
 
     def barrier():
@@ -508,52 +724,102 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(device)
 
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    def timed_steps(wl, steps, use_graph, small, flush, marks_out=None, extra=None):
+        """K steps between two events on the launching stream (per-step pairs around the L2 flush for small working
+        sets); `extra()` runs after every step inside the region.  → (ms on this rank, launches)."""
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches = 0
+        t0.record()
+        for s in range(steps):
+            if small:
+                flush.fill_(float(s))
+                sev[s][0].record()
+            if use_graph:
+                wl.graph.replay()
+                launches += len(wl.step_kernels)
+            else:
+                marks = [] if marks_out is not None else None
+                launches += wl.step(marks)
+                if marks_out is not None:
+                    marks_out.append(marks)
+            if extra is not None:
+                launches += extra()
+            if small:
+                sev[s][1].record()
+        t1.record()
+        barrier()
+        return (sum(a.elapsed_time(b) for a, b in sev) if small else t0.elapsed_time(t1)), launches
+
     for _ in range(args.warmup):
         w.step()
     barrier()
     # A working set that fits the 126 MB L2 (configs C1, C2) is (a) evicted before every step by a 256 MB write that
     # is left out of the timing, and (b) launch-bound: its stage — three tiny launches — is replayed as ONE CUDA
     # graph, which removes the host's per-launch cost (≈ 35 µs per hook call from Python) the way the box-model driver
-    # does.  Large workloads keep one event pair around all K steps, as before.
+    # does.  Large workloads keep one event pair around all K steps.
     small = w.cells * w.tendency_bytes_per_cell <= 4e8
     use_graph = args.graph == "on" or (args.graph == "auto" and small and w.kind != "carbon")
     if use_graph:
         w.capture()
     flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device=device) if small else None
-    # ---- timed region: K steps, CUDA events on the launching stream --------------------------------
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    # ---- timed region A: K stages, CUDA events on the launching stream, every launch group marked -----------------
+    step_marks = []
     sampler.start()
-    launches = 0
-    t0.record()
-    for s in range(args.steps):
-        if small:
-            flush.fill_(float(s))
-            sev[s][0].record()
-        if use_graph:
-            w.graph.replay()
-            launches += len(w.step_kernels)
-        else:
-            launches += w.step(ev[s])
-        if small:
-            sev[s][1].record()
-    t1.record()
-    barrier()
+    ms, launches = timed_steps(w, args.steps, use_graph, small, flush, marks_out=None if use_graph else step_marks)
     sampler.stop_flag = True
-    ms = sum(a.elapsed_time(b) for a, b in sev) if small else t0.elapsed_time(t1)
-    if use_graph:  # the tendency kernel's own time: a few eager steps with an event pair around it
+    if use_graph:  # per-kernel times of a graphed stage: a few eager steps with the markers (they include launch latency)
         for s in range(args.steps):
             flush.fill_(float(s)) if small else None
-            w.step(ev[s])
+            marks = []
+            w.step(marks)
+            step_marks.append(marks)
         torch.cuda.synchronize(device)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
-    total_cells = w.cells * world
-    value = total_cells * args.steps / (ms * 1e-3) / 1e9
+    ktimes = kernel_times(step_marks, w.stage_kernels)
+    kernel_ms = ktimes["tendencies"]
+    ms = max_over_ranks(ms)
+    global_cells = w.cells * world
+    value = global_cells * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- timed region B: the same stages with the conservation diagnostic every stage ------------------------------
+    inventory = None
+    if not args.no_inventory and w.groups and w.kind != "carbon":
+        diag = InventoryDiagnostic(w.grid, w.model.tracers, w.groups)
+        inv_ev = []
+
+        def run_inventory():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            diag()  # obm_inventory (2 launches) + all-reduce of len(groups) doubles
+            b.record()
+            inv_ev.append((a, b))
+            return 2
+        for _ in range(2):
+            w.step(); run_inventory()
+        barrier()
+        inv_ev.clear()
+        ms_b, _ = timed_steps(w, args.steps, False, small, flush, extra=run_inventory)
+        ms_b = max_over_ranks(ms_b)
+        inv_ms = max_over_ranks(float(np.mean([a.elapsed_time(b) for a, b in inv_ev])))
+        totals = diag().clone().cpu().numpy().tolist()
+        again = diag().clone().cpu().numpy().tolist()
+        inventory = {"groups": len(w.groups), "tracers_read": len(diag.names),
+                     "collective": f"all_reduce(SUM) of {len(w.groups)} doubles over {'NCCL' if world > 1 else 'no other rank (N = 1)'}",
+                     "every": "stage", "ms_per_stage_inventory_and_allreduce": inv_ms,
+                     "ms_per_step_with_inventory": ms_b / args.steps,
+                     "value_with_inventory": global_cells * args.steps / (ms_b * 1e-3) / 1e9,
+                     "algorithmic_bytes_per_cell": 8 * len(diag.names),
+                     "GBs_per_gpu": 8 * len(diag.names) * w.cells / (inv_ms * 1e-3) / 1e9,
+                     "totals": totals, "run_to_run_identical": totals == again,
+                     "check": inventory_check(w, diag, rank, world, rows_info)}
 
     # ---- end-to-end through the public API with host buffers ------------------------------------------
     e2e = None
@@ -567,8 +833,8 @@ def main():
             local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
             budget = 0.5 * psutil.virtual_memory().available / max(1, local_world)
             if need > budget:
-                scale_e2e = max(1.0 / w.grid.Ny, budget / need) * args.scale
-                we = Workload(name, device, scale_e2e)
+                ny_e = max(1, int(w.grid.Ny * budget / need))
+                we = Workload(name, device, 1.0, rows=(0, ny_e, ny_e))
                 note = f"host RAM limits pinned buffers: e2e grid reduced to {we.grid.Nx}x{we.grid.Ny}x{we.grid.Nz} per GPU"
         hs = HostStage(we, args.copy_engine, args.e2e_slabs)
         for _ in range(2):
@@ -581,21 +847,68 @@ def main():
             hs.step()
         b.record()
         barrier()
-        ems = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ems], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = t.item()
+        ems = max_over_ranks(a.elapsed_time(b))
         e2e = {"value": we.cells * world * k / (ems * 1e-3) / 1e9, "unit": "Gcell-updates/s",
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k,
-               "cells_per_gpu": we.cells, "copy_engine": args.copy_engine,
+               "cells_per_gpu": we.cells, "copy_engine": args.copy_engine, "numa_bound": bool(hs.numa_bound),
                "pcie_GBs_each_direction": max(hs.h2d_bytes, hs.d2h_bytes) * k / (ems * 1e-3) / 1e9}
-        if rank == 0:  # the leg's own roofline: both copy directions busy, measured here on this box
-            peak = pcie_peak_gbs(device)
-            e2e["pcie_peak_GBs_each_direction"] = peak
-            e2e["pcie_frac"] = e2e["pcie_GBs_each_direction"] / peak
+        # the leg's own roofline, measured the way the leg runs: EVERY rank copies in both directions at the same time
+        del hs
+        barrier()
+        peak_c = pcie_peak_gbs(device)
+        hostbw_c = host_memcpy_gbs()
+        barrier()
+        if world > 1:
+            t = torch.tensor([peak_c, hostbw_c], dtype=torch.float64, device=device)
+            allp = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allp, t)
+            peaks = [x[0].item() for x in allp]
+            hostbws = [x[1].item() for x in allp]
+        else:
+            peaks, hostbws = [peak_c], [hostbw_c]
+        if world > 1:  # and with the other ranks idle, for the contrast
+            if rank == 0:
+                solo, host_solo = pcie_peak_gbs(device), host_memcpy_gbs()
+            barrier()
+        else:
+            solo, host_solo = peak_c, hostbw_c
+        if rank == 0:
+            e2e["pcie_peak_GBs_each_direction"] = float(np.mean(peaks))
+            e2e["pcie_peak_per_rank"] = [round(p, 2) for p in peaks]
+            e2e["pcie_peak_how"] = (f"two 1 GiB pinned copies (H2D and D2H) in flight on each of the {world} ranks AT THE SAME TIME; "
+                                    "mean over ranks")
+            e2e["pcie_frac"] = e2e["pcie_GBs_each_direction"] / e2e["pcie_peak_GBs_each_direction"]
+            e2e["pcie_peak_solo_GBs_each_direction"] = solo
+            e2e["host_memcpy_GBs_per_rank_concurrent"] = float(np.mean(hostbws))
+            e2e["host_memcpy_GBs_solo"] = host_solo
+            e2e["limiter"] = ("PCIe link of the one GPU" if world == 1 else
+                              f"shared host side: {world} ranks copying at once get {np.mean(peaks):.1f} GB/s per direction each "
+                              f"({world * np.mean(peaks):.0f} GB/s per direction in aggregate) against {solo:.1f} GB/s for one rank alone")
         if note:
             e2e["note"] = note
+        if we is not w:
+            del we
+
+    # ---- weak-scaling sub-record (N > 1): one full-size grid per GPU ---------------------------------------------------
+    weak = None
+    if world > 1 and mode == "strong" and not args.no_weak:
+        cells_strong = w.cells
+        del w
+        if inventory is not None:
+            del diag
+        torch.cuda.empty_cache()
+        ww = Workload(name, device, args.scale)
+        for _ in range(args.warmup):
+            ww.step()
+        barrier()
+        kw_steps = max(3, min(args.steps, 10))
+        wms, _ = timed_steps(ww, kw_steps, False, False, None)
+        wms = max_over_ranks(wms)
+        weak = {"scaling": "weak", "cells_per_gpu": ww.cells, "steps": kw_steps, "ms_per_step": wms / kw_steps,
+                "value": ww.cells * world * kw_steps / (wms * 1e-3) / 1e9, "unit": "Gcell-updates/s"}
+        w_cells, w_obj = cells_strong, ww
+    else:
+        w_cells, w_obj = w.cells, w
 
     if rank != 0:
         if world > 1:
@@ -603,34 +916,45 @@ def main():
         return
 
     peak, peak_src = measured_peaks()
-    alg_bytes = w.tendency_bytes_per_cell * w.cells
+    alg_bytes = w_obj.tendency_bytes_per_cell * w_cells
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic, traffic_src = ncu_traffic(name, w.cells)
-    roofline = {"bound": "hbm", "kernel": w.step_kernels[-1] if w.step_kernels else None, "achieved": achieved, "peak": peak,
+    traffic, traffic_src = ncu_traffic(name, w_cells)
+    step_ms = ms / args.steps
+    kernels = []
+    for label, (kname, nbytes, bound) in w_obj.stage_kernels.items():
+        if label in ktimes:
+            gbs = nbytes * w_cells / (ktimes[label] * 1e-3) / 1e9
+            kernels.append({"kernel": kname, "hook": label, "algorithmic_bytes_per_cell": nbytes, "ms": ktimes[label],
+                            "achieved": gbs, "unit": "GB/s", "frac": gbs / peak, "bound": bound,
+                            "share_of_step": None if use_graph else ktimes[label] / step_ms})
+    stage_gbs = w_obj.stage_bytes_per_cell * w_cells / (step_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": w_obj.stage_kernels["tendencies"][0], "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                "algorithmic_bytes_per_cell": w.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_cell": w_obj.tendency_bytes_per_cell, "kernel_ms": kernel_ms,
                 # graph mode: kernel_ms comes from separate eager launches (it includes their launch latency, which the
                 # graphed stage does not pay), so a share of the graphed step would be meaningless
-                "kernel_share_of_step": None if use_graph else kernel_ms / (ms / args.steps),
-                "fp64": fp64_roofline(name, w.cells, kernel_ms)}
-    cpu = None
+                "kernel_share_of_step": None if use_graph else kernel_ms / step_ms,
+                "fp64": fp64_roofline(name, w_cells, kernel_ms),
+                # the whole stage (every launch of the step, gaps included) against the same HBM peak
+                "stage": {"algorithmic_bytes_per_cell": w_obj.stage_bytes_per_cell, "ms": step_ms, "achieved": stage_gbs,
+                          "unit": "GB/s", "frac": stage_gbs / peak,
+                          "how": "sum of the kernels' algorithmic bytes x cells / ms_per_step (per GPU; max over ranks)"},
+                "kernels": kernels}
+    cpu = cpu_fused = None
     if not args.no_cpu_baseline and world == 1:
-        desc, cfg = workload_table()[name]
         # ≈ 10 s of one host core on the GPU box: PISCES ≈ 0.13, LOBSTER ≈ 2, the carbonate solve ≈ 0.4 Mcell/s
         budget = {"pisces": 1_500_000, "carbon": 4_000_000}.get(cfg["model"], 8_000_000)
-        v, sample = cpu_sample(name, 1, budget)
+        v, sample, _ = cpu_sample(name, 1, budget)
         cpu = {"value": v / 1e9, "unit": "Gcell-updates/s", "cores": 1, "kind": "port", "sample": sample}
+        cpu_fused = fused_cpu_sample(name, 1, budget)
     line = {
         "metric": "BGC tendency Gcell-updates/s", "value": value, "unit": "Gcell-updates/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": name, "description": w.description, "cells_per_gpu": w.cells,
-                   "l2": "inputs larger than L2 (no flush needed)" if not small
-                         else "working set fits L2: evicted by a 256 MB write before every step (not timed); time = sum of per-step event pairs",
-                   "cuda_graph": bool(use_graph),
-                   "parallelism": f"xy-slab x{world}, no data-path collective",
-                   "carbonate_solve": "cold start from pH 8 every step (warm start disabled: static synthetic state)"},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": mode if world > 1 else args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(name, world, args.scaling),
+        "cells_per_gpu": w_cells, "cuda_graph": bool(use_graph),
         "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        "cpu_baseline_fused": cpu_fused, "inventory": inventory, "weak": weak,
     }
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -29,6 +29,14 @@ class Biogeochemistry:
         self.particles = particles
         self.modifiers = modifiers
         self.fuse_state_update = True  # False: one launch per reference step, in the reference's order
+        # callable(label) invoked after each launch group of a stage ("modifiers", "light", "state", "sediment",
+        # "tendencies", "sediment_tendencies", "particles") — bench.py records a CUDA event there to time every kernel
+        # inside the timed region; None costs nothing
+        self.stage_marker = None
+
+    def _mark(self, label):
+        if self.stage_marker is not None:
+            self.stage_marker(label)
 
     # ---- forwarding (OceanBioME.jl:122-131) -------------------------------------------------------
     def required_biogeochemical_tracers(self):
@@ -59,6 +67,7 @@ class Biogeochemistry:
         u = self.underlying_biogeochemistry
         epilogue = u.calcite_saturation_arguments(model) if (self.fuse_state_update and hasattr(u, "calcite_saturation_arguments")) else None
         fused = _update_modifiers(model, self.modifiers, stream, epilogue)
+        self._mark("modifiers")
         # PISCES: zₑᵤ and the mixed-layer mean PAR ride in the launch of the multi-band PAR scan
         light_done = False
         if self.light_attenuation is not None:
@@ -71,12 +80,15 @@ class Biogeochemistry:
                 light_done = True
             else:
                 self.light_attenuation.update_biogeochemical_state(model, stream)
+        self._mark("light")
         if fused or light_done:
             u.update_biogeochemical_state(model, stream, calcite_saturation_done=fused, light_state_done=light_done)
         else:
             u.update_biogeochemical_state(model, stream)
+        self._mark("state")
         if self.sediment is not None:
             self.sediment.update_biogeochemical_state(model, stream)
+            self._mark("sediment")
 
     # ---- update_tendencies!(bgc, model) — OceanBioME.jl:148-152 -----------------------------------
     def update_tendencies(self, model, stream: Optional[int] = None):
@@ -86,10 +98,13 @@ class Biogeochemistry:
         self.underlying_biogeochemistry.compute_tendencies(model.grid, model.tracers,
                                                            self.biogeochemical_auxiliary_fields(), model.Gn,
                                                            accumulate=True, stream=stream, time=model.clock.time)
+        self._mark("tendencies")
         if self.sediment is not None:
             self.sediment.update_tendencies(self, model, stream)
+            self._mark("sediment_tendencies")
         if self.particles is not None:  # OceanBioME.jl:150: update_tendencies!(bgc, bgc.particles, model)
             self.particles.update_tendencies(self, model, stream)
+            self._mark("particles")
 
     def __call__(self, *args):
         """Per-point callable `bgc(i, j, k, grid, Val(name), clock, fields)` — reduced to zero(grid)

@@ -23,16 +23,30 @@
 namespace obm {
 namespace cc {
 
-// exp of the solve: the library exp.  (The lean exp of obm_common.cuh, -DOBM_CC_EXP=1, was measured here: its four
-// extra FP64 instructions and 8 more registers cost the fused scaling + Ω kernel 6 %, profiles/r02_kernel_variants.txt.)
+// exp / log of the solve.  OBM_CC_EXP: 0 the library exp; 1 exp_lean of obm_common.cuh (even / odd Horner, out-of-line
+// library fall-back: measured r02, +6 % on the fused scaling + Ω kernel); 2 exp_horner below — plain degree-13 Horner
+// (17 FP64 instructions, one constant-bank operand each), range guard as ONE integer compare, the library exp inline in
+// the cold branch (no call, so no ABI register constraints on the hot path).  OBM_CC_LOG: 0 library log; 1 log_lean.
 #ifndef OBM_CC_EXP
-#define OBM_CC_EXP 0
+#define OBM_CC_EXP 2
+#endif
+#ifndef OBM_CC_LOG
+#define OBM_CC_LOG 1
 #endif
 __device__ __forceinline__ double cexp(double x) {
 #if OBM_CC_EXP == 0
     return exp(x);
-#else
+#elif OBM_CC_EXP == 1
     return exp_lean(x);
+#else
+    return exp_horner(x);
+#endif
+}
+__device__ __forceinline__ double clog(double x) {
+#if OBM_CC_LOG == 0
+    return log(x);
+#else
+    return log_lean(x);
 #endif
 }
 
@@ -85,13 +99,13 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     constexpr double LN10 = 2.302585092994045684;
     const double T = Tc_in + KD(273.15);
     const double invT = rcp_fast(T);
-    const double logT = log(T);
+    const double logT = clog(T);
     const double sqS = sqrt(S);
     const double S15 = S * sqS;
     const double Is = KD(19.924) * S * rcp_fast(1000.0 + KD(-1.005) * S);  // :341
     const double sqIs = sqrt(Is);
     const double Is15 = Is * sqIs;
-    const double logS1 = log(1 + KD(-0.001005) * S);
+    const double logS1 = clog(1 + KD(-0.001005) * S);
     double Tc = 0, inv_RT = 0;
     if (HAS_P) {
         Tc = T - KD(273.15);
@@ -202,6 +216,18 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 
 // solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]: Newton on x = ln[H⁺] carried multiplicatively (H ← H·e^(−Δx)),
 // step clamped to one pH unit, at most `iterations` steps from H0.
+// OBM_CC_TOL: the warp-uniform exit threshold on |Δx|.  Newton converges quadratically here with a measured constant
+// |e₊| ≈ 0.30·Δx² in ln H (sea-water states; ≤ 1 over the robust box), so leaving after a step below 2·10⁻⁶ puts the
+// root within ≈ 10⁻¹² in ln H, 5·10⁻¹³ in pH — two orders inside the stated 10⁻¹⁰.
+// OBM_CC_POLYEXP: once every lane's step is below 1/8 the factor e^(−Δx) is its degree-5 Taylor polynomial (5 FMAs
+// instead of an exp); the polynomial's own error, Δx⁶/720, is part of the NEXT iterate's error like the Newton remainder
+// and vanishes with it — the root is unchanged.
+#ifndef OBM_CC_TOL
+#define OBM_CC_TOL 2e-6
+#endif
+#ifndef OBM_CC_POLYEXP
+#define OBM_CC_POLYEXP 1
+#endif
 __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, bool need_phosphate, bool need_silicate,
                                           double H0, int iterations) {
     constexpr double LN10 = 2.302585092994045684;
@@ -213,25 +239,52 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
         double dx = f * rcp_fast(Hdf);
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
-        H *= cexp(-dx);
-        // Warp-uniform early exit (no divergence): once every lane's step is below 1e-7 the quadratic convergence
-        // of Newton puts the next iterate within ~1e-14 of the root; NaN lanes count as converged (they stay NaN).
-        if (__all_sync(mask, !(fabs(dx) >= KD(1e-7)))) break;
+        const double adx = fabs(dx);
+#if OBM_CC_POLYEXP
+        if (__all_sync(mask, adx < 0.125)) {  // warp-uniform; a NaN lane sends its warp through the exp (and stays NaN)
+            double q = fma(KD(-1.0 / 120), dx, KD(1.0 / 24));
+            q = fma(q, dx, KD(-1.0 / 6));
+            q = fma(q, dx, 0.5);
+            q = fma(q, dx, -1.0);
+            H = fma(H * dx, q, H);  // H (1 − Δx + Δx²/2 − Δx³/6 + Δx⁴/24 − Δx⁵/120)
+        } else
+#endif
+            H *= cexp(-dx);
+        // Warp-uniform early exit (no divergence): once every lane's step is below the threshold the quadratic
+        // convergence of Newton puts this iterate within ~1e-12 of the root; NaN lanes count as converged (they stay NaN).
+        if (__all_sync(mask, !(adx >= KD(OBM_CC_TOL)))) break;
     }
     return H;
 }
 
 // Where the iteration starts when there is no stored [H⁺]: the positive root of the carbonate-alkalinity quadratic
-//   A_C H² + K1 (A_C − DIC) H + K1 K2 (A_C − 2 DIC) = 0,   A_C = Alk − B_T K_B / (K_B + H_init)
-// (bicarbonate + carbonate only, borate evaluated at the reference's initial guess H_init = 10⁻⁸), which is within a
-// few hundredths of a pH unit of the root for sea water: ≈ 3 Newton steps instead of ≈ 5–6 from pH 8.  The reference
-// starts every solve at pH 8 (carbon_chemistry.jl:121); only the starting point differs, not the root.
-__device__ __forceinline__ double initial_H(const Constants& c, const Totals& t, double H_init) {
-    const double AC = t.Alk - t.boron * c.KB * rcp_fast(c.KB + H_init);
+//   A_C H² + K1 (A_C − DIC) H + K1 K2 (A_C − 2 DIC) = 0,   A_C = Alk − (every other species at the previous estimate)
+// first with borate alone at the reference's initial guess H_init = 10⁻⁸ (carbon_chemistry.jl:121), then OBM_CC_INIT
+// more times with borate, silicate, OH⁻ and free H⁺ evaluated at the estimate just obtained.  The plain quadratic is
+// 0.07 pH units off on average for sea water (0.14 at worst: borate alkalinity moves with pH) and Newton then needs four
+// steps; two refinements (≈ 55 instructions each, a third of a Newton step with its derivative and exponential) leave
+// ≤ 0.02 pH units and three steps reach 10⁻¹⁴.  Only the starting point differs from the reference, not the root.
+#ifndef OBM_CC_INIT
+#define OBM_CC_INIT 2
+#endif
+__device__ __forceinline__ double quadratic_H(const Constants& c, const Totals& t, double AC) {
     const double b = c.K1 * (AC - t.DIC);
     const double disc = b * b - 4.0 * AC * (c.K1 * c.K2) * (AC - 2.0 * t.DIC);
-    const double H0 = (sqrt(disc) - b) * rcp_fast(2.0 * AC);
-    return (H0 > KD(1e-12) && H0 < KD(1e-3)) ? H0 : H_init;  // NaN (disc < 0, AC ≤ 0 …) fails both comparisons
+    return (sqrt(disc) - b) * rcp_fast(2.0 * AC);
+}
+__device__ __forceinline__ double initial_H(const Constants& c, const Totals& t, bool need_silicate, double H_init) {
+    // an estimate outside pH 3 … 12 (or NaN: disc < 0, A_C ≤ 0 … fail both comparisons) is not taken
+    auto plausible = [](double H) { return H > KD(1e-12) && H < KD(1e-3); };
+    double H0 = quadratic_H(c, t, t.Alk - t.boron * c.KB * rcp_fast(c.KB + H_init));
+    H0 = plausible(H0) ? H0 : H_init;
+#pragma unroll
+    for (int r = 0; r < OBM_CC_INIT; r++) {
+        double AC = t.Alk - t.boron * c.KB * rcp_fast(c.KB + H0) - c.KW * rcp_fast(H0) + H0 * c.isd;
+        if (need_silicate) AC -= t.silicate * c.KSi * rcp_fast(c.KSi + H0);
+        const double Hn = quadratic_H(c, t, AC);
+        H0 = plausible(Hn) ? Hn : H0;
+    }
+    return H0;
 }
 
 // K0 — equilibrium_constants.jl:65-80
@@ -285,7 +338,7 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
     } else {
         // warm start: [H⁺] kept from the previous call on this cell, if it is a plausible value (pH 2 … 13)
         double H0 = H_io ? *H_io : 0.0;
-        if (!(H0 > KD(1e-13) && H0 < KD(1e-2))) H0 = initial_H(c, t, H_init);
+        if (!(H0 > KD(1e-13) && H0 < KD(1e-2))) H0 = initial_H(c, t, has_sil, H_init);
         H = solve_H(c, t, has_phos, has_sil, H0, iterations);
         if (H_io) *H_io = H;
     }

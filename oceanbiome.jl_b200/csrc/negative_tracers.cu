@@ -97,7 +97,10 @@ struct ScaleOmegaArgs {
     double H_init;
 };
 
-__global__ void __launch_bounds__(SN_BLOCK) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
+#ifndef OBM_SN_MIN_BLOCKS
+#define OBM_SN_MIN_BLOCKS 8  // 64 registers: 32 warps per SM for the issue-bound solve
+#endif
+__global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
     int i, j, k;
     if (!thread_cell(a.s.d, i, j, k)) return;
@@ -130,6 +133,9 @@ __global__ void __launch_bounds__(256) zero_negative_kernel(const __grid_constan
 }
 
 // ---- inventory: out[g] = Σ_cells (Σ_f sf·c_f)·V — deterministic two-level tree, no double atomics ----
+// ONE pass over the cells for all groups: every distinct tracer is read once per cell (8 B × ntracers, HBM-bound), the
+// groups are rows of a dense weight table W[g][t] (0 where tracer t is not a member of group g) held in the constant
+// bank.  Blocks walk (j, k) rows, threads stride along x: coalesced, one integer division per ROW.
 constexpr int INV_BLOCKS = 148 * 4;
 constexpr int INV_THREADS = 256;
 
@@ -137,7 +143,7 @@ struct InvArgs {
     GridDims d;
     int ntracers, ngroups;
     const double* tracers[OBM_MAX_SCALE_TRACERS];
-    obm_scale_group groups[OBM_MAX_SCALE_GROUPS];
+    double w[OBM_MAX_SCALE_GROUPS][OBM_MAX_SCALE_TRACERS];
     const double* volume;
     double uniform_volume;
     double* partial;  // [ngroups][INV_BLOCKS]
@@ -145,35 +151,49 @@ struct InvArgs {
 };
 
 __global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __grid_constant__ InvArgs a) {
-    __shared__ double red[INV_THREADS / 32];
+    __shared__ double red[OBM_MAX_SCALE_GROUPS][INV_THREADS / 32];
     const GridDims& d = a.d;
     const int nx = d.i1 - d.i0, ny = d.j1 - d.j0;
-    const long long total = (long long)nx * ny * d.Nz;
+    const int rows = ny * d.Nz;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int q = 0; q < a.ngroups; q++) {
-        const obm_scale_group& g = a.groups[q];
-        double acc = 0.0;
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-            const long long row = t / nx;
-            const int i = d.i0 + (int)(t - row * nx);
-            const int k = (int)(row / ny);
-            const int j = d.j0 + (int)(row - (long long)k * ny);
-            const long long idx = cell_index(d, i, j, k);
-            double s = 0.0;
-            for (int m = 0; m < g.n; m++) s += g.scalefactor[m] * a.tracers[g.index[m]][idx];
-            acc += s * (a.volume ? a.volume[idx] : a.uniform_volume);
-        }
+    double acc[OBM_MAX_SCALE_GROUPS];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) red[warp] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            double v = lane < INV_THREADS / 32 ? red[lane] : 0.0;
+    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) acc[g] = 0.0;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int k = row / ny;
+        const int j = d.j0 + (row - k * ny);
+        for (int ii = threadIdx.x; ii < nx; ii += INV_THREADS) {
+            const long long idx = cell_index(d, d.i0 + ii, j, k);
+            double s[OBM_MAX_SCALE_GROUPS];
+#pragma unroll
+            for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) s[g] = 0.0;
+            for (int t = 0; t < a.ntracers; t++) {
+                const double v = __ldcs(a.tracers[t] + idx);  // streamed: read once
+#pragma unroll
+                for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++)
+                    if (g < a.ngroups) s[g] = fma(a.w[g][t], v, s[g]);
+            }
+            const double V = a.volume ? a.volume[idx] : a.uniform_volume;
+#pragma unroll
+            for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) acc[g] = fma(s[g], V, acc[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) {
+        double v = acc[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[g][warp] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) {
+            double v = lane < INV_THREADS / 32 ? red[g][lane] : 0.0;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) a.partial[q * INV_BLOCKS + blockIdx.x] = v;
+            if (lane == 0 && g < a.ngroups) a.partial[g * INV_BLOCKS + blockIdx.x] = v;
         }
-        __syncthreads();
     }
 }
 
@@ -305,7 +325,7 @@ extern "C" int obm_inventory(const obm_grid* grid, int ntracers, const double* c
     int rc = check_groups("obm_inventory", ntracers, ngroups, groups);
     if (rc) return rc;
     if (ngroups == 0) return 0;
-    InvArgs a;
+    static thread_local InvArgs a;  // 2.4 KB of kernel arguments, kept off the caller's stack
     memset(&a, 0, sizeof(a));
     rc = make_dims(grid, &a.d, false);
     if (rc) return rc;
@@ -315,7 +335,8 @@ extern "C" int obm_inventory(const obm_grid* grid, int ntracers, const double* c
         OBM_REQUIRE(tracers[t] != nullptr, OBM_ENULL, "obm_inventory: tracers[%d] is NULL", t);
         a.tracers[t] = tracers[t];
     }
-    for (int q = 0; q < ngroups; q++) a.groups[q] = groups[q];
+    for (int q = 0; q < ngroups; q++)
+        for (int m = 0; m < groups[q].n; m++) a.w[q][groups[q].index[m]] += groups[q].scalefactor[m];
     a.volume = cell_volume;
     a.uniform_volume = uniform_volume;
     a.partial = (double*)workspace;

@@ -96,6 +96,65 @@ __device__ __forceinline__ double exp_lean(double x) {
     return __hiloint2double(__double2hiint(p) + (int)((unsigned)k << 20), __double2loint(p));
 }
 
+// e^x for |x| < 700 (no guard): k = round(x·log₂e) by the 1.5·2⁵² shift, r = x − k·ln2 (two-term Cody–Waite),
+// e^r by the degree-13 Taylor polynomial (|r| ≤ ln2/2 ⇒ truncation r¹⁴/14! < 2⁻⁵⁷), exponent advanced by k.  ≤ 2 ulp.
+// NaN → NaN (the shifted sum of a NaN is the canonical NaN, low word 0 ⇒ k = 0).
+__device__ __forceinline__ double exp_unguarded(double x) {
+    const double SHIFT = KD(6755399441055744.0);
+    const double t = fma(x, KD(1.4426950408889634), SHIFT);
+    const int k = __double2loint(t);
+    const double kf = t - SHIFT;
+    double r = fma(kf, KD(-6.93147180559945286e-01), x);
+    r = fma(kf, KD(-2.31904681384629956e-17), r);
+    double p = fma(KD(1.0 / 6227020800.0), r, KD(1.0 / 479001600));
+    p = fma(p, r, KD(1.0 / 39916800));
+    p = fma(p, r, KD(1.0 / 3628800));
+    p = fma(p, r, KD(1.0 / 362880));
+    p = fma(p, r, KD(1.0 / 40320));
+    p = fma(p, r, KD(1.0 / 5040));
+    p = fma(p, r, KD(1.0 / 720));
+    p = fma(p, r, KD(1.0 / 120));
+    p = fma(p, r, KD(1.0 / 24));
+    p = fma(p, r, KD(1.0 / 6));
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (int)((unsigned)k << 20), __double2loint(p));
+}
+// |x| < 700 and not NaN ⇔ the high word without its sign is below that of 700.0 (0x4085e000): one integer compare
+__device__ __forceinline__ bool exp_in_range(double x) { return ((unsigned)__double2hiint(x) & 0x7fffffffu) < 0x4085e000u; }
+__device__ __forceinline__ double exp_horner(double x) {
+    if (!exp_in_range(x)) return exp(x);  // overflow, underflow to subnormals / 0, ±Inf, NaN: the library's answer
+    return exp_unguarded(x);
+}
+// ln x for positive normal x: x = 2^e·m, m ∈ [√½, √2), s = (m − 1)/(m + 1), ln m = 2s·Σ s^(2k)/(2k + 1) to k = 9
+// (s² ≤ 0.0295 ⇒ truncation < 2⁻⁵⁵), ln x = e·ln2 + ln m with ln2 split in two.  ≤ 2 ulp; ≈ 30 instructions against
+// ≈ 60 for the library log (two of them per solve: ln T and ln(1 − 0.001005 S)).  Anything else (≤ 0, subnormal, ±Inf,
+// NaN) takes the library log, inline in the cold branch.
+__device__ __forceinline__ double log_lean(double x) {
+    const int hi = __double2hiint(x);
+    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
+    int e = (hi >> 20) - 1023;
+    int mh = (hi & 0x000fffff) | 0x3ff00000;      // m ∈ [1, 2)
+    const bool up = mh >= 0x3ff6a09f;              // m ≥ √2 (to 2⁻²⁰): halve it
+    mh = up ? mh - 0x00100000 : mh;
+    e = up ? e + 1 : e;
+    const double m = __hiloint2double(mh, __double2loint(x));
+    const double f = m - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s;
+    double q = fma(KD(2.0 / 19), z, KD(2.0 / 17));
+    q = fma(q, z, KD(2.0 / 15));
+    q = fma(q, z, KD(2.0 / 13));
+    q = fma(q, z, KD(2.0 / 11));
+    q = fma(q, z, KD(2.0 / 9));
+    q = fma(q, z, KD(2.0 / 7));
+    q = fma(q, z, KD(2.0 / 5));
+    q = fma(q, z, KD(2.0 / 3));
+    const double lm = fma(s * z, q, 2.0 * s);      // ln m
+    const double ef = (double)e;
+    return fma(ef, KD(6.93147180369123816490e-01), fma(ef, KD(1.90821492927058770002e-10), lm));
+}
 // ---- grid indexing -----------------------------------------------------------------------------
 struct GridDims {
     int Nx, Ny, Nz, Hx, Hy, Hz;

@@ -67,7 +67,7 @@ constexpr int NOUT = 24;  // tendencies
 // compare + select.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
 // by a min/max) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
 #ifndef OBM_PISCES_EXP
-#define OBM_PISCES_EXP 0  // 0: library exp; 1: exp_lean of obm_common.cuh (measured: no gain here, r02)
+#define OBM_PISCES_EXP 0  // 0: library exp; 1: exp_lean of obm_common.cuh (measured: no gain here, r02); 2: exp_horner
 #endif
 template <bool EXACT>
 struct Ar {
@@ -93,8 +93,10 @@ struct Ar {
     static __device__ __forceinline__ double ex(double x) {
 #if OBM_PISCES_EXP == 0
         return exp(x);
-#else
+#elif OBM_PISCES_EXP == 1
         return EXACT ? exp(x) : exp_lean(x);
+#else
+        return EXACT ? exp(x) : exp_horner(x);
 #endif
     }
 };

@@ -58,24 +58,53 @@ def inventory_groups(groups: Sequence):
     return names, garr
 
 
+class InventoryDiagnostic:
+    """The conservation diagnostic as a reusable object: buffers (output, reduction workspace, the cell-volume array a
+    stretched grid needs) are allocated once, so calling it every stage costs one `obm_inventory` (one fused pass over
+    the cells for all groups, HBM-bound) plus ONE all-reduce of `len(groups)` doubles — the only collective of the path.
+    `groups` is a list of (tracer_names, scalefactors), e.g. the five PISCES element budgets of
+    `conserved_tracers` (PISCES/coupling_utils.jl:10-33) or the N / C budgets the reference's tests sum by hand
+    (test/test_NutrientsPlanktonDetritus.jl:8-21)."""
+
+    def __init__(self, grid: RectilinearGrid, tracers: dict, groups: Sequence):
+        import numpy as np
+        self.grid, self.groups = grid, list(groups)
+        self.names, self.garr = inventory_groups(groups)
+        self.fields = [tracers[n] for n in self.names]
+        require_cuda(*self.fields)
+        lib = _lib.load()
+        dev = grid.device
+        self.out = torch.zeros(len(self.groups), dtype=torch.float64, device=dev)
+        self.workspace = torch.empty(lib.obm_inventory_workspace_bytes(len(self.groups)) // 8, dtype=torch.float64, device=dev)
+        dz = grid.dz
+        if np.allclose(dz, dz[0], rtol=1e-14, atol=0.0):
+            self.volume, self.uniform_volume = None, float(dz[0] * grid.dx * grid.dy)
+        else:  # stretched z: per-cell volumes, built once
+            self.volume = torch.zeros(grid.parent_shape, dtype=torch.float64, device=dev)
+            grid.interior(self.volume)[...] = grid.cell_volume()
+            self.uniform_volume = 0.0
+        self.table = _lib.pointer_table([f.ptr for f in self.fields])
+
+    def local(self, stream: Optional[int] = None) -> torch.Tensor:
+        """This GPU's slab: out[g] = Σ_cells (Σ_f sf·c_f)·V (device tensor, overwritten by every call)."""
+        cg = self.grid.c_grid()
+        s = stream if stream is not None else current_stream_ptr(self.grid.device)
+        rc = _lib.load().obm_inventory(C.byref(cg), len(self.names), self.table, len(self.groups), self.garr,
+                                       self.volume.data_ptr() if self.volume is not None else None, self.uniform_volume,
+                                       self.out.data_ptr(), self.workspace.data_ptr(), s)
+        _lib.check(rc, "obm_inventory")
+        return self.out
+
+    def __call__(self, stream: Optional[int] = None) -> torch.Tensor:
+        """Global inventory: the local reduction, then the all-reduce (sum) over the slabs."""
+        return allreduce_sum(self.local(stream))
+
+
 def local_inventory(grid: RectilinearGrid, tracers: dict, groups: Sequence, stream: Optional[int] = None) -> torch.Tensor:
     """Per-GPU fused reduction out[g] = Σ_cells (Σ_f sf·c_f)·V (obm_inventory).  `groups` is a list of
-    (tracer_names, scalefactors); returns a device tensor of len(groups) doubles."""
-    names, garr = inventory_groups(groups)
-    fields = [tracers[n] for n in names]
-    require_cuda(*fields)
-    lib = _lib.load()
-    dev = grid.device
-    out = torch.zeros(len(groups), dtype=torch.float64, device=dev)
-    ws = torch.empty(lib.obm_inventory_workspace_bytes(len(groups)) // 8, dtype=torch.float64, device=dev)
-    vol = torch.zeros(grid.parent_shape, dtype=torch.float64, device=dev)
-    grid.interior(vol)[...] = grid.cell_volume()
-    cg = grid.c_grid()
-    s = stream if stream is not None else current_stream_ptr(dev)
-    rc = lib.obm_inventory(C.byref(cg), len(names), _lib.pointer_table([f.ptr for f in fields]), len(groups), garr,
-                           vol.data_ptr(), 0.0, out.data_ptr(), ws.data_ptr(), s)
-    _lib.check(rc, "obm_inventory")
-    return out
+    (tracer_names, scalefactors); returns a device tensor of len(groups) doubles.  One-off form of
+    `InventoryDiagnostic` (which keeps its buffers between calls)."""
+    return InventoryDiagnostic(grid, tracers, groups).local(stream).clone()
 
 
 def allreduce_sum(values: torch.Tensor) -> torch.Tensor:

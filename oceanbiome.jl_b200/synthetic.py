@@ -67,23 +67,42 @@ def _shape(u, lo, hi, log):
     return lo + (hi - lo) * u
 
 
-def fill_numpy(parent: np.ndarray, grid, name: str, lo: float, hi: float, log: bool = False, seed: int = SEED):
-    """Fill the interior of a halo'd parent array (linear index n = i + Nx (j + Ny k)), zero-gradient halos."""
+def fill_numpy(parent: np.ndarray, grid, name: str, lo: float, hi: float, log: bool = False, seed: int = SEED,
+               rows=None):
+    """Fill the interior of a halo'd parent array (linear index n = i + Nx (j + Ny k)), zero-gradient halos.
+    `rows = (j0, Ny_global)`: `grid` is a y-slab of a global grid of Ny_global rows starting at global row j0 — the
+    values are those rows of the GLOBAL field (n = i + Nx ((j0 + j) + Ny_global k))."""
     n3 = 1 if parent.shape[0] == 1 else grid.Nz
-    u = uniform_numpy(field_id(name), 0, grid.Nx * grid.Ny * n3, seed)
-    grid.interior(parent)[...] = _shape(u, lo, hi, log).reshape(n3, grid.Ny, grid.Nx)
+    fid = field_id(name)
+    if rows is None:
+        u = uniform_numpy(fid, 0, grid.Nx * grid.Ny * n3, seed)
+        grid.interior(parent)[...] = _shape(u, lo, hi, log).reshape(n3, grid.Ny, grid.Nx)
+    else:
+        j0, nyg = rows
+        for k in range(n3):
+            u = uniform_numpy(fid, grid.Nx * (j0 + nyg * k), grid.Nx * grid.Ny, seed)
+            grid.interior(parent)[k] = _shape(u, lo, hi, log).reshape(grid.Ny, grid.Nx)
     _halos(parent, grid)
     return parent
 
 
-def fill_torch(field, name: str, lo: float, hi: float, log: bool = False, seed: int = SEED, chunk: int = 1 << 26):
-    """Same values as fill_numpy, generated on the device chunk by chunk (no host round trip unless log)."""
+def fill_torch(field, name: str, lo: float, hi: float, log: bool = False, seed: int = SEED, chunk: int = 1 << 26,
+               rows=None):
+    """Same values as fill_numpy, generated on the device chunk by chunk (no host round trip unless log).
+    `rows = (j0, Ny_global)` as in `fill_numpy`: this rank's rows of the global field (multi-GPU slabs)."""
     grid = field.grid
     interior = field.interior
     n3 = interior.shape[0]
     plane = grid.Nx * grid.Ny
-    kper = max(1, chunk // plane)
     fid = field_id(name)
+    if rows is not None:
+        j0, nyg = rows
+        for k in range(n3):
+            u = uniform_torch(fid, grid.Nx * (j0 + nyg * k), plane, field.data.device, seed)
+            interior[k] = _shape(u, lo, hi, log).reshape(grid.Ny, grid.Nx)
+        field.fill_halos_zero_gradient()
+        return field
+    kper = max(1, chunk // plane)
     for k0 in range(0, n3, kper):
         k1 = min(n3, k0 + kper)
         u = uniform_torch(fid, k0 * plane, (k1 - k0) * plane, field.data.device, seed)

@@ -127,6 +127,51 @@ def test_nan_inputs_propagate_like_the_reference(cuda, oracle, accumulate):
     assert poisoned >= 9 * 3  # every injected NaN reaches several tendencies
 
 
+def test_extreme_finite_states_match_the_reference_patterns(cuda, oracle):
+    """Finite but extreme inputs (zeros, 1e±30, positive biomasses far below their pigment incl. denormals — the states a
+    blown-up run hands over just before its first NaN): NaNs are then BORN mid-way (Inf − Inf of overflowed quotas, 0·Inf),
+    not read.  Wherever the reference's NaN-propagating arithmetic (the oracle) gives NaN / ±Inf the kernel gives the
+    same, every other tendency meets the stated metric — i.e. the fast pass's selects swallowed nothing and the exact
+    pass redid every such cell (r01 recorded the denormal-biomass case as a known hole; closed by the operand order of
+    min(L_N, L_PO₄, L_Fe, L_Si), tests/test_oracle_pisces.py::test_quota_overflow_reaches_the_exact_pass)."""
+    n = 4096
+    grid, bgc, model = build(cuda, (n, 1, 1), (1e5, 10.0, 40.0))
+    u = bgc.underlying_biogeochemistry
+    fill(model, bgc)
+    model.update_state()
+    rng = np.random.default_rng(20261018)
+    aux_dev = bgc.biogeochemical_auxiliary_fields()
+    picks = np.array([0.0, 1e-30, 1e-6, 1.0, 1e6, 1e30])
+    tiny = np.array([0.0, 5e-324, 1e-310, 1e-280, 1e-200, 1e-30, 1e-6, 1.0, 1e6])
+    for name in pisces.TRACERS[:24]:
+        src = tiny if name in ("P", "D", "Z", "M") else picks
+        v = rng.choice(src, n)
+        keep = rng.random(n) < 0.5  # half of the entries stay ordinary, so that single extremes are seen in isolation too
+        cur = model.tracers[name].interior[0, 0, :].cpu().numpy()
+        model.tracers[name].interior[0, 0, :] = torch.from_numpy(np.where(keep, cur, v)).to(cuda)
+    og = oracle.Grid.like(grid)
+    host = {m: np.ascontiguousarray(f.data.cpu().numpy()) for m, f in model.tracers.items()}
+    aux = host_aux(og, grid, bgc)
+    G = {m: ob.CenterField(grid, fill=3.0) for m in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, aux_dev, G, accumulate=False, time=0.0)
+    torch.cuda.synchronize()
+    params = u.c_params(0.0)
+    tr = [host[m] for m in pisces.TRACERS]
+    Go = oracle.pisces_tendencies(og, params, tr, aux)
+    So = oracle.pisces_tendency_scales(og, params, tr, aux)
+    nonfinite = 0
+    for m, g, sc in zip(pisces.TRACERS[:24], Go, So):
+        want, got, S = og.interior(g), og.interior(G[m].data.cpu().numpy()), og.interior(sc)
+        assert np.array_equal(np.isnan(want), np.isnan(got)), m
+        inf = np.isinf(want)
+        assert np.array_equal(inf, np.isinf(got)) and np.array_equal(want[inf], got[inf]), m
+        ok = np.isfinite(want) & np.isfinite(S)
+        den = np.maximum(np.maximum(np.abs(want[ok]), S[ok]), 1e-300)
+        assert np.max(np.abs(got[ok] - want[ok]) / den) <= RTOL_TENDENCY, m
+        nonfinite += int((~np.isfinite(want)).sum())
+    assert nonfinite > 100  # the states do produce mid-way NaNs / overflows
+
+
 def test_accumulate_into_existing_tendencies(cuda, oracle):
     grid, bgc, model = build(cuda, (20, 5, 12), (1e4, 1e3, 300.0))
     u = bgc.underlying_biogeochemistry
