@@ -98,7 +98,7 @@ struct ScaleOmegaArgs {
 };
 
 #ifndef OBM_SN_MIN_BLOCKS
-#define OBM_SN_MIN_BLOCKS 8  // 64 registers: 32 warps per SM for the issue-bound solve
+#define OBM_SN_MIN_BLOCKS 6  // 80 registers, no spill (7: 72 registers + 32 B, 8: 64 + 48 B of spill — timed in profiles/r03_kernel_variants.txt)
 #endif
 __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
