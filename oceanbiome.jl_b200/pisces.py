@@ -469,6 +469,49 @@ class PISCESModel:
         rc = _lib.load().obm_pisces_tendencies(C.byref(cg), C.byref(p), tptr, C.byref(f), gptr, 1 if accumulate else 0, s)
         _lib.check(rc, "obm_pisces_tendencies")
 
+    AUXILIARY_DEFAULTS = {"PAR₁": 0.0, "PAR₂": 0.0, "PAR₃": 0.0, "PAR": None, "Ω": 1.0, "zₘₓₗ": -10.0, "zₑᵤ": -10.0, "κ": 1.0,
+                          "mixed_layer_PAR": 0.0, "wPOC": 0.0, "wGOC": 0.0}
+
+    def __call__(self, name: str, *, z: float = -5.0, time: float = 0.0, device="cuda", **state):
+        """The per-tracer form of the plugin API, `bgc(i, j, k, grid, Val(name), clock, fields, auxiliary_fields)`
+        (PISCES.jl:120-123; the continuous form `bgc(Val(name), x, y, z, t, fields...)` of
+        docs/src/model_implementation.md:34-75): the tendency of ONE tracer at the given state.  `state` holds tracer
+        values (absent ones are 0) and the auxiliary fields of `required_biogeochemical_auxiliary_fields` by their
+        reference names — PAR₁, PAR₂, PAR₃, PAR (default: their sum), Ω, zₘₓₗ, zₑᵤ, κ, mixed_layer_PAR, wPOC, wGOC (the
+        cell-centre sinking speeds) — as scalars or as arrays of states evaluated side by side.  The fused kernel runs on
+        a row of boxes centred on depth `z` at model time `time`; a float is returned for scalar input, else a device
+        tensor.  NPD's counterpart: `NutrientsPlanktonDetritus.__call__`."""
+        from .box_model import BoxModelGrid
+        if name not in TRACERS:
+            raise KeyError(f"{name} is not a tracer of PISCES {TRACERS}")
+        unknown = set(state) - set(TRACERS) - set(self.AUXILIARY_DEFAULTS)
+        if unknown:
+            raise KeyError(f"unknown fields {sorted(unknown)}; PISCES carries {TRACERS} and reads {tuple(self.AUXILIARY_DEFAULTS)}")
+        flat = lambda v: torch.as_tensor(v, dtype=torch.float64).reshape(-1)  # noqa: E731
+        vals = {n: flat(state.get(n, 0.0)) for n in TRACERS}
+        aux = {n: flat(state.get(n, d if d is not None else 0.0)) for n, d in self.AUXILIARY_DEFAULTS.items()}
+        if "PAR" not in state:
+            aux["PAR"] = aux["PAR₁"] + aux["PAR₂"] + aux["PAR₃"]
+        n = max(v.numel() for v in list(vals.values()) + list(aux.values()))
+        grid = BoxModelGrid(n, device=device, z=z)
+        row = lambda v: v.expand(n).reshape(1, 1, n)  # noqa: E731
+        tr = {k: CenterField(grid, k).set(row(v)) for k, v in vals.items()}
+        fields = {}
+        for k, v in aux.items():
+            if k in ("zₘₓₗ", "zₑᵤ", "κ", "mixed_layer_PAR"):
+                fields[k] = Field2D(grid, k).set(row(v))
+            elif k in ("wPOC", "wGOC"):  # ℑzᵃᵃᶜ(w) of two equal faces is the cell-centre speed
+                f = ZFaceField(grid, k)
+                f.face_interior[...] = row(v).to(f.data.device).expand(2, 1, n)
+                fields[k] = f
+            else:
+                fields[k] = CenterField(grid, k).set(row(v))
+        G = {k: CenterField(grid, "G" + k) for k in TRACERS}
+        self.compute_tendencies(grid, tr, fields, G, accumulate=False, time=time)
+        out = G[name].interior.reshape(-1)
+        scalar = n == 1 and not any(torch.is_tensor(v) for v in state.values())
+        return out.item() if scalar else out
+
     def summary(self):
         return "PISCES biogeochemical model (24 tracers)"
 

@@ -126,3 +126,146 @@ def test_julia_ccall_signatures_have_the_prototypes_arity():
                 assert jt == scalar, f"{name} argument {pos}: Julia {jt}, C {ct.__name__}"
             else:
                 assert any(k in jt for k in ("Ptr", "Ref", "F64", "Cstring")), f"{name} argument {pos}: Julia {jt} for a C pointer"
+
+
+# ---- the reference-side binding against the reference's own struct definitions ----------------------------------------
+REFERENCE = "/root/reference"  # present in the build container only; these checks are skipped elsewhere
+
+# Julia path in julia/obm_fill.jl → (reference file, struct name, … alternatives the component may be)
+PISCES_DIR = "src/Models/AdvectedPopulations/PISCES/"
+NPD_DIR = "src/Models/AdvectedPopulations/NutrientsPlanktonDetritus/"
+FILL_SOURCES = {
+    "ObmNpdParams": {
+        "bgc.plankton": [(NPD_DIR + "plankton.jl", "PhytoZoo")],
+        "bgc.nutrients": [(NPD_DIR + "nutrients.jl", "NitrateAmmonia"), (NPD_DIR + "nutrients.jl", "NitrateAmmoniaIron")],
+        "bgc.detritus": [(NPD_DIR + "detritus.jl", "TwoParticleAndDissolved"), (NPD_DIR + "detritus.jl", "VariableRedfieldDetritus"),
+                         (NPD_DIR + "detritus.jl", "Detritus")],
+        "bgc.oxygen": [(NPD_DIR + "oxygen.jl", "Oxygen")]},
+    "ObmPiscesParams": {
+        "bgc": [(PISCES_DIR + "PISCES.jl", "PISCES")],
+        "bgc.phytoplankton": [(PISCES_DIR + "phytoplankton/nano_and_diatoms.jl", "NanoAndDiatoms")],
+        "bgc.phytoplankton.nano": [(PISCES_DIR + "phytoplankton/mixed_mondo.jl", "MixedMondo")],
+        "bgc.phytoplankton.diatoms": [(PISCES_DIR + "phytoplankton/mixed_mondo.jl", "MixedMondo")],
+        "bgc.phytoplankton.nano.growth_rate": [(PISCES_DIR + "phytoplankton/growth_rate.jl", "GrowthRespirationLimitedProduction"),
+                                               (PISCES_DIR + "phytoplankton/growth_rate.jl", "NutrientLimitedProduction")],
+        "bgc.phytoplankton.diatoms.growth_rate": [(PISCES_DIR + "phytoplankton/growth_rate.jl", "GrowthRespirationLimitedProduction"),
+                                                  (PISCES_DIR + "phytoplankton/growth_rate.jl", "NutrientLimitedProduction")],
+        "bgc.phytoplankton.nano.nutrient_limitation": [(PISCES_DIR + "phytoplankton/nutrient_limitation.jl", "NitrogenIronPhosphateSilicateLimitation")],
+        "bgc.phytoplankton.diatoms.nutrient_limitation": [(PISCES_DIR + "phytoplankton/nutrient_limitation.jl", "NitrogenIronPhosphateSilicateLimitation")],
+        "bgc.zooplankton": [(PISCES_DIR + "zooplankton/micro_and_meso.jl", "MicroAndMeso")],
+        "bgc.zooplankton.micro": [(PISCES_DIR + "zooplankton/food_quality_dependant.jl", "QualityDependantZooplankton")],
+        "bgc.zooplankton.meso": [(PISCES_DIR + "zooplankton/food_quality_dependant.jl", "QualityDependantZooplankton")],
+        "bgc.dissolved_organic_matter": [(PISCES_DIR + "dissolved_organic_matter/dissolved_organic_carbon.jl", "DissolvedOrganicCarbon")],
+        "bgc.particulate_organic_matter": [(PISCES_DIR + "particulate_organic_matter/two_size_class.jl", "TwoCompartmentCarbonIronParticles")],
+        "bgc.nitrogen": [(PISCES_DIR + "nitrogen/nitrate_ammonia.jl", "NitrateAmmonia")],
+        "bgc.iron": [(PISCES_DIR + "iron/simple_iron.jl", "SimpleIron")],
+        "bgc.oxygen": [(PISCES_DIR + "oxygen.jl", "Oxygen")],
+        "bgc.latitude": [(PISCES_DIR + "common.jl", "PrescribedLatitude")]},
+    "ObmTwobandParams": {"par": [("src/Light/2band.jl", "TwoBandPhotosyntheticallyActiveRadiation")]},
+    "ObmMultibandParams": {"par": [("src/Light/multi_band.jl", "MultiBandPhotosyntheticallyActiveRadiation")]},
+    "ObmSedimentParams": {"sed.biogeochemistry": [("src/Models/Sediments/simple_multi_G.jl", "SimpleMultiG"),
+                                                  ("src/Models/Sediments/instant_remineralisation.jl", "InstantRemineralisation")]},
+}
+# reference fields that are NOT parameters of a kernel, with where they go instead
+NOT_PARAMETERS = {
+    "PhytoZoo": {"phytoplankton_sinking_velocity", "zooplankton_sinking_velocity"},      # → biogeochemical_drift_velocity (w fields)
+    "TwoParticleAndDissolved": {"small_particle_sinking_velocity", "large_particle_sinking_velocity"},
+    "VariableRedfieldDetritus": {"small_particle_sinking_velocity", "large_particle_sinking_velocity"},
+    "Detritus": {"sinking_speeds"},
+    "MixedMondo": {"growth_rate", "nutrient_limitation"},                                 # sub-structs, consumed field by field
+    "NanoAndDiatoms": {"nano", "diatoms"},
+    "MicroAndMeso": {"micro", "meso"},
+    "QualityDependantZooplankton": {"food_preferences"},                                   # NamedTuple, consumed key by key
+    "DissolvedOrganicCarbon": {"bacteria_concentration_depth_exponent"},                   # unused by the reference's DOC methods (the zooplankton's is)
+    "PISCES": {"phytoplankton", "zooplankton", "dissolved_organic_matter", "particulate_organic_matter", "nitrogen", "iron",
+               "silicate", "oxygen", "phosphate", "inorganic_carbon", "latitude", "day_length",   # components; day length: two host-evaluated calls
+               "mixed_layer_depth", "euphotic_depth", "mean_mixed_layer_vertical_diffusivity", "mean_mixed_layer_light",
+               "carbon_chemistry", "calcite_saturation", "sinking_velocities"},           # fields → ObmPiscesFields / obm_calcite_saturation
+    "TwoBandPhotosyntheticallyActiveRadiation": {"field", "surface_PAR"},                  # arrays / callables → kernel arguments
+    "MultiBandPhotosyntheticallyActiveRadiation": {"total", "fields", "field_names", "surface_PAR"},
+    "SimpleMultiG": {"sinking_nitrogen", "sinking_carbon"},                                # tracer-name tuples → counts + pointer tables
+    "InstantRemineralisation": {"sinking_tracers", "remineralisation_reciever"},
+}
+
+
+def reference_struct_fields(path, name):
+    """Field names of `struct name{…}` in a reference source file (up to its inner constructor or `end`)."""
+    src = open(os.path.join(REFERENCE, path), encoding="utf-8").read()
+    m = re.search(r"^\s*(?:@kwdef\s+)?struct\s+" + name + r"\b[^\n]*\n(.*?)^\s*end\b", src, flags=re.S | re.M)
+    assert m, (path, name)
+    fields = []
+    for line in m.group(1).splitlines():
+        line = line.split("#")[0]
+        if re.match(r"\s*(function\b|" + name + r"\b)", line):
+            break
+        f = re.match(r"\s*([A-Za-z_][\w′]*)\s*::", line)
+        if f:
+            fields.append(f.group(1))
+    return fields
+
+
+def fill_functions():
+    src = open(os.path.join(ROOT, "julia", "obm_fill.jl"), encoding="utf-8").read()
+    out = {}
+    for m in re.finditer(r"^(Obm\w+)\(([^)]*)\) = \1\(;\n(.*?)^\)\n", src, flags=re.S | re.M):
+        out[m.group(1)] = m.group(3)
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree is only in the build container")
+def test_julia_fill_constructors_consume_every_reference_field_once():
+    """julia/obm_fill.jl against the reference's own struct definitions: every field a fill constructor reads exists in
+    the reference struct it is read from; every field of those structs is consumed exactly once per place it occurs (or is
+    listed in NOT_PARAMETERS with where it goes instead); every member of the C struct is assigned."""
+    fills = fill_functions()
+    assert set(FILL_SOURCES) <= set(fills), sorted(fills)
+    for fn, sources in FILL_SOURCES.items():
+        body = fills[fn]
+        reads = re.findall(r"(?:fieldor|tupleor)\(([\w.]+), :([\w′]+)(?:, \d+)?\)", body) + \
+            re.findall(r"bandor\((par)\.(\w+), \d+\)", body)
+        by_parent = {}
+        for parent, field in reads:
+            by_parent.setdefault(parent, []).append(field)
+        # fields consumed through a hand-written expression (an enumeration from a type, a flag, the day-length calls)
+        manual = {}
+        for parent in sources:
+            for field in re.findall(r"(?<![\w.])" + re.escape(parent) + r"\.([A-Za-z_]\w*)(?![\w.])", body):
+                manual.setdefault(parent, set()).add(field)
+        for parent, fields in by_parent.items():
+            if parent.endswith(".food_preferences"):
+                assert sorted(set(fields)) == ["D", "P", "POC", "Z"], (fn, parent, fields)  # defaults.jl:4,12 NamedTuple keys
+                continue
+            assert parent in sources, f"{fn}: reads from {parent}, which has no reference struct listed"
+            known = set()
+            for path, name in sources[parent]:
+                known |= set(reference_struct_fields(path, name))
+            assert set(fields) <= known, f"{fn}: {parent} has no field(s) {sorted(set(fields) - known)} in {sources[parent]}"
+        for parent, structs in sources.items():
+            got = by_parent.get(parent, [])
+            for path, name in structs:
+                want = [f for f in reference_struct_fields(path, name) if f not in NOT_PARAMETERS.get(name, ())]
+                assert want, (path, name)
+                for f in want:
+                    n = got.count(f)
+                    if n == 0 and f in manual.get(parent, ()):
+                        continue
+                    # a scalar field is read once; a tuple field once per element
+                    assert n >= 1, f"{fn}: reference field {name}.{f} ({path}) is never consumed from {parent}"
+                    if n > 1:
+                        idx = re.findall(r"(?:tupleor\(" + re.escape(parent) + r", :" + f + r", (\d+)\)|bandor\(par\." + f + r", (\d+)\))", body)
+                        assert len(idx) == n and len(set(idx)) == n, f"{fn}: {name}.{f} consumed {n} times"
+    # every member of every C struct with a fill constructor is assigned, by its own name, exactly once
+    for fn, body in fills.items():
+        cname = "obm_" + re.sub(r"(?<!^)([A-Z])", r"_\1", fn[3:]).lower()
+        cls = _lib.STRUCTS[cname]
+        top = re.findall(r"^    (\w+) = ", body, flags=re.M)
+        assert top == [n for n, _ in cls._fields_], (fn, top)
+
+
+def test_generated_julia_fill_constructors_are_in_sync():
+    """julia/obm_fill.jl is generated from the Python host mirror's own c_params(); regenerate it when a mirror changes."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_julia_fill.py")], capture_output=True, text=True,
+                         check=True).stdout
+    assert out == open(os.path.join(ROOT, "julia", "obm_fill.jl"), encoding="utf-8").read()

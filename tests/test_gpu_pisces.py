@@ -351,3 +351,25 @@ def test_par_scan_with_column_state_matches_oracle(cuda, oracle, size, extent):
     mean = oracle.mixed_layer_mean(og, u.mixed_layer_depth.data.cpu().numpy(), PARd)
     gm = u.mean_mixed_layer_light.data.cpu().numpy()
     assert float(np.max(np.abs(og.interior(gm) - og.interior(mean)) / np.abs(og.interior(mean)))) <= RTOL_TENDENCY
+
+
+def test_per_tracer_call_form(cuda, oracle):
+    """`bgc(i, j, k, grid, Val(name), clock, fields, auxiliary_fields)` (PISCES.jl:120-123): one tracer's tendency at a
+    state is the fused kernel evaluated on boxes — against the oracle's point evaluation of the same state."""
+    grid, bgc, model = build(cuda, (4, 2, 3), (10.0, 10.0, 30.0))
+    u = bgc.underlying_biogeochemistry
+    state = dict(pisces.PISCES_INITIAL_VALUES)
+    state.update({"T": 14.0, "S": 35.0})
+    aux = {"PAR₁": 31.0, "PAR₂": 22.0, "PAR₃": 9.0, "Ω": 0.8, "zₘₓₗ": -40.0, "zₑᵤ": -70.0, "κ": 1e-3, "mixed_layer_PAR": 25.0,
+           "wPOC": -2 / 86400, "wGOC": -40 / 86400}
+    t, z = 0.4 * 365 * 86400.0, -55.0
+    want, S = oracle.pisces_point_terms(u.c_params(t), [state.get(n, 0.0) for n in pisces.TRACERS], aux["PAR₁"], aux["PAR₂"],
+                                        aux["PAR₃"], 62.0, aux["Ω"], aux["wPOC"], aux["wGOC"], aux["zₘₓₗ"], aux["zₑᵤ"], aux["κ"],
+                                        aux["mixed_layer_PAR"], z)
+    for q, n in enumerate(pisces.TRACERS[:24]):
+        got = u(n, z=z, time=t, device=cuda, **state, **aux)
+        assert isinstance(got, float) and abs(got - want[q]) <= RTOL_TENDENCY * max(abs(want[q]), S[q]), (n, got, want[q])
+    assert u("T", z=z, time=t, device=cuda, **state, **aux) == 0.0  # zero(grid), PISCES.jl:120
+    Fe = torch.linspace(0.05, 1.5, 9, dtype=torch.float64)
+    gP = u("PFe", z=z, time=t, device=cuda, **{**state, "Fe": Fe}, **aux)
+    assert gP.shape == (9,) and bool((gP[1:] > gP[:-1]).all())  # iron uptake grows with dissolved iron

@@ -220,3 +220,20 @@ def test_computed_light_with_a_constant_column_field_takes_the_plain_scan(lib):
     bgc = ob.PISCES(g, euphotic_depth=ob.ConstantField(g, -50.0))
     ob.BiogeochemicalModel(g, bgc).update_state()
     assert lib.calls == ["obm_par_multiband", "obm_mixed_layer_mean", "obm_calcite_saturation"]
+
+
+def test_pisces_per_tracer_call_form_is_one_fused_launch(lib):
+    """`bgc(i, j, k, grid, Val(name), clock, fields, auxiliary_fields)` (PISCES.jl:120-123) in the host mirror: one
+    `obm_pisces_tendencies` launch on a row of boxes, whatever the tracer asked for; unknown names are refused."""
+    import torch
+    g = grid3()
+    u = ob.PISCES(g).underlying_biogeochemistry
+    out = u("P", device="cpu", P=1.0, PChl=0.3, PFe=0.01, **{"NO₃": 4.0, "PAR₁": 20.0, "PAR₂": 20.0, "PAR₃": 20.0, "zₘₓₗ": -30.0})
+    assert isinstance(out, float) and lib.calls == ["obm_pisces_tendencies"]
+    lib.calls.clear()
+    many = u("Fe", device="cpu", z=-120.0, time=86400.0, Fe=torch.linspace(0.1, 1.0, 5, dtype=torch.float64), **{"O₂": 200.0})
+    assert many.shape == (5,) and lib.calls == ["obm_pisces_tendencies"]
+    with pytest.raises(KeyError):
+        u("Q", device="cpu")
+    with pytest.raises(KeyError):
+        u("P", device="cpu", Q=1.0)
