@@ -11,10 +11,11 @@ from dataclasses import dataclass
 from typing import Optional
 
 import ctypes as C
+import math
 
 
 from . import _lib
-from .grids import CenterField, Field, RectilinearGrid, ZFaceField, current_stream_ptr
+from .grids import CenterField, Field, RectilinearGrid, ZFaceField, current_stream_ptr, fill_z_halos
 from .negative_tracers import ScaleNegativeTracers, apply_scalers
 
 
@@ -188,7 +189,21 @@ class BiogeochemicalModel:
             self.tracers[n].set(v)
         return self
 
+    def sinking_tracer_names(self):
+        """Tracers whose z-halos a hook reads: those advected by a drift velocity here, and the sediment's sinking fluxes."""
+        names = []
+        if self.sinking_advection is not None:
+            names += [n for n in self.tracers if n not in ("T", "S") and self.drift_velocity_field(n) is not None]
+        sed = getattr(self.biogeochemistry, "sediment", None)
+        if sed is not None:
+            names += [n for n in sed.biogeochemistry.sinking_fluxes() if n not in names]
+        return names
+
     def update_state(self):
+        # Oceananigans' update_state! fills the halo regions before the biogeochemistry hooks run; of those halos the
+        # path reads only the z-planes below / above the sinking tracers' columns (face value of the open bottom face)
+        for n in self.sinking_tracer_names():
+            fill_z_halos(self.tracers[n])
         self.biogeochemistry.update_biogeochemical_state(self)
 
     def compute_tendencies(self):
@@ -210,7 +225,10 @@ class BiogeochemicalModel:
                 self._drift[name] = w
             else:
                 f = ZFaceField(self.grid, "w" + name)
-                f.face_interior[:self.grid.Nz] = float(w)
+                u = getattr(self.biogeochemistry, "underlying_biogeochemistry", self.biogeochemistry)
+                is_open = getattr(u, "drift_velocity_open_bottom", lambda n: True)(name)
+                for k in range(self.grid.Nz):  # faces 1 … Nz; closed bottom: w (1 − e^{(1−k)/2}), k 1-based (:15-17)
+                    f.face_interior[k] = float(w) * (1.0 if is_open else (1 - math.exp((1 - (k + 1)) / 2)))
                 self._drift[name] = f
         return self._drift[name]
 

@@ -141,8 +141,8 @@ class BoxModel:
 
     # ---- compute_tendencies!(model) — timesteppers.jl:30-55 --------------------------------------------------
     def compute_tendencies(self):
-        for n in self.prognostic:
-            f = self.forcing.get(n)
+        for n in self.Gn:  # every Gⁿ the fused launch adds into — prescribed tracers that are also biogeochemical
+            f = self.forcing.get(n) if n in self.prognostic else None  # tracers included (graph mode clears the whole slab)
             if f is None:
                 self.Gn[n].data.zero_()  # the per-point callable returns zero(grid), `no_func` forcing
             else:

@@ -239,6 +239,20 @@ class Field:
         return self
 
 
+def fill_z_halos(field: Field, j0: int = 0, j1: int = 0):
+    """Zero-gradient z-halos of a 3-D field (what Oceananigans' `fill_halo_regions!` leaves for a tracer with the default
+    no-flux boundary conditions), optionally for the interior rows j ∈ [j0, j1) only.  The sinking operators read the cell
+    below the bottom one (sinking.cu `face_value`, sediments.cu `sinking_flux`), so the host mirror refreshes these planes
+    whenever the tracer has changed — Oceananigans does it in `update_state!` before the hooks run."""
+    g, d = field.grid, field.data
+    if not g.Hz or field.is_2d:
+        return field
+    rows = slice(g.Hy + j0, g.Hy + (j1 or g.Ny)) if (j0 or j1) else slice(None)
+    d[:g.Hz, rows] = d[g.Hz:g.Hz + 1, rows]
+    d[g.Hz + g.Nz:, rows] = d[g.Hz + g.Nz - 1:g.Hz + g.Nz, rows]
+    return field
+
+
 def CenterField(grid: RectilinearGrid, name: str = "", fill: float = 0.0) -> Field:
     return Field(grid, torch.full(grid.parent_shape, fill, dtype=torch.float64, device=grid.device), name)
 

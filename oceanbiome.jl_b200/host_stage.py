@@ -20,6 +20,7 @@ from typing import Optional
 import torch
 
 from . import _lib
+from .grids import fill_z_halos
 
 
 def gpu_local_cpus(device) -> Optional[set]:
@@ -89,6 +90,8 @@ class HostStagedStage:
         self.h2d_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * len(self.names)
         self.d2h_bytes = sum((j1 - j0) for j0, j1 in self.slabs) * plane_bytes * (
             len(self.gnames) + (len(self.names) if self.return_tracers else 0))
+        sed = getattr(model.biogeochemistry, "sediment", None)
+        self._halo_names = list(sed.biogeochemistry.sinking_fluxes()) if sed is not None else []
         self._src_in = _lib.pointer_table([self.host_tracers[n].data_ptr() + skip for n in self.names])
         self._dst_in = _lib.pointer_table([model.tracers[n].ptr + skip for n in self.names])
         self._src_out = _lib.pointer_table([model.Gn[n].ptr + skip for n in self.gnames])
@@ -117,6 +120,11 @@ class HostStagedStage:
             ready = self.s_in.record_event()
             self.s_run.wait_event(ready)
             with torch.cuda.stream(self.s_run), g.restrict(j0, j1):
+                # only interior planes travel; the one halo a hook reads — the plane below the bottom cells of the
+                # sediment's sinking tracers — is rebuilt on the device for this slab's rows (zero gradient, as
+                # Oceananigans' fill_halo_regions! leaves it)
+                for n in self._halo_names:
+                    fill_z_halos(m.tracers[n], j0, j1)
                 bgc.update_biogeochemical_state(m)
                 bgc.underlying_biogeochemistry.compute_tendencies(g, m.tracers, bgc.biogeochemical_auxiliary_fields(), m.Gn,
                                                                  accumulate=False, time=m.clock.time)

@@ -85,6 +85,7 @@ class PhytoZoo:
     # not by the tendency kernels (plankton.jl:56-76)
     phytoplankton_sinking_speed: float = 0.0
     zooplankton_sinking_speed: float = 0.0
+    open_bottom: bool = True  # `PhytoZoo(grid; …, open_bottom = true)` plankton.jl:65-76: False tapers w to 0 at the bottom face
 
 
 # ---- detritus (detritus.jl) --------------------------------------------------------------------------
@@ -98,6 +99,7 @@ class TwoParticleAndDissolved:
     redfield_ratio: float = 6.56
     small_particle_sinking_speed: float = 3.47e-5  # m/s (w = -speed)
     large_particle_sinking_speed: float = 200 / day
+    open_bottom: bool = True  # `TwoParticleAndDissolved(grid; …, open_bottom = true)` detritus.jl:107-123
 
 
 @dataclass
@@ -109,6 +111,7 @@ class VariableRedfieldDetritus:
     small_solid_waste_fraction: float = 0.5
     small_particle_sinking_speed: float = 3.47e-5
     large_particle_sinking_speed: float = 200 / day
+    open_bottom: bool = True
 
 
 @dataclass
@@ -117,6 +120,7 @@ class Detritus:
     small_particle_fraction: float = 0.5
     redfield_ratio: float = 6.56
     sinking_speed: float = 2.7489 / day
+    open_bottom: bool = True  # `Detritus(grid; sinking_speed, open_bottom = true)` detritus.jl:274-283
 
 
 # ---- carbonate system / oxygen (carbonate_system.jl:39-46, oxygen.jl:14-17) ------------
@@ -253,6 +257,12 @@ class NutrientsPlanktonDetritus:
         if isinstance(de, Detritus) and name == "D":
             return -de.sinking_speed
         return None
+
+    def drift_velocity_open_bottom(self, name) -> bool:
+        """Whether the drift velocity of `name` keeps its full speed at the bottom face (`open_bottom = true`, the default)
+        or is tapered to zero there, w·(1 − e^{(1−k)/2}) (`setup_velocity_fields`, sinking_velocity_fields.jl:15-17)."""
+        owner = self.plankton if name in ("P", "Z") else self.detritus
+        return bool(getattr(owner, "open_bottom", True))
 
     def conserved_tracers(self, labeled=False):
         """coupling_utils.jl:1-52 — nitrogen group, plus the carbon group (with scale factors)

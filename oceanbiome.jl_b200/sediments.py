@@ -160,7 +160,10 @@ class BiogeochemicalSediment:
                 cache[name] = w
             else:
                 f = ZFaceField(self.grid, "w" + name)
-                f.face_interior[:self.grid.Nz] = 0.0 if w is None else float(w)
+                u = getattr(bgc, "underlying_biogeochemistry", bgc)
+                is_open = getattr(u, "drift_velocity_open_bottom", lambda n: True)(name)
+                for k in range(self.grid.Nz):  # sinking_velocity_fields.jl:15-17; a closed bottom feeds the sediment nothing
+                    f.face_interior[k] = (0.0 if w is None else float(w)) * (1.0 if is_open else (1 - math.exp((1 - (k + 1)) / 2)))
                 cache[name] = f
         return cache[name]
 
