@@ -8,6 +8,18 @@
 
 #include "../../include/obm_b200.h"
 
+#ifndef __CUDACC__
+// Host build of the arithmetic headers (g++, bench_ref/fused_host.cpp): the few device intrinsics they use, as plain C++.
+#include <string.h>
+static inline double __longlong_as_double(long long x) { double d; memcpy(&d, &x, 8); return d; }
+static inline long long __double_as_longlong(double d) { long long x; memcpy(&x, &d, 8); return x; }
+static inline int __double2hiint(double d) { return (int)(__double_as_longlong(d) >> 32); }
+static inline int __double2loint(double d) { return (int)(__double_as_longlong(d) & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) {
+    return __longlong_as_double((long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo));
+}
+#endif
+
 namespace obm {
 
 // ---- thread-local error string (obm_last_error) -------------------------------------------
@@ -45,10 +57,14 @@ __device__ __forceinline__ double jl_eps(double x) {
 // no slow-path call.  Valid for normal, finite b (0 → Inf → NaN, NaN → NaN: garbage in, NaN out);
 // callers that need the IEEE special cases use `/`.
 __device__ __forceinline__ double rcp_fast(double b) {
+#ifdef __CUDACC__
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     const double e = fma(-b, r, 1.0);
     return fma(fma(e, e, e), r, r);
+#else
+    return 1.0 / b;  // host build: IEEE reciprocal (≤ 0.5 ulp; the device sequence is ≤ 1 ulp)
+#endif
 }
 
 // KD(x): the double literal x as a constant-bank operand.  ptxas materialises a 64-bit FP immediate with TWO moves
@@ -56,9 +72,13 @@ __device__ __forceinline__ double rcp_fast(double b) {
 // constants, their pressure corrections) that was more issue slots than the arithmetic itself (805 moves vs 693 FP64
 // instructions, static).  A variable template keyed by the bit pattern puts each distinct literal in bank 3 once; it is
 // then fetched by one LDC(U).64 — or two neighbours by one LDCU.128 — and the value is bit-identical.
+#ifdef __CUDACC__
 template <unsigned long long BITS>
 static __constant__ double CONST_BANK_DOUBLE = __builtin_bit_cast(double, BITS);
 #define KD(x) (::obm::CONST_BANK_DOUBLE<__builtin_bit_cast(unsigned long long, (double)(x))>)
+#else
+#define KD(x) ((double)(x))
+#endif
 
 // Lean exp: k = round(x·log₂e) by the 1.5·2⁵² shift, r = x − k·ln2 (two-term Cody–Waite), e^r = (1 + r) + r²·Q(r) with Q
 // the degree-11 Taylor tail Σ r^m/(m+2)! (|r| ≤ ln2/2 ⇒ truncation < 2⁻⁵⁷) as even / odd Horner chains in r² — ONE
@@ -68,6 +88,10 @@ static __constant__ double CONST_BANK_DOUBLE = __builtin_bit_cast(double, BITS);
 // taken branch.  Used by the PAR scans (issue-bound); measured and NOT adopted in the PISCES tendency kernel (± 0) and
 // the carbonate solve (+6 %: 4 more FP64 instructions per call) — an Estrin variant was slower everywhere (two
 // constants per pair FMA) and is gone.
+#ifndef __CUDACC__
+#define __constant__
+#define __noinline__
+#endif
 static __constant__ double EXP_C[12] = {  // 1/n!, n = 2 … 13
     0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800, 1.0 / 39916800,
     1.0 / 479001600, 1.0 / 6227020800.0};
@@ -195,6 +219,7 @@ __device__ __forceinline__ long long plane_index(const GridDims& d, int i, int j
     return (long long)(i + d.Hx) + d.sy * (j + d.Hy);
 }
 
+#ifdef __CUDACC__
 // One thread per interior cell of the sub-range, x fastest (coalesced along the contiguous axis).
 // 3-D launch without any integer division: blockIdx.x ↔ x chunk, blockIdx.y ↔ j, blockIdx.z ↔ k
 // (when Ny exceeds the 65535 limit of gridDim.y, j is folded into blockIdx.x).
@@ -219,6 +244,7 @@ inline dim3 cell_grid(const GridDims& d, int block) {
     if (ny <= 65535u) return dim3(chunks, ny, (unsigned)d.Nz);
     return dim3(chunks * ny, 1, (unsigned)d.Nz);
 }
+#endif  // __CUDACC__
 inline long long cell_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0) * d.Nz; }
 inline long long column_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0); }
 
