@@ -89,7 +89,9 @@ static __constant__ double CONST_BANK_DOUBLE = __builtin_bit_cast(double, BITS);
 // the carbonate solve (+6 %: 4 more FP64 instructions per call) — an Estrin variant was slower everywhere (two
 // constants per pair FMA) and is gone.
 #ifndef __CUDACC__
+#undef __constant__
 #define __constant__
+#undef __noinline__
 #define __noinline__
 #endif
 static __constant__ double EXP_C[12] = {  // 1/n!, n = 2 … 13

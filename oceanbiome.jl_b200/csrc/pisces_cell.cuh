@@ -59,6 +59,9 @@ constexpr int NOUT = 24;  // tendencies
 // (x·2¹⁰⁷⁴: 0 → 0, finite → ±Inf or the scaled value, NaN → NaN) done by a select, and min/max as
 // compare + select.  A cell whose FAST results contain a non-finite value (or whose NaN could be swallowed
 // by a min/max) is recomputed with EXACT, so NaN/Inf patterns match the reference everywhere.
+#ifndef OBM_PISCES_ROLL
+#define OBM_PISCES_ROLL 0  // 1: class-symmetric sub-models as real loops (one copy of their code), see cell_tendencies
+#endif
 #ifndef OBM_PISCES_EXP
 #define OBM_PISCES_EXP 0  // 0: library exp; 1: exp_lean of obm_common.cuh (measured: no gain here, r02); 2: exp_horner
 #endif
@@ -235,6 +238,43 @@ __device__ __forceinline__ Zoo zooplankton(const obm_pisces_zoo& z, const double
     r.iron_ff = r.base_ff * flux_Fe * I;
     return r;
 }
+// the same with the number of prey classes as a (warp-uniform) run-time value: the rolled form of the kernel evaluates micro- and
+// mesozooplankton by ONE copy of this code (operation order per class unchanged: a skipped fourth prey adds nothing)
+template <class A>
+__device__ __forceinline__ Zoo zooplankton_n(const obm_pisces_zoo& z, const int N, const double (&food)[4], const double (&iron)[4],
+                                             double I, double fT, double dO2, double flux_C, double flux_Fe) {
+    Zoo r;
+    const double J = z.specific_food_threshold_concentration;
+    const double base = z.maximum_grazing_rate * fT;
+    double total_food = food[0] * z.food_preferences[0];
+    double avail = A::mx(0.0, (food[0] - J)) * z.food_preferences[0];
+    double total_iron = iron[0] * z.food_preferences[0];
+    double s = A::mx(0.0, (food[0] - J)) * z.food_preferences[0] * iron[0];
+#pragma unroll
+    for (int n = 1; n < 4; n++) {
+        if (n < N) {
+            total_food += food[n] * z.food_preferences[n];
+            const double a = A::mx(0.0, (food[n] - J)) * z.food_preferences[n];
+            avail += a;
+            total_iron += iron[n] * z.food_preferences[n];
+            s += a * iron[n];
+        }
+    }
+    const double clg = A::mx(0.0, avail - A::mn(avail / 2, z.food_threshold_concentration));
+    r.tsg = A::div(base * clg, z.grazing_half_saturation + total_food);
+    r.avail = avail;
+    const double igr = A::gdiv(total_iron, z.iron_ratio * r.tsg);
+    r.ge = A::mn(1.0, igr) * A::mn(z.minimum_growth_efficiency, (1 - z.non_assimilated_fraction) * igr);
+    r.gI = r.tsg * I;
+    r.base_ff = z.maximum_flux_feeding_rate * fT;
+    r.gfI = r.base_ff * flux_C * I;
+    const double cf = A::div(I, I + z.mortality_half_saturation);
+    r.mort = fT * I * (z.quadratic_mortality * I + z.linear_mortality * (cf + 3 * dO2));
+    r.lin_mort = fT * z.linear_mortality * (cf + 3 * dO2) * I;
+    r.iron_graze = A::gdiv(s * r.tsg, avail) * I;
+    r.iron_ff = r.base_ff * flux_Fe * I;
+    return r;
+}
 // grazing on one prey — food_quality_dependant.jl:226-255
 template <class A>
 __device__ __forceinline__ double graze_on(const obm_pisces_zoo& z, const Zoo& r, double pref, double prey, double I) {
@@ -261,6 +301,7 @@ __device__ __forceinline__ void cell_tendencies(const PiscesArgs& a, const Input
     // ---- shared scalars --------------------------------------------------------------------------------
     const double shear = c.z < c.zmxl ? p.background_shear : p.mixed_layer_shear;
     const double dO2 = A::mn(1.0, A::mx(0.0, A::div(0.4 * (p.first_anoxia_threshold - c.O2), p.second_anoxia_threshold + c.O2)));
+#if !OBM_PISCES_ROLL
     // b^T once per distinct base (A::ex(T ln b); bases are parameters, ln b is host-evaluated; `same_as`
     // is uniform, so these are uniform branches / selects on scalars — no local array)
     const int s1 = a.same_as[1], s2 = a.same_as[2], s3 = a.same_as[3], s4 = a.same_as[4], s5 = a.same_as[5];
@@ -301,6 +342,67 @@ __device__ __forceinline__ void cell_tendencies(const PiscesArgs& a, const Input
     const double upFe_n = iron_uptake<A>(a, 0, c, n, P), upFe_d = iron_uptake<A>(a, 1, c, d, D);
     put(T_PFe, upFe_n - (deathP + gP) * n.tFe);
     put(T_DFe, upFe_d - (deathD + gD) * d.tFe);
+#else
+    // ROLLED form (-DOBM_PISCES_ROLL=1): the class-symmetric sub-models — nano / diatoms, micro / meso — and the six b^T run
+    // through ONE copy of their code each, in real loops over class-indexed parameters.  Same operations in the same order
+    // per class; what changes is the instruction footprint of the fast path (≈ 54 KB unrolled, against a 32 KB L1.5
+    // instruction cache: ncu shows the GPC instruction cache at 91 % of its request peak, profiles/r02_full_pisces_c4.txt).
+    double fTs[6];
+#pragma unroll 1
+    for (int u = 0; u < 6; u++) {
+        const int from = a.same_as[u];
+        fTs[u] = from < 0 ? A::ex(c.T * a.ln_base[u]) : fTs[from < 0 ? 0 : from];
+    }
+    const double fT[6] = {fTs[0], fTs[1], fTs[2], fTs[3], fTs[4], fTs[5]};
+
+    // ---- phytoplankton ------------------------------------------------------------------------------------
+    Phyto n, d;
+#pragma unroll 1
+    for (int cls = 0; cls < 2; cls++) {
+        const Phyto r = phytoplankton<A>(a, cls, c, cls ? D : P, cls ? DChl : PChl, cls ? DFe : PFe, cls ? fT[1] : fT[0], shear);
+        if (cls) d = r; else n = r;
+    }
+
+    // ---- zooplankton ----------------------------------------------------------------------------------------
+    const double fluxPOC = POC * wPOC, fluxGOC = GOC * wGOC, fluxSFe = SFe * wPOC, fluxBFe = BFe * wGOC;
+    const double tSFe = A::gdiv(SFe, POC);
+    const double food[4] = {P, D, POC, Z};
+    const double iron[4] = {n.tFe, d.tFe, tSFe, p.micro.iron_ratio};
+    Zoo zz, zm;
+    double gP_micro, gP_meso, gD_micro, gD_meso, gPOC_micro, gPOC_meso, gZ_meso;
+#pragma unroll 1
+    for (int q = 0; q < 2; q++) {
+        const obm_pisces_zoo& z = q ? p.meso : p.micro;
+        const double I = q ? M : Z;
+        const Zoo r = zooplankton_n<A>(z, q ? 4 : 3, food, iron, I, q ? fT[3] : fT[2], dO2, fluxPOC + fluxGOC, fluxSFe + fluxBFe);
+        const double g0 = graze_on<A>(z, r, z.food_preferences[0], P, I);
+        const double g1 = graze_on<A>(z, r, z.food_preferences[1], D, I);
+        const double g2 = graze_on<A>(z, r, z.food_preferences[2], POC, I);
+        const double g3 = graze_on<A>(z, r, z.food_preferences[3], Z, I);  // used for meso only (micro_and_meso.jl:36-48)
+        if (q) { zm = r; gP_meso = g0; gD_meso = g1; gPOC_meso = g2; gZ_meso = g3; }
+        else { zz = r; gP_micro = g0; gD_micro = g1; gPOC_micro = g2; }
+    }
+    // grazing(zoo::MicroAndMeso, prey) = micro + meso (micro_and_meso.jl:50-52)
+    const double gP = gP_micro + gP_meso;
+    const double gD = gD_micro + gD_meso;
+    const double gPOC = gPOC_micro + gPOC_meso;
+
+    // ---- P, D, chlorophyll, iron, silicon quotas: mixed_mondo_nano_diatoms.jl:45-112 -----------------
+    const double deathP = (n.lin + n.quad), deathD = (d.lin + d.quad);
+    double upFe_n, upFe_d;
+#pragma unroll 1
+    for (int cls = 0; cls < 2; cls++) {
+        const obm_pisces_phyto& ph = cls ? p.diatoms : p.nano;
+        const Phyto r = cls ? d : n;
+        const double I = cls ? D : P, IChl = cls ? DChl : PChl;
+        const double death = cls ? deathD : deathP, g = cls ? gD : gP;
+        put(cls ? T_D : T_P, (1 - ph.exudated_fraction) * r.muI - death - g);
+        put(cls ? T_DChl : T_PChl, chlorophyll_growth<A>(a, cls, c, r, I, IChl) - (death + g) * r.tChl * 12);
+        const double up = iron_uptake<A>(a, cls, c, r, I);
+        put(cls ? T_DFe : T_PFe, up - (death + g) * r.tFe);
+        if (cls) upFe_d = up; else upFe_n = up;
+    }
+#endif
     // silicate_uptake (diatoms) mixed_mondo.jl:217-248
     double upSi;
     {
