@@ -663,6 +663,8 @@ def inventory_check(w, diag, rank, world, rows_info):
         want += pyoracle.inventory(og, fields, cg, cell_volume=vol)
         mag += pyoracle.inventory(og, [np.abs(f) for f in fields],
                                   pyoracle.make_groups(names, [(tn, tuple(abs(x) for x in sf)) for tn, sf in diag.groups]), cell_volume=vol)
+    if world > 1 and not rows_info:  # independent replicas of the same grid: the all-reduce adds `world` equal inventories
+        want, mag = want * world, mag * world
     err = float(np.max(np.abs(got - want) / mag))
     return {"cells": int(g.Nx * R * g.Nz * (world if rows_info else 1)), "rows_per_rank": R, "max_err_over_sum_abs_terms": err,
             "tolerance": 1e-12, "ok": bool(err <= 1e-12),
@@ -886,8 +888,7 @@ def main():
                               f"({world * np.mean(peaks):.0f} GB/s per direction in aggregate) against {solo:.1f} GB/s for one rank alone")
         if note:
             e2e["note"] = note
-        if we is not w:
-            del we
+        we = None  # (it may be `w` itself: drop the reference so that the weak leg below can free the slab)
 
     # ---- weak-scaling sub-record (N > 1): one full-size grid per GPU ---------------------------------------------------
     weak = None
