@@ -177,7 +177,9 @@ class Workload:
     def _stage_kernels(self, nscaled, sediment):
         """marker label → (kernel, ALGORITHMIC bytes per cell — SURVEY §8d's per-unit figures —, what bounds it)."""
         if self.kind == "pisces":
-            return {"modifiers": ("scale_negative_calcite_kernel", 8 * nscaled + 16 + 8, "issue / FP64 (Ω solve); HBM roof shown"),
+            # 20 distinct scaled tracers (carbon 9, iron + 5, phosphate + 1, silicon + 3, nitrogen + 2) + Alk + T + S read, Ω written
+            # = 192 B (r01 / r02 documents said 200: one field too many)
+            return {"modifiers": ("scale_negative_calcite_kernel", 8 * nscaled + 8 + 16 + 8, "issue / FP64 (Ω solve); HBM roof shown"),
                     "light": ("par_multiband_kernel<3,DIAG>", 16 + 32, "issue / FP64 (1 log + 6 exp per cell); HBM roof shown"),
                     "tendencies": ("pisces_tendency_kernel", 256 + 16 * 24, "latency of dependent FP64 chains; HBM roof shown")}
         npd = {"lobster": 8 * (7 + 1) + 16 * 10, "npzd": 8 * (5 + 1) + 16 * 4}[self.kind]
