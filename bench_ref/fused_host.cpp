@@ -119,6 +119,7 @@ extern "C" int fused_scale_negative_tracers_calcite_saturation(const obm_grid* g
                     v[t] = tracers[t][idx];
                     touched |= (unsigned)__double2hiint(v[t]) >= 0x7ff00000u;
                 }
+                if (d.bottom != nullptr && (long long)k + 1 < d.bottom[pidx(d, i, j)]) touched = false;  // immersed cell
                 if (touched) {  // negative_tracers.cu scale_cell
                     unsigned dirty = 0;
                     for (int q = 0; q < ngroups; q++) {

@@ -54,6 +54,12 @@ typedef struct obm_grid {
     int32_t i0, i1, j0, j1; /* half-open 0-based interior sub-range; i1<=0 → Nx, j1<=0 → Ny   */
     const double* zc;       /* DEVICE: parent of z centres, Nz+2Hz entries, cell k at zc[k+Hz] */
     const double* zf;       /* DEVICE: parent of z faces, Nz+1+2Hz entries, face k at zf[k+Hz] */
+    /* Immersed boundary (grid-fitted bottom), nullable: DEVICE x–y plane (parent layout, halos included) of the 1-based
+     * index of the bottom-most ACTIVE cell of every column, as `calculate_bottom_indices` returns it
+     * (src/Sediments/bottom_indices.jl:19-26; obm_find_bottom_cells).  Cells below it are `immersed_cell`s: the kernels
+     * the reference guards with `!immersed_cell(i, j, k, grid)` — ScaleNegativeTracers, src/Utils/negative_tracers.jl:194,253
+     * — leave them untouched.  NULL = no immersed cells. */
+    const int64_t* bottom_indices_xy;
 } obm_grid;
 
 /* ------------------------------------------------------------------------------------

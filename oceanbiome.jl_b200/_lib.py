@@ -36,6 +36,7 @@ class obm_grid(C.Structure):
         ("Hx", C.c_int32), ("Hy", C.c_int32), ("Hz", C.c_int32),
         ("i0", C.c_int32), ("i1", C.c_int32), ("j0", C.c_int32), ("j1", C.c_int32),
         ("zc", C.c_void_p), ("zf", C.c_void_p),
+        ("bottom_indices_xy", C.c_void_p),  # nullable: 1-based bottom-most active cell per column (immersed boundary)
     ]
 
 

@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(SN_BLOCK) scale_negative_kernel(const __grid_c
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
+    if (immersed_cell(a.d, i, j, k)) return;  // negative_tracers.jl:194,253
     scale_cell(a, sm + threadIdx.x, cell_index(a.d, i, j, k));
 }
 
@@ -107,10 +108,13 @@ __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_ca
     const long long idx = cell_index(a.s.d, i, j, k);
     double* mine = sm + threadIdx.x;
     const double T = a.T[idx], S = a.S[idx];  // never rescaled (not members of any conserved group)
-    scale_cell(a.s, mine, idx);
-    const double DIC = a.iDIC >= 0 ? mine[a.iDIC * SN_BLOCK] : a.DIC[idx];
-    const double Alk = a.iAlk >= 0 ? mine[a.iAlk * SN_BLOCK] : a.Alk[idx];
-    const double Si = a.iSi >= 0 ? mine[a.iSi * SN_BLOCK] : a.Si[idx];
+    // an immersed cell is not rescaled (negative_tracers.jl:194,253); Ω is still computed there, from the values as they
+    // are — compute_calcite_saturation! has no such guard (PISCES/compute_calcite_saturation.jl:9-37)
+    const bool dry = immersed_cell(a.s.d, i, j, k);
+    if (!dry) scale_cell(a.s, mine, idx);
+    const double DIC = (a.iDIC >= 0 && !dry) ? mine[a.iDIC * SN_BLOCK] : a.DIC[idx];
+    const double Alk = (a.iAlk >= 0 && !dry) ? mine[a.iAlk * SN_BLOCK] : a.Alk[idx];
+    const double Si = (a.iSi >= 0 && !dry) ? mine[a.iSi * SN_BLOCK] : a.Si[idx];
     const double P = fabs(a.s.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;  // compute_calcite_saturation.jl:27
     a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, T, S, DIC, Alk, P, true, Si, false, 0.0, false, 0.0, a.H_init,
                                    a.iterations, a.Hst ? a.Hst + idx : nullptr);

@@ -188,6 +188,7 @@ struct GridDims {
     long long sy, sz;  // element strides of the parent array (sx = 1)
     const double* zc;  // shifted so that zc[k] is interior level k (k = -Hz … Nz-1+Hz valid)
     const double* zf;
+    const long long* bottom;  // nullable: 1-based index of the bottom-most active cell per column (x–y parent plane)
 };
 
 inline int make_dims(const obm_grid* g, GridDims* d, bool need_z) {
@@ -201,6 +202,7 @@ inline int make_dims(const obm_grid* g, GridDims* d, bool need_z) {
     d->j1 = g->j1 > 0 ? g->j1 : g->Ny;
     OBM_REQUIRE(d->i0 >= 0 && d->i1 <= g->Nx && d->i0 < d->i1 && d->j0 >= 0 && d->j1 <= g->Ny && d->j0 < d->j1,
                 OBM_ESIZE, "bad sub-range i=[%d,%d) j=[%d,%d)", d->i0, d->i1, d->j0, d->j1);
+    d->bottom = (const long long*)g->bottom_indices_xy;
     d->sy = (long long)g->Nx + 2 * g->Hx;
     d->sz = d->sy * ((long long)g->Ny + 2 * g->Hy);
     if (need_z) {
@@ -247,6 +249,10 @@ inline dim3 cell_grid(const GridDims& d, int block) {
     return dim3(chunks * ny, 1, (unsigned)d.Nz);
 }
 #endif  // __CUDACC__
+// `immersed_cell(i, j, k, grid)` of a grid-fitted bottom: below the bottom-most active cell of the column
+__device__ __forceinline__ bool immersed_cell(const GridDims& d, int i, int j, int k) {
+    return d.bottom != nullptr && (long long)k + 1 < d.bottom[plane_index(d, i, j)];
+}
 inline long long cell_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0) * d.Nz; }
 inline long long column_count(const GridDims& d) { return (long long)(d.i1 - d.i0) * (d.j1 - d.j0); }
 

@@ -122,8 +122,20 @@ class RectilinearGrid:
     def c_grid(self, i0=None, i1=None, j0=None, j1=None) -> _lib.obm_grid:
         r = getattr(self, "_subrange", (0, 0, 0, 0))
         i0, i1, j0, j1 = (r[n] if v is None else v for n, v in enumerate((i0, i1, j0, j1)))
+        bottom = getattr(self, "bottom_indices", None)
         return _lib.obm_grid(self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz, i0, i1, j0, j1,
-                             self.zc_dev.data_ptr(), self.zf_dev.data_ptr())
+                             self.zc_dev.data_ptr(), self.zf_dev.data_ptr(), bottom.data_ptr() if bottom is not None else None)
+
+    def immersed(self, bottom_height: "Field") -> "RectilinearGrid":
+        """`ImmersedBoundaryGrid(grid, GridFittedBottom(bottom_height))` restricted to what the path reads: the index of
+        the bottom-most active cell of every column (`calculate_bottom_indices`, src/Sediments/bottom_indices.jl:19-26).
+        Kernels the reference guards with `!immersed_cell(i, j, k, grid)` — ScaleNegativeTracers — then leave the cells
+        below it untouched.  Returns a grid sharing everything else with this one."""
+        from .sediments import calculate_bottom_indices
+        g = type(self).__new__(type(self))
+        g.__dict__.update(self.__dict__)
+        g.bottom_indices = calculate_bottom_indices(self, bottom_height)
+        return g
 
     @contextlib.contextmanager
     def restrict(self, j0: int, j1: int, i0: int = 0, i1: int = 0):

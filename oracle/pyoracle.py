@@ -82,14 +82,17 @@ def set_threads(n: int):
 class Grid:
     """Host twin of oceanbiome_b200.RectilinearGrid for the oracle: same sizes/halos, host z arrays."""
 
-    def __init__(self, Nx, Ny, Nz, Hx, Hy, Hz, zc_parent, zf_parent):
+    def __init__(self, Nx, Ny, Nz, Hx, Hy, Hz, zc_parent, zf_parent, bottom_indices=None):
         self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz = Nx, Ny, Nz, Hx, Hy, Hz
         self.zc_parent = np.ascontiguousarray(zc_parent, dtype=np.float64)
         self.zf_parent = np.ascontiguousarray(zf_parent, dtype=np.float64)
+        # immersed boundary: int64 x–y parent plane of 1-based bottom-most active cells (or None)
+        self.bottom_indices = None if bottom_indices is None else np.ascontiguousarray(bottom_indices, dtype=np.int64)
 
     @classmethod
     def like(cls, g):
-        return cls(g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz, g.zc_host, g.zf_host)
+        b = getattr(g, "bottom_indices", None)
+        return cls(g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz, g.zc_host, g.zf_host, None if b is None else b.cpu().numpy())
 
     @property
     def parent_shape(self):
@@ -106,7 +109,8 @@ class Grid:
 
     def c_grid(self, i0=0, i1=0, j0=0, j1=0):
         return abi.obm_grid(self.Nx, self.Ny, self.Nz, self.Hx, self.Hy, self.Hz, i0, i1, j0, j1,
-                            self.zc_parent.ctypes.data, self.zf_parent.ctypes.data)
+                            self.zc_parent.ctypes.data, self.zf_parent.ctypes.data,
+                            None if self.bottom_indices is None else self.bottom_indices.ctypes.data)
 
 
 def _ptr(a):

@@ -24,6 +24,8 @@ int orc_scale_negative_group(const obm_grid* g, int n, double* const* fields, co
         for (int j = j0; j < j1; j++)
             for (int i = i0; i < i1; i++) {
                 int64_t idx = cell_index(g, i, j, k);
+                /* `if !immersed_cell(i, j, k, grid)` :253 — grid-fitted bottom: below the bottom-most active cell */
+                if (g->bottom_indices_xy && (int64_t)k + 1 < g->bottom_indices_xy[plane_index(g, i, j)]) continue;
                 double t = 0.0, p = 0.0;
                 for (int f = 0; f < n; f++) {
                     double value = fields[f][idx];

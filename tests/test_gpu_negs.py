@@ -122,6 +122,33 @@ def test_absorbed_negative_member_is_still_zeroed(cuda, oracle):
         assert np.array_equal(og.interior(got)[~touched], og.interior(before[n])[~touched]), n  # clean cells: bit for bit
 
 
+def test_immersed_cells_are_left_alone(cuda, oracle):
+    """Grid-fitted bottom: `grid.immersed(bottom_height)` = `ImmersedBoundaryGrid(grid, GridFittedBottom(h))`; the scaling
+    kernels skip the cells below the bottom-most active one like the reference's `!immersed_cell` guard
+    (negative_tracers.jl:194,253) — against the oracle, bit for bit where nothing is rescaled."""
+    base = ob.RectilinearGrid(size=(29, 7, 13), extent=(29, 7, 130), device=cuda)
+    h = ob.Field2D(base, "bottom_height")
+    synthetic.fill_torch(h, "bottom_height", -140.0, -5.0)
+    grid = base.immersed(h)
+    names = ("P", "Z", "NO₃", "NH₄")
+    dev, host, og = synthetic_state(grid, names, {n: (-0.4, 1.0, False) for n in names})
+    assert og.bottom_indices is not None and og.interior(og.bottom_indices).max() > 3
+    before = {n: host[n].copy() for n in names}
+    groups = [(names, (1, 1, 1, 1))]
+    scalers = tuple(ob.ScaleNegativeTracers(t, s) for t, s in groups)
+    ob.biogeochemistry._update_modifiers(M(grid, dev), scalers, None)
+    oracle.scale_negative_tracers(og, [host[n] for n in names], oracle.make_groups(names, groups))
+    kb = og.interior(og.bottom_indices)[0] - 1                       # 0-based bottom-most active k per column
+    dry = np.arange(grid.Nz).reshape(-1, 1, 1) < kb[None]            # immersed cells
+    assert dry.any() and (~dry).any()
+    for n in names:
+        got = dev[n].data.cpu().numpy()
+        assert np.array_equal(og.interior(got)[dry], og.interior(before[n])[dry]), n   # untouched, negatives included
+        assert (og.interior(got)[~dry] >= 0).all(), n
+        assert np.array_equal(got == 0, host[n] == 0) and np.all(np.abs(got - host[n]) <= 1e-12 * np.maximum(np.abs(host[n]), 1.0)), n
+    assert (og.interior(dev["P"].data.cpu().numpy())[dry] < 0).any()
+
+
 def test_zero_negative_bit_exact(cuda, oracle):
     grid = ob.RectilinearGrid(size=(13, 5, 7), extent=(13, 5, 7), device=cuda)
     dev, host, og = synthetic_state(grid, ["A", "B", "C"], {n: (-1.0, 1.0, False) for n in "ABC"})

@@ -90,3 +90,23 @@ def test_group_order_matters(oracle):
         r.append([og.interior(a)[0, 0, 0] for a in f])
     np.testing.assert_allclose(r[0], [0.0, 2 / 3, 1 / 3, 0.0], rtol=1e-15)  # g1: B, C ×2/3; g2: C = 4/3·(1/3)/(4/3)
     np.testing.assert_allclose(r[1], [0.0, 0.5, 0.5, 0.0], rtol=1e-15)      # g2: C = 1; g1: B, C ×1/2
+
+
+def test_immersed_cells_are_left_alone(oracle):
+    """`if !immersed_cell(i, j, k, grid)` (negative_tracers.jl:194,253) with a grid-fitted bottom: cells below the
+    bottom-most active cell of a column (1-based `bottom_indices`, bottom_indices.jl:19-26) keep their values, negative or
+    not; the active cells of the same column are rescaled as usual."""
+    g = ob.RectilinearGrid(size=(3, 2, 5), extent=(3, 2, 50), device="cpu")
+    bottom = np.ones(oracle.Grid.like(g).plane_shape, dtype=np.int64)
+    og0 = oracle.Grid.like(g)
+    og0.interior(bottom)[0, :, :] = [[1, 3, 5], [2, 1, 4]]   # bottom-most active cell (1-based k) of the six columns
+    og = oracle.Grid(g.Nx, g.Ny, g.Nz, g.Hx, g.Hy, g.Hz, g.zc_host, g.zf_host, bottom)
+    names = ("N", "P")
+    N, P = cell(og, 2.0), cell(og, -1.0)
+    oracle.scale_negative_tracers(og, [N, P], oracle.make_groups(names, [(names, (1, 1))]))
+    for j in range(2):
+        for i in range(3):
+            kb = og.interior(bottom)[0, j, i] - 1
+            for k in range(5):
+                want = (2.0, -1.0) if k < kb else (1.0, 0.0)
+                assert (og.interior(N)[k, j, i], og.interior(P)[k, j, i]) == want, (i, j, k)
