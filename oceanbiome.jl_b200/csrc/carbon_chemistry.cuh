@@ -33,6 +33,9 @@ namespace cc {
 #ifndef OBM_CC_LOG
 #define OBM_CC_LOG 1
 #endif
+#ifndef OBM_CC_BATCH
+#define OBM_CC_BATCH 1  // the lean exp / log of the equilibrium constants branch-free in one basic block (see constants())
+#endif
 __device__ __forceinline__ double cexp(double x) {
 #if OBM_CC_EXP == 0
     return exp(x);
@@ -99,13 +102,21 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     constexpr double LN10 = 2.302585092994045684;
     const double T = Tc_in + KD(273.15);
     const double invT = rcp_fast(T);
-    const double logT = clog(T);
     const double sqS = sqrt(S);
     const double S15 = S * sqS;
     const double Is = KD(19.924) * S * rcp_fast(1000.0 + KD(-1.005) * S);  // :341
     const double sqIs = sqrt(Is);
     const double Is15 = Is * sqIs;
+#if OBM_CC_LOG == 1 && OBM_CC_BATCH
+    // both logarithms branch-free in ONE basic block (their chains interleave); a single, rarely taken branch redoes
+    // them with the library when an argument is not a positive normal number
+    const double argS1 = 1 + KD(-0.001005) * S;
+    double logT = log_unguarded(T), logS1 = log_unguarded(argS1);
+    if (!(log_in_range(T) & log_in_range(argS1))) { logT = log(T); logS1 = log(argS1); }
+#else
+    const double logT = clog(T);
     const double logS1 = clog(1 + KD(-0.001005) * S);
+#endif
     double Tc = 0, inv_RT = 0;
     if (HAS_P) {
         Tc = T - KD(273.15);
@@ -134,12 +145,36 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
         eS += ln_pc(KD(-18.03), KD(0.0466), KD(0.000316), KD(-0.00453), KD(0.00009), Tc, P, inv_RT);
         eF += ln_pc(KD(-9.78), KD(-0.0090), KD(-0.000942), KD(-0.00391), KD(0.000054), Tc, P, inv_RT);
     }
+    // KSi :706-713 (no pressure correction)
+    const double eSi = KD(117.385) + KD(-8904.2) * invT + KD(-19.334) * logT + (KD(3.5913) + KD(-458.79) * invT) * sqIs
+                       + (KD(-1.5998) + KD(188.74) * invT) * Is + (KD(0.07871) + KD(-12.1652) * invT) * (Is * Is) + logS1;
+    c.KSi = 1.0;
+#if OBM_CC_EXP == 2 && OBM_CC_BATCH
+    // The kernel is bound by the LATENCY of dependent FP64 chains at 6 – 8 warps per scheduler (ncu, r3a: issue 66 %, FP64
+    // pipe 62 %, neither saturated), and a guarded exp is its own basic block: six serial Horner chains.  Branch-free in
+    // one block the six chains interleave; ONE combined range test (integer compares) sends the rare out-of-range or
+    // NaN exponent through the library for all six.
+    c.K1 = exp_unguarded(e1);
+    c.K2 = exp_unguarded(e2);
+    c.KB = exp_unguarded(eB);
+    c.KW = exp_unguarded(eW);
+    c.KS = exp_unguarded(eS);
+    c.KF = exp_unguarded(eF);
+    if (need_silicate) c.KSi = exp_unguarded(eSi);
+    if (!(exp_in_range(e1) & exp_in_range(e2) & exp_in_range(eB) & exp_in_range(eW) & exp_in_range(eS) & exp_in_range(eF)
+          & (!need_silicate | exp_in_range(eSi)))) {
+        c.K1 = exp(e1); c.K2 = exp(e2); c.KB = exp(eB); c.KW = exp(eW); c.KS = exp(eS); c.KF = exp(eF);
+        if (need_silicate) c.KSi = exp(eSi);
+    }
+#else
+    if (need_silicate) c.KSi = cexp(eSi);
     c.K1 = cexp(e1);
     c.K2 = cexp(e2);
     c.KB = cexp(eB);
     c.KW = cexp(eW);
     c.KS = cexp(eS);
     c.KF = cexp(eF);
+#endif
     c.KP1 = c.KP2 = c.KP3 = 1.0;
     if (need_phosphate) {  // KP1-3 :523-529, :558-651
         double p1 = KD(115.525) + KD(-4576.752) * invT + KD(-18.453) * logT + (KD(0.69171) + KD(-106.736) * invT) * sqS + (KD(-0.01844) + KD(-0.65643) * invT) * S;
@@ -154,10 +189,6 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
         c.KP2 = cexp(p2);
         c.KP3 = cexp(p3);
     }
-    c.KSi = 1.0;
-    if (need_silicate)  // KSi :706-713 (no pressure correction)
-        c.KSi = cexp(KD(117.385) + KD(-8904.2) * invT + KD(-19.334) * logT + (KD(3.5913) + KD(-458.79) * invT) * sqIs + (KD(-1.5998) + KD(188.74) * invT) * Is
-                    + (KD(0.07871) + KD(-12.1652) * invT) * (Is * Is) + logS1);
     c.Tk = T;
     c.Is = Is;
     c.sqrtS = sqS;

@@ -157,9 +157,10 @@ __device__ __forceinline__ double exp_horner(double x) {
 // (s² ≤ 0.0295 ⇒ truncation < 2⁻⁵⁵), ln x = e·ln2 + ln m with ln2 split in two.  ≤ 2 ulp; ≈ 30 instructions against
 // ≈ 60 for the library log (two of them per solve: ln T and ln(1 − 0.001005 S)).  Anything else (≤ 0, subnormal, ±Inf,
 // NaN) takes the library log, inline in the cold branch.
-__device__ __forceinline__ double log_lean(double x) {
+// positive and normal ⇔ one unsigned compare of the high word
+__device__ __forceinline__ bool log_in_range(double x) { return (unsigned)(__double2hiint(x) - 0x00100000) < 0x7fe00000u; }
+__device__ __forceinline__ double log_unguarded(double x) {  // valid for positive normal x only (see log_in_range)
     const int hi = __double2hiint(x);
-    if ((unsigned)(hi - 0x00100000) >= 0x7fe00000u) return log(x);
     int e = (hi >> 20) - 1023;
     int mh = (hi & 0x000fffff) | 0x3ff00000;      // m ∈ [1, 2)
     const bool up = mh >= 0x3ff6a09f;              // m ≥ √2 (to 2⁻²⁰): halve it
@@ -180,6 +181,10 @@ __device__ __forceinline__ double log_lean(double x) {
     const double lm = fma(s * z, q, 2.0 * s);      // ln m
     const double ef = (double)e;
     return fma(ef, KD(6.93147180369123816490e-01), fma(ef, KD(1.90821492927058770002e-10), lm));
+}
+__device__ __forceinline__ double log_lean(double x) {
+    if (!log_in_range(x)) return log(x);
+    return log_unguarded(x);
 }
 // ---- grid indexing -----------------------------------------------------------------------------
 struct GridDims {
