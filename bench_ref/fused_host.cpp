@@ -98,7 +98,7 @@ extern "C" int fused_pisces_tendencies(const obm_grid* grid, const obm_pisces_pa
 extern "C" int fused_scale_negative_tracers_calcite_saturation(const obm_grid* grid, int ntracers, double* const* tracers, int ngroups,
                                                                const obm_scale_group* groups, double fill, const double* T,
                                                                const double* S, const double* DIC, const double* Alk,
-                                                               const double* Si, double* Omega) {
+                                                               const double* Si, double* Omega, int level_tables) {
     GridDims d;
     int rc = make_dims(grid, &d, true);
     if (rc) return rc;
@@ -108,6 +108,10 @@ extern "C" int fused_scale_negative_tracers_calcite_saturation(const obm_grid* g
         if (tracers[t] == Alk) iAlk = t;
         if (tracers[t] == Si) iSi = t;
     }
+    // what the first threads of a block build in shared memory: the level's TEOS-10 and pressure-correction tables
+    cc::LevelTables* tables = new cc::LevelTables[d.Nz];
+    for (int k = 0; k < d.Nz; k++)
+        for (int n = 0; n < 64; n++) cc::fill_level_entry(tables[k], fabs(d.zc[k]) * 9.80665 * 1026.0 / 100000.0, n);
 #pragma omp parallel for collapse(2) schedule(static)
     for (int k = 0; k < d.Nz; k++)
         for (int j = d.j0; j < d.j1; j++)
@@ -148,8 +152,10 @@ extern "C" int fused_scale_negative_tracers_calcite_saturation(const obm_grid* g
                 }
                 const double P = fabs(d.zc[k]) * 9.80665 * 1026.0 / 100000.0;
                 Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, T[idx], S[idx], iDIC >= 0 ? v[iDIC] : DIC[idx], iAlk >= 0 ? v[iAlk] : Alk[idx],
-                                             P, true, iSi >= 0 ? v[iSi] : Si[idx], false, 0.0, false, 0.0, 1e-8, 12, nullptr);
+                                             P, true, iSi >= 0 ? v[iSi] : Si[idx], false, 0.0, false, 0.0, 1e-8, 12, nullptr,
+                                             level_tables ? &tables[k] : nullptr);
             }
+    delete[] tables;
     return 0;
 }
 

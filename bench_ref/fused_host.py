@@ -64,12 +64,13 @@ def pisces_tendencies(grid, params, tracers, aux: dict, G=None, accumulate=False
     return G
 
 
-def scale_negative_tracers_calcite_saturation(grid, tracers, groups, T, S, DIC, Alk, Si, Omega=None, fill=float("nan")):
+def scale_negative_tracers_calcite_saturation(grid, tracers, groups, T, S, DIC, Alk, Si, Omega=None, fill=float("nan"),
+                                              level_tables=True):
     Omega = np.zeros(grid.parent_shape) if Omega is None else Omega
     cg = grid.c_grid()
     rc = lib().fused_scale_negative_tracers_calcite_saturation(
         C.byref(cg), len(tracers), _table(tracers), len(groups), groups, C.c_double(fill), C.c_void_p(_ptr(T)), C.c_void_p(_ptr(S)),
-        C.c_void_p(_ptr(DIC)), C.c_void_p(_ptr(Alk)), C.c_void_p(_ptr(Si)), C.c_void_p(_ptr(Omega)))
+        C.c_void_p(_ptr(DIC)), C.c_void_p(_ptr(Alk)), C.c_void_p(_ptr(Si)), C.c_void_p(_ptr(Omega)), 1 if level_tables else 0)
     assert rc == 0
     return Omega
 

@@ -32,13 +32,21 @@ struct OmegaArgs {
 };
 
 __global__ void __launch_bounds__(128) calcite_saturation_kernel(const __grid_constant__ OmegaArgs a) {
+#if OBM_CC_LEVEL
+    __shared__ cc::LevelTables level;  // the block's z-level fixes the pressure (see carbon_chemistry.cuh)
+    cc::fill_level_entry(level, fabs(a.d.zc[blockIdx.z]) * 9.80665 * 1026.0 / 100000.0, threadIdx.x);
+    __syncthreads();
+    const cc::LevelTables* lvl = &level;
+#else
+    const cc::LevelTables* lvl = nullptr;
+#endif
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
     // P = abs(z) * g * 1026 / 100000 with g = Oceananigans.defaults.gravitational_acceleration
     const double P = fabs(a.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;
     a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, a.T[idx], a.S[idx], a.DIC[idx], a.Alk[idx], P, true, a.Si[idx],
-                                   false, 0.0, false, 0.0, a.H_init, a.iterations, a.Hst ? a.Hst + idx : nullptr);
+                                   false, 0.0, false, 0.0, a.H_init, a.iterations, a.Hst ? a.Hst + idx : nullptr, lvl);
 }
 
 static void defaults(const obm_carbchem_params* p, int* iterations, double* pH0) {

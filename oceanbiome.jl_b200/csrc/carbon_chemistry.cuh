@@ -80,6 +80,91 @@ __device__ __forceinline__ double teos10_rho(double T, double Sp, double Pbar) {
     return r0 + (((rp3 * z + rp2) * z + rp1) * z + rp0);
 }
 
+// ---- per-level tables: everything of the Ω solve that depends on PRESSURE only -------------------------------------------------
+// In the gridded kernels a block works on one z-level (blockIdx.z = k), so the pressure is uniform over its threads.  The
+// TEOS-10 polynomial collapses in ζ = −10 P / 10⁴ to a bivariate one in (s, τ): C_ij = Σ_k R_ijk ζ^k, 28 coefficients
+// (+ r₀(ζ) in C_00), and every pressure correction ln Pc = (−ΔV + ½ Δκ P) P / (R T) becomes (A₀ + A₁ T_c + A₂ T_c²) / T
+// with A_n(P).  The first threads of the block build the 49 numbers once in shared memory; each cell then spends 27
+// FMAs on the density instead of ≈ 60 and 4 FP64 operations per correction instead of 8 (7 corrections): ≈ 60 of the
+// ≈ 790 FP64 instructions per cell of the fused scaling + Ω kernel, which is bound by exactly those (ncu r3a: FP64 pipe
+// 62 %, issue 66 %, 6 warps per scheduler).  Same polynomial, same coefficients, different association: ρ agrees to
+// 1e-16, Ω to 1e-13 with the direct form (tests/test_fused_host.py; tests/test_gpu_pisces.py against the oracle).
+#ifndef OBM_CC_LEVEL
+#define OBM_CC_LEVEL 1
+#endif
+struct LevelTables {
+    double rho[28];    // C_ij in the Horner order of teos10_rho's ζ⁰ block
+    double pc[7][3];   // A₀, A₁, A₂ of K1, K2, KB, KW, KS, KF, KSP(calcite)
+};
+static __constant__ double TEOS_R[28][4] = {  // R_ij0 … R_ij3; (i, j) = powers of (s, τ)
+    {-1.9083568888e-01, 0, 0, 0},                                                   // (0,6)
+    {4.8169980163e-01, 0, 0, 0},                                                    // (1,5)
+    {5.4048723791e-01, 0, 0, 0},                                                    // (0,5)
+    {-5.3563304045e+00, 0, 0, 0},                                                   // (2,4)
+    {1.1311538584e+01, 0, 0, 0},                                                    // (1,4)
+    {-8.3627885467e+00, 5.5927935970e-01, 0, 0},                                    // (0,4)
+    {-3.1742946532e+00, 0, 0, 0},                                                   // (3,3)
+    {1.9717078466e+01, 0, 0, 0},                                                    // (2,3)
+    {-3.3449108469e+01, -5.5077101279e-01, 0, 0},                                   // (1,3)
+    {2.1661789529e+01, -2.4649669534e+00, 0, 0},                                    // (0,3)
+    {-5.4723692739e+00, 0, 0, 0},                                                   // (4,2)
+    {2.9130021253e+01, 0, 0, 0},                                                    // (3,2)
+    {-6.0362551501e+01, -1.8795372996e+00, 0, 0},                                   // (2,2)
+    {6.1548258127e+01, 3.5063081279e+00, 0, 0},                                     // (1,2)
+    {-3.7074170417e+01, 6.7080479603e+00, -1.2419983026e+00, 0},                    // (0,2)
+    {-1.9193502195e+00, 0, 0, 0},                                                   // (5,1)
+    {1.7681814114e+01, 0, 0, 0},                                                    // (4,1)
+    {-5.6888046321e+01, -6.5399043664e-01, 0, 0},                                   // (3,1)
+    {8.1770425108e+01, 5.0042598061e+00, 0, 0},                                     // (2,1)
+    {-6.5281885265e+01, -4.4870114575e+00, -2.1311365518e-01, 0},                   // (1,1)
+    {2.6010145068e+01, -1.3336301113e+01, 2.0564311499e+00, 3.7969820455e-01},      // (0,1)
+    {-6.0579916612e+01, 0, 0, 0},                                                   // (6,0)
+    {4.3227585684e+02, 0, 0, 0},                                                    // (5,0)
+    {-1.2849161071e+03, 6.6051753097e+00, 0, 0},                                    // (4,0)
+    {2.0375295546e+03, -3.0938076334e+01, 0, 0},                                    // (3,0)
+    {-1.7864682637e+03, 5.0774768218e+01, 2.5019633244e+00, 0},                     // (2,0)
+    {8.6672408165e+02, -4.2549998214e+01, -4.9527603989e+00, -1.8507636718e-02},    // (1,0)
+    {8.0189615746e+02, 1.9681925209e+01, 2.0660924175e+00, -2.3342758797e-02}};     // (0,0)
+static __constant__ double TEOS_R0[6] = {4.6494977072e+01, -5.2099962525e+00, 2.2601900708e-01, 6.4326772569e-02,
+                                         1.5616995503e-02, -1.7243708991e-03};
+static __constant__ double PC_TABLE[7][5] = {  // a0, a1, a2, b0, b1 — equilibrium_constants.jl pressure corrections
+    {-25.50, 0.1271, 0.0, -0.00308, 0.0000877},          // K1
+    {-15.82, -0.0219, 0.0, 0.00113, -0.0001475},         // K2
+    {-29.48, 0.1622, -0.0026080, -0.00284, 0.0},         // KB
+    {-20.02, 0.1119, -0.001409, -0.00513, 0.0000794},    // KW
+    {-18.03, 0.0466, 0.000316, -0.00453, 0.00009},       // KS
+    {-9.78, -0.0090, -0.000942, -0.00391, 0.000054},     // KF
+    {-48.76, 0.5304, -0.0, -0.01176, 0.0003692}};        // KSP calcite
+enum { LVL_K1 = 0, LVL_K2, LVL_KB, LVL_KW, LVL_KS, LVL_KF, LVL_KSP };
+
+// entry `n` of the tables of the level at pressure P (bar); n = 0 … 27: density, 32 … 52: corrections (one per thread)
+__device__ __forceinline__ void fill_level_entry(LevelTables& t, double P, int n) {
+    if (n < 28) {
+        const double z = -(10.0 * P) * 1e-4;
+        double c = ((TEOS_R[n][3] * z + TEOS_R[n][2]) * z + TEOS_R[n][1]) * z + TEOS_R[n][0];
+        if (n == 27)
+            c += (((((TEOS_R0[5] * z + TEOS_R0[4]) * z + TEOS_R0[3]) * z + TEOS_R0[2]) * z + TEOS_R0[1]) * z + TEOS_R0[0]) * z;
+        t.rho[n] = c;
+    } else if (n >= 32 && n < 32 + 21) {
+        const int which = (n - 32) / 3, q = (n - 32) - 3 * which;
+        const double* a = PC_TABLE[which];
+        const double PR = P * (1.0 / 83.14472);
+        t.pc[which][q] = q == 0 ? (-a[0] + 0.5 * a[3] * P) * PR : (q == 1 ? (-a[1] + 0.5 * a[4] * P) * PR : -a[2] * PR);
+    }
+}
+__device__ __forceinline__ double teos10_rho_level(double T, double Sp, const double* C) {
+    const double t = T * KD(0.025);
+    const double s = sqrt((Sp + 32.0) * KD(1.0 / (40.0 * 35.16504 / 35.0)));
+    return (((((C[0] * t + C[1] * s + C[2]) * t + (C[3] * s + C[4]) * s + C[5]) * t + ((C[6] * s + C[7]) * s + C[8]) * s + C[9]) * t
+             + (((C[10] * s + C[11]) * s + C[12]) * s + C[13]) * s + C[14]) * t
+            + ((((C[15] * s + C[16]) * s + C[17]) * s + C[18]) * s + C[19]) * s + C[20]) * t
+           + (((((C[21] * s + C[22]) * s + C[23]) * s + C[24]) * s + C[25]) * s + C[26]) * s + C[27];
+}
+// ln of a pressure correction from the level's table
+__device__ __forceinline__ double ln_pc_level(const LevelTables* l, int which, double Tc, double Tc2, double invT) {
+    return (l->pc[which][0] + l->pc[which][1] * Tc + l->pc[which][2] * Tc2) * invT;
+}
+
 struct PC { double a0, a1, a2, b0, b1; };
 // ln of the pressure-correction factor, equilibrium_constants.jl:29-38
 __device__ __forceinline__ double ln_pc(double a0, double a1, double a2, double b0, double b1, double Tc, double P,
@@ -98,7 +183,7 @@ struct Constants {
 // all equilibrium constants of carbon_chemistry.jl:140-149 (defaults of :66-87)
 template <bool HAS_P>
 __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool need_phosphate, bool need_silicate,
-                                          Constants& c) {
+                                          Constants& c, const LevelTables* lvl = nullptr) {
     constexpr double LN10 = 2.302585092994045684;
     const double T = Tc_in + KD(273.15);
     const double invT = rcp_fast(T);
@@ -137,7 +222,15 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
                 + (KD(-771.54) + 35474.0 * invT + KD(114.723) * logT) * Is + -2698.0 * Is15 * invT + 1776.0 * (Is * Is) * invT + logS1;
     // KF :481-487 (log(1 + 0·S) terms are exactly 0)
     double eF = KD(-9.68) + 874.0 * invT + KD(0.111) * sqS;
-    if (HAS_P) {
+    if (HAS_P && lvl != nullptr) {
+        const double Tc2 = Tc * Tc;
+        e1 += ln_pc_level(lvl, LVL_K1, Tc, Tc2, invT);
+        e2 += ln_pc_level(lvl, LVL_K2, Tc, Tc2, invT);
+        eB += ln_pc_level(lvl, LVL_KB, Tc, Tc2, invT);
+        eW += ln_pc_level(lvl, LVL_KW, Tc, Tc2, invT);
+        eS += ln_pc_level(lvl, LVL_KS, Tc, Tc2, invT);
+        eF += ln_pc_level(lvl, LVL_KF, Tc, Tc2, invT);
+    } else if (HAS_P) {
         e1 += ln_pc(-25.50, KD(0.1271), 0.0, KD(-0.00308), KD(0.0000877), Tc, P, inv_RT);
         e2 += ln_pc(KD(-15.82), KD(-0.0219), 0.0, KD(0.00113), KD(-0.0001475), Tc, P, inv_RT);
         eB += ln_pc(KD(-29.48), KD(0.1622), KD(-0.0026080), KD(-0.00284), 0.0, Tc, P, inv_RT);
@@ -326,13 +419,17 @@ __device__ __forceinline__ double K0(double T, double logT, double S) {
 
 // KSP calcite — equilibrium_constants.jl:754-764, :789-810 (the log10(T) in a "ln K" is the reference's, :758)
 template <bool HAS_P>
-__device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P) {
+__device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P, const LevelTables* lvl = nullptr) {
     constexpr double LN10 = 2.302585092994045684;
     const double iT = rcp_fast(T);
     const double therm = KD(-171.9065) + KD(-0.077993) * T + KD(2839.319) * iT + KD(71.595) * (logT * KD(1.0 / LN10));
     const double sea = ((KD(-0.77712) + KD(0.0028426) * T + KD(178.34) * iT) * sqS + KD(-0.07711) * S + KD(0.0041249) * (S * sqS));
     double e = (therm + sea) * KD(LN10);
-    if (HAS_P) e += ln_pc(KD(-48.76), KD(0.5304), -0.0, KD(-0.01176), KD(0.0003692), T - KD(273.15), P, iT * KD(1.0 / 83.14472));
+    if (HAS_P && lvl != nullptr) {
+        const double Tc = T - KD(273.15);
+        e += ln_pc_level(lvl, LVL_KSP, Tc, Tc * Tc, iT);
+    } else if (HAS_P)
+        e += ln_pc(KD(-48.76), KD(0.5304), -0.0, KD(-0.01176), KD(0.0003692), T - KD(273.15), P, iT * KD(1.0 / 83.14472));
     return cexp(e);
 }
 
@@ -340,14 +437,16 @@ __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, do
 template <bool HAS_P>
 __device__ __forceinline__ double solve(int output_kind, double T, double S, double DIC, double Alk, double P,
                                         bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
-                                        double pH, double H_init, int iterations, double* H_io = nullptr) {
+                                        double pH, double H_init, int iterations, double* H_io = nullptr,
+                                        const LevelTables* lvl = nullptr) {
     constexpr double LN10 = 2.302585092994045684;
     const bool calcite_path = (output_kind == OBM_CC_CO3 || output_kind == OBM_CC_OMEGA_CALCITE);
     // density: P|1 for the main call (carbon_chemistry.jl:123), P|0 for carbonate_concentration
     // (calcite_concentration.jl:13) — reproduced as found (SURVEY App. A bug 4)
-    const double rho = teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
+    const double rho = (HAS_P && lvl != nullptr) ? teos10_rho_level(T, S, lvl->rho)
+                                                 : teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
     Constants c;
-    constants<HAS_P>(T, S, P, has_phos, has_sil, c);
+    constants<HAS_P>(T, S, P, has_phos, has_sil, c, lvl);
     const double scale = KD(1e-3) * rcp_fast(rho);
     Totals t;
     t.DIC = DIC * scale;
@@ -388,7 +487,7 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
             const double CO3 = t.DIC * c.K1 * c.K2 * rcp_fast(denom1 * denom2);
             if (output_kind == OBM_CC_CO3) return CO3;
             const double calcium = KD(0.0103) * S * KD(1.0 / 35);
-            return calcium * CO3 * rcp_fast(KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P));
+            return calcium * CO3 * rcp_fast(KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P, lvl));
         }
         default: break;
     }

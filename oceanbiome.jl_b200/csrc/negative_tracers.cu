@@ -103,6 +103,15 @@ struct ScaleOmegaArgs {
 #endif
 __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
+#if OBM_CC_LEVEL
+    // the block's z-level (blockIdx.z) fixes the pressure: its TEOS-10 and pressure-correction tables, built once
+    __shared__ cc::LevelTables level;
+    cc::fill_level_entry(level, fabs(a.s.d.zc[blockIdx.z]) * 9.80665 * 1026.0 / 100000.0, threadIdx.x);
+    __syncthreads();
+    const cc::LevelTables* lvl = &level;
+#else
+    const cc::LevelTables* lvl = nullptr;
+#endif
     int i, j, k;
     if (!thread_cell(a.s.d, i, j, k)) return;
     const long long idx = cell_index(a.s.d, i, j, k);
@@ -117,7 +126,7 @@ __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_ca
     const double Si = (a.iSi >= 0 && !dry) ? mine[a.iSi * SN_BLOCK] : a.Si[idx];
     const double P = fabs(a.s.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;  // compute_calcite_saturation.jl:27
     a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, T, S, DIC, Alk, P, true, Si, false, 0.0, false, 0.0, a.H_init,
-                                   a.iterations, a.Hst ? a.Hst + idx : nullptr);
+                                   a.iterations, a.Hst ? a.Hst + idx : nullptr, lvl);
 }
 
 struct ZeroArgs {

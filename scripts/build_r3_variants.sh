@@ -16,13 +16,7 @@ v p5_nobatch_newton_b8 negative_tracers $NEWTON -DOBM_CC_BATCH=0 -DOBM_SN_MIN_BL
 v p6_batch_newton_b7 negative_tracers $NEWTON -DOBM_SN_MIN_BLOCKS=7 &
 v p7_liblog_batchexp_b8 negative_tracers $NEWTON -DOBM_CC_LOG=0 -DOBM_SN_MIN_BLOCKS=8 &
 wait
-v t1_exp2 pisces_tendencies -DOBM_PISCES_EXP=2 &
-v t2_b4 pisces_tendencies -DOBM_PISCES_MIN_BLOCKS=4 &
-v t3_exp2_b4 pisces_tendencies -DOBM_PISCES_EXP=2 -DOBM_PISCES_MIN_BLOCKS=4 &
-v t4_roll pisces_tendencies -DOBM_PISCES_ROLL=1 &
-wait
-v t5_roll_b4 pisces_tendencies -DOBM_PISCES_ROLL=1 -DOBM_PISCES_MIN_BLOCKS=4 &
-v t6_b2 pisces_tendencies -DOBM_PISCES_MIN_BLOCKS=2 &
-v t7_roll_exp2 pisces_tendencies -DOBM_PISCES_ROLL=1 -DOBM_PISCES_EXP=2 &
+v p8_batch_newton_b8_nolevel negative_tracers $NEWTON -DOBM_SN_MIN_BLOCKS=8 -DOBM_CC_LEVEL=0 &   # without the per-level tables
+v p9_lib_newton_b8_nolevel negative_tracers -DOBM_CC_EXP=0 -DOBM_CC_LOG=0 $NEWTON -DOBM_SN_MIN_BLOCKS=8 -DOBM_CC_LEVEL=0 &
 wait
 ls build/variants

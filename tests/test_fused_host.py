@@ -77,6 +77,13 @@ def test_fused_prologue_and_light_match_oracle_on_the_host(oracle, fused):
     cg = oracle.make_groups(snames, groups)
     mine = {n: host[n].copy() for n in host}
     Om = fused.scale_negative_tracers_calcite_saturation(og, [mine[n] for n in snames], cg, mine["T"], mine["S"], mine["DIC"], mine["Alk"], mine["Si"])
+    # the per-level tables (TEOS-10 collapsed in ζ, pressure corrections as quadratics in T_c) against the direct form
+    direct = {n: host[n].copy() for n in host}
+    Om_direct = fused.scale_negative_tracers_calcite_saturation(og, [direct[n] for n in snames], cg, direct["T"], direct["S"],
+                                                                direct["DIC"], direct["Alk"], direct["Si"], level_tables=False)
+    a, b = og.interior(Om), og.interior(Om_direct)
+    both = np.isfinite(a) & np.isfinite(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and float(np.max(np.abs(a[both] - b[both]) / np.abs(b[both]))) <= 1e-13
     oracle.scale_negative_tracers(og, [host[n] for n in snames], cg)
     for n in snames:
         a, b = og.interior(mine[n]), og.interior(host[n])
