@@ -341,13 +341,14 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 // solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]: Newton on x = ln[H⁺] carried multiplicatively (H ← H·e^(−Δx)),
 // step clamped to one pH unit, at most `iterations` steps from H0.
 // OBM_CC_TOL: the warp-uniform exit threshold on |Δx|.  Newton converges quadratically here with a measured constant
-// |e₊| ≈ 0.30·Δx² in ln H (sea-water states; ≤ 1 over the robust box), so leaving after a step below 2·10⁻⁶ puts the
-// root within ≈ 10⁻¹² in ln H, 5·10⁻¹³ in pH — two orders inside the stated 10⁻¹⁰.
+// |e₊| ≈ 0.30·Δx² in ln H (sea-water states; ≤ 1 over the robust box), so leaving after a step below 10⁻⁵ puts the
+// root within ≈ 3·10⁻¹¹ in ln H, 1.3·10⁻¹¹ in pH (robust box: ≤ 4.3·10⁻¹¹) — inside the stated 10⁻¹⁰; the exit is
+// warp-uniform, so all but the slowest lane of a warp end far below that (measured on the GPU: ≤ 2·10⁻¹³).
 // OBM_CC_POLYEXP: once every lane's step is below 1/8 the factor e^(−Δx) is its degree-5 Taylor polynomial (5 FMAs
 // instead of an exp); the polynomial's own error, Δx⁶/720, is part of the NEXT iterate's error like the Newton remainder
 // and vanishes with it — the root is unchanged.
 #ifndef OBM_CC_TOL
-#define OBM_CC_TOL 2e-6
+#define OBM_CC_TOL 1e-5
 #endif
 #ifndef OBM_CC_POLYEXP
 #define OBM_CC_POLYEXP 1
@@ -386,10 +387,11 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
 // first with borate alone at the reference's initial guess H_init = 10⁻⁸ (carbon_chemistry.jl:121), then OBM_CC_INIT
 // more times with borate, silicate, OH⁻ and free H⁺ evaluated at the estimate just obtained.  The plain quadratic is
 // 0.07 pH units off on average for sea water (0.14 at worst: borate alkalinity moves with pH) and Newton then needs four
-// steps; two refinements (≈ 55 instructions each, a third of a Newton step with its derivative and exponential) leave
-// ≤ 0.02 pH units and three steps reach 10⁻¹⁴.  Only the starting point differs from the reference, not the root.
+// steps; each refinement (≈ 55 instructions, a third of a Newton step with its derivative and exponential) halves the
+// distance or better.  Timed on the B200 (profiles/r03_kernel_variants.txt): one refinement + exit at 10⁻⁵ is the
+// fastest combination (two refinements + 2·10⁻⁶: +4 %).  Only the starting point differs from the reference, not the root.
 #ifndef OBM_CC_INIT
-#define OBM_CC_INIT 2
+#define OBM_CC_INIT 1
 #endif
 __device__ __forceinline__ double quadratic_H(const Constants& c, const Totals& t, double AC) {
     const double b = c.K1 * (AC - t.DIC);
@@ -433,35 +435,47 @@ __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, do
     return cexp(e);
 }
 
-// The whole `(p::CarbonChemistry)(; DIC, T, S, Alk, pH, P, output, silicate, phosphate)` call.
+// Everything of the call that depends on (T, S, P) only: density, the equilibrium constants, the S-proportional totals —
+// about half of the work of an Ω solve, and none of it needs DIC, Alk or Si.  The fused scaling + Ω kernel evaluates it
+// while the cell's tracers are still on their way from HBM (cp.async), then calls `finish`.
+struct Prepared {
+    Constants c;
+    Totals t;       // boron, sulfate, fluoride filled; DIC, Alk, silicate, phosphate by `finish`
+    double scale;   // 1e-3 / ρ: mmol m⁻³ → mol kg⁻¹
+    double KSP;     // calcite solubility product (calcite path with `with_KSP` only)
+};
 template <bool HAS_P>
-__device__ __forceinline__ double solve(int output_kind, double T, double S, double DIC, double Alk, double P,
-                                        bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
-                                        double pH, double H_init, int iterations, double* H_io = nullptr,
-                                        const LevelTables* lvl = nullptr) {
-    constexpr double LN10 = 2.302585092994045684;
-    const bool calcite_path = (output_kind == OBM_CC_CO3 || output_kind == OBM_CC_OMEGA_CALCITE);
+__device__ __forceinline__ void prepare(Prepared& q, bool calcite_path, double T, double S, double P, bool has_sil, bool has_phos,
+                                        const LevelTables* lvl, bool with_KSP) {
     // density: P|1 for the main call (carbon_chemistry.jl:123), P|0 for carbonate_concentration
     // (calcite_concentration.jl:13) — reproduced as found (SURVEY App. A bug 4)
     const double rho = (HAS_P && lvl != nullptr) ? teos10_rho_level(T, S, lvl->rho)
                                                  : teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
-    Constants c;
-    constants<HAS_P>(T, S, P, has_phos, has_sil, c, lvl);
-    const double scale = KD(1e-3) * rcp_fast(rho);
-    Totals t;
+    constants<HAS_P>(T, S, P, has_phos, has_sil, q.c, lvl);
+    q.scale = KD(1e-3) * rcp_fast(rho);
+    q.t.boron = KD(0.000232 / 10.811) * S * KD(1.0 / 1.80655);
+    q.t.sulfate = KD(0.14 / 96.06) * S * KD(1.0 / 1.80655);
+    q.t.fluoride = KD(0.000067 / 18.9984) * S * KD(1.0 / 1.80655);
+    const double sd = 1 + q.t.sulfate * rcp_fast(q.c.KS);
+    q.c.isd = rcp_fast(sd);
+    q.c.KSsd = q.c.KS * sd;
+    q.KSP = with_KSP ? KSP_calcite<HAS_P>(q.c.Tk, S, q.c.sqrtS, q.c.logT, P, lvl) : 0.0;
+}
+
+// The whole `(p::CarbonChemistry)(; DIC, T, S, Alk, pH, P, output, silicate, phosphate)` call, second half.
+template <bool HAS_P>
+__device__ __forceinline__ double finish(Prepared& q, bool with_KSP, int output_kind, double S, double DIC, double Alk, double P,
+                                         bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
+                                         double pH, double H_init, int iterations, double* H_io, const LevelTables* lvl) {
+    constexpr double LN10 = 2.302585092994045684;
+    Constants& c = q.c;
+    Totals& t = q.t;
+    const double scale = q.scale;
     t.DIC = DIC * scale;
     t.Alk = Alk * scale;
     t.phosphate = phosphate * scale;
     t.silicate = silicate * scale;
-    t.boron = KD(0.000232 / 10.811) * S * KD(1.0 / 1.80655);
-    t.sulfate = KD(0.14 / 96.06) * S * KD(1.0 / 1.80655);
-    t.fluoride = KD(0.000067 / 18.9984) * S * KD(1.0 / 1.80655);
 
-    {
-        const double sd = 1 + t.sulfate * rcp_fast(c.KS);
-        c.isd = rcp_fast(sd);
-        c.KSsd = c.KS * sd;
-    }
     double H;
     if (has_pH) {
         H = cexp(-pH * KD(LN10));
@@ -487,7 +501,7 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
             const double CO3 = t.DIC * c.K1 * c.K2 * rcp_fast(denom1 * denom2);
             if (output_kind == OBM_CC_CO3) return CO3;
             const double calcium = KD(0.0103) * S * KD(1.0 / 35);
-            return calcium * CO3 * rcp_fast(KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P, lvl));
+            return calcium * CO3 * rcp_fast(with_KSP ? q.KSP : KSP_calcite<HAS_P>(c.Tk, S, c.sqrtS, c.logT, P, lvl));
         }
         default: break;
     }
@@ -511,6 +525,18 @@ __device__ __forceinline__ double solve(int output_kind, double T, double S, dou
         x = fCO2 * rcp_fast(phi) * iPp;
     }
     return fCO2 * rcp_fast(phi) * KD(1.0 / 0.09807);
+}
+
+template <bool HAS_P>
+__device__ __forceinline__ double solve(int output_kind, double T, double S, double DIC, double Alk, double P,
+                                        bool has_sil, double silicate, bool has_phos, double phosphate, bool has_pH,
+                                        double pH, double H_init, int iterations, double* H_io = nullptr,
+                                        const LevelTables* lvl = nullptr) {
+    const bool calcite_path = (output_kind == OBM_CC_CO3 || output_kind == OBM_CC_OMEGA_CALCITE);
+    Prepared q;
+    prepare<HAS_P>(q, calcite_path, T, S, P, has_sil, has_phos, lvl, false);
+    return finish<HAS_P>(q, false, output_kind, S, DIC, Alk, P, has_sil, silicate, has_phos, phosphate, has_pH, pH, H_init,
+                         iterations, H_io, lvl);
 }
 
 }  // namespace cc

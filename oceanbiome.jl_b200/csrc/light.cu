@@ -22,15 +22,21 @@ namespace obm {
 
 // exp of the scans: the lean exp of obm_common.cuh (≈ 26 instructions, ≤ 2 ulp, library call for |x| ≥ 700 / NaN) —
 // these kernels are issue-bound on their 4 (two-band) / 2·bands (N-band) exps per cell: 3-band PAR 3.2 → 2.65 ms.
-// -DOBM_LIGHT_EXP=0 restores the library exp.
+// -DOBM_LIGHT_EXP=0 restores the library exp; 2 / 3: see lexp.
 #ifndef OBM_LIGHT_EXP
-#define OBM_LIGHT_EXP 1
+#define OBM_LIGHT_EXP 3
 #endif
 __device__ __forceinline__ double lexp(double x) {
 #if OBM_LIGHT_EXP == 0
     return exp(x);
-#else
+#elif OBM_LIGHT_EXP == 1
     return exp_lean(x);
+#elif OBM_LIGHT_EXP == 2
+    return exp_horner(x);   // plain Horner, integer range test, library exp inline in the cold branch (no call)
+#else
+    // branch-free: the argument is clamped to where the polynomial form is valid.  −745 → 5e-324 instead of the exact 0
+    // of exp(−Inf) (Chl = 0: χ·5e-324 vanishes in kʷ + χ Chl^e), 709 → 8e307 instead of +Inf (Chl ≳ 1e300); NaN stays NaN.
+    return exp_unguarded(x < -745.0 ? -745.0 : (x > 709.0 ? 709.0 : x));
 #endif
 }
 

@@ -31,15 +31,21 @@ struct ScaleArgs {
 
 // One cell: stage its distinct tracers in `mine` (stride SN_BLOCK), apply the groups in order, write back what changed.
 // On return `mine` holds the cell's tracers as the rest of the stage will see them.
+// STAGED: the values are already in `mine` (the caller's cp.async copies have landed).
+template <bool STAGED = false>
 __device__ __forceinline__ void scale_cell(const ScaleArgs& a, double* mine, long long idx) {
     bool touched = false;  // some value is negative or non-finite: only then can any group have p ≠ t
     for (int t = 0; t < a.ntracers; t++) {
-        const double v = a.tracers[t][idx];
-        mine[t * SN_BLOCK] = v;
         // negative, −0.0, ±Inf or NaN ⇔ sign bit set or exponent all ones ⇔ high word ≥ 0x7ff00000 as unsigned: one
         // integer compare (the FP64 form `!(v >= 0 && v < Inf)` compiled to ≈ 14 integer instructions per value).
         // −0.0 is flagged too; its group then runs with t / p = 1 and writes +0.0, as the reference's `ifelse(…, 0)` does.
-        touched |= (unsigned)__double2hiint(v) >= 0x7ff00000u;
+        if (STAGED) {
+            touched |= reinterpret_cast<const unsigned*>(mine + t * SN_BLOCK)[1] >= 0x7ff00000u;  // the high word alone
+        } else {
+            const double v = a.tracers[t][idx];
+            mine[t * SN_BLOCK] = v;
+            touched |= (unsigned)__double2hiint(v) >= 0x7ff00000u;
+        }
     }
     if (!__any_sync(__activemask(), touched)) return;  // warp-uniform: the common case reads its cells and leaves
     unsigned dirty = 0;  // bit t ⇔ tracer t was rescaled and must be written back
@@ -98,12 +104,41 @@ struct ScaleOmegaArgs {
     double H_init;
 };
 
+#ifndef OBM_SN_ASYNC
+#define OBM_SN_ASYNC 1
+#endif
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 #ifndef OBM_SN_MIN_BLOCKS
-#define OBM_SN_MIN_BLOCKS 6  // 80 registers, no spill (7: 72 registers + 32 B, 8: 64 + 48 B of spill — timed in profiles/r03_kernel_variants.txt)
+#define OBM_SN_MIN_BLOCKS 8  // 64 registers + 96 B of spill; 7: 72, none; 6: 80, none — timed in profiles/r03_kernel_variants.txt (8 blocks: −9 %)
+#endif
+// OBM_SN_LEVEL: the per-level TEOS-10 / pressure-correction tables of carbon_chemistry.cuh in this kernel.  Timed on the
+// B200 (profiles/r03_kernel_variants.txt): with 8 resident blocks the tables' block barrier costs more than the ≈ 60 FP64
+// instructions per cell they save (1.026 ms with, 0.976 ms without, per 16.8 M cells), so they are off here; the
+// stand-alone Ω kernel keeps them (OBM_CC_LEVEL).
+#ifndef OBM_SN_LEVEL
+#define OBM_SN_LEVEL 0
 #endif
 __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
-#if OBM_CC_LEVEL
+    int i = 0, j = 0, k = 0;
+    const bool inside = thread_cell(a.s.d, i, j, k);
+    const long long idx = cell_index(a.s.d, i, j, k);
+    double* mine = sm + threadIdx.x;
+    // an immersed cell is not rescaled (negative_tracers.jl:194,253); Ω is still computed there, from the values as they
+    // are — compute_calcite_saturation! has no such guard (PISCES/compute_calcite_saturation.jl:9-37)
+    const bool dry = inside && immersed_cell(a.s.d, i, j, k);
+#if OBM_SN_ASYNC
+    // The cell's tracers travel HBM → shared memory by cp.async (no registers, nothing waits on them) while the thread
+    // evaluates everything of the Ω solve that needs T, S and the pressure only — density, seven equilibrium constants,
+    // the solubility product: half of the kernel's arithmetic.  ncu (r3b) had 19 % of this kernel's stall samples on the
+    // first use of the tracer loads, which used to come first.  A thread reads back only what it copied itself: no barrier.
+    if (inside && !dry)
+        for (int t = 0; t < a.s.ntracers; t++) cp_async8(mine + t * SN_BLOCK, a.s.tracers[t] + idx);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+#if OBM_SN_LEVEL
     // the block's z-level (blockIdx.z) fixes the pressure: its TEOS-10 and pressure-correction tables, built once
     __shared__ cc::LevelTables level;
     cc::fill_level_entry(level, fabs(a.s.d.zc[blockIdx.z]) * 9.80665 * 1026.0 / 100000.0, threadIdx.x);
@@ -112,21 +147,27 @@ __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_ca
 #else
     const cc::LevelTables* lvl = nullptr;
 #endif
-    int i, j, k;
-    if (!thread_cell(a.s.d, i, j, k)) return;
-    const long long idx = cell_index(a.s.d, i, j, k);
-    double* mine = sm + threadIdx.x;
+    if (!inside) return;
+    const double P = fabs(a.s.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;  // compute_calcite_saturation.jl:27
     const double T = a.T[idx], S = a.S[idx];  // never rescaled (not members of any conserved group)
-    // an immersed cell is not rescaled (negative_tracers.jl:194,253); Ω is still computed there, from the values as they
-    // are — compute_calcite_saturation! has no such guard (PISCES/compute_calcite_saturation.jl:9-37)
-    const bool dry = immersed_cell(a.s.d, i, j, k);
+#if OBM_SN_ASYNC
+    cc::Prepared q;
+    cc::prepare<true>(q, true, T, S, P, true, false, lvl, true);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (!dry) scale_cell<true>(a.s, mine, idx);
+#else
     if (!dry) scale_cell(a.s, mine, idx);
+#endif
     const double DIC = (a.iDIC >= 0 && !dry) ? mine[a.iDIC * SN_BLOCK] : a.DIC[idx];
     const double Alk = (a.iAlk >= 0 && !dry) ? mine[a.iAlk * SN_BLOCK] : a.Alk[idx];
     const double Si = (a.iSi >= 0 && !dry) ? mine[a.iSi * SN_BLOCK] : a.Si[idx];
-    const double P = fabs(a.s.d.zc[k]) * 9.80665 * 1026.0 / 100000.0;  // compute_calcite_saturation.jl:27
+#if OBM_SN_ASYNC
+    a.Omega[idx] = cc::finish<true>(q, true, OBM_CC_OMEGA_CALCITE, S, DIC, Alk, P, true, Si, false, 0.0, false, 0.0, a.H_init,
+                                    a.iterations, a.Hst ? a.Hst + idx : nullptr, lvl);
+#else
     a.Omega[idx] = cc::solve<true>(OBM_CC_OMEGA_CALCITE, T, S, DIC, Alk, P, true, Si, false, 0.0, false, 0.0, a.H_init,
                                    a.iterations, a.Hst ? a.Hst + idx : nullptr, lvl);
+#endif
 }
 
 struct ZeroArgs {

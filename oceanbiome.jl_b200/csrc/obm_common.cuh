@@ -67,6 +67,38 @@ __device__ __forceinline__ double rcp_fast(double b) {
 #endif
 }
 
+// Division for the few quotients that feed a cancellation (PISCES free iron: Fe − Fe′ with Fe′ → Fe): the lean reciprocal
+// plus one Markstein correction — q = a·r, q′ = q + (a − q·b)·r — which lands on the correctly rounded quotient (the
+// residual a − q·b is exact in an FMA), where a·r alone can be 1 ulp off and the subtraction would turn that ulp into
+// the whole result.  3 more FP64 instructions than `a * rcp_fast(b)`, still branch-free.
+__device__ __forceinline__ double div_cr(double a, double b) {
+#ifdef __CUDACC__
+    const double r = rcp_fast(b);
+    const double q = a * r;
+    return fma(fma(-q, b, a), r, q);
+#else
+    return a / b;
+#endif
+}
+// a·b and a + b rounded separately (never contracted into an FMA): for expressions whose result is a difference of nearly
+// equal numbers, where the reference's (Julia: no contraction) rounding sequence decides which noise comes out.
+__device__ __forceinline__ double mul_rn(double a, double b) {
+#ifdef __CUDACC__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b;
+    return r;
+#endif
+}
+__device__ __forceinline__ double add_rn(double a, double b) {
+#ifdef __CUDACC__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b;
+    return r;
+#endif
+}
+
 // KD(x): the double literal x as a constant-bank operand.  ptxas materialises a 64-bit FP immediate with TWO moves
 // (UMOV lo / UMOV hi) in front of every use — in the carbonate solve (≈ 150 literals: TEOS-10, the equilibrium
 // constants, their pressure corrections) that was more issue slots than the arithmetic itself (805 moves vs 693 FP64

@@ -465,10 +465,15 @@ __device__ __forceinline__ void cell_tendencies(const PiscesArgs& a, const Input
     // ---- iron chemistry: iron/iron.jl:25-37, particulate_organic_matter/iron.jl:97-126 ------------------------
     double Fep;
     {
-        const double ligands = A::mx(0.6, 0.09 * (DOC + 40) - 3);
-        const double K = A::ex(16.27 - A::div(1565.7, A::mx(c.T + 273.15, 5.0)));
-        const double Dl = 1 + K * ligands - K * c.Fe;
-        Fep = A::div(-Dl + sqrt(Dl * Dl + 4 * K * c.Fe), 2 * K);
+        const double ligands = A::mx(0.6, add_rn(mul_rn(0.09, DOC + 40), -3.0));
+        const double Tk = A::mx(c.T + 273.15, 5.0);
+        const double K = A::ex(add_rn(16.27, -(A::EX ? 1565.7 / Tk : div_cr(1565.7, Tk))));
+        // Fe′ → Fe when ligands ≪ Fe and Fe′ → 0 when ligands ≫ Fe: either way a difference of nearly equal numbers follows
+        // (here or in `colloidal` below), so the reference's rounding sequence is kept — products and sums rounded one by
+        // one, a correctly rounded quotient — in the fast pass too (7 instructions more than the contracted form).
+        const double Dl = add_rn(add_rn(1.0, mul_rn(K, ligands)), -mul_rn(K, c.Fe));
+        const double root = sqrt(add_rn(mul_rn(Dl, Dl), mul_rn(4 * K, c.Fe)));
+        Fep = A::EX ? (-Dl + root) / (2 * K) : div_cr(-Dl + root, 2 * K);
     }
     const double lFe = p.minimum_iron_scavenging_rate + p.load_specific_iron_scavenging_rate * (POC + GOC + CaCO3 + PSi);
     const double BactFe = A::div(p.maximum_bacterial_growth_rate * fT[5] * LBact * p.maximum_iron_ratio_in_bacteria * c.Fe,

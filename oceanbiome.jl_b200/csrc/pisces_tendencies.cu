@@ -140,113 +140,86 @@ __global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__
     if (sink.pending) cell_exact(a, idx, pl, k, sink.pending);  // rare: non-finite results, NaN inputs
 }
 
-// ---- the same cell arithmetic behind a TMA-staged, persistent launch ------------------------------------------------------------
-// ncu (r3a, source page): 15 % of all warp-state samples of the kernel above sit on ONE instruction — the first use of a
-// loaded input — because a thread's 38 loads go out together and, with 12 warps per SM, nothing else is ready while they
-// are in flight.  Here a block owns a sequence of tiles (128 cells of one x-row) and the inputs of tile n + 1 travel while
-// tile n is computed: one elected thread issues 36 `cp.async.bulk` row copies (TMA, global → shared, no registers, no
-// L1) that complete on an mbarrier; every thread then takes its 38 values from shared memory.  One __syncthreads per tile
-// (≈ 2 500 instructions) frees the single buffer for the next copy: 36 × 1 040 B = 37 KB per block, three blocks per SM.
-// Rows start 24 B off a 16-byte boundary when Hx is odd, so a row copy starts one element early (ROW = 130 doubles) and
-// thread t reads slot t + shift.  Launched only when the geometry allows it (whole 128-cell chunks, 16-byte aligned
-// bases); anything else takes the kernel above — same arithmetic, same results bit for bit.
-#ifndef OBM_PISCES_TMA
-#define OBM_PISCES_TMA 1
+// ---- the same cell arithmetic, software-pipelined over a persistent launch (build option OBM_PISCES_PIPE) -------------------------
+// ncu (r3a, source page): ≈ 15 % of the warp-state samples of the kernel above sit on the first use of a loaded input — a
+// thread's 38 loads go out together and, at 12 warps per SM, little else is ready while they are in flight.  Here a block
+// walks a sequence of 128-cell row chunks and every thread copies the inputs of ITS cell of the next chunk into ITS
+// shared-memory column (cp.async, 8 bytes each: no registers, no barrier — a thread only reads back what it copied
+// itself) while it computes the current one.
+#ifndef OBM_PISCES_PIPE
+#define OBM_PISCES_PIPE 0
 #endif
-constexpr int TMA_ROWS = 36;         // 23 tracers + PAR₁₂₃ + PAR + Ω + 2 × 2 faces of w + 4 column fields
-constexpr int TMA_ROW = PB + 2;      // doubles per staged row: 16-byte multiple, one element of slack on either side
-static_assert((TMA_ROW * 8) % 16 == 0, "row copies are multiples of 16 bytes");
-
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+constexpr int PIPE_ROWS = 36;  // 23 tracers + PAR₁₂₃ + PAR + Ω + 2 × 2 faces of w + 4 column fields
+__device__ __forceinline__ void cp_async8(double* dst, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_row(double* dst, const double* src, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"((unsigned)(TMA_ROW * 8)), "r"(smem_u32(bar)) : "memory");
-}
-
-struct Tile { int i0, j, k; };
-__device__ __forceinline__ Tile tile_of(const GridDims& d, long long t) {
-    const int chunks = (d.i1 - d.i0) / PB, ny = d.j1 - d.j0;
-    const long long row = t / chunks;
-    Tile r;
-    r.i0 = d.i0 + (int)(t - row * chunks) * PB;
+struct Chunk { int i, j, k; };
+__device__ __forceinline__ Chunk chunk_of(const GridDims& d, unsigned t, unsigned chunks, unsigned ny) {
+    const unsigned row = t / chunks;
+    Chunk r;
+    r.i = d.i0 + (int)(t - row * chunks) * PB + (int)threadIdx.x;
     r.k = (int)(row / ny);
-    r.j = d.j0 + (int)(row - (long long)r.k * ny);
+    r.j = d.j0 + (int)(row - (unsigned)r.k * ny);
     return r;
 }
-
-// the 36 row sources of a tile, in the order the threads read them back (kept in step with staged_inputs below)
-__device__ __forceinline__ void issue_tile(const PiscesArgs& a, const Tile t, int shift, double (*buf)[TMA_ROW], unsigned long long* bar) {
-    const long long idx = cell_index(a.d, t.i0, t.j, t.k) - shift;
-    const long long pl = plane_index(a.d, t.i0, t.j) - shift;
-    mbar_expect_tx(bar, TMA_ROWS * TMA_ROW * 8);
+__device__ __forceinline__ void pipe_issue(const PiscesArgs& a, double* mine, long long idx, long long pl) {
     int r = 0;
 #pragma unroll
     for (int n = 0; n < OBM_PISCES_NTRACERS; n++)
-        if (!(n == T_DIC || n == T_Alk || n == T_S)) bulk_row(buf[r++], a.c[n] + idx, bar);
-    bulk_row(buf[r++], a.f.PAR1 + idx, bar); bulk_row(buf[r++], a.f.PAR2 + idx, bar); bulk_row(buf[r++], a.f.PAR3 + idx, bar);
-    bulk_row(buf[r++], a.f.PAR + idx, bar); bulk_row(buf[r++], a.f.Omega + idx, bar);
-    bulk_row(buf[r++], a.f.wPOC + idx, bar); bulk_row(buf[r++], a.f.wPOC + idx + a.d.sz, bar);
-    bulk_row(buf[r++], a.f.wGOC + idx, bar); bulk_row(buf[r++], a.f.wGOC + idx + a.d.sz, bar);
-    bulk_row(buf[r++], a.f.mixed_layer_depth_xy + pl, bar); bulk_row(buf[r++], a.f.euphotic_depth_xy + pl, bar);
-    bulk_row(buf[r++], a.f.mean_mixed_layer_vertical_diffusivity_xy + pl, bar); bulk_row(buf[r++], a.f.mean_mixed_layer_light_xy + pl, bar);
+        if (!(n == T_DIC || n == T_Alk || n == T_S)) cp_async8(mine + PB * (r++), a.c[n] + idx);
+    cp_async8(mine + PB * (r++), a.f.PAR1 + idx); cp_async8(mine + PB * (r++), a.f.PAR2 + idx); cp_async8(mine + PB * (r++), a.f.PAR3 + idx);
+    cp_async8(mine + PB * (r++), a.f.PAR + idx); cp_async8(mine + PB * (r++), a.f.Omega + idx);
+    cp_async8(mine + PB * (r++), a.f.wPOC + idx); cp_async8(mine + PB * (r++), a.f.wPOC + idx + a.d.sz);
+    cp_async8(mine + PB * (r++), a.f.wGOC + idx); cp_async8(mine + PB * (r++), a.f.wGOC + idx + a.d.sz);
+    cp_async8(mine + PB * (r++), a.f.mixed_layer_depth_xy + pl); cp_async8(mine + PB * (r++), a.f.euphotic_depth_xy + pl);
+    cp_async8(mine + PB * (r++), a.f.mean_mixed_layer_vertical_diffusivity_xy + pl); cp_async8(mine + PB * (r++), a.f.mean_mixed_layer_light_xy + pl);
 }
-
-__device__ __forceinline__ Inputs staged_inputs(const PiscesArgs& a, const double (*buf)[TMA_ROW], int s, int k) {
+__device__ __forceinline__ Inputs pipe_read(const PiscesArgs& a, const double* mine, int k) {
     Inputs in;
     int r = 0;
-    in.P = buf[r++][s]; in.PChl = buf[r++][s]; in.PFe = buf[r++][s]; in.D = buf[r++][s]; in.DChl = buf[r++][s];
-    in.DFe = buf[r++][s]; in.DSi = buf[r++][s]; in.Z = buf[r++][s]; in.M = buf[r++][s]; in.DOC = buf[r++][s];
-    in.POC = buf[r++][s]; in.GOC = buf[r++][s]; in.SFe = buf[r++][s]; in.BFe = buf[r++][s]; in.PSi = buf[r++][s];
-    in.CaCO3 = buf[r++][s]; in.c.NO3 = buf[r++][s]; in.c.NH4 = buf[r++][s]; in.c.PO4 = buf[r++][s]; in.c.Fe = buf[r++][s];
-    in.c.Si = buf[r++][s]; in.c.O2 = buf[r++][s]; in.c.T = buf[r++][s];              // tracer order minus DIC, Alk, S
-    in.c.PAR1 = buf[r++][s]; in.c.PAR2 = buf[r++][s]; in.c.PAR3 = buf[r++][s]; in.PARt = buf[r++][s]; in.Omega = buf[r++][s];
-    const double wP0 = buf[r++][s], wP1 = buf[r++][s], wG0 = buf[r++][s], wG1 = buf[r++][s];
+    auto ld = [&](int row) { return mine[PB * row]; };
+    in.P = ld(r++); in.PChl = ld(r++); in.PFe = ld(r++); in.D = ld(r++); in.DChl = ld(r++);
+    in.DFe = ld(r++); in.DSi = ld(r++); in.Z = ld(r++); in.M = ld(r++); in.DOC = ld(r++);
+    in.POC = ld(r++); in.GOC = ld(r++); in.SFe = ld(r++); in.BFe = ld(r++); in.PSi = ld(r++);
+    in.CaCO3 = ld(r++); in.c.NO3 = ld(r++); in.c.NH4 = ld(r++); in.c.PO4 = ld(r++); in.c.Fe = ld(r++);
+    in.c.Si = ld(r++); in.c.O2 = ld(r++); in.c.T = ld(r++);              // tracer order minus DIC, Alk, S
+    in.c.PAR1 = ld(r++); in.c.PAR2 = ld(r++); in.c.PAR3 = ld(r++); in.PARt = ld(r++); in.Omega = ld(r++);
+    const double wP0 = ld(r++), wP1 = ld(r++), wG0 = ld(r++), wG1 = ld(r++);
     in.wPOC = (wP0 + wP1) / 2;  // ℑzᵃᵃᶜ(i, j, k, grid, w) — two_size_class.jl:95-98
     in.wGOC = (wG0 + wG1) / 2;
-    in.c.zmxl = buf[r++][s]; in.c.zeu = buf[r++][s]; in.c.kappa = buf[r++][s]; in.mlPAR = buf[r++][s];
+    in.c.zmxl = ld(r++); in.c.zeu = ld(r++); in.c.kappa = ld(r++); in.mlPAR = ld(r++);
     in.c.z = a.d.zc[k];
     return in;
 }
 
 template <bool ACC, bool FULL>
-__global__ void OBM_PISCES_BOUNDS pisces_tendency_tma_kernel(const __grid_constant__ PiscesArgs a, long long ntiles, int shift) {
-    __shared__ alignas(128) double buf[TMA_ROWS][TMA_ROW];
-    __shared__ alignas(8) unsigned long long bar;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    long long t = blockIdx.x;
-    if (threadIdx.x == 0 && t < ntiles) issue_tile(a, tile_of(a.d, t), shift, buf, &bar);
-    unsigned parity = 0;
-    for (; t < ntiles; t += gridDim.x) {
-        const Tile tl = tile_of(a.d, t);
-        mbar_wait(&bar, parity);
-        parity ^= 1u;
-        const Inputs in = staged_inputs(a, buf, (int)threadIdx.x + shift, tl.k);
-        __syncthreads();  // every thread holds its cell: the buffer is free for the next tile's rows
-        if (threadIdx.x == 0 && t + gridDim.x < ntiles) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy reads before async-proxy writes
-            issue_tile(a, tile_of(a.d, t + gridDim.x), shift, buf, &bar);
-        }
-        const int i = tl.i0 + (int)threadIdx.x;
-        const long long idx = cell_index(a.d, i, tl.j, tl.k);
-        FastSink<ACC, FULL> sink{a, idx, 0u, needs_exact(in) ? 1u : 0u};
-        cell_tendencies<false>(a, in, sink);
-        if (sink.pending) cell_exact(a, idx, plane_index(a.d, i, tl.j), tl.k, sink.pending);
+__global__ void OBM_PISCES_BOUNDS pisces_tendency_pipe_kernel(const __grid_constant__ PiscesArgs a, unsigned ntiles, unsigned chunks) {
+    __shared__ double buf[PIPE_ROWS][PB];
+    const unsigned ny = (unsigned)(a.d.j1 - a.d.j0);
+    unsigned t = blockIdx.x;  // the only loop state that lives across a cell's arithmetic: everything else is recomputed
+    {
+        const Chunk c = chunk_of(a.d, t, chunks, ny);
+        if (c.i < a.d.i1) pipe_issue(a, &buf[0][threadIdx.x], cell_index(a.d, c.i, c.j, c.k), plane_index(a.d, c.i, c.j));
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
+    do {
+        double* mine = &buf[0][threadIdx.x];
+        const Chunk c = chunk_of(a.d, t, chunks, ny);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const Inputs in = pipe_read(a, mine, c.k);  // (a thread beyond the row's end reads its idle column: never used)
+        t += gridDim.x;
+        if (t < ntiles) {  // the column is free (its values are in registers): the next chunk's copies may land
+            const Chunk n = chunk_of(a.d, t, chunks, ny);
+            if (n.i < a.d.i1) pipe_issue(a, mine, cell_index(a.d, n.i, n.j, n.k), plane_index(a.d, n.i, n.j));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (c.i < a.d.i1) {
+            const long long idx = cell_index(a.d, c.i, c.j, c.k);
+            FastSink<ACC, FULL> sink{a, idx, 0u, needs_exact(in) ? 1u : 0u};
+            cell_tendencies<false>(a, in, sink);
+            if (sink.pending) cell_exact(a, idx, plane_index(a.d, c.i, c.j), c.k, sink.pending);
+        }
+    } while (t < ntiles);
 }
 
 }  // namespace obm
@@ -292,29 +265,22 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
     }();
     (void)carveout_set;
     const bool full = A.out_mask == (1u << NOUT) - 1u;
-#if OBM_PISCES_TMA
-    {   // TMA-staged persistent launch when every row copy is a whole, 16-byte aligned chunk inside its array
-        const int nx = A.d.i1 - A.d.i0, shift = (A.d.i0 + A.d.Hx) & 1;
-        const char* sw = getenv("OBM_PISCES_TMA");  // "0": take the direct-load kernel (A/B timing, the equivalence test)
-        bool ok = !(sw && sw[0] == '0') && nx % PB == 0 && (A.d.sy % 2) == 0 && A.d.Hx >= 1;
-        auto aligned = [](const void* q) { return ((uintptr_t)q & 15u) == 0; };
-        for (int n = 0; n < OBM_PISCES_NTRACERS && ok; n++)
-            if (!(n == T_DIC || n == T_Alk || n == T_S)) ok = aligned(A.c[n]);
-        ok = ok && aligned(aux->PAR1) && aligned(aux->PAR2) && aligned(aux->PAR3) && aligned(aux->PAR) && aligned(aux->Omega)
-             && aligned(aux->wPOC) && aligned(aux->wGOC) && aligned(aux->mixed_layer_depth_xy) && aligned(aux->euphotic_depth_xy)
-             && aligned(aux->mean_mixed_layer_vertical_diffusivity_xy) && aligned(aux->mean_mixed_layer_light_xy);
-        if (ok) {
-            const long long ntiles = (long long)(nx / PB) * (A.d.j1 - A.d.j0) * A.d.Nz;
+#if OBM_PISCES_PIPE
+    {
+        const unsigned chunks = (unsigned)((A.d.i1 - A.d.i0 + PB - 1) / PB);
+        const long long nt = (long long)chunks * (A.d.j1 - A.d.j0) * A.d.Nz;
+        if (nt < (1LL << 31)) {
             static const int sms = [] { int dev = 0, n = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }();
-            const unsigned blocks = (unsigned)(ntiles < (long long)sms * OBM_PISCES_MIN_BLOCKS ? ntiles : (long long)sms * OBM_PISCES_MIN_BLOCKS);
+            const long long resident = (long long)sms * OBM_PISCES_MIN_BLOCKS;
+            const unsigned blocks = (unsigned)(nt < resident ? nt : resident);
             if (A.accumulate) {
-                if (full) pisces_tendency_tma_kernel<true, true><<<blocks, PB, 0, st>>>(A, ntiles, shift);
-                else pisces_tendency_tma_kernel<true, false><<<blocks, PB, 0, st>>>(A, ntiles, shift);
+                if (full) pisces_tendency_pipe_kernel<true, true><<<blocks, PB, 0, st>>>(A, (unsigned)nt, chunks);
+                else pisces_tendency_pipe_kernel<true, false><<<blocks, PB, 0, st>>>(A, (unsigned)nt, chunks);
             } else {
-                if (full) pisces_tendency_tma_kernel<false, true><<<blocks, PB, 0, st>>>(A, ntiles, shift);
-                else pisces_tendency_tma_kernel<false, false><<<blocks, PB, 0, st>>>(A, ntiles, shift);
+                if (full) pisces_tendency_pipe_kernel<false, true><<<blocks, PB, 0, st>>>(A, (unsigned)nt, chunks);
+                else pisces_tendency_pipe_kernel<false, false><<<blocks, PB, 0, st>>>(A, (unsigned)nt, chunks);
             }
-            return launch_status("pisces_tendency_tma_kernel");
+            return launch_status("pisces_tendency_pipe_kernel");
         }
     }
 #endif

@@ -313,6 +313,12 @@ def pisces_tendency_scales(grid: Grid, params, tracers, aux: dict):
     return S
 
 
+def set_nested_free_iron_scale(on: bool):
+    """S of SFe, BFe, Fe with Fe′'s OWN Σ|terms| in place of |Fe′| (oracle_pisces.c::free_iron): for the test of extreme
+    finite states, where Fe′ = −Δ + √(Δ² + 4K·Fe) is cancellation noise.  Off by default; switch it back off after use."""
+    lib().orc_pisces_set_nested_free_iron_scale(1 if on else 0)
+
+
 _select_lib = None
 
 

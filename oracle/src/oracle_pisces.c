@@ -400,11 +400,21 @@ static double bacteria_activity(PP p, PC c) {
 
 /* ===================== iron chemistry ===================== */
 /* iron/iron.jl:25-37 */
+/* Fe′ is the small root of a quadratic written as a difference: −Δ + √(Δ² + 4K·Fe) with Δ = 1 + K·L − K·Fe, itself a
+ * difference.  orc_fep_scale records ITS Σ|additive terms| (Δ's included): the tendencies that multiply Fe′ use it in
+ * place of |Fe′| when orc_nested_free_iron is set — the convention of oracle_common.h ("a term that is itself a
+ * difference contributes its own Σ|terms|") applied one level further down, for states where Fe′ is pure cancellation
+ * noise (ligands ≫ Fe or Fe ≫ ligands by ten orders: tests of extreme finite states only; off by default). */
+int orc_nested_free_iron = 0;
+static __thread double orc_fep_scale = 0.0;
+void orc_pisces_set_nested_free_iron_scale(int on) { orc_nested_free_iron = on; }
 static double free_iron(PC c) {
     double ligands = jl_max(0.6, 0.09 * (c->DOC + 40) - 3);
     double K = exp(16.27 - 1565.7 / jl_max(c->T + 273.15, 5));
     double D = 1 + K * ligands - K * c->Fe;
-    return (-D + sqrt(D * D + 4 * K * c->Fe)) / (2 * K);
+    double root = sqrt(D * D + 4 * K * c->Fe);
+    orc_fep_scale = orc_nested_free_iron ? (1 + fabs(K * ligands) + fabs(K * c->Fe) + root) / fabs(2 * K) : fabs((-D + root) / (2 * K));
+    return (-D + root) / (2 * K);
 }
 
 /* ===================== dissolved organic matter ===================== */
@@ -428,6 +438,7 @@ static void dom_aggregation(PP p, PC c, double* total, double* F1, double* F2, d
     if (F3) *F3 = P3;
 }
 /* :96-110 → (CgFe1 + CgFe2, CgFe1, CgFe2) */
+static __thread double orc_cg_scale[2]; /* Σ|terms| of CgFe1, CgFe2 (see free_iron) */
 static void aggregation_of_colloidal_iron(PP p, PC c, double* total, double* Cg1, double* Cg2) {
     double F1, F2, F3;
     dom_aggregation(p, c, NULL, &F1, &F2, &F3);
@@ -436,6 +447,9 @@ static void aggregation_of_colloidal_iron(PP p, PC c, double* total, double* Cg1
     double colloidal_iron = 0.5 * ligand_iron;
     double C1 = (F1 + F3) * colloidal_iron / (c->DOC + EPS0);
     double C2 = F2 * colloidal_iron / (c->DOC + EPS0);
+    double li_s = orc_nested_free_iron ? fabs(c->Fe) + orc_fep_scale : fabs(ligand_iron); /* Σ|terms| of Fe − Fe′ */
+    orc_cg_scale[0] = fabs((F1 + F3) * 0.5 * li_s / (c->DOC + EPS0));
+    orc_cg_scale[1] = fabs(F2 * 0.5 * li_s / (c->DOC + EPS0));
     if (total) *total = C1 + C2;
     if (Cg1) *Cg1 = C1;
     if (Cg2) *Cg2 = C2;
@@ -694,7 +708,7 @@ static double tendency(PP p, PC c, int name) {
             double gr = total_grazing_POC(p, c) * theta;
             double atl = pom_aggregation(p, c) * theta;
             double sb = specific_degradation_rate(p, c) * c->SFe;
-            ORC_TERMS(gw, pm, zm, lb, scav, ba, ca, gr, atl, sb);
+            ORC_TERMS(gw, pm, zm, lb, lFe * c->POC * orc_fep_scale, ba, orc_cg_scale[0], gr, atl, sb);
             return (gw + pm + zm + lb + scav + ba + ca - gr - atl - sb);
         }
         case T_BFe: { /* iron.jl:47-89 */
@@ -712,7 +726,7 @@ static double tendency(PP p, PC c, int name) {
             aggregation_of_colloidal_iron(p, c, NULL, NULL, &ca);
             double gr = total_grazing_GOC(p, c) * tB;
             double lb = specific_degradation_rate(p, c) * c->BFe;
-            ORC_TERMS(gw, pm, zm, utf, scav, ba, ca, atl, gr, lb);
+            ORC_TERMS(gw, pm, zm, utf, lFe * c->GOC * orc_fep_scale, ba, orc_cg_scale[1], atl, gr, lb);
             return (gw + pm + zm + utf + scav + ba + ca + atl - gr - lb);
         }
         case T_PSi: { /* particulate_organic_matter/silicate.jl:1-9 */
@@ -767,7 +781,9 @@ static double tendency(PP p, PC c, int name) {
             double gw = non_assimilated_iron(p, c);
             double s_gw = orc_term_scale; /* itself intake − waste − growth: its own Σ|terms| */
             double utw = upper_trophic_dissolved_iron(p, c);
-            ORC_TERMS(small_particles, s_gw, utw, consumption, ligand_aggregation, colloidal, scav, BactFe);
+            ORC_TERMS(small_particles, s_gw, utw, consumption,
+                      p->excess_scavenging_enhancement * lFe * jl_max(0, c->Fe - total_ligand) * orc_fep_scale,
+                      orc_cg_scale[0] + orc_cg_scale[1], lFe * (c->POC + c->GOC) * orc_fep_scale, BactFe);
             return (small_particles + gw + utw - consumption - ligand_aggregation - colloidal - scav - BactFe);
         }
         case T_Si: { /* silicate.jl:20-26 */

@@ -19,4 +19,7 @@ wait
 v p8_batch_newton_b8_nolevel negative_tracers $NEWTON -DOBM_SN_MIN_BLOCKS=8 -DOBM_CC_LEVEL=0 &   # without the per-level tables
 v p9_lib_newton_b8_nolevel negative_tracers -DOBM_CC_EXP=0 -DOBM_CC_LOG=0 $NEWTON -DOBM_SN_MIN_BLOCKS=8 -DOBM_CC_LEVEL=0 &
 wait
+v l2_exp_horner light -DOBM_LIGHT_EXP=2 &
+v l3_exp_clamped light -DOBM_LIGHT_EXP=3 &
+wait
 ls build/variants

@@ -10,6 +10,9 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytes
 echo "== tendency kernel: TMA-staged vs direct (16.8 M cells)"
 for m in 1 0 1 0; do OBM_PISCES_TMA=$m python scripts/time_kernels.py pisces_c4 0.125 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('TMA=$m', *[(k, round(d[k],4)) for k in ('tendencies_ms','tendencies_overwrite_ms','scale_negative_calcite_fused_ms','light_with_column_state_ms')])" | tee -a gpurun_out/variants.txt; done
 echo "== prologue variants (16.8 M cells)"
+for so in build/variants/libobm_l*.so; do
+  OBM_B200_LIB=$PWD/$so timeout 300 python scripts/time_kernels.py pisces_c4 0.125 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$so', *[(k, round(d[k],4)) for k in ('light_ms','light_with_column_state_ms')])" | tee -a gpurun_out/variants.txt
+done
 for so in build/variants/libobm_p*.so; do
   OBM_B200_LIB=$PWD/$so timeout 300 python scripts/time_kernels.py pisces_c4 0.125 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$so', *[(k, round(d[k],4)) for k in ('scale_negative_calcite_fused_ms','underlying_state_ms')])" | tee -a gpurun_out/variants.txt
 done

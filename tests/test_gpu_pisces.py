@@ -159,7 +159,14 @@ def test_extreme_finite_states_match_the_reference_patterns(cuda, oracle):
     params = u.c_params(0.0)
     tr = [host[m] for m in pisces.TRACERS]
     Go = oracle.pisces_tendencies(og, params, tr, aux)
-    So = oracle.pisces_tendency_scales(og, params, tr, aux)
+    # Fe′ = (−Δ + √(Δ² + 4K·Fe)) / 2K is cancellation noise in these states (Fe = 1e30 against ligands of 0.6, or DOC = 1e6
+    # against Fe = 0.1: ten and more digits lost, so one ulp in exp — CUDA's vs libm's — decides the value): the three iron
+    # tendencies are measured against Σ|terms| with Fe′'s own Σ|terms| counted (oracle_pisces.c::free_iron)
+    oracle.set_nested_free_iron_scale(True)
+    try:
+        So = oracle.pisces_tendency_scales(og, params, tr, aux)
+    finally:
+        oracle.set_nested_free_iron_scale(False)
     nonfinite = 0
     for m, g, sc in zip(pisces.TRACERS[:24], Go, So):
         want, got, S = og.interior(g), og.interior(G[m].data.cpu().numpy()), og.interior(sc)
@@ -374,32 +381,3 @@ def test_per_tracer_call_form(cuda, oracle):
     Fe = torch.linspace(0.05, 1.5, 9, dtype=torch.float64)
     gP = u("PFe", z=z, time=t, device=cuda, **{**state, "Fe": Fe}, **aux)
     assert gP.shape == (9,) and bool((gP[1:] > gP[:-1]).all())  # iron uptake grows with dissolved iron
-
-
-@pytest.mark.parametrize("accumulate", [False, True])
-def test_tma_staged_launch_equals_the_direct_launch(cuda, oracle, accumulate, monkeypatch):
-    """The tendency kernel has two launch forms with ONE cell arithmetic: the persistent, TMA-staged one (whole 128-cell
-    chunks: `cp.async.bulk` row copies of the next tile fly while a tile is computed) and the direct-load one (any
-    geometry).  Same inputs → the same bits, halos untouched, NaN inputs handled by the same exact pass; and the result
-    is the oracle's.  Several tiles per block (more tiles than 3 × 148 blocks) so that the buffer is reused."""
-    grid, bgc, model = build(cuda, (256, 9, 40), (1e4, 1e3, 400.0))   # 2 chunks × 9 rows × 40 levels = 720 tiles > 444 blocks
-    u = bgc.underlying_biogeochemistry
-    host = fill(model, bgc)
-    model.update_state()
-    model.tracers["Fe"].interior[3, 4, 200] = float("nan")            # one cell through the exact pass
-    host["Fe"] = np.ascontiguousarray(model.tracers["Fe"].data.cpu().numpy())
-    aux = bgc.biogeochemical_auxiliary_fields()
-    out = {}
-    for mode in ("1", "0"):
-        monkeypatch.setenv("OBM_PISCES_TMA", mode)
-        G = {n: ob.CenterField(grid, fill=2.5e-7) for n in pisces.TRACERS}
-        u.compute_tendencies(grid, model.tracers, aux, G, accumulate=accumulate, time=0.0)
-        torch.cuda.synchronize()
-        out[mode] = G
-    for n in pisces.TRACERS:
-        a, b = out["1"][n].data, out["0"][n].data
-        assert bool(((a == b) | (a.isnan() & b.isnan())).all()), n
-    og = oracle.Grid.like(grid)
-    worst, _ = compare(oracle, og, u, host, host_aux(og, grid, bgc), out["1"], 0.0, accumulate=accumulate, g0=2.5e-7,
-                       label=f"pisces_tma_staged[acc={accumulate}]")
-    assert max(worst.values()) <= RTOL_TENDENCY
