@@ -212,3 +212,9 @@ extern "C" int fused_carbon_chemistry(long long n, const double* T, const double
         out[c] = cc::solve<false>(output_kind, T[c], S[c], DIC[c], Alk[c], 0.0, false, 0.0, false, 0.0, false, 0.0, 1e-8, iterations, nullptr);
     return 0;
 }
+
+// exp_table of csrc/obm_common.cuh over an array (tests/test_fused_host.py: accuracy against libm)
+extern "C" int fused_exp_table(long long n, const double* x, double* out, int clamped) {
+    for (long long q = 0; q < n; q++) out[q] = clamped ? exp_table_clamped(x[q]) : exp_table(x[q]);
+    return 0;
+}

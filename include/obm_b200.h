@@ -638,6 +638,27 @@ int obm_rk3_substep(const obm_grid* grid, int nfields, double* const* U, const d
                     int cache_previous, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-2) Tendencies AND the tracer update in ONE launch, for models in which nothing but the
+ * biogeochemistry (and a forcing already sitting in Gⁿ) moves the tracers — box models, column
+ * ensembles, parameter sweeps (src/BoxModel/timesteppers.jl:30-93: compute_tendencies! →
+ * rk3_substep! → cache_previous_tendencies!, three passes over every field per stage):
+ *     G      = bgc_n(U) (+ Gⁿ[n] as found, when accumulate != 0: the forcing)
+ *     U[n]  += Δt·(γ·G + ζ·G⁻[n])        (has_zeta = 0, first stage / Euler: U[n] += Δt·γ·G)
+ *     G⁻[n] ← G                           (Gⁿ[n] ← G as well when store_Gn != 0)
+ * evaluated per cell from one read of the cell's tracers, so Gⁿ never travels: 312 instead of
+ * ≈ 630 B per cell and stage for LOBSTER + carbonates + O₂.  `tracers` are read AND written
+ * (every thread reads its whole cell before it writes any of it: pointwise, no hazard); a
+ * tracer whose Gm[n] is NULL is not stepped (prescribed fields, T); G may be NULL when neither
+ * accumulate nor store_Gn asks for it.  nvary > 0: per-column parameter values exactly as in
+ * obm_npd_tendencies_ensemble.  Same arithmetic, same operation order as obm_npd_tendencies
+ * followed by obm_rk3_substep — the two paths agree bit for bit (tests/test_gpu_box_model.py).
+ * ------------------------------------------------------------------------------------ */
+int obm_npd_tendencies_substep(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
+                               const double* values, double* const* tracers, const double* PAR, double* const* G,
+                               int accumulate, int store_Gn, double* const* Gm, double dt, double gamma, double zeta,
+                               int has_zeta, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
  * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
  * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics

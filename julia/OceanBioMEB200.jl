@@ -445,6 +445,14 @@ rk3_substep!(g, U, Gⁿ, G⁻, Δt, γ, ζ, has_ζ, cache_previous, s) =
                 (Ref{ObmGrid}, Cint, Ptr{F64}, Ptr{F64}, Ptr{F64}, Cdouble, Cdouble, Cdouble, Cint, Cint, Ptr{Cvoid}),
                 g, length(U), U, Gⁿ, G⁻, Δt, γ, ζ, has_ζ, cache_previous, s), "obm_rk3_substep")
 
+# the same with the tendencies evaluated in the launch itself (NPZD / LOBSTER family): compute_tendencies! + rk3_substep! +
+# cache_previous_tendencies! of src/BoxModel/timesteppers.jl:30-93 in one pass; Gⁿ may be C_NULL (no forcing, nothing stored)
+npd_tendencies_substep!(g, p, nvary, which, values, U, PAR, Gⁿ, accumulate, store_Gⁿ, G⁻, Δt, γ, ζ, has_ζ, s) =
+    check(ccall((:obm_npd_tendencies_substep, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmNpdParams}, Cint, Ptr{Int32}, F64, Ptr{F64}, F64, Ptr{F64}, Cint, Cint, Ptr{F64}, Cdouble, Cdouble,
+                 Cdouble, Cint, Ptr{Cvoid}),
+                g, p, nvary, which, values, U, PAR, Gⁿ, accumulate, store_Gⁿ, G⁻, Δt, γ, ζ, has_ζ, s), "obm_npd_tendencies_substep")
+
 # CarbonChemistry()(; DIC, Alk, T, S, …) over flat device arrays (src/Models/CarbonChemistry/carbon_chemistry.jl:84-181)
 carbon_chemistry!(out, p, T, S, DIC, Alk, P_bar, silicate, phosphate, pH, output_kind, n, s) =
     check(ccall((:obm_carbon_chemistry, libobm), Cint,

@@ -297,6 +297,9 @@ PROTOTYPES = {
     "obm_gas_exchange_flux": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_gas_exchange_params)] + [C.c_void_p] * 12),
     "obm_rk3_substep": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                                   C.c_double, C.c_int, C.c_int, C.c_void_p]),
+    "obm_npd_tendencies_substep": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double,
+                                             C.c_double, C.c_double, C.c_int, C.c_void_p]),
     "obm_copy_slab": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_copy_slab_sm": (C.c_int, [C.POINTER(obm_grid), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "obm_fp64_peak_dfma_per_s": (C.c_double, [C.c_void_p, C.c_int, C.c_void_p]),

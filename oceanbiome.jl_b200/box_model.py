@@ -79,7 +79,11 @@ class BoxModel:
 
     def __init__(self, biogeochemistry, grid: Optional[RectilinearGrid] = None, forcing: Optional[dict] = None,
                  timestepper: str = "RungeKutta3", clock: Optional[Clock] = None,
-                 prescribed_tracers: Optional[Dict[str, Callable]] = None):
+                 prescribed_tracers: Optional[Dict[str, Callable]] = None, fused_step: bool = False):
+        """`fused_step=True` (NPZD / LOBSTER family without sediment or particles): every stage is ONE launch —
+        `compute_tendencies!`, `rk3_substep!` and `cache_previous_tendencies!` (timesteppers.jl:30-93) evaluated per
+        cell from one read of its tracers (`obm_npd_tendencies_substep`); the tracers and G⁻ are those of the
+        three-launch path bit for bit, Gⁿ is not materialised (`model.Gn` then only carries the forcing)."""
         self.biogeochemistry = biogeochemistry
         self.grid = grid if grid is not None else BoxModelGrid()
         self.clock = clock or Clock()
@@ -106,6 +110,13 @@ class BoxModel:
         self._tables = None
         self._graph = None
         self._needs_initial_update = True
+        self.fused_step = bool(fused_step)
+        if self.fused_step:
+            u = biogeochemistry.underlying_biogeochemistry
+            if not hasattr(u, "compute_tendencies_and_substep"):
+                raise ValueError(f"fused_step: {type(u).__name__} has no fused tendency + substep launch")
+            if getattr(biogeochemistry, "sediment", None) is not None or getattr(biogeochemistry, "particles", None) is not None:
+                raise ValueError("fused_step: sediment / particles add tendencies of their own; use the three-launch path")
 
     # the hooks read `model.tracers` (an Oceananigans model's NamedTuple of tracer fields)
     @property
@@ -161,19 +172,33 @@ class BoxModel:
                                          0.0 if zeta is None else float(zeta), int(zeta is not None), 1, s)
         _lib.check(rc, "obm_rk3_substep")
 
+    def _fused_stage(self, dt, gamma, zeta, stream=None):
+        """One stage as one launch: Gⁿ of every tracer from the current state (+ the forcing waiting in `Gn`), the tracer
+        update and the G⁻ cache."""
+        forced = {n: self.Gn[n] for n in self.prognostic if self.forcing.get(n) is not None}
+        self.biogeochemistry.underlying_biogeochemistry.compute_tendencies_and_substep(
+            self.grid, self.fields, self.auxiliary_fields, {n: self.Gm[n] for n in self.prognostic}, dt, gamma, zeta,
+            G=forced or None, accumulate=bool(forced), stream=stream)
+
     def time_step(self, dt: float):
         """`time_step!(model, Δt)`: Oceananigans' RK3 (or forward Euler) over the box-model methods above."""
         if self._needs_initial_update:  # what `run!` / the first `time_step!` do at iteration 0
-            self.update_state()
+            self.update_state(compute_tendencies=not self.fused_step)
             self._needs_initial_update = False
         stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
         for gamma, zeta in stages:
             self.clock.rk3_gamma, self.clock.rk3_zeta = gamma, (zeta if zeta is not None else float("nan"))
-            self._substep(dt, gamma, zeta)
+            if self.fused_step:
+                for n in self.prognostic:  # the forcing the three-launch path evaluated at the end of the previous stage
+                    if self.forcing.get(n) is not None:
+                        self.Gn[n].set(self.forcing[n](self.clock.time))
+                self._fused_stage(dt, gamma, zeta)
+            else:
+                self._substep(dt, gamma, zeta)
             stage_dt = dt * (gamma + (zeta or 0.0))
             self.clock.time += stage_dt
             self.clock.last_stage_dt = stage_dt
-            self.update_state()
+            self.update_state(compute_tendencies=not self.fused_step)
         self.clock.iteration += 1
 
     # ---- run!(simulation) --------------------------------------------------------------------------------------
@@ -238,26 +263,36 @@ class BoxModel:
             raise ValueError("graph=True: a surface PAR function of time is evaluated on the host; prescribe PAR "
                              "(prescribed_tracers={'PAR': f}) or use a constant surface PAR")
         if self._needs_initial_update:
-            self.update_state()
+            self.update_state(compute_tendencies=not self.fused_step)
             self._needs_initial_update = False
         stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
         times, tabs = self._tabulate(dt, steps)
         dev = self.grid.device
         row = torch.zeros(1, dtype=torch.long, device=dev)  # device-side cursor into the tables
 
+        if self.fused_step:  # the first stage finds the forcing of the initial time in Gⁿ, every later one that of the row before
+            for n in self.prognostic:
+                if self.forcing.get(n) is not None:
+                    self.Gn[n].set(self.forcing[n](self.clock.time))
+
         def one_step():
             for gamma, zeta in stages:
-                self._substep(dt, gamma, zeta)
+                if self.fused_step:
+                    self._fused_stage(dt, gamma, zeta)
+                else:
+                    self._substep(dt, gamma, zeta)
                 for (kind, n), tab in tabs.items():
                     if kind == "prescribed":
                         self._prescribed_target(n).interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
                 self.biogeochemistry.update_biogeochemical_state(self)
-                self._Gn_slab.zero_()
+                if not self.fused_step:
+                    self._Gn_slab.zero_()
                 for n in self.prognostic:
                     tab = tabs.get(("forcing", n))
                     if tab is not None:
                         self.Gn[n].interior.reshape(-1).copy_(tab.index_select(0, row).reshape(-1))
-                self.biogeochemistry.update_tendencies(self)
+                if not self.fused_step:
+                    self.biogeochemistry.update_tendencies(self)
                 row.add_(1)
 
         # warm-up on a side stream (allocator, lazy module loads), with the state restored afterwards

@@ -26,9 +26,11 @@ namespace cc {
 // exp / log of the solve.  OBM_CC_EXP: 0 the library exp; 1 exp_lean of obm_common.cuh (even / odd Horner, out-of-line
 // library fall-back: measured r02, +6 % on the fused scaling + Ω kernel); 2 exp_horner below — plain degree-13 Horner
 // (17 FP64 instructions, one constant-bank operand each), range guard as ONE integer compare, the library exp inline in
-// the cold branch (no call, so no ABI register constraints on the hot path).  OBM_CC_LOG: 0 library log; 1 log_lean.
+// the cold branch (no call, so no ABI register constraints on the hot path); 3 exp_table of obm_common.cuh (64-entry table +
+// degree-5 polynomial: 10 FP64 instructions per exp instead of 17; −2.5 % on the fused scaling + Ω kernel, the default).
+// OBM_CC_LOG: 0 library log; 1 log_lean.
 #ifndef OBM_CC_EXP
-#define OBM_CC_EXP 2
+#define OBM_CC_EXP 3
 #endif
 #ifndef OBM_CC_LOG
 #define OBM_CC_LOG 1
@@ -41,8 +43,17 @@ __device__ __forceinline__ double cexp(double x) {
     return exp(x);
 #elif OBM_CC_EXP == 1
     return exp_lean(x);
-#else
+#elif OBM_CC_EXP == 2
     return exp_horner(x);
+#else
+    return exp_in_range(x) ? exp_table(x) : exp(x);  // 3: the 64-entry table form of obm_common.cuh
+#endif
+}
+__device__ __forceinline__ double cexp_unguarded(double x) {  // callers test exp_in_range themselves
+#if OBM_CC_EXP == 3
+    return exp_table(x);
+#else
+    return exp_unguarded(x);
 #endif
 }
 __device__ __forceinline__ double clog(double x) {
@@ -242,18 +253,18 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     const double eSi = KD(117.385) + KD(-8904.2) * invT + KD(-19.334) * logT + (KD(3.5913) + KD(-458.79) * invT) * sqIs
                        + (KD(-1.5998) + KD(188.74) * invT) * Is + (KD(0.07871) + KD(-12.1652) * invT) * (Is * Is) + logS1;
     c.KSi = 1.0;
-#if OBM_CC_EXP == 2 && OBM_CC_BATCH
+#if OBM_CC_EXP >= 2 && OBM_CC_BATCH
     // The kernel is bound by the LATENCY of dependent FP64 chains at 6 – 8 warps per scheduler (ncu, r3a: issue 66 %, FP64
     // pipe 62 %, neither saturated), and a guarded exp is its own basic block: six serial Horner chains.  Branch-free in
     // one block the six chains interleave; ONE combined range test (integer compares) sends the rare out-of-range or
     // NaN exponent through the library for all six.
-    c.K1 = exp_unguarded(e1);
-    c.K2 = exp_unguarded(e2);
-    c.KB = exp_unguarded(eB);
-    c.KW = exp_unguarded(eW);
-    c.KS = exp_unguarded(eS);
-    c.KF = exp_unguarded(eF);
-    if (need_silicate) c.KSi = exp_unguarded(eSi);
+    c.K1 = cexp_unguarded(e1);
+    c.K2 = cexp_unguarded(e2);
+    c.KB = cexp_unguarded(eB);
+    c.KW = cexp_unguarded(eW);
+    c.KS = cexp_unguarded(eS);
+    c.KF = cexp_unguarded(eF);
+    if (need_silicate) c.KSi = cexp_unguarded(eSi);
     if (!(exp_in_range(e1) & exp_in_range(e2) & exp_in_range(eB) & exp_in_range(eW) & exp_in_range(eS) & exp_in_range(eF)
           & (!need_silicate | exp_in_range(eSi)))) {
         c.K1 = exp(e1); c.K2 = exp(e2); c.KB = exp(eB); c.KW = exp(eW); c.KS = exp(eS); c.KF = exp(eF);
@@ -342,8 +353,10 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 // step clamped to one pH unit, at most `iterations` steps from H0.
 // OBM_CC_TOL: the warp-uniform exit threshold on |Δx|.  Newton converges quadratically here with a measured constant
 // |e₊| ≈ 0.30·Δx² in ln H (sea-water states; ≤ 1 over the robust box), so leaving after a step below 10⁻⁵ puts the
-// root within ≈ 3·10⁻¹¹ in ln H, 1.3·10⁻¹¹ in pH (robust box: ≤ 4.3·10⁻¹¹) — inside the stated 10⁻¹⁰; the exit is
-// warp-uniform, so all but the slowest lane of a warp end far below that (measured on the GPU: ≤ 2·10⁻¹³).
+// iterate within ≈ 3·10⁻¹¹ in ln H — and OBM_CC_EXTRAP (below) then removes the predictable part of that: measured
+// |ΔpH| ≤ 10⁻¹³ against the reference's damped Newton with every lane leaving on its own (host build; on the GPU the
+// slowest lane of a warp decides, so most lanes end far below).  Thresholds between 5·10⁻⁶ and 2·10⁻⁶ trigger one more
+// step for most warps: +6 … +8 % on the fused scaling + Ω kernel (profiles/r03_kernel_variants.txt).
 // OBM_CC_POLYEXP: once every lane's step is below 1/8 the factor e^(−Δx) is its degree-5 Taylor polynomial (5 FMAs
 // instead of an exp); the polynomial's own error, Δx⁶/720, is part of the NEXT iterate's error like the Newton remainder
 // and vanishes with it — the root is unchanged.
@@ -353,16 +366,27 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 #ifndef OBM_CC_POLYEXP
 #define OBM_CC_POLYEXP 1
 #endif
+// OBM_CC_EXTRAP: what is left after the last step is predicted and removed.  Newton's error obeys e₊ = C·e² with a
+// constant that two consecutive steps reveal — Δxₙ ≈ eₙ ≈ C·Δxₙ₋₁² — so the error of the final iterate, C·Δxₙ², is
+// Δxₙ³ / Δxₙ₋₁² to a relative O(Δxₙ₋₁); subtracting it costs one reciprocal and five multiplications per CELL (not per
+// step) and leaves ≈ 10⁻² of the exit error: with the 10⁻⁵ threshold the root is within 10⁻¹² in ln H instead of
+// 3·10⁻¹¹, at 1 % of the cost of the extra Newton step a 2·10⁻⁶ threshold would trigger (+7 %, timed).  Applied only when
+// both steps are inside the asymptotic regime (|Δxₙ| < |Δxₙ₋₁| < 1/8 and the prediction below 10⁻² |Δxₙ|).
+#ifndef OBM_CC_EXTRAP
+#define OBM_CC_EXTRAP 1
+#endif
 __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, bool need_phosphate, bool need_silicate,
                                           double H0, int iterations) {
     constexpr double LN10 = 2.302585092994045684;
     double H = H0;
+    double dx = 0.0, dx_prev = 0.0;
     const unsigned mask = __activemask();
 #pragma unroll 1
     for (int n = 0; n < iterations; n++) {
         double f, Hdf;
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
-        double dx = f * rcp_fast(Hdf);
+        dx_prev = dx;
+        dx = f * rcp_fast(Hdf);
         dx = dx < -LN10 ? -LN10 : (dx > LN10 ? LN10 : dx);  // selects, not fmin/fmax: NaN must propagate
         const double adx = fabs(dx);
 #if OBM_CC_POLYEXP
@@ -377,8 +401,17 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
             H *= cexp(-dx);
         // Warp-uniform early exit (no divergence): once every lane's step is below the threshold the quadratic
         // convergence of Newton puts this iterate within ~1e-12 of the root; NaN lanes count as converged (they stay NaN).
-        if (__all_sync(mask, !(adx >= KD(OBM_CC_TOL)))) break;
+        // (a FIRST step has no predecessor to extrapolate with: it ends the iteration only below 10⁻⁷ — a warm start)
+        if (__all_sync(mask, !(adx >= (n == 0 ? KD(1e-7) : KD(OBM_CC_TOL))))) break;
     }
+#if OBM_CC_EXTRAP
+    {
+        const double ap = fabs(dx_prev), an = fabs(dx);
+        const double pred = (dx * dx) * dx * rcp_fast(dx_prev * dx_prev);
+        const bool use = an < ap && ap < 0.125 && fabs(pred) < KD(1e-2) * an;  // false for NaN, for a single step (Δxₙ₋₁ = 0)
+        H = use ? fma(-H, pred, H) : H;  // H·e^(−pred), |pred| < 10⁻⁷
+    }
+#endif
     return H;
 }
 

@@ -22,9 +22,9 @@ namespace obm {
 
 // exp of the scans: the lean exp of obm_common.cuh (≈ 26 instructions, ≤ 2 ulp, library call for |x| ≥ 700 / NaN) —
 // these kernels are issue-bound on their 4 (two-band) / 2·bands (N-band) exps per cell: 3-band PAR 3.2 → 2.65 ms.
-// -DOBM_LIGHT_EXP=0 restores the library exp; 2 / 3: see lexp.
+// -DOBM_LIGHT_EXP=0 restores the library exp; 2 / 3 / 4: see lexp (4, the table form, is the fastest: profiles/r03_kernel_variants.txt).
 #ifndef OBM_LIGHT_EXP
-#define OBM_LIGHT_EXP 3
+#define OBM_LIGHT_EXP 4
 #endif
 __device__ __forceinline__ double lexp(double x) {
 #if OBM_LIGHT_EXP == 0
@@ -33,10 +33,14 @@ __device__ __forceinline__ double lexp(double x) {
     return exp_lean(x);
 #elif OBM_LIGHT_EXP == 2
     return exp_horner(x);   // plain Horner, integer range test, library exp inline in the cold branch (no call)
+#elif OBM_LIGHT_EXP == 4
+    return exp_table_clamped(x);  // 64-entry table + degree-5 polynomial (obm_common.cuh), same clamp semantics as 3
 #else
-    // branch-free: the argument is clamped to where the polynomial form is valid.  −745 → 5e-324 instead of the exact 0
-    // of exp(−Inf) (Chl = 0: χ·5e-324 vanishes in kʷ + χ Chl^e), 709 → 8e307 instead of +Inf (Chl ≳ 1e300); NaN stays NaN.
-    return exp_unguarded(x < -745.0 ? -745.0 : (x > 709.0 ? 709.0 : x));
+    // branch-free: the argument is clamped to where the exponent-field arithmetic of exp_unguarded is valid (normal
+    // results).  −708 → 3.3e-308 instead of the subnormals / exact 0 below it (Chl = 0: ln 0 = −Inf and χ·3e-308 vanishes
+    // in kʷ + χ Chl^e; an attenuation factor that small multiplies a PAR already far below any threshold), 709 → 8e307
+    // instead of +Inf (Chl ≳ 1e300); NaN stays NaN.
+    return exp_unguarded(x < -708.0 ? -708.0 : (x > 709.0 ? 709.0 : x));
 #endif
 }
 

@@ -28,6 +28,13 @@ struct NpdArgs {
     double* gAlk[MAX_REPLICATES];
     int nrep;
     int accumulate;
+    // f-2, tendencies + tracer update in one launch (obm_npd_tendencies_substep): U ← U + Δt(γG + ζG⁻), G⁻ ← G with G the
+    // tendency this thread has just computed (+ the forcing found in Gⁿ when `accumulate`); u* / m* are the tracer itself
+    // (written) and its G⁻, NULL for an output that is not stepped
+    struct Step { int on, has_zeta, store_gn; double dt, gamma, zeta; } step;
+    double *uNO3, *uNH4, *uFe, *uN, *uP, *uZ, *uD, *usPOM, *ubPOM, *uDOM, *usPOC, *ubPOC, *uDOC, *uO2;
+    double *mNO3, *mNH4, *mFe, *mN, *mP, *mZ, *mD, *msPOM, *mbPOM, *mDOM, *msPOC, *mbPOC, *mDOC, *mO2;
+    double *uDIC[MAX_REPLICATES], *uAlk[MAX_REPLICATES], *mDIC[MAX_REPLICATES], *mAlk[MAX_REPLICATES];
     // parameter-sweep ensembles: member = horizontal column (i + Nx·j); values[v·members + member] replaces parameter which[v]
     int nvary;
     int which[OBM_NPD_MAX_VARIED];
@@ -71,18 +78,27 @@ __device__ __forceinline__ void set_param(obm_npd_params& p, int which, double v
     }
 }
 
-__device__ __forceinline__ void put(double* g, long long idx, double t, int accumulate) {
-    if (g == nullptr) return;
-    if (accumulate) t += g[idx];
-    g[idx] = t;
-}
 // `accumulate` read issued up front (with the tracer loads) so that no store waits on a late, dependent load
 __device__ __forceinline__ double old_value(const double* g, long long idx, int accumulate) {
     return (accumulate && g != nullptr) ? g[idx] : 0.0;
 }
-__device__ __forceinline__ void put(double* g, long long idx, double t, double old) {
-    if (g != nullptr) g[idx] = t + old;
+// One output leaves the thread: Gⁿ ← t + old — or, in the fused tendency + substep launch, the tracer update of
+// src/BoxModel/timesteppers.jl:66-93 with this value as Gⁿ (same unfused operation order as rk3_substep_kernel:
+// the two paths agree bit for bit) and `cache_previous_tendencies!` (:20-28).
+__device__ __forceinline__ void deliver(const NpdArgs& a, double* g, double* u, double* m, long long idx, double G) {
+    if (!a.step.on) {
+        if (g != nullptr) g[idx] = G;
+        return;
+    }
+    if (g != nullptr && a.step.store_gn) g[idx] = G;
+    if (u == nullptr) return;
+    double rhs;
+    if (a.step.has_zeta) rhs = __dmul_rn(a.step.dt, __dadd_rn(__dmul_rn(a.step.gamma, G), __dmul_rn(a.step.zeta, m[idx])));
+    else rhs = __dmul_rn(__dmul_rn(a.step.dt, a.step.gamma), G);
+    u[idx] = __dadd_rn(u[idx], rhs);
+    if (m != nullptr) m[idx] = G;
 }
+#define PUT(name, value, old) deliver(a, a.g##name, a.u##name, a.m##name, idx, (value) + (old))
 
 // plankton.jl:86-90
 __device__ __forceinline__ double mortality(int form, double X, double m) { return form == OBM_LINEAR ? m * X : m * (X * X); }
@@ -171,8 +187,8 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
     else dinw = ponw + sw;
 
     // ---- plankton: plankton.jl:92-116 -----------------------------------------------------------
-    put(a.gP, idx, (1 - p.phytoplankton_exudation_fraction) * muP - Gp - nuP, oP);
-    put(a.gZ, idx, p.zooplankton_assimilation_fraction * Gtot - mZZ - exc * Z, oZ);
+    PUT(P, (1 - p.phytoplankton_exudation_fraction) * muP - Gp - nuP, oP);
+    PUT(Z, p.zooplankton_assimilation_fraction * Gtot - mZZ - exc * Z, oZ);
 
     // ---- nutrients: nutrients.jl:22-64, uptake plankton.jl:223-278 --------------------------
     double tNO3 = 0, tNH4 = 0, tN = 0, nitrif = 0;
@@ -182,31 +198,31 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
         const double lim = nl + al + eps0();
         tNO3 = nitrif - muP * nl / lim;
         tNH4 = pinw + dinw - nitrif - (muP * al / lim - ag * muP);
-        put(a.gNO3, idx, tNO3, oNO3);
-        put(a.gNH4, idx, tNH4, oNH4);
-        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) put(a.gFe, idx, -(p.iron_ratio * muP), oFe);
+        PUT(NO3, tNO3, oNO3);
+        PUT(NH4, tNH4, oNH4);
+        if constexpr (NUT == OBM_NUT_NITRATE_AMMONIA_IRON) PUT(Fe, -(p.iron_ratio * muP), oFe);
     } else {
         tN = pinw + dinw - muP * (1 - ag);
-        put(a.gN, idx, tN, oN);
+        PUT(N, tN, oN);
     }
 
     // ---- detritus: detritus.jl:85-101, 143-158, 282-288 --------------------------------------
     const double R = p.redfield_ratio;
     if constexpr (DET == OBM_DET_DETRITUS) {
-        put(a.gD, idx, ponw + sw - Gd - p.remineralisation_rate * D, oD);
+        PUT(D, ponw + sw - Gd - p.remineralisation_rate * D, oD);
     }
     if constexpr (TWO_SIZE) {
         const double ssf = p.small_solid_waste_fraction;
-        put(a.gsPOM, idx, ssf * sw - Gd - sm * sPOM, osPOM);
-        put(a.gbPOM, idx, (1 - ssf) * sw - bm * bPOM, obPOM);
-        put(a.gDOM, idx, ponw + (1 - af) * (sm * sPOM + bm * bPOM) - dm * DOM, oDOM);
+        PUT(sPOM, ssf * sw - Gd - sm * sPOM, osPOM);
+        PUT(bPOM, (1 - ssf) * sw - bm * bPOM, obPOM);
+        PUT(DOM, ponw + (1 - af) * (sm * sPOM + bm * bPOM) - dm * DOM, oDOM);
         if constexpr (DET == OBM_DET_VARIABLE_REDFIELD) {
             const double scw = sw * R;  // solid_carbon_waste plankton.jl:348
             // calcite_production plankton.jl:399-412
             const double cprod = (Gp * (1 - p.zooplankton_gut_calcite_dissolution) + nuP) * p.carbon_calcite_ratio * R;
-            put(a.gsPOC, idx, ssf * scw - Gd * R - sm * sPOC, osPOC);
-            put(a.gbPOC, idx, (1 - ssf) * scw + cprod - bm * bPOC, obPOC);
-            put(a.gDOC, idx, R * ponw + (1 - af) * (sm * sPOC + bm * bPOC) - dm * DOC, oDOC);
+            PUT(sPOC, ssf * scw - Gd * R - sm * sPOC, osPOC);
+            PUT(bPOC, (1 - ssf) * scw + cprod - bm * bPOC, obPOC);
+            PUT(DOC, R * ponw + (1 - af) * (sm * sPOC + bm * bPOC) - dm * DOC, oDOC);
         }
     }
 
@@ -236,19 +252,19 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
         double tAlk;
         if constexpr (HAS_NA) tAlk = tNH4 * (1 - 1.0 / 16) - tNO3 * (1 + 1.0 / 16) - 2.0 * cupt + 2.0 * cdis;
         else tAlk = tN - 2.0 * cupt + 2.0 * cdis;
-        put(a.gDIC[0], idx, tDIC, oDIC);
-        put(a.gAlk[0], idx, tAlk, oAlk);
+        deliver(a, a.gDIC[0], a.uDIC[0], a.mDIC[0], idx, tDIC + oDIC);
+        deliver(a, a.gAlk[0], a.uAlk[0], a.mAlk[0], idx, tAlk + oAlk);
 #pragma unroll 1
         for (int r = 1; r < a.nrep; r++) {  // CarbonateSystem(N): every replicate gets the same tendency (:70-83)
-            put(a.gDIC[r], idx, tDIC, a.accumulate);
-            put(a.gAlk[r], idx, tAlk, a.accumulate);
+            deliver(a, a.gDIC[r], a.uDIC[r], a.mDIC[r], idx, tDIC + old_value(a.gDIC[r], idx, a.accumulate));
+            deliver(a, a.gAlk[r], a.uAlk[r], a.mAlk[r], idx, tAlk + old_value(a.gAlk[r], idx, a.accumulate));
         }
     }
 
     // ---- oxygen: oxygen.jl:21-31 (Nutrient models: bgc(Val(:NH₄)) = 0, nitrification = 0) -------
-    if (a.gO2 != nullptr) {
+    if (a.gO2 != nullptr || a.uO2 != nullptr) {
         const double Rp = p.respiration_oxygen_nitrogen_ratio, Rn = p.nitrification_oxygen_nitrogen_ratio;
-        put(a.gO2, idx, Rp * muP - (Rp - Rn) * tNH4 - Rp * nitrif, oO2);
+        PUT(O2, Rp * muP - (Rp - Rn) * tNH4 - Rp * nitrif, oO2);
     }
 }
 
@@ -337,11 +353,21 @@ extern "C" int obm_npd_param_index(const char* name) {
     return OBM_EENUM;
 }
 
+struct StepSpec {  // the fused tendency + substep launch; null: tendencies only
+    double* const* U;
+    double* const* Gm;
+    double dt, gamma, zeta;
+    int has_zeta, store_gn;
+};
 static int npd_launch(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which, const double* values,
                       const double* const* tracers, const double* PAR, double* const* G, int accumulate, void* stream,
-                      bool ensemble) {
-    OBM_REQUIRE(p != nullptr && tracers != nullptr && G != nullptr && PAR != nullptr, OBM_ENULL,
+                      bool ensemble, const StepSpec* step = nullptr) {
+    OBM_REQUIRE(p != nullptr && tracers != nullptr && (G != nullptr || step != nullptr) && PAR != nullptr, OBM_ENULL,
                 "obm_npd_tendencies: params / tracers / G / PAR is NULL");
+    OBM_REQUIRE(step == nullptr || (step->U != nullptr && step->Gm != nullptr), OBM_ENULL,
+                "obm_npd_tendencies_substep: tracers / G⁻ table is NULL");
+    OBM_REQUIRE(step == nullptr || G != nullptr || (!accumulate && !step->store_gn), OBM_ENULL,
+                "obm_npd_tendencies_substep: accumulate / store_Gn need the Gⁿ table");
     NpdArgs a;
     memset(&a, 0, sizeof(a));
     int rc = make_dims(grid, &a.d, false);
@@ -367,30 +393,41 @@ static int npd_launch(const obm_grid* grid, const obm_npd_params* p, int nvary, 
     a.p = *p;
     a.PAR = PAR;
     a.accumulate = accumulate ? 1 : 0;
+    if (step) {
+        a.step.on = 1;
+        a.step.has_zeta = step->has_zeta ? 1 : 0;
+        a.step.store_gn = step->store_gn ? 1 : 0;
+        a.step.dt = step->dt; a.step.gamma = step->gamma; a.step.zeta = step->zeta;
+    }
     int nd = 0, na = 0;
     for (int n = 0; n < nt; n++) {
         const double* c = tracers[n];
-        double* g = G[n];
+        double* g = G ? G[n] : nullptr;
+        double* u = step ? step->U[n] : nullptr;          // stepped only where BOTH the tracer and its G⁻ are given
+        double* m = step ? step->Gm[n] : nullptr;
+        if (step && (u == nullptr || (m == nullptr))) u = m = nullptr;
+        OBM_REQUIRE(!step || u == nullptr || u == c, OBM_ESIZE,
+                    "obm_npd_tendencies_substep: tracers[%d] and the stepped field differ", n);
         const bool read = !(roles[n] == R_DIC || roles[n] == R_ALK || roles[n] == R_O2);  // one-way coupled: never read
         OBM_REQUIRE(!read || c != nullptr, OBM_ENULL, "obm_npd_tendencies: tracers[%d] is NULL", n);
         switch (roles[n]) {
-            case R_NO3: a.NO3 = c; a.gNO3 = g; break;
-            case R_NH4: a.NH4 = c; a.gNH4 = g; break;
-            case R_FE: a.Fe = c; a.gFe = g; break;
-            case R_N: a.N = c; a.gN = g; break;
-            case R_P: a.P = c; a.gP = g; break;
-            case R_Z: a.Z = c; a.gZ = g; break;
+            case R_NO3: a.NO3 = c; a.gNO3 = g; a.uNO3 = u; a.mNO3 = m; break;
+            case R_NH4: a.NH4 = c; a.gNH4 = g; a.uNH4 = u; a.mNH4 = m; break;
+            case R_FE: a.Fe = c; a.gFe = g; a.uFe = u; a.mFe = m; break;
+            case R_N: a.N = c; a.gN = g; a.uN = u; a.mN = m; break;
+            case R_P: a.P = c; a.gP = g; a.uP = u; a.mP = m; break;
+            case R_Z: a.Z = c; a.gZ = g; a.uZ = u; a.mZ = m; break;
             case R_T: a.T = c; break;  // no biogeochemical tendency: zero(grid) NutrientsPlanktonDetritus.jl:88
-            case R_D: a.D = c; a.gD = g; break;
-            case R_SPOM: a.sPOM = c; a.gsPOM = g; break;
-            case R_BPOM: a.bPOM = c; a.gbPOM = g; break;
-            case R_DOM: a.DOM = c; a.gDOM = g; break;
-            case R_SPOC: a.sPOC = c; a.gsPOC = g; break;
-            case R_BPOC: a.bPOC = c; a.gbPOC = g; break;
-            case R_DOC: a.DOC = c; a.gDOC = g; break;
-            case R_DIC: a.gDIC[nd++] = g; break;
-            case R_ALK: a.gAlk[na++] = g; break;
-            case R_O2: a.gO2 = g; break;
+            case R_D: a.D = c; a.gD = g; a.uD = u; a.mD = m; break;
+            case R_SPOM: a.sPOM = c; a.gsPOM = g; a.usPOM = u; a.msPOM = m; break;
+            case R_BPOM: a.bPOM = c; a.gbPOM = g; a.ubPOM = u; a.mbPOM = m; break;
+            case R_DOM: a.DOM = c; a.gDOM = g; a.uDOM = u; a.mDOM = m; break;
+            case R_SPOC: a.sPOC = c; a.gsPOC = g; a.usPOC = u; a.msPOC = m; break;
+            case R_BPOC: a.bPOC = c; a.gbPOC = g; a.ubPOC = u; a.mbPOC = m; break;
+            case R_DOC: a.DOC = c; a.gDOC = g; a.uDOC = u; a.mDOC = m; break;
+            case R_DIC: a.gDIC[nd] = g; a.uDIC[nd] = u; a.mDIC[nd] = m; nd++; break;
+            case R_ALK: a.gAlk[na] = g; a.uAlk[na] = u; a.mAlk[na] = m; na++; break;
+            case R_O2: a.gO2 = g; a.uO2 = u; a.mO2 = m; break;
         }
     }
     a.nrep = nd;
@@ -410,4 +447,13 @@ extern "C" int obm_npd_tendencies_ensemble(const obm_grid* grid, const obm_npd_p
                                            const double* values, const double* const* tracers, const double* PAR,
                                            double* const* G, int accumulate, void* stream) {
     return npd_launch(grid, p, nvary, which, values, tracers, PAR, G, accumulate, stream, true);
+}
+
+// f-2: the tendencies and the tracer update in ONE launch (see include/obm_b200.h)
+extern "C" int obm_npd_tendencies_substep(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
+                                          const double* values, double* const* tracers, const double* PAR, double* const* G,
+                                          int accumulate, int store_Gn, double* const* Gm, double dt, double gamma, double zeta,
+                                          int has_zeta, void* stream) {
+    const StepSpec step{tracers, Gm, dt, gamma, zeta, has_zeta, store_Gn};
+    return npd_launch(grid, p, nvary, which, values, tracers, PAR, G, accumulate, stream, nvary > 0, &step);
 }

@@ -91,8 +91,15 @@ struct Ar {
         return exp(x);
 #elif OBM_PISCES_EXP == 1
         return EXACT ? exp(x) : exp_lean(x);
-#else
+#elif OBM_PISCES_EXP == 2
         return EXACT ? exp(x) : exp_horner(x);
+#else
+        // 3: the 64-entry table form of obm_common.cuh, branch-free.  Below −707 the argument is clamped (9e-308 for what is
+        // a subnormal or 0: every use adds the result to, or multiplies it with, ordinary numbers); above 709 the result is
+        // +Inf like the reference's — non-finite, so the cell is redone by the exact pass; NaN → NaN.
+        if (EXACT) return exp(x);
+        const double v = exp_table(x < -707.0 ? -707.0 : (x > 709.0 ? 709.0 : x));
+        return x > 709.0 ? __longlong_as_double(0x7ff0000000000000LL) : v;
 #endif
     }
 };

@@ -328,6 +328,42 @@ class NutrientsPlanktonDetritus:
                                              gptr, 1 if accumulate else 0, s)
         _lib.check(rc, "obm_npd_tendencies_ensemble")
 
+    def compute_tendencies_and_substep(self, grid: RectilinearGrid, tracers: dict, auxiliary_fields: dict, Gm: dict,
+                                       dt: float, gamma: float, zeta: Optional[float], G: Optional[dict] = None,
+                                       accumulate: bool = False, store_Gn: bool = False, stream: Optional[int] = None):
+        """f-2: `compute_tendencies!` + `rk3_substep!` + `cache_previous_tendencies!` (src/BoxModel/timesteppers.jl:30-93)
+        of every tracer in ONE launch — U += Δt(γG + ζG⁻), G⁻ ← G with G evaluated from the cell's tracers in the same
+        thread (plus the forcing found in G[name] when `accumulate`).  A tracer without an entry in `Gm` is not stepped.
+        Bit-identical to `compute_tendencies` followed by `obm_rk3_substep`."""
+        names = self.required_biogeochemical_tracers()
+        PAR = auxiliary_fields["PAR"]
+        require_cuda(PAR, *[tracers[n] for n in names])
+        lib = _lib.load()
+        cg = grid.c_grid()
+        p = self.c_params()
+        tptr = _lib.pointer_table([tracers[n].ptr for n in names])
+        mptr = _lib.pointer_table([Gm[n].ptr if (n in Gm and Gm[n] is not None and n != "T") else None for n in names])
+        gptr = None
+        if G is not None:
+            gptr = _lib.pointer_table([G[n].ptr if (n in G and G[n] is not None and n != "T") else None for n in names])
+        elif accumulate or store_Gn:
+            raise ValueError("accumulate / store_Gn need the Gⁿ fields")
+        s = stream if stream is not None else current_stream_ptr(grid.device)
+        nvary, which, values = 0, None, None
+        if self.parameter_ensemble is not None:
+            which, table, _ = self.parameter_ensemble
+            members = grid.Nx * grid.Ny
+            if table.shape[1] != members:
+                raise ValueError(f"parameter ensemble has {table.shape[1]} members, the grid has {members} columns")
+            if table.device != PAR.data.device:
+                table = table.to(PAR.data.device)
+                self.parameter_ensemble = (which, table, self.parameter_ensemble[2])
+            nvary, values = len(which), table.data_ptr()
+        rc = lib.obm_npd_tendencies_substep(C.byref(cg), C.byref(p), nvary, which, values, tptr, PAR.ptr, gptr,
+                                            1 if accumulate else 0, 1 if store_Gn else 0, mptr, float(dt), float(gamma),
+                                            0.0 if zeta is None else float(zeta), int(zeta is not None), s)
+        _lib.check(rc, "obm_npd_tendencies_substep")
+
     def __call__(self, name: str, *, PAR, device="cuda", **tracers):
         """The per-tracer form `bgc(Val(name), x, y, z, t, tracers..., PAR)` of the plugin API
         (docs/src/model_implementation.md:34-75; the built-in models' discrete form

@@ -24,7 +24,7 @@ def PAR_func(t):
     return PAR0 * math.exp(0.2 * -10)
 
 
-def build(n, sweep):
+def build(n, sweep, fused=False):
     grid = ob.BoxModelGrid(n, device="cuda")
     PAR = ob.CenterField(grid, "PAR")
     kw = {}
@@ -37,7 +37,7 @@ def build(n, sweep):
             "phytoplankton_mortality_rate": 0.0761 / day * rng.uniform(0.7, 1.3, n),
             "phytoplankton_solid_waste_fraction": 0.1327 * rng.uniform(0.7, 1.3, n)}
     bgc = ob.NPZD(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR), **kw)
-    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func})  # T stays 0, as in the benchmark
+    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func}, fused_step=fused)  # T stays 0, as in the benchmark
     model.set(N=10.0, P=0.1, Z=0.01)
     return model
 
@@ -45,8 +45,10 @@ def build(n, sweep):
 def main():
     steps, rows = 1000, []
     build(1, False).run(20 * minutes, 20, graph=True)  # module loads, allocator
-    for n, sweep in ((1, False), (8, True), (4096, True), (262144, True), (1048576, True)):
-        model = build(n, sweep)
+    build(1, False, True).run(20 * minutes, 20, graph=True)
+    for n, sweep, fused in ((1, False, False), (1, False, True), (8, True, False), (8, True, True), (4096, True, False), (4096, True, True),
+                            (262144, True, False), (262144, True, True), (1048576, True, False), (1048576, True, True)):
+        model = build(n, sweep, fused)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = model.run(20 * minutes, steps, graph=True, output_every=20)
@@ -54,7 +56,7 @@ def main():
         wall = time.perf_counter() - t0
         replay = model.replay_events[0].elapsed_time(model.replay_events[1]) * 1e-3  # the 1000 replays alone, on the device
         P = out["P"]
-        rows.append({"boxes": n, "parameter_sweep": sweep, "steps": steps, "run_wall_s": round(wall, 4),
+        rows.append({"boxes": n, "parameter_sweep": sweep, "fused_tendency_and_substep": fused, "steps": steps, "run_wall_s": round(wall, 4),
                      "replays_s": round(replay, 4), "us_per_rk3_stage": round(replay / steps / 3 * 1e6, 2),
                      "box_steps_per_s": round(n * steps / wall, 1),
                      "reference_one_box_s": 0.0235, "speedup_vs_reference_sequential": round(0.0235 * n / wall, 1),

@@ -33,7 +33,7 @@ def tendency_parity(got: np.ndarray, want: np.ndarray, S: np.ndarray, offset: fl
         err = |got − want| / max(|want|, S),   S = Σ |additive terms| of THAT tendency in that cell
 
     (S from the oracle's `*_tendency_scales`; in accumulate mode the pre-existing Gⁿ value `offset` is one more term).
-    Also the PURE relative error |got − want| / |want| over the cells where the tendency is not a near-total
+    Also the PURE relative error |got − want| / |want − offset| over the cells where the tendency is not a near-total
     cancellation of its terms (|want − offset| ≥ 1e-3·S): (max, 99.9th percentile).  NaN positions must match exactly.
     Returns (err_max, rel_max, rel_p999)."""
     assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN patterns differ"
@@ -46,9 +46,11 @@ def tendency_parity(got: np.ndarray, want: np.ndarray, S: np.ndarray, offset: fl
     d = np.abs(g - w)
     den = np.maximum(np.abs(w), s)
     err = float(np.max(d / np.where(den == 0, 1.0, den)))
-    big = (np.abs(w - offset) >= 1e-3 * s) & (np.abs(w) > 0)
+    # accumulate mode: relative to the tendency itself, |want − offset| — offset + tendency can land near zero (a
+    # cancellation between the pre-existing Gⁿ and what was added, nothing to do with the kernel's arithmetic)
+    big = (np.abs(w - offset) >= 1e-3 * s) & (np.abs(w - offset) > 0)
     if big.any():
-        rel = d[big] / np.abs(w[big])
+        rel = d[big] / np.abs(w[big] - offset)
         return err, float(rel.max()), float(np.quantile(rel, 0.999))
     return err, 0.0, 0.0
 

@@ -188,3 +188,91 @@ def test_reference_simulation_with_speedy_output(cuda, tmp_path):
     assert results["t"][0] == 0.0 and math.isclose(results["t"][-1], 1000 * 20 * minutes, rel_tol=1e-12)
     assert all(r[0].tolist() != r[-1].tolist() for r in results.values())
     assert np.array_equal(ob.load_output(fast_output, "P"), results["P"])
+
+
+# ---- f-2: tendencies + tracer update in one launch (obm_npd_tendencies_substep) ---------------------------------------
+@pytest.mark.parametrize("timestepper,graph", [("RungeKutta3", False), ("Euler", False), ("RungeKutta3", True)])
+def test_fused_stage_is_bit_identical_to_the_three_launch_path(cuda, timestepper, graph):
+    """`BoxModel(fused_step=True)`: compute_tendencies! + rk3_substep! + cache_previous_tendencies! (timesteppers.jl:30-93)
+    as ONE launch per stage.  LOBSTER + carbonates + O₂ with a forcing and two prescribed series, eager and as a replayed
+    CUDA graph: every tracer and every G⁻ equal those of the three-launch path bit for bit."""
+    n, steps = 1500, 12
+    rng = np.random.default_rng(14)
+    ics = {k: torch.from_numpy(v * rng.uniform(0.5, 1.5, n)) for k, v in DEFAULTS.items()}
+    ics.update(sPOM=0.2, bPOM=0.1, DOM=0.3, DIC=2200.0, Alk=2400.0, **{"O₂": 240.0})
+    T_fn = lambda t: 12.0 + 3.0 * math.sin(2 * math.pi * t / day)  # noqa: E731
+    src = lambda t: 1e-7 * (1 + math.cos(2 * math.pi * t / day))  # noqa: E731
+
+    def build(fused):
+        grid = ob.BoxModelGrid(n, device=cuda)
+        PAR = ob.CenterField(grid, "PAR")
+        bgc = ob.LOBSTER(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR),
+                         carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen())
+        m = ob.BoxModel(biogeochemistry=bgc, grid=grid, timestepper=timestepper, forcing={"NO₃": src},
+                        prescribed_tracers={"PAR": PAR_fn, "T": T_fn}, fused_step=fused)
+        m.set(**ics)
+        return m
+
+    three, one = build(False), build(True)
+    three.run(20 * minutes, steps, graph=graph)
+    one.run(20 * minutes, steps, graph=graph)
+    torch.cuda.synchronize()
+    for name in three.prognostic:
+        assert torch.equal(three.fields[name].data, one.fields[name].data), name
+        assert torch.equal(three.Gm[name].data, one.Gm[name].data), name
+    assert not torch.equal(one.fields["P"].interior.reshape(-1), ics["P"].to(cuda))
+    assert one.clock.iteration == steps and abs(one.clock.time - three.clock.time) < 1e-9
+
+
+def test_fused_stage_against_the_oracle_and_argument_errors(cuda, oracle):
+    """One fused launch on a 3-D grid against the oracle's tendencies followed by the oracle's substep (bit-exact update
+    arithmetic ⇒ the tracers differ only through the tendencies' 1e-12); Gⁿ stored on request; T and tracers without a G⁻
+    are left alone; refused: a stepped field that is not the tracer, accumulate without Gⁿ."""
+    import ctypes as C
+    from oceanbiome_b200 import _lib, synthetic
+    grid = ob.RectilinearGrid(size=(40, 3, 5), extent=(1, 1, 50), device=cuda)
+    og = oracle.Grid.like(grid)
+    bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen()).underlying_biogeochemistry
+    names = list(bgc.required_biogeochemical_tracers())
+    rng = np.random.default_rng(21)
+    hU = {m: rng.uniform(0.05, 2.0, og.parent_shape) for m in names}
+    hGm = {m: rng.normal(size=og.parent_shape) * 1e-6 for m in names}
+    hPAR = rng.uniform(0.0, 80.0, og.parent_shape)
+    mk = lambda h: ob.CenterField(grid).set(og.interior(h))  # noqa: E731
+    U, Gm, Gn = {m: mk(hU[m]) for m in names}, {m: mk(hGm[m]) for m in names}, {m: ob.CenterField(grid, fill=7.0) for m in names}
+    for m in names:
+        U[m].data.copy_(torch.from_numpy(hU[m])); Gm[m].data.copy_(torch.from_numpy(hGm[m]))
+    PAR = ob.CenterField(grid); PAR.data.copy_(torch.from_numpy(hPAR))
+    skip = "sPOM"                                       # no G⁻ given: not stepped
+    dt, gamma, zeta = 900.0, 5 / 12, -17 / 60
+    bgc.compute_tendencies_and_substep(grid, U, {"PAR": PAR}, {m: f for m, f in Gm.items() if m != skip}, dt, gamma, zeta,
+                                       G=Gn, store_Gn=True)
+    torch.cuda.synchronize()
+    params = bgc.c_params()
+    want_G = oracle.npd_tendencies(og, params, [hU[m] for m in names], hPAR)
+    wU, wGm = [hU[m].copy() for m in names], [hGm[m].copy() for m in names]
+    oracle.rk3_substep(og, wU, want_G, wGm, dt, gamma, zeta, cache_previous=True)
+    for q, m in enumerate(names):
+        gotU, gotGm, gotGn = (og.interior(host(f)) for f in (U[m], Gm[m], Gn[m]))
+        if m == skip:
+            assert np.array_equal(gotU, og.interior(hU[m])) and np.array_equal(gotGm, og.interior(hGm[m]))
+        else:
+            scale = np.maximum(np.abs(og.interior(wU[q])), dt * np.abs(og.interior(want_G[q])))
+            assert np.max(np.abs(gotU - og.interior(wU[q])) / scale) <= 10 * RTOL_TENDENCY, m
+            assert np.array_equal(gotGm, gotGn), m       # G⁻ ← Gⁿ, the value just computed
+        g = og.interior(want_G[q])
+        assert np.max(np.abs(gotGn - g)) <= 10 * RTOL_TENDENCY * max(np.max(np.abs(g)), 1e-30), m
+        full = host(U[m]).copy(); og.interior(full)[...] = og.interior(hU[m])
+        assert np.array_equal(full, hU[m]), m            # halos untouched
+    # argument errors
+    lib = _lib.load()
+    cg = grid.c_grid()
+    tab = lambda fs: _lib.pointer_table([f.ptr for f in fs])  # noqa: E731
+    order = [U[m] for m in names]
+    other = [ob.CenterField(grid) for _ in names]
+    p = bgc.c_params()
+    call = lambda t, G, acc, store, m: lib.obm_npd_tendencies_substep(  # noqa: E731
+        C.byref(cg), C.byref(p), 0, None, None, t, PAR.ptr, G, acc, store, m, dt, gamma, zeta, 1, None)
+    assert call(tab(order), None, 1, 0, tab([Gm[m] for m in names])) == -1     # accumulate needs Gⁿ
+    assert call(tab(order), None, 0, 0, None) == -1                            # no G⁻ table
+    assert call(None, None, 0, 0, tab(other)) == -1
