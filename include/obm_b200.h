@@ -428,7 +428,7 @@ int obm_zero_negative_tracers(int64_t n_parent, int ntracers, double* const* tra
  * and the stepping order / flux operator live in Oceananigans (not in the tree) — see DESIGN.md.
  * ------------------------------------------------------------------------------------ */
 enum { OBM_SED_INSTANT_REMINERALISATION = 0, OBM_SED_SIMPLE_MULTI_G = 1 };
-enum { OBM_ADV_UPWIND1 = 0, OBM_ADV_CENTERED2 = 1, OBM_ADV_UPWIND3 = 2 }; /* face reconstruction of advective_tracer_flux_z (UPWIND3: obm_sinking_tendencies only) */
+enum { OBM_ADV_UPWIND1 = 0, OBM_ADV_CENTERED2 = 1, OBM_ADV_UPWIND3 = 2, OBM_ADV_WENO5 = 3 }; /* face reconstruction of advective_tracer_flux_z (UPWIND3, WENO5: obm_sinking_tendencies; the sediment's bottom face is first-order upwind for every upwind-biased scheme) */
 enum { OBM_TS_AB2 = 0, OBM_TS_RK3 = 1 };             /* Sediments.jl:48: timestepper                   */
 #define OBM_SED_MAX_SINKING 4
 #define OBM_SED_MAX_POOLS 6
@@ -614,8 +614,10 @@ double obm_kelp_seasonal_limitation(const obm_sugar_kelp_params* p, double t);
  * one launch.  w_faces[t]: the z-face field `biogeochemical_drift_velocity(bgc, Val(c)).w`
  * (`setup_velocity_fields` src/Utils/sinking_velocity_fields.jl:10-35, `DepthDependantSinkingSpeed`
  * PISCES/common.jl:39-55; face k at plane k, Nz + 1 faces).  Flux form  F_k = w_k·c̃_k,
- * G_k −= (F_{k+1} − F_k)/Δz_k  with c̃ by `advection` (OBM_ADV_UPWIND1 | CENTERED2 | UPWIND3; UPWIND3
- * falls back to first order where its stencil would leave the interior).  This is the
+ * G_k −= (F_{k+1} − F_k)/Δz_k  with c̃ by `advection` (OBM_ADV_UPWIND1 | CENTERED2 | UPWIND3 | WENO5;
+ * UPWIND3 falls back to first order, WENO5 — fifth-order WENO with the Z weights of Borges et al. 2008,
+ * uniform-grid coefficients, ε = 1e-8 — to WENO3 and then to first order where the stencil would leave
+ * the interior).  This is the
  * `div_Uc(…, total_velocities, c)` term of Oceananigans' tracer tendency for models without a
  * resolved vertical velocity (column / box ensembles, the reference's sediment tests); the
  * bottom-face flux is the one obm_sediment_update_state reads.  Tracer z-halos are read as found.

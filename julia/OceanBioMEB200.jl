@@ -67,7 +67,11 @@ sinking_nitrogen(b::SimpleMultiG) = b.sinking_nitrogen; sinking_nitrogen(b::Inst
 sinking_carbon(b::SimpleMultiG) = has_carbon(b) ? b.sinking_carbon : (); sinking_carbon(::InstantRemineralisation) = ()
 timestepper_kind(ts) = Int32(ts isa Oceananigans.TimeSteppers.RungeKutta3TimeStepper)                       # OBM_TS_AB2 = 0, OBM_TS_RK3 = 1
 advection_kind(::Oceananigans.Advection.Centered) = Int32(1)                                                 # OBM_ADV_CENTERED2
-advection_kind(_) = Int32(0)   # OBM_ADV_UPWIND1: the sediment's bottom-face flux for every upwind scheme (DESIGN.md §4: WENO not restated)
+advection_kind(_) = Int32(0)   # OBM_ADV_UPWIND1: the sediment's bottom-face flux is first order for every upwind-biased scheme (WENO included)
+# the interior faces of obm_sinking_tendencies (column / box models): UpwindBiased(order = 3) → 2, WENO(order = 5) → 3
+sinking_advection_kind(a::Oceananigans.Advection.UpwindBiased) = Int32(a isa Oceananigans.Advection.UpwindBiased{1} ? 0 : 2)
+sinking_advection_kind(::Oceananigans.Advection.WENO) = Int32(3)
+sinking_advection_kind(a) = advection_kind(a)
 
 include("obm_fill.jl")      # ObmNpdParams(bgc), ObmPiscesParams(bgc, clock), ObmTwobandParams(par), ObmMultibandParams(par),
                             # ObmSedimentParams(sed, advection)

@@ -163,7 +163,7 @@ class obm_pisces_fields(C.Structure):
 OBM_PISCES_NTRACERS = 26
 
 SED_INSTANT_REMINERALISATION, SED_SIMPLE_MULTI_G = 0, 1
-ADV_UPWIND1, ADV_CENTERED2, ADV_UPWIND3 = 0, 1, 2
+ADV_UPWIND1, ADV_CENTERED2, ADV_UPWIND3, ADV_WENO5 = 0, 1, 2, 3
 OBM_MAX_SINKING_TRACERS = 8
 TS_AB2, TS_RK3 = 0, 1
 OBM_SED_MAX_SINKING, OBM_SED_MAX_POOLS, OBM_SED_MAX_COUPLED = 4, 6, 4

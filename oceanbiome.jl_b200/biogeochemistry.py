@@ -158,7 +158,8 @@ class BiogeochemicalModel:
 
     RK3 = ((8 / 15, 0.0), (5 / 12, -17 / 60), (3 / 4, -5 / 12))  # (γⁿ, ζⁿ) of Oceananigans' RK3
 
-    ADVECTION = {"UpwindBiased1": _lib.ADV_UPWIND1, "Centered2": _lib.ADV_CENTERED2, "UpwindBiased3": _lib.ADV_UPWIND3}
+    ADVECTION = {"UpwindBiased1": _lib.ADV_UPWIND1, "Centered2": _lib.ADV_CENTERED2, "UpwindBiased3": _lib.ADV_UPWIND3,
+                 "WENO5": _lib.ADV_WENO5}  # WENO(order = 5), what test/test_sediments.jl:37-80 builds its model with
 
     def __init__(self, grid: RectilinearGrid, biogeochemistry, extra_tracers=(), timestepper="RungeKutta3",
                  boundary_conditions=None, sinking_advection: Optional[str] = None):

@@ -12,7 +12,7 @@
 // (sediments.cu: same face value) and 0 at the closed top face (w = 0 there).
 // Face reconstructions (Oceananigans' uniform-grid coefficients): UpwindBiased(order = 1), Centered(order = 2),
 // UpwindBiased(order = 3) — the latter drops to order 1 where its stencil would leave the interior
-// (bounded-direction buffer scheme).  Tracer halos below / above the column are read as found for orders 1, 2.
+// (bounded-direction buffer scheme) — and WENO(order = 5) with the Z weights (→ WENO3 → order 1 towards the boundaries).  Tracer halos below / above the column are read as found for orders 1, 2.
 // HBM-bound: per tracer per cell 8 B (c; the z-neighbours come from L2) + 8 B (w) + 16 B (Gⁿ read-modify-write).
 #include "obm_common.cuh"
 
@@ -26,10 +26,46 @@ struct SinkArgs {
     double* G[OBM_MAX_SINKING_TRACERS];
 };
 
+// WENO reconstructions of the face value from the UPWIND side: u0 is the upwind cell next to the face, um1, um2 the two
+// behind it, up1, up2 the two ahead (downwind).  Candidate polynomials and smoothness indicators of Jiang & Shu (1996),
+// non-linear weights of WENO-Z (Borges et al. 2008): α_k = d_k (1 + (τ / (β_k + ε))²), τ₅ = |β₀ − β₂|, τ₃ = |β₀ − β₁|.
+__device__ __forceinline__ double weno5_face(double um2, double um1, double u0, double up1, double up2) {
+    const double eps = 1e-8;
+    const double p0 = (2 * um2 - 7 * um1 + 11 * u0) / 6, p1 = (-um1 + 5 * u0 + 2 * up1) / 6, p2 = (2 * u0 + 5 * up1 - up2) / 6;
+    const double a0 = um2 - 2 * um1 + u0, b0 = um2 - 4 * um1 + 3 * u0;
+    const double a1 = um1 - 2 * u0 + up1, b1 = um1 - up1;
+    const double a2 = u0 - 2 * up1 + up2, b2 = 3 * u0 - 4 * up1 + up2;
+    const double be0 = 13.0 / 12 * (a0 * a0) + 0.25 * (b0 * b0);
+    const double be1 = 13.0 / 12 * (a1 * a1) + 0.25 * (b1 * b1);
+    const double be2 = 13.0 / 12 * (a2 * a2) + 0.25 * (b2 * b2);
+    const double tau = fabs(be0 - be2);
+    const double r0 = tau / (be0 + eps), r1 = tau / (be1 + eps), r2 = tau / (be2 + eps);
+    const double w0 = 0.1 * (1 + r0 * r0), w1 = 0.6 * (1 + r1 * r1), w2 = 0.3 * (1 + r2 * r2);
+    return (w0 * p0 + w1 * p1 + w2 * p2) / (w0 + w1 + w2);
+}
+__device__ __forceinline__ double weno3_face(double um1, double u0, double up1) {
+    const double eps = 1e-8;
+    const double p0 = (-um1 + 3 * u0) / 2, p1 = (u0 + up1) / 2;
+    const double be0 = (u0 - um1) * (u0 - um1), be1 = (up1 - u0) * (up1 - u0);
+    const double tau = fabs(be0 - be1);
+    const double r0 = tau / (be0 + eps), r1 = tau / (be1 + eps);
+    const double w0 = (1.0 / 3) * (1 + r0 * r0), w1 = (2.0 / 3) * (1 + r1 * r1);
+    return (w0 * p0 + w1 * p1) / (w0 + w1);
+}
+
 // value of c at face k (0 … Nz) seen by a flow of vertical velocity w; `col` points at cell k = 0 of the column
 __device__ __forceinline__ double face_value(int scheme, const double* col, long long sz, int k, int Nz, double w) {
     const double below = col[sz * (k - 1)], above = col[sz * k];
     if (scheme == OBM_ADV_CENTERED2) return (below + above) / 2;
+    if (scheme == OBM_ADV_WENO5) {
+        // s = +1: the flow comes from below (upwind cell k − 1), s = −1 from above (upwind cell k); m-th cell behind the
+        // upwind one: u − s·m, ahead of it: u + s·m.  Order drops where the stencil would leave the interior.
+        const int s = w > 0 ? 1 : -1, u = w > 0 ? k - 1 : k;
+        const int lo5 = u - 2 * s < u + 2 * s ? u - 2 * s : u + 2 * s, hi5 = u - 2 * s < u + 2 * s ? u + 2 * s : u - 2 * s;
+        if (lo5 >= 0 && hi5 <= Nz - 1)
+            return weno5_face(col[sz * (u - 2 * s)], col[sz * (u - s)], col[sz * u], col[sz * (u + s)], col[sz * (u + 2 * s)]);
+        if (u - 1 >= 0 && u + 1 <= Nz - 1) return weno3_face(col[sz * (u - s)], col[sz * u], col[sz * (u + s)]);
+    }
     if (scheme == OBM_ADV_UPWIND3) {
         if (w > 0 && k - 2 >= 0 && k <= Nz - 1) return (-col[sz * (k - 2)] + 5 * below + 2 * above) / 6;
         if (w < 0 && k - 1 >= 0 && k + 1 <= Nz - 1) return (2 * below + 5 * above - col[sz * (k + 1)]) / 6;
@@ -65,7 +101,7 @@ extern "C" int obm_sinking_tendencies(const obm_grid* grid, int ntracers, const 
                 "obm_sinking_tendencies: ntracers = %d outside [0, %d]", ntracers, OBM_MAX_SINKING_TRACERS);
     if (ntracers == 0) return 0;
     OBM_REQUIRE(tracers && w_faces && G, OBM_ENULL, "obm_sinking_tendencies: tracers / w_faces / G is NULL");
-    OBM_REQUIRE(advection == OBM_ADV_UPWIND1 || advection == OBM_ADV_CENTERED2 || advection == OBM_ADV_UPWIND3, OBM_EENUM,
+    OBM_REQUIRE(advection == OBM_ADV_UPWIND1 || advection == OBM_ADV_CENTERED2 || advection == OBM_ADV_UPWIND3 || advection == OBM_ADV_WENO5, OBM_EENUM,
                 "obm_sinking_tendencies: unknown advection scheme %d", advection);
     SinkArgs a;
     int rc = make_dims(grid, &a.d, true);

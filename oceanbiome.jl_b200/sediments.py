@@ -111,7 +111,9 @@ class BiogeochemicalSediment:
     # -- C structs -----------------------------------------------------------------------------------------
     def c_params(self) -> _lib.obm_sediment_params:
         b, p = self.biogeochemistry, _lib.obm_sediment_params()
-        p.advection = _lib.ADV_UPWIND1 if self.advection == "UpwindBiased1" else _lib.ADV_CENTERED2
+        # the bottom face: every upwind-biased scheme (UpwindBiased 1 / 3, WENO5) is first-order there — its higher-order
+        # stencils would leave the interior (sinking.cu::face_value) — so only Centered2 differs
+        p.advection = _lib.ADV_CENTERED2 if self.advection == "Centered2" else _lib.ADV_UPWIND1
         p.timestepper = _lib.TS_AB2 if self.timestepper == "QuasiAdamsBashforth2" else _lib.TS_RK3
         if isinstance(b, InstantRemineralisation):
             p.model = _lib.SED_INSTANT_REMINERALISATION
