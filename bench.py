@@ -860,7 +860,31 @@ def main():
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k,
                "cells_per_gpu": we.cells, "copy_engine": args.copy_engine, "numa_bound": bool(hs.numa_bound),
                "pcie_GBs_each_direction": max(hs.h2d_bytes, hs.d2h_bytes) * k / (ems * 1e-3) / 1e9}
-        # the leg's own roofline, measured the way the leg runs: EVERY rank copies in both directions at the same time
+        # the leg's ceiling on THIS box, measured with the leg's own pinned buffers and copy pattern on every rank at once:
+        # the same slab copies without the kernels between them, then each direction alone (profiles/r04_e2e_probe_*:
+        # with 8 ranks the two directions do not overlap on the host side — copies-only ≈ H2D-only + D2H-only — and the
+        # ranks behind one host bridge share what it delivers, whatever the copy pattern, slab count or copy engine)
+        if we.kind != "carbon":
+            def copies(**kw):
+                hs.stage.step(kernels=False, **kw)
+                barrier()
+                a.record()
+                for _ in range(2):
+                    hs.stage.step(kernels=False, **kw)
+                b.record()
+                barrier()
+                return max_over_ranks(a.elapsed_time(b)) / 2
+            c_both, c_in, c_out = copies(), copies(d2h=False), copies(h2d=False)
+            e2e["ceiling"] = {
+                "how": "the stage's own slab copies of its own pinned buffers with no kernels between them, all ranks at once "
+                       "(max over ranks), and each direction alone",
+                "copies_only_ms": c_both, "h2d_only_ms": c_in, "d2h_only_ms": c_out, "stage_ms": ems / k,
+                "value": we.cells * world / (c_both * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+                "frac": c_both / (ems / k),
+                "directions_overlap": (c_in + c_out) / c_both,  # 2 = full duplex, 1 = the directions serialise
+                "GBs_h2d_alone_per_rank": hs.h2d_bytes / (c_in * 1e-3) / 1e9,
+                "GBs_d2h_alone_per_rank": hs.d2h_bytes / (c_out * 1e-3) / 1e9}
+        # and the link's own peak: EVERY rank copies one large buffer in both directions at the same time
         del hs
         barrier()
         peak_c = pcie_peak_gbs(device, reps=8 if world > 1 else 3, barrier=barrier if world > 1 else None)
@@ -892,6 +916,12 @@ def main():
             e2e["limiter"] = ("PCIe link of the one GPU" if world == 1 else
                               f"shared host side: {world} ranks copying at once get {np.mean(peaks):.1f} GB/s per direction each "
                               f"({world * np.mean(peaks):.0f} GB/s per direction in aggregate) against {solo:.1f} GB/s for one rank alone")
+            c = e2e.get("ceiling")
+            if c and world > 1:
+                e2e["limiter"] += (f"; with the stage's own buffers the slowest rank moves {c['GBs_h2d_alone_per_rank']:.1f} GB/s in alone, "
+                                   f"{c['GBs_d2h_alone_per_rank']:.1f} GB/s out alone, and both together take {c['copies_only_ms']:.0f} ms against "
+                                   f"{c['h2d_only_ms']:.0f} + {c['d2h_only_ms']:.0f} ms (overlap factor {c['directions_overlap']:.2f} of 2): "
+                                   f"the stage runs at {c['frac']:.2f} of that copies-only ceiling")
         if note:
             e2e["note"] = note
         we = None  # (it may be `w` itself: drop the reference so that the weak leg below can free the slab)

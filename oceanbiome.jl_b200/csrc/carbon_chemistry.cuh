@@ -349,6 +349,105 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
     Hdf = H * df;
 }
 
+// ---- FP32 pre-solve (OBM_CC_F32PRE) ----------------------------------------------------------------------------------
+// The Newton iteration only has to END in FP64: its early steps are a search.  With no stored [H⁺] the search runs in
+// FP32 — the carbonate-alkalinity quadratic with borate at the reference's initial guess, then THREE Newton steps in
+// x = ln[H⁺] on the same residual, written with the O(1) speciation fractions (a₀, a₁, a₂ of the carbonate system,
+// r = H / (K + H) of every one-proton pair: nothing leaves the FP32 range, no cubes of 10⁻¹⁴) and with MUFU
+// reciprocals / ex2 — ≈ 55 FP32-pipe instructions per step against ≈ 125 issue slots (80 on the FP64 pipe, 7 MUFU.RCP64H
+// + moves, constant loads) of an FP64 step.  FP32 rounding of the residual (≈ 6·10⁻⁸ · Alk / |∂ₓ residual|) leaves the
+// iterate ≈ 3·10⁻⁶ from the root in ln H; ONE FP64 Newton step from there has the error C·Δx², C = g″ / (2 g′), and C —
+// needed to three digits only — comes out of the last FP32 step for a dozen more FP32 instructions.  After the
+// correction what is left is O(Δx³) ≲ 10⁻¹⁵.  The FP64 step doubles as the check: a lane whose |Δx| is not below 10⁻⁵
+// (a state outside sea-water conditions, an FP32 overflow) keeps its warp in the ordinary FP64 loop, which starts from
+// wherever the pre-solve ended (or from the reference's initial guess if that is not a plausible [H⁺]).
+// Only the starting point differs from the reference; the root is the same (tests: |ΔpH| ≤ 1e-10 stated).
+#ifndef OBM_CC_F32PRE
+#define OBM_CC_F32PRE 1
+#endif
+#ifndef OBM_CC_TOL0
+#define OBM_CC_TOL0 1e-5  // exit threshold of the one FP64 step after the pre-solve
+#endif
+__device__ __forceinline__ float rcp_f32(float x) {
+#ifdef __CUDACC__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+__device__ __forceinline__ float exp_f32(float x) {
+#ifdef __CUDACC__
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f));
+    return r;
+#else
+    return expf(x);
+#endif
+}
+__device__ __forceinline__ float sqrt_f32(float x) {
+#ifdef __CUDACC__
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return sqrtf(x);
+#endif
+}
+// → starting [H⁺] for the FP64 iteration; C2 = g″ / (2 g′) at (almost) the root, in the variable ln H
+__device__ __forceinline__ double presolve_f32(const Constants& c, const Totals& t, bool need_silicate, double H_init, double& C2,
+                                               bool& converged_range) {
+    const float K1 = (float)c.K1, K2 = (float)c.K2, KB = (float)c.KB, KW = (float)c.KW, KSsd = (float)c.KSsd, KF = (float)c.KF;
+    const float KSi = (float)c.KSi, isd = (float)c.isd;
+    const float DIC = (float)t.DIC, Alk = (float)t.Alk, BT = (float)t.boron, ST = (float)t.sulfate, FT = (float)t.fluoride;
+    const float SiT = (float)t.silicate;
+    const float Hi = (float)H_init;
+    const float K1K2 = K1 * K2;
+    float H;
+    {
+        const float AC = Alk - BT * KB * rcp_f32(KB + Hi);
+        const float b = K1 * (AC - DIC);
+        const float disc = b * b - 4.0f * AC * K1K2 * (AC - 2.0f * DIC);
+        H = (sqrt_f32(disc) - b) * rcp_f32(2.0f * AC);
+        H = (H > 1e-12f && H < 1e-3f) ? H : Hi;  // NaN (disc < 0, A_C ≤ 0 …) fails both comparisons
+    }
+    float c2 = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+        const float icd = rcp_f32((H + K1) * H + K1K2);
+        const float a0 = H * H * icd, a1 = K1 * H * icd, a2 = K1K2 * icd;
+        const float m = 2.0f * a0 + a1;            // mean number of protons on the carbonate species
+        const float rB = H * rcp_f32(KB + H), rS = H * rcp_f32(H + KSsd), rF = H * rcp_f32(H + KF);
+        const float oh = KW * rcp_f32(H), hf = H * isd;
+        const float qB = rB * (1.0f - rB), qS = rS * (1.0f - rS), qF = rF * (1.0f - rF);
+        float g = DIC * (a1 + 2.0f * a2) + BT * (1.0f - rB) + (oh - hf) - ST * rS - FT * rF - Alk;
+        float gp = DIC * (a1 * (1.0f - m) - 2.0f * a2 * m) - BT * qB - (oh + hf) - ST * qS - FT * qF;
+        float rSi = 0.0f, qSi = 0.0f;
+        if (need_silicate) {
+            rSi = H * rcp_f32(KSi + H);
+            qSi = rSi * (1.0f - rSi);
+            g += SiT * (1.0f - rSi);
+            gp -= SiT * qSi;
+        }
+        const float igp = rcp_f32(gp);
+        if (n == 2) {  // g″ at the last FP32 iterate (≲ 10⁻³ from the root: C to three digits)
+            const float v = 2.0f * a0 * (2.0f - m) + a1 * (1.0f - m);  // ∂ₓ m
+            float gpp = DIC * (a1 * (1.0f - m) * (1.0f - m) + 2.0f * a2 * m * m - (a1 + 2.0f * a2) * v) - BT * qB * (1.0f - 2.0f * rB)
+                        + (oh - hf) - ST * qS * (1.0f - 2.0f * rS) - FT * qF * (1.0f - 2.0f * rF);
+            if (need_silicate) gpp -= SiT * qSi * (1.0f - 2.0f * rSi);
+            c2 = 0.5f * gpp * igp;
+        }
+        float dx = g * igp;
+        dx = dx > -2.302585f ? (dx < 2.302585f ? dx : 2.302585f) : -2.302585f;  // NaN → −ln 10: the FP64 loop sorts it out
+        H *= exp_f32(-dx);
+    }
+    const bool ok = H > 1e-13f && H < 1e-2f && fabsf(c2) < 8.0f;
+    C2 = ok ? (double)c2 : 0.0;
+    converged_range = ok;
+    return ok ? (double)H : H_init;
+}
+
 // solve_for_H (carbon_chemistry.jl:217-218) → [H⁺]: Newton on x = ln[H⁺] carried multiplicatively (H ← H·e^(−Δx)),
 // step clamped to one pH unit, at most `iterations` steps from H0.
 // OBM_CC_TOL: the warp-uniform exit threshold on |Δx|.  Newton converges quadratically here with a measured constant
@@ -376,7 +475,7 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 #define OBM_CC_EXTRAP 1
 #endif
 __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, bool need_phosphate, bool need_silicate,
-                                          double H0, int iterations) {
+                                          double H0, int iterations, bool presolved = false, double C2 = 0.0) {
     constexpr double LN10 = 2.302585092994045684;
     double H = H0;
     double dx = 0.0, dx_prev = 0.0;
@@ -402,7 +501,13 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         // Warp-uniform early exit (no divergence): once every lane's step is below the threshold the quadratic
         // convergence of Newton puts this iterate within ~1e-12 of the root; NaN lanes count as converged (they stay NaN).
         // (a FIRST step has no predecessor to extrapolate with: it ends the iteration only below 10⁻⁷ — a warm start)
-        if (__all_sync(mask, !(adx >= (n == 0 ? KD(1e-7) : KD(OBM_CC_TOL))))) break;
+        // (after the FP32 pre-solve the first step is the LAST one when it is below 10⁻⁵: its error C·Δx² is removed with
+        // the C the pre-solve delivered — see presolve_f32)
+        const double tol0 = presolved ? KD(OBM_CC_TOL0) : KD(1e-7);
+        if (__all_sync(mask, !(adx >= (n == 0 ? tol0 : KD(OBM_CC_TOL))))) {
+            if (n == 0) H = fma(-H, C2 * (dx * dx), H);  // C2 = 0 without a pre-solve
+            break;
+        }
     }
 #if OBM_CC_EXTRAP
     {
@@ -515,8 +620,17 @@ __device__ __forceinline__ double finish(Prepared& q, bool with_KSP, int output_
     } else {
         // warm start: [H⁺] kept from the previous call on this cell, if it is a plausible value (pH 2 … 13)
         double H0 = H_io ? *H_io : 0.0;
-        if (!(H0 > KD(1e-13) && H0 < KD(1e-2))) H0 = initial_H(c, t, has_sil, H_init);
-        H = solve_H(c, t, has_phos, has_sil, H0, iterations);
+        bool presolved = false;
+        double C2 = 0.0;
+        if (!(H0 > KD(1e-13) && H0 < KD(1e-2))) {
+#if OBM_CC_F32PRE
+            if (!has_phos) {
+                H0 = presolve_f32(c, t, has_sil, H_init, C2, presolved);
+            } else
+#endif
+                H0 = initial_H(c, t, has_sil, H_init);
+        }
+        H = solve_H(c, t, has_phos, has_sil, H0, iterations, presolved, C2);
         if (H_io) *H_io = H;
     }
 

@@ -183,6 +183,10 @@ struct MultiBandArgs {
     double* mlmean;      // 2-D out: mixed-layer mean of the total PAR
 };
 
+// OBM_PAR_SCAN4: four levels per lane in the N-band scan (see the kernel)
+#ifndef OBM_PAR_SCAN4
+#define OBM_PAR_SCAN4 1
+#endif
 #ifndef OBM_PAR_DIAG_BLOCKS
 #define OBM_PAR_DIAG_BLOCKS 5
 #endif
@@ -253,6 +257,58 @@ __global__ void __launch_bounds__(TC* NWARP, DIAG ? OBM_PAR_DIAG_BLOCKS : 5) par
             tile[l][lane] = v;
         }
         __syncthreads();
+#if OBM_PAR_SCAN4
+        // lane ↔ (column q = lane & 3 of the warp's four, levels 4g … 4g + 3 of the z-tile, g = lane >> 2): the prefix product
+        // is three serial multiplications inside the lane, a 3-step scan over the eight lanes of the column (stride 4) and
+        // one multiplication per level — 7 issue slots per cell and band instead of the 27 of a 5-step scan per level.
+        // Shared-memory rows 4g + i at column 4·warp + q: (4g + q) mod 16 is distinct over a half-warp — conflict-free.
+        {
+            const int q4 = lane & 3, g = lane >> 2;
+            const int c = warp * CPW + q4;
+            double lchl[4], dz[4];
+            bool live[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = ktop - (4 * g + i);
+                live[i] = k >= 0;
+                // multi_band.jl:156 (k = Nz: factor zᶜ[Nz], seeded with surface_PAR·division) / :160-161 (Δz)
+                dz[i] = !live[i] ? 0.0 : (k == Nz - 1 ? d.zc[k] : d.zc[k] - d.zc[k + 1]);
+                lchl[i] = log(tile[4 * g + i][c]);  // Chl^e = exp(e ln Chl): one log shared by all bands
+            }
+            double top = 0.0;
+#pragma unroll
+            for (int n = 0; n < NB; n++) {
+                const double kw = a.m.water_attenuation_coefficient[n], e = a.m.chlorophyll_exponent[n];
+                const double chi = a.m.chlorophyll_attenuation_coefficient[n];
+                double t[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double chle = e == 0.0 ? 1.0 : lexp(e * lchl[i]);  // x^0 ≡ 1 (also for x = 0)
+                    t[i] = live[i] ? lexp(dz[i] * (kw + chi * chle)) : 1.0;
+                }
+                if (ktop == Nz - 1 && g == 0) t[0] = col_par0[c] * a.m.surface_PAR_division[n] * t[0];
+                const double p1 = t[0] * t[1], p2 = p1 * t[2], p3 = p2 * t[3];
+                double sc = p3;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    const double nb = __shfl_up_sync(0xffffffffu, sc, 4 * o);
+                    if (g >= o) sc *= nb;
+                }
+                double ex = __shfl_up_sync(0xffffffffu, sc, 4);
+                if (g == 0) ex = 1.0;
+                const double base = carry[0][n] * ex;  // carry[0][n]: this lane's column (field[k+1] just above the z-tile)
+                const double f0 = base * t[0], f1 = base * p1, f2 = base * p2, f3 = base * p3;
+                carry[0][n] = __shfl_sync(0xffffffffu, f3, 28 + q4);
+                out[n][4 * g + 0][c] = f0;
+                out[n][4 * g + 1][c] = f1;
+                out[n][4 * g + 2][c] = f2;
+                out[n][4 * g + 3][c] = f3;
+                if (DIAG) top = (n == 0) ? f0 : top + f0;
+            }
+            // threshold of the column from its top level: PAR[Nz] (+ the halo cell above it) — compute_euphotic_depth.jl:6
+            if (DIAG && ktop == Nz - 1 && g == 0) col_thr[c] = (top + col_halo[c]) / 2 * a.cutoff;
+        }
+#else
         const int k = ktop - lane;
         const bool live = k >= 0;
         // multi_band.jl:156 (k = Nz: factor zᶜ[Nz], seeded with surface_PAR·division) / :160-161 (Δz)
@@ -277,6 +333,7 @@ __global__ void __launch_bounds__(TC* NWARP, DIAG ? OBM_PAR_DIAG_BLOCKS : 5) par
             // threshold of the column from its top level: PAR[Nz] (+ the halo cell above it) — compute_euphotic_depth.jl:6
             if (DIAG && ktop == Nz - 1 && lane == 0) col_thr[c] = (top + col_halo[c]) / 2 * a.cutoff;
         }
+#endif
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < TZ / NWARP; q++) {

@@ -102,8 +102,11 @@ class HostStagedStage:
         for n in self.names:
             self.host_tracers[n].copy_(self.model.tracers[n].data)
 
-    def step(self):
-        """One stage, host → host.  Returns after all work is enqueued; `synchronize()` to wait."""
+    def step(self, kernels: bool = True, h2d: bool = True, d2h: bool = True):
+        """One stage, host → host.  Returns after all work is enqueued; `synchronize()` to wait.
+        `kernels=False` / `h2d=False` / `d2h=False` leave that part of the pipeline out: the same copies of the same
+        buffers without the work between them (or one direction of them) are the measured ceiling of this path on the
+        box at hand (bench.py's e2e roofline) — results are only meaningful with all three on."""
         lib = _lib.load()
         copy_in = lib.obm_copy_slab_sm if self.copy_engine in ("sm", "sm_h2d") else lib.obm_copy_slab
         copy_out = lib.obm_copy_slab_sm if self.copy_engine in ("sm", "sm_d2h") else lib.obm_copy_slab
@@ -114,26 +117,30 @@ class HostStagedStage:
             s.wait_stream(cur)
         for j0, j1 in self.slabs:
             cg = g.c_grid(j0=j0, j1=j1)
-            rc = copy_in(C.byref(cg), len(self.names), self._dst_in, self._src_in, self.nplanes, 0,
-                                   self.s_in.cuda_stream)
-            _lib.check(rc, "obm_copy_slab(H2D)")
+            if h2d:
+                rc = copy_in(C.byref(cg), len(self.names), self._dst_in, self._src_in, self.nplanes, 0,
+                             self.s_in.cuda_stream)
+                _lib.check(rc, "obm_copy_slab(H2D)")
             ready = self.s_in.record_event()
             self.s_run.wait_event(ready)
-            with torch.cuda.stream(self.s_run), g.restrict(j0, j1):
-                # only interior planes travel; the one halo a hook reads — the plane below the bottom cells of the
-                # sediment's sinking tracers — is rebuilt on the device for this slab's rows (zero gradient, as
-                # Oceananigans' fill_halo_regions! leaves it)
-                for n in self._halo_names:
-                    fill_z_halos(m.tracers[n], j0, j1)
-                bgc.update_biogeochemical_state(m)
-                bgc.underlying_biogeochemistry.compute_tendencies(g, m.tracers, bgc.biogeochemical_auxiliary_fields(), m.Gn,
-                                                                 accumulate=False, time=m.clock.time)
-                if bgc.sediment is not None:
-                    bgc.sediment.update_tendencies(bgc, m, None)
+            if kernels:
+                with torch.cuda.stream(self.s_run), g.restrict(j0, j1):
+                    # only interior planes travel; the one halo a hook reads — the plane below the bottom cells of the
+                    # sediment's sinking tracers — is rebuilt on the device for this slab's rows (zero gradient, as
+                    # Oceananigans' fill_halo_regions! leaves it)
+                    for n in self._halo_names:
+                        fill_z_halos(m.tracers[n], j0, j1)
+                    bgc.update_biogeochemical_state(m)
+                    bgc.underlying_biogeochemistry.compute_tendencies(g, m.tracers, bgc.biogeochemical_auxiliary_fields(),
+                                                                     m.Gn, accumulate=False, time=m.clock.time)
+                    if bgc.sediment is not None:
+                        bgc.sediment.update_tendencies(bgc, m, None)
             done = self.s_run.record_event()
             self.s_out.wait_event(done)
+            if not d2h:
+                continue
             rc = copy_out(C.byref(cg), len(self.gnames), self._dst_out, self._src_out, self.nplanes, 1,
-                                   self.s_out.cuda_stream)
+                          self.s_out.cuda_stream)
             _lib.check(rc, "obm_copy_slab(D2H)")
             if self.return_tracers:  # src / dst swapped: device tracers → host tracers
                 rc = copy_out(C.byref(cg), len(self.names), self._src_in, self._dst_in, self.nplanes, 1,

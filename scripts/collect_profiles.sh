@@ -43,6 +43,19 @@ t = {"pisces_c4": {"kernel": "pisces_tendency_kernel", "bytes_per_launch": traff
                    "note": "captured at full size (134 M cells), accumulate mode", "cells": 134217728, "source": f"profiles/{R}_full_pisces_c4.txt"},
      "lobster_c3": {"kernel": "npd_tendency_kernel", "bytes_per_launch": traffic(f"profiles/{R}_full_lobster_c3.txt", "npd_tendency_kernel"),
                     "note": "full size (16.8 M cells), accumulate mode", "cells": 16777216, "source": f"profiles/{R}_full_lobster_c3.txt"}}
+# the other roof: FP64-pipe thread instructions per cell of the dominant PISCES kernel (source page of the same capture) and
+# the DFMA rate measured by obm_fp64_peak_dfma_per_s on the same visit
+import subprocess
+ops = json.loads(subprocess.run([sys.executable, "scripts/ncu_opcodes.py", "gpurun_out/prof_pisces_c4_pisces_tendency.ncu-rep",
+                                 str(t["pisces_c4"]["cells"]), "--json"], capture_output=True, text=True, check=True).stdout)
+t["pisces_c4"]["fp64_instr_per_cell"] = ops["fp64_instr_per_cell"]
+t["pisces_c4"]["fp64_source"] = ("ncu source page of the same capture: " + " + ".join(f"{k} {v}" for k, v in ops["by_opcode"].items())
+                                 + f" thread instructions per cell (scripts/ncu_opcodes.py; profiles/{R}_opcodes_pisces_c4.txt)")
+rates = [float(x) for x in re.findall(r"DFMA/s\s+([\d.]+)", open(f"profiles/{R}_fp64_peak_dfma.txt").read())]
+t["fp64_peak_instr_per_s"] = max(rates) if rates else 16.9e12
+t["fp64_peak_source"] = f"profiles/{R}_fp64_peak_dfma.txt (obm_fp64_peak_dfma_per_s: 8 independent DFMA chains per thread, best of three)"
 json.dump(t, open("profiles/traffic.json", "w"), indent=1)
 PY
+{ echo "# $R — executed instructions per cell by SASS opcode (scripts/ncu_opcodes.py on the full captures above; 134 M cells)"
+  for K in pisces_tendency scale_negative_calcite par_multiband; do echo "===== $K"; python scripts/ncu_opcodes.py gpurun_out/prof_pisces_c4_$K.ncu-rep 134217728; done; } > profiles/${R}_opcodes_pisces_c4.txt
 echo "profiles/${R}_* refreshed"

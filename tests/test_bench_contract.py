@@ -51,11 +51,14 @@ def test_product_arm_fails_loudly_without_a_gpu():
 def test_roofline_helpers():
     sys.path.insert(0, ROOT)
     import bench
+    import json
+    rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["pisces_c4"]
     traffic, note = bench.ncu_traffic("pisces_c4", 134217728 // 2)
-    assert abs(traffic - 90631106000.0 / 2) < 1 and "r02_full_pisces_c4" in note
+    assert abs(traffic - rec["bytes_per_launch"] / 2) < 1 and rec["source"] in note and os.path.exists(os.path.join(ROOT, rec["source"]))
+    assert 0.95 * 640 < rec["bytes_per_launch"] / rec["cells"] < 1.15 * 640  # ncu DRAM traffic within 15 % of the algorithmic bytes
     assert bench.ncu_traffic("npzd_c1", 10) == (None, None)
     f = bench.fp64_roofline("pisces_c4", 134217728, 19.03)
-    assert f["unit"] == "T FP64 instr/s" and 0.4 < f["frac"] < 0.6 and f["instr_per_cell"] == 1174.5
+    assert f["unit"] == "T FP64 instr/s" and 0.4 < f["frac"] < 0.6 and 1100 < f["instr_per_cell"] < 1250
     assert bench.fp64_roofline("lobster_c3", 1, 1.0) is None
     names = set(bench.workload_table())
     assert names == {"pisces_c4", "lobster_c3", "lobster_c2", "npzd_c1", "carbon_c5"} and bench.default_workload() == "pisces_c4"

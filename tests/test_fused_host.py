@@ -99,3 +99,32 @@ def test_fused_prologue_and_light_match_oracle_on_the_host(oracle, fused):
     rel = lambda a, b: float(np.max(np.abs(og.interior(a) - og.interior(b)) / np.abs(og.interior(b))))  # noqa: E731
     assert max(rel(bands[n], ob_[n]) for n in range(3)) <= 1e-12 and rel(total, ot) <= 1e-12
     assert rel(zeu, oracle.euphotic_depth(og, ot)) <= 1e-12 and rel(mean, oracle.mixed_layer_mean(og, zmxl, ot)) <= 1e-12
+
+
+def test_fp32_presolve_then_one_fp64_step_reaches_the_reference_root(oracle, fused):
+    """carbon_chemistry.cuh presolve_f32: three FP32 Newton steps from the carbonate-alkalinity quadratic, then ONE FP64 step
+    whose C·Δx² error is removed with the C the pre-solve delivers.  On sea-water states that single FP64 step
+    (iterations = 1) must already sit on the root of the reference's damped Newton (oracle): |ΔpH| ≤ 1e-12 here against
+    the stated 1e-10; over a box far outside sea water the ordinary FP64 loop takes over and the stated bound holds."""
+    from oceanbiome_b200 import _lib as abi
+    rng = np.random.default_rng(11)
+    n = 20000
+    T, S = rng.uniform(-1.5, 32, n), rng.uniform(28, 40, n)
+    DIC = rng.uniform(1800, 2400, n)
+    Alk = DIC * rng.uniform(1.02, 1.25, n)
+    want, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=abi.CC_PH_FREE)
+    for iterations in (1, 12):
+        got = fused.carbon_chemistry_sweep(T, S, DIC, Alk, iterations=iterations)
+        err = float(np.max(np.abs(got - want)))
+        print(f"[parity] FP32 pre-solve + {iterations} FP64 step(s), sea water: max |dpH| {err:.2e}")
+        assert err <= 1e-12, (iterations, err)
+    for kind in (abi.CC_OMEGA_CALCITE, abi.CC_FCO2):
+        w, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=kind)
+        g = fused.carbon_chemistry_sweep(T, S, DIC, Alk, output=kind)
+        assert float(np.max(np.abs(g - w) / np.abs(w))) <= 1e-12, kind
+    T, S = rng.uniform(-2, 40, n), rng.uniform(1, 45, n)
+    DIC, Alk = rng.uniform(100, 4000, n), rng.uniform(100, 4500, n)
+    want, _ = oracle.carbon_chemistry_sweep(T, S, DIC, Alk, output=abi.CC_PH_FREE)
+    got = fused.carbon_chemistry_sweep(T, S, DIC, Alk)
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), ok) and float(np.max(np.abs(got - want)[ok])) <= 1e-10
