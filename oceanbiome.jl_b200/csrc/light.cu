@@ -26,6 +26,11 @@ namespace obm {
 #ifndef OBM_LIGHT_EXP
 #define OBM_LIGHT_EXP 4
 #endif
+// OBM_PAR_SCAN4: four levels per lane in the scans (see par_multiband_kernel): 3-band PAR 0.392 → 0.350 ms per 16.8 M cells
+// (profiles/r04_kernel_variants.txt); 0 restores one level per lane and a 5-step scan per level.
+#ifndef OBM_PAR_SCAN4
+#define OBM_PAR_SCAN4 1
+#endif
 __device__ __forceinline__ double lexp(double x) {
 #if OBM_LIGHT_EXP == 0
     return exp(x);
@@ -86,7 +91,10 @@ struct TwoBandArgs {
     double* PAR;
 };
 
-__global__ void __launch_bounds__(TC* NWARP) par_twoband_kernel(const __grid_constant__ TwoBandArgs a) {
+#ifndef OBM_PAR_TWOBAND_BLOCKS
+#define OBM_PAR_TWOBAND_BLOCKS 4  // 64 registers; 3 (≤ 80): +3 %, 5 (48): +5 % (profiles/r04_kernel_variants.txt)
+#endif
+__global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband_kernel(const __grid_constant__ TwoBandArgs a) {
     __shared__ double tile[TZ][TC + 1];
     __shared__ long long col_base[TC];
     __shared__ double col_par0[TC];
@@ -123,6 +131,64 @@ __global__ void __launch_bounds__(TC* NWARP) par_twoband_kernel(const __grid_con
             tile[l][lane] = (k >= 0 && b >= 0) ? a.P[b + d.sz * k] : 0.0;
         }
         __syncthreads();
+#if OBM_PAR_SCAN4
+        // 2. lane ↔ (column q = lane & 3 of the warp's four, levels 4g … 4g + 3 of the z-tile, g = lane >> 2): three serial
+        // additions inside the lane, a 3-step scan over the column's eight lanes (stride 4), one addition per level —
+        // see par_multiband_kernel.  The level above a lane's first level is the last level of lane − 4 (or the carry).
+        {
+            const int q4 = lane & 3, g = lane >> 2;
+            const int c = warp * CPW + q4;
+            double pr[4], pb[4], zck[4], w_above[4], w_here[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int k = ktop - (4 * g + i);
+                const bool live = k >= 0;
+                zck[i] = live ? d.zc[k] : 0.0;
+                // weights of 2band.jl:20-21 (top level) / :28-29 (the rest)
+                w_above[i] = (live && k < Nz - 1) ? (d.zc[k + 1] - d.zf[k + 1]) : 0.0;
+                w_here[i] = live ? (d.zf[k + 1] - zck[i]) : 0.0;
+                const double lp = log(tile[4 * g + i][c] * Rcp / r);  // x^e = exp(e ln x), one logarithm for both bands
+                pr[i] = live ? (er == 0.0 ? 1.0 : lexp(er * lp)) : 0.0;  // x^0 ≡ 1
+                pb[i] = live ? (eb == 0.0 ? 1.0 : lexp(eb * lp)) : 0.0;
+            }
+            double pr_up = __shfl_up_sync(0xffffffffu, pr[3], 4);
+            double pb_up = __shfl_up_sync(0xffffffffu, pb[3], 4);
+            if (g == 0) { pr_up = prev_pr[0]; pb_up = prev_pb[0]; }
+            // running integral inside the lane; w_above = 0 at the top level so the (undefined) level above adds exactly +0
+            double sr[4], sb[4];
+            sr[0] = w_above[0] * pr_up + w_here[0] * pr[0];
+            sb[0] = w_above[0] * pb_up + w_here[0] * pb[0];
+#pragma unroll
+            for (int i = 1; i < 4; i++) {
+                sr[i] = sr[i - 1] + (w_above[i] * pr[i - 1] + w_here[i] * pr[i]);
+                sb[i] = sb[i - 1] + (w_above[i] * pb[i - 1] + w_here[i] * pb[i]);
+            }
+            double scr = sr[3], scb = sb[3];
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const double nr = __shfl_up_sync(0xffffffffu, scr, 4 * o);
+                const double nb = __shfl_up_sync(0xffffffffu, scb, 4 * o);
+                if (g >= o) { scr += nr; scb += nb; }
+            }
+            double exr = __shfl_up_sync(0xffffffffu, scr, 4);
+            double exb = __shfl_up_sync(0xffffffffu, scb, 4);
+            if (g == 0) exr = exb = 0.0;
+            const double base_r = carry_r[0] + exr, base_b = carry_b[0] + exb;
+            const double par0 = col_par0[c];
+            double ir3 = 0.0, ib3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double ir = base_r + sr[i], ib = base_b + sb[i];
+                tile[4 * g + i][c] = par0 * (lexp(kr * zck[i] - xr * ir) + lexp(kb * zck[i] - xb * ib)) / 2;  // in place
+                ir3 = ir;
+                ib3 = ib;
+            }
+            carry_r[0] = __shfl_sync(0xffffffffu, ir3, 28 + q4);
+            carry_b[0] = __shfl_sync(0xffffffffu, ib3, 28 + q4);
+            prev_pr[0] = __shfl_sync(0xffffffffu, pr[3], 28 + q4);
+            prev_pb[0] = __shfl_sync(0xffffffffu, pb[3], 28 + q4);
+        }
+#else
         // 2. lane ↔ level
         const int k = ktop - lane;
         const bool live = k >= 0;
@@ -154,6 +220,7 @@ __global__ void __launch_bounds__(TC* NWARP) par_twoband_kernel(const __grid_con
             prev_pb[q] = __shfl_sync(0xffffffffu, pb, 31);
             tile[lane][c] = par;  // in place: only this warp touches column c between the barriers
         }
+#endif
         __syncthreads();
         // 3. coalesced store
 #pragma unroll
@@ -183,10 +250,6 @@ struct MultiBandArgs {
     double* mlmean;      // 2-D out: mixed-layer mean of the total PAR
 };
 
-// OBM_PAR_SCAN4: four levels per lane in the N-band scan (see the kernel)
-#ifndef OBM_PAR_SCAN4
-#define OBM_PAR_SCAN4 1
-#endif
 #ifndef OBM_PAR_DIAG_BLOCKS
 #define OBM_PAR_DIAG_BLOCKS 5
 #endif
