@@ -690,6 +690,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling sub-record of a multi-GPU run")
+    ap.add_argument("--no-e2e-balance", action="store_true",
+                    help="multi-GPU e2e leg: keep equal slabs (default: re-share the rows by each rank's measured host-link rate)")
     ap.add_argument("--no-inventory", action="store_true")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
                     help="replay the stage as one CUDA graph (auto: when the working set fits L2, i.e. the stage is launch-bound)")
@@ -855,11 +857,48 @@ def main():
             hs.step()
         b.record()
         barrier()
-        ems = max_over_ranks(a.elapsed_time(b))
-        e2e = {"value": we.cells * world * k / (ems * 1e-3) / 1e9, "unit": "Gcell-updates/s",
+        my_ms = a.elapsed_time(b)
+        ems = max_over_ranks(my_ms)
+        e2e_cells = we.cells * world
+        equal = None
+        # Strong scaling over ranks whose host links are not equally fast (the 8-GPU box: two groups of four GPUs, 1.43×
+        # apart, profiles/r04_e2e_probe_n8.jsonl): a stage ends with the slowest link.  Re-share the rows of the ONE grid in
+        # proportion to each rank's rate just measured (oceanbiome_b200.distributed.slab_ranges_by_rate) and time again;
+        # the device-resident `value` keeps equal slabs.  Both numbers are reported.
+        if world > 1 and rows_info is not None and we is w and w.kind != "carbon" and not args.no_e2e_balance:
+            from oceanbiome_b200.distributed import slab_ranges_by_rate
+            t = torch.tensor([my_ms], dtype=torch.float64, device=device)
+            allms = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allms, t)
+            times = [x.item() for x in allms]
+            nyg = rows_info[2]
+            ranges = slab_ranges_by_rate(nyg, [1.0 / x for x in times], minimum=8)
+            if max(times) > 1.05 * min(times):
+                equal = {"value": e2e_cells * k / (ems * 1e-3) / 1e9, "ms_per_step_per_rank": [round(x / k, 2) for x in times],
+                         "rows_per_rank": nyg // world}
+                del hs
+                j0b, j1b = ranges[rank]
+                we = Workload(name, device, 1.0, rows=(j0b, j1b - j0b, nyg))
+                hs = HostStage(we, args.copy_engine, args.e2e_slabs)
+                for _ in range(2):
+                    hs.step()
+                barrier()
+                a.record()
+                for _ in range(k):
+                    hs.step()
+                b.record()
+                barrier()
+                my_ms = a.elapsed_time(b)
+                ems = max_over_ranks(my_ms)
+                e2e_cells = w.grid.Nx * nyg * w.grid.Nz
+        e2e = {"value": e2e_cells * k / (ems * 1e-3) / 1e9, "unit": "Gcell-updates/s",
                "h2d_bytes_per_step": hs.h2d_bytes, "d2h_bytes_per_step": hs.d2h_bytes, "steps": k,
                "cells_per_gpu": we.cells, "copy_engine": args.copy_engine, "numa_bound": bool(hs.numa_bound),
                "pcie_GBs_each_direction": max(hs.h2d_bytes, hs.d2h_bytes) * k / (ems * 1e-3) / 1e9}
+        if equal is not None:
+            e2e["slabs"] = {"how": "rows of the one grid shared out in proportion to each rank's host-link rate measured with equal slabs "
+                                   "in this run (a stage ends with the slowest link); bytes and cells_per_gpu are rank 0's",
+                            "rows_per_rank": [j1 - j0 for j0, j1 in ranges], "equal_slabs": equal}
         # the leg's ceiling on THIS box, measured with the leg's own pinned buffers and copy pattern on every rank at once:
         # the same slab copies without the kernels between them, then each direction alone (profiles/r04_e2e_probe_*:
         # with 8 ranks the two directions do not overlap on the host side — copies-only ≈ H2D-only + D2H-only — and the

@@ -372,6 +372,17 @@ int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_params* p,
                           const double* const* tracers, const obm_pisces_fields* aux,
                           double* const* G, int accumulate, void* stream);
 
+/* The same launch for `latitude = ModelLatitude()` (PISCES/common.jl:9-13,27-28: φ = φnode(i, j, k, grid), what a
+ * LatitudeLongitudeGrid needs; PISCES.jl:360-367 decides between the two).  The three members of obm_pisces_params
+ * that depend on the latitude then differ from row to row: `row_latitude_daylengths` is a DEVICE array [3][grid->Ny] —
+ * latitude (°), day_length(φ, t) (the swapped call of growth_rate.jl:29-30) and day_length(t, φ) (:141-143) of every
+ * interior row j — evaluated by the host like their scalar counterparts; the members of `p` are ignored.  Everything
+ * else, and the results for a table of Ny identical rows, are those of obm_pisces_tendencies bit for bit. */
+int obm_pisces_tendencies_rows(const obm_grid* grid, const obm_pisces_params* p,
+                               const double* row_latitude_daylengths, const double* const* tracers,
+                               const obm_pisces_fields* aux, double* const* G, int accumulate,
+                               void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (a9) ScaleNegativeTracers — src/Utils/negative_tracers.jl:137-276.  All groups of a model
  * in ONE launch, applied sequentially in the given order (PISCES: carbon, iron, phosphate,

@@ -51,6 +51,8 @@ include("obm_structs.jl")   # ObmGrid, ObmNpdParams, ObmTwobandParams, ObmMultib
 
 # helpers the generated constructors use
 fieldor(x, f::Symbol) = (hasproperty(x, f) && !isnothing(getproperty(x, f))) ? Float64(getproperty(x, f)) : 0.0
+# the scalar latitude of a PrescribedLatitude (PISCES/common.jl:20-25); 0.0 for ModelLatitude, whose per-row values travel separately
+prescribed_latitude(bgc) = hasproperty(bgc.latitude, :latitude) ? Float64(bgc.latitude.latitude) : 0.0
 tupleor(x, f::Symbol, n) = (hasproperty(x, f) && length(getproperty(x, f)) ≥ n) ? Float64(getproperty(x, f)[n]) : 0.0
 bandor(v, n) = n ≤ length(v) ? Float64(v[n]) : 0.0
 # enumerations of include/obm_b200.h, chosen by the TYPE of the reference component
@@ -367,6 +369,17 @@ function add_tendencies!(b, u::PISCES, model, g)                       # replace
                         euphotic_depth_xy = dptr(aux.zₑᵤ), mean_mixed_layer_vertical_diffusivity_xy = dptr(aux.κ),
                         mean_mixed_layer_light_xy = dptr(aux.mixed_layer_PAR))
     G = F64[n in (:T, :S) ? CU_NULL : dptr(model.timestepper.Gⁿ[n]) for n in names]
+    if u.latitude isa OceanBioME.Models.PISCESModel.ModelLatitude       # PISCES/common.jl:27-28: φ = φnode(i, j, k, grid) — a row's own day lengths
+        φ = Float64.(φnodes(model.grid, Center(), Center(), Center()))  # the Ny interior rows
+        t = model.clock.time
+        rows = CuArray(hcat(φ, Float64[u.day_length(x, t) for x in φ],  # growth_rate.jl:29-30 (the swapped call)
+                            Float64[u.day_length(t, x) for x in φ]))    # :141-143; an Ny × 3 column-major matrix = the C array [3][Ny]
+        check(ccall((:obm_pisces_tendencies_rows, libobm), Cint,
+                    (Ref{ObmGrid}, Ref{ObmPiscesParams}, F64, Ptr{F64}, Ref{ObmPiscesFields}, Ptr{F64}, Cint, Ptr{Cvoid}),
+                    g, Ref(ObmPiscesParams(u, model.clock)), pointer(rows), table(model.tracers[n] for n in names), Ref(f), G, 1, stream()),
+              "obm_pisces_tendencies_rows")
+        return nothing
+    end
     check(ccall((:obm_pisces_tendencies, libobm), Cint,
                 (Ref{ObmGrid}, Ref{ObmPiscesParams}, Ptr{F64}, Ref{ObmPiscesFields}, Ptr{F64}, Cint, Ptr{Cvoid}),
                 g, Ref(ObmPiscesParams(u, model.clock)), table(model.tracers[n] for n in names), Ref(f), G, 1, stream()),

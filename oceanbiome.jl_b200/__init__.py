@@ -16,7 +16,7 @@ from .npd import (LOBSTER, NPZD, AnalyticalLightLimitation, CarbonateSystem, Det
                   NitrateAmmonia, NitrateAmmoniaIron, Nutrient, NutrientsPlanktonDetritus, Oxygen, PhytoZoo, Quadratic,
                   TwoParticleAndDissolved, VariableRedfieldDetritus)
 from . import pisces
-from .pisces import PISCES, CBMDayLength, DepthDependantSinkingSpeed, PrescribedLatitude
+from .pisces import PISCES, CBMDayLength, DepthDependantSinkingSpeed, ModelLatitude, PrescribedLatitude
 from .sediments import (BiogeochemicalSediment, InstantRemineralisation, InstantRemineralisationSediment, SimpleMultiG,
                         SimpleMultiGSediment, calculate_bottom_indices)
 from .gas_exchange import (CarbonDioxideConcentration, CarbonDioxideGasExchangeBoundaryCondition,

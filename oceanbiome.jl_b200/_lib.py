@@ -260,6 +260,8 @@ PROTOTYPES = {
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "obm_pisces_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p,
                                         C.POINTER(obm_pisces_fields), C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_pisces_tendencies_rows": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p, C.c_void_p,
+                                             C.POINTER(obm_pisces_fields), C.c_void_p, C.c_int, C.c_void_p]),
     "obm_par_twoband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_twoband_params), C.c_void_p, C.c_void_p,
                                   C.c_double, C.c_void_p, C.c_void_p]),
     "obm_par_multiband": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_multiband_params), C.c_void_p, C.c_void_p,

@@ -140,6 +140,47 @@ __global__ void OBM_PISCES_BOUNDS pisces_tendency_kernel(const __grid_constant__
     if (sink.pending) cell_exact(a, idx, pl, k, sink.pending);  // rare: non-finite results, NaN inputs
 }
 
+// ---- ModelLatitude (PISCES/common.jl:27-28: φ = φnode(i, j, k, grid)) ------------------------------------------------------------
+// On a grid that carries its own latitude the three host-evaluated quantities of obm_pisces_params that depend on it —
+// latitude, day_length(φ, t) with the reference's swapped arguments (growth_rate.jl:29-30) and day_length(t, φ)
+// (:141-143) — differ from row to row.  A block works on one (j, k) row (thread_cell), so it copies the kernel
+// arguments to shared memory, patches those three values and the parameter-only sub-expressions derived from them
+// (pisces_prepare's formulas, IEEE arithmetic: bit-identical to the host evaluation) for ITS row, and runs the very same
+// cell code on the patched copy.  Nothing changes in the prescribed-latitude kernel above, which every named
+// configuration uses; this variant reads its parameters from shared memory instead of the constant bank.
+template <bool ACC>
+__global__ void OBM_PISCES_BOUNDS pisces_tendency_rows_kernel(const __grid_constant__ PiscesArgs a, const double* __restrict__ rows) {
+    __shared__ PiscesArgs sa;
+    static_assert(sizeof(PiscesArgs) % sizeof(double) == 0, "PiscesArgs is copied in 8-byte words");
+    {
+        const double* src = reinterpret_cast<const double*>(&a);
+        double* dst = reinterpret_cast<double*>(&sa);
+        for (int w = threadIdx.x; w < (int)(sizeof(PiscesArgs) / sizeof(double)); w += blockDim.x) dst[w] = src[w];
+    }
+    __syncthreads();
+    int i = 0, j = 0, k = 0;
+    const bool inside = thread_cell(a.d, i, j, k);
+    if (threadIdx.x == 0) {  // always inside: its block exists
+        const int Ny = a.d.Ny;
+        const double lat = rows[j], dlg = rows[Ny + j], dlc = rows[2 * Ny + j];
+        sa.p.latitude = lat;
+        sa.p.day_length_growth = dlg;
+        sa.p.day_length_chlorophyll = dlc;
+        sa.dv.f1_growth = 1.5 * dlg / (dlg + 0.5 * DAY);
+        sa.dv.dl_over_f1_chl = dlc / (1.5 * dlc / (dlc + 0.5 * DAY));
+        sa.dv.inv_resp[0] = 1.0 / (dlg * (a.p.nano.basal_respiration_rate + a.p.nano.reference_growth_rate));
+        sa.dv.inv_resp[1] = 1.0 / (dlg * (a.p.diatoms.basal_respiration_rate + a.p.diatoms.reference_growth_rate));
+    }
+    __syncthreads();
+    if (!inside) return;
+    const long long idx = cell_index(a.d, i, j, k);
+    const long long pl = plane_index(a.d, i, j);
+    const Inputs in = load_inputs(a, idx, pl, k);
+    FastSink<ACC, false> sink{sa, idx, 0u, needs_exact(in) ? 1u : 0u};
+    cell_tendencies<false>(sa, in, sink);
+    if (sink.pending) cell_exact(sa, idx, pl, k, sink.pending);
+}
+
 // ---- the same cell arithmetic, software-pipelined over a persistent launch (build option OBM_PISCES_PIPE) -------------------------
 // ncu (r3a, source page): ≈ 15 % of the warp-state samples of the kernel above sit on the first use of a loaded input — a
 // thread's 38 loads go out together and, at 12 warps per SM, little else is ready while they are in flight.  Here a block
@@ -226,13 +267,11 @@ __global__ void OBM_PISCES_BOUNDS pisces_tendency_pipe_kernel(const __grid_const
 
 using namespace obm;
 
-extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_params* p, const double* const* tracers,
-                                     const obm_pisces_fields* aux, double* const* G, int accumulate, void* stream) {
+static int pisces_arguments(PiscesArgs& A, const obm_grid* grid, const obm_pisces_params* p, const double* const* tracers,
+                            const obm_pisces_fields* aux, double* const* G, int accumulate) {
     OBM_REQUIRE(p && tracers && aux && G, OBM_ENULL, "obm_pisces_tendencies: params / tracers / aux / G is NULL");
-    static thread_local PiscesArgs tl;  // ~2 KB of kernel arguments, kept off the caller's stack
-    PiscesArgs& A = tl;
     memset(&A, 0, sizeof(A));
-    int rc = make_dims(grid, &A.d, true);
+    const int rc = make_dims(grid, &A.d, true);
     if (rc) return rc;
     A.p = *p;
     A.f = *aux;
@@ -254,6 +293,15 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
     for (int n = 0; n < NOUT; n++)
         if (A.g[n]) A.out_mask |= 1u << n;
     pisces_prepare(A, p);
+    return 0;
+}
+
+extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_params* p, const double* const* tracers,
+                                     const obm_pisces_fields* aux, double* const* G, int accumulate, void* stream) {
+    static thread_local PiscesArgs tl;  // ~2 KB of kernel arguments, kept off the caller's stack
+    PiscesArgs& A = tl;
+    const int rc = pisces_arguments(A, grid, p, tracers, aux, G, accumulate);
+    if (rc) return rc;
     const dim3 gr = cell_grid(A.d, PB);
     cudaStream_t st = (cudaStream_t)stream;
     static const bool carveout_set = [] {  // no shared memory is used: give the whole array to L1 (spill slots)
@@ -292,4 +340,18 @@ extern "C" int obm_pisces_tendencies(const obm_grid* grid, const obm_pisces_para
         else pisces_tendency_kernel<false, false><<<gr, PB, 0, st>>>(A);
     }
     return launch_status("pisces_tendency_kernel");
+}
+
+extern "C" int obm_pisces_tendencies_rows(const obm_grid* grid, const obm_pisces_params* p, const double* row_latitude_daylengths,
+                                          const double* const* tracers, const obm_pisces_fields* aux, double* const* G,
+                                          int accumulate, void* stream) {
+    OBM_REQUIRE(row_latitude_daylengths, OBM_ENULL, "obm_pisces_tendencies_rows: the per-row table is NULL");
+    static thread_local PiscesArgs tl;
+    PiscesArgs& A = tl;
+    const int rc = pisces_arguments(A, grid, p, tracers, aux, G, accumulate);
+    if (rc) return rc;
+    const dim3 gr = cell_grid(A.d, PB);
+    if (A.accumulate) pisces_tendency_rows_kernel<true><<<gr, PB, 0, (cudaStream_t)stream>>>(A, row_latitude_daylengths);
+    else pisces_tendency_rows_kernel<false><<<gr, PB, 0, (cudaStream_t)stream>>>(A, row_latitude_daylengths);
+    return launch_status("pisces_tendency_rows_kernel");
 }

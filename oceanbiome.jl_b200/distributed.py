@@ -42,6 +42,31 @@ def slab_ranges(Ny: int, world: int):
     return [(r * n, (r + 1) * n) for r in range(world)]
 
 
+def slab_ranges_by_rate(Ny: int, rates: Sequence[float], minimum: int = 1):
+    """[j0, j1) of every rank's slab with the rows shared out in proportion to `rates` (largest-remainder rounding, at
+    least `minimum` rows each).  For the HOST-buffer path on a node whose GPUs do not see the same host bandwidth
+    (measured on the 8-GPU box: the four GPUs behind one host bridge move 1.43× what the other four do,
+    profiles/r04_e2e_probe_n8.jsonl) a stage ends when the slowest link has finished, so equal slabs leave the fast links
+    idle; the device-resident path keeps `slab_ranges` (equal work per GPU)."""
+    world = len(rates)
+    if world < 1 or Ny < world * minimum or any(not (r > 0) for r in rates):
+        raise ValueError(f"cannot share {Ny} rows over rates {list(rates)} with at least {minimum} each")
+    total = float(sum(rates))
+    exact = [Ny * r / total for r in rates]
+    rows = [int(e) for e in exact]
+    for q in sorted(range(world), key=lambda q: exact[q] - rows[q], reverse=True)[:Ny - sum(rows)]:
+        rows[q] += 1
+    while min(rows) < minimum:  # a very slow rank still gets `minimum` rows, taken from the largest slab
+        rows[rows.index(max(rows))] -= 1
+        rows[rows.index(min(rows))] += 1
+    out, j = [], 0
+    for q in range(world):
+        out.append((j, j + rows[q]))
+        j += rows[q]
+    assert j == Ny
+    return out
+
+
 def inventory_groups(groups: Sequence):
     """→ (distinct tracer names, ctypes obm_scale_group array) for a list of (names, scalefactors)."""
     names = []

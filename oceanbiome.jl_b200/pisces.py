@@ -78,6 +78,15 @@ class PrescribedLatitude:
     latitude: float = 45.0
 
 
+class ModelLatitude:
+    """`ModelLatitude()` — PISCES/common.jl:9-13,27-28: the latitude of the model grid's own rows, φnode(i, j, k, grid).
+    Needs a grid that has one (`LatitudeLongitudeGrid`); the day lengths then differ from row to row and the tendencies
+    go through `obm_pisces_tendencies_rows`."""
+
+    def __repr__(self):
+        return "ModelLatitude()"
+
+
 @dataclass
 class DepthDependantSinkingSpeed:
     """common.jl:39-55 — note the literal 5000 (the `maximum_depth` field is ignored by the reference)."""
@@ -403,13 +412,22 @@ class PISCESModel:
         for k in ("first_anoxia_threshold", "second_anoxia_threshold", "nitrogen_redfield_ratio", "phosphate_redfield_ratio",
                   "mixed_layer_shear", "background_shear"):
             setattr(p, k, float(getattr(self, k)))
-        φ = float(self.latitude.latitude)
+        # ModelLatitude: the per-row values travel in `row_table`; the scalar members are then ignored by the kernel
+        φ = 0.0 if isinstance(self.latitude, ModelLatitude) else float(self.latitude.latitude)
         p.latitude = φ
         # the reference's two call orders (growth_rate.jl:30 swapped, :143 correct) — SURVEY App. A bug 1
         p.day_length_growth = float(self.day_length(φ, time))
         p.day_length_chlorophyll = float(self.day_length(time, φ))
         p.silicate_climatology = float(self.silicate_climatology)
         return p
+
+    def row_table(self, grid, time: float) -> torch.Tensor:
+        """ModelLatitude: latitude, day_length(φ, t) (the reference's swapped call, growth_rate.jl:29-30) and
+        day_length(t, φ) (:141-143) of every interior row j as a device array [3][Ny] — host-evaluated per launch like
+        their scalar counterparts in `c_params`."""
+        φs = [float(v) for v in grid.latitude_centers]
+        rows = [φs, [float(self.day_length(φ, time)) for φ in φs], [float(self.day_length(time, φ)) for φ in φs]]
+        return torch.tensor(rows, dtype=torch.float64).to(grid.device)
 
     def c_fields(self, aux: dict) -> _lib.obm_pisces_fields:
         f = _lib.obm_pisces_fields()
@@ -466,6 +484,13 @@ class PISCESModel:
         tptr = _lib.pointer_table([tracers[n].ptr for n in TRACERS])
         gptr = _lib.pointer_table([G[n].ptr if (n in G and G[n] is not None and n not in ("T", "S")) else None for n in TRACERS])
         s = stream if stream is not None else current_stream_ptr(grid.device)
+        if isinstance(self.latitude, ModelLatitude):
+            rows = self.row_table(grid, time)  # (kept alive by the local name until the launch is enqueued; same stream order)
+            rc = _lib.load().obm_pisces_tendencies_rows(C.byref(cg), C.byref(p), C.c_void_p(rows.data_ptr()), tptr, C.byref(f),
+                                                        gptr, 1 if accumulate else 0, s)
+            _lib.check(rc, "obm_pisces_tendencies_rows")
+            self._row_table = rows  # the launch reads it asynchronously: keep it until the next one replaces it
+            return
         rc = _lib.load().obm_pisces_tendencies(C.byref(cg), C.byref(p), tptr, C.byref(f), gptr, 1 if accumulate else 0, s)
         _lib.check(rc, "obm_pisces_tendencies")
 
@@ -551,12 +576,25 @@ def PISCES(grid: RectilinearGrid, phytoplankton=None, zooplankton=None, dissolve
             velocities[name] = w.face_field(grid, mixed_layer_depth, euphotic_depth)  # `compute!(w)` once, at setup
         else:
             velocities[name] = w
+    # PISCES.jl:360-367: a grid with its own latitude overrides a prescribed one (the reference warns and then stores
+    # `nothing`, which its kernels cannot call — the stated intent, the grid's latitude, is what is built here); a
+    # RectilinearGrid has none to offer
+    from .grids import LatitudeLongitudeGrid
+    latitude = latitude or PrescribedLatitude(45.0)
+    if isinstance(latitude, PrescribedLatitude) and isinstance(grid, LatitudeLongitudeGrid):
+        import warnings
+        φ = grid.latitude_centers
+        warnings.warn(f"A latitude of {latitude} was given but the grid has its own latitude ({min(φ)}, {max(φ)}) so the "
+                      "prescribed value is ignored")
+        latitude = ModelLatitude()
+    elif isinstance(latitude, ModelLatitude) and not isinstance(grid, LatitudeLongitudeGrid):
+        raise ValueError("You must prescribe a latitude when using a `RectilinearGrid`")
     underlying = PISCESModel(
         grid, phytoplankton or MixedMondoNanoAndDiatoms(), zooplankton or MicroAndMesoZooplankton(),
         dissolved_organic_matter or DissolvedOrganicCarbon(), particulate_organic_matter or TwoCompartmentCarbonIronParticles(),
         nitrogen or NitrateAmmonia(), iron or SimpleIron(), oxygen or Oxygen(), first_anoxia_threshold,
         second_anoxia_threshold, nitrogen_redfield_ratio, phosphate_redfield_ratio, mixed_layer_shear, background_shear,
-        latitude or PrescribedLatitude(45.0), day_length or CBMDayLength(), mixed_layer_depth, euphotic_depth,
+        latitude, day_length or CBMDayLength(), mixed_layer_depth, euphotic_depth,
         silicate_climatology, mean_mixed_layer_vertical_diffusivity, mean_mixed_layer_light,
         carbon_chemistry or CarbonChemistry(newton_iterations=8), calcite_saturation, velocities)
     if scale_negatives:

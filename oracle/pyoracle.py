@@ -289,25 +289,27 @@ def pisces_fields(aux: dict):
     return f
 
 
-def pisces_tendencies(grid: Grid, params, tracers, aux: dict, G=None, accumulate=False, skip=("T", "S")):
-    """One full-grid pass per tracer (reference launch structure).  tracers: list of 26 parent arrays."""
+def pisces_tendencies(grid: Grid, params, tracers, aux: dict, G=None, accumulate=False, skip=("T", "S"), rows=None):
+    """One full-grid pass per tracer (reference launch structure).  tracers: list of 26 parent arrays.
+    `rows = (j0, j1)`: only those interior rows (ModelLatitude: one call per row with that row's parameter block)."""
     _check(tracers)
     if G is None:
         G = [np.zeros(grid.parent_shape) if n < 24 else None for n in range(abi.OBM_PISCES_NTRACERS)]
     f = pisces_fields(aux)
-    cg = grid.c_grid()
+    cg = grid.c_grid() if rows is None else grid.c_grid(j0=rows[0], j1=rows[1])
     rc = lib().orc_pisces_tendencies(C.byref(cg), C.byref(params), _table(tracers), C.byref(f), _table(G),
                                      1 if accumulate else 0)
     assert rc == 0, f"orc_pisces_tendencies → {rc}"
     return G
 
 
-def pisces_tendency_scales(grid: Grid, params, tracers, aux: dict):
+def pisces_tendency_scales(grid: Grid, params, tracers, aux: dict, S=None, rows=None):
     """Σ|additive terms| of each of the 24 tendencies — the S of the parity metric."""
     _check(tracers)
-    S = [np.zeros(grid.parent_shape) if n < 24 else None for n in range(abi.OBM_PISCES_NTRACERS)]
+    if S is None:
+        S = [np.zeros(grid.parent_shape) if n < 24 else None for n in range(abi.OBM_PISCES_NTRACERS)]
     f = pisces_fields(aux)
-    cg = grid.c_grid()
+    cg = grid.c_grid() if rows is None else grid.c_grid(j0=rows[0], j1=rows[1])
     rc = lib().orc_pisces_tendency_scales(C.byref(cg), C.byref(params), _table(tracers), C.byref(f), _table(S))
     assert rc == 0, f"orc_pisces_tendency_scales → {rc}"
     return S

@@ -176,8 +176,8 @@ def main():
     for name in ("first_anoxia_threshold", "second_anoxia_threshold", "nitrogen_redfield_ratio", "phosphate_redfield_ratio",
                  "mixed_layer_shear", "background_shear", "silicate_climatology"):
         setattr(u, name, s.next(("bgc", name, None)))
-    manual = {"day_length_growth": "Float64(bgc.day_length(bgc.latitude.latitude, clock.time))  # growth_rate.jl:30 — the reference's (φ, t) order",
-              "day_length_chlorophyll": "Float64(bgc.day_length(clock.time, bgc.latitude.latitude))  # growth_rate.jl:143 — (t, φ)"}
+    manual = {"day_length_growth": "Float64(bgc.day_length(prescribed_latitude(bgc), clock.time))  # growth_rate.jl:30 — the reference's (φ, t) order (ModelLatitude: per row, obm_pisces_tendencies_rows)",
+              "day_length_chlorophyll": "Float64(bgc.day_length(clock.time, prescribed_latitude(bgc)))  # growth_rate.jl:143 — (t, φ)"}
     for cls in ("nano", "diatoms"):
         manual[f"{cls}.growth_rate_kind"] = f"growth_rate_kind(bgc.phytoplankton.{cls}.growth_rate)"
         manual[f"{cls}.silicate_limited"] = f"Int32(bgc.phytoplankton.{cls}.nutrient_limitation.silicate_limited)"

@@ -381,3 +381,54 @@ def test_per_tracer_call_form(cuda, oracle):
     Fe = torch.linspace(0.05, 1.5, 9, dtype=torch.float64)
     gP = u("PFe", z=z, time=t, device=cuda, **{**state, "Fe": Fe}, **aux)
     assert gP.shape == (9,) and bool((gP[1:] > gP[:-1]).all())  # iron uptake grows with dissolved iron
+
+
+def test_model_latitude_rows_match_oracle_row_by_row(cuda, oracle):
+    """`latitude = ModelLatitude()` on a LatitudeLongitudeGrid (PISCES/common.jl:27-28, PISCES.jl:360-367): every row of
+    columns has its own latitude, hence its own day lengths — both of the reference's argument orders — and, south of
+    the equator, the enhanced silicate limitation.  `obm_pisces_tendencies_rows` against the oracle called row by row
+    with that row's scalar parameter block; and a table of identical rows ≡ the prescribed-latitude launch bit for bit."""
+    from helpers import tendency_parity
+    t = 0.61 * 365 * 86400.0
+    grid = ob.LatitudeLongitudeGrid(size=(40, 6, 9), longitude=(0.0, 10.0), latitude=(-50.0, 58.0), z=(-300.0, 0.0), device=cuda)
+    with pytest.warns(UserWarning, match="prescribed value is ignored"):
+        ob.PISCES(grid, latitude=ob.PrescribedLatitude(10.0))
+    bgc = ob.PISCES(grid, latitude=ob.ModelLatitude(), surface_photosynthetically_active_radiation=120.0)
+    model = ob.BiogeochemicalModel(grid, bgc)
+    u = bgc.underlying_biogeochemistry
+    host = fill(model, bgc)
+    model.clock.time = t
+    model.update_state()
+    og = oracle.Grid.like(grid)
+    aux = host_aux(og, grid, bgc)
+    G = {n: ob.CenterField(grid, fill=3.0) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G, accumulate=False, time=t)
+    tr = [host[n] for n in pisces.TRACERS]
+    Go = [np.zeros(og.parent_shape) if n < 24 else None for n in range(26)]
+    So = [np.zeros(og.parent_shape) if n < 24 else None for n in range(26)]
+    lats = [float(v) for v in grid.latitude_centers]
+    assert min(lats) < 0 < max(lats)
+    day_lengths = set()
+    for j, lat in enumerate(lats):
+        u.latitude = ob.PrescribedLatitude(lat)
+        p = u.c_params(t)
+        day_lengths.add((p.day_length_growth, p.day_length_chlorophyll))
+        oracle.pisces_tendencies(og, p, tr, aux, G=Go, rows=(j, j + 1))
+        oracle.pisces_tendency_scales(og, p, tr, aux, S=So, rows=(j, j + 1))
+    assert len(day_lengths) == len(lats)  # the rows really differ
+    worst = 0.0
+    for n, name in enumerate(pisces.TRACERS[:24]):
+        err, rel_max, rel_p = tendency_parity(og.interior(G[name].data.cpu().numpy()), og.interior(Go[n]), og.interior(So[n]))
+        assert err <= RTOL_TENDENCY and rel_p <= 1e-12, (name, err, rel_max, rel_p)
+        worst = max(worst, err)
+    print(f"[parity] PISCES ModelLatitude, {len(lats)} rows: scale-aware max {worst:.2e}")
+    # identical rows ≡ the scalar launch, bit for bit (same cell code, same derived values)
+    u.latitude = ob.PrescribedLatitude(lats[1])
+    G1 = {n: ob.CenterField(grid, fill=3.0) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G1, accumulate=False, time=t)
+    u.latitude = ob.ModelLatitude()
+    u.row_table = lambda g, time, _r=u.row_table: _r(g, time)[:, 1:2].expand(3, g.Ny).contiguous()
+    G2 = {n: ob.CenterField(grid, fill=3.0) for n in pisces.TRACERS}
+    u.compute_tendencies(grid, model.tracers, bgc.biogeochemical_auxiliary_fields(), G2, accumulate=False, time=t)
+    for n in pisces.TRACERS[:24]:
+        assert torch.equal(G1[n].data, G2[n].data), n

@@ -131,3 +131,48 @@ def test_latitude_longitude_grid_geometry():
     assert t.parent_shape == (2 + 6, 5 + 6, 5 + 6) and list(t.zc) == [-1.5, -0.5]
     with pytest.raises(ValueError):
         ob.LatitudeLongitudeGrid(size=(5, 5, 2), longitude=(-180, 180), latitude=(-95, 85), z=(-2, 0), device="cpu")
+
+
+def test_pisces_latitude_choice_follows_the_reference():
+    """PISCES.jl:360-367: a grid with its own latitude overrides a prescribed one (with the reference's warning), a
+    RectilinearGrid cannot offer one; ModelLatitude's per-row table holds the latitude and BOTH argument orders of the
+    reference's day-length calls (growth_rate.jl:29-30 swapped, :141-143) for every interior row."""
+    import pytest
+    import oceanbiome_b200 as ob
+    g = ob.LatitudeLongitudeGrid(size=(4, 5, 2), longitude=(0, 10), latitude=(-40, 60), z=(-10, 0), device="cpu")
+    with pytest.warns(UserWarning, match="prescribed value is ignored"):
+        u = ob.PISCES(g, latitude=ob.PrescribedLatitude(45.0)).underlying_biogeochemistry
+    assert isinstance(u.latitude, ob.ModelLatitude)
+    u = ob.PISCES(g, latitude=ob.ModelLatitude()).underlying_biogeochemistry
+    t = 0.3 * 365 * 86400.0
+    rows = u.row_table(g, t)
+    assert tuple(rows.shape) == (3, 5)
+    for j, lat in enumerate(g.latitude_centers):
+        assert float(rows[0, j]) == float(lat)
+        assert float(rows[1, j]) == u.day_length(float(lat), t) and float(rows[2, j]) == u.day_length(t, float(lat))
+    assert float(rows[2, 0]) < float(rows[2, -1])  # late April: the southern rows have the shorter days
+    assert u.c_params(t).latitude == 0.0  # the scalar members are not used by the per-row launch
+    with pytest.raises(ValueError, match="prescribe a latitude"):
+        ob.PISCES(ob.RectilinearGrid(size=(2, 2, 2), extent=(1, 1, 1), device="cpu"), latitude=ob.ModelLatitude())
+    # a slab keeps its own rows
+    g6 = ob.LatitudeLongitudeGrid(size=(4, 6, 2), longitude=(0, 10), latitude=(-30, 30), z=(-10, 0), device="cpu")
+    assert list(g6.slab(1, 2).latitude_centers) == list(g6.latitude_centers[3:])
+
+
+def test_slab_ranges_by_rate():
+    """Rows shared out in proportion to the ranks' host-link rates: contiguous, complete, at least `minimum` each, equal
+    rates = equal slabs, and the measured 8-GPU case (two groups 1.43× apart) lands on the expected split."""
+    import pytest
+    from oceanbiome_b200.distributed import slab_ranges, slab_ranges_by_rate
+    assert slab_ranges_by_rate(1024, [3.0] * 8) == slab_ranges(1024, 8)
+    r = slab_ranges_by_rate(1024, [1 / 396.0] * 4 + [1 / 277.0] * 4, minimum=8)
+    assert r[0][0] == 0 and r[-1][1] == 1024 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+    rows = [j1 - j0 for j0, j1 in r]
+    assert rows[:4] == [rows[0]] * 4 and rows[4:] == [rows[4]] * 4 and 104 <= rows[0] <= 107 and 149 <= rows[4] <= 152
+    # the slower group's stage time with its smaller slab equals the faster group's with its larger one (to a row)
+    assert abs(rows[0] * 396.0 - rows[4] * 277.0) <= 396.0
+    assert [j1 - j0 for j0, j1 in slab_ranges_by_rate(10, [1, 1, 1])] in ([4, 3, 3], [3, 4, 3], [3, 3, 4])
+    assert slab_ranges_by_rate(8, [1, 100]) == [(0, 1), (1, 8)]
+    for bad in ((4, [1, 0]), (4, [1, float("nan")]), (1, [1, 1])):
+        with pytest.raises(ValueError):
+            slab_ranges_by_rate(*bad)
