@@ -872,13 +872,13 @@ def main():
             dist.all_gather(allms, t)
             times = [x.item() for x in allms]
             nyg = rows_info[2]
-            ranges = slab_ranges_by_rate(nyg, [1.0 / x for x in times], minimum=8)
+            ranges = slab_ranges_by_rate(nyg, [1.0 / x for x in times], minimum=max(1, min(8, nyg // (2 * world))))
             if max(times) > 1.05 * min(times):
                 equal = {"value": e2e_cells * k / (ems * 1e-3) / 1e9, "ms_per_step_per_rank": [round(x / k, 2) for x in times],
                          "rows_per_rank": nyg // world}
                 del hs
                 j0b, j1b = ranges[rank]
-                we = Workload(name, device, 1.0, rows=(j0b, j1b - j0b, nyg))
+                we = Workload(name, device, args.scale, rows=(j0b, j1b - j0b, nyg))
                 hs = HostStage(we, args.copy_engine, args.e2e_slabs)
                 for _ in range(2):
                     hs.step()

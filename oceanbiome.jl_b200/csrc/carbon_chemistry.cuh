@@ -35,6 +35,9 @@ namespace cc {
 #ifndef OBM_CC_LOG
 #define OBM_CC_LOG 1
 #endif
+#ifndef OBM_CC_LOG1M
+#define OBM_CC_LOG1M 0  // 1: ln(1 − 0.001005 S) as a 12-term series for S ≤ 50 (see constants())
+#endif
 #ifndef OBM_CC_BATCH
 #define OBM_CC_BATCH 1  // the lean exp / log of the equilibrium constants branch-free in one basic block (see constants())
 #endif
@@ -207,8 +210,23 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     // both logarithms branch-free in ONE basic block (their chains interleave); a single, rarely taken branch redoes
     // them with the library when an argument is not a positive normal number
     const double argS1 = 1 + KD(-0.001005) * S;
+#if OBM_CC_LOG1M
+    // ln(1 − u), u = 0.001005 S ∈ [0, 0.05] for S ≤ 50: the Mercator series −(u + u²/2 + … + u¹²/12) truncates below 4·10⁻¹⁸
+    // there — 12 FMAs in place of a logarithm (exponent split, reciprocal, degree-9 polynomial in s²)
+    double logT = log_unguarded(T), logS1;
+    {
+        const double u = KD(0.001005) * S;
+        double q = KD(-1.0 / 12);
+        q = fma(q, u, KD(-1.0 / 11)); q = fma(q, u, KD(-1.0 / 10)); q = fma(q, u, KD(-1.0 / 9)); q = fma(q, u, KD(-1.0 / 8));
+        q = fma(q, u, KD(-1.0 / 7)); q = fma(q, u, KD(-1.0 / 6)); q = fma(q, u, KD(-1.0 / 5)); q = fma(q, u, KD(-1.0 / 4));
+        q = fma(q, u, KD(-1.0 / 3)); q = fma(q, u, -0.5); q = fma(q, u, -1.0);
+        logS1 = q * u;
+    }
+    if (!(log_in_range(T) & (S >= 0.0) & (S <= 50.0))) { logT = log(T); logS1 = log(argS1); }
+#else
     double logT = log_unguarded(T), logS1 = log_unguarded(argS1);
     if (!(log_in_range(T) & log_in_range(argS1))) { logT = log(T); logS1 = log(argS1); }
+#endif
 #else
     const double logT = clog(T);
     const double logS1 = clog(1 + KD(-0.001005) * S);
@@ -365,6 +383,12 @@ __device__ __forceinline__ void residual(double H, const Constants& c, const Tot
 #ifndef OBM_CC_F32PRE
 #define OBM_CC_F32PRE 1
 #endif
+#ifndef OBM_CC_F32_STEPS
+#define OBM_CC_F32_STEPS 3   // FP32 Newton steps of the pre-solve
+#endif
+#ifndef OBM_CC_F32_REFINE
+#define OBM_CC_F32_REFINE 0  // 1: refine the quadratic start once (then 2 steps do; timed in profiles/r04_kernel_variants.txt)
+#endif
 #ifndef OBM_CC_TOL0
 #define OBM_CC_TOL0 1e-5  // exit threshold of the one FP64 step after the pre-solve
 #endif
@@ -411,10 +435,21 @@ __device__ __forceinline__ double presolve_f32(const Constants& c, const Totals&
         const float disc = b * b - 4.0f * AC * K1K2 * (AC - 2.0f * DIC);
         H = (sqrt_f32(disc) - b) * rcp_f32(2.0f * AC);
         H = (H > 1e-12f && H < 1e-3f) ? H : Hi;  // NaN (disc < 0, A_C ≤ 0 …) fails both comparisons
+#if OBM_CC_F32_REFINE
+        // one refinement of the quadratic with every other species at the estimate just obtained (≈ 20 instructions: a third
+        // of a Newton step) brings the start from ≈ 0.07 to ≈ 0.01 pH units, so that TWO Newton steps reach the FP32 floor
+        float AC2 = Alk - BT * KB * rcp_f32(KB + H) - KW * rcp_f32(H) + H * isd;
+        if (need_silicate) AC2 -= SiT * KSi * rcp_f32(KSi + H);
+        const float b2 = K1 * (AC2 - DIC);
+        const float disc2 = b2 * b2 - 4.0f * AC2 * K1K2 * (AC2 - 2.0f * DIC);
+        const float H2 = (sqrt_f32(disc2) - b2) * rcp_f32(2.0f * AC2);
+        H = (H2 > 1e-12f && H2 < 1e-3f) ? H2 : H;
+#endif
     }
     float c2 = 0.0f;
+    constexpr int STEPS = OBM_CC_F32_STEPS;
 #pragma unroll
-    for (int n = 0; n < 3; n++) {
+    for (int n = 0; n < STEPS; n++) {
         const float icd = rcp_f32((H + K1) * H + K1K2);
         const float a0 = H * H * icd, a1 = K1 * H * icd, a2 = K1K2 * icd;
         const float m = 2.0f * a0 + a1;            // mean number of protons on the carbonate species
@@ -431,7 +466,7 @@ __device__ __forceinline__ double presolve_f32(const Constants& c, const Totals&
             gp -= SiT * qSi;
         }
         const float igp = rcp_f32(gp);
-        if (n == 2) {  // g″ at the last FP32 iterate (≲ 10⁻³ from the root: C to three digits)
+        if (n == STEPS - 1) {  // g″ at the last FP32 iterate (≲ 10⁻³ from the root: C to three digits)
             const float v = 2.0f * a0 * (2.0f - m) + a1 * (1.0f - m);  // ∂ₓ m
             float gpp = DIC * (a1 * (1.0f - m) * (1.0f - m) + 2.0f * a2 * m * m - (a1 + 2.0f * a2) * v) - BT * qB * (1.0f - 2.0f * rB)
                         + (oh - hf) - ST * qS * (1.0f - 2.0f * rS) - FT * qF * (1.0f - 2.0f * rF);
