@@ -690,6 +690,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling sub-record of a multi-GPU run")
+    ap.add_argument("--e2e-balance-threshold", type=float, default=1.05,
+                    help="re-share the rows when the slowest rank's equal-slab stage takes more than this × the fastest's")
     ap.add_argument("--no-e2e-balance", action="store_true",
                     help="multi-GPU e2e leg: keep equal slabs (default: re-share the rows by each rank's measured host-link rate)")
     ap.add_argument("--no-inventory", action="store_true")
@@ -873,7 +875,7 @@ def main():
             times = [x.item() for x in allms]
             nyg = rows_info[2]
             ranges = slab_ranges_by_rate(nyg, [1.0 / x for x in times], minimum=max(1, min(8, nyg // (2 * world))))
-            if max(times) > 1.05 * min(times):
+            if max(times) > args.e2e_balance_threshold * min(times):
                 equal = {"value": e2e_cells * k / (ems * 1e-3) / 1e9, "ms_per_step_per_rank": [round(x / k, 2) for x in times],
                          "rows_per_rank": nyg // world}
                 del hs

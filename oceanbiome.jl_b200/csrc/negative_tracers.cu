@@ -14,6 +14,8 @@
 // them with value·t/t, i.e. value up to 1 ulp of rounding noise): half the HBM traffic in the common case.
 #include <string.h>
 
+#include <atomic>
+
 #include "carbon_chemistry.cuh"
 #include "obm_common.cuh"
 
@@ -102,6 +104,7 @@ struct ScaleOmegaArgs {
     double *Omega, *Hst;
     int iterations;
     double H_init;
+    const cc::LevelTables* levels;  // OBM_SN_LEVEL == 2: per-level tables of this launch's grid in global memory, or nullptr
 };
 
 #ifndef OBM_SN_ASYNC
@@ -120,6 +123,17 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src) {
 #ifndef OBM_SN_LEVEL
 #define OBM_SN_LEVEL 0
 #endif
+// Per-level tables in global memory (OBM_SN_LEVEL == 2).  Static storage — the C ABI hands the library no workspace — as a
+// ring: every launch takes the next slot, so launches in flight on different streams with different grids do not share
+// one (up to LEVEL_RING of them; launches on the same grid write identical values anyway).
+constexpr int LEVEL_RING = 8;
+constexpr int LEVEL_MAX = 512;  // deeper grids use the direct form
+__device__ cc::LevelTables g_level_tables[LEVEL_RING][LEVEL_MAX];
+__global__ void __launch_bounds__(64) level_tables_kernel(cc::LevelTables* out, const double* zc) {
+    // the same pressure expression as the cells of this level evaluate (compute_calcite_saturation.jl:27)
+    cc::fill_level_entry(out[blockIdx.x], fabs(zc[blockIdx.x]) * 9.80665 * 1026.0 / 100000.0, threadIdx.x);
+}
+
 __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_calcite_kernel(const __grid_constant__ ScaleOmegaArgs a) {
     extern __shared__ double sm[];  // [ntracers][SN_BLOCK]
     int i = 0, j = 0, k = 0;
@@ -138,7 +152,12 @@ __global__ void __launch_bounds__(SN_BLOCK, OBM_SN_MIN_BLOCKS) scale_negative_ca
         for (int t = 0; t < a.s.ntracers; t++) cp_async8(mine + t * SN_BLOCK, a.s.tracers[t] + idx);
     asm volatile("cp.async.commit_group;" ::: "memory");
 #endif
-#if OBM_SN_LEVEL
+#if OBM_SN_LEVEL == 2
+    // the block's z-level (blockIdx.z) fixes the pressure: its TEOS-10 and pressure-correction tables come from a table
+    // of all levels that a 3 µs launch built just before this one (level_tables_kernel) — block-uniform addresses, read
+    // through L1 like constants, no shared memory and no barrier
+    const cc::LevelTables* lvl = a.levels ? a.levels + blockIdx.z : nullptr;
+#elif OBM_SN_LEVEL
     // the block's z-level (blockIdx.z) fixes the pressure: its TEOS-10 and pressure-correction tables, built once
     __shared__ cc::LevelTables level;
     cc::fill_level_entry(level, fabs(a.s.d.zc[blockIdx.z]) * 9.80665 * 1026.0 / 100000.0, threadIdx.x);
@@ -344,6 +363,23 @@ extern "C" int obm_scale_negative_tracers_calcite_saturation(const obm_grid* gri
     a.iterations = (p && p->newton_iterations > 0) ? p->newton_iterations : 12;
     a.H_init = pow(10.0, -((p && p->initial_pH_guess > 0) ? p->initial_pH_guess : 8.0));
     const size_t smem = (size_t)ntracers * SN_BLOCK * sizeof(double);
+    a.levels = nullptr;
+#if OBM_SN_LEVEL == 2
+    if (a.s.d.Nz <= LEVEL_MAX) {
+        static cc::LevelTables* base = [] {
+            void* q = nullptr;
+            return cudaGetSymbolAddress(&q, g_level_tables) == cudaSuccess ? (cc::LevelTables*)q : nullptr;
+        }();
+        static std::atomic<unsigned> next{0};
+        if (base) {
+            cc::LevelTables* slot = base + (size_t)(next.fetch_add(1u) % LEVEL_RING) * LEVEL_MAX;
+            level_tables_kernel<<<a.s.d.Nz, 64, 0, (cudaStream_t)stream>>>(slot, a.s.d.zc);
+            rc = launch_status("level_tables_kernel");
+            if (rc) return rc;
+            a.levels = slot;
+        }
+    }
+#endif
     scale_negative_calcite_kernel<<<cell_grid(a.s.d, SN_BLOCK), SN_BLOCK, smem, (cudaStream_t)stream>>>(a);
     return launch_status("scale_negative_calcite_kernel");
 }
