@@ -100,8 +100,9 @@ def config_dict(name, world, scaling):
                    if small else "inputs larger than L2 (no flush needed)"),
             "state": "static synthetic fields (splitmix64, seed 20260117), all positive: the negative-scaling pass reads every "
                      "scaled tracer and rewrites none",
-            "carbonate_solve": ("Newton in ln[H+] started every step from the analytic root of the carbonate-alkalinity quadratic "
-                                "(no stored [H+]: warm start disabled for the static state)" if cfg["model"] in ("pisces", "carbon") else None)}
+            "carbonate_solve": ("cold every step (no stored [H+]: warm start disabled for the static state): carbonate-alkalinity "
+                                "quadratic + 3 Newton steps in ln[H+] in FP32, then FP64 Newton steps (one for sea water) with the "
+                                "second-order error term removed" if cfg["model"] in ("pisces", "carbon") else None)}
 
 
 class Workload:

@@ -139,3 +139,37 @@ def test_euphotic_depth_and_mixed_layer_means(cuda, oracle):
     assert rel(og.interior(zeu.data.cpu().numpy()), og.interior(zo)) <= RTOL_TENDENCY
     assert rel(og.interior(mean.data.cpu().numpy()), og.interior(mo)) <= RTOL_TENDENCY
     assert og.interior(zo)[0, 0, 0] == og.zc_parent[og.Hz - 1]
+
+
+@pytest.mark.parametrize("Nz", [1, 3, 5, 31, 35, 97])
+def test_scans_at_depths_that_do_not_fill_a_lane_group(cuda, oracle, Nz):
+    """The scans give every lane four consecutive levels of a 32-level z-tile (r04): level counts that leave the last
+    group of four, the last tile, or both partly empty — and a single level — for the two-band sum scan, the N-band
+    product scan and the fused column diagnostics, on 37 × 3 columns (the column tile is ragged too)."""
+    grid = ob.RectilinearGrid(size=(37, 3, Nz), x=(0, 37), y=(0, 3), z=lambda k: -6.0 * Nz * (1 - ((k - 1) / Nz) ** 1.3), device=cuda)
+    dev, host, og = synthetic_state(grid, ["P", "PChl", "DChl"], {"P": (0.005, 2.0, True), "PChl": (0.001, 1.0, True), "DChl": (0.001, 1.0, True)})
+    sdev = ob.Field2D(grid, "sPAR")
+    synthetic.fill_torch(sdev, "sPAR", 10.0, 300.0)
+    par = ob.TwoBandPhotosyntheticallyActiveRadiation(grid=grid, surface_PAR=sdev)
+    par.update_biogeochemical_state(M(grid, dev))
+    want = oracle.par_twoband(og, par.c_params(), host["P"], sdev.data.cpu().numpy())
+    assert rel(og.interior(par.field.data.cpu().numpy()), og.interior(want)) <= RTOL_TENDENCY
+    m = ob.MultiBandPhotosyntheticallyActiveRadiation(grid=grid, surface_PAR=83.0)
+
+    class B:
+        def chlorophyll(self, model):
+            return model.tracers["PChl"], model.tracers["DChl"], 1.0
+    zmxl, zeu, mean = ob.Field2D(grid), ob.Field2D(grid), ob.Field2D(grid)
+    synthetic.fill_torch(zmxl, "zmxl", -5.0 * Nz, -0.5)
+    for column_state in (None, (zmxl, 1 / 1000, zeu, mean)):
+        for f in m.fields.values():
+            f.data.zero_()
+        m.update_biogeochemical_state(M(grid, dev, B()), column_state=column_state)
+        bo, to = oracle.par_multiband(og, m.c_params(), host["PChl"], host["DChl"], 1.0, 83.0)
+        for n, name in enumerate(m.field_names):
+            assert rel(og.interior(m.fields[name].data.cpu().numpy()), og.interior(bo[n])) <= RTOL_TENDENCY
+        assert rel(og.interior(m.total.data.cpu().numpy()), og.interior(to)) <= RTOL_TENDENCY
+    PARh = m.total.data.cpu().numpy()
+    zo, mo = oracle.euphotic_depth(og, PARh), oracle.mixed_layer_mean(og, zmxl.data.cpu().numpy(), PARh)
+    assert rel(og.interior(zeu.data.cpu().numpy()), og.interior(zo)) <= RTOL_TENDENCY
+    assert rel(og.interior(mean.data.cpu().numpy()), og.interior(mo)) <= RTOL_TENDENCY
