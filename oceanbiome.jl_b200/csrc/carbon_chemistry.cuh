@@ -35,6 +35,9 @@ namespace cc {
 #ifndef OBM_CC_LOG
 #define OBM_CC_LOG 1
 #endif
+#ifndef OBM_CC_KSP_BATCH
+#define OBM_CC_KSP_BATCH 1  // the solubility product's exp in the same branch-free block as the equilibrium constants' (prepare())
+#endif
 #ifndef OBM_CC_LOG1M
 #define OBM_CC_LOG1M 0  // 1: ln(1 − 0.001005 S) as a 12-term series for S ≤ 50 (see constants())
 #endif
@@ -188,6 +191,22 @@ __device__ __forceinline__ double ln_pc(double a0, double a1, double a2, double 
     return (-dV + 0.5 * dk * P) * P * inv_RT;
 }
 
+// exponent of KSP calcite — equilibrium_constants.jl:754-764, :789-810 (the log10(T) in a "ln K" is the reference's, :758)
+template <bool HAS_P>
+__device__ __forceinline__ double KSP_calcite_exponent(double T, double S, double sqS, double logT, double P, const LevelTables* lvl) {
+    constexpr double LN10 = 2.302585092994045684;
+    const double iT = rcp_fast(T);
+    const double therm = KD(-171.9065) + KD(-0.077993) * T + KD(2839.319) * iT + KD(71.595) * (logT * KD(1.0 / LN10));
+    const double sea = ((KD(-0.77712) + KD(0.0028426) * T + KD(178.34) * iT) * sqS + KD(-0.07711) * S + KD(0.0041249) * (S * sqS));
+    double e = (therm + sea) * KD(LN10);
+    if (HAS_P && lvl != nullptr) {
+        const double Tc = T - KD(273.15);
+        e += ln_pc_level(lvl, LVL_KSP, Tc, Tc * Tc, iT);
+    } else if (HAS_P)
+        e += ln_pc(KD(-48.76), KD(0.5304), -0.0, KD(-0.01176), KD(0.0003692), T - KD(273.15), P, iT * KD(1.0 / 83.14472));
+    return e;
+}
+
 struct Constants {
     double K1, K2, KB, KW, KS, KF, KP1, KP2, KP3, KSi;
     double Tk, Is, sqrtS, logT;
@@ -197,7 +216,8 @@ struct Constants {
 // all equilibrium constants of carbon_chemistry.jl:140-149 (defaults of :66-87)
 template <bool HAS_P>
 __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool need_phosphate, bool need_silicate,
-                                          Constants& c, const LevelTables* lvl = nullptr) {
+                                          Constants& c, const LevelTables* lvl = nullptr, bool with_KSP = false,
+                                          double* KSP_out = nullptr) {
     constexpr double LN10 = 2.302585092994045684;
     const double T = Tc_in + KD(273.15);
     const double invT = rcp_fast(T);
@@ -271,6 +291,8 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     const double eSi = KD(117.385) + KD(-8904.2) * invT + KD(-19.334) * logT + (KD(3.5913) + KD(-458.79) * invT) * sqIs
                        + (KD(-1.5998) + KD(188.74) * invT) * Is + (KD(0.07871) + KD(-12.1652) * invT) * (Is * Is) + logS1;
     c.KSi = 1.0;
+    // (the calcite solubility product rides in the same batch when the caller wants it: its exponent needs T, S, √S, ln T only)
+    const double eK = with_KSP ? KSP_calcite_exponent<HAS_P>(T, S, sqS, logT, P, lvl) : 0.0;
 #if OBM_CC_EXP >= 2 && OBM_CC_BATCH
     // The kernel is bound by the LATENCY of dependent FP64 chains at 6 – 8 warps per scheduler (ncu, r3a: issue 66 %, FP64
     // pipe 62 %, neither saturated), and a guarded exp is its own basic block: six serial Horner chains.  Branch-free in
@@ -283,11 +305,15 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     c.KS = cexp_unguarded(eS);
     c.KF = cexp_unguarded(eF);
     if (need_silicate) c.KSi = cexp_unguarded(eSi);
+    double KSPv = 0.0;
+    if (with_KSP) KSPv = cexp_unguarded(eK);
     if (!(exp_in_range(e1) & exp_in_range(e2) & exp_in_range(eB) & exp_in_range(eW) & exp_in_range(eS) & exp_in_range(eF)
-          & (!need_silicate | exp_in_range(eSi)))) {
+          & (!need_silicate | exp_in_range(eSi)) & (!with_KSP | exp_in_range(eK)))) {
         c.K1 = exp(e1); c.K2 = exp(e2); c.KB = exp(eB); c.KW = exp(eW); c.KS = exp(eS); c.KF = exp(eF);
         if (need_silicate) c.KSi = exp(eSi);
+        if (with_KSP) KSPv = exp(eK);
     }
+    if (with_KSP) *KSP_out = KSPv;
 #else
     if (need_silicate) c.KSi = cexp(eSi);
     c.K1 = cexp(e1);
@@ -296,6 +322,7 @@ __device__ __forceinline__ void constants(double Tc_in, double S, double P, bool
     c.KW = cexp(eW);
     c.KS = cexp(eS);
     c.KF = cexp(eF);
+    if (with_KSP) *KSP_out = cexp(eK);
 #endif
     c.KP1 = c.KP2 = c.KP3 = 1.0;
     if (need_phosphate) {  // KP1-3 :523-529, :558-651
@@ -595,17 +622,7 @@ __device__ __forceinline__ double K0(double T, double logT, double S) {
 // KSP calcite — equilibrium_constants.jl:754-764, :789-810 (the log10(T) in a "ln K" is the reference's, :758)
 template <bool HAS_P>
 __device__ __forceinline__ double KSP_calcite(double T, double S, double sqS, double logT, double P, const LevelTables* lvl = nullptr) {
-    constexpr double LN10 = 2.302585092994045684;
-    const double iT = rcp_fast(T);
-    const double therm = KD(-171.9065) + KD(-0.077993) * T + KD(2839.319) * iT + KD(71.595) * (logT * KD(1.0 / LN10));
-    const double sea = ((KD(-0.77712) + KD(0.0028426) * T + KD(178.34) * iT) * sqS + KD(-0.07711) * S + KD(0.0041249) * (S * sqS));
-    double e = (therm + sea) * KD(LN10);
-    if (HAS_P && lvl != nullptr) {
-        const double Tc = T - KD(273.15);
-        e += ln_pc_level(lvl, LVL_KSP, Tc, Tc * Tc, iT);
-    } else if (HAS_P)
-        e += ln_pc(KD(-48.76), KD(0.5304), -0.0, KD(-0.01176), KD(0.0003692), T - KD(273.15), P, iT * KD(1.0 / 83.14472));
-    return cexp(e);
+    return cexp(KSP_calcite_exponent<HAS_P>(T, S, sqS, logT, P, lvl));
 }
 
 // Everything of the call that depends on (T, S, P) only: density, the equilibrium constants, the S-proportional totals —
@@ -624,7 +641,13 @@ __device__ __forceinline__ void prepare(Prepared& q, bool calcite_path, double T
     // (calcite_concentration.jl:13) — reproduced as found (SURVEY App. A bug 4)
     const double rho = (HAS_P && lvl != nullptr) ? teos10_rho_level(T, S, lvl->rho)
                                                  : teos10_rho(T, S, HAS_P ? P : (calcite_path ? 0.0 : 1.0));
+    q.KSP = 0.0;
+#if OBM_CC_KSP_BATCH
+    constants<HAS_P>(T, S, P, has_phos, has_sil, q.c, lvl, with_KSP, &q.KSP);
+#else
     constants<HAS_P>(T, S, P, has_phos, has_sil, q.c, lvl);
+    if (with_KSP) q.KSP = KSP_calcite<HAS_P>(q.c.Tk, S, q.c.sqrtS, q.c.logT, P, lvl);
+#endif
     q.scale = KD(1e-3) * rcp_fast(rho);
     q.t.boron = KD(0.000232 / 10.811) * S * KD(1.0 / 1.80655);
     q.t.sulfate = KD(0.14 / 96.06) * S * KD(1.0 / 1.80655);
@@ -632,7 +655,6 @@ __device__ __forceinline__ void prepare(Prepared& q, bool calcite_path, double T
     const double sd = 1 + q.t.sulfate * rcp_fast(q.c.KS);
     q.c.isd = rcp_fast(sd);
     q.c.KSsd = q.c.KS * sd;
-    q.KSP = with_KSP ? KSP_calcite<HAS_P>(q.c.Tk, S, q.c.sqrtS, q.c.logT, P, lvl) : 0.0;
 }
 
 // The whole `(p::CarbonChemistry)(; DIC, T, S, Alk, pH, P, output, silicate, phosphate)` call, second half.

@@ -26,6 +26,29 @@ namespace obm {
 #ifndef OBM_LIGHT_EXP
 #define OBM_LIGHT_EXP 4
 #endif
+// OBM_LIGHT_LOG: 1 = the lean logarithm of obm_common.cuh for the four levels of a lane, branch-free in one block with ONE
+// combined range test (a non-positive, subnormal, infinite or NaN argument sends all four through the library log);
+// 0 = the library log.
+#ifndef OBM_LIGHT_LOG
+#define OBM_LIGHT_LOG 1
+#endif
+__device__ __forceinline__ void log4(const double (&x)[4], double (&out)[4]) {
+#if OBM_LIGHT_LOG
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        out[i] = log_unguarded(x[i]);
+        ok &= log_in_range(x[i]);
+    }
+    if (!ok) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) out[i] = log(x[i]);
+    }
+#else
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = log(x[i]);
+#endif
+}
 // OBM_PAR_SCAN4: four levels per lane in the scans (see par_multiband_kernel): 3-band PAR 0.392 → 0.350 ms per 16.8 M cells
 // (profiles/r04_kernel_variants.txt); 0 restores one level per lane and a 5-step scan per level.
 #ifndef OBM_PAR_SCAN4
@@ -138,7 +161,10 @@ __global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband
         {
             const int q4 = lane & 3, g = lane >> 2;
             const int c = warp * CPW + q4;
-            double pr[4], pb[4], zck[4], w_above[4], w_here[4];
+            double pr[4], pb[4], zck[4], w_above[4], w_here[4], lx[4], lp4[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) lx[i] = tile[4 * g + i][c] * Rcp / r;
+            log4(lx, lp4);  // x^e = exp(e ln x), one logarithm for both bands
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int k = ktop - (4 * g + i);
@@ -147,7 +173,7 @@ __global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband
                 // weights of 2band.jl:20-21 (top level) / :28-29 (the rest)
                 w_above[i] = (live && k < Nz - 1) ? (d.zc[k + 1] - d.zf[k + 1]) : 0.0;
                 w_here[i] = live ? (d.zf[k + 1] - zck[i]) : 0.0;
-                const double lp = log(tile[4 * g + i][c] * Rcp / r);  // x^e = exp(e ln x), one logarithm for both bands
+                const double lp = lp4[i];
                 pr[i] = live ? (er == 0.0 ? 1.0 : lexp(er * lp)) : 0.0;  // x^0 ≡ 1
                 pb[i] = live ? (eb == 0.0 ? 1.0 : lexp(eb * lp)) : 0.0;
             }
@@ -328,15 +354,17 @@ __global__ void __launch_bounds__(TC* NWARP, DIAG ? OBM_PAR_DIAG_BLOCKS : 5) par
         {
             const int q4 = lane & 3, g = lane >> 2;
             const int c = warp * CPW + q4;
-            double lchl[4], dz[4];
+            double lchl[4], dz[4], chl4[4];
             bool live[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) chl4[i] = tile[4 * g + i][c];
+            log4(chl4, lchl);  // Chl^e = exp(e ln Chl): one log shared by all bands
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int k = ktop - (4 * g + i);
                 live[i] = k >= 0;
                 // multi_band.jl:156 (k = Nz: factor zᶜ[Nz], seeded with surface_PAR·division) / :160-161 (Δz)
                 dz[i] = !live[i] ? 0.0 : (k == Nz - 1 ? d.zc[k] : d.zc[k] - d.zc[k + 1]);
-                lchl[i] = log(tile[4 * g + i][c]);  // Chl^e = exp(e ln Chl): one log shared by all bands
             }
             double top = 0.0;
 #pragma unroll
