@@ -72,6 +72,24 @@ __device__ __forceinline__ double lexp(double x) {
 #endif
 }
 
+// OBM_LIGHT_EXP_BATCH (with the table exp): the exps of a lane's four levels run unclamped, with ONE combined range test
+// (an integer compare per argument instead of the clamp's two FP64 compares and two 64-bit selects); a lane with an
+// argument outside |x| < 700 — Chl = 0 (ln 0 = −Inf), a level below the bottom, NaN — redoes its four levels with the
+// clamped form: same results, the cold branch is out of the way of the other 99.9 %.
+// Timed (profiles/r04_kernel_variants.txt, visit r4l): +2.5 % on the 3-band scan, +7 % on the two-band one — the fallback's live values
+// cost 16 – 48 B more stack than the clamps' selects cost issue slots — so it is OFF; kept as a build option.
+#ifndef OBM_LIGHT_EXP_BATCH
+#define OBM_LIGHT_EXP_BATCH 0
+#endif
+__device__ __forceinline__ double lexp_try(double x, bool& ok) {
+#if OBM_LIGHT_EXP_BATCH
+    ok &= exp_in_range(x);
+    return exp_table(x);
+#else
+    return lexp(x);
+#endif
+}
+
 constexpr int TC = 32;        // columns per block tile
 constexpr int TZ = 32;        // levels per z-tile (= warp width)
 constexpr int NWARP = 8;      // warps per block
@@ -162,6 +180,7 @@ __global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband
             const int q4 = lane & 3, g = lane >> 2;
             const int c = warp * CPW + q4;
             double pr[4], pb[4], zck[4], w_above[4], w_here[4], lx[4], lp4[4];
+            bool live4[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) lx[i] = tile[4 * g + i][c] * Rcp / r;
             log4(lx, lp4);  // x^e = exp(e ln x), one logarithm for both bands
@@ -173,9 +192,22 @@ __global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband
                 // weights of 2band.jl:20-21 (top level) / :28-29 (the rest)
                 w_above[i] = (live && k < Nz - 1) ? (d.zc[k + 1] - d.zf[k + 1]) : 0.0;
                 w_here[i] = live ? (d.zf[k + 1] - zck[i]) : 0.0;
-                const double lp = lp4[i];
-                pr[i] = live ? (er == 0.0 ? 1.0 : lexp(er * lp)) : 0.0;  // x^0 ≡ 1
-                pb[i] = live ? (eb == 0.0 ? 1.0 : lexp(eb * lp)) : 0.0;
+                live4[i] = live;
+            }
+            {
+                bool ok = true;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    pr[i] = live4[i] ? (er == 0.0 ? 1.0 : lexp_try(er * lp4[i], ok)) : 0.0;  // x^0 ≡ 1
+                    pb[i] = live4[i] ? (eb == 0.0 ? 1.0 : lexp_try(eb * lp4[i], ok)) : 0.0;
+                }
+                if (!ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        pr[i] = live4[i] ? (er == 0.0 ? 1.0 : lexp(er * lp4[i])) : 0.0;
+                        pb[i] = live4[i] ? (eb == 0.0 ? 1.0 : lexp(eb * lp4[i])) : 0.0;
+                    }
+                }
             }
             double pr_up = __shfl_up_sync(0xffffffffu, pr[3], 4);
             double pb_up = __shfl_up_sync(0xffffffffu, pb[3], 4);
@@ -201,13 +233,24 @@ __global__ void __launch_bounds__(TC* NWARP, OBM_PAR_TWOBAND_BLOCKS) par_twoband
             if (g == 0) exr = exb = 0.0;
             const double base_r = carry_r[0] + exr, base_b = carry_b[0] + exb;
             const double par0 = col_par0[c];
-            double ir3 = 0.0, ib3 = 0.0;
+            const double ir3 = base_r + sr[3], ib3 = base_b + sb[3];
+            {
+                bool ok = true;
+                double par4[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double ir = base_r + sr[i], ib = base_b + sb[i];
-                tile[4 * g + i][c] = par0 * (lexp(kr * zck[i] - xr * ir) + lexp(kb * zck[i] - xb * ib)) / 2;  // in place
-                ir3 = ir;
-                ib3 = ib;
+                for (int i = 0; i < 4; i++) {
+                    const double ir = base_r + sr[i], ib = base_b + sb[i];
+                    par4[i] = par0 * (lexp_try(kr * zck[i] - xr * ir, ok) + lexp_try(kb * zck[i] - xb * ib, ok)) / 2;
+                }
+                if (!ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double ir = base_r + sr[i], ib = base_b + sb[i];
+                        par4[i] = par0 * (lexp(kr * zck[i] - xr * ir) + lexp(kb * zck[i] - xb * ib)) / 2;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) tile[4 * g + i][c] = par4[i];  // in place
             }
             carry_r[0] = __shfl_sync(0xffffffffu, ir3, 28 + q4);
             carry_b[0] = __shfl_sync(0xffffffffu, ib3, 28 + q4);
@@ -372,10 +415,18 @@ __global__ void __launch_bounds__(TC* NWARP, DIAG ? OBM_PAR_DIAG_BLOCKS : 5) par
                 const double kw = a.m.water_attenuation_coefficient[n], e = a.m.chlorophyll_exponent[n];
                 const double chi = a.m.chlorophyll_attenuation_coefficient[n];
                 double t[4];
+                bool ok = true;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
-                    const double chle = e == 0.0 ? 1.0 : lexp(e * lchl[i]);  // x^0 ≡ 1 (also for x = 0)
-                    t[i] = live[i] ? lexp(dz[i] * (kw + chi * chle)) : 1.0;
+                    const double chle = e == 0.0 ? 1.0 : lexp_try(e * lchl[i], ok);  // x^0 ≡ 1 (also for x = 0)
+                    t[i] = live[i] ? lexp_try(dz[i] * (kw + chi * chle), ok) : 1.0;
+                }
+                if (!ok) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const double chle = e == 0.0 ? 1.0 : lexp(e * lchl[i]);
+                        t[i] = live[i] ? lexp(dz[i] * (kw + chi * chle)) : 1.0;
+                    }
                 }
                 if (ktop == Nz - 1 && g == 0) t[0] = col_par0[c] * a.m.surface_PAR_division[n] * t[0];
                 const double p1 = t[0] * t[1], p2 = p1 * t[2], p3 = p2 * t[3];

@@ -36,19 +36,22 @@ struct ScaleArgs {
 // STAGED: the values are already in `mine` (the caller's cp.async copies have landed).
 template <bool STAGED = false>
 __device__ __forceinline__ void scale_cell(const ScaleArgs& a, double* mine, long long idx) {
-    bool touched = false;  // some value is negative or non-finite: only then can any group have p ≠ t
+    // some value is negative or non-finite: only then can any group have p ≠ t.
+    // negative, −0.0, ±Inf or NaN ⇔ sign bit set or exponent all ones ⇔ high word ≥ 0x7ff00000 as unsigned (the FP64 form
+    // `!(v >= 0 && v < Inf)` compiled to ≈ 14 integer instructions per value) — and the largest high word decides for
+    // all of them: a running unsigned maximum (three-input VIMNMX3: one instruction per two values) and ONE compare.
+    // −0.0 is flagged too; its group then runs with t / p = 1 and writes +0.0, as the reference's `ifelse(…, 0)` does.
+    unsigned highest = 0u;
     for (int t = 0; t < a.ntracers; t++) {
-        // negative, −0.0, ±Inf or NaN ⇔ sign bit set or exponent all ones ⇔ high word ≥ 0x7ff00000 as unsigned: one
-        // integer compare (the FP64 form `!(v >= 0 && v < Inf)` compiled to ≈ 14 integer instructions per value).
-        // −0.0 is flagged too; its group then runs with t / p = 1 and writes +0.0, as the reference's `ifelse(…, 0)` does.
         if (STAGED) {
-            touched |= reinterpret_cast<const unsigned*>(mine + t * SN_BLOCK)[1] >= 0x7ff00000u;  // the high word alone
+            highest = max(highest, reinterpret_cast<const unsigned*>(mine + t * SN_BLOCK)[1]);  // the high word alone
         } else {
             const double v = a.tracers[t][idx];
             mine[t * SN_BLOCK] = v;
-            touched |= (unsigned)__double2hiint(v) >= 0x7ff00000u;
+            highest = max(highest, (unsigned)__double2hiint(v));
         }
     }
+    const bool touched = highest >= 0x7ff00000u;
     if (!__any_sync(__activemask(), touched)) return;  // warp-uniform: the common case reads its cells and leaves
     unsigned dirty = 0;  // bit t ⇔ tracer t was rescaled and must be written back
     for (int q = 0; q < a.ngroups; q++) {
