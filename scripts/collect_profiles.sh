@@ -58,4 +58,6 @@ json.dump(t, open("profiles/traffic.json", "w"), indent=1)
 PY
 { echo "# $R — executed instructions per cell by SASS opcode (scripts/ncu_opcodes.py on the full captures above; 134 M cells)"
   for K in pisces_tendency scale_negative_calcite par_multiband; do echo "===== $K"; python scripts/ncu_opcodes.py gpurun_out/prof_pisces_c4_$K.ncu-rep 134217728; done; } > profiles/${R}_opcodes_pisces_c4.txt
+{ echo "# $R — executed warp instructions per cell by the source function / line they were written in (scripts/ncu_lines.py on the full captures above)"
+  for K in scale_negative_calcite par_multiband pisces_tendency; do echo "===== $K"; python scripts/ncu_lines.py gpurun_out/prof_pisces_c4_$K.ncu-rep 134217728 20; done; } > profiles/${R}_functions_pisces_c4.txt
 echo "profiles/${R}_* refreshed"
