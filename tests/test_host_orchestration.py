@@ -237,3 +237,22 @@ def test_pisces_per_tracer_call_form_is_one_fused_launch(lib):
         u("Q", device="cpu")
     with pytest.raises(KeyError):
         u("P", device="cpu", Q=1.0)
+
+
+def test_model_latitude_goes_through_the_per_row_entry_point(lib):
+    """`latitude = ModelLatitude()` (PISCES/common.jl:27-28) on a grid with its own latitude: same hooks, same order, the
+    tendencies through `obm_pisces_tendencies_rows` with a [3][Ny] table; a prescribed latitude keeps the scalar entry point."""
+    g = ob.LatitudeLongitudeGrid(size=(4, 6, 8), longitude=(0, 4), latitude=(-30, 30), z=(-80, 0), device="cpu")
+    bgc = ob.PISCES(g, latitude=ob.ModelLatitude(), scale_negatives=True)
+    model = ob.BiogeochemicalModel(g, bgc)
+    model.update_state()
+    assert lib.calls == ["obm_scale_negative_tracers_calcite_saturation", "obm_par_multiband_column_state"]
+    lib.calls.clear()
+    bgc.update_tendencies(model)
+    assert lib.calls == ["obm_pisces_tendencies_rows"]
+    assert tuple(bgc.underlying_biogeochemistry._row_table.shape) == (3, 6)
+    lib.calls.clear()
+    bgc2 = ob.PISCES(grid3(), latitude=ob.PrescribedLatitude(-12.0))
+    m2 = ob.BiogeochemicalModel(bgc2.underlying_biogeochemistry.grid, bgc2)
+    bgc2.update_tendencies(m2)
+    assert lib.calls == ["obm_pisces_tendencies"]
