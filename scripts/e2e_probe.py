@@ -6,6 +6,7 @@ every rank.  Variants:
   dma:<n> / sm:<n> / sm_d2h:<n>   HostStagedStage with n pipeline slabs and that copy engine
   copies:<n>                      the stage's slab copies alone (no kernels in between), DMA
   h2d:<n> / d2h:<n>               one direction of those copies alone
+  wc:<n>                          the stage with its H2D sources in write-combined pinned memory
   flat:<n>                        the same bytes as contiguous chunks (one cudaMemcpyAsync per field and slab) — what a
                                   slab-major host layout would give
 usage: torchrun … scripts/e2e_probe.py [variant …]"""
@@ -106,13 +107,37 @@ def flat(st, n):
     return fn
 
 
+def write_combined_copies(tensors):
+    """The same host arrays in pinned WRITE-COMBINED memory (cudaHostAllocWriteCombined: device reads of it are not snooped
+    through the CPU caches) — for the H2D sources only; the CPU must not read such memory back at speed."""
+    import ctypes
+    import numpy as np
+    rt = ctypes.CDLL("libcudart.so.12")
+    assert rt.cudaSetDevice(local) == 0
+    out, keep = {}, []
+    for n, t in tensors.items():
+        nbytes = t.numel() * 8
+        p = ctypes.c_void_p()
+        rc = rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(nbytes), ctypes.c_uint(0x04 | 0x01))  # write-combined | portable
+        assert rc == 0, f"cudaHostAlloc → {rc}"
+        a = np.ctypeslib.as_array((ctypes.c_double * t.numel()).from_address(p.value)).reshape(tuple(t.shape))
+        a[...] = t.numpy()
+        out[n] = torch.from_numpy(a)
+        keep.append(p)
+    return out, keep
+
+
 specs = sys.argv[1:] or ["dma:8", "dma:1", "dma:2", "dma:4", "dma:16", "copies:8", "copies:2", "h2d:8", "d2h:8", "flat:8", "flat:1",
                          "sm:8", "sm_d2h:8", "dma:8"]
 for spec in specs:
     kind, n = spec.split(":")
     n = int(n)
     try:
-        if kind in ("dma", "sm", "sm_h2d", "sm_d2h"):
+        if kind == "wc":
+            wc, _keep = write_combined_copies(bufs[0])
+            st = HostStagedStage(w.model, nslabs=n, host_buffers=(wc, bufs[1]))
+            fn = st.step
+        elif kind in ("dma", "sm", "sm_h2d", "sm_d2h"):
             st = HostStagedStage(w.model, nslabs=n, copy_engine=kind, host_buffers=bufs)
             fn = st.step
         else:
