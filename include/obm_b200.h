@@ -672,6 +672,32 @@ int obm_npd_tendencies_substep(const obm_grid* grid, const obm_npd_params* p, in
                                int has_zeta, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (f-3) The whole RUN of a box-model ensemble in ONE launch — `run!(simulation)` over
+ * src/BoxModel/boxmodel.jl:92-110 + timesteppers.jl:30-93 for n independent boxes laid along x
+ * (grid->Ny = grid->Nz = 1).  Boxes do not interact, so a thread integrates its box through
+ * `nsteps` time steps of `nstages` stages each (RK3: γ = 8/15, 5/12, 3/4, ζ = NaN, −17/60,
+ * −5/12; forward Euler: one stage, γ = 1, ζ = NaN — NaN marks a stage without a ζ term); a
+ * stage is exactly obm_npd_tendencies_substep (store_Gn = accumulate = 0) on values held on
+ * chip.  Prescribed series come from host-tabulated DEVICE tables with one row per global
+ * stage r = step·nstages + stage, row r holding what `update_state!` leaves AFTER that stage
+ * (the stage itself sees row r − 1, the very first one the values found in the fields):
+ * `PAR_table` [nsteps·nstages][PAR_per_box ? n : 1], optional `T_table` likewise for the
+ * temperature tracer.  On return tracers, G⁻, the PAR field and T hold what nsteps calls of
+ * time_step! would have left; `snapshots[t]` (tracer order, nullable entries or table)
+ * receives tracer t of every box after every `output_every`-th step: [nsteps/output_every][n].
+ * Results are those of the per-stage launches bit for bit (tests/test_gpu_box_model.py); the
+ * reference's benchmark/box_model.jl (NPZD box, 1000 RK3 steps: 23.5 ms on its CPU for ONE
+ * box) takes one launch for the whole ensemble.  Every tracer the tendencies read must be
+ * stepped (Gm[t] != NULL) — OBM_ENOTIMPL otherwise: use the per-stage path for prescribed
+ * biogeochemical tracers and for forcings.
+ * ------------------------------------------------------------------------------------ */
+int obm_npd_box_run(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which,
+                    const double* values, double* const* tracers, double* const* Gm, double* PAR,
+                    const double* PAR_table, int PAR_per_box, const double* T_table, int T_per_box,
+                    int nsteps, int nstages, const double* gamma, const double* zeta, double dt,
+                    int output_every, double* const* snapshots, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * (e) Tracer inventory for conservation diagnostics: out[g] = Σ_cells Σ_f sf[g][f]·c_f·V_cell
  * (the user-side sums of test/test_NutrientsPlanktonDetritus.jl:8-21 at scale).  `out` is a
  * DEVICE array of ngroups doubles, overwritten (deterministic two-level reduction; no atomics

@@ -258,6 +258,9 @@ PROTOTYPES = {
     "obm_npd_param_index": (C.c_int, [C.c_char_p]),
     "obm_npd_tendencies_ensemble": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "obm_npd_box_run": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_npd_params), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "obm_pisces_tendencies": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p,
                                         C.POINTER(obm_pisces_fields), C.c_void_p, C.c_int, C.c_void_p]),
     "obm_pisces_tendencies_rows": (C.c_int, [C.POINTER(obm_grid), C.POINTER(obm_pisces_params), C.c_void_p, C.c_void_p,

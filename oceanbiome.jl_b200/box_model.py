@@ -203,11 +203,15 @@ class BoxModel:
 
     # ---- run!(simulation) --------------------------------------------------------------------------------------
     def run(self, dt: float, steps: int, graph: bool = False, output_every: int = 0, output_names=None,
-            output: Optional[SpeedyOutput] = None):
+            output: Optional[SpeedyOutput] = None, device_loop: bool = False):
         """Integrate `steps` time steps.  Returns a dict name → tensor (n_outputs, n_boxes) of snapshots taken
         every `output_every` steps (device-resident).  `output`: a `SpeedyOutput` called at iteration 0 and every
         `output_every` steps like `simulation.callbacks[:output] = Callback(SpeedyOutput(f), IterationInterval(n))`
         (eager mode), and written to disk at the end of the run.
+
+        `device_loop=True` (with `fused_step=True`; NPZD / LOBSTER family, only PAR and T prescribed, no forcing): the
+        WHOLE run is one launch — every thread integrates its box through all stages (`obm_npd_box_run`), the tabulated
+        series and the snapshots never leave the device; bit-identical to `graph=True`.
 
         `graph=True`: prescribed tracers and forcings are tabulated for every stage of the run, uploaded once,
         and ONE captured time step is replayed `steps` times; requires a biogeochemistry whose kernel parameters do
@@ -215,8 +219,10 @@ class BoxModel:
         names = list(output_names or self.prognostic)
         nout = steps // output_every if output_every else 0
         out = {n: torch.empty((nout, self.grid.Nx), dtype=torch.float64, device=self.grid.device) for n in names}
-        if output is not None and graph:
-            raise ValueError("SpeedyOutput is an eager-mode callback; graph=True returns the snapshots as tensors")
+        if output is not None and (graph or device_loop):
+            raise ValueError("SpeedyOutput is an eager-mode callback; graph=True / device_loop=True return the snapshots as tensors")
+        if device_loop:
+            return self._run_device_loop(dt, steps, output_every, names, out)
         if not graph:
             if output is not None and output_every:
                 output(self)  # IterationInterval fires at iteration 0 too
@@ -255,6 +261,38 @@ class BoxModel:
         tabs = {("prescribed", n): table(f) for n, f in self.prescribed_tracers.items()}
         tabs.update({("forcing", n): table(f) for n, f in self.forcing.items() if f is not None and n in self.prognostic})
         return times, tabs
+
+    def _run_device_loop(self, dt, steps, output_every, names, out):
+        u = self.biogeochemistry.underlying_biogeochemistry
+        if not self.fused_step or not hasattr(u, "run_boxes"):
+            raise ValueError("device_loop=True needs fused_step=True and a biogeochemistry with a whole-run launch (NPZD / LOBSTER family)")
+        if any(f is not None for f in self.forcing.values()):
+            raise ValueError("device_loop=True: forcings are not tabulated for the whole-run launch; use graph=True")
+        extra = set(self.prescribed_tracers) - {"PAR", "T"}
+        if extra or "PAR" not in self.prescribed_tracers:
+            raise ValueError(f"device_loop=True prescribes PAR (and optionally T) from tables; got {sorted(self.prescribed_tracers)}")
+        if self._needs_initial_update:
+            self.update_state(compute_tendencies=False)
+            self._needs_initial_update = False
+        stages = self.RK3 if self.timestepper == "RungeKutta3" else ((1.0, None),)
+        times, tabs = self._tabulate(dt, steps)
+        if not times:
+            return out
+        snaps = {n: out[n] for n in names if n in self.prognostic} if output_every else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        T_table = tabs.get(("prescribed", "T"))
+        reads_T = "T" in u.required_biogeochemical_tracers()
+        u.run_boxes(self.grid, self.fields, self.auxiliary_fields, {n: self.Gm[n] for n in self.prognostic}, dt, stages, steps,
+                    tabs[("prescribed", "PAR")], T_table if reads_T else None, output_every, snaps)
+        if T_table is not None and not reads_T:  # a prescribed series nothing reads: leave the field as the per-stage path does
+            self.fields["T"].interior.reshape(-1).copy_(T_table[-1].reshape(-1).expand(self.grid.Nx))
+        e1.record()
+        self.replay_events = (e0, e1)
+        self.clock.time = times[-1]
+        self.clock.iteration += steps
+        self.clock.last_stage_dt = dt * (stages[-1][0] + (stages[-1][1] or 0.0))
+        return out
 
     def _run_graph(self, dt, steps, output_every, names, out):
         if getattr(self.biogeochemistry.underlying_biogeochemistry, "clock_dependent_parameters", False):

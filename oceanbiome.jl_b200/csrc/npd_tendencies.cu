@@ -106,6 +106,9 @@ __device__ __forceinline__ double concentration_limit(int form, double X, double
     return form == OBM_LINEAR ? X / (X + k) : (X * X) / (X * X + k * k);
 }
 
+template <int NUT, int DET>
+__device__ __forceinline__ void npd_cell(const NpdArgs& a, const obm_npd_params& p, long long idx);
+
 template <int NUT, int DET, bool ENSEMBLE>
 __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant__ NpdArgs a) {
     int i, j, k;
@@ -118,7 +121,13 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
 #pragma unroll 1
         for (int v = 0; v < a.nvary; v++) set_param(member, a.which[v], a.values[v * members + m]);
     }
-    const obm_npd_params& p = ENSEMBLE ? member : a.p;
+    npd_cell<NUT, DET>(a, ENSEMBLE ? member : a.p, idx);
+}
+
+// Everything a cell does: one read of its tracers, every tendency delivered (stored, accumulated or stepped) once.
+// `a` may live in the kernel's parameter space (the launches above) or in shared memory (npd_box_run_kernel below).
+template <int NUT, int DET>
+__device__ __forceinline__ void npd_cell(const NpdArgs& a, const obm_npd_params& p, long long idx) {
     constexpr bool HAS_NA = (NUT != OBM_NUT_NUTRIENT);
     constexpr bool TWO_SIZE = (DET == OBM_DET_TWO_PARTICLE || DET == OBM_DET_VARIABLE_REDFIELD);
 
@@ -268,6 +277,126 @@ __global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant
     }
 }
 
+// ---- the whole RUN of a box-model ensemble in one launch (obm_npd_box_run) ----------------------------------------------------
+// Boxes do not talk to each other, so nothing forces a launch per stage: a thread owns a box and integrates it through every
+// stage of every time step.  The stage itself is npd_cell — the code of the fused tendency + substep launch, unchanged —
+// run on a copy of the kernel arguments in shared memory whose field pointers are redirected to the block's staging
+// arrays (one slot per thread and field: tracers, G⁻, PAR, T), so that a stage costs shared-memory traffic and arithmetic
+// only; thread 0 rewrites the stage's (γ, ζ) between two block barriers.  The prescribed series (PAR, T: one value per
+// stage, shared or per box) come from tables the host tabulated, exactly as the CUDA-graph path reads them; snapshots go
+// straight to their device arrays.  Same operations in the same order as a replayed graph of obm_npd_tendencies_substep
+// launches ⇒ the same bits (tests/test_gpu_box_model.py); 1000 RK3 steps of the reference's NPZD box benchmark
+// (benchmark/box_model.jl: 23.5 ms on its CPU) take one launch instead of ≈ 12 000.
+constexpr int RUN_BLOCK = 64;
+constexpr int RUN_MAX_SLOTS = OBM_NPD_MAX_TRACERS + 2 * MAX_REPLICATES;
+struct RunArgs {
+    int nsteps, nstages, ncells, output_every, nslots;
+    double gamma[3], zeta[3];
+    int has_zeta[3];
+    double* PAR_field;              // written back at the end: the state update's last prescribed value
+    const double* PAR_table;        // [nsteps·nstages][PAR_per_box ? ncells : 1]; row r = what the stage AFTER global stage r sees
+    int PAR_per_box;
+    double* T_field;                // nullable (no temperature dependence)
+    const double* T_table;          // nullable: T is then constant over the run
+    int T_per_box;
+    double* snap[RUN_MAX_SLOTS];    // per staged tracer (slot order): [nsteps / output_every][ncells], or nullptr
+};
+
+template <int NUT, int DET, bool ENSEMBLE>
+__global__ void __launch_bounds__(RUN_BLOCK) npd_box_run_kernel(const __grid_constant__ NpdArgs a, const __grid_constant__ RunArgs r) {
+    __shared__ NpdArgs sa;
+    __shared__ double* gU[RUN_MAX_SLOTS];
+    __shared__ double* gM[RUN_MAX_SLOTS];
+    extern __shared__ double stage_mem[];  // U[nslots][RUN_BLOCK], M[nslots][RUN_BLOCK], PAR[RUN_BLOCK], T[RUN_BLOCK]
+    double* U = stage_mem;
+    double* M = U + (size_t)r.nslots * RUN_BLOCK;
+    double* PARs = M + (size_t)r.nslots * RUN_BLOCK;
+    double* Ts = PARs + RUN_BLOCK;
+    const int tid = threadIdx.x;
+    static_assert(sizeof(NpdArgs) % sizeof(double) == 0, "NpdArgs is copied in 8-byte words");
+    for (int w = tid; w < (int)(sizeof(NpdArgs) / sizeof(double)); w += RUN_BLOCK)
+        reinterpret_cast<double*>(&sa)[w] = reinterpret_cast<const double*>(&a)[w];
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;
+#define OBM_STAGE(name)                                                   \
+    if (a.u##name != nullptr) {                                           \
+        gU[s] = a.u##name; gM[s] = a.m##name;                             \
+        sa.name = sa.u##name = U + s * RUN_BLOCK; sa.m##name = M + s * RUN_BLOCK; s++; \
+    }
+        OBM_STAGE(NO3) OBM_STAGE(NH4) OBM_STAGE(Fe) OBM_STAGE(N) OBM_STAGE(P) OBM_STAGE(Z) OBM_STAGE(D) OBM_STAGE(sPOM)
+        OBM_STAGE(bPOM) OBM_STAGE(DOM) OBM_STAGE(sPOC) OBM_STAGE(bPOC) OBM_STAGE(DOC)
+#undef OBM_STAGE
+        for (int q = 0; q < a.nrep; q++) {  // one-way coupled: stepped, never read
+            gU[s] = a.uDIC[q]; gM[s] = a.mDIC[q]; sa.uDIC[q] = U + s * RUN_BLOCK; sa.mDIC[q] = M + s * RUN_BLOCK; s++;
+            gU[s] = a.uAlk[q]; gM[s] = a.mAlk[q]; sa.uAlk[q] = U + s * RUN_BLOCK; sa.mAlk[q] = M + s * RUN_BLOCK; s++;
+        }
+        if (a.uO2 != nullptr) { gU[s] = a.uO2; gM[s] = a.mO2; sa.uO2 = U + s * RUN_BLOCK; sa.mO2 = M + s * RUN_BLOCK; s++; }
+        sa.PAR = PARs;
+        if (a.T != nullptr) sa.T = Ts;
+    }
+    __syncthreads();
+    const int cell = blockIdx.x * RUN_BLOCK + tid;
+    const bool inside = cell < r.ncells;
+    const long long gidx = cell_index(a.d, a.d.i0 + (inside ? cell : 0), a.d.j0, 0);
+    obm_npd_params member;  // dead unless ENSEMBLE
+    if constexpr (ENSEMBLE) {
+        member = a.p;
+        if (inside) {
+#pragma unroll 1
+            for (int v = 0; v < a.nvary; v++) set_param(member, a.which[v], a.values[(long long)v * r.ncells + cell]);
+        }
+    }
+    for (int s = 0; s < r.nslots; s++) {
+        U[s * RUN_BLOCK + tid] = inside ? gU[s][gidx] : 0.0;
+        M[s * RUN_BLOCK + tid] = inside ? gM[s][gidx] : 0.0;
+    }
+    double PARv = inside ? r.PAR_field[gidx] : 0.0;
+    double Tv = (inside && r.T_field != nullptr) ? r.T_field[gidx] : 0.0;
+    long long row = 0;
+    for (int it = 0; it < r.nsteps; it++) {
+#pragma unroll 1
+        for (int st = 0; st < r.nstages; st++) {
+            if (tid == 0) {
+                sa.step.gamma = r.gamma[st];
+                sa.step.zeta = r.zeta[st];
+                sa.step.has_zeta = r.has_zeta[st];
+            }
+            PARs[tid] = PARv;
+            Ts[tid] = Tv;
+            __syncthreads();
+            if constexpr (ENSEMBLE) {
+                // the member's parameters are opaque to the optimiser at every stage, as they are to a per-stage launch:
+                // a parameter-only product hoisted out of this loop would be rounded on its own where the per-stage
+                // kernel contracts it into an FMA — the two paths would drift apart by an ulp
+#define X(name) asm volatile("" : "+d"(member.name));
+                OBM_NPD_DOUBLE_PARAMS(X)
+#undef X
+            }
+            if (inside) npd_cell<NUT, DET>(sa, ENSEMBLE ? member : sa.p, tid);
+            __syncthreads();  // every thread has read this stage's coefficients
+            // what update_state! leaves for the next stage: the prescribed series at the time after this one
+            if (inside) {
+                PARv = r.PAR_table[r.PAR_per_box ? row * r.ncells + cell : row];
+                if (r.T_table != nullptr) Tv = r.T_table[r.T_per_box ? row * r.ncells + cell : row];
+            }
+            row++;
+        }
+        if (r.output_every > 0 && (it + 1) % r.output_every == 0 && inside) {
+            const long long o = (long long)((it + 1) / r.output_every - 1) * r.ncells + cell;
+            for (int s = 0; s < r.nslots; s++)
+                if (r.snap[s] != nullptr) r.snap[s][o] = U[s * RUN_BLOCK + tid];
+        }
+    }
+    if (!inside) return;
+    for (int s = 0; s < r.nslots; s++) {
+        gU[s][gidx] = U[s * RUN_BLOCK + tid];
+        gM[s][gidx] = M[s * RUN_BLOCK + tid];
+    }
+    r.PAR_field[gidx] = PARv;
+    if (r.T_field != nullptr) r.T_field[gidx] = Tv;
+}
+
 // tracer order = required_biogeochemical_tracers (NutrientsPlanktonDetritus.jl:69-74)
 enum Role { R_NO3, R_NH4, R_FE, R_N, R_P, R_Z, R_T, R_D, R_SPOM, R_BPOM, R_DOM, R_SPOC, R_BPOC, R_DOC, R_DIC, R_ALK, R_O2 };
 
@@ -335,6 +464,24 @@ static void launch_nut(const NpdArgs& a, int nut, int det, dim3 blocks, cudaStre
     }
 }
 
+template <int NUT, bool ENSEMBLE>
+static void run_det(const NpdArgs& a, const RunArgs& r, int det, unsigned blocks, size_t smem, cudaStream_t s) {
+    switch (det) {
+        case OBM_DET_NONE: npd_box_run_kernel<NUT, OBM_DET_NONE, ENSEMBLE><<<blocks, RUN_BLOCK, smem, s>>>(a, r); break;
+        case OBM_DET_DETRITUS: npd_box_run_kernel<NUT, OBM_DET_DETRITUS, ENSEMBLE><<<blocks, RUN_BLOCK, smem, s>>>(a, r); break;
+        case OBM_DET_TWO_PARTICLE: npd_box_run_kernel<NUT, OBM_DET_TWO_PARTICLE, ENSEMBLE><<<blocks, RUN_BLOCK, smem, s>>>(a, r); break;
+        default: npd_box_run_kernel<NUT, OBM_DET_VARIABLE_REDFIELD, ENSEMBLE><<<blocks, RUN_BLOCK, smem, s>>>(a, r); break;
+    }
+}
+template <bool ENSEMBLE>
+static void run_nut(const NpdArgs& a, const RunArgs& r, int nut, int det, unsigned blocks, size_t smem, cudaStream_t s) {
+    switch (nut) {
+        case OBM_NUT_NUTRIENT: run_det<OBM_NUT_NUTRIENT, ENSEMBLE>(a, r, det, blocks, smem, s); break;
+        case OBM_NUT_NITRATE_AMMONIA: run_det<OBM_NUT_NITRATE_AMMONIA, ENSEMBLE>(a, r, det, blocks, smem, s); break;
+        default: run_det<OBM_NUT_NITRATE_AMMONIA_IRON, ENSEMBLE>(a, r, det, blocks, smem, s); break;
+    }
+}
+
 }  // namespace obm
 
 using namespace obm;
@@ -359,9 +506,13 @@ struct StepSpec {  // the fused tendency + substep launch; null: tendencies only
     double dt, gamma, zeta;
     int has_zeta, store_gn;
 };
+struct RunSpec {  // obm_npd_box_run: the whole run in one launch
+    RunArgs r;
+    double* const* snapshots;  // per tracer (tracer order), nullable entries / nullable table
+};
 static int npd_launch(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which, const double* values,
                       const double* const* tracers, const double* PAR, double* const* G, int accumulate, void* stream,
-                      bool ensemble, const StepSpec* step = nullptr) {
+                      bool ensemble, const StepSpec* step = nullptr, RunSpec* run = nullptr) {
     OBM_REQUIRE(p != nullptr && tracers != nullptr && (G != nullptr || step != nullptr) && PAR != nullptr, OBM_ENULL,
                 "obm_npd_tendencies: params / tracers / G / PAR is NULL");
     OBM_REQUIRE(step == nullptr || (step->U != nullptr && step->Gm != nullptr), OBM_ENULL,
@@ -431,8 +582,44 @@ static int npd_launch(const obm_grid* grid, const obm_npd_params* p, int nvary, 
         }
     }
     a.nrep = nd;
-    const dim3 blocks = cell_grid(a.d, 256);
     cudaStream_t s = (cudaStream_t)stream;
+    if (run != nullptr) {
+        RunArgs& r = run->r;
+        OBM_REQUIRE(a.d.Ny == 1 && a.d.Nz == 1, OBM_ENOTIMPL, "obm_npd_box_run: boxes lie along x (Ny = Nz = 1), got %d x %d x %d",
+                    a.d.Nx, a.d.Ny, a.d.Nz);
+        r.ncells = a.d.i1 - a.d.i0;
+        // slot order of the kernel's staging (OBM_STAGE there): every tracer the cell READS must be stepped — a prescribed
+        // P or Z would have to come from a table this entry point does not take
+        double* slot[RUN_MAX_SLOTS];
+        int ns = 0;
+#define OBM_SLOT(name)                                                                                                  \
+    if (a.u##name != nullptr) slot[ns++] = a.u##name;                                                                     \
+    else OBM_REQUIRE(a.name == nullptr, OBM_ENOTIMPL, "obm_npd_box_run: tracer " #name " is read but not stepped (prescribed?)");
+        OBM_SLOT(NO3) OBM_SLOT(NH4) OBM_SLOT(Fe) OBM_SLOT(N) OBM_SLOT(P) OBM_SLOT(Z) OBM_SLOT(D) OBM_SLOT(sPOM)
+        OBM_SLOT(bPOM) OBM_SLOT(DOM) OBM_SLOT(sPOC) OBM_SLOT(bPOC) OBM_SLOT(DOC)
+#undef OBM_SLOT
+        for (int q = 0; q < a.nrep; q++) {
+            OBM_REQUIRE(a.uDIC[q] && a.uAlk[q], OBM_ENOTIMPL, "obm_npd_box_run: DIC / Alk replicate %d is not stepped", q);
+            slot[ns++] = a.uDIC[q];
+            slot[ns++] = a.uAlk[q];
+        }
+        if (a.uO2 != nullptr) slot[ns++] = a.uO2;
+        r.nslots = ns;
+        for (int q = 0; q < ns; q++) {
+            r.snap[q] = nullptr;
+            for (int n = 0; n < nt && run->snapshots != nullptr; n++)
+                if (step->U[n] == slot[q]) r.snap[q] = run->snapshots[n];
+        }
+        r.T_field = const_cast<double*>(a.T);
+        OBM_REQUIRE(r.T_table == nullptr || r.T_field != nullptr, OBM_ESIZE,
+                    "obm_npd_box_run: a temperature table for a model without temperature dependence");
+        const unsigned blocks = (unsigned)((r.ncells + RUN_BLOCK - 1) / RUN_BLOCK);
+        const size_t smem = ((size_t)2 * ns + 2) * RUN_BLOCK * sizeof(double);
+        if (ensemble) run_nut<true>(a, r, p->nutrients, p->detritus, blocks, smem, s);
+        else run_nut<false>(a, r, p->nutrients, p->detritus, blocks, smem, s);
+        return launch_status("npd_box_run_kernel");
+    }
+    const dim3 blocks = cell_grid(a.d, 256);
     if (ensemble) launch_nut<true>(a, p->nutrients, p->detritus, blocks, s);
     else launch_nut<false>(a, p->nutrients, p->detritus, blocks, s);
     return launch_status("npd_tendency_kernel");
@@ -456,4 +643,29 @@ extern "C" int obm_npd_tendencies_substep(const obm_grid* grid, const obm_npd_pa
                                           int has_zeta, void* stream) {
     const StepSpec step{tracers, Gm, dt, gamma, zeta, has_zeta, store_Gn};
     return npd_launch(grid, p, nvary, which, values, tracers, PAR, G, accumulate, stream, nvary > 0, &step);
+}
+
+// f-3: every stage of every time step of a box-model ensemble in ONE launch (see include/obm_b200.h)
+extern "C" int obm_npd_box_run(const obm_grid* grid, const obm_npd_params* p, int nvary, const int32_t* which, const double* values,
+                               double* const* tracers, double* const* Gm, double* PAR, const double* PAR_table, int PAR_per_box,
+                               const double* T_table, int T_per_box, int nsteps, int nstages, const double* gamma,
+                               const double* zeta, double dt, int output_every, double* const* snapshots, void* stream) {
+    OBM_REQUIRE(PAR && PAR_table && gamma && zeta, OBM_ENULL, "obm_npd_box_run: PAR / PAR_table / gamma / zeta is NULL");
+    OBM_REQUIRE(nsteps >= 0 && nstages >= 1 && nstages <= 3 && output_every >= 0, OBM_ESIZE,
+                "obm_npd_box_run: nsteps = %d, nstages = %d, output_every = %d", nsteps, nstages, output_every);
+    if (nsteps == 0) return 0;
+    RunSpec run;
+    memset(&run, 0, sizeof(run));
+    RunArgs& r = run.r;
+    r.nsteps = nsteps; r.nstages = nstages; r.output_every = output_every;
+    for (int q = 0; q < nstages; q++) {
+        r.gamma[q] = gamma[q];
+        r.has_zeta[q] = zeta[q] == zeta[q] ? 1 : 0;  // NaN: a stage without a ζ term (the first of RK3, forward Euler)
+        r.zeta[q] = r.has_zeta[q] ? zeta[q] : 0.0;
+    }
+    r.PAR_field = PAR; r.PAR_table = PAR_table; r.PAR_per_box = PAR_per_box ? 1 : 0;
+    r.T_table = T_table; r.T_per_box = T_per_box ? 1 : 0;
+    run.snapshots = snapshots;
+    const StepSpec step{tracers, Gm, dt, gamma[0], 0.0, 0, 0};
+    return npd_launch(grid, p, nvary, which, values, tracers, PAR, nullptr, 0, stream, nvary > 0, &step, &run);
 }

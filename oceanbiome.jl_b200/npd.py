@@ -364,6 +364,47 @@ class NutrientsPlanktonDetritus:
                                             0.0 if zeta is None else float(zeta), int(zeta is not None), s)
         _lib.check(rc, "obm_npd_tendencies_substep")
 
+    def run_boxes(self, grid: RectilinearGrid, tracers: dict, auxiliary_fields: dict, Gm: dict, dt: float, stages, steps: int,
+                  PAR_table: torch.Tensor, T_table: Optional[torch.Tensor] = None, output_every: int = 0,
+                  snapshots: Optional[dict] = None, stream: Optional[int] = None):
+        """f-3: the whole run of a box-model ensemble in ONE launch (`obm_npd_box_run`): `steps` time steps of
+        `stages` = ((γ, ζ or None), …), each stage exactly `compute_tendencies_and_substep`, with the prescribed PAR (and
+        temperature) read from device tables of one row per stage — (rows, 1) shared by every box or (rows, n) — and
+        `snapshots[name]` (n_outputs, n) filled every `output_every` steps.  Every tracer must have its G⁻ in `Gm`."""
+        names = self.required_biogeochemical_tracers()
+        PAR = auxiliary_fields["PAR"]
+        require_cuda(PAR, *[tracers[n] for n in names])
+        rows = steps * len(stages)
+        for tab, what in ((PAR_table, "PAR"), (T_table, "T")):
+            if tab is not None and (tab.dim() != 2 or tab.shape[0] != rows or tab.shape[1] not in (1, grid.Nx)
+                                    or tab.dtype != torch.float64 or not tab.is_contiguous()):
+                raise ValueError(f"{what} table must be a contiguous float64 tensor ({rows}, 1) or ({rows}, {grid.Nx})")
+        lib = _lib.load()
+        cg = grid.c_grid()
+        p = self.c_params()
+        tptr = _lib.pointer_table([tracers[n].ptr for n in names])
+        mptr = _lib.pointer_table([Gm[n].ptr if (n in Gm and Gm[n] is not None and n != "T") else None for n in names])
+        sptr = None
+        if snapshots:
+            sptr = _lib.pointer_table([snapshots[n].data_ptr() if n in snapshots else None for n in names])
+        nvary, which, values = 0, None, None
+        if self.parameter_ensemble is not None:
+            which, table, _ = self.parameter_ensemble
+            if table.shape[1] != grid.Nx * grid.Ny:
+                raise ValueError(f"parameter ensemble has {table.shape[1]} members, the grid has {grid.Nx * grid.Ny} columns")
+            if table.device != PAR.data.device:
+                table = table.to(PAR.data.device)
+                self.parameter_ensemble = (which, table, self.parameter_ensemble[2])
+            nvary, values = len(which), table.data_ptr()
+        gam = (C.c_double * len(stages))(*[float(g) for g, _ in stages])
+        zet = (C.c_double * len(stages))(*[float("nan") if z is None else float(z) for _, z in stages])
+        s = stream if stream is not None else current_stream_ptr(grid.device)
+        rc = lib.obm_npd_box_run(C.byref(cg), C.byref(p), nvary, which, values, tptr, mptr, PAR.ptr, PAR_table.data_ptr(),
+                                 int(PAR_table.shape[1] != 1), T_table.data_ptr() if T_table is not None else None,
+                                 int(T_table is not None and T_table.shape[1] != 1), int(steps), len(stages), gam, zet,
+                                 float(dt), int(output_every), sptr, s)
+        _lib.check(rc, "obm_npd_box_run")
+
     def __call__(self, name: str, *, PAR, device="cuda", **tracers):
         """The per-tracer form `bgc(Val(name), x, y, z, t, tracers..., PAR)` of the plugin API
         (docs/src/model_implementation.md:34-75; the built-in models' discrete form

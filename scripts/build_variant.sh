@@ -8,7 +8,8 @@ mkdir -p build/variants build/obj build/vobj
 objs=$(ls build/obj/*.o)
 extra=""
 for base in ${bases//,/ }; do
-  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c oceanbiome.jl_b200/csrc/$base.cu -o build/vobj/${base}_$name.o
+  per_source=""; [ "$base" = npd_tendencies ] && per_source="-fmad=false"  # as __graft_entry__.PER_SOURCE_FLAGS
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $per_source "$@" -c oceanbiome.jl_b200/csrc/$base.cu -o build/vobj/${base}_$name.o
   objs=$(echo "$objs" | grep -v "/$base.o")
   extra="$extra build/vobj/${base}_$name.o"
 done

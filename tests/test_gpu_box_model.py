@@ -276,3 +276,70 @@ def test_fused_stage_against_the_oracle_and_argument_errors(cuda, oracle):
     assert call(tab(order), None, 1, 0, tab([Gm[m] for m in names])) == -1     # accumulate needs Gⁿ
     assert call(tab(order), None, 0, 0, None) == -1                            # no G⁻ table
     assert call(None, None, 0, 0, tab(other)) == -1
+
+
+# ---- f-3: the whole run in one launch (obm_npd_box_run) ----------------------------------------------------------------
+@pytest.mark.parametrize("timestepper,model", [("RungeKutta3", "lobster"), ("Euler", "lobster"), ("RungeKutta3", "npzd_sweep")])
+def test_whole_run_launch_is_bit_identical_to_the_replayed_graph(cuda, timestepper, model):
+    """`run(..., device_loop=True)`: every thread integrates its box through all stages of all steps in ONE launch, the
+    prescribed series read from the same device tables.  Tracers, G⁻, the PAR / T fields left behind and every snapshot
+    equal those of the replayed CUDA graph of per-stage launches bit for bit — LOBSTER + carbonates + O₂ with prescribed
+    PAR and temperature over a ragged number of boxes, and the reference's NPZD box benchmark as a parameter sweep with a
+    per-box PAR series; argument errors are refused."""
+    n, steps, every = (1500, 12, 4) if model == "lobster" else (333, 9, 3)
+    rng = np.random.default_rng(5)
+    T_fn = lambda t: 12.0 + 3.0 * math.sin(2 * math.pi * t / day)  # noqa: E731
+    if model == "lobster":
+        ics = {k: torch.from_numpy(v * rng.uniform(0.5, 1.5, n)) for k, v in DEFAULTS.items()}
+        ics.update(sPOM=0.2, bPOM=0.1, DOM=0.3, DIC=2200.0, Alk=2400.0, **{"O₂": 240.0})
+        par = PAR_fn
+    else:
+        ics = {"N": torch.from_numpy(rng.uniform(5.0, 12.0, n)), "P": 0.1, "Z": 0.01, "D": 0.0}
+        scale = torch.from_numpy(rng.uniform(0.5, 1.5, n))
+        par = lambda t: PAR_fn(t) * scale  # noqa: E731  (one PAR series per box)
+
+    def build():
+        grid = ob.BoxModelGrid(n, device=cuda)
+        PAR = ob.CenterField(grid, "PAR")
+        light = ob.PrescribedPhotosyntheticallyActiveRadiation(PAR)
+        if model == "lobster":
+            bgc = ob.LOBSTER(grid, light_attenuation=light, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen())
+        else:
+            sweep = {"phytoplankton_maximum_growth_rate": torch.from_numpy(np.linspace(0.5, 1.5, n) * 0.6989 / day),
+                     "maximum_grazing_rate": torch.from_numpy(np.linspace(1.5, 0.5, n) * 2.1522 / day)}
+            bgc = ob.NPZD(grid, light_attenuation=light, parameter_ensemble=sweep)
+        m = ob.BoxModel(biogeochemistry=bgc, grid=grid, timestepper=timestepper, prescribed_tracers={"PAR": par, "T": T_fn},
+                        fused_step=True)
+        m.set(**ics)
+        return m
+
+    a, b = build(), build()
+    ra = a.run(20 * minutes, steps, graph=True, output_every=every)
+    rb = b.run(20 * minutes, steps, device_loop=True, output_every=every)
+    torch.cuda.synchronize()
+    for name in a.prognostic:
+        assert torch.equal(a.fields[name].data, b.fields[name].data), name
+        assert torch.equal(a.Gm[name].data, b.Gm[name].data), name
+        assert torch.equal(ra[name], rb[name]) and ra[name].shape == (steps // every, n), name
+    assert torch.equal(a.auxiliary_fields["PAR"].data, b.auxiliary_fields["PAR"].data)
+    assert torch.equal(a.fields["T"].data, b.fields["T"].data)
+    assert b.clock.iteration == steps and abs(a.clock.time - b.clock.time) < 1e-9
+    assert not torch.equal(b.fields["P"].interior.reshape(-1), torch.as_tensor(ics["P"], dtype=torch.float64).expand(n).to(cuda))
+    # a second call continues from where the first one stopped, like a second replay loop
+    a.run(20 * minutes, 3, graph=True)
+    b.run(20 * minutes, 3, device_loop=True)
+    torch.cuda.synchronize()
+    for name in a.prognostic:
+        assert torch.equal(a.fields[name].data, b.fields[name].data), name
+    # refused: no fused step; a forcing; a prescribed biogeochemical tracer
+    grid = ob.BoxModelGrid(4, device=cuda)
+    PAR = ob.CenterField(grid, "PAR")
+    bgc = ob.NPZD(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR))
+    with pytest.raises(ValueError, match="fused_step"):
+        ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_fn, "T": T_fn}).run(60.0, 2, device_loop=True)
+    with pytest.raises(ValueError, match="forcings"):
+        ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_fn, "T": T_fn}, forcing={"N": lambda t: 1e-9},
+                    fused_step=True).run(60.0, 2, device_loop=True)
+    with pytest.raises(ValueError, match="prescribes PAR"):
+        ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_fn, "T": T_fn, "Z": lambda t: 0.05},
+                    fused_step=True).run(60.0, 2, device_loop=True)
