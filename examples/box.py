@@ -34,7 +34,7 @@ def build(boxes=1, device="cuda"):
     grid = ob.BoxModelGrid(boxes, device=device)
     PAR = ob.CenterField(grid, "PAR")
     bgc = ob.LOBSTER(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR))
-    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func})
+    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func}, fused_step=True)
     model.set(**{"NO₃": 10.0, "NH₄": 0.1, "P": 0.1, "Z": 0.01})
     return model
 
@@ -49,7 +49,7 @@ def main():
     dt = 5 * minutes
     every = int(round(10 * day / dt))  # TimeInterval(10days)
     steps = int(round(args.years * year / dt))
-    series = model.run(dt, steps, graph=True, output_every=every)
+    series = model.run(dt, steps, device_loop=True, output_every=every)  # the whole run is one launch (obm_npd_box_run)
     times = (np.arange(steps // every) + 1) * every * dt
     np.savez(args.out, t=times, **{n: v.cpu().numpy() for n, v in series.items()})
     print(f"{steps} steps of {args.boxes} box(es): {args.out} holds {len(times)} outputs of {', '.join(series)}")

@@ -3,8 +3,9 @@ examples/data_assimilation.jl, with the whole ensemble stepped in ONE device-res
 
 The reference builds one `BoxModel` per parameter vector (`run_box_simulation`, :26-62) and runs the N_ensemble = 8
 members of each of the 5 iterations on CPU threads (:118-130).  Here the members are the boxes of `BoxModelGrid(n)`:
-`NPZD(grid, parameter_ensemble={…})` gives every box its own PhytoZoo parameters, and `run(..., graph=True)` replays one
-captured time step for all of them.  The Kalman update itself (EnsembleKalmanProcesses.jl's `Inversion()`, a
+`NPZD(grid, parameter_ensemble={…})` gives every box its own PhytoZoo parameters, and `run(..., device_loop=True)` integrates every
+member through the whole run in ONE launch (`obm_npd_box_run`; `graph=True` would replay one captured time step for all of
+them).  The Kalman update itself (EnsembleKalmanProcesses.jl's `Inversion()`, a
 third-party package) is the textbook perturbed-observation update, written out in NumPy below.
 
     python examples/data_assimilation.py            # 2 model years per forward run, as in the reference
@@ -46,11 +47,11 @@ def run_box_simulations(u, stop_time=2 * year, dt=20 * minutes, output_interval=
     PAR = ob.CenterField(grid, "PAR")
     bgc = ob.NPZD(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR),
                   parameter_ensemble=phytozoo_parameters(u))
-    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func})
+    model = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": PAR_func}, fused_step=True)
     model.set(N=10.0, P=0.1, Z=0.01)
     every = int(round(output_interval / dt))
     steps = int(round(stop_time / dt))
-    out = model.run(dt, steps, graph=True, output_every=every, output_names=["P"])
+    out = model.run(dt, steps, device_loop=True, output_every=every, output_names=["P"])  # every member, every step: one launch
     times = (np.arange(out["P"].shape[0]) + 1) * every * dt
     last = min(len(times), int(round(year / output_interval)) - 2)  # the reference keeps the last 1093 outputs
     return out["P"][-last:], times[-last:]
