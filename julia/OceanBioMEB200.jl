@@ -400,6 +400,29 @@ function update_tendencies!(b::B200NPD, model, which::Vector{Int32}, values::CuM
     return nothing
 end
 
+# ---- the whole run of a box-model ensemble in ONE launch (`run!(simulation)` over src/BoxModel/boxmodel.jl:92-110 and
+#      timesteppers.jl:30-93; the reference's benchmark/box_model.jl).  The boxes lie along x (`BoxModelGrid` with Nx members);
+#      `PAR_series` / `T_series` hold what `update_state!` prescribes AFTER every stage — one row per global stage, one column
+#      (shared) or Nx columns — as CuMatrix{Float64}(columns, rows), i.e. row-major [rows][columns] for the C side;
+#      `snapshots[n]` is a CuMatrix (Nx, nsteps ÷ output_every) per tracer, or `nothing`.  RK3 coefficients are Oceananigans'.
+function run_boxes!(b::B200NPD, model, Δt, nsteps; PAR_series::CuMatrix{Float64}, T_series = nothing, output_every = 0,
+                    snapshots = nothing, which = Int32[], values = nothing,
+                    γ = Float64[8/15, 5/12, 3/4], ζ = Float64[NaN, -17/60, -5/12])
+    u = b.reference.underlying_biogeochemistry
+    names = required_biogeochemical_tracers(u)
+    U  = table(model.fields[n] for n in names)
+    G⁻ = F64[n === :T ? CU_NULL : dptr(model.timestepper.G⁻[n]) for n in names]
+    S  = isnothing(snapshots) ? Ptr{F64}(C_NULL) : F64[haskey(snapshots, n) ? pointer(snapshots[n]) : CU_NULL for n in names]
+    check(ccall((:obm_npd_box_run, libobm), Cint,
+                (Ref{ObmGrid}, Ref{ObmNpdParams}, Cint, Ptr{Int32}, F64, Ptr{F64}, Ptr{F64}, F64, F64, Cint, F64, Cint, Cint, Cint,
+                 Ptr{Float64}, Ptr{Float64}, Cdouble, Cint, Ptr{F64}, Ptr{Cvoid}),
+                Ref(ObmGrid(model.grid)), Ref(ObmNpdParams(u)), length(which), which, isnothing(values) ? CU_NULL : pointer(values),
+                U, G⁻, dptr(biogeochemical_auxiliary_fields(b.reference).PAR), pointer(PAR_series), size(PAR_series, 1) != 1,
+                isnothing(T_series) ? CU_NULL : pointer(T_series), !isnothing(T_series) && size(T_series, 1) != 1,
+                nsteps, length(γ), γ, ζ, Δt, output_every, S, stream()), "obm_npd_box_run")
+    return nothing
+end
+
 # ---- air–sea gas exchange (src/Models/GasExchange/gas_exchange.jl:26-38): the reference evaluates `g(i, j, grid, clock, fields)`
 #      per surface cell inside Oceananigans' boundary-condition kernel; here the whole x–y plane is computed by one launch into
 #      a flux field, and the boundary condition reads that field: `FluxBoundaryCondition(flux_field)`.  Call it from a
