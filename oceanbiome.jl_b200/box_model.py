@@ -279,15 +279,18 @@ class BoxModel:
         if not times:
             return out
         snaps = {n: out[n] for n in names if n in self.prognostic} if output_every else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        on_gpu = torch.device(self.grid.device).type == "cuda"
+        e0, e1 = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if on_gpu else (None, None)
+        if on_gpu:
+            e0.record()
         T_table = tabs.get(("prescribed", "T"))
         reads_T = "T" in u.required_biogeochemical_tracers()
         u.run_boxes(self.grid, self.fields, self.auxiliary_fields, {n: self.Gm[n] for n in self.prognostic}, dt, stages, steps,
                     tabs[("prescribed", "PAR")], T_table if reads_T else None, output_every, snaps)
         if T_table is not None and not reads_T:  # a prescribed series nothing reads: leave the field as the per-stage path does
             self.fields["T"].interior.reshape(-1).copy_(T_table[-1].reshape(-1).expand(self.grid.Nx))
-        e1.record()
+        if on_gpu:
+            e1.record()
         self.replay_events = (e0, e1)
         self.clock.time = times[-1]
         self.clock.iteration += steps

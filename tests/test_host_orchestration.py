@@ -256,3 +256,21 @@ def test_model_latitude_goes_through_the_per_row_entry_point(lib):
     m2 = ob.BiogeochemicalModel(bgc2.underlying_biogeochemistry.grid, bgc2)
     bgc2.update_tendencies(m2)
     assert lib.calls == ["obm_pisces_tendencies"]
+
+
+def test_whole_run_of_a_box_ensemble_is_one_call(lib):
+    """`BoxModel.run(device_loop=True)`: the tabulated series go to ONE `obm_npd_box_run` whatever the number of steps; the
+    clock ends where the per-stage path would leave it; a prescribed series nothing reads still ends up in its field."""
+    import math
+    grid = ob.BoxModelGrid(5, device="cpu")
+    PAR = ob.CenterField(grid, "PAR")
+    bgc = ob.LOBSTER(grid, light_attenuation=ob.PrescribedPhotosyntheticallyActiveRadiation(PAR))
+    m = ob.BoxModel(biogeochemistry=bgc, grid=grid, prescribed_tracers={"PAR": lambda t: 10 + math.sin(t), "T": lambda t: 3.0 + t},
+                    fused_step=True)
+    m.set(**{"NO₃": 10.0, "NH₄": 0.1, "P": 0.1, "Z": 0.01})
+    lib.calls.clear()
+    out = m.run(600.0, 7, device_loop=True, output_every=2)
+    assert lib.calls == ["obm_npd_box_run"]
+    assert m.clock.iteration == 7 and abs(m.clock.time - 7 * 600.0) < 1e-6
+    assert set(out) == set(m.prognostic) and out["P"].shape == (3, 5)
+    assert abs(float(m.fields["T"].interior.reshape(-1)[0]) - (3.0 + m.clock.time)) < 1e-9  # LOBSTER does not read T
