@@ -475,29 +475,35 @@ __device__ __forceinline__ double presolve_f32(const Constants& c, const Totals&
     }
     float c2 = 0.0f;
     constexpr int STEPS = OBM_CC_F32_STEPS;
+    // every sum below is written as a chain of fused multiply-adds (the optimiser cannot turn BT·(1 − r) into one):
+    // ≈ 50 FP32-pipe instructions per step.  c0 collects the H-independent part of the residual.
+    const float SiTe = need_silicate ? SiT : 0.0f;
+    const float c0 = (BT + SiTe) - Alk;
 #pragma unroll
     for (int n = 0; n < STEPS; n++) {
-        const float icd = rcp_f32((H + K1) * H + K1K2);
-        const float a0 = H * H * icd, a1 = K1 * H * icd, a2 = K1K2 * icd;
-        const float m = 2.0f * a0 + a1;            // mean number of protons on the carbonate species
+        const float icd = rcp_f32(fmaf(H + K1, H, K1K2));
+        const float t = H * icd;
+        const float a0 = H * t, a1 = K1 * t, a2 = K1K2 * icd;   // speciation fractions of the carbonate system
+        const float m = fmaf(2.0f, a0, a1);                      // mean number of protons on them
+        const float s12 = fmaf(2.0f, a2, a1);                    // their alkalinity per unit DIC
         const float rB = H * rcp_f32(KB + H), rS = H * rcp_f32(H + KSsd), rF = H * rcp_f32(H + KF);
-        const float oh = KW * rcp_f32(H), hf = H * isd;
-        const float qB = rB * (1.0f - rB), qS = rS * (1.0f - rS), qF = rF * (1.0f - rF);
-        float g = DIC * (a1 + 2.0f * a2) + BT * (1.0f - rB) + (oh - hf) - ST * rS - FT * rF - Alk;
-        float gp = DIC * (a1 * (1.0f - m) - 2.0f * a2 * m) - BT * qB - (oh + hf) - ST * qS - FT * qF;
-        float rSi = 0.0f, qSi = 0.0f;
-        if (need_silicate) {
-            rSi = H * rcp_f32(KSi + H);
-            qSi = rSi * (1.0f - rSi);
-            g += SiT * (1.0f - rSi);
-            gp -= SiT * qSi;
-        }
+        const float rSi = need_silicate ? H * rcp_f32(KSi + H) : 0.0f;
+        const float oh = KW * rcp_f32(H);
+        const float qB = fmaf(-rB, rB, rB), qS = fmaf(-rS, rS, rS), qF = fmaf(-rF, rF, rF), qSi = fmaf(-rSi, rSi, rSi);  // r (1 − r)
+        float g = fmaf(DIC, s12, c0);
+        g = fmaf(-BT, rB, g); g = fmaf(-SiTe, rSi, g); g = fmaf(-ST, rS, g); g = fmaf(-FT, rF, g);
+        g = fmaf(-H, isd, g + oh);
+        float gp = DIC * fmaf(-m, s12, a1);                      // a₁(1 − m) − 2 a₂ m
+        gp = fmaf(-BT, qB, gp); gp = fmaf(-SiTe, qSi, gp); gp = fmaf(-ST, qS, gp); gp = fmaf(-FT, qF, gp);
+        gp = fmaf(-H, isd, gp - oh);
         const float igp = rcp_f32(gp);
         if (n == STEPS - 1) {  // g″ at the last FP32 iterate (≲ 10⁻³ from the root: C to three digits)
-            const float v = 2.0f * a0 * (2.0f - m) + a1 * (1.0f - m);  // ∂ₓ m
-            float gpp = DIC * (a1 * (1.0f - m) * (1.0f - m) + 2.0f * a2 * m * m - (a1 + 2.0f * a2) * v) - BT * qB * (1.0f - 2.0f * rB)
-                        + (oh - hf) - ST * qS * (1.0f - 2.0f * rS) - FT * qF * (1.0f - 2.0f * rF);
-            if (need_silicate) gpp -= SiT * qSi * (1.0f - 2.0f * rSi);
+            const float w = 1.0f - m;
+            const float v = fmaf(2.0f * a0, 1.0f + w, a1 * w);  // ∂ₓ m = 2 a₀ (2 − m) + a₁ (1 − m)
+            float gpp = DIC * fmaf(-s12, v, fmaf(a1 * w, w, 2.0f * a2 * m * m));
+            gpp = fmaf(-BT * qB, fmaf(-2.0f, rB, 1.0f), gpp); gpp = fmaf(-SiTe * qSi, fmaf(-2.0f, rSi, 1.0f), gpp);
+            gpp = fmaf(-ST * qS, fmaf(-2.0f, rS, 1.0f), gpp); gpp = fmaf(-FT * qF, fmaf(-2.0f, rF, 1.0f), gpp);
+            gpp = fmaf(-H, isd, gpp + oh);
             c2 = 0.5f * gpp * igp;
         }
         float dx = g * igp;
@@ -541,9 +547,11 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
     constexpr double LN10 = 2.302585092994045684;
     double H = H0;
     double dx = 0.0, dx_prev = 0.0;
+    int steps_done = 0;
     const unsigned mask = __activemask();
 #pragma unroll 1
     for (int n = 0; n < iterations; n++) {
+        steps_done = n + 1;
         double f, Hdf;
         residual(H, c, t, need_phosphate, need_silicate, f, Hdf);
         dx_prev = dx;
@@ -572,7 +580,7 @@ __device__ __forceinline__ double solve_H(const Constants& c, const Totals& t, b
         }
     }
 #if OBM_CC_EXTRAP
-    {
+    if (steps_done > 1) {  // warp-uniform (the exit is a vote): a single step has no predecessor to extrapolate with
         const double ap = fabs(dx_prev), an = fabs(dx);
         const double pred = (dx * dx) * dx * rcp_fast(dx_prev * dx_prev);
         const bool use = an < ap && ap < 0.125 && fabs(pred) < KD(1e-2) * an;  // false for NaN, for a single step (Δxₙ₋₁ = 0)
