@@ -685,6 +685,7 @@ int obm_npd_tendencies_substep(const obm_grid* grid, const obm_npd_params* p, in
  * temperature tracer.  On return tracers, G⁻, the PAR field and T hold what nsteps calls of
  * time_step! would have left; `snapshots[t]` (tracer order, nullable entries or table)
  * receives tracer t of every box after every `output_every`-th step: [nsteps/output_every][n].
+ * Tables, parameter values and snapshots are indexed by the box's position along x (n = grid->Nx).
  * Results are those of the per-stage launches bit for bit (tests/test_gpu_box_model.py); the
  * reference's benchmark/box_model.jl (NPZD box, 1000 RK3 steps: 23.5 ms on its CPU for ONE
  * box) takes one launch for the whole ensemble.  Every tracer the tendencies read must be

@@ -338,13 +338,14 @@ __global__ void __launch_bounds__(RUN_BLOCK) npd_box_run_kernel(const __grid_con
     __syncthreads();
     const int cell = blockIdx.x * RUN_BLOCK + tid;
     const bool inside = cell < r.ncells;
-    const long long gidx = cell_index(a.d, a.d.i0 + (inside ? cell : 0), a.d.j0, 0);
+    const int nx = a.d.Nx, ibox = a.d.i0 + (inside ? cell : 0);  // tables, parameter values and snapshots are indexed by the box
+    const long long gidx = cell_index(a.d, ibox, a.d.j0, 0);
     obm_npd_params member;  // dead unless ENSEMBLE
     if constexpr (ENSEMBLE) {
         member = a.p;
         if (inside) {
 #pragma unroll 1
-            for (int v = 0; v < a.nvary; v++) set_param(member, a.which[v], a.values[(long long)v * r.ncells + cell]);
+            for (int v = 0; v < a.nvary; v++) set_param(member, a.which[v], a.values[(long long)v * nx + ibox]);
         }
     }
     for (int s = 0; s < r.nslots; s++) {
@@ -377,13 +378,13 @@ __global__ void __launch_bounds__(RUN_BLOCK) npd_box_run_kernel(const __grid_con
             __syncthreads();  // every thread has read this stage's coefficients
             // what update_state! leaves for the next stage: the prescribed series at the time after this one
             if (inside) {
-                PARv = r.PAR_table[r.PAR_per_box ? row * r.ncells + cell : row];
-                if (r.T_table != nullptr) Tv = r.T_table[r.T_per_box ? row * r.ncells + cell : row];
+                PARv = r.PAR_table[r.PAR_per_box ? row * nx + ibox : row];
+                if (r.T_table != nullptr) Tv = r.T_table[r.T_per_box ? row * nx + ibox : row];
             }
             row++;
         }
         if (r.output_every > 0 && (it + 1) % r.output_every == 0 && inside) {
-            const long long o = (long long)((it + 1) / r.output_every - 1) * r.ncells + cell;
+            const long long o = (long long)((it + 1) / r.output_every - 1) * nx + ibox;
             for (int s = 0; s < r.nslots; s++)
                 if (r.snap[s] != nullptr) r.snap[s][o] = U[s * RUN_BLOCK + tid];
         }
