@@ -13,6 +13,8 @@ from typing import Optional
 import ctypes as C
 import math
 
+import torch
+
 
 from . import _lib
 from .grids import CenterField, Field, RectilinearGrid, ZFaceField, current_stream_ptr, fill_z_halos
@@ -245,6 +247,82 @@ class BiogeochemicalModel:
                 _lib.pointer_table([self.drift_velocity_field(n).ptr for n in chunk]),
                 _lib.pointer_table([self.Gn[n].ptr for n in chunk]), self.ADVECTION[self.sinking_advection], 1, s)
             _lib.check(rc, "obm_sinking_tendencies")
+
+    # ---- run!(simulation) for column ensembles (many independent 1-D models stepped on the device) ------------
+    def run(self, dt: float, steps: int, graph: bool = False, output_every: int = 0, output_names=None):
+        """Integrate `steps` time steps; returns {name: tensor (n_outputs, Nz, Ny, Nx)} of interior snapshots taken every
+        `output_every` steps (device-resident).
+
+        `graph=True`: the FIRST step runs eagerly (it alone sees the pre-run `last_stage_dt`), then ONE time step — every
+        stage's negative scaling, PAR scan, fused tendencies, sinking, sediment hooks, boundary fluxes and tracer update —
+        is captured in a CUDA graph and replayed for the rest of the run: ≈ 15 launches per step with no host work between
+        them, whatever the number of columns.  Needs kernel arguments that do not depend on the clock: NPZD / LOBSTER
+        family (not PISCES: its day lengths are host-evaluated per stage), a constant or field surface PAR, no particles.
+        Bit-identical to the eager loop."""
+        names = list(output_names or [n for n in self.tracers if n not in ("T", "S")])
+        nout = steps // output_every if output_every else 0
+        shape = (nout, self.grid.Nz, self.grid.Ny, self.grid.Nx)
+        out = {n: torch.empty(shape, dtype=torch.float64, device=self.grid.device) for n in names}
+
+        def snapshot(it):
+            if output_every and (it + 1) % output_every == 0:
+                for n in names:
+                    out[n][(it + 1) // output_every - 1].copy_(self.tracers[n].interior)
+
+        if not graph or steps < 3:
+            for it in range(steps):
+                self.time_step(dt)
+                snapshot(it)
+            return out
+        bgc = self.biogeochemistry
+        u = getattr(bgc, "underlying_biogeochemistry", bgc)
+        if getattr(u, "clock_dependent_parameters", False):
+            raise ValueError("graph=True needs kernel parameters that do not depend on the clock (not PISCES)")
+        if getattr(bgc, "particles", None) is not None:
+            raise ValueError("graph=True: particles are stepped with host logic between the launches; use the eager loop")
+        if callable(getattr(getattr(bgc, "light_attenuation", None), "surface_PAR", None)):
+            raise ValueError("graph=True: a surface PAR function of time is evaluated on the host; use a constant or a field")
+        self.time_step(dt)
+        snapshot(0)
+        dev = self.grid.device
+        sediment = getattr(bgc, "sediment", None)
+        state = [self.tracers, self.Gn, self.Gm, self.auxiliary_fields] + ([sediment.fields] if sediment is not None else [])
+        for extra in ("Gn", "Gm", "tendencies", "previous_tendencies"):
+            d = getattr(sediment, extra, None) if sediment is not None else None
+            if isinstance(d, dict):
+                state.append(d)
+        saved = [(f, f.data.clone()) for d in state if d is not None for f in d.values() if hasattr(f, "data")]
+        clock = (self.clock.time, self.clock.iteration, self.clock.last_stage_dt)
+        sed_host = (sediment.last_dt, sediment.iteration) if sediment is not None and hasattr(sediment, "last_dt") else None
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up: lazily built fields, allocator
+            self.time_step(dt)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        for f, v in saved:
+            f.data.copy_(v)
+        self.clock.time, self.clock.iteration, self.clock.last_stage_dt = clock
+        if sed_host is not None:  # the sediment's own stepper keeps Δt of its last call and a counter on the host
+            sediment.last_dt, sediment.iteration = sed_host
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.time_step(dt)
+        if sed_host is not None:
+            sediment.iteration = sed_host[1] + (sediment.iteration - sed_host[1]) * (steps - 1)
+        # the capture does not execute; the host-side clock advanced once while capturing: rewind, then count the replays
+        self.clock.time, self.clock.iteration, self.clock.last_stage_dt = clock
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for it in range(1, steps):
+            g.replay()
+            snapshot(it)
+        e1.record()
+        self._graph, self.replay_events = g, (e0, e1)
+        self.clock.time = clock[0] + (steps - 1) * dt
+        self.clock.iteration = clock[1] + steps - 1
+        stages = self.RK3 if self.timestepper != "Euler" else ((1.0, 0.0),)
+        self.clock.last_stage_dt = dt * (stages[-1][0] + stages[-1][1])
+        return out
 
     def _substep(self, dt, gamma, zeta):
         """U += Δt(γGⁿ + ζG⁻), G⁻ ← Gⁿ for every tracer in one launch (csrc/timestepping.cu)."""

@@ -312,6 +312,9 @@ class Oxygen:  # oxygen.jl:21-24
 class PISCESModel:
     """The underlying biogeochemistry `PISCES{…}` (PISCES.jl:53-92)."""
 
+    # the two day lengths are host-evaluated from (clock.time, latitude) at every launch: a captured CUDA graph would freeze them
+    clock_dependent_parameters = True
+
     def __init__(self, grid, phytoplankton, zooplankton, dissolved_organic_matter, particulate_organic_matter, nitrogen,
                  iron, oxygen, first_anoxia_threshold, second_anoxia_threshold, nitrogen_redfield_ratio,
                  phosphate_redfield_ratio, mixed_layer_shear, background_shear, latitude, day_length, mixed_layer_depth,

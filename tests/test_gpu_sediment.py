@@ -143,3 +143,51 @@ def test_total_nitrogen_is_conserved_with_sinking_into_the_sediment(cuda):
     assert abs(N1 - N0) <= 1e-12 * abs(N0), (N0, N1)
     assert sum(f.interior.sum().item() for f in sed.fields.values()) > 0.01  # a visible amount reached the sediment
     assert all(bool((f.interior > 0).all()) for f in sed.fields.values())
+
+
+@pytest.mark.parametrize("timestepper,with_sediment", [("RungeKutta3", True), ("Euler", False)])
+def test_column_ensemble_run_as_a_replayed_graph_is_bit_identical_to_the_eager_loop(cuda, timestepper, with_sediment):
+    """SURVEY §8 f-3, the 1-D half: an ensemble of independent columns (LOBSTER + carbonates + O₂, sinking POM, optionally the
+    SimpleMultiG sediment with its own stepper) stepped on the device.  `run(graph=True)` — first step eager, then one
+    captured time step replayed — leaves every tracer, every G⁻, the sediment pools and every snapshot exactly as the
+    eager loop of `time_step` does, and the clock where it belongs; PISCES (host-evaluated day lengths) is refused."""
+    def build():
+        grid = ob.RectilinearGrid(size=(48, 2, 20), extent=(48.0, 2.0, 200.0), device=cuda)
+        sed = ob.SimpleMultiGSediment(grid) if with_sediment else None
+        bgc = ob.LOBSTER(grid, carbonate_system=ob.CarbonateSystem(), oxygen=ob.Oxygen(), sediment=sed, scale_negatives=True,
+                         surface_photosynthetically_active_radiation=100.0)
+        model = ob.BiogeochemicalModel(grid, bgc, timestepper=timestepper, sinking_advection="UpwindBiased3")
+        for n, f in model.tracers.items():
+            synthetic.fill_torch(f, n, *synthetic.lobster_range(n))
+        if sed is not None:
+            for n, f in sed.fields.items():
+                synthetic.fill_torch(f, "sed" + n, 1e-2, 10.0, True)
+        return model, sed
+
+    steps, every, dt = 9, 3, 120.0
+    (a, sa), (b, sb) = build(), build()
+    ra = a.run(dt, steps, graph=False, output_every=every)
+    rb = b.run(dt, steps, graph=True, output_every=every)
+    torch.cuda.synchronize()
+    for n in a.tracers:
+        assert torch.equal(a.tracers[n].data, b.tracers[n].data), n
+        if a.Gm is not None:
+            assert torch.equal(a.Gm[n].data, b.Gm[n].data), n
+    for n in ra:
+        assert torch.equal(ra[n], rb[n]) and ra[n].shape == (steps // every, 20, 2, 48), n
+    if with_sediment:
+        for n in sa.fields:
+            assert torch.equal(sa.fields[n].data, sb.fields[n].data), n
+        assert sa.iteration == sb.iteration and sa.last_dt == sb.last_dt
+    assert a.clock.iteration == b.clock.iteration == steps and abs(a.clock.time - b.clock.time) < 1e-9
+    assert a.clock.last_stage_dt == b.clock.last_stage_dt
+    assert not torch.equal(b.tracers["P"].data, build()[0].tracers["P"].data)  # it did move
+    # and it continues: three more steps either way
+    a.run(dt, 3)
+    b.run(dt, 3, graph=True)
+    torch.cuda.synchronize()
+    for n in a.tracers:
+        assert torch.equal(a.tracers[n].data, b.tracers[n].data), n
+    grid = ob.RectilinearGrid(size=(4, 2, 6), extent=(4.0, 2.0, 60.0), device=cuda)
+    with pytest.raises(ValueError, match="not PISCES"):
+        ob.BiogeochemicalModel(grid, ob.PISCES(grid)).run(60.0, 5, graph=True)
