@@ -179,7 +179,9 @@ class BiogeochemicalModel:
         names = list(biogeochemistry.required_biogeochemical_tracers())
         names += [t for t in extra_tracers if t not in names]
         self.tracers = {n: CenterField(grid, n) for n in names}
-        self.Gn = {n: CenterField(grid, "G" + n) for n in names}
+        # Gⁿ of every tracer in one allocation: clearing them is one memset per stage (one graph node instead of one per tracer)
+        self._Gn_slab = torch.zeros((len(names),) + tuple(grid.parent_shape), dtype=torch.float64, device=grid.device)
+        self.Gn = {n: Field(grid, self._Gn_slab[i], "G" + n) for i, n in enumerate(names)}
         self.Gm = None  # G⁻, allocated on first RK3 step
         self.timestepper = timestepper
 
@@ -210,8 +212,7 @@ class BiogeochemicalModel:
         self.biogeochemistry.update_biogeochemical_state(self)
 
     def compute_tendencies(self):
-        for g in self.Gn.values():
-            g.data.zero_()
+        self._Gn_slab.zero_()
         self.biogeochemistry.update_tendencies(self)
         if self.sinking_advection is not None:
             self.add_sinking_tendencies()
