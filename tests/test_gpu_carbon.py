@@ -81,7 +81,10 @@ def test_full_validation_box_robustness(cuda, oracle):
     ok = np.isfinite(want)
     err = np.abs(got[ok] - want[ok])
     assert ok.mean() > 0.99
-    assert (err <= ATOL_PH).mean() > 0.999, f"{(err > ATOL_PH).sum()} of {ok.sum()} disagree, worst {err.max():.2e}"
+    # (r02 accepted 0.1 % disagreeing roots here; with the FP32 pre-solve + FP64 loop every state of the box lands on the
+    # reference's root — the host build of the same header: 0 of 20 000 above 1e-10, worst 1.9e-13)
+    assert (err <= ATOL_PH).all(), f"{(err > ATOL_PH).sum()} of {ok.sum()} disagree, worst {err.max():.2e}"
+    print(f"[parity] validation box: max |dpH| {err.max():.2e} over {ok.sum()} states")
 
 
 def test_nan_inputs_propagate(cuda):
