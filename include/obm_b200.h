@@ -245,7 +245,11 @@ enum {
 };
 
 typedef struct obm_carbchem_params {
-    int32_t newton_iterations; /* fixed iteration count of the branch-free ln[H] Newton (default 12 when <= 0) */
+    int32_t newton_iterations; /* upper bound on the FP64 steps of the branch-free ln[H] Newton (default 12 when <= 0).  Without a
+                                * stored [H⁺] (and without phosphate) the search — carbonate-alkalinity quadratic + three Newton
+                                * steps — runs in FP32, and ONE FP64 step with its second-order error removed finishes it: a fixed
+                                * count for every sea-water state; a state whose FP64 step is not below 1e-5 in ln H keeps its
+                                * warp in the FP64 loop (warp-uniform exit, never more than this many steps). */
     int32_t _pad;
     double initial_pH_guess;   /* default 8 (carbon_chemistry.jl:121) when <= 0: fallback start and borate term of the analytic start */
 } obm_carbchem_params;
