@@ -212,7 +212,15 @@ __global__ void __launch_bounds__(256) zero_negative_kernel(const __grid_constan
 // ONE pass over the cells for all groups: every distinct tracer is read once per cell (8 B × ntracers, HBM-bound), the
 // groups are rows of a dense weight table W[g][t] (0 where tracer t is not a member of group g) held in the constant
 // bank.  Blocks walk (j, k) rows, threads stride along x: coalesced, one integer division per ROW.
-constexpr int INV_BLOCKS = 148 * 4;
+// OBM_INV_BATCH tracers' loads issued before the first is used.  Timed at 33.5 M cells (scripts/time_inventory.py, r5f): 1 → 1.48 ms
+// (3.6 TB/s), 4 → 2.11 ms, 8 → 2.59 ms — the registers the batch holds cost more warps than the loads in flight gain; 8 blocks per SM: ± 0.
+#ifndef OBM_INV_BATCH
+#define OBM_INV_BATCH 1
+#endif
+#ifndef OBM_INV_BLOCKS_PER_SM
+#define OBM_INV_BLOCKS_PER_SM 4
+#endif
+constexpr int INV_BLOCKS = 148 * OBM_INV_BLOCKS_PER_SM;
 constexpr int INV_THREADS = 256;
 
 struct InvArgs {
@@ -243,8 +251,20 @@ __global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __
             double s[OBM_MAX_SCALE_GROUPS];
 #pragma unroll
             for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) s[g] = 0.0;
-            for (int t = 0; t < a.ntracers; t++) {
-                const double v = __ldcs(a.tracers[t] + idx);  // streamed: read once
+            // (OBM_INV_BATCH > 1: that many tracers' loads in flight before the first is used — measured slower, see above)
+            int t = 0;
+            for (; t + OBM_INV_BATCH <= a.ntracers; t += OBM_INV_BATCH) {
+                double v[OBM_INV_BATCH];
+#pragma unroll
+                for (int q = 0; q < OBM_INV_BATCH; q++) v[q] = __ldcs(a.tracers[t + q] + idx);  // streamed: read once
+#pragma unroll
+                for (int q = 0; q < OBM_INV_BATCH; q++)
+#pragma unroll
+                    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++)
+                        if (g < a.ngroups) s[g] = fma(a.w[g][t + q], v[q], s[g]);
+            }
+            for (; t < a.ntracers; t++) {
+                const double v = __ldcs(a.tracers[t] + idx);
 #pragma unroll
                 for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++)
                     if (g < a.ngroups) s[g] = fma(a.w[g][t], v, s[g]);
