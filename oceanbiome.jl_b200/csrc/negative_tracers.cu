@@ -217,8 +217,11 @@ __global__ void __launch_bounds__(256) zero_negative_kernel(const __grid_constan
 #ifndef OBM_INV_BATCH
 #define OBM_INV_BATCH 1
 #endif
+// Blocks per SM of the persistent grid.  With the kernel templated on the number of groups PISCES' five budgets take 46 registers,
+// so five blocks of 256 threads are resident: 33.5 M cells in 1.48 ms (r03: 16 accumulators, 61 registers, 4 blocks) → 1.06 ms (4 blocks)
+// → 0.94 ms (5 blocks) = 5.7 TB/s, 0.87 of the measured HBM peak; 6 → 1.38 ms (a tail wave), 8 → 1.09 ms (scripts/time_inventory.py, r5g).
 #ifndef OBM_INV_BLOCKS_PER_SM
-#define OBM_INV_BLOCKS_PER_SM 4
+#define OBM_INV_BLOCKS_PER_SM 5
 #endif
 constexpr int INV_BLOCKS = 148 * OBM_INV_BLOCKS_PER_SM;
 constexpr int INV_THREADS = 256;
@@ -234,23 +237,26 @@ struct InvArgs {
     double* out;
 };
 
+// NG = the number of groups, a compile-time constant: acc / s cost 2·NG registers instead of 16 (PISCES' five budgets: 61 → ≈ 45
+// registers), and every resident warp more is another row of loads in flight — what this kernel lives on (see OBM_INV_BATCH)
+template <int NG>
 __global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __grid_constant__ InvArgs a) {
-    __shared__ double red[OBM_MAX_SCALE_GROUPS][INV_THREADS / 32];
+    __shared__ double red[NG][INV_THREADS / 32];
     const GridDims& d = a.d;
     const int nx = d.i1 - d.i0, ny = d.j1 - d.j0;
     const int rows = ny * d.Nz;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double acc[OBM_MAX_SCALE_GROUPS];
+    double acc[NG];
 #pragma unroll
-    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) acc[g] = 0.0;
+    for (int g = 0; g < NG; g++) acc[g] = 0.0;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
         const int k = row / ny;
         const int j = d.j0 + (row - k * ny);
         for (int ii = threadIdx.x; ii < nx; ii += INV_THREADS) {
             const long long idx = cell_index(d, d.i0 + ii, j, k);
-            double s[OBM_MAX_SCALE_GROUPS];
+            double s[NG];
 #pragma unroll
-            for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) s[g] = 0.0;
+            for (int g = 0; g < NG; g++) s[g] = 0.0;
             // (OBM_INV_BATCH > 1: that many tracers' loads in flight before the first is used — measured slower, see above)
             int t = 0;
             for (; t + OBM_INV_BATCH <= a.ntracers; t += OBM_INV_BATCH) {
@@ -260,22 +266,22 @@ __global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __
 #pragma unroll
                 for (int q = 0; q < OBM_INV_BATCH; q++)
 #pragma unroll
-                    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++)
-                        if (g < a.ngroups) s[g] = fma(a.w[g][t + q], v[q], s[g]);
+                    for (int g = 0; g < NG; g++)
+                        s[g] = fma(a.w[g][t + q], v[q], s[g]);
             }
             for (; t < a.ntracers; t++) {
                 const double v = __ldcs(a.tracers[t] + idx);
 #pragma unroll
-                for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++)
-                    if (g < a.ngroups) s[g] = fma(a.w[g][t], v, s[g]);
+                for (int g = 0; g < NG; g++)
+                    s[g] = fma(a.w[g][t], v, s[g]);
             }
             const double V = a.volume ? a.volume[idx] : a.uniform_volume;
 #pragma unroll
-            for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) acc[g] = fma(s[g], V, acc[g]);
+            for (int g = 0; g < NG; g++) acc[g] = fma(s[g], V, acc[g]);
         }
     }
 #pragma unroll
-    for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) {
+    for (int g = 0; g < NG; g++) {
         double v = acc[g];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -284,11 +290,11 @@ __global__ void __launch_bounds__(INV_THREADS) inventory_partial_kernel(const __
     __syncthreads();
     if (warp == 0) {
 #pragma unroll
-        for (int g = 0; g < OBM_MAX_SCALE_GROUPS; g++) {
+        for (int g = 0; g < NG; g++) {
             double v = lane < INV_THREADS / 32 ? red[g][lane] : 0.0;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && g < a.ngroups) a.partial[g * INV_BLOCKS + blockIdx.x] = v;
+            if (lane == 0) a.partial[g * INV_BLOCKS + blockIdx.x] = v;
         }
     }
 }
@@ -455,7 +461,16 @@ extern "C" int obm_inventory(const obm_grid* grid, int ntracers, const double* c
     a.partial = (double*)workspace;
     a.out = out;
     cudaStream_t s = (cudaStream_t)stream;
-    inventory_partial_kernel<<<INV_BLOCKS, INV_THREADS, 0, s>>>(a);
+    switch (ngroups) {
+        case 1: inventory_partial_kernel<1><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 2: inventory_partial_kernel<2><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 3: inventory_partial_kernel<3><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 4: inventory_partial_kernel<4><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 5: inventory_partial_kernel<5><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 6: inventory_partial_kernel<6><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        case 7: inventory_partial_kernel<7><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+        default: inventory_partial_kernel<8><<<INV_BLOCKS, INV_THREADS, 0, s>>>(a); break;
+    }
     rc = launch_status("inventory_partial_kernel");
     if (rc) return rc;
     inventory_final_kernel<<<ngroups, INV_THREADS, 0, s>>>(a.partial, INV_BLOCKS, out);
