@@ -53,7 +53,7 @@ def test_argument_errors_are_reported_without_a_gpu():
     assert lib.obm_carbon_chemistry(-1, None, dummy, dummy, dummy, dummy, None, None, None, None, 0, dummy, None) == -2
     assert lib.obm_carbon_chemistry(4, None, dummy, dummy, dummy, dummy, None, None, None, None, 42, dummy, None) == -3
     assert lib.obm_carbon_chemistry(0, None, None, None, None, None, None, None, None, None, 0, None, None) == 0
-    assert lib.obm_inventory_workspace_bytes(5) == 5 * 148 * 4 * 8
+    assert lib.obm_inventory_workspace_bytes(5) == 5 * 148 * 5 * 8  # groups × (148 SMs × 5 resident blocks) partial sums of 8 bytes
     # the ensemble entry point refuses a bad sweep description before it touches the device
     p = _lib.obm_npd_params()
     ens = lambda nvary, which, values: lib.obm_npd_tendencies_ensemble(  # noqa: E731
