@@ -109,8 +109,15 @@ __device__ __forceinline__ double concentration_limit(int form, double X, double
 template <int NUT, int DET>
 __device__ __forceinline__ void npd_cell(const NpdArgs& a, const obm_npd_params& p, long long idx);
 
+// Resident blocks of 256 threads the register allocation must allow.  LOBSTER + carbonates + O₂ takes 74 registers (3 blocks) left
+// alone; 4 blocks (64 registers, 16 B of stack) is faster on this HBM-bound kernel — C3: 0.678 → 0.663 ms accumulating, 0.585 → 0.537 ms
+// overwriting; 5 blocks (48 registers, 104 B) 0.850 ms (visit r5i).  The parameter-sweep instantiations keep a member's 35 parameters
+// in registers and are left unconstrained, like the variable-Redfield detritus (six more tracers: ≈ 90 B of stack at 64 registers).
+#ifndef OBM_NPD_MIN_BLOCKS
+#define OBM_NPD_MIN_BLOCKS 4
+#endif
 template <int NUT, int DET, bool ENSEMBLE>
-__global__ void __launch_bounds__(256) npd_tendency_kernel(const __grid_constant__ NpdArgs a) {
+__global__ void __launch_bounds__(256, (ENSEMBLE || DET == OBM_DET_VARIABLE_REDFIELD) ? 1 : OBM_NPD_MIN_BLOCKS) npd_tendency_kernel(const __grid_constant__ NpdArgs a) {
     int i, j, k;
     if (!thread_cell(a.d, i, j, k)) return;
     const long long idx = cell_index(a.d, i, j, k);
