@@ -274,3 +274,18 @@ def test_whole_run_of_a_box_ensemble_is_one_call(lib):
     assert m.clock.iteration == 7 and abs(m.clock.time - 7 * 600.0) < 1e-6
     assert set(out) == set(m.prognostic) and out["P"].shape == (3, 5)
     assert abs(float(m.fields["T"].interior.reshape(-1)[0]) - (3.0 + m.clock.time)) < 1e-9  # LOBSTER does not read T
+
+
+def test_column_model_run_loops_time_step_and_takes_snapshots(lib):
+    """`BiogeochemicalModel.run` without a graph is the eager loop of `time_step` (three stages of hooks + one substep launch each)
+    with interior snapshots every `output_every` steps; PISCES is refused by the graph mode before anything is captured."""
+    import pytest
+    g = grid3()
+    model = ob.BiogeochemicalModel(g, ob.LOBSTER(g, scale_negatives=True), sinking_advection="UpwindBiased1")
+    lib.calls.clear()
+    out = model.run(60.0, 4, output_every=2)
+    stage = ["obm_scale_negative_tracers", "obm_par_twoband", "obm_npd_tendencies", "obm_sinking_tendencies", "obm_rk3_substep"]
+    assert lib.calls == stage * 12
+    assert out["P"].shape == (2, g.Nz, g.Ny, g.Nx) and model.clock.iteration == 4 and abs(model.clock.time - 240.0) < 1e-9
+    with pytest.raises(ValueError, match="not PISCES"):
+        ob.BiogeochemicalModel(g, ob.PISCES(g)).run(60.0, 5, graph=True)
